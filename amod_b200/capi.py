@@ -1,0 +1,118 @@
+"""ctypes binding of include/amod_b200.h (libamod_b200.so).
+
+This is the whole Python↔CUDA boundary: plain pointers and sizes.  There is no CPU
+fallback — if the shared library is missing or no CUDA device is present the calls
+raise (SURVEY.md §8b "Errors").
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "csrc", "libamod_b200.so")
+
+OK, E_BADARG, E_CUDA, E_CAPACITY, E_LEVELS, E_NOMEM, E_LIMIT = 0, -1, -2, -3, -4, -5, -6
+LOC_HOST, LOC_DEVICE = 0, 1
+TT_F32, TT_F64 = 0, 1
+
+_i32p, _f64p, _u8p, _i64p = C.POINTER(C.c_int32), C.POINTER(C.c_double), C.POINTER(C.c_uint8), C.POINTER(C.c_int64)
+
+
+class AmodEpoch(C.Structure):
+    _fields_ = [("n_veh", C.c_int32), ("n_req", C.c_int32), ("n_search", C.c_int32), ("cap", C.c_int32),
+                ("mode", C.c_int32), ("reserved", C.c_int32), ("T", C.c_int64),
+                ("veh_nid", C.c_void_p), ("veh_t_to_nid", C.c_void_p), ("veh_load", C.c_void_p),
+                ("veh_status", C.c_void_p), ("veh_sche_off", C.c_void_p), ("sche_code", C.c_void_p),
+                ("sche_onboard", C.c_void_p), ("veh_reb_node", C.c_void_p), ("veh_reb_ddl", C.c_void_p),
+                ("req_onid", C.c_void_p), ("req_dnid", C.c_void_p), ("req_clp", C.c_void_p),
+                ("req_cld", C.c_void_p), ("req_tr", C.c_void_p), ("req_ts", C.c_void_p), ("search", C.c_void_p)]
+
+
+EPOCH_PTR_FIELDS = ("veh_nid", "veh_t_to_nid", "veh_load", "veh_status", "veh_sche_off", "sche_code",
+                    "sche_onboard", "veh_reb_node", "veh_reb_ddl", "req_onid", "req_dnid", "req_clp",
+                    "req_cld", "req_tr", "req_ts", "search")
+
+
+class AmodPool(C.Structure):
+    _fields_ = [("cap_entries", C.c_int64), ("cap_trip_reqs", C.c_int64), ("cap_stops", C.c_int64),
+                ("n_entries", C.c_int64), ("n_trip_reqs", C.c_int64), ("n_stops", C.c_int64),
+                ("ent_veh", C.c_void_p), ("ent_kind", C.c_void_p), ("ent_trip_off", C.c_void_p),
+                ("ent_sche_off", C.c_void_p), ("ent_cost", C.c_void_p), ("ent_delay", C.c_void_p),
+                ("ent_nfeas", C.c_void_p), ("trip_req", C.c_void_p), ("sche_code", C.c_void_p)]
+
+
+POOL_FIELDS = (("ent_veh", np.int32, "e"), ("ent_kind", np.int32, "e"), ("ent_trip_off", np.int64, "e1"),
+               ("ent_sche_off", np.int64, "e1"), ("ent_cost", np.float64, "e"), ("ent_delay", np.float64, "e"),
+               ("ent_nfeas", np.int32, "e"), ("trip_req", np.int32, "t"), ("sche_code", np.int32, "s"))
+
+
+class AmodStats(C.Structure):
+    _fields_ = [("n_screens", C.c_int64), ("n_evals", C.c_int64), ("n_lookups", C.c_int64),
+                ("n_entries", C.c_int64), ("n_sches_stored", C.c_int64), ("n_tasks", C.c_int64),
+                ("n_levels", C.c_int32), ("n_kernel_launches", C.c_int32), ("ms_build", C.c_double),
+                ("ms_eval", C.c_double), ("n_eval_launches", C.c_int32), ("reserved", C.c_int32)]
+
+    def as_dict(self):
+        return {f: getattr(self, f) for f, _ in self._fields_ if f != "reserved"}
+
+
+def epoch_struct(ep, ptr_of=None) -> AmodEpoch:
+    """Fill an AmodEpoch from an amod_b200.marshal.Epoch (numpy arrays -> host pointers), or
+    from any object whose fields `ptr_of` can turn into addresses (e.g. torch CUDA tensors)."""
+    s = AmodEpoch()
+    s.n_veh, s.n_req, s.n_search, s.cap = ep.n_veh, ep.n_req, ep.n_search, ep.cap
+    s.mode, s.T = ep.mode, ep.T
+    if ptr_of is None:
+        ptr_of = lambda a: a.ctypes.data
+    for f in EPOCH_PTR_FIELDS:
+        setattr(s, f, ptr_of(getattr(ep, f)))
+    return s
+
+
+EXPORTS = ("amod_create", "amod_destroy", "amod_last_error", "amod_version", "amod_set_stream",
+           "amod_osp_build", "amod_sba_build", "amod_pool_fetch", "amod_pool_view", "amod_npo_match",
+           "amod_gather_bench")
+
+_lib = None
+
+
+def load_library(path: str | None = None) -> C.CDLL:
+    """Load libamod_b200.so; raises (never falls back) if it is missing."""
+    global _lib
+    if _lib is not None and path is None:
+        return _lib
+    p = path or LIB_PATH
+    if not os.path.exists(p):
+        raise RuntimeError(f"{p} not found: build it with `python __graft_entry__.py` "
+                           f"(there is no CPU fallback for the OSP pool builder)")
+    lib = C.CDLL(p)
+    lib.amod_create.argtypes = [C.POINTER(C.c_void_p), C.c_int, C.c_int, C.c_void_p, C.c_int]
+    lib.amod_create.restype = C.c_int
+    lib.amod_destroy.argtypes = [C.c_void_p]
+    lib.amod_destroy.restype = None
+    lib.amod_last_error.argtypes = [C.c_void_p]
+    lib.amod_last_error.restype = C.c_char_p
+    lib.amod_version.argtypes = []
+    lib.amod_version.restype = C.c_char_p
+    lib.amod_set_stream.argtypes = [C.c_void_p, C.c_void_p]
+    lib.amod_set_stream.restype = C.c_int
+    for name in ("amod_osp_build", "amod_sba_build"):
+        fn = getattr(lib, name)
+        fn.argtypes = [C.c_void_p, C.POINTER(AmodEpoch), C.c_int, C.POINTER(AmodStats)]
+        fn.restype = C.c_int
+    lib.amod_pool_fetch.argtypes = [C.c_void_p, C.POINTER(AmodPool), C.c_int]
+    lib.amod_pool_fetch.restype = C.c_int
+    lib.amod_pool_view.argtypes = [C.c_void_p, C.POINTER(AmodPool)]
+    lib.amod_pool_view.restype = C.c_int
+    lib.amod_npo_match.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_int,
+                                   C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_int32), C.POINTER(C.c_int32)]
+    lib.amod_npo_match.restype = C.c_int
+    lib.amod_gather_bench.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int,
+                                      C.POINTER(C.c_double)]
+    lib.amod_gather_bench.restype = C.c_int
+    if path is None:
+        _lib = lib
+    return lib

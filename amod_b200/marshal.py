@@ -1,0 +1,305 @@
+"""Host-side marshalling between the reference's Python records and the SoA epoch
+arrays that cross the C-ABI (include/amod_b200.h, struct amod_epoch / amod_pool).
+
+Record layouts mirrored here:
+  stop       (rid, pod, tnid, ddl)                    types.py:66-69, scheduling.py:56-57
+  Veh fields id, nid, t_to_nid, load, status, sche, onboard_rids   vehicle.py:41-70
+  Req fields id, onid, dnid, Clp, Cld, Tr, Ts, status              request.py:25-41
+  pool entry [veh, trip, sche, cost, score]           dispatch_osp.py:105
+
+Stop code (int32): 2*req_index + (0 pick-up | 1 drop-off), or -1 for the rebalancing
+stop (rid=-1, pod=0) whose node/deadline are per-vehicle (rebalancing_npo.py:37).
+"""
+from __future__ import annotations
+
+import numpy as np
+
+MODE_OSP = 0      # enable_reoptimization=True   dispatch_osp.py:301-322
+MODE_OSP_NR = 1   # enable_reoptimization=False  dispatch_osp.py:301-303
+MODE_SBA = 2      # dispatch_sba.py:44-74
+
+KIND_BASIC, KIND_TRIP, KIND_CURRENT, KIND_SBA_PAIR, KIND_SBA_EMPTY = 0, 1, 2, 3, 4
+
+ST_IDLE, ST_WORKING, ST_REBALANCING = 1, 2, 3  # types.py:18-21
+
+
+def _status_value(s) -> int:
+    return int(getattr(s, "value", s))
+
+
+class Epoch:
+    """SoA view of one epoch's seam inputs.  All arrays are C-contiguous numpy."""
+
+    FIELDS = ("veh_nid", "veh_t_to_nid", "veh_load", "veh_status", "veh_sche_off", "sche_code",
+              "sche_onboard", "veh_reb_node", "veh_reb_ddl", "req_id", "req_onid", "req_dnid",
+              "req_clp", "req_cld", "req_tr", "req_ts", "search")
+
+    def __init__(self, **kw):
+        self.T = int(kw.pop("T"))
+        self.cap = int(kw.pop("cap"))
+        self.mode = int(kw.pop("mode"))
+        for f in self.FIELDS:
+            setattr(self, f, kw.pop(f))
+        assert not kw, kw
+        self.canon()
+
+    def canon(self):
+        dt = dict(veh_nid=np.int32, veh_t_to_nid=np.float64, veh_load=np.int32, veh_status=np.int32,
+                  veh_sche_off=np.int32, sche_code=np.int32, sche_onboard=np.uint8, veh_reb_node=np.int32,
+                  veh_reb_ddl=np.float64, req_id=np.int32, req_onid=np.int32, req_dnid=np.int32,
+                  req_clp=np.float64, req_cld=np.float64, req_tr=np.float64, req_ts=np.float64,
+                  search=np.int32)
+        for f, d in dt.items():
+            setattr(self, f, np.ascontiguousarray(getattr(self, f), dtype=d))
+
+    @property
+    def n_veh(self):
+        return self.veh_nid.size
+
+    @property
+    def n_req(self):
+        return self.req_onid.size
+
+    @property
+    def n_search(self):
+        return self.search.size
+
+    def to_npz_dict(self, prefix=""):
+        d = {prefix + f: getattr(self, f) for f in self.FIELDS}
+        d[prefix + "scalars"] = np.array([self.T, self.cap, self.mode], dtype=np.int64)
+        return d
+
+    @classmethod
+    def from_npz_dict(cls, d, prefix=""):
+        T, cap, mode = (int(x) for x in d[prefix + "scalars"])
+        return cls(T=T, cap=cap, mode=mode, **{f: d[prefix + f] for f in cls.FIELDS})
+
+    def shard(self, rank: int, world: int) -> tuple["Epoch", np.ndarray]:
+        """Vehicles rank, rank+world, ... (interleaved: vehicle work is heavy-tailed and
+        spatially correlated with fleet order, platform.py:51-55).  Requests are replicated."""
+        sel = np.arange(rank, self.n_veh, world, dtype=np.int64)
+        lens = np.diff(self.veh_sche_off)[sel]
+        off = np.zeros(sel.size + 1, dtype=np.int32)
+        np.cumsum(lens, out=off[1:])
+        idx = np.concatenate([np.arange(self.veh_sche_off[v], self.veh_sche_off[v + 1]) for v in sel]) \
+            if sel.size else np.zeros(0, dtype=np.int64)
+        idx = idx.astype(np.int64)
+        kw = {f: getattr(self, f) for f in self.FIELDS}
+        for f in ("veh_nid", "veh_t_to_nid", "veh_load", "veh_status", "veh_reb_node", "veh_reb_ddl"):
+            kw[f] = kw[f][sel]
+        kw["veh_sche_off"] = off
+        kw["sche_code"] = self.sche_code[idx]
+        kw["sche_onboard"] = self.sche_onboard[idx]
+        return Epoch(T=self.T, cap=self.cap, mode=self.mode, **kw), sel
+
+
+def marshal_epoch(reqs, vehs, search_rids, T: int, cap: int, mode: int, check: bool = True):
+    """Veh/Req objects -> Epoch.  `search_rids` is considered_rids (OSP, dispatch_osp.py:33-39)
+    or new_received_rids (SBA, dispatch_sba.py:56).  Returns (epoch, req_objs) where
+    req_objs[i] is the Req behind request index i."""
+    rid_set = set(int(r) for r in search_rids)
+    for veh in vehs:
+        for stop in veh.sche:
+            if stop[0] >= 0:
+                rid_set.add(int(stop[0]))
+    rids = sorted(rid_set)
+    index_of = {rid: i for i, rid in enumerate(rids)}
+    req_objs = [reqs[rid] for rid in rids]
+    nr = len(rids)
+    req_id = np.fromiter(rids, dtype=np.int32, count=nr)
+    req_onid = np.fromiter((r.onid for r in req_objs), dtype=np.int32, count=nr)
+    req_dnid = np.fromiter((r.dnid for r in req_objs), dtype=np.int32, count=nr)
+    req_clp = np.fromiter((r.Clp for r in req_objs), dtype=np.float64, count=nr)
+    req_cld = np.fromiter((r.Cld for r in req_objs), dtype=np.float64, count=nr)
+    req_tr = np.fromiter((r.Tr for r in req_objs), dtype=np.float64, count=nr)
+    req_ts = np.fromiter((r.Ts for r in req_objs), dtype=np.float64, count=nr)
+    search = np.fromiter((index_of[int(r)] for r in search_rids), dtype=np.int32, count=len(search_rids))
+
+    nv = len(vehs)
+    veh_nid = np.fromiter((v.nid for v in vehs), dtype=np.int32, count=nv)
+    veh_t = np.fromiter((v.t_to_nid for v in vehs), dtype=np.float64, count=nv)
+    veh_load = np.fromiter((v.load for v in vehs), dtype=np.int32, count=nv)
+    veh_status = np.fromiter((_status_value(v.status) for v in vehs), dtype=np.int32, count=nv)
+    off = np.zeros(nv + 1, dtype=np.int32)
+    np.cumsum(np.fromiter((len(v.sche) for v in vehs), dtype=np.int32, count=nv), out=off[1:])
+    ns = int(off[-1])
+    code = np.empty(ns, dtype=np.int32)
+    onboard = np.zeros(ns, dtype=np.uint8)
+    reb_node = np.zeros(nv, dtype=np.int32)
+    reb_ddl = np.zeros(nv, dtype=np.float64)
+    k = 0
+    for vi, veh in enumerate(vehs):
+        ob = veh.onboard_rids
+        for (rid, pod, tnid, ddl) in veh.sche:
+            if rid < 0:
+                if check and not (rid == -1 and pod == 0):
+                    raise ValueError(f"vehicle {vi}: unexpected stop {(rid, pod, tnid, ddl)}")
+                code[k] = -1
+                reb_node[vi] = tnid
+                reb_ddl[vi] = ddl
+            else:
+                i = index_of[int(rid)]
+                code[k] = 2 * i + (1 if pod == -1 else 0)
+                if rid in ob:
+                    onboard[k] = 1
+                if check:
+                    r = req_objs[i]
+                    exp = (r.onid, r.Clp) if pod == 1 else (r.dnid, r.Cld)
+                    if pod not in (1, -1) or tnid != exp[0] or ddl != exp[1]:
+                        raise ValueError(f"vehicle {vi}: stop {(rid, pod, tnid, ddl)} does not match its request")
+            k += 1
+    ep = Epoch(T=T, cap=cap, mode=mode, veh_nid=veh_nid, veh_t_to_nid=veh_t, veh_load=veh_load,
+               veh_status=veh_status, veh_sche_off=off, sche_code=code, sche_onboard=onboard,
+               veh_reb_node=reb_node, veh_reb_ddl=reb_ddl, req_id=req_id, req_onid=req_onid,
+               req_dnid=req_dnid, req_clp=req_clp, req_cld=req_cld, req_tr=req_tr, req_ts=req_ts,
+               search=search)
+    return ep, req_objs
+
+
+class Pool:
+    """SoA pool as returned over the C-ABI (struct amod_pool)."""
+
+    FIELDS = ("ent_veh", "ent_kind", "ent_trip_off", "ent_sche_off", "ent_cost", "ent_delay",
+              "ent_nfeas", "trip_req", "sche_code")
+
+    def __init__(self, **kw):
+        self.stats = dict(kw.pop("stats", {}))
+        for f in self.FIELDS:
+            setattr(self, f, kw.pop(f))
+        assert not kw, kw
+
+    @property
+    def n_entries(self):
+        return self.ent_veh.size
+
+    def to_npz_dict(self, prefix=""):
+        return {prefix + f: getattr(self, f) for f in self.FIELDS}
+
+    @classmethod
+    def from_npz_dict(cls, d, prefix=""):
+        return cls(**{f: d[prefix + f] for f in cls.FIELDS})
+
+    def take(self, idx: np.ndarray) -> "Pool":
+        """Entries `idx` in that order (re-packs the two CSR payloads)."""
+        idx = np.asarray(idx, dtype=np.int64)
+
+        def regather(off, data):
+            lens = (off[1:] - off[:-1])[idx]
+            new_off = np.zeros(idx.size + 1, dtype=np.int64)
+            np.cumsum(lens, out=new_off[1:])
+            src = np.repeat(off[:-1][idx] - new_off[:-1], lens) + np.arange(new_off[-1])
+            return new_off, data[src]
+
+        toff, treq = regather(self.ent_trip_off.astype(np.int64), self.trip_req)
+        soff, scode = regather(self.ent_sche_off.astype(np.int64), self.sche_code)
+        return Pool(ent_veh=self.ent_veh[idx], ent_kind=self.ent_kind[idx], ent_trip_off=toff,
+                    ent_sche_off=soff, ent_cost=self.ent_cost[idx], ent_delay=self.ent_delay[idx],
+                    ent_nfeas=self.ent_nfeas[idx], trip_req=treq, sche_code=scode, stats=self.stats)
+
+
+def concat_pools(pools: list["Pool"]) -> "Pool":
+    def cat_off(name):
+        outs, base = [np.zeros(1, dtype=np.int64)], 0
+        for p in pools:
+            o = getattr(p, name).astype(np.int64)
+            outs.append(o[1:] + base)
+            base += int(o[-1])
+        return np.concatenate(outs)
+
+    kw = {f: np.concatenate([getattr(p, f) for p in pools]) for f in Pool.FIELDS
+          if f not in ("ent_trip_off", "ent_sche_off")}
+    kw["ent_trip_off"] = cat_off("ent_trip_off")
+    kw["ent_sche_off"] = cat_off("ent_sche_off")
+    stats = {}
+    for p in pools:
+        for k, v in p.stats.items():
+            stats[k] = stats.get(k, 0) + v
+    return Pool(stats=stats, **kw)
+
+
+def records_to_pool(records, vehs, index_of_rid: dict, mode: int) -> Pool:
+    """Reference pool records -> Pool arrays (used to store golden vectors).  `cost` is
+    record[3] as returned by the seam, i.e. before the scorer overwrites it
+    (scheduling.py:145); delay/nfeas are filled by the caller if known."""
+    veh_index = {id(v): i for i, v in enumerate(vehs)}
+    n = len(records)
+    ent_veh = np.empty(n, dtype=np.int32)
+    ent_kind = np.zeros(n, dtype=np.int32)
+    ent_cost = np.empty(n, dtype=np.float64)
+    toff = np.zeros(n + 1, dtype=np.int64)
+    soff = np.zeros(n + 1, dtype=np.int64)
+    treq, scode = [], []
+    for e, (veh, trip, sche, cost, _score) in enumerate(records):
+        ent_veh[e] = veh_index[id(veh)]
+        ent_cost[e] = cost
+        treq.extend(index_of_rid[r.id] for r in trip)
+        for (rid, pod, _tnid, _ddl) in sche:
+            scode.append(-1 if rid < 0 else 2 * index_of_rid[rid] + (1 if pod == -1 else 0))
+        toff[e + 1] = len(treq)
+        soff[e + 1] = len(scode)
+    return Pool(ent_veh=ent_veh, ent_kind=ent_kind, ent_trip_off=toff, ent_sche_off=soff,
+                ent_cost=ent_cost, ent_delay=np.zeros(n), ent_nfeas=np.zeros(n, dtype=np.int32),
+                trip_req=np.asarray(treq, dtype=np.int32), sche_code=np.asarray(scode, dtype=np.int32))
+
+
+class PoolRecords(list):
+    """The list the seams return: plain 5-element lists [veh, trip, sche, cost, score]
+    (consumers index and overwrite pair[3], pair[4]: scheduling.py:145,161), plus the
+    device-computed delays so the scorer pass can be skipped."""
+    delays: np.ndarray | None = None
+    stats: dict | None = None
+
+
+def pool_to_records(pool: Pool, ep: Epoch, vehs, req_objs) -> PoolRecords:
+    """Pool arrays -> the reference's record list with live Veh/Req references and a
+    fresh mutable list of 4-tuples per schedule (vehicle.py:234-245 pops from it)."""
+    pick = [(r.id, 1, r.onid, r.Clp) for r in req_objs]
+    drop = [(r.id, -1, r.dnid, r.Cld) for r in req_objs]
+    reb = {}
+    out = PoolRecords()
+    ent_veh = pool.ent_veh.tolist()
+    toff = pool.ent_trip_off.tolist()
+    soff = pool.ent_sche_off.tolist()
+    treq = pool.trip_req.tolist()
+    scode = pool.sche_code.tolist()
+    cost = pool.ent_cost  # keep numpy float64 scalars like the reference (np.float64 costs)
+    for e in range(len(ent_veh)):
+        vi = ent_veh[e]
+        veh = vehs[vi]
+        sche = []
+        for c in scode[soff[e]:soff[e + 1]]:
+            if c < 0:
+                if vi not in reb:
+                    reb[vi] = next(s for s in veh.sche if s[0] == -1)
+                sche.append(reb[vi])
+            else:
+                sche.append(drop[c >> 1] if c & 1 else pick[c >> 1])
+        out.append([veh, [req_objs[i] for i in treq[toff[e]:toff[e + 1]]], sche, cost[e], 0.0])
+    out.delays = pool.ent_delay
+    out.stats = pool.stats
+    return out
+
+
+def pools_equal(a: Pool, b: Pool, rtol: float = 0.0, check_delay: bool = True, check_nfeas: bool = True,
+                check_kind: bool = False) -> tuple[bool, str]:
+    """Bit-exact structure; cost/delay within rtol (0.0 = bit-exact)."""
+    if a.n_entries != b.n_entries:
+        return False, f"n_entries {a.n_entries} != {b.n_entries}"
+    for f in ("ent_veh", "ent_trip_off", "ent_sche_off", "trip_req", "sche_code"):
+        x, y = getattr(a, f).astype(np.int64), getattr(b, f).astype(np.int64)
+        if x.shape != y.shape or not np.array_equal(x, y):
+            bad = np.flatnonzero(x[:min(x.size, y.size)] != y[:min(x.size, y.size)])
+            return False, f"{f} differs (first at {bad[:1]}; sizes {x.size},{y.size})"
+    if check_kind and not np.array_equal(a.ent_kind, b.ent_kind):
+        return False, "ent_kind differs"
+    if check_nfeas and not np.array_equal(a.ent_nfeas, b.ent_nfeas):
+        bad = np.flatnonzero(a.ent_nfeas != b.ent_nfeas)
+        return False, f"ent_nfeas differs at {bad[:5]}"
+    names = ("ent_cost", "ent_delay") if check_delay else ("ent_cost",)
+    for f in names:
+        x, y = getattr(a, f), getattr(b, f)
+        ok = (x == y) if rtol == 0.0 else (np.abs(x - y) <= rtol * np.maximum(np.abs(x), np.abs(y)))
+        if not ok.all():
+            bad = np.flatnonzero(~ok)
+            return False, f"{f} differs at {bad[:5]}: {x[bad[:5]]} vs {y[bad[:5]]}"
+    return True, ""

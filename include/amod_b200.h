@@ -1,0 +1,158 @@
+/* amod_b200.h — C-ABI of the B200-native Optimal-Schedule-Pool builder.
+ *
+ * The reference (Leot6/AMoD) is pure Python and has no FFI; the seams this library
+ * stands behind are three module-level functions:
+ *   B1  src/dispatcher/dispatch_osp.py:94-129   compute_candidate_veh_trip_pairs
+ *   B2  src/dispatcher/dispatch_sba.py:44-74    compute_candidate_veh_req_pairs
+ *   B3  src/rebalancer/rebalancing_npo.py:8-62  reposition_idle_vehicles_to_nearest_pending_orders
+ * A maintainer binds these entry points with ctypes; the Python
+ * mirror in amod_b200/pool.py does exactly that.  Plain pointers and sizes only.
+ *
+ * Conventions: every function returns 0 (AMOD_OK) or a negative error code;
+ * amod_last_error() gives the text.  Node ids are 1-based as in the reference
+ * (route_functions.py:23).  There is no CPU fallback: without a CUDA device
+ * amod_create fails with AMOD_E_CUDA.
+ */
+#ifndef AMOD_B200_H
+#define AMOD_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define AMOD_OK 0
+#define AMOD_E_BADARG (-1)   /* malformed input (sizes, node ids, codes out of range)            */
+#define AMOD_E_CUDA (-2)     /* CUDA runtime error or no device                                   */
+#define AMOD_E_CAPACITY (-3) /* caller buffer too small; required sizes are written to n_*        */
+#define AMOD_E_LEVELS (-4)   /* a feasible trip of size cap+4 exists: the reference raises
+                                IndexError there (dispatch_osp.py:8,226); so do we               */
+#define AMOD_E_NOMEM (-5)
+#define AMOD_E_LIMIT (-6)    /* input exceeds a compiled limit (stops per schedule, requests)     */
+
+#define AMOD_LOC_HOST 0      /* pointers in the struct are host memory   */
+#define AMOD_LOC_DEVICE 1    /* pointers are device memory of ctx's GPU  */
+
+#define AMOD_TT_F32 0        /* travel-time table element type */
+#define AMOD_TT_F64 1
+
+/* dispatch mode = which reference seam/branch is being replaced */
+#define AMOD_MODE_OSP 0      /* dispatch_osp.py, enable_reoptimization=True  */
+#define AMOD_MODE_OSP_NR 1   /* dispatch_osp.py, enable_reoptimization=False */
+#define AMOD_MODE_SBA 2      /* dispatch_sba.py                              */
+
+/* pool entry kinds */
+#define AMOD_KIND_BASIC 0     /* dispatch_osp.py:113,148  [veh, [], basic_sches[0], cost]     */
+#define AMOD_KIND_TRIP 1      /* dispatch_osp.py:115-117  one feasible trip                   */
+#define AMOD_KIND_CURRENT 2   /* dispatch_osp.py:120-125  the current working schedule        */
+#define AMOD_KIND_SBA_PAIR 3  /* dispatch_sba.py:65                                           */
+#define AMOD_KIND_SBA_EMPTY 4 /* dispatch_sba.py:68-69                                        */
+
+#define AMOD_MAX_STOPS 40     /* stops in one schedule: 3*cap+8 (cap<=10)     */
+#define AMOD_MAX_CAP 10
+#define AMOD_MAX_TRIP 14      /* cap+4 */
+
+typedef struct amod_ctx amod_ctx;
+
+/* One epoch's inputs, structure-of-arrays (vehicle.py:41-70, request.py:25-41).
+ * A stop code is 2*req_index + (0 pick-up | 1 drop-off); -1 is the vehicle's
+ * rebalancing stop (rid=-1,pod=0; rebalancing_npo.py:37) whose node/deadline are
+ * veh_reb_node/veh_reb_ddl.  A request stop's node/deadline are (onid,Clp) or
+ * (dnid,Cld) of its request (scheduling.py:56-57). */
+typedef struct amod_epoch {
+    int32_t n_veh, n_req, n_search, cap;
+    int32_t mode;                 /* AMOD_MODE_*                                            */
+    int32_t reserved;
+    int64_t T;                    /* system_time_sec (epoch end)                            */
+    const int32_t* veh_nid;       /* [n_veh] current node                                   */
+    const double*  veh_t_to_nid;  /* [n_veh]                                                */
+    const int32_t* veh_load;      /* [n_veh]                                                */
+    const int32_t* veh_status;    /* [n_veh] 1 idle, 2 working, 3 rebalancing (types.py:18) */
+    const int32_t* veh_sche_off;  /* [n_veh+1] CSR offsets into sche_code/sche_onboard      */
+    const int32_t* sche_code;     /* [n_stops] veh.sche as stop codes                       */
+    const uint8_t* sche_onboard;  /* [n_stops] 1 if the stop's rid is in veh.onboard_rids   */
+    const int32_t* veh_reb_node;  /* [n_veh]                                                */
+    const double*  veh_reb_ddl;   /* [n_veh]                                                */
+    const int32_t* req_onid;      /* [n_req]                                                */
+    const int32_t* req_dnid;      /* [n_req]                                                */
+    const double*  req_clp;       /* [n_req] latest pick-up  (request.py:33)                */
+    const double*  req_cld;       /* [n_req] latest drop-off (request.py:34)                */
+    const double*  req_tr;        /* [n_req] request time                                   */
+    const double*  req_ts;        /* [n_req] shortest travel time                           */
+    const int32_t* search;        /* [n_search] request indices: considered_rids (OSP) or
+                                     new_received_rids (SBA), in the reference's order      */
+} amod_epoch;
+
+/* The candidate pool in the reference's order (dispatch_osp.py:107-125 vehicle-major;
+ * dispatch_sba.py:56-69 request-major then one empty pair per vehicle). */
+typedef struct amod_pool {
+    int64_t cap_entries, cap_trip_reqs, cap_stops; /* in: capacities of the buffers below  */
+    int64_t n_entries, n_trip_reqs, n_stops;       /* out                                  */
+    int32_t* ent_veh;       /* [n_entries] vehicle index                                   */
+    int32_t* ent_kind;      /* [n_entries] AMOD_KIND_*                                     */
+    int64_t* ent_trip_off;  /* [n_entries+1] CSR into trip_req                             */
+    int64_t* ent_sche_off;  /* [n_entries+1] CSR into sche_code                            */
+    double*  ent_cost;      /* [n_entries] schedule completion time (scheduling.py:98,107) */
+    double*  ent_delay;     /* [n_entries] compute_sche_delay (scheduling.py:126-137)      */
+    int32_t* ent_nfeas;     /* [n_entries] number of feasible schedules of the trip        */
+    int32_t* trip_req;      /* request indices, ascending (dispatch_osp.py:124,187)        */
+    int32_t* sche_code;     /* stop codes of the entry's schedule                          */
+} amod_pool;
+
+typedef struct amod_stats {
+    int64_t n_screens;      /* reachability screens (dispatch_osp.py:160, dispatch_sba.py:59)        */
+    int64_t n_evals;        /* test_constraints_get_cost executions AS THE REFERENCE WOULD PERFORM
+                               THEM (scheduling.py:28, dispatch_osp.py:318), i.e. honouring its
+                               early exits (scheduling.py:41-44)                                     */
+    int64_t n_lookups;      /* travel-time lookups the reference would perform       */
+    int64_t n_entries;
+    int64_t n_sches_stored; /* feasible schedules materialised over all levels                       */
+    int64_t n_tasks;        /* compute_schedule calls                                                */
+    int32_t n_levels;
+    int32_t n_kernel_launches;
+    double  ms_build;       /* device time of the whole build (CUDA events)                          */
+    double  ms_eval;        /* device time inside the insertion-search kernels                       */
+    int32_t n_eval_launches;
+    int32_t reserved;
+} amod_stats;
+
+/* Upload the travel-time table (row = origin, col = destination; route_functions.py:22-25). */
+int amod_create(amod_ctx** out, int device, int n_nodes, const void* tt_host, int tt_dtype);
+void amod_destroy(amod_ctx* ctx);
+const char* amod_last_error(amod_ctx* ctx);
+const char* amod_version(void);
+
+/* Use an existing CUDA stream (cudaStream_t) for all work of this context; 0 = own stream. */
+int amod_set_stream(amod_ctx* ctx, void* cuda_stream);
+
+/* B1: build the OSP pool for one epoch into the context's device-resident pool.
+ * ep->mode is AMOD_MODE_OSP or AMOD_MODE_OSP_NR.  `loc` says where ep's arrays live. */
+int amod_osp_build(amod_ctx* ctx, const amod_epoch* ep, int loc, amod_stats* stats);
+
+/* B2: SBA vehicle-request feasibility/cost matrix (ep->mode = AMOD_MODE_SBA). */
+int amod_sba_build(amod_ctx* ctx, const amod_epoch* ep, int loc, amod_stats* stats);
+
+/* Copy the last built pool into caller-owned buffers (host or device).  Returns
+ * AMOD_E_CAPACITY with the required n_* filled if a buffer is too small. */
+int amod_pool_fetch(amod_ctx* ctx, amod_pool* out, int loc);
+
+/* Device pointers of the last built pool (valid until the next build on ctx). */
+int amod_pool_view(amod_ctx* ctx, amod_pool* view);
+
+/* B3: NPO matching (rebalancing_npo.py:26-59).  idle_nid[i] = node of the i-th IDLE vehicle
+ * in fleet order, pend_onid[j] = origin of the j-th PENDING request in id order.  Writes
+ * min(n_idle,n_pend) matches in the reference's selection order. */
+int amod_npo_match(amod_ctx* ctx, const int32_t* idle_nid, int32_t n_idle, const int32_t* pend_onid,
+                   int32_t n_pend, int loc, int32_t* out_idle_idx, int32_t* out_pend_idx, double* out_dt,
+                   int32_t* n_out, int32_t* n_rounds);
+
+/* Raw travel-time gather out[i] = tt[o[i]][d[i]] (route_functions.py:22-25): used by the
+ * L2-gather roofline microbenchmark.  Device pointers.  Returns device ms in *ms. */
+int amod_gather_bench(amod_ctx* ctx, const int32_t* o_dev, const int32_t* d_dev, float* out_dev,
+                      int64_t n, int iters, double* ms);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* AMOD_B200_H */
