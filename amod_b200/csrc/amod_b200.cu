@@ -1,0 +1,654 @@
+// amod_b200.cu — host side of the C-ABI (include/amod_b200.h): level-synchronous construction of
+// the Optimal Schedule Pool on one B200.  See DESIGN.md for the data layout and kernel list.
+#include <algorithm>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <type_traits>
+#include <vector>
+
+#include "common.cuh"
+#include "eval.cuh"
+#include "levels.cuh"
+#include "npo.cuh"
+#include "pool.cuh"
+#include "scan.cuh"
+
+#define CK(call)                                                                                         \
+    do {                                                                                                 \
+        cudaError_t e_ = (call);                                                                         \
+        if (e_ != cudaSuccess) return ctx->fail(AMOD_E_CUDA, "%s:%d %s: %s", __FILE__, __LINE__, #call,   \
+                                                 cudaGetErrorString(e_));                                \
+    } while (0)
+#define CKR(expr)                    \
+    do {                             \
+        int r_ = (expr);             \
+        if (r_ != AMOD_OK) return r_; \
+    } while (0)
+
+struct DevBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+    cudaError_t ensure(size_t bytes) {
+        if (bytes <= cap) return cudaSuccess;
+        if (p) cudaFree(p);
+        p = nullptr; cap = 0;
+        size_t want = std::max(bytes + bytes / 4, (size_t)4096);
+        cudaError_t e = cudaMalloc(&p, want);
+        if (e == cudaSuccess) cap = want;
+        return e;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+    template <typename T> T* as() { return (T*)p; }
+};
+
+struct LevelBufs { DevBuf trip_veh, trip_req, sch_off, nfeas, rot, cost, sch, veh_start; };
+
+struct amod_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    int n_nodes = 0, tt_dtype = 0;
+    void* d_tt = nullptr;
+    int n_sm = 148;
+    std::string err;
+    // staging of host epochs
+    DevBuf ep_dev; void* ep_pinned = nullptr; size_t ep_pinned_cap = 0;
+    // workspace
+    DevBuf len0, S0, words0, flag8, pos, pos2, partial, total, stats, task_veh[2], task_base[2], task_q[2], task_nfeas,
+        task_cost, words, hash, row_cnt, row_off, tmp_j, tmp_q, tmp_row;
+    LevelBufs lv[MAX_LEVELS];
+    // pool
+    DevBuf veh_cnt, veh_off, ent_veh, ent_kind, ent_nfeas, ent_tlen, ent_slen, ent_src, ent_trip, ent_cost, ent_delay,
+        trip_off, sche_off, trip_req, sche_code;
+    i64 pool_entries = 0, pool_trip_reqs = 0, pool_stops = 0;
+    bool pool_valid = false;
+    // npo
+    DevBuf npo_in, npo_vm, npo_rm, npo_rb, npo_vb, npo_rdt, npo_mdt, npo_cnt;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    std::vector<cudaEvent_t> ev_pool;
+    int n_launches = 0;
+
+    int fail(int code, const char* fmt, ...) {
+        char buf[512];
+        va_list ap; va_start(ap, fmt); vsnprintf(buf, sizeof buf, fmt, ap); va_end(ap);
+        err = buf;
+        return code;
+    }
+};
+
+static thread_local std::string g_err;
+
+template <typename F>
+static int dispatch_tt(amod_ctx* ctx, F&& f) {
+    if (ctx->tt_dtype == AMOD_TT_F64) return f(Table<double>{(const double*)ctx->d_tt, ctx->n_nodes});
+    return f(Table<float>{(const float*)ctx->d_tt, ctx->n_nodes});
+}
+
+static inline int nblk(i64 n, int per) { return (int)((n + per - 1) / per); }
+
+// exclusive scan in[0..n) -> out[0..n], total also copied to *h_total when requested (synchronises)
+template <typename Tin>
+static int scan_excl(amod_ctx* ctx, const Tin* in, i64 n, i64* out, i64* h_total) {
+    cudaStream_t st = ctx->stream;
+    if (n == 0) {
+        CK(cudaMemsetAsync(out, 0, sizeof(i64), st));
+        if (h_total) *h_total = 0;
+        return AMOD_OK;
+    }
+    int nb = nblk(n, SCAN_TILE);
+    CK(ctx->partial.ensure(sizeof(i64) * (size_t)nb));
+    CK(ctx->total.ensure(sizeof(i64)));
+    k_scan_reduce<Tin><<<nb, SCAN_THREADS, 0, st>>>(in, n, ctx->partial.as<i64>());
+    k_scan_partials<<<1, SCAN_THREADS, 0, st>>>(ctx->partial.as<i64>(), nb, ctx->total.as<i64>());
+    k_scan_final<Tin><<<nb, SCAN_THREADS, 0, st>>>(in, n, ctx->partial.as<i64>(), out);
+    ctx->n_launches += 3;
+    if (h_total) {
+        CK(cudaMemcpyAsync(h_total, ctx->total.p, sizeof(i64), cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+    }
+    return AMOD_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+extern "C" const char* amod_version(void) { return "amod_b200 0.1 (sm_100a)"; }
+
+extern "C" const char* amod_last_error(amod_ctx* ctx) { return ctx ? ctx->err.c_str() : g_err.c_str(); }
+
+extern "C" int amod_create(amod_ctx** out, int device, int n_nodes, const void* tt_host, int tt_dtype) {
+    if (!out || !tt_host || n_nodes <= 0 || (tt_dtype != AMOD_TT_F32 && tt_dtype != AMOD_TT_F64)) {
+        g_err = "amod_create: bad argument";
+        return AMOD_E_BADARG;
+    }
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0 || device >= ndev) {
+        g_err = std::string("amod_create: no usable CUDA device (") + cudaGetErrorString(e) + "); there is no CPU fallback";
+        return AMOD_E_CUDA;
+    }
+    amod_ctx* ctx = new amod_ctx();
+    ctx->device = device; ctx->n_nodes = n_nodes; ctx->tt_dtype = tt_dtype;
+    auto bail = [&](const char* what, cudaError_t ce) {
+        g_err = std::string("amod_create: ") + what + ": " + cudaGetErrorString(ce);
+        delete ctx;
+        return AMOD_E_CUDA;
+    };
+    if ((e = cudaSetDevice(device)) != cudaSuccess) return bail("cudaSetDevice", e);
+    if ((e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking)) != cudaSuccess) return bail("stream", e);
+    ctx->own_stream = true;
+    cudaDeviceGetAttribute(&ctx->n_sm, cudaDevAttrMultiProcessorCount, device);
+    size_t bytes = (size_t)n_nodes * n_nodes * (tt_dtype == AMOD_TT_F64 ? 8 : 4);
+    if ((e = cudaMalloc(&ctx->d_tt, bytes)) != cudaSuccess) return bail("cudaMalloc(table)", e);
+    if ((e = cudaMemcpy(ctx->d_tt, tt_host, bytes, cudaMemcpyHostToDevice)) != cudaSuccess) return bail("upload table", e);
+    // Keep the table resident in L2 (126 MB on B200): persisting access-policy window on our stream.
+    int max_win = 0, max_persist = 0;
+    cudaDeviceGetAttribute(&max_win, cudaDevAttrMaxAccessPolicyWindowSize, device);
+    cudaDeviceGetAttribute(&max_persist, cudaDevAttrMaxPersistingL2CacheSize, device);
+    if (max_win > 0 && max_persist > 0) {
+        size_t win = std::min(bytes, (size_t)max_win);
+        cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, std::min((size_t)max_persist, win));
+        cudaStreamAttrValue av; memset(&av, 0, sizeof av);
+        av.accessPolicyWindow.base_ptr = ctx->d_tt;
+        av.accessPolicyWindow.num_bytes = win;
+        av.accessPolicyWindow.hitRatio = (float)std::min(1.0, (double)max_persist / (double)win);
+        av.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+        av.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+        cudaStreamSetAttribute(ctx->stream, cudaStreamAttributeAccessPolicyWindow, &av);
+        cudaGetLastError();
+    }
+    cudaEventCreate(&ctx->ev0); cudaEventCreate(&ctx->ev1);
+    *out = ctx;
+    return AMOD_OK;
+}
+
+extern "C" void amod_destroy(amod_ctx* ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    cudaDeviceSynchronize();
+    DevBuf* all[] = {&ctx->ep_dev, &ctx->len0, &ctx->S0, &ctx->words0, &ctx->flag8, &ctx->pos, &ctx->pos2, &ctx->partial,
+                     &ctx->total, &ctx->stats, &ctx->task_veh[0], &ctx->task_veh[1], &ctx->task_base[0], &ctx->task_base[1],
+                     &ctx->task_q[0], &ctx->task_q[1], &ctx->task_nfeas, &ctx->task_cost, &ctx->words, &ctx->hash,
+                     &ctx->row_cnt, &ctx->row_off, &ctx->tmp_j, &ctx->tmp_q, &ctx->tmp_row, &ctx->veh_cnt, &ctx->veh_off,
+                     &ctx->ent_veh, &ctx->ent_kind, &ctx->ent_nfeas, &ctx->ent_tlen, &ctx->ent_slen, &ctx->ent_src,
+                     &ctx->ent_trip, &ctx->ent_cost, &ctx->ent_delay, &ctx->trip_off, &ctx->sche_off, &ctx->trip_req,
+                     &ctx->sche_code, &ctx->npo_in, &ctx->npo_vm, &ctx->npo_rm, &ctx->npo_rb, &ctx->npo_vb, &ctx->npo_rdt,
+                     &ctx->npo_mdt, &ctx->npo_cnt};
+    for (DevBuf* b : all) b->release();
+    for (auto& l : ctx->lv) { l.trip_veh.release(); l.trip_req.release(); l.sch_off.release(); l.nfeas.release(); l.rot.release();
+                              l.cost.release(); l.sch.release(); l.veh_start.release(); }
+    if (ctx->ep_pinned) cudaFreeHost(ctx->ep_pinned);
+    if (ctx->d_tt) cudaFree(ctx->d_tt);
+    for (auto e : ctx->ev_pool) cudaEventDestroy(e);
+    if (ctx->ev0) cudaEventDestroy(ctx->ev0);
+    if (ctx->ev1) cudaEventDestroy(ctx->ev1);
+    if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+
+extern "C" int amod_set_stream(amod_ctx* ctx, void* cuda_stream) {
+    if (!ctx) return AMOD_E_BADARG;
+    if (ctx->own_stream && ctx->stream) { cudaStreamSynchronize(ctx->stream); cudaStreamDestroy(ctx->stream); }
+    if (cuda_stream) { ctx->stream = (cudaStream_t)cuda_stream; ctx->own_stream = false; }
+    else { CK(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking)); ctx->own_stream = true; }
+    return AMOD_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// epoch upload / validation
+// ------------------------------------------------------------------------------------------------
+static int validate_host_epoch(amod_ctx* ctx, const amod_epoch* ep) {
+    const int N = ctx->n_nodes;
+    for (int v = 0; v < ep->n_veh; v++) {
+        if (ep->veh_nid[v] < 1 || ep->veh_nid[v] > N) return ctx->fail(AMOD_E_BADARG, "vehicle %d: node id %d out of range", v, ep->veh_nid[v]);
+        if (ep->veh_sche_off[v + 1] < ep->veh_sche_off[v]) return ctx->fail(AMOD_E_BADARG, "veh_sche_off not monotone at %d", v);
+        if (ep->veh_sche_off[v + 1] - ep->veh_sche_off[v] > AMOD_MAX_STOPS - 2)
+            return ctx->fail(AMOD_E_LIMIT, "vehicle %d: schedule longer than %d stops", v, AMOD_MAX_STOPS - 2);
+        if (ep->veh_load[v] < 0) return ctx->fail(AMOD_E_BADARG, "vehicle %d: negative load", v);
+    }
+    for (int r = 0; r < ep->n_req; r++)
+        if (ep->req_onid[r] < 1 || ep->req_onid[r] > N || ep->req_dnid[r] < 1 || ep->req_dnid[r] > N)
+            return ctx->fail(AMOD_E_BADARG, "request %d: node id out of range", r);
+    const int ns = ep->n_veh ? ep->veh_sche_off[ep->n_veh] : 0;
+    for (int v = 0, k = 0; v < ep->n_veh; v++)
+        for (k = ep->veh_sche_off[v]; k < ep->veh_sche_off[v + 1]; k++) {
+            int c = ep->sche_code[k];
+            if (c < -1 || (c >> 1) >= ep->n_req) return ctx->fail(AMOD_E_BADARG, "stop code %d out of range", c);
+            if (c == -1 && (ep->veh_reb_node[v] < 1 || ep->veh_reb_node[v] > N))
+                return ctx->fail(AMOD_E_BADARG, "vehicle %d: rebalancing node out of range", v);
+        }
+    (void)ns;
+    for (int s = 0; s < ep->n_search; s++)
+        if (ep->search[s] < 0 || ep->search[s] >= ep->n_req) return ctx->fail(AMOD_E_BADARG, "search[%d] out of range", s);
+    return AMOD_OK;
+}
+
+static int upload_epoch(amod_ctx* ctx, const amod_epoch* ep, int loc, DEpoch* d) {
+    if (ep->n_veh < 0 || ep->n_req < 0 || ep->n_search < 0) return ctx->fail(AMOD_E_BADARG, "negative size");
+    if (ep->cap < 1 || ep->cap > AMOD_MAX_CAP) return ctx->fail(AMOD_E_LIMIT, "capacity %d outside 1..%d", ep->cap, AMOD_MAX_CAP);
+    if (ep->n_req > 16383) return ctx->fail(AMOD_E_LIMIT, "more than 16383 live requests in one epoch");
+    d->n_veh = ep->n_veh; d->n_req = ep->n_req; d->n_search = ep->n_search; d->cap = ep->cap; d->mode = ep->mode;
+    d->T = (double)ep->T;
+    if (loc == AMOD_LOC_DEVICE) {
+        d->veh_nid = ep->veh_nid; d->veh_t = ep->veh_t_to_nid; d->veh_load = ep->veh_load; d->veh_status = ep->veh_status;
+        d->veh_sche_off = ep->veh_sche_off; d->sche_code = ep->sche_code; d->sche_onboard = ep->sche_onboard;
+        d->reb_node = ep->veh_reb_node; d->reb_ddl = ep->veh_reb_ddl; d->onid = ep->req_onid; d->dnid = ep->req_dnid;
+        d->clp = ep->req_clp; d->cld = ep->req_cld; d->tr = ep->req_tr; d->ts = ep->req_ts; d->search = ep->search;
+        return AMOD_OK;
+    }
+    CKR(validate_host_epoch(ctx, ep));
+    const size_t V = ep->n_veh, R = ep->n_req, Q = ep->n_search;
+    const size_t NS = V ? (size_t)ep->veh_sche_off[V] : 0;
+    struct Part { const void* src; size_t bytes; const void** dst; };
+    Part parts[] = {
+        {ep->veh_t_to_nid, V * 8, (const void**)&d->veh_t}, {ep->veh_reb_ddl, V * 8, (const void**)&d->reb_ddl},
+        {ep->req_clp, R * 8, (const void**)&d->clp}, {ep->req_cld, R * 8, (const void**)&d->cld},
+        {ep->req_tr, R * 8, (const void**)&d->tr}, {ep->req_ts, R * 8, (const void**)&d->ts},
+        {ep->veh_nid, V * 4, (const void**)&d->veh_nid}, {ep->veh_load, V * 4, (const void**)&d->veh_load},
+        {ep->veh_status, V * 4, (const void**)&d->veh_status}, {ep->veh_sche_off, (V + 1) * 4, (const void**)&d->veh_sche_off},
+        {ep->veh_reb_node, V * 4, (const void**)&d->reb_node}, {ep->req_onid, R * 4, (const void**)&d->onid},
+        {ep->req_dnid, R * 4, (const void**)&d->dnid}, {ep->search, Q * 4, (const void**)&d->search},
+        {ep->sche_code, NS * 4, (const void**)&d->sche_code}, {ep->sche_onboard, NS, (const void**)&d->sche_onboard},
+    };
+    size_t total = 0;
+    for (auto& p : parts) total += (p.bytes + 15) & ~(size_t)15;
+    total = std::max(total, (size_t)16);
+    if (total > ctx->ep_pinned_cap) {
+        if (ctx->ep_pinned) cudaFreeHost(ctx->ep_pinned);
+        ctx->ep_pinned = nullptr; ctx->ep_pinned_cap = 0;
+        CK(cudaMallocHost(&ctx->ep_pinned, total * 2));
+        ctx->ep_pinned_cap = total * 2;
+    }
+    CK(ctx->ep_dev.ensure(total));
+    size_t off = 0;
+    for (auto& p : parts) {
+        if (p.bytes) memcpy((char*)ctx->ep_pinned + off, p.src, p.bytes);
+        *p.dst = (char*)ctx->ep_dev.p + off;
+        off += (p.bytes + 15) & ~(size_t)15;
+    }
+    CK(cudaMemcpyAsync(ctx->ep_dev.p, ctx->ep_pinned, total, cudaMemcpyHostToDevice, ctx->stream));
+    return AMOD_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// the build
+// ------------------------------------------------------------------------------------------------
+static int alloc_level(amod_ctx* ctx, int k, int n_trips, i64 n_words, int n_veh, Level* lv) {
+    LevelBufs& b = ctx->lv[k];
+    size_t n = (size_t)std::max(n_trips, 1);
+    CK(b.trip_veh.ensure(4 * n)); CK(b.trip_req.ensure(4 * n * (size_t)std::max(k, 1))); CK(b.sch_off.ensure(8 * n));
+    CK(b.nfeas.ensure(4 * n)); CK(b.rot.ensure(4 * n)); CK(b.cost.ensure(8 * n));
+    CK(b.sch.ensure(sizeof(code_t) * (size_t)std::max(n_words, (i64)1)));
+    CK(b.veh_start.ensure(4 * ((size_t)n_veh + 2)));
+    lv->k = k; lv->n_trips = n_trips;
+    lv->trip_veh = b.trip_veh.as<int>(); lv->trip_req = b.trip_req.as<int>(); lv->sch_off = b.sch_off.as<i64>();
+    lv->nfeas = b.nfeas.as<int>(); lv->rot = b.rot.as<int>(); lv->cost = b.cost.as<double>(); lv->sch = b.sch.as<code_t>();
+    lv->veh_start = b.veh_start.as<int>();
+    return AMOD_OK;
+}
+
+static cudaEvent_t get_event(amod_ctx* ctx, size_t i) {
+    while (ctx->ev_pool.size() <= i) { cudaEvent_t e; cudaEventCreate(&e); ctx->ev_pool.push_back(e); }
+    return ctx->ev_pool[i];
+}
+
+template <typename TT>
+static int build_impl(amod_ctx* ctx, const amod_epoch* ep, int loc, amod_stats* out_stats, Table<TT> tt) {
+    cudaStream_t st = ctx->stream;
+    CK(cudaSetDevice(ctx->device));
+    ctx->pool_valid = false;
+    ctx->n_launches = 0;
+    DEpoch d;
+    CK(cudaEventRecord(ctx->ev0, st));
+    CKR(upload_epoch(ctx, ep, loc, &d));
+    const int V = d.n_veh, Q = d.n_search, mode = d.mode;
+    const int max_level = mode == AMOD_MODE_SBA ? 1 : d.cap + 4;
+    size_t n_ev = 0;
+
+    CK(ctx->stats.ensure(sizeof(Stats)));
+    CK(cudaMemsetAsync(ctx->stats.p, 0, sizeof(Stats), st));
+    Stats* dstats = ctx->stats.as<Stats>();
+    LevelSet ls; memset(&ls, 0, sizeof ls);
+
+    // ---- level 0: basic schedules --------------------------------------------------------------
+    CK(ctx->len0.ensure(4 * (size_t)(V + 1))); CK(ctx->S0.ensure(4 * (size_t)(V + 1))); CK(ctx->words0.ensure(4 * (size_t)(V + 1)));
+    CK(ctx->pos.ensure(8 * (size_t)(V + 2)));
+    int* len0 = ctx->len0.as<int>();
+    i64 words0 = 0;
+    if (V > 0) {
+        k_basic<TT, 0><<<nblk(V, WARPS_PER_BLOCK), WARPS_PER_BLOCK * 32, 0, st>>>(d, tt, len0, ctx->S0.as<int>(), ctx->words0.as<int>(),
+                                                                               nullptr, nullptr, dstats);
+        ctx->n_launches++;
+    }
+    CKR(scan_excl<int>(ctx, ctx->words0.as<int>(), V, ctx->pos.as<i64>(), &words0));
+    CKR(alloc_level(ctx, 0, V, words0, V, &ls.lv[0]));
+    if (V > 0) {
+        CK(cudaMemcpyAsync(ls.lv[0].sch_off, ctx->pos.p, 8 * (size_t)V, cudaMemcpyDeviceToDevice, st));
+        k_basic<TT, 1><<<nblk(V, WARPS_PER_BLOCK), WARPS_PER_BLOCK * 32, 0, st>>>(d, tt, len0, ctx->S0.as<int>(), ctx->words0.as<int>(),
+                                                                               ls.lv[0].sch_off, ls.lv[0].sch, dstats);
+        k_level0_finish<<<nblk(V + 1, 256), 256, 0, st>>>(V, ctx->S0.as<int>(), ls.lv[0].trip_veh, ls.lv[0].nfeas, ls.lv[0].rot,
+                                                        ls.lv[0].veh_start);
+        ctx->n_launches += 2;
+    }
+    ls.n = 1;
+
+    // ---- level-1 tasks: reachability screen -----------------------------------------------------
+    const i64 n_screen = (i64)V * Q;
+    i64 n_tasks = 0;
+    int cur = 0;
+    CK(ctx->flag8.ensure((size_t)std::max(n_screen, (i64)1)));
+    CK(ctx->pos.ensure(8 * (size_t)(n_screen + 2)));
+    if (n_screen > 0) {
+        k_screen<TT><<<nblk(n_screen, 256), 256, 0, st>>>(d, tt, ctx->flag8.as<uint8_t>(), n_screen);
+        ctx->n_launches++;
+    }
+    CKR(scan_excl<uint8_t>(ctx, ctx->flag8.as<uint8_t>(), n_screen, ctx->pos.as<i64>(), &n_tasks));
+    if (n_tasks > 0x7fffffff) return ctx->fail(AMOD_E_LIMIT, "too many size-1 candidates");
+    auto ensure_tasks = [&](int which, i64 n) -> int {
+        size_t b = 4 * (size_t)std::max(n, (i64)1);
+        CK(ctx->task_veh[which].ensure(b)); CK(ctx->task_base[which].ensure(b)); CK(ctx->task_q[which].ensure(b));
+        return AMOD_OK;
+    };
+    CKR(ensure_tasks(cur, n_tasks));
+    if (n_tasks > 0) {
+        k_tasks_from_screen<<<nblk(n_screen, 256), 256, 0, st>>>(d, ctx->flag8.as<uint8_t>(), ctx->pos.as<i64>(), n_screen,
+                                                               ctx->task_veh[cur].as<int>(), ctx->task_base[cur].as<int>(),
+                                                               ctx->task_q[cur].as<int>());
+        ctx->n_launches++;
+    }
+    i64 total_tasks = 0, total_sches = 0;
+    int levels_done = 0;
+    bool level_overflow = false;
+
+    // ---- levels 1..cap+4 --------------------------------------------------------------------------
+    for (int k = 1; k <= max_level && n_tasks > 0; k++) {
+        const int nt = (int)n_tasks;
+        total_tasks += nt;
+        int* tv = ctx->task_veh[cur].as<int>(); int* tb = ctx->task_base[cur].as<int>(); int* tq = ctx->task_q[cur].as<int>();
+        CK(ctx->task_nfeas.ensure(4 * (size_t)nt)); CK(ctx->task_cost.ensure(8 * (size_t)nt));
+        CK(ctx->words.ensure(4 * (size_t)nt)); CK(ctx->flag8.ensure((size_t)nt));
+        CK(ctx->pos.ensure(8 * (size_t)(nt + 2))); CK(ctx->pos2.ensure(8 * (size_t)(nt + 2)));
+        const Level& prev = ls.lv[k - 1];
+        Level curlv; memset(&curlv, 0, sizeof curlv);
+        const int eval_blocks = std::min(nblk(nt, WARPS_PER_BLOCK), ctx->n_sm * 8);
+        CK(cudaEventRecord(get_event(ctx, n_ev++), st));
+        k_eval<TT, 0><<<eval_blocks, WARPS_PER_BLOCK * 32, 0, st>>>(d, tt, prev, len0, nt, tv, tb, tq, ctx->task_nfeas.as<int>(),
+                                                                   ctx->task_cost.as<double>(), nullptr, curlv, dstats);
+        CK(cudaEventRecord(get_event(ctx, n_ev++), st));
+        k_task_flags<<<nblk(nt, 256), 256, 0, st>>>(nt, ctx->task_nfeas.as<int>(), tv, len0, k, ctx->flag8.as<uint8_t>(),
+                                                  ctx->words.as<int>(), dstats);
+        ctx->n_launches += 2;
+        i64 n_trips = 0, n_words = 0;
+        CKR(scan_excl<uint8_t>(ctx, ctx->flag8.as<uint8_t>(), nt, ctx->pos.as<i64>(), nullptr));
+        CK(cudaMemcpyAsync(&n_trips, ctx->total.p, 8, cudaMemcpyDeviceToHost, st));
+        CKR(scan_excl<int>(ctx, ctx->words.as<int>(), nt, ctx->pos2.as<i64>(), &n_words));   // synchronises both copies
+        CKR(alloc_level(ctx, k, (int)n_trips, n_words, V, &curlv));
+        levels_done = k;
+        total_sches += n_words;  // converted to schedules below via stats
+        k_compact_trips<<<nblk(nt, 256), 256, 0, st>>>(nt, ctx->task_nfeas.as<int>(), ctx->task_cost.as<double>(), tv, tb, tq,
+                                                     ctx->pos.as<i64>(), ctx->pos2.as<i64>(), prev, curlv);
+        k_veh_start<<<nblk(n_trips + 1, 256), 256, 0, st>>>((int)n_trips, V, curlv.trip_veh, curlv.veh_start);
+        ctx->n_launches += 2;
+        if (n_trips > 0) {
+            CK(cudaEventRecord(get_event(ctx, n_ev++), st));
+            k_eval<TT, 1><<<eval_blocks, WARPS_PER_BLOCK * 32, 0, st>>>(d, tt, prev, len0, nt, tv, tb, tq, ctx->task_nfeas.as<int>(),
+                                                                       ctx->task_cost.as<double>(), ctx->pos.as<i64>(), curlv, dstats);
+            CK(cudaEventRecord(get_event(ctx, n_ev++), st));
+            ctx->n_launches++;
+        }
+        ls.lv[k] = curlv; ls.n = k + 1;
+        n_tasks = 0;
+        if (n_trips == 0) break;
+        if (k == max_level) { if (mode != AMOD_MODE_SBA) level_overflow = true; break; }
+        if (k + 1 > AMOD_MAX_TRIP) return ctx->fail(AMOD_E_LIMIT, "trip size limit");
+        // ---- candidates of size k+1 -----------------------------------------------------------------
+        TripHash th; th.slots = nullptr; th.mask = 0;
+        if (k >= 2) {
+            unsigned sz = 64; while (sz < 2u * (unsigned)n_trips + 2u) sz <<= 1;
+            CK(ctx->hash.ensure(4 * (size_t)sz));
+            CK(cudaMemsetAsync(ctx->hash.p, 0xff, 4 * (size_t)sz, st));
+            th.slots = ctx->hash.as<int>(); th.mask = sz - 1;
+            k_hash_build<<<nblk(n_trips, 256), 256, 0, st>>>(curlv, th);
+            ctx->n_launches++;
+        }
+        CK(ctx->row_cnt.ensure(4 * (size_t)n_trips)); CK(ctx->row_off.ensure(8 * (size_t)(n_trips + 2)));
+        k_gen<0><<<nblk(n_trips, WARPS_PER_BLOCK), WARPS_PER_BLOCK * 32, 0, st>>>(ls.lv[1], curlv, th, ctx->row_cnt.as<int>(), nullptr,
+                                                                                nullptr, nullptr, nullptr);
+        ctx->n_launches++;
+        i64 n_next = 0;
+        CKR(scan_excl<int>(ctx, ctx->row_cnt.as<int>(), n_trips, ctx->row_off.as<i64>(), &n_next));
+        if (n_next > 0x7fffffff) return ctx->fail(AMOD_E_LIMIT, "too many size-%d candidates", k + 1);
+        if (n_next > 0) {
+            size_t b = 4 * (size_t)n_next;
+            CK(ctx->tmp_j.ensure(b)); CK(ctx->tmp_q.ensure(b)); CK(ctx->tmp_row.ensure(b));
+            CKR(ensure_tasks(cur ^ 1, n_next));
+            k_gen<1><<<nblk(n_trips, WARPS_PER_BLOCK), WARPS_PER_BLOCK * 32, 0, st>>>(ls.lv[1], curlv, th, nullptr, ctx->row_off.as<i64>(),
+                                                                                    ctx->tmp_j.as<int>(), ctx->tmp_q.as<int>(),
+                                                                                    ctx->tmp_row.as<int>());
+            k_gen_rank<<<nblk(n_next, 256), 256, 0, st>>>(n_next, ctx->row_off.as<i64>(), ctx->tmp_j.as<int>(), ctx->tmp_q.as<int>(),
+                                                        ctx->tmp_row.as<int>(), curlv.trip_veh, k == 1 ? 1 : 0,
+                                                        ctx->task_veh[cur ^ 1].as<int>(), ctx->task_base[cur ^ 1].as<int>(),
+                                                        ctx->task_q[cur ^ 1].as<int>());
+            ctx->n_launches += 2;
+            cur ^= 1;
+        }
+        n_tasks = n_next;
+    }
+
+    // ---- pool assembly ------------------------------------------------------------------------------
+    i64 P = 0;
+    i64 sba_base = 0;
+    CK(ctx->veh_off.ensure(8 * (size_t)(V + 2)));
+    if (mode == AMOD_MODE_SBA) {
+        sba_base = ls.n > 1 ? ls.lv[1].n_trips : 0;
+        P = sba_base + V;
+    } else {
+        CK(ctx->veh_cnt.ensure(4 * (size_t)(V + 1)));
+        if (V > 0) { k_pool_veh_count<<<nblk(V, 256), 256, 0, st>>>(V, mode, ls, ctx->veh_cnt.as<int>()); ctx->n_launches++; }
+        CKR(scan_excl<int>(ctx, ctx->veh_cnt.as<int>(), V, ctx->veh_off.as<i64>(), &P));
+    }
+    {
+        size_t n = (size_t)std::max(P, (i64)1);
+        CK(ctx->ent_veh.ensure(4 * n)); CK(ctx->ent_kind.ensure(4 * n)); CK(ctx->ent_nfeas.ensure(4 * n)); CK(ctx->ent_tlen.ensure(4 * n));
+        CK(ctx->ent_slen.ensure(4 * n)); CK(ctx->ent_src.ensure(4 * n)); CK(ctx->ent_trip.ensure(4 * n)); CK(ctx->ent_cost.ensure(8 * n));
+        CK(ctx->ent_delay.ensure(8 * n)); CK(ctx->trip_off.ensure(8 * (n + 1))); CK(ctx->sche_off.ensure(8 * (n + 1)));
+    }
+    i64 NT = 0, NS = 0;
+    if (P > 0) {
+        if (V > 0) {
+            k_pool_meta_veh<<<nblk(V, 256), 256, 0, st>>>(d, ls, len0, ctx->veh_off.as<i64>(), sba_base, ctx->ent_veh.as<int>(),
+                                                        ctx->ent_kind.as<int>(), ctx->ent_nfeas.as<int>(), ctx->ent_tlen.as<int>(),
+                                                        ctx->ent_slen.as<int>(), ctx->ent_src.as<int>(), ctx->ent_trip.as<int>(), dstats);
+            ctx->n_launches++;
+        }
+        for (int k = 1; k < ls.n; k++) {
+            if (ls.lv[k].n_trips == 0) continue;
+            k_pool_meta_level<<<nblk(ls.lv[k].n_trips, 256), 256, 0, st>>>(d, ls, k, len0, ctx->veh_off.as<i64>(), ctx->ent_veh.as<int>(),
+                                                                         ctx->ent_kind.as<int>(), ctx->ent_nfeas.as<int>(),
+                                                                         ctx->ent_tlen.as<int>(), ctx->ent_slen.as<int>(),
+                                                                         ctx->ent_src.as<int>(), ctx->ent_trip.as<int>());
+            ctx->n_launches++;
+        }
+        CKR(scan_excl<int>(ctx, ctx->ent_tlen.as<int>(), P, ctx->trip_off.as<i64>(), nullptr));
+        CK(cudaMemcpyAsync(&NT, ctx->total.p, 8, cudaMemcpyDeviceToHost, st));
+        CKR(scan_excl<int>(ctx, ctx->ent_slen.as<int>(), P, ctx->sche_off.as<i64>(), &NS));
+        CK(ctx->trip_req.ensure(4 * (size_t)std::max(NT, (i64)1))); CK(ctx->sche_code.ensure(4 * (size_t)std::max(NS, (i64)1)));
+        k_pool_payload<TT><<<nblk(P, 128), 128, 0, st>>>(d, tt, ls, P, ctx->ent_veh.as<int>(), ctx->ent_src.as<int>(), ctx->ent_trip.as<int>(),
+                                                       ctx->trip_off.as<i64>(), ctx->sche_off.as<i64>(), ctx->trip_req.as<int>(),
+                                                       ctx->sche_code.as<int>(), ctx->ent_cost.as<double>(), ctx->ent_delay.as<double>());
+        ctx->n_launches++;
+    } else {
+        CK(cudaMemsetAsync(ctx->trip_off.p, 0, 8, st)); CK(cudaMemsetAsync(ctx->sche_off.p, 0, 8, st));
+    }
+    CK(cudaEventRecord(ctx->ev1, st));
+    Stats hs;
+    CK(cudaMemcpyAsync(&hs, dstats, sizeof hs, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    CK(cudaGetLastError());
+    if (hs.flags & 1ull) return ctx->fail(AMOD_E_LIMIT, "a vehicle schedule exceeds the compiled stop/capacity limits");
+    ctx->pool_entries = P; ctx->pool_trip_reqs = NT; ctx->pool_stops = NS;
+    ctx->pool_valid = true;
+    if (out_stats) {
+        memset(out_stats, 0, sizeof *out_stats);
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1);
+        out_stats->ms_build = ms;
+        double me = 0.0;
+        for (size_t i = 0; i + 1 < n_ev; i += 2) { float x = 0.f; cudaEventElapsedTime(&x, ctx->ev_pool[i], ctx->ev_pool[i + 1]); me += x; }
+        out_stats->ms_eval = me;
+        out_stats->n_eval_launches = (int)(n_ev / 2);
+        out_stats->n_screens = n_screen;
+        out_stats->n_evals = (int64_t)hs.n_evals;
+        // lookups as the reference would do them: evaluations + one per screen + the cost walk of the
+        // basic/current pairs + the delay walk of every pool entry
+        out_stats->n_lookups = (int64_t)hs.n_lookups + n_screen + NS;
+        out_stats->n_entries = P;
+        out_stats->n_tasks = total_tasks;
+        out_stats->n_levels = levels_done;
+        out_stats->n_kernel_launches = ctx->n_launches;
+        out_stats->n_sches_stored = (int64_t)hs.n_sches;
+    }
+    (void)total_sches;
+    if (level_overflow)
+        return ctx->fail(AMOD_E_LEVELS, "a feasible trip of size cap+4=%d exists; the reference raises IndexError here "
+                                        "(dispatch_osp.py:8,226)", max_level);
+    return AMOD_OK;
+}
+
+extern "C" int amod_osp_build(amod_ctx* ctx, const amod_epoch* ep, int loc, amod_stats* stats) {
+    if (!ctx || !ep) return AMOD_E_BADARG;
+    if (ep->mode != AMOD_MODE_OSP && ep->mode != AMOD_MODE_OSP_NR) return ctx->fail(AMOD_E_BADARG, "amod_osp_build: mode must be OSP or OSP_NR");
+    return dispatch_tt(ctx, [&](auto tt) { return build_impl(ctx, ep, loc, stats, tt); });
+}
+
+extern "C" int amod_sba_build(amod_ctx* ctx, const amod_epoch* ep, int loc, amod_stats* stats) {
+    if (!ctx || !ep) return AMOD_E_BADARG;
+    if (ep->mode != AMOD_MODE_SBA) return ctx->fail(AMOD_E_BADARG, "amod_sba_build: mode must be SBA");
+    return dispatch_tt(ctx, [&](auto tt) { return build_impl(ctx, ep, loc, stats, tt); });
+}
+
+extern "C" int amod_pool_view(amod_ctx* ctx, amod_pool* v) {
+    if (!ctx || !v) return AMOD_E_BADARG;
+    if (!ctx->pool_valid) return ctx->fail(AMOD_E_BADARG, "no pool has been built on this context");
+    v->n_entries = v->cap_entries = ctx->pool_entries;
+    v->n_trip_reqs = v->cap_trip_reqs = ctx->pool_trip_reqs;
+    v->n_stops = v->cap_stops = ctx->pool_stops;
+    v->ent_veh = ctx->ent_veh.as<int32_t>(); v->ent_kind = ctx->ent_kind.as<int32_t>();
+    v->ent_trip_off = (int64_t*)ctx->trip_off.p; v->ent_sche_off = (int64_t*)ctx->sche_off.p;
+    v->ent_cost = ctx->ent_cost.as<double>(); v->ent_delay = ctx->ent_delay.as<double>(); v->ent_nfeas = ctx->ent_nfeas.as<int32_t>();
+    v->trip_req = ctx->trip_req.as<int32_t>(); v->sche_code = ctx->sche_code.as<int32_t>();
+    return AMOD_OK;
+}
+
+extern "C" int amod_pool_fetch(amod_ctx* ctx, amod_pool* o, int loc) {
+    if (!ctx || !o) return AMOD_E_BADARG;
+    if (!ctx->pool_valid) return ctx->fail(AMOD_E_BADARG, "no pool has been built on this context");
+    const i64 P = ctx->pool_entries, NT = ctx->pool_trip_reqs, NS = ctx->pool_stops;
+    o->n_entries = P; o->n_trip_reqs = NT; o->n_stops = NS;
+    if (o->cap_entries < P || o->cap_trip_reqs < NT || o->cap_stops < NS)
+        return ctx->fail(AMOD_E_CAPACITY, "pool buffers too small: need %lld entries, %lld trip requests, %lld stops", P, NT, NS);
+    CK(cudaSetDevice(ctx->device));
+    cudaMemcpyKind kind = loc == AMOD_LOC_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost;
+    cudaStream_t st = ctx->stream;
+    if (P > 0) {
+        CK(cudaMemcpyAsync(o->ent_veh, ctx->ent_veh.p, 4 * (size_t)P, kind, st));
+        CK(cudaMemcpyAsync(o->ent_kind, ctx->ent_kind.p, 4 * (size_t)P, kind, st));
+        CK(cudaMemcpyAsync(o->ent_nfeas, ctx->ent_nfeas.p, 4 * (size_t)P, kind, st));
+        CK(cudaMemcpyAsync(o->ent_cost, ctx->ent_cost.p, 8 * (size_t)P, kind, st));
+        CK(cudaMemcpyAsync(o->ent_delay, ctx->ent_delay.p, 8 * (size_t)P, kind, st));
+    }
+    CK(cudaMemcpyAsync(o->ent_trip_off, ctx->trip_off.p, 8 * (size_t)(P + 1), kind, st));
+    CK(cudaMemcpyAsync(o->ent_sche_off, ctx->sche_off.p, 8 * (size_t)(P + 1), kind, st));
+    if (NT > 0) CK(cudaMemcpyAsync(o->trip_req, ctx->trip_req.p, 4 * (size_t)NT, kind, st));
+    if (NS > 0) CK(cudaMemcpyAsync(o->sche_code, ctx->sche_code.p, 4 * (size_t)NS, kind, st));
+    CK(cudaStreamSynchronize(st));
+    return AMOD_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// NPO
+// ------------------------------------------------------------------------------------------------
+template <typename TT>
+static int npo_impl(amod_ctx* ctx, const int32_t* idle_nid, int n_idle, const int32_t* pend_onid, int n_pend, int loc,
+                    int32_t* out_idle, int32_t* out_pend, double* out_dt, int32_t* n_out, int32_t* n_rounds, Table<TT> tt) {
+    cudaStream_t st = ctx->stream;
+    CK(cudaSetDevice(ctx->device));
+    *n_out = 0;
+    if (n_rounds) *n_rounds = 0;
+    const int target = std::min(n_idle, n_pend);
+    if (target == 0) return AMOD_OK;
+    const int* d_idle = idle_nid; const int* d_pend = pend_onid;
+    if (loc == AMOD_LOC_HOST) {
+        for (int i = 0; i < n_idle; i++) if (idle_nid[i] < 1 || idle_nid[i] > ctx->n_nodes) return ctx->fail(AMOD_E_BADARG, "idle node out of range");
+        for (int i = 0; i < n_pend; i++) if (pend_onid[i] < 1 || pend_onid[i] > ctx->n_nodes) return ctx->fail(AMOD_E_BADARG, "pending node out of range");
+        CK(ctx->npo_in.ensure(4 * (size_t)(n_idle + n_pend)));
+        CK(cudaMemcpyAsync(ctx->npo_in.p, idle_nid, 4 * (size_t)n_idle, cudaMemcpyHostToDevice, st));
+        CK(cudaMemcpyAsync(ctx->npo_in.as<int>() + n_idle, pend_onid, 4 * (size_t)n_pend, cudaMemcpyHostToDevice, st));
+        d_idle = ctx->npo_in.as<int>(); d_pend = ctx->npo_in.as<int>() + n_idle;
+    }
+    CK(ctx->npo_vm.ensure(4 * (size_t)n_idle)); CK(ctx->npo_rm.ensure(4 * (size_t)n_pend)); CK(ctx->npo_rb.ensure(4 * (size_t)n_pend));
+    CK(ctx->npo_vb.ensure(4 * (size_t)n_idle)); CK(ctx->npo_rdt.ensure(8 * (size_t)n_pend)); CK(ctx->npo_mdt.ensure(8 * (size_t)n_pend));
+    CK(ctx->npo_cnt.ensure(4));
+    CK(cudaMemsetAsync(ctx->npo_vm.p, 0xff, 4 * (size_t)n_idle, st));
+    CK(cudaMemsetAsync(ctx->npo_rm.p, 0xff, 4 * (size_t)n_pend, st));
+    CK(cudaMemsetAsync(ctx->npo_cnt.p, 0, 4, st));
+    int matched = 0, rounds = 0;
+    while (matched < target) {
+        k_npo_best<TT><<<n_pend, NPO_THREADS, 0, st>>>(tt, d_idle, n_idle, d_pend, n_pend, ctx->npo_vm.as<int>(), ctx->npo_rm.as<int>(), 0,
+                                                      ctx->npo_rb.as<int>(), ctx->npo_rdt.as<double>());
+        k_npo_best<TT><<<n_idle, NPO_THREADS, 0, st>>>(tt, d_idle, n_idle, d_pend, n_pend, ctx->npo_vm.as<int>(), ctx->npo_rm.as<int>(), 1,
+                                                      ctx->npo_vb.as<int>(), nullptr);
+        k_npo_commit<<<nblk(n_pend, 256), 256, 0, st>>>(n_pend, ctx->npo_rb.as<int>(), ctx->npo_rdt.as<double>(), ctx->npo_vb.as<int>(),
+                                                      ctx->npo_vm.as<int>(), ctx->npo_rm.as<int>(), ctx->npo_mdt.as<double>(),
+                                                      ctx->npo_cnt.as<int>());
+        rounds++;
+        int prev = matched;
+        CK(cudaMemcpyAsync(&matched, ctx->npo_cnt.p, 4, cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        if (matched == prev) return ctx->fail(AMOD_E_CUDA, "npo: no progress in round %d", rounds);
+    }
+    std::vector<int> rm(n_pend);
+    std::vector<double> mdt(n_pend);
+    CK(cudaMemcpyAsync(rm.data(), ctx->npo_rm.p, 4 * (size_t)n_pend, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(mdt.data(), ctx->npo_mdt.p, 8 * (size_t)n_pend, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    // selection order of the reference: ascending (dt, request rank, vehicle rank)
+    std::vector<int> order;
+    for (int r = 0; r < n_pend; r++) if (rm[r] >= 0) order.push_back(r);
+    std::sort(order.begin(), order.end(), [&](int a, int b) { return mdt[a] < mdt[b] || (mdt[a] == mdt[b] && a < b); });
+    for (size_t i = 0; i < order.size(); i++) { out_pend[i] = order[i]; out_idle[i] = rm[order[i]]; out_dt[i] = mdt[order[i]]; }
+    *n_out = (int)order.size();
+    if (n_rounds) *n_rounds = rounds;
+    return AMOD_OK;
+}
+
+extern "C" int amod_npo_match(amod_ctx* ctx, const int32_t* idle_nid, int32_t n_idle, const int32_t* pend_onid, int32_t n_pend,
+                              int loc, int32_t* out_idle_idx, int32_t* out_pend_idx, double* out_dt, int32_t* n_out, int32_t* n_rounds) {
+    if (!ctx || !n_out || n_idle < 0 || n_pend < 0) return AMOD_E_BADARG;
+    return dispatch_tt(ctx, [&](auto tt) {
+        return npo_impl(ctx, idle_nid, n_idle, pend_onid, n_pend, loc, out_idle_idx, out_pend_idx, out_dt, n_out, n_rounds, tt);
+    });
+}
+
+extern "C" int amod_gather_bench(amod_ctx* ctx, const int32_t* o_dev, const int32_t* d_dev, float* out_dev, int64_t n, int iters,
+                                 double* ms) {
+    if (!ctx || !ms) return AMOD_E_BADARG;
+    return dispatch_tt(ctx, [&](auto tt) -> int {
+        cudaStream_t st = ctx->stream;
+        CK(cudaSetDevice(ctx->device));
+        using T = decltype(tt);
+        auto launch = [&]() {
+            if constexpr (std::is_same<T, Table<double>>::value) k_gather_bench<double><<<ctx->n_sm * 16, 256, 0, st>>>(tt, o_dev, d_dev, out_dev, n);
+            else k_gather_bench<float><<<ctx->n_sm * 16, 256, 0, st>>>(tt, o_dev, d_dev, out_dev, n);
+        };
+        launch();
+        CK(cudaEventRecord(ctx->ev0, st));
+        for (int i = 0; i < iters; i++) launch();
+        CK(cudaEventRecord(ctx->ev1, st));
+        CK(cudaStreamSynchronize(st));
+        float f = 0.f;
+        CK(cudaEventElapsedTime(&f, ctx->ev0, ctx->ev1));
+        *ms = f / std::max(iters, 1);
+        return AMOD_OK;
+    });
+}

@@ -1,0 +1,89 @@
+// common.cuh — shared device structs and helpers for the OSP pool builder (sm_100a).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/amod_b200.h"
+
+#define MAXS AMOD_MAX_STOPS
+#define WARPS_PER_BLOCK 8
+#define FULL 0xffffffffu
+
+typedef long long i64;
+typedef int16_t code_t;  // stop code: 2*req + (0 pick | 1 drop), -1 = rebalancing stop
+
+// Device view of one epoch (include/amod_b200.h: struct amod_epoch).
+struct DEpoch {
+    int n_veh, n_req, n_search, cap, mode;
+    double T;
+    const int* veh_nid; const double* veh_t; const int* veh_load; const int* veh_status;
+    const int* veh_sche_off; const int* sche_code; const uint8_t* sche_onboard;
+    const int* reb_node; const double* reb_ddl;
+    const int* onid; const int* dnid; const double* clp; const double* cld; const double* tr; const double* ts;
+    const int* search;
+};
+
+// Travel-time table mean_travel_time_table[o-1][d-1] (route_functions.py:22-25), kept L2-resident.
+template <typename TT>
+struct Table {
+    const TT* p;
+    int n;
+    __device__ __forceinline__ double operator()(int o, int d) const {
+        return (double)__ldg(p + (size_t)(o - 1) * (size_t)n + (size_t)(d - 1));
+    }
+};
+
+// One trip-size level of the per-vehicle feasible-trip table (FEASIBLE_TRIP_TABLE[veh][k-1],
+// dispatch_osp.py:8) flattened over all vehicles.  Level 0 holds the basic schedules.
+// The feasible schedules of trip t are nfeas[t] rows of `len` codes starting at sch[sch_off[t]];
+// the reference's list order (records newest-first, then the rest; scheduling.py:31-36) is
+// memory order rotated by rot[t]:  logical p -> row (p + rot) % nfeas.
+struct Level {
+    int k;
+    int n_trips;
+    int* trip_veh;
+    int* trip_req;     // [n_trips * k] ascending request indices
+    i64* sch_off;
+    int* nfeas;
+    int* rot;
+    double* cost;      // min cost (scheduling.py:33)
+    code_t* sch;
+    int* veh_start;    // [n_veh+1] trips of vehicle v are [veh_start[v], veh_start[v+1])  (OSP modes)
+};
+
+struct Stats {            // device counters
+    unsigned long long n_screens, n_evals, n_lookups, n_sches, n_tasks, flags;
+};
+
+__device__ __forceinline__ void stop_info(const DEpoch& ep, int v, int code, int& node, double& ddl, int& pod) {
+    if (code < 0) { node = ep.reb_node[v]; ddl = ep.reb_ddl[v]; pod = 0; return; }
+    int r = code >> 1;
+    if (code & 1) { node = ep.dnid[r]; ddl = ep.cld[r]; pod = -1; }
+    else          { node = ep.onid[r]; ddl = ep.clp[r]; pod = 1; }
+}
+
+__device__ __forceinline__ double warp_min(double x) {
+    for (int o = 16; o; o >>= 1) x = fmin(x, __shfl_xor_sync(FULL, x, o));
+    return x;
+}
+__device__ __forceinline__ unsigned long long warp_sum(unsigned long long x) {
+    for (int o = 16; o; o >>= 1) x += __shfl_xor_sync(FULL, x, o);
+    return x;
+}
+__device__ __forceinline__ int warp_sum(int x) {
+    for (int o = 16; o; o >>= 1) x += __shfl_xor_sync(FULL, x, o);
+    return x;
+}
+// exclusive prefix over lanes
+__device__ __forceinline__ int warp_excl_sum(int x, int lane) {
+    int y = x;
+    for (int o = 1; o < 32; o <<= 1) { int t = __shfl_up_sync(FULL, y, o); if (lane >= o) y += t; }
+    return y - x;
+}
+__device__ __forceinline__ double warp_excl_min(double x, int lane) {  // +inf for lane 0
+    double y = x;
+    for (int o = 1; o < 32; o <<= 1) { double t = __shfl_up_sync(FULL, y, o); if (lane >= o) y = fmin(y, t); }
+    double e = __shfl_up_sync(FULL, y, 1);
+    return lane == 0 ? __longlong_as_double(0x7ff0000000000000LL) : e;
+}
+#define DINF __longlong_as_double(0x7ff0000000000000LL)

@@ -1,0 +1,71 @@
+"""Multi-GPU: vehicles shard across ranks (each vehicle's trip table depends only on that
+vehicle, the shared request list and the read-only table: dispatch_osp.py:107-111), every rank
+builds its slice of the pool, and one all-gather assembles the vehicle-major pool for the
+unchanged assigner.  One process per GPU, torch.distributed for the plumbing."""
+from __future__ import annotations
+
+import numpy as np
+
+from .marshal import Pool, concat_pools
+
+
+def merge_vehicle_major(parts: list[tuple[Pool, np.ndarray]], n_veh: int) -> Pool:
+    """parts[r] = (pool of rank r, global vehicle index of each of its local vehicles).
+    Rank pools are vehicle-major over their own vehicles; the merged pool is vehicle-major over
+    the whole fleet (the reference's order, dispatch_osp.py:107)."""
+    pools = []
+    for pool, sel in parts:
+        p = Pool(stats=pool.stats, **{f: getattr(pool, f) for f in Pool.FIELDS})
+        p.ent_veh = np.asarray(sel, dtype=np.int32)[pool.ent_veh] if pool.n_entries else pool.ent_veh
+        pools.append(p)
+    cat = concat_pools(pools)
+    order = np.argsort(cat.ent_veh, kind="stable")
+    return cat.take(order)
+
+
+def merge_sba(parts: list[tuple[Pool, np.ndarray]], n_veh: int) -> Pool:
+    """SBA order is request-major then one empty pair per vehicle (dispatch_sba.py:56-69):
+    pairs sort by (request position, vehicle), the empty pairs by vehicle."""
+    pools = []
+    for pool, sel in parts:
+        p = Pool(stats=pool.stats, **{f: getattr(pool, f) for f in Pool.FIELDS})
+        p.ent_veh = np.asarray(sel, dtype=np.int32)[pool.ent_veh] if pool.n_entries else pool.ent_veh
+        pools.append(p)
+    cat = concat_pools(pools)
+    is_empty = (cat.ent_trip_off[1:] - cat.ent_trip_off[:-1]) == 0
+    req = np.where(is_empty, np.iinfo(np.int32).max, cat.trip_req[np.minimum(cat.ent_trip_off[:-1], max(cat.trip_req.size - 1, 0))]
+                   if cat.trip_req.size else 0)
+    order = np.lexsort((cat.ent_veh, req))
+    return cat.take(order)
+
+
+def allgather_pool(local: Pool, sel: np.ndarray, n_veh: int, mode_sba: bool = False, device=None) -> Pool:
+    """All-gather the rank-local pools (torch.distributed; NCCL over NVLink when `device` is a
+    CUDA device, gloo on CPU) and return the full vehicle-major pool on every rank."""
+    import torch
+    import torch.distributed as dist
+
+    world = dist.get_world_size()
+    dev = device if device is not None else torch.device("cpu")
+    sizes = torch.tensor([local.n_entries, local.trip_req.size, local.sche_code.size, len(sel)], dtype=torch.int64, device=dev)
+    all_sizes = [torch.zeros_like(sizes) for _ in range(world)]
+    dist.all_gather(all_sizes, sizes)
+    all_sizes = torch.stack(all_sizes).cpu().numpy()
+    mx = all_sizes.max(axis=0)
+
+    def gather(arr: np.ndarray, n_max: int, col: int, extra: int = 0):
+        n_max = int(n_max) + extra
+        buf = torch.zeros(max(n_max, 1), dtype=torch.from_numpy(np.zeros(1, arr.dtype)).dtype, device=dev)
+        if arr.size:
+            buf[:arr.size] = torch.from_numpy(np.ascontiguousarray(arr)).to(dev)
+        outs = [torch.zeros_like(buf) for _ in range(world)]
+        dist.all_gather(outs, buf)
+        return [o.cpu().numpy()[:int(all_sizes[r, col]) + extra] for r, o in enumerate(outs)]
+
+    fields = {}
+    for f, col, extra in (("ent_veh", 0, 0), ("ent_kind", 0, 0), ("ent_cost", 0, 0), ("ent_delay", 0, 0), ("ent_nfeas", 0, 0),
+                          ("ent_trip_off", 0, 1), ("ent_sche_off", 0, 1), ("trip_req", 1, 0), ("sche_code", 2, 0)):
+        fields[f] = gather(getattr(local, f), mx[col], col, extra)
+    sels = gather(np.asarray(sel, dtype=np.int64), mx[3], 3)
+    parts = [(Pool(**{f: fields[f][r] for f in Pool.FIELDS}), sels[r]) for r in range(world)]
+    return (merge_sba if mode_sba else merge_vehicle_major)(parts, n_veh)

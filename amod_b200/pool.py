@@ -1,0 +1,172 @@
+"""Host-side mirror of the reference's three seam functions on top of the
+C-ABI (include/amod_b200.h).  Same names, argument meaning and return records as
+
+  B1  dispatch_osp.compute_candidate_veh_trip_pairs   (dispatch_osp.py:94-129)
+  B2  dispatch_sba.compute_candidate_veh_req_pairs    (dispatch_sba.py:44-74)
+  B3  rebalancing_npo.reposition_idle_vehicles_to_nearest_pending_orders (rebalancing_npo.py:8-62)
+
+so a maintainer can rebind the module globals (amod_b200/install.py).  All compute is CUDA;
+there is no CPU path here — a missing library or device raises RuntimeError.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import capi, marshal
+from .marshal import MODE_OSP, MODE_OSP_NR, MODE_SBA, Epoch, Pool
+
+
+class AmodError(RuntimeError):
+    def __init__(self, code: int, msg: str):
+        super().__init__(f"amod_b200 error {code}: {msg}")
+        self.code = code
+
+
+class PoolBuilder:
+    """One GPU context holding the travel-time table (route_functions.py:14-15) L2-resident."""
+
+    def __init__(self, tt: np.ndarray, device: int = 0, lib_path: str | None = None):
+        self.lib = capi.load_library(lib_path)
+        tt = np.ascontiguousarray(tt)
+        if tt.dtype not in (np.float32, np.float64) or tt.ndim != 2 or tt.shape[0] != tt.shape[1]:
+            raise ValueError("travel-time table must be a square float32/float64 array")
+        self.n_nodes = tt.shape[0]
+        self.tt_dtype = capi.TT_F64 if tt.dtype == np.float64 else capi.TT_F32
+        self.device = device
+        h = C.c_void_p()
+        rc = self.lib.amod_create(C.byref(h), device, self.n_nodes, tt.ctypes.data, self.tt_dtype)
+        if rc != capi.OK:
+            raise AmodError(rc, self.lib.amod_last_error(None).decode())
+        self.h = h
+        self.last_stats: dict = {}
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.amod_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc: int):
+        if rc == capi.E_LEVELS:
+            # same exception type the reference raises at dispatch_osp.py:226
+            raise IndexError(self.lib.amod_last_error(self.h).decode())
+        if rc != capi.OK:
+            raise AmodError(rc, self.lib.amod_last_error(self.h).decode())
+
+    def set_stream(self, cuda_stream: int):
+        self._check(self.lib.amod_set_stream(self.h, C.c_void_p(cuda_stream)))
+
+    # ---- array level -----------------------------------------------------------------------
+    def build(self, ep, loc: int = capi.LOC_HOST, ptr_of=None) -> dict:
+        """Build the pool for `ep` (Epoch of numpy arrays, or device tensors with `ptr_of`);
+        the pool stays on the device.  Returns the stats dict."""
+        s = capi.epoch_struct(ep, ptr_of)
+        st = capi.AmodStats()
+        fn = self.lib.amod_sba_build if ep.mode == MODE_SBA else self.lib.amod_osp_build
+        rc = fn(self.h, C.byref(s), loc, C.byref(st))
+        self.last_stats = st.as_dict()
+        self._check(rc)
+        return self.last_stats
+
+    def pool_sizes(self):
+        v = capi.AmodPool()
+        self._check(self.lib.amod_pool_view(self.h, C.byref(v)))
+        return int(v.n_entries), int(v.n_trip_reqs), int(v.n_stops)
+
+    def pool_view(self) -> capi.AmodPool:
+        v = capi.AmodPool()
+        self._check(self.lib.amod_pool_view(self.h, C.byref(v)))
+        return v
+
+    def fetch(self) -> Pool:
+        """Copy the device pool into fresh numpy arrays."""
+        P, NT, NS = self.pool_sizes()
+        n = {"e": P, "e1": P + 1, "t": NT, "s": NS}
+        arrs = {name: np.empty(max(n[key], 1), dtype=dt) for name, dt, key in capi.POOL_FIELDS}
+        o = capi.AmodPool()
+        o.cap_entries, o.cap_trip_reqs, o.cap_stops = P, NT, NS
+        for name, _dt, _key in capi.POOL_FIELDS:
+            setattr(o, name, arrs[name].ctypes.data)
+        self._check(self.lib.amod_pool_fetch(self.h, C.byref(o), capi.LOC_HOST))
+        return Pool(stats=dict(self.last_stats), **{name: arrs[name][:n[key]] for name, _dt, key in capi.POOL_FIELDS})
+
+    def build_pool(self, ep: Epoch) -> Pool:
+        self.build(ep)
+        return self.fetch()
+
+    def npo_match(self, idle_nid, pend_onid):
+        idle_nid = np.ascontiguousarray(idle_nid, dtype=np.int32)
+        pend_onid = np.ascontiguousarray(pend_onid, dtype=np.int32)
+        m = min(idle_nid.size, pend_onid.size)
+        oi, op, od = np.zeros(max(m, 1), np.int32), np.zeros(max(m, 1), np.int32), np.zeros(max(m, 1), np.float64)
+        n_out, n_rounds = C.c_int32(0), C.c_int32(0)
+        self._check(self.lib.amod_npo_match(self.h, idle_nid.ctypes.data, idle_nid.size, pend_onid.ctypes.data,
+                                            pend_onid.size, capi.LOC_HOST, oi.ctypes.data, op.ctypes.data,
+                                            od.ctypes.data, C.byref(n_out), C.byref(n_rounds)))
+        self.last_npo_rounds = n_rounds.value
+        k = n_out.value
+        return oi[:k], op[:k], od[:k]
+
+    # ---- the reference's seams ---------------------------------------------------------------
+    def compute_candidate_veh_trip_pairs(self, new_received_rids, considered_rids, reqs, vehs, system_time_sec,
+                                         cutoff_time_for_a_size_k_trip_search_per_veh_sec, enable_reoptimization,
+                                         enable_fast_compute, capacity: int | None = None):
+        """B1.  The wall-clock cut-off argument is accepted and ignored: the GPU search is
+        exhaustive, i.e. the reference with the cut-off disabled (SURVEY.md hard part 4)."""
+        if enable_fast_compute:
+            raise NotImplementedError("enable_fast_compute is disabled in the reference (dispatch_osp.py:29)")
+        cap = capacity if capacity is not None else _capacity_of(vehs)
+        mode = MODE_OSP if enable_reoptimization else MODE_OSP_NR
+        ep, req_objs = marshal.marshal_epoch(reqs, vehs, considered_rids, system_time_sec, cap, mode)
+        pool = self.build_pool(ep)
+        return marshal.pool_to_records(pool, ep, vehs, req_objs)
+
+    def compute_candidate_veh_req_pairs(self, new_received_rids, reqs, vehs, system_time_sec,
+                                        capacity: int | None = None):
+        """B2."""
+        cap = capacity if capacity is not None else _capacity_of(vehs)
+        ep, req_objs = marshal.marshal_epoch(reqs, vehs, new_received_rids, system_time_sec, cap, MODE_SBA)
+        pool = self.build_pool(ep)
+        return marshal.pool_to_records(pool, ep, vehs, req_objs)
+
+    def reposition_idle_vehicles_to_nearest_pending_orders(self, reqs, vehs, system_time_sec, num_of_new_reqs,
+                                                           value_func, detour_sec: int = 240):
+        """B3: candidates, sort and greedy selection on the GPU; veh.build_route stays host
+        (rebalancing_npo.py:62)."""
+        pending = [r for r in reqs if _status_value(r.status) == 1]          # OrderStatus.PENDING (:13-16)
+        idle = [v for v in vehs if _status_value(v.status) == marshal.ST_IDLE]   # (:29-31)
+        if not pending or not idle:
+            return
+        oi, op, od = self.npo_match([v.nid for v in idle], [r.onid for r in pending])
+        tt_type = np.float64
+        for vi, ri, dt in zip(oi.tolist(), op.tolist(), od):
+            req = pending[ri]
+            idle[vi].build_route([(-1, 0, req.onid, system_time_sec + tt_type(dt) + detour_sec)])   # (:37,:62)
+
+
+def _status_value(s) -> int:
+    return int(getattr(s, "value", s))
+
+
+def _capacity_of(vehs) -> int:
+    # VEH_CAPACITY[0] (scheduling.py:76) equals every vehicle's K (platform.py:55)
+    return int(vehs[0].K)
+
+
+def score_vt_pairs_with_num_of_orders_and_sche_cost(veh_trip_pairs, reqs, system_time_sec):
+    """Drop-in for scheduling.py:140-161 when the pool came from PoolBuilder: pair[3] := delay
+    (computed on the GPU in the pool pass), pair[4] := len(trip).  Falls back to nothing: a
+    pool without device delays is an error."""
+    delays = getattr(veh_trip_pairs, "delays", None)
+    if delays is None or len(delays) != len(veh_trip_pairs):
+        raise RuntimeError("pool was not produced by amod_b200 (no device delays attached)")
+    for pair, d in zip(veh_trip_pairs, delays):
+        pair[3] = d
+        pair[4] = len(pair[1])

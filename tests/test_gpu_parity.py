@@ -1,0 +1,150 @@
+"""GPU parity (run on the B200 box): the CUDA pool, through the C-ABI, against
+ (a) the committed golden vectors produced by the unmodified reference, and
+ (b) the C oracle on larger seeded inputs.
+Bar: bit-exact entry set, order, trips, chosen schedules AND float64 costs/delays (rtol 0):
+the kernels accumulate in the reference's order, so no tolerance is needed (north_star allows 1e-6)."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN, golden_families, load_golden, table_from_spec
+from amod_b200 import marshal, synth
+from amod_b200.pool import PoolBuilder
+
+pytestmark = pytest.mark.gpu
+
+_builders = {}
+
+
+def builder_for(tt):
+    key = (tt.ctypes.data, tt.shape, tt.dtype.str)
+    if key not in _builders:
+        _builders[key] = (PoolBuilder(tt), tt)
+    return _builders[key][0]
+
+
+@pytest.mark.parametrize("family", golden_families(("rand_", "sim_")))
+def test_cuda_pool_matches_reference_golden(family):
+    import oracle
+    tt, cases = load_golden(family)
+    b = builder_for(tt)
+    for i, (ep, gold) in enumerate(cases):
+        got = b.build_pool(ep)
+        ok, why = marshal.pools_equal(got, gold, rtol=0.0, check_kind=True)
+        assert ok, f"{family} case {i}: {why}"
+        ref = (oracle.sba_build if ep.mode == marshal.MODE_SBA else oracle.osp_build)(ep, tt)
+        for key in ("n_evals", "n_lookups", "n_tasks", "n_sches_stored", "n_screens"):
+            assert got.stats[key] == ref.stats[key], (family, i, key, got.stats[key], ref.stats[key])
+
+
+def test_cuda_level_overflow_raises_indexerror_like_reference():
+    tt, cases = load_golden("levels")
+    b = builder_for(tt)
+    (ep_ok, gold_ok), (ep_bad, _none) = cases
+    ok, why = marshal.pools_equal(b.build_pool(ep_ok), gold_ok, check_kind=True)
+    assert ok, why
+    with pytest.raises(IndexError):
+        b.build_pool(ep_bad)
+
+
+def test_cuda_f32_and_f64_tables_agree_on_fp32_representable_data():
+    tt, cases = load_golden("rand_real32_osp_cap2")
+    assert tt.dtype == np.float32
+    b32, b64 = PoolBuilder(tt), PoolBuilder(tt.astype(np.float64))
+    for ep, gold in cases[:2]:
+        for b in (b32, b64):
+            ok, why = marshal.pools_equal(b.build_pool(ep), gold, check_kind=True)
+            assert ok, why
+
+
+@pytest.mark.parametrize("mode,cap,n_veh,n_pending,wait", [
+    (marshal.MODE_OSP, 4, 300, 120, 260), (marshal.MODE_OSP, 8, 120, 60, 200), (marshal.MODE_OSP_NR, 4, 300, 150, 300),
+    (marshal.MODE_SBA, 4, 800, 500, 420), (marshal.MODE_OSP, 1, 200, 100, 300)])
+def test_cuda_pool_matches_oracle_on_manhattan_grid(mode, cap, n_veh, n_pending, wait):
+    """Larger seeded epochs on the 4,091-node synthetic Manhattan table (fp32)."""
+    import oracle
+    tt = _grid()
+    b = builder_for(tt)
+    ep = synth.random_epoch(tt, n_veh=n_veh, n_pending=n_pending, cap=cap, mode=mode, seed=77 + cap, wait_sec=wait,
+                            near=True, T=5000)
+    ref = (oracle.sba_build if mode == marshal.MODE_SBA else oracle.osp_build)(ep, tt, n_threads=oracle.max_threads())
+    assert ref.error == 0
+    got = b.build_pool(ep)
+    ok, why = marshal.pools_equal(got, ref, rtol=0.0, check_kind=True)
+    assert ok, why
+    for key in ("n_evals", "n_lookups", "n_tasks", "n_sches_stored"):
+        assert got.stats[key] == ref.stats[key], (key, got.stats[key], ref.stats[key])
+    assert got.stats["n_evals"] > 1000
+
+
+_grid_tt = None
+
+
+def _grid():
+    global _grid_tt
+    if _grid_tt is None:
+        _grid_tt = synth.make_road_graph(seed=0).tt
+    return _grid_tt
+
+
+def test_cuda_empty_and_degenerate_inputs():
+    tt = synth.random_table(12, 3, "ties")
+    b = builder_for(tt)
+    import oracle
+    for mode in (marshal.MODE_OSP, marshal.MODE_OSP_NR, marshal.MODE_SBA):
+        # no requests at all
+        ep = synth.random_epoch(tt, n_veh=9, n_pending=0, cap=3, mode=mode, seed=5, max_picking=0 if mode != marshal.MODE_OSP else 1)
+        ref = (oracle.sba_build if mode == marshal.MODE_SBA else oracle.osp_build)(ep, tt)
+        ok, why = marshal.pools_equal(b.build_pool(ep), ref, check_kind=True)
+        assert ok, (mode, why)
+    # no vehicles
+    ep = synth.random_epoch(tt, n_veh=4, n_pending=5, cap=3, mode=marshal.MODE_OSP, seed=6)
+    sub, _sel = ep.shard(7, 8)          # rank 7 of 8 gets no vehicle
+    assert sub.n_veh == 0
+    assert b.build_pool(sub).n_entries == 0
+
+
+@pytest.mark.parametrize("family", golden_families(("npo_",)))
+def test_cuda_npo_matches_reference(family):
+    z = np.load(os.path.join(GOLDEN, family + ".npz"))
+    tt = table_from_spec(json.loads(str(z["spec"])))
+    b = builder_for(tt)
+    for i in range(int(z["n_cases"])):
+        idle, pend, T = z[f"c{i}_idle_nid"], z[f"c{i}_pend_onid"], int(z[f"c{i}_T"])
+        oi, op, od = b.npo_match(idle, pend)
+        order = np.argsort(oi)
+        assert np.array_equal(oi[order], z[f"c{i}_m_idle"])
+        assert np.array_equal(pend[op[order]], z[f"c{i}_m_node"])
+        assert np.array_equal(T + od[order] + 240, z[f"c{i}_m_ddl"])
+
+
+def test_cuda_npo_matches_oracle_with_ties():
+    import oracle
+    tt = synth.random_table(30, 9, "ties")
+    b = builder_for(tt)
+    rng = np.random.default_rng(4)
+    for n_idle, n_pend in ((40, 25), (25, 40), (1, 7), (300, 200)):
+        idle = rng.integers(1, 31, size=n_idle).astype(np.int32)
+        pend = rng.integers(1, 31, size=n_pend).astype(np.int32)
+        a = oracle.npo_match(tt, idle, pend)
+        g = b.npo_match(idle, pend)
+        for x, y in zip(a, g):
+            assert np.array_equal(x, y)
+
+
+def test_seam_functions_return_reference_style_records():
+    """B1/B2 through duck-typed Veh/Req objects: live references, fresh mutable schedules."""
+    from test_marshal_cpu import _objects
+    import oracle
+    tt, cases = load_golden("sim_osp_cap4")
+    b = builder_for(tt)
+    ep, gold = cases[1]
+    reqs, objs, vehs = _objects(ep)
+    search_rids = [int(ep.req_id[i]) for i in ep.search]
+    recs = b.compute_candidate_veh_trip_pairs(search_rids, search_rids, reqs, vehs, ep.T, 0.1, True, False)
+    assert len(recs) == gold.n_entries
+    for e, (veh, trip, sche, cost, score) in enumerate(recs):
+        assert veh is vehs[gold.ent_veh[e]] and cost == gold.ent_cost[e]
+    assert np.array_equal(recs.delays, gold.ent_delay)

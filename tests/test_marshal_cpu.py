@@ -1,0 +1,97 @@
+"""Host logic: marshalling Veh/Req objects <-> SoA arrays <-> reference-style records."""
+import collections
+import types
+
+import numpy as np
+
+from conftest import load_golden
+from amod_b200 import marshal
+import oracle
+
+
+class _Status:
+    def __init__(self, v):
+        self.value = v
+
+
+def _objects(ep):
+    """Minimal duck-typed Veh/Req objects from an Epoch (what the seams read)."""
+    reqs = {}
+    objs = []
+    for i in range(ep.n_req):
+        r = types.SimpleNamespace(id=int(ep.req_id[i]), onid=int(ep.req_onid[i]), dnid=int(ep.req_dnid[i]),
+                                  Clp=float(ep.req_clp[i]), Cld=float(ep.req_cld[i]), Tr=float(ep.req_tr[i]),
+                                  Ts=float(ep.req_ts[i]), status=_Status(1))
+        reqs[r.id] = r
+        objs.append(r)
+    vehs = []
+    for v in range(ep.n_veh):
+        sche, onboard = [], []
+        for k in range(ep.veh_sche_off[v], ep.veh_sche_off[v + 1]):
+            c = int(ep.sche_code[k])
+            if c < 0:
+                sche.append((-1, 0, int(ep.veh_reb_node[v]), float(ep.veh_reb_ddl[v])))
+            else:
+                r = objs[c >> 1]
+                sche.append((r.id, -1, r.dnid, r.Cld) if c & 1 else (r.id, 1, r.onid, r.Clp))
+                if ep.sche_onboard[k]:
+                    onboard.append(r.id)
+        vehs.append(types.SimpleNamespace(id=v, nid=int(ep.veh_nid[v]), t_to_nid=float(ep.veh_t_to_nid[v]),
+                                          load=int(ep.veh_load[v]), status=_Status(int(ep.veh_status[v])), sche=sche,
+                                          onboard_rids=onboard, K=ep.cap))
+    return reqs, objs, vehs
+
+
+def test_marshal_roundtrip_reproduces_epoch():
+    tt, cases = load_golden("rand_real_osp_cap4")
+    for ep, _gold in cases[:3]:
+        reqs, objs, vehs = _objects(ep)
+        search_rids = [int(ep.req_id[i]) for i in ep.search]
+        ep2, req_objs = marshal.marshal_epoch(reqs, vehs, search_rids, ep.T, ep.cap, ep.mode)
+        # request set = searched + referenced by a schedule; indices may be a subset of the original
+        remap = {int(ep.req_id[i]): i for i in range(ep.n_req)}
+        assert [remap[int(r)] for r in ep2.req_id[ep2.search]] == ep.search.tolist()
+        a = oracle.osp_build(ep, tt)
+        b = oracle.osp_build(ep2, tt)
+        back = np.array([remap[int(r)] for r in ep2.req_id])
+        assert np.array_equal(a.ent_veh, b.ent_veh) and np.array_equal(a.ent_cost, b.ent_cost)
+        assert np.array_equal(a.trip_req, back[b.trip_req])
+        bc = np.where(b.sche_code < 0, -1, 2 * back[np.maximum(b.sche_code, 0) >> 1] + (b.sche_code & 1))
+        assert np.array_equal(a.sche_code, bc)
+
+
+def test_pool_to_records_layout():
+    tt, cases = load_golden("rand_ties_osp_cap4")
+    ep, gold = cases[0]
+    reqs, objs, vehs = _objects(ep)
+    recs = marshal.pool_to_records(gold, ep, vehs, objs)
+    assert len(recs) == gold.n_entries
+    for e, rec in enumerate(recs):
+        veh, trip, sche, cost, score = rec
+        assert isinstance(rec, list) and isinstance(sche, list) and all(isinstance(s, tuple) and len(s) == 4 for s in sche)
+        assert veh is vehs[gold.ent_veh[e]]
+        assert [r.id for r in trip] == sorted(r.id for r in trip)
+        assert cost == gold.ent_cost[e] and score == 0.0
+    # records_to_pool inverts it
+    index_of = {int(r): i for i, r in enumerate(ep.req_id)}
+    back = marshal.records_to_pool(recs, vehs, index_of, ep.mode)
+    ok, why = marshal.pools_equal(back, gold, check_delay=False, check_nfeas=False)
+    assert ok, why
+    # a consumer may pop the rebalancing stop in place (vehicle.py:234-241): lists must be fresh
+    recs2 = marshal.pool_to_records(gold, ep, vehs, objs)
+    assert all(a[2] is not b[2] for a, b in zip(recs, recs2))
+
+
+def test_shard_and_merge_is_vehicle_major():
+    from amod_b200 import dist
+    tt, cases = load_golden("rand_real_osp_cap4")
+    ep, gold = cases[1]
+    world = 3
+    parts = []
+    for rank in range(world):
+        sub, sel = ep.shard(rank, world)
+        p = oracle.osp_build(sub, tt)
+        parts.append((p, sel))
+    merged = dist.merge_vehicle_major(parts, ep.n_veh)
+    ok, why = marshal.pools_equal(merged, gold, check_kind=True)
+    assert ok, why
