@@ -51,6 +51,7 @@ struct amod_ctx {
     bool own_stream = false;
     int n_nodes = 0, tt_dtype = 0;
     void* d_tt = nullptr;
+    size_t tt_bytes = 0;
     int n_sm = 148;
     std::string err;
     // staging of host epochs
@@ -111,6 +112,25 @@ static int scan_excl(amod_ctx* ctx, const Tin* in, i64 n, i64* out, i64* h_total
     return AMOD_OK;
 }
 
+// Keep the travel-time table resident in L2 (126 MB on B200; 67 MB as fp32): persisting
+// access-policy window on the stream the kernels run on.
+static void apply_l2_policy(amod_ctx* ctx, cudaStream_t stream) {
+    int max_win = 0, max_persist = 0;
+    cudaDeviceGetAttribute(&max_win, cudaDevAttrMaxAccessPolicyWindowSize, ctx->device);
+    cudaDeviceGetAttribute(&max_persist, cudaDevAttrMaxPersistingL2CacheSize, ctx->device);
+    if (max_win <= 0 || max_persist <= 0 || !ctx->d_tt) return;
+    size_t win = std::min(ctx->tt_bytes, (size_t)max_win);
+    cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, std::min((size_t)max_persist, win));
+    cudaStreamAttrValue av; memset(&av, 0, sizeof av);
+    av.accessPolicyWindow.base_ptr = ctx->d_tt;
+    av.accessPolicyWindow.num_bytes = win;
+    av.accessPolicyWindow.hitRatio = (float)std::min(1.0, (double)max_persist / (double)win);
+    av.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+    av.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+    cudaStreamSetAttribute(stream, cudaStreamAttributeAccessPolicyWindow, &av);
+    cudaGetLastError();
+}
+
 // ------------------------------------------------------------------------------------------------
 extern "C" const char* amod_version(void) { return "amod_b200 0.1 (sm_100a)"; }
 
@@ -141,22 +161,8 @@ extern "C" int amod_create(amod_ctx** out, int device, int n_nodes, const void* 
     size_t bytes = (size_t)n_nodes * n_nodes * (tt_dtype == AMOD_TT_F64 ? 8 : 4);
     if ((e = cudaMalloc(&ctx->d_tt, bytes)) != cudaSuccess) return bail("cudaMalloc(table)", e);
     if ((e = cudaMemcpy(ctx->d_tt, tt_host, bytes, cudaMemcpyHostToDevice)) != cudaSuccess) return bail("upload table", e);
-    // Keep the table resident in L2 (126 MB on B200): persisting access-policy window on our stream.
-    int max_win = 0, max_persist = 0;
-    cudaDeviceGetAttribute(&max_win, cudaDevAttrMaxAccessPolicyWindowSize, device);
-    cudaDeviceGetAttribute(&max_persist, cudaDevAttrMaxPersistingL2CacheSize, device);
-    if (max_win > 0 && max_persist > 0) {
-        size_t win = std::min(bytes, (size_t)max_win);
-        cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, std::min((size_t)max_persist, win));
-        cudaStreamAttrValue av; memset(&av, 0, sizeof av);
-        av.accessPolicyWindow.base_ptr = ctx->d_tt;
-        av.accessPolicyWindow.num_bytes = win;
-        av.accessPolicyWindow.hitRatio = (float)std::min(1.0, (double)max_persist / (double)win);
-        av.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
-        av.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
-        cudaStreamSetAttribute(ctx->stream, cudaStreamAttributeAccessPolicyWindow, &av);
-        cudaGetLastError();
-    }
+    ctx->tt_bytes = bytes;
+    apply_l2_policy(ctx, ctx->stream);
     cudaEventCreate(&ctx->ev0); cudaEventCreate(&ctx->ev1);
     *out = ctx;
     return AMOD_OK;
@@ -189,8 +195,8 @@ extern "C" void amod_destroy(amod_ctx* ctx) {
 extern "C" int amod_set_stream(amod_ctx* ctx, void* cuda_stream) {
     if (!ctx) return AMOD_E_BADARG;
     if (ctx->own_stream && ctx->stream) { cudaStreamSynchronize(ctx->stream); cudaStreamDestroy(ctx->stream); }
-    if (cuda_stream) { ctx->stream = (cudaStream_t)cuda_stream; ctx->own_stream = false; }
-    else { CK(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking)); ctx->own_stream = true; }
+    if (cuda_stream) { ctx->stream = (cudaStream_t)cuda_stream; ctx->own_stream = false; apply_l2_policy(ctx, ctx->stream); }
+    else { CK(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking)); ctx->own_stream = true; apply_l2_policy(ctx, ctx->stream); }
     return AMOD_OK;
 }
 

@@ -1,0 +1,368 @@
+#!/usr/bin/env python
+"""bench.py — OSP pool-build throughput on B200 (BASELINE.json metric: schedules evaluated/s and
+pool-build ms/epoch, 2,000 vehicles, capacity 4, Manhattan-scale synthetic demand, 30 s epochs).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+A *step* is one pass of the hot path (dispatch_osp.compute_candidate_veh_trip_pairs, cut-off
+disabled) over one recorded epoch snapshot (bench_data/cfg2_epoch*.npz, produced by running the
+reference simulator on the synthetic table, see bench_data/make_snapshots.py).  The unit, a
+"schedule evaluated", is one execution of scheduling.test_constraints_get_cost AS THE REFERENCE
+WOULD PERFORM IT; the kernels count it with the reference's early-exit semantics and the tests
+check the count against the oracle, so GPU and CPU arms share the numerator.
+
+N > 1 (torchrun, one rank per GPU): weak scaling — the fleet is N x 2,000 vehicles (the snapshot's
+fleet tiled N times against the same request set, BASELINE.json configs[3] at N=4), vehicles are
+interleaved over ranks, every rank builds its slice and an NCCL all-gather assembles the pool.
+"""
+from __future__ import annotations
+
+import argparse
+import glob
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "schedules evaluated/sec; OSP pool-build ms/epoch (2000 veh cap4)"
+UNIT = "schedules/s"
+
+
+def load_snapshots(tag="cfg2"):
+    from amod_b200.marshal import Epoch
+    files = sorted(glob.glob(os.path.join(ROOT, "bench_data", f"{tag}_epoch*.npz")))
+    if not files:
+        raise SystemExit("bench_data/ holds no epoch snapshots (run bench_data/make_snapshots.py)")
+    snaps = []
+    for f in files:
+        z = np.load(f)
+        snaps.append((os.path.basename(f), Epoch.from_npz_dict(z, "ep_"), int(z["n_evals"]), int(z["n_lookups"])))
+    return snaps
+
+
+def tile_fleet(ep, n):
+    """Fleet of n x V vehicles: the snapshot's fleet repeated n times (same requests)."""
+    if n == 1:
+        return ep
+    from amod_b200.marshal import Epoch
+    kw = {f: getattr(ep, f) for f in Epoch.FIELDS}
+    for f in ("veh_nid", "veh_t_to_nid", "veh_load", "veh_status", "veh_reb_node", "veh_reb_ddl", "sche_code", "sche_onboard"):
+        kw[f] = np.tile(kw[f], n)
+    lens = np.tile(np.diff(ep.veh_sche_off), n)
+    off = np.zeros(lens.size + 1, dtype=np.int32)
+    np.cumsum(lens, out=off[1:])
+    kw["veh_sche_off"] = off
+    return Epoch(T=ep.T, cap=ep.cap, mode=ep.mode, **kw)
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md)."""
+
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        super().__init__(daemon=True)
+        self.gpu = gpu_index
+        self.rows = []
+        self.proc = None
+
+    def run(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            for line in self.proc.stdout:
+                self.rows.append([x.strip() for x in line.split(",")])
+        except Exception:
+            pass
+
+    def stop(self) -> dict:
+        if self.proc:
+            self.proc.terminate()
+        sm = [float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({names[i] for r in self.rows if len(r) >= 7 for i in range(4) if r[3 + i].lower() == "active"})
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(sm)}
+
+
+def cpu_leg(snaps, tt, budget_s=12.0):
+    """Oracle (the C port of the reference's path) on the host cores, bounded sample."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import oracle
+    threads = oracle.max_threads()
+    name, ep, n_evals, _ = snaps[0]
+    # calibrate on every 64th vehicle, then size the vehicle stride for ~budget_s
+    t = time.perf_counter()
+    p = oracle.osp_build(ep, tt, n_threads=threads, veh_step=64)
+    dt = time.perf_counter() - t
+    rate = max(p.stats["n_evals"], 1) / max(dt, 1e-6)
+    step = int(max(1, min(64, np.ceil(n_evals / (rate * budget_s)))))
+    t = time.perf_counter()
+    p = oracle.osp_build(ep, tt, n_threads=threads, veh_step=step)
+    dt = time.perf_counter() - t
+    return {"value": p.stats["n_evals"] / dt, "unit": UNIT, "cores": threads, "kind": "port",
+            "sample": f"{name}: every {step}th vehicle ({(ep.n_veh + step - 1) // step} of {ep.n_veh}), "
+                      f"{p.stats['n_evals']} schedules in {dt:.2f} s, oracle/amod_oracle.c with OpenMP",
+            "ms_per_epoch_extrapolated": 1e3 * n_evals / (p.stats["n_evals"] / dt)}
+
+
+def run_reference(args):
+    """--impl reference: the reference's CPU path (oracle port: the Python reference cannot travel
+    to the GPU box) on all host threads, same snapshots, each step a bounded vehicle sample."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from amod_b200 import synth
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import oracle
+    tt = synth.make_road_graph(seed=0).tt
+    snaps = load_snapshots()
+    threads = oracle.max_threads()
+    name, ep, n_evals, _ = snaps[0]
+    t = time.perf_counter()
+    p = oracle.osp_build(ep, tt, n_threads=threads, veh_step=64)
+    rate = max(p.stats["n_evals"], 1) / max(time.perf_counter() - t, 1e-6)
+    per_step_budget = max(2.0, min(20.0, 150.0 / max(args.steps + args.warmup, 1)))
+    step = int(max(1, min(64, np.ceil(n_evals / (rate * per_step_budget)))))
+    evals, t_total = 0, 0.0
+    for i in range(args.warmup + args.steps):
+        _n, e, _ne, _nl = snaps[i % len(snaps)]
+        t = time.perf_counter()
+        p = oracle.osp_build(e, tt, n_threads=threads, veh_lo=i % step, veh_step=step)
+        dt = time.perf_counter() - t
+        if i >= args.warmup:
+            evals += p.stats["n_evals"]; t_total += dt
+    val = evals / t_total
+    line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": 1e3 * t_total / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "OSP pool build, 2000 veh cap 4, Manhattan-scale synthetic epoch snapshots (bench_data/cfg2_*)",
+                       "sample": f"every {step}th vehicle per step"},
+            "cpu_baseline": {"value": val, "unit": UNIT, "cores": threads, "kind": "port",
+                             "sample": f"every {step}th vehicle of each snapshot, {args.steps} steps, oracle/amod_oracle.c (OpenMP); "
+                                       f"the Python reference itself measured 45-71k schedules/s/core (BASELINE.md)"},
+            "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=16)
+    ap.add_argument("--warmup", type=int, default=4)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import torch
+    import torch.distributed as dist
+    from amod_b200 import capi, synth
+    from amod_b200.pool import PoolBuilder
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the pool builder has no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    assert world == args.gpus or world == 1
+
+    tt = synth.make_road_graph(seed=0).tt
+    snaps = load_snapshots()
+    b = PoolBuilder(tt, device=local)
+    stream = torch.cuda.current_stream()
+    b.set_stream(stream.cuda_stream)          # CUDA events below bracket the stream the kernels run on
+
+    # per-rank slice of the (tiled) fleet, resident in HBM before the timed region
+    work = []
+    for name, ep, n_evals, n_lookups in snaps:
+        full = tile_fleet(ep, world)
+        mine, sel = full.shard(rank, world)
+        tens = {f: torch.from_numpy(getattr(mine, f)).to(dev) for f in capi.EPOCH_PTR_FIELDS}
+        work.append(dict(name=name, host=mine, dev=tens, sel=sel, n_evals_full=n_evals * world, n_veh_full=full.n_veh))
+
+    class DevEp:
+        pass
+
+    def dev_epoch(w):
+        d = DevEp()
+        h = w["host"]
+        d.n_veh, d.n_req, d.n_search, d.cap, d.mode, d.T = h.n_veh, h.n_req, h.n_search, h.cap, h.mode, h.T
+        for f, t in w["dev"].items():
+            setattr(d, f, t)
+        return d
+
+    gather_bufs = {}
+
+    def allgather_pool():
+        """NCCL all-gather of the rank pools (padded), payload stays on the device."""
+        P, NT, NS = b.pool_sizes()
+        sizes = torch.tensor([P, NT, NS], dtype=torch.int64, device=dev)
+        all_sizes = torch.empty(world * 3, dtype=torch.int64, device=dev)
+        dist.all_gather_into_tensor(all_sizes, sizes)
+        mx = all_sizes.view(world, 3).max(dim=0).values.tolist()
+        o = capi.AmodPool()
+        o.cap_entries, o.cap_trip_reqs, o.cap_stops = mx[0], mx[1], mx[2]
+        bufs = {}
+        for fname, dt, key in capi.POOL_FIELDS:
+            n = {"e": mx[0], "e1": mx[0] + 1, "t": mx[1], "s": mx[2]}[key]
+            tdt = {np.int32: torch.int32, np.int64: torch.int64, np.float64: torch.float64}[dt]
+            k = (fname, n)
+            if k not in gather_bufs:
+                gather_bufs[k] = (torch.empty(max(n, 1), dtype=tdt, device=dev), torch.empty(world * max(n, 1), dtype=tdt, device=dev))
+            bufs[fname] = gather_bufs[k]
+            setattr(o, fname, bufs[fname][0].data_ptr())
+        b._check(b.lib.amod_pool_fetch(b.h, o, capi.LOC_DEVICE))
+        nbytes = 0
+        for fname, (src, dst) in bufs.items():
+            dist.all_gather_into_tensor(dst, src)
+            nbytes += dst.numel() * dst.element_size()
+        return nbytes
+
+    ptr_of = lambda t: t.data_ptr()
+
+    def step_resident(i):
+        w = work[i % len(work)]
+        st = b.build(dev_epoch(w), loc=capi.LOC_DEVICE, ptr_of=ptr_of)
+        if world > 1:
+            allgather_pool()
+        return st
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident arm (value) ---------------------------------------------------------------
+    for i in range(args.warmup):
+        step_resident(i)
+    barrier()
+    sampler = ClockSampler(local) if rank == 0 else None
+    if sampler:
+        sampler.start()
+        time.sleep(0.25)
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    evals = lookups_eval = launches = 0
+    ms_eval = 0.0
+    n_eval_launches = 0
+    entries = 0
+    ev0.record(stream)
+    for i in range(args.steps):
+        st = step_resident(args.warmup + i)
+        evals += st["n_evals"]; launches += st["n_kernel_launches"]; ms_eval += st["ms_eval"]
+        n_eval_launches += st["n_eval_launches"]; entries += st["n_entries"]
+        lookups_eval += st["n_lookups"] - st["n_screens"]
+    ev1.record(stream)
+    barrier()
+    ms = ev0.elapsed_time(ev1)
+    clocks = sampler.stop() if sampler else None
+    t_ms = torch.tensor([ms], dtype=torch.float64, device=dev)
+    tot = torch.tensor([float(evals), float(launches), float(entries)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t_ms, op=dist.ReduceOp.MAX)
+        dist.all_reduce(tot, op=dist.ReduceOp.SUM)
+    ms = float(t_ms.item())
+    evals_all, launches_all, entries_all = (float(x) for x in tot.tolist())
+
+    # ---- end-to-end arm: C-ABI call with HOST buffers, H2D + D2H inside the timed region ------------
+    def step_e2e(i):
+        w = work[i % len(work)]
+        pool = b.build_pool(w["host"])
+        if world > 1:
+            allgather_pool()
+        h2d = sum(getattr(w["host"], f).nbytes for f in capi.EPOCH_PTR_FIELDS)
+        d2h = sum(getattr(pool, f).nbytes for f, _d, _k in capi.POOL_FIELDS)
+        return pool.stats["n_evals"], h2d, d2h
+
+    for i in range(min(args.warmup, 2)):
+        step_e2e(i)
+    barrier()
+    t0 = time.perf_counter()
+    e_evals = e_h2d = e_d2h = 0
+    for i in range(args.steps):
+        a, h, d = step_e2e(args.warmup + i)
+        e_evals += a; e_h2d += h; e_d2h += d
+    barrier()
+    e_s = time.perf_counter() - t0
+    t_e = torch.tensor([e_s], dtype=torch.float64, device=dev)
+    tot_e = torch.tensor([float(e_evals)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t_e, op=dist.ReduceOp.MAX)
+        dist.all_reduce(tot_e, op=dist.ReduceOp.SUM)
+    e2e_val = float(tot_e.item()) / float(t_e.item())
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline of the dominant kernel (k_eval: the insertion search) -----------------------------
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+    peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
+    # L2 random-gather peak of the table on this box (the bound SURVEY.md §8d names), measured live
+    rng = np.random.default_rng(0)
+    ng = 1 << 24
+    o_t = torch.from_numpy(rng.integers(1, tt.shape[0] + 1, size=ng).astype(np.int32)).to(dev)
+    d_t = torch.from_numpy(rng.integers(1, tt.shape[0] + 1, size=ng).astype(np.int32)).to(dev)
+    out_t = torch.empty(ng, dtype=torch.float32, device=dev)
+    import ctypes as C
+    gms = C.c_double(0.0)
+    b._check(b.lib.amod_gather_bench(b.h, o_t.data_ptr(), d_t.data_ptr(), out_t.data_ptr(), ng, 5, C.byref(gms)))
+    l2_gather_gbs = ng * 32 / (gms.value * 1e-3) / 1e9
+    alg_bytes = lookups_eval * 32.0            # one 32 B L2 sector per reference lookup
+    achieved = alg_bytes / (ms_eval * 1e-3) / 1e9 if ms_eval > 0 else 0.0
+    traffic = None
+    try:
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "eval_traffic.json")))["dram_bytes_per_launch"]
+    except Exception:
+        pass
+    roofline = {"bound": "hbm", "kernel": "k_eval (insertion search, count + fill launches)", "achieved": achieved,
+                "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak, "traffic": traffic, "peak_source": peak_src,
+                "algorithmic_bytes_per_launch": alg_bytes / max(n_eval_launches, 1), "launches": n_eval_launches,
+                "avg_launch_ms": ms_eval / max(n_eval_launches, 1), "kernel_share_of_step": ms_eval / ms,
+                "l2_gather_peak_gbs": l2_gather_gbs, "frac_of_l2_gather_peak": achieved / l2_gather_gbs,
+                "note": "algorithmic bytes = reference travel-time lookups inside evaluations x 32 B sector; the table is "
+                        "L2-resident so HBM peak is the fallback bound and the measured L2 random-gather rate the real one"}
+
+    cpu = None if (args.no_cpu or world > 1) else cpu_leg(snaps, tt)
+    line = {"metric": METRIC, "value": evals_all / (ms * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": f"OSP pool build (cut-off disabled), {work[0]['n_veh_full']} veh cap {work[0]['host'].cap}, "
+                                   f"Manhattan-scale synthetic epoch snapshots x{len(work)} (bench_data/cfg2_*), 4091-node fp32 table",
+                       "fleet": work[0]["n_veh_full"], "requests_considered": int(np.mean([w["host"].n_search for w in work])),
+                       "parallelism": f"vehicles interleaved over {world} rank(s)" + (", NCCL all-gather of the pool" if world > 1 else ""),
+                       "l2_policy": "inputs differ every step (8 snapshots cycled); table deliberately L2-resident (67 MB persisting window)",
+                       "pool_entries_per_step": entries_all / args.steps, "schedules_per_step": evals_all / args.steps},
+            "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": e_h2d // args.steps, "d2h_bytes_per_step": e_d2h // args.steps,
+                    "ms_per_step": 1e3 * float(t_e.item()) / args.steps,
+                    "path": "amod_osp_build(host pointers) + amod_pool_fetch(host buffers) through ctypes"},
+            "gpu_launches": int(launches_all), "clocks": clocks, "roofline": roofline}
+    if cpu:
+        line["cpu_baseline"] = cpu
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
