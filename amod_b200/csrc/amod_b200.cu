@@ -43,7 +43,7 @@ struct DevBuf {
     template <typename T> T* as() { return (T*)p; }
 };
 
-struct LevelBufs { DevBuf trip_veh, trip_req, sch_off, nfeas, rot, cost, sch, veh_start; };
+struct LevelBufs { DevBuf trip_veh, trip_req, s0, nfeas, cost, sch, sch_cost, order, veh_start; };
 
 struct amod_ctx {
     int device = 0;
@@ -56,15 +56,21 @@ struct amod_ctx {
     std::string err;
     // staging of host epochs
     DevBuf ep_dev; void* ep_pinned = nullptr; size_t ep_pinned_cap = 0;
+    // device control block + pinned host mirror
+    DevBuf ctl; Control* h_ctl = nullptr;
+    // capacities (grown from the sizes an epoch needed; persisted across epochs)
+    i64 cap_tasks = 1 << 18, cap_chunks = 1 << 19, cap_ent = 1 << 18, cap_ptr = 1 << 19, cap_pst = 1 << 21;
+    i64 cap_trips[MAX_LEVELS], cap_sch[MAX_LEVELS];
     // workspace
-    DevBuf len0, S0, words0, flag8, pos, pos2, partial, total, stats, task_veh[2], task_base[2], task_q[2], task_nfeas,
-        task_cost, words, hash, row_cnt, row_off, tmp_j, tmp_q, tmp_row;
+    DevBuf len0, S0, s0pos, flag8, pos, partial, task_veh[2], task_base[2], task_q[2], task_nchunk[2], task_chunk0, trip_pos,
+        chunk_task, chunk_cnt, lane_cnt, chunk_pos, hash, row_cnt, row_off, tmp_j, tmp_q;
     LevelBufs lv[MAX_LEVELS];
     // pool
     DevBuf veh_cnt, veh_off, ent_veh, ent_kind, ent_nfeas, ent_tlen, ent_slen, ent_src, ent_trip, ent_cost, ent_delay,
         trip_off, sche_off, trip_req, sche_code;
     i64 pool_entries = 0, pool_trip_reqs = 0, pool_stops = 0;
     bool pool_valid = false;
+    int n_attempts = 0;
     // npo
     DevBuf npo_in, npo_vm, npo_rm, npo_rb, npo_vb, npo_rdt, npo_mdt, npo_cnt;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
@@ -89,27 +95,13 @@ static int dispatch_tt(amod_ctx* ctx, F&& f) {
 
 static inline int nblk(i64 n, int per) { return (int)((n + per - 1) / per); }
 
-// exclusive scan in[0..n) -> out[0..n], total also copied to *h_total when requested (synchronises)
-template <typename Tin>
-static int scan_excl(amod_ctx* ctx, const Tin* in, i64 n, i64* out, i64* h_total) {
-    cudaStream_t st = ctx->stream;
-    if (n == 0) {
-        CK(cudaMemsetAsync(out, 0, sizeof(i64), st));
-        if (h_total) *h_total = 0;
-        return AMOD_OK;
-    }
-    int nb = nblk(n, SCAN_TILE);
-    CK(ctx->partial.ensure(sizeof(i64) * (size_t)nb));
-    CK(ctx->total.ensure(sizeof(i64)));
-    k_scan_reduce<Tin><<<nb, SCAN_THREADS, 0, st>>>(in, n, ctx->partial.as<i64>());
-    k_scan_partials<<<1, SCAN_THREADS, 0, st>>>(ctx->partial.as<i64>(), nb, ctx->total.as<i64>());
-    k_scan_final<Tin><<<nb, SCAN_THREADS, 0, st>>>(in, n, ctx->partial.as<i64>(), out);
-    ctx->n_launches += 3;
-    if (h_total) {
-        CK(cudaMemcpyAsync(h_total, ctx->total.p, sizeof(i64), cudaMemcpyDeviceToHost, st));
-        CK(cudaStreamSynchronize(st));
-    }
-    return AMOD_OK;
+// exclusive scan (length and result sizes live on the device; no synchronisation)
+template <typename In, typename Fin>
+static void scan_dev(amod_ctx* ctx, In in, i64* out, Fin fin) {
+    const int g = ctx->n_sm;
+    k_scan_a<In><<<g, SCAN_THREADS, 0, ctx->stream>>>(in, ctx->partial.as<i64>());
+    k_scan_b<In, Fin><<<g, SCAN_THREADS, 0, ctx->stream>>>(in, ctx->partial.as<i64>(), out, fin);
+    ctx->n_launches += 2;
 }
 
 // Keep the travel-time table resident in L2 (126 MB on B200; 67 MB as fp32): persisting
@@ -162,6 +154,8 @@ extern "C" int amod_create(amod_ctx** out, int device, int n_nodes, const void* 
     if ((e = cudaMalloc(&ctx->d_tt, bytes)) != cudaSuccess) return bail("cudaMalloc(table)", e);
     if ((e = cudaMemcpy(ctx->d_tt, tt_host, bytes, cudaMemcpyHostToDevice)) != cudaSuccess) return bail("upload table", e);
     ctx->tt_bytes = bytes;
+    for (int k = 0; k < MAX_LEVELS; k++) { ctx->cap_trips[k] = 1 << 16; ctx->cap_sch[k] = 1 << 18; }
+    if ((e = cudaMallocHost((void**)&ctx->h_ctl, sizeof(Control))) != cudaSuccess) return bail("cudaMallocHost", e);
     apply_l2_policy(ctx, ctx->stream);
     cudaEventCreate(&ctx->ev0); cudaEventCreate(&ctx->ev1);
     *out = ctx;
@@ -172,17 +166,18 @@ extern "C" void amod_destroy(amod_ctx* ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     cudaDeviceSynchronize();
-    DevBuf* all[] = {&ctx->ep_dev, &ctx->len0, &ctx->S0, &ctx->words0, &ctx->flag8, &ctx->pos, &ctx->pos2, &ctx->partial,
-                     &ctx->total, &ctx->stats, &ctx->task_veh[0], &ctx->task_veh[1], &ctx->task_base[0], &ctx->task_base[1],
-                     &ctx->task_q[0], &ctx->task_q[1], &ctx->task_nfeas, &ctx->task_cost, &ctx->words, &ctx->hash,
-                     &ctx->row_cnt, &ctx->row_off, &ctx->tmp_j, &ctx->tmp_q, &ctx->tmp_row, &ctx->veh_cnt, &ctx->veh_off,
-                     &ctx->ent_veh, &ctx->ent_kind, &ctx->ent_nfeas, &ctx->ent_tlen, &ctx->ent_slen, &ctx->ent_src,
-                     &ctx->ent_trip, &ctx->ent_cost, &ctx->ent_delay, &ctx->trip_off, &ctx->sche_off, &ctx->trip_req,
+    DevBuf* all[] = {&ctx->ep_dev, &ctx->ctl, &ctx->len0, &ctx->S0, &ctx->s0pos, &ctx->flag8, &ctx->pos, &ctx->partial,
+                     &ctx->task_veh[0], &ctx->task_veh[1], &ctx->task_base[0], &ctx->task_base[1], &ctx->task_q[0], &ctx->task_q[1],
+                     &ctx->task_nchunk[0], &ctx->task_nchunk[1], &ctx->task_chunk0, &ctx->trip_pos, &ctx->chunk_task, &ctx->chunk_cnt,
+                     &ctx->lane_cnt, &ctx->chunk_pos, &ctx->hash, &ctx->row_cnt, &ctx->row_off, &ctx->tmp_j, &ctx->tmp_q,
+                     &ctx->veh_cnt, &ctx->veh_off, &ctx->ent_veh, &ctx->ent_kind, &ctx->ent_nfeas, &ctx->ent_tlen, &ctx->ent_slen,
+                     &ctx->ent_src, &ctx->ent_trip, &ctx->ent_cost, &ctx->ent_delay, &ctx->trip_off, &ctx->sche_off, &ctx->trip_req,
                      &ctx->sche_code, &ctx->npo_in, &ctx->npo_vm, &ctx->npo_rm, &ctx->npo_rb, &ctx->npo_vb, &ctx->npo_rdt,
                      &ctx->npo_mdt, &ctx->npo_cnt};
     for (DevBuf* b : all) b->release();
-    for (auto& l : ctx->lv) { l.trip_veh.release(); l.trip_req.release(); l.sch_off.release(); l.nfeas.release(); l.rot.release();
-                              l.cost.release(); l.sch.release(); l.veh_start.release(); }
+    for (auto& l : ctx->lv) { l.trip_veh.release(); l.trip_req.release(); l.s0.release(); l.nfeas.release(); l.cost.release();
+                              l.sch.release(); l.sch_cost.release(); l.order.release(); l.veh_start.release(); }
+    if (ctx->h_ctl) cudaFreeHost(ctx->h_ctl);
     if (ctx->ep_pinned) cudaFreeHost(ctx->ep_pinned);
     if (ctx->d_tt) cudaFree(ctx->d_tt);
     for (auto e : ctx->ev_pool) cudaEventDestroy(e);
@@ -279,23 +274,160 @@ static int upload_epoch(amod_ctx* ctx, const amod_epoch* ep, int loc, DEpoch* d)
 // ------------------------------------------------------------------------------------------------
 // the build
 // ------------------------------------------------------------------------------------------------
-static int alloc_level(amod_ctx* ctx, int k, int n_trips, i64 n_words, int n_veh, Level* lv) {
-    LevelBufs& b = ctx->lv[k];
-    size_t n = (size_t)std::max(n_trips, 1);
-    CK(b.trip_veh.ensure(4 * n)); CK(b.trip_req.ensure(4 * n * (size_t)std::max(k, 1))); CK(b.sch_off.ensure(8 * n));
-    CK(b.nfeas.ensure(4 * n)); CK(b.rot.ensure(4 * n)); CK(b.cost.ensure(8 * n));
-    CK(b.sch.ensure(sizeof(code_t) * (size_t)std::max(n_words, (i64)1)));
-    CK(b.veh_start.ensure(4 * ((size_t)n_veh + 2)));
-    lv->k = k; lv->n_trips = n_trips;
-    lv->trip_veh = b.trip_veh.as<int>(); lv->trip_req = b.trip_req.as<int>(); lv->sch_off = b.sch_off.as<i64>();
-    lv->nfeas = b.nfeas.as<int>(); lv->rot = b.rot.as<int>(); lv->cost = b.cost.as<double>(); lv->sch = b.sch.as<code_t>();
-    lv->veh_start = b.veh_start.as<int>();
-    return AMOD_OK;
-}
-
 static cudaEvent_t get_event(amod_ctx* ctx, size_t i) {
     while (ctx->ev_pool.size() <= i) { cudaEvent_t e; cudaEventCreate(&e); ctx->ev_pool.push_back(e); }
     return ctx->ev_pool[i];
+}
+
+static int ensure_buffers(amod_ctx* ctx, int V, i64 n_screen, int max_level, const int* stride, LevelSet* ls, PoolBufs* pb) {
+    const size_t T = (size_t)ctx->cap_tasks, C = (size_t)ctx->cap_chunks;
+    CK(ctx->ctl.ensure(sizeof(Control)));
+    CK(ctx->len0.ensure(4 * (size_t)(V + 1))); CK(ctx->S0.ensure(4 * (size_t)(V + 1))); CK(ctx->s0pos.ensure(8 * (size_t)(V + 2)));
+    CK(ctx->flag8.ensure((size_t)std::max(n_screen, (i64)1))); CK(ctx->pos.ensure(8 * (size_t)(n_screen + 2)));
+    CK(ctx->partial.ensure(8 * (size_t)(ctx->n_sm + 1)));
+    for (int w = 0; w < 2; w++) {
+        CK(ctx->task_veh[w].ensure(4 * T)); CK(ctx->task_base[w].ensure(4 * T)); CK(ctx->task_q[w].ensure(4 * T));
+        CK(ctx->task_nchunk[w].ensure(4 * T));
+    }
+    CK(ctx->task_chunk0.ensure(8 * (T + 2))); CK(ctx->trip_pos.ensure(8 * (T + 2)));
+    CK(ctx->chunk_task.ensure(4 * C)); CK(ctx->chunk_cnt.ensure(4 * C)); CK(ctx->lane_cnt.ensure(64 * C)); CK(ctx->chunk_pos.ensure(8 * (C + 2)));
+    CK(ctx->tmp_j.ensure(4 * T)); CK(ctx->tmp_q.ensure(4 * T));
+    size_t max_trips = 1;
+    memset(ls, 0, sizeof *ls);
+    for (int k = 0; k <= max_level; k++) {
+        LevelBufs& b = ctx->lv[k];
+        const size_t nt = (size_t)std::max(ctx->cap_trips[k], (i64)(k == 0 ? V + 1 : 1));
+        ctx->cap_trips[k] = (i64)nt;
+        const size_t nsch = (size_t)std::max(ctx->cap_sch[k], (i64)1);
+        max_trips = std::max(max_trips, nt);
+        CK(b.trip_veh.ensure(4 * nt)); CK(b.trip_req.ensure(4 * nt * (size_t)std::max(k, 1))); CK(b.s0.ensure(8 * nt));
+        CK(b.nfeas.ensure(4 * nt)); CK(b.cost.ensure(8 * nt));
+        CK(b.sch.ensure(sizeof(code_t) * nsch * (size_t)stride[k])); CK(b.sch_cost.ensure(8 * nsch)); CK(b.order.ensure(4 * nsch));
+        CK(b.veh_start.ensure(4 * ((size_t)V + 2)));
+        Level& lv = ls->lv[k];
+        lv.k = k; lv.stride = stride[k]; lv.cap_trips = (int)nt; lv.cap_sch = (i64)nsch;
+        lv.trip_veh = b.trip_veh.as<int>(); lv.trip_req = b.trip_req.as<int>(); lv.s0 = b.s0.as<i64>(); lv.nfeas = b.nfeas.as<int>();
+        lv.cost = b.cost.as<double>(); lv.sch = b.sch.as<code_t>(); lv.sch_cost = b.sch_cost.as<double>(); lv.order = b.order.as<int>();
+        lv.veh_start = b.veh_start.as<int>();
+    }
+    ls->n = max_level + 1;
+    CK(ctx->row_cnt.ensure(4 * max_trips)); CK(ctx->row_off.ensure(8 * (max_trips + 2)));
+    unsigned hsz = 64; while (hsz < 2u * (unsigned)max_trips + 2u) hsz <<= 1;
+    CK(ctx->hash.ensure(4 * (size_t)hsz));
+    CK(ctx->veh_cnt.ensure(4 * (size_t)(V + 1))); CK(ctx->veh_off.ensure(8 * (size_t)(V + 2)));
+    const size_t E = (size_t)ctx->cap_ent, PT = (size_t)ctx->cap_ptr, PS = (size_t)ctx->cap_pst;
+    CK(ctx->ent_veh.ensure(4 * E)); CK(ctx->ent_kind.ensure(4 * E)); CK(ctx->ent_nfeas.ensure(4 * E)); CK(ctx->ent_tlen.ensure(4 * E));
+    CK(ctx->ent_slen.ensure(4 * E)); CK(ctx->ent_src.ensure(4 * E)); CK(ctx->ent_trip.ensure(4 * E)); CK(ctx->ent_cost.ensure(8 * E));
+    CK(ctx->ent_delay.ensure(8 * E)); CK(ctx->trip_off.ensure(8 * (E + 2))); CK(ctx->sche_off.ensure(8 * (E + 2)));
+    CK(ctx->trip_req.ensure(4 * PT)); CK(ctx->sche_code.ensure(4 * PS));
+    pb->cap_ent = (i64)E; pb->cap_ptr = (i64)PT; pb->cap_pst = (i64)PS;
+    pb->ent_veh = ctx->ent_veh.as<int>(); pb->ent_kind = ctx->ent_kind.as<int>(); pb->ent_nfeas = ctx->ent_nfeas.as<int>();
+    pb->ent_tlen = ctx->ent_tlen.as<int>(); pb->ent_slen = ctx->ent_slen.as<int>(); pb->ent_src = ctx->ent_src.as<int>();
+    pb->ent_trip = ctx->ent_trip.as<int>(); pb->ent_cost = ctx->ent_cost.as<double>(); pb->ent_delay = ctx->ent_delay.as<double>();
+    pb->trip_off = ctx->trip_off.as<i64>(); pb->sche_off = ctx->sche_off.as<i64>(); pb->trip_req = ctx->trip_req.as<int>();
+    pb->sche_code = ctx->sche_code.as<int>();
+    return AMOD_OK;
+}
+
+// One attempt: enqueue the whole level-synchronous pipeline on the stream without any host
+// synchronisation; every size is produced and consumed on the device (Control block).
+template <typename TT>
+static int enqueue_build(amod_ctx* ctx, const DEpoch& d, Table<TT> tt, int max_level, const LevelSet& ls, const PoolBufs& pb,
+                         size_t* n_ev_out) {
+    cudaStream_t st = ctx->stream;
+    const int V = d.n_veh, Q = d.n_search, mode = d.mode;
+    const int sba = mode == AMOD_MODE_SBA;
+    Control* ctl = ctx->ctl.as<Control>();
+    Stats* dstats = &ctl->stats;
+    const int G = ctx->n_sm * 2;                 // elementwise kernels: grid-stride on a fixed grid
+    const int GE = ctx->n_sm * 8;                // warp-per-item kernels
+    size_t n_ev = 0;
+    int* len0 = ctx->len0.as<int>();
+
+    memset(ctx->h_ctl, 0, sizeof(Control));
+    ctx->h_ctl->n_trips[0] = V;
+    CK(cudaMemcpyAsync(ctl, ctx->h_ctl, sizeof(Control), cudaMemcpyHostToDevice, st));
+
+    // ---- level 0: basic schedules -----------------------------------------------------------------
+    if (V > 0) {
+        k_basic<TT, 0><<<nblk(V, WARPS_PER_BLOCK), WARPS_PER_BLOCK * 32, 0, st>>>(d, tt, ls.lv[0], len0, ctx->S0.as<int>(), nullptr, ctl, dstats);
+        scan_dev(ctx, InArray<int>{ctx->S0.as<int>(), nullptr, V}, ctx->s0pos.as<i64>(),
+                 FinCountI64{&ctl->n_sch[0], ls.lv[0].cap_sch, &ctl->need_sch[0], &ctl->overflow, OVF_SCH});
+        k_basic<TT, 1><<<nblk(V, WARPS_PER_BLOCK), WARPS_PER_BLOCK * 32, 0, st>>>(d, tt, ls.lv[0], len0, ctx->S0.as<int>(),
+                                                                               ctx->s0pos.as<i64>(), ctl, dstats);
+        ctx->n_launches += 2;
+    }
+    // ---- level-1 tasks: reachability screen ---------------------------------------------------------
+    const i64 n_screen = (i64)V * Q;
+    if (n_screen > 0) {
+        k_screen<TT><<<std::min((i64)G * 4, (n_screen + 255) / 256), 256, 0, st>>>(d, tt, ctx->flag8.as<uint8_t>(), n_screen);
+        scan_dev(ctx, InArray<uint8_t>{ctx->flag8.as<uint8_t>(), nullptr, n_screen}, ctx->pos.as<i64>(),
+                 FinCountInt{&ctl->n_tasks[0], ctx->cap_tasks, &ctl->need_tasks, &ctl->overflow, OVF_TASKS});
+        k_tasks_from_screen<<<std::min((i64)G * 4, (n_screen + 255) / 256), 256, 0, st>>>(
+            d, ctx->flag8.as<uint8_t>(), ctx->pos.as<i64>(), n_screen, ctl, len0, ctx->S0.as<int>(), ctx->task_veh[0].as<int>(),
+            ctx->task_base[0].as<int>(), ctx->task_q[0].as<int>(), ctx->task_nchunk[0].as<int>());
+        ctx->n_launches += 2;
+    }
+    // ---- levels 1..max_level ----------------------------------------------------------------------------
+    for (int k = 1; k <= max_level && n_screen > 0; k++) {
+        const int cur = (k - 1) & 1, nxt = k & 1;
+        int* tv = ctx->task_veh[cur].as<int>(); int* tb = ctx->task_base[cur].as<int>(); int* tq = ctx->task_q[cur].as<int>();
+        const Level& prev = ls.lv[k - 1];
+        const Level& lv = ls.lv[k];
+        i64* chunk0 = ctx->task_chunk0.as<i64>();
+        i64* cpos = ctx->chunk_pos.as<i64>();
+        scan_dev(ctx, InArray<int>{ctx->task_nchunk[cur].as<int>(), &ctl->n_tasks[cur], 0}, chunk0,
+                 FinCountInt{&ctl->n_chunks, ctx->cap_chunks, &ctl->need_chunks, &ctl->overflow, OVF_CHUNKS});
+        k_expand_chunks<<<G, 256, 0, st>>>(ctl, cur, chunk0, ctx->chunk_task.as<int>());
+        CK(cudaEventRecord(get_event(ctx, n_ev++), st));
+        k_eval<TT, 0><<<GE, WARPS_PER_BLOCK * 32, 0, st>>>(d, tt, prev, lv, len0, ctl, tv, tb, tq, chunk0, ctx->chunk_task.as<int>(),
+                                                          ctx->chunk_cnt.as<int>(), ctx->lane_cnt.as<uint8_t>(), nullptr, dstats);
+        CK(cudaEventRecord(get_event(ctx, n_ev++), st));
+        scan_dev(ctx, InArray<int>{ctx->chunk_cnt.as<int>(), &ctl->n_chunks, 0}, cpos,
+                 FinCountI64{&ctl->n_sch[k], lv.cap_sch, &ctl->need_sch[k], &ctl->overflow, OVF_SCH});
+        scan_dev(ctx, InTaskFeasible{ctl, cur, chunk0, cpos}, ctx->trip_pos.as<i64>(),
+                 FinCountInt{&ctl->n_trips[k], (i64)lv.cap_trips, &ctl->need_trips[k], &ctl->overflow, OVF_TRIPS});
+        k_compact_trips<<<G, 256, 0, st>>>(ctl, cur, tv, tb, tq, chunk0, cpos, ctx->trip_pos.as<i64>(), prev, lv, dstats);
+        CK(cudaEventRecord(get_event(ctx, n_ev++), st));
+        k_eval<TT, 1><<<GE, WARPS_PER_BLOCK * 32, 0, st>>>(d, tt, prev, lv, len0, ctl, tv, tb, tq, chunk0, ctx->chunk_task.as<int>(),
+                                                          ctx->chunk_cnt.as<int>(), ctx->lane_cnt.as<uint8_t>(), cpos, dstats);
+        CK(cudaEventRecord(get_event(ctx, n_ev++), st));
+        k_classify<<<G, WARPS_PER_BLOCK * 32, 0, st>>>(ctl, lv, V, sba);
+        ctx->n_launches += 5;
+        if (k == max_level) break;
+        // ---- candidates of size k+1 ---------------------------------------------------------------------
+        TripHash th; th.slots = ctx->hash.as<int>(); th.mask = 0;
+        if (k >= 2) {
+            unsigned sz = 64; while (sz < 2u * (unsigned)lv.cap_trips + 2u) sz <<= 1;
+            th.mask = sz - 1;
+            CK(cudaMemsetAsync(ctx->hash.p, 0xff, 4 * (size_t)sz, st));
+            k_hash_build<<<G, 256, 0, st>>>(ctl, lv, th);
+            ctx->n_launches++;
+        }
+        k_gen<0><<<GE, WARPS_PER_BLOCK * 32, 0, st>>>(ctl, nxt, ls.lv[1], lv, th, len0, ctx->row_cnt.as<int>(), nullptr, nullptr, nullptr,
+                                                     nullptr, nullptr, nullptr, nullptr);
+        scan_dev(ctx, InArray<int>{ctx->row_cnt.as<int>(), &ctl->n_trips[k], 0}, ctx->row_off.as<i64>(),
+                 FinCountInt{&ctl->n_tasks[nxt], ctx->cap_tasks, &ctl->need_tasks, &ctl->overflow, OVF_TASKS});
+        k_gen<1><<<GE, WARPS_PER_BLOCK * 32, 0, st>>>(ctl, nxt, ls.lv[1], lv, th, len0, nullptr, ctx->row_off.as<i64>(), ctx->tmp_j.as<int>(),
+                                                     ctx->tmp_q.as<int>(), ctx->task_veh[nxt].as<int>(), ctx->task_base[nxt].as<int>(),
+                                                     ctx->task_q[nxt].as<int>(), ctx->task_nchunk[nxt].as<int>());
+        ctx->n_launches += 2;
+    }
+    // ---- pool assembly --------------------------------------------------------------------------------
+    if (V > 0) {
+        LevelSet lsp = ls;
+        if (n_screen == 0) lsp.n = 1;
+        k_pool_veh_count<<<nblk(V, 256), 256, 0, st>>>(V, mode, lsp, ctl, ctx->veh_cnt.as<int>());
+        scan_dev(ctx, InArray<int>{ctx->veh_cnt.as<int>(), nullptr, V}, ctx->veh_off.as<i64>(), FinPoolEntries{ctl, pb.cap_ent, sba});
+        k_pool_meta_veh<<<nblk(V, 256), 256, 0, st>>>(d, lsp, len0, ctx->veh_off.as<i64>(), ctl, pb);
+        k_pool_meta_levels<<<G, 256, 0, st>>>(d, lsp, len0, ctx->veh_off.as<i64>(), ctl, pb);
+        scan_dev(ctx, InEntLen{pb.ent_tlen, ctl}, pb.trip_off, FinCountI64{&ctl->n_ptr, pb.cap_ptr, &ctl->need_ptr, &ctl->overflow, OVF_POOL});
+        scan_dev(ctx, InEntLen{pb.ent_slen, ctl}, pb.sche_off, FinCountI64{&ctl->n_pst, pb.cap_pst, &ctl->need_pst, &ctl->overflow, OVF_POOL});
+        k_pool_payload<TT><<<G * 2, 128, 0, st>>>(d, tt, lsp, ctl, pb);
+        ctx->n_launches += 4;
+    }
+    *n_ev_out = n_ev;
+    return AMOD_OK;
 }
 
 template <typename TT>
@@ -307,193 +439,53 @@ static int build_impl(amod_ctx* ctx, const amod_epoch* ep, int loc, amod_stats* 
     DEpoch d;
     CK(cudaEventRecord(ctx->ev0, st));
     CKR(upload_epoch(ctx, ep, loc, &d));
-    const int V = d.n_veh, Q = d.n_search, mode = d.mode;
+    const int V = d.n_veh, mode = d.mode;
     const int max_level = mode == AMOD_MODE_SBA ? 1 : d.cap + 4;
+    if (max_level > AMOD_MAX_TRIP) return ctx->fail(AMOD_E_LIMIT, "trip size limit");
+    // row stride of each level's schedule store: longest possible base schedule + 2 stops per level
+    int base_len = ep->reserved > 0 ? ep->reserved : 0;
+    if (mode == AMOD_MODE_OSP) base_len = std::max(d.cap, 1);
+    else if (base_len == 0) {
+        if (loc == AMOD_LOC_HOST) { for (int v = 0; v < V; v++) base_len = std::max(base_len, ep->veh_sche_off[v + 1] - ep->veh_sche_off[v]); }
+        else if (V > 0) {
+            std::vector<int> off((size_t)V + 1);
+            CK(cudaMemcpyAsync(off.data(), ep->veh_sche_off, 4 * ((size_t)V + 1), cudaMemcpyDeviceToHost, st));
+            CK(cudaStreamSynchronize(st));
+            for (int v = 0; v < V; v++) base_len = std::max(base_len, off[v + 1] - off[v]);
+        }
+    }
+    int stride[MAX_LEVELS];
+    for (int k = 0; k < MAX_LEVELS; k++) stride[k] = std::max(1, std::min(MAXS, base_len + 2 * k));
+
+    LevelSet ls; PoolBufs pb;
     size_t n_ev = 0;
-
-    CK(ctx->stats.ensure(sizeof(Stats)));
-    CK(cudaMemsetAsync(ctx->stats.p, 0, sizeof(Stats), st));
-    Stats* dstats = ctx->stats.as<Stats>();
-    LevelSet ls; memset(&ls, 0, sizeof ls);
-
-    // ---- level 0: basic schedules --------------------------------------------------------------
-    CK(ctx->len0.ensure(4 * (size_t)(V + 1))); CK(ctx->S0.ensure(4 * (size_t)(V + 1))); CK(ctx->words0.ensure(4 * (size_t)(V + 1)));
-    CK(ctx->pos.ensure(8 * (size_t)(V + 2)));
-    int* len0 = ctx->len0.as<int>();
-    i64 words0 = 0;
-    if (V > 0) {
-        k_basic<TT, 0><<<nblk(V, WARPS_PER_BLOCK), WARPS_PER_BLOCK * 32, 0, st>>>(d, tt, len0, ctx->S0.as<int>(), ctx->words0.as<int>(),
-                                                                               nullptr, nullptr, dstats);
-        ctx->n_launches++;
+    Control* h = ctx->h_ctl;
+    int attempt = 0;
+    for (;; attempt++) {
+        if (attempt > 24) return ctx->fail(AMOD_E_NOMEM, "pool build did not converge after %d regrow attempts", attempt);
+        CKR(ensure_buffers(ctx, V, (i64)V * d.n_search, max_level, stride, &ls, &pb));
+        CKR(enqueue_build(ctx, d, tt, max_level, ls, pb, &n_ev));
+        CK(cudaEventRecord(ctx->ev1, st));
+        CK(cudaMemcpyAsync(h, ctx->ctl.p, sizeof(Control), cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        CK(cudaGetLastError());
+        if (!h->overflow) break;
+        // regrow exactly what overflowed (with headroom) and rerun the epoch
+        auto grow = [](i64& cap, i64 need) { if (need > cap) cap = need + need / 2 + 1024; };
+        grow(ctx->cap_tasks, h->need_tasks); grow(ctx->cap_chunks, h->need_chunks);
+        for (int k = 0; k <= max_level; k++) { grow(ctx->cap_trips[k], h->need_trips[k]); grow(ctx->cap_sch[k], h->need_sch[k]); }
+        grow(ctx->cap_ent, h->need_ent); grow(ctx->cap_ptr, h->need_ptr); grow(ctx->cap_pst, h->need_pst);
+        if (ctx->cap_tasks > 0x7ffffff0 || ctx->cap_chunks > 0x7ffffff0) return ctx->fail(AMOD_E_LIMIT, "more than 2^31 candidates in one level");
     }
-    CKR(scan_excl<int>(ctx, ctx->words0.as<int>(), V, ctx->pos.as<i64>(), &words0));
-    CKR(alloc_level(ctx, 0, V, words0, V, &ls.lv[0]));
-    if (V > 0) {
-        CK(cudaMemcpyAsync(ls.lv[0].sch_off, ctx->pos.p, 8 * (size_t)V, cudaMemcpyDeviceToDevice, st));
-        k_basic<TT, 1><<<nblk(V, WARPS_PER_BLOCK), WARPS_PER_BLOCK * 32, 0, st>>>(d, tt, len0, ctx->S0.as<int>(), ctx->words0.as<int>(),
-                                                                               ls.lv[0].sch_off, ls.lv[0].sch, dstats);
-        k_level0_finish<<<nblk(V + 1, 256), 256, 0, st>>>(V, ctx->S0.as<int>(), ls.lv[0].trip_veh, ls.lv[0].nfeas, ls.lv[0].rot,
-                                                        ls.lv[0].veh_start);
-        ctx->n_launches += 2;
-    }
-    ls.n = 1;
-
-    // ---- level-1 tasks: reachability screen -----------------------------------------------------
-    const i64 n_screen = (i64)V * Q;
-    i64 n_tasks = 0;
-    int cur = 0;
-    CK(ctx->flag8.ensure((size_t)std::max(n_screen, (i64)1)));
-    CK(ctx->pos.ensure(8 * (size_t)(n_screen + 2)));
-    if (n_screen > 0) {
-        k_screen<TT><<<nblk(n_screen, 256), 256, 0, st>>>(d, tt, ctx->flag8.as<uint8_t>(), n_screen);
-        ctx->n_launches++;
-    }
-    CKR(scan_excl<uint8_t>(ctx, ctx->flag8.as<uint8_t>(), n_screen, ctx->pos.as<i64>(), &n_tasks));
-    if (n_tasks > 0x7fffffff) return ctx->fail(AMOD_E_LIMIT, "too many size-1 candidates");
-    auto ensure_tasks = [&](int which, i64 n) -> int {
-        size_t b = 4 * (size_t)std::max(n, (i64)1);
-        CK(ctx->task_veh[which].ensure(b)); CK(ctx->task_base[which].ensure(b)); CK(ctx->task_q[which].ensure(b));
-        return AMOD_OK;
-    };
-    CKR(ensure_tasks(cur, n_tasks));
-    if (n_tasks > 0) {
-        k_tasks_from_screen<<<nblk(n_screen, 256), 256, 0, st>>>(d, ctx->flag8.as<uint8_t>(), ctx->pos.as<i64>(), n_screen,
-                                                               ctx->task_veh[cur].as<int>(), ctx->task_base[cur].as<int>(),
-                                                               ctx->task_q[cur].as<int>());
-        ctx->n_launches++;
-    }
-    i64 total_tasks = 0, total_sches = 0;
-    int levels_done = 0;
-    bool level_overflow = false;
-
-    // ---- levels 1..cap+4 --------------------------------------------------------------------------
-    for (int k = 1; k <= max_level && n_tasks > 0; k++) {
-        const int nt = (int)n_tasks;
-        total_tasks += nt;
-        int* tv = ctx->task_veh[cur].as<int>(); int* tb = ctx->task_base[cur].as<int>(); int* tq = ctx->task_q[cur].as<int>();
-        CK(ctx->task_nfeas.ensure(4 * (size_t)nt)); CK(ctx->task_cost.ensure(8 * (size_t)nt));
-        CK(ctx->words.ensure(4 * (size_t)nt)); CK(ctx->flag8.ensure((size_t)nt));
-        CK(ctx->pos.ensure(8 * (size_t)(nt + 2))); CK(ctx->pos2.ensure(8 * (size_t)(nt + 2)));
-        const Level& prev = ls.lv[k - 1];
-        Level curlv; memset(&curlv, 0, sizeof curlv);
-        const int eval_blocks = std::min(nblk(nt, WARPS_PER_BLOCK), ctx->n_sm * 8);
-        CK(cudaEventRecord(get_event(ctx, n_ev++), st));
-        k_eval<TT, 0><<<eval_blocks, WARPS_PER_BLOCK * 32, 0, st>>>(d, tt, prev, len0, nt, tv, tb, tq, ctx->task_nfeas.as<int>(),
-                                                                   ctx->task_cost.as<double>(), nullptr, curlv, dstats);
-        CK(cudaEventRecord(get_event(ctx, n_ev++), st));
-        k_task_flags<<<nblk(nt, 256), 256, 0, st>>>(nt, ctx->task_nfeas.as<int>(), tv, len0, k, ctx->flag8.as<uint8_t>(),
-                                                  ctx->words.as<int>(), dstats);
-        ctx->n_launches += 2;
-        i64 n_trips = 0, n_words = 0;
-        CKR(scan_excl<uint8_t>(ctx, ctx->flag8.as<uint8_t>(), nt, ctx->pos.as<i64>(), nullptr));
-        CK(cudaMemcpyAsync(&n_trips, ctx->total.p, 8, cudaMemcpyDeviceToHost, st));
-        CKR(scan_excl<int>(ctx, ctx->words.as<int>(), nt, ctx->pos2.as<i64>(), &n_words));   // synchronises both copies
-        CKR(alloc_level(ctx, k, (int)n_trips, n_words, V, &curlv));
-        levels_done = k;
-        total_sches += n_words;  // converted to schedules below via stats
-        k_compact_trips<<<nblk(nt, 256), 256, 0, st>>>(nt, ctx->task_nfeas.as<int>(), ctx->task_cost.as<double>(), tv, tb, tq,
-                                                     ctx->pos.as<i64>(), ctx->pos2.as<i64>(), prev, curlv);
-        k_veh_start<<<nblk(n_trips + 1, 256), 256, 0, st>>>((int)n_trips, V, curlv.trip_veh, curlv.veh_start);
-        ctx->n_launches += 2;
-        if (n_trips > 0) {
-            CK(cudaEventRecord(get_event(ctx, n_ev++), st));
-            k_eval<TT, 1><<<eval_blocks, WARPS_PER_BLOCK * 32, 0, st>>>(d, tt, prev, len0, nt, tv, tb, tq, ctx->task_nfeas.as<int>(),
-                                                                       ctx->task_cost.as<double>(), ctx->pos.as<i64>(), curlv, dstats);
-            CK(cudaEventRecord(get_event(ctx, n_ev++), st));
-            ctx->n_launches++;
-        }
-        ls.lv[k] = curlv; ls.n = k + 1;
-        n_tasks = 0;
-        if (n_trips == 0) break;
-        if (k == max_level) { if (mode != AMOD_MODE_SBA) level_overflow = true; break; }
-        if (k + 1 > AMOD_MAX_TRIP) return ctx->fail(AMOD_E_LIMIT, "trip size limit");
-        // ---- candidates of size k+1 -----------------------------------------------------------------
-        TripHash th; th.slots = nullptr; th.mask = 0;
-        if (k >= 2) {
-            unsigned sz = 64; while (sz < 2u * (unsigned)n_trips + 2u) sz <<= 1;
-            CK(ctx->hash.ensure(4 * (size_t)sz));
-            CK(cudaMemsetAsync(ctx->hash.p, 0xff, 4 * (size_t)sz, st));
-            th.slots = ctx->hash.as<int>(); th.mask = sz - 1;
-            k_hash_build<<<nblk(n_trips, 256), 256, 0, st>>>(curlv, th);
-            ctx->n_launches++;
-        }
-        CK(ctx->row_cnt.ensure(4 * (size_t)n_trips)); CK(ctx->row_off.ensure(8 * (size_t)(n_trips + 2)));
-        k_gen<0><<<nblk(n_trips, WARPS_PER_BLOCK), WARPS_PER_BLOCK * 32, 0, st>>>(ls.lv[1], curlv, th, ctx->row_cnt.as<int>(), nullptr,
-                                                                                nullptr, nullptr, nullptr);
-        ctx->n_launches++;
-        i64 n_next = 0;
-        CKR(scan_excl<int>(ctx, ctx->row_cnt.as<int>(), n_trips, ctx->row_off.as<i64>(), &n_next));
-        if (n_next > 0x7fffffff) return ctx->fail(AMOD_E_LIMIT, "too many size-%d candidates", k + 1);
-        if (n_next > 0) {
-            size_t b = 4 * (size_t)n_next;
-            CK(ctx->tmp_j.ensure(b)); CK(ctx->tmp_q.ensure(b)); CK(ctx->tmp_row.ensure(b));
-            CKR(ensure_tasks(cur ^ 1, n_next));
-            k_gen<1><<<nblk(n_trips, WARPS_PER_BLOCK), WARPS_PER_BLOCK * 32, 0, st>>>(ls.lv[1], curlv, th, nullptr, ctx->row_off.as<i64>(),
-                                                                                    ctx->tmp_j.as<int>(), ctx->tmp_q.as<int>(),
-                                                                                    ctx->tmp_row.as<int>());
-            k_gen_rank<<<nblk(n_next, 256), 256, 0, st>>>(n_next, ctx->row_off.as<i64>(), ctx->tmp_j.as<int>(), ctx->tmp_q.as<int>(),
-                                                        ctx->tmp_row.as<int>(), curlv.trip_veh, k == 1 ? 1 : 0,
-                                                        ctx->task_veh[cur ^ 1].as<int>(), ctx->task_base[cur ^ 1].as<int>(),
-                                                        ctx->task_q[cur ^ 1].as<int>());
-            ctx->n_launches += 2;
-            cur ^= 1;
-        }
-        n_tasks = n_next;
-    }
-
-    // ---- pool assembly ------------------------------------------------------------------------------
-    i64 P = 0;
-    i64 sba_base = 0;
-    CK(ctx->veh_off.ensure(8 * (size_t)(V + 2)));
-    if (mode == AMOD_MODE_SBA) {
-        sba_base = ls.n > 1 ? ls.lv[1].n_trips : 0;
-        P = sba_base + V;
-    } else {
-        CK(ctx->veh_cnt.ensure(4 * (size_t)(V + 1)));
-        if (V > 0) { k_pool_veh_count<<<nblk(V, 256), 256, 0, st>>>(V, mode, ls, ctx->veh_cnt.as<int>()); ctx->n_launches++; }
-        CKR(scan_excl<int>(ctx, ctx->veh_cnt.as<int>(), V, ctx->veh_off.as<i64>(), &P));
-    }
-    {
-        size_t n = (size_t)std::max(P, (i64)1);
-        CK(ctx->ent_veh.ensure(4 * n)); CK(ctx->ent_kind.ensure(4 * n)); CK(ctx->ent_nfeas.ensure(4 * n)); CK(ctx->ent_tlen.ensure(4 * n));
-        CK(ctx->ent_slen.ensure(4 * n)); CK(ctx->ent_src.ensure(4 * n)); CK(ctx->ent_trip.ensure(4 * n)); CK(ctx->ent_cost.ensure(8 * n));
-        CK(ctx->ent_delay.ensure(8 * n)); CK(ctx->trip_off.ensure(8 * (n + 1))); CK(ctx->sche_off.ensure(8 * (n + 1)));
-    }
-    i64 NT = 0, NS = 0;
-    if (P > 0) {
-        if (V > 0) {
-            k_pool_meta_veh<<<nblk(V, 256), 256, 0, st>>>(d, ls, len0, ctx->veh_off.as<i64>(), sba_base, ctx->ent_veh.as<int>(),
-                                                        ctx->ent_kind.as<int>(), ctx->ent_nfeas.as<int>(), ctx->ent_tlen.as<int>(),
-                                                        ctx->ent_slen.as<int>(), ctx->ent_src.as<int>(), ctx->ent_trip.as<int>(), dstats);
-            ctx->n_launches++;
-        }
-        for (int k = 1; k < ls.n; k++) {
-            if (ls.lv[k].n_trips == 0) continue;
-            k_pool_meta_level<<<nblk(ls.lv[k].n_trips, 256), 256, 0, st>>>(d, ls, k, len0, ctx->veh_off.as<i64>(), ctx->ent_veh.as<int>(),
-                                                                         ctx->ent_kind.as<int>(), ctx->ent_nfeas.as<int>(),
-                                                                         ctx->ent_tlen.as<int>(), ctx->ent_slen.as<int>(),
-                                                                         ctx->ent_src.as<int>(), ctx->ent_trip.as<int>());
-            ctx->n_launches++;
-        }
-        CKR(scan_excl<int>(ctx, ctx->ent_tlen.as<int>(), P, ctx->trip_off.as<i64>(), nullptr));
-        CK(cudaMemcpyAsync(&NT, ctx->total.p, 8, cudaMemcpyDeviceToHost, st));
-        CKR(scan_excl<int>(ctx, ctx->ent_slen.as<int>(), P, ctx->sche_off.as<i64>(), &NS));
-        CK(ctx->trip_req.ensure(4 * (size_t)std::max(NT, (i64)1))); CK(ctx->sche_code.ensure(4 * (size_t)std::max(NS, (i64)1)));
-        k_pool_payload<TT><<<nblk(P, 128), 128, 0, st>>>(d, tt, ls, P, ctx->ent_veh.as<int>(), ctx->ent_src.as<int>(), ctx->ent_trip.as<int>(),
-                                                       ctx->trip_off.as<i64>(), ctx->sche_off.as<i64>(), ctx->trip_req.as<int>(),
-                                                       ctx->sche_code.as<int>(), ctx->ent_cost.as<double>(), ctx->ent_delay.as<double>());
-        ctx->n_launches++;
-    } else {
-        CK(cudaMemsetAsync(ctx->trip_off.p, 0, 8, st)); CK(cudaMemsetAsync(ctx->sche_off.p, 0, 8, st));
-    }
-    CK(cudaEventRecord(ctx->ev1, st));
-    Stats hs;
-    CK(cudaMemcpyAsync(&hs, dstats, sizeof hs, cudaMemcpyDeviceToHost, st));
-    CK(cudaStreamSynchronize(st));
-    CK(cudaGetLastError());
-    if (hs.flags & 1ull) return ctx->fail(AMOD_E_LIMIT, "a vehicle schedule exceeds the compiled stop/capacity limits");
+    ctx->n_attempts = attempt + 1;
+    if (h->stats.flags & 1ull) return ctx->fail(AMOD_E_LIMIT, "a vehicle schedule exceeds the compiled stop/capacity limits");
+    const i64 P = V > 0 ? h->n_ent : 0, NT = V > 0 ? h->n_ptr : 0, NS = V > 0 ? h->n_pst : 0;
     ctx->pool_entries = P; ctx->pool_trip_reqs = NT; ctx->pool_stops = NS;
     ctx->pool_valid = true;
+    if (V == 0) { CK(cudaMemsetAsync(ctx->trip_off.p, 0, 8, st)); CK(cudaMemsetAsync(ctx->sche_off.p, 0, 8, st)); CK(cudaStreamSynchronize(st)); }
+    int levels_done = 0;
+    i64 total_tasks = 0;
+    for (int k = 1; k <= max_level; k++) if (h->n_trips[k] > 0) levels_done = k;
     if (out_stats) {
         memset(out_stats, 0, sizeof *out_stats);
         float ms = 0.f;
@@ -503,19 +495,21 @@ static int build_impl(amod_ctx* ctx, const amod_epoch* ep, int loc, amod_stats* 
         for (size_t i = 0; i + 1 < n_ev; i += 2) { float x = 0.f; cudaEventElapsedTime(&x, ctx->ev_pool[i], ctx->ev_pool[i + 1]); me += x; }
         out_stats->ms_eval = me;
         out_stats->n_eval_launches = (int)(n_ev / 2);
+        const i64 n_screen = (i64)V * d.n_search;
         out_stats->n_screens = n_screen;
-        out_stats->n_evals = (int64_t)hs.n_evals;
+        out_stats->n_evals = (int64_t)h->stats.n_evals;
         // lookups as the reference would do them: evaluations + one per screen + the cost walk of the
         // basic/current pairs + the delay walk of every pool entry
-        out_stats->n_lookups = (int64_t)hs.n_lookups + n_screen + NS;
+        out_stats->n_lookups = (int64_t)h->stats.n_lookups + n_screen + NS;
         out_stats->n_entries = P;
-        out_stats->n_tasks = total_tasks;
+        out_stats->n_tasks = (int64_t)h->stats.n_tasks;
         out_stats->n_levels = levels_done;
         out_stats->n_kernel_launches = ctx->n_launches;
-        out_stats->n_sches_stored = (int64_t)hs.n_sches;
+        out_stats->n_sches_stored = (int64_t)h->stats.n_sches;
+        out_stats->reserved = ctx->n_attempts;
     }
-    (void)total_sches;
-    if (level_overflow)
+    (void)total_tasks;
+    if (mode != AMOD_MODE_SBA && h->n_trips[max_level] > 0)
         return ctx->fail(AMOD_E_LEVELS, "a feasible trip of size cap+4=%d exists; the reference raises IndexError here "
                                         "(dispatch_osp.py:8,226)", max_level);
     return AMOD_OK;

@@ -35,24 +35,51 @@ struct Table {
 
 // One trip-size level of the per-vehicle feasible-trip table (FEASIBLE_TRIP_TABLE[veh][k-1],
 // dispatch_osp.py:8) flattened over all vehicles.  Level 0 holds the basic schedules.
-// The feasible schedules of trip t are nfeas[t] rows of `len` codes starting at sch[sch_off[t]];
-// the reference's list order (records newest-first, then the rest; scheduling.py:31-36) is
-// memory order rotated by rot[t]:  logical p -> row (p + rot) % nfeas.
+// Feasible schedules of trip t are rows [s0[t], s0[t]+nfeas[t]) of the level's schedule store
+// (fixed `stride` codes per row), kept in ENCOUNTER order (the reference's loop order); the
+// reference's list order (running-minimum records newest-first, then the rest; scheduling.py:31-36)
+// is the permutation order[s0[t] + p] -> row offset within the trip.
 struct Level {
     int k;
-    int n_trips;
+    int stride;          // codes per schedule row (>= longest schedule of this level)
+    int cap_trips;
+    i64 cap_sch;
     int* trip_veh;
-    int* trip_req;     // [n_trips * k] ascending request indices
-    i64* sch_off;
+    int* trip_req;       // [n_trips * k] ascending request indices
+    i64* s0;             // first schedule row of the trip
     int* nfeas;
-    int* rot;
-    double* cost;      // min cost (scheduling.py:33)
-    code_t* sch;
-    int* veh_start;    // [n_veh+1] trips of vehicle v are [veh_start[v], veh_start[v+1])  (OSP modes)
+    double* cost;        // min cost (scheduling.py:33)
+    code_t* sch;         // [n_sch * stride]
+    double* sch_cost;    // [n_sch] cost of each feasible schedule (encounter order)
+    int* order;          // [n_sch] list position -> encounter position within its trip
+    int* veh_start;      // [n_veh+1] trips of vehicle v are [veh_start[v], veh_start[v+1])  (OSP modes)
 };
+
+#define MAX_LEVELS (AMOD_MAX_TRIP + 1)
 
 struct Stats {            // device counters
     unsigned long long n_screens, n_evals, n_lookups, n_sches, n_tasks, flags;
+};
+
+// Device-resident control block: every size the level-synchronous pipeline produces lives here, so
+// the host never has to synchronise between phases.  A kernel that would exceed a buffer capacity
+// records the size it needs, raises `overflow` and clamps; the host regrows and reruns the epoch.
+#define OVF_TASKS 1ull
+#define OVF_CHUNKS 2ull
+#define OVF_TRIPS 4ull
+#define OVF_SCH 8ull
+#define OVF_POOL 16ull
+struct Control {
+    int n_tasks[2];
+    int n_chunks;
+    int n_trips[MAX_LEVELS];
+    i64 n_sch[MAX_LEVELS];
+    i64 n_ent, n_ptr, n_pst;
+    unsigned long long overflow;
+    i64 need_tasks, need_chunks, need_trips[MAX_LEVELS], need_sch[MAX_LEVELS], need_ent, need_ptr, need_pst;
+    int max_level_nonempty;
+    int pad;
+    Stats stats;
 };
 
 __device__ __forceinline__ void stop_info(const DEpoch& ep, int v, int code, int& node, double& ddl, int& pod) {

@@ -1,16 +1,21 @@
 // eval.cuh — the insertion search (scheduling.py:13-98) as a warp-cooperative kernel.
 //
-// One warp owns one compute_schedule() call = one task (vehicle v, base trip, inserted request q).
-// Work items are (sub_sche s, pick-up index i) pairs in the reference's loop order, 32 per warp
-// step; a lane walks the drop-off index j sequentially with incremental partial sums, which is
-// exactly the reference's inner loop and lets its early exits (scheduling.py:41-44) be applied
-// per lane (j-loop breaks) and by ballot (viol==3 ends the i-loop of that sub_sche).
-// All arithmetic is float64, accumulated left to right in the reference's order, so costs and
-// every comparison are bit-identical to the reference.
+// A *task* is one compute_schedule() call (vehicle v, base trip, inserted request q); it is cut
+// into *chunks* of whole base schedules so that one warp step covers one chunk: work items are
+// (sub_sche s, pick-up index i) pairs in the reference's loop order, one per lane, and a lane walks
+// the drop-off index j sequentially with incremental partial sums.  That is exactly the reference's
+// inner loop, so its early exits (scheduling.py:41-44) apply per lane (j-loop breaks) and by ballot
+// (viol==3 ends the i-loop of that sub_sche).  Chunks of one task run on different warps: heavy
+// tasks (thousands of base schedules) no longer serialise on one warp.
+// All arithmetic is float64 accumulated left to right in the reference's order: costs and every
+// comparison are bit-identical to the reference.
+//
+// MODE 0 counts the feasible insertions of every lane (-> offsets by prefix sum);
+// MODE 1 re-walks only lanes that found something and writes schedules + costs in encounter order.
 #pragma once
 #include "common.cuh"
 
-#define STAGE_SLOTS 128   // stops staged per warp step: nsub*l <= 32 + 2*l <= 108
+#define STAGE_SLOTS 96    // stops staged per warp step: nsub*l <= 32 (whole schedules) or l <= 38
 
 struct WarpStage {
     double ddl[STAGE_SLOTS];
@@ -19,28 +24,26 @@ struct WarpStage {
     signed char pod[STAGE_SLOTS];
 };
 
-struct LaneOut {
-    unsigned long long feas;   // bit j set: insertion (i, j) feasible
-    unsigned long long rec;    // bit j set: it was a new running minimum (scheduling.py:31-34)
-    double lmin;               // min cost over this lane's feasible insertions
-    int evals, lookups;        // as the reference would have executed them
-};
+__device__ __forceinline__ int chunk_group(int l) { return l + 1 >= 32 ? 1 : 32 / (l + 1); }   // base schedules per chunk
+
+struct LaneCount { int n, evals, lookups; };
 
 // Walk j = i+1 .. for one (sub_sche, i).  `A` = accumulated time at the inserted pick-up.
-// CLASSIFY: also mark running-minimum records given the minimum seen before this lane.
-template <typename TT, bool CLASSIFY>
-__device__ __forceinline__ void walk_j(const Table<TT>& tt, const int* __restrict__ nd, const double* __restrict__ ddl, int l,
-                                       int i, double A, int P, int D, double cld, double T, unsigned long long fullmask,
-                                       double running, LaneOut& o) {
+// WRITE: emit each feasible schedule (codes + cost) to consecutive rows starting at `row`.
+template <typename TT, bool WRITE>
+__device__ __forceinline__ void walk_j(const Table<TT>& tt, const int* __restrict__ nd, const double* __restrict__ ddl,
+                                       const code_t* __restrict__ codes, int l, int i, double A, int P, int D, int q,
+                                       double cld, double T, unsigned long long fullmask, LaneCount& o, i64 row,
+                                       code_t* __restrict__ out_sch, double* __restrict__ out_cost, int stride) {
     // capacity (scheduling.py:74-77): (i,j) is over capacity iff fullmask has a bit in [i, j-1]
     unsigned long long hi = fullmask >> (i + 1);
-    int b = hi ? (i + __ffsll((long long)hi)) : 64;    // lowest set bit above i; j <= b is capacity-feasible
+    const int b = hi ? (i + __ffsll((long long)hi)) : 64;     // lowest set bit above i; j <= b is capacity-feasible
     double B = A;
     int nodeB = P;
     for (int j = i + 1;; j++) {
         o.evals++;
         double C = B + tt(nodeB, D);
-        if (T + C > cld) { o.lookups += j + 1; break; }            // viol 2 -> break (scheduling.py:41)
+        if (T + C > cld) { o.lookups += j + 1; break; }              // viol 2 -> break (scheduling.py:41)
         int node = D;
         bool ok = true;
         for (int m = j - 1; m < l; m++) {
@@ -50,88 +53,94 @@ __device__ __forceinline__ void walk_j(const Table<TT>& tt, const int* __restric
         }
         if (ok) {
             o.lookups += l + 2;
-            o.feas |= 1ull << j;
-            if (C < o.lmin) o.lmin = C;
-            if (CLASSIFY) { if (C < running) { running = C; o.rec |= 1ull << j; } }
+            o.n++;
+            if (WRITE) {
+                code_t* dst = out_sch + row * stride;
+                int w = 0;
+                for (int m = 0; m < i; m++) dst[w++] = codes[m];
+                dst[w++] = (code_t)(2 * q);
+                for (int m = i; m < j - 1; m++) dst[w++] = codes[m];
+                dst[w++] = (code_t)(2 * q + 1);
+                for (int m = j - 1; m < l; m++) dst[w++] = codes[m];
+                out_cost[row] = C;
+                row++;
+            }
         }
         if (j == l + 1) break;
-        if (j == b) { o.evals++; break; }                         // next j is over capacity: viol 1 -> break
-        B += tt(nodeB, nd[j - 1]);                                // extend the pick-up side over base stop j-1
+        if (j == b) { o.evals++; break; }                           // next j is over capacity: viol 1 -> break
+        B += tt(nodeB, nd[j - 1]);                                  // extend the pick-up side over base stop j-1
         nodeB = nd[j - 1];
         if (T + B > ddl[j - 1]) { o.evals++; o.lookups += j + 1; break; }   // viol 4 at (i, j+1) -> break
     }
 }
 
-// MODE 0: count feasible schedules + min cost per task.  MODE 1: materialise them in list order.
 template <typename TT, int MODE>
 __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32)
-k_eval(DEpoch ep, Table<TT> tt, Level prev, const int* __restrict__ len0, int n_tasks,
+k_eval(DEpoch ep, Table<TT> tt, Level prev, Level cur, const int* __restrict__ len0, const Control* __restrict__ ctl,
        const int* __restrict__ task_veh, const int* __restrict__ task_base, const int* __restrict__ task_q,
-       int* __restrict__ task_nfeas, double* __restrict__ task_cost,
-       const i64* __restrict__ task_trip /* exclusive scan of feasible flags */, Level cur, Stats* stats) {
+       const i64* __restrict__ task_chunk0, const int* __restrict__ chunk_task,
+       int* __restrict__ chunk_cnt, uint8_t* __restrict__ lane_cnt, const i64* __restrict__ chunk_pos, Stats* stats) {
     __shared__ WarpStage stage_all[WARPS_PER_BLOCK];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     WarpStage& st = stage_all[wib];
     const int warp0 = blockIdx.x * WARPS_PER_BLOCK + wib, nwarps = gridDim.x * WARPS_PER_BLOCK;
     unsigned long long acc_evals = 0, acc_lookups = 0;
     const double T = ep.T;
+    const int n_chunks = ctl->overflow ? 0 : ctl->n_chunks;
 
-    for (int task = warp0; task < n_tasks; task += nwarps) {
-        if (MODE == 1 && task_nfeas[task] == 0) continue;
+    for (int c = warp0; c < n_chunks; c += nwarps) {
+        if (MODE == 1 && chunk_cnt[c] == 0) continue;
+        const int task = chunk_task[c];
         const int v = task_veh[task], base = task_base[task], q = task_q[task];
         const int l = len0[v] + 2 * prev.k;
-        if (l + 2 > MAXS) {   // compiled stop limit: reported as AMOD_E_LIMIT by the host
-            if (lane == 0) { atomicOr(&stats->flags, 1ull); if (MODE == 0) { task_nfeas[task] = 0; task_cost[task] = DINF; } }
+        if (l + 2 > MAXS || l + 2 > cur.stride) {   // compiled stop limit: reported as AMOD_E_LIMIT by the host
+            if (MODE == 0) {
+                if (lane == 0) { atomicOr(&stats->flags, 1ull); chunk_cnt[c] = 0; }
+                lane_cnt[(i64)c * 64 + lane] = 0; lane_cnt[(i64)c * 64 + 32 + lane] = 0;
+            }
             continue;
         }
-        const int S = prev.nfeas[base], rot = prev.rot[base];
-        const code_t* __restrict__ sch = prev.sch + prev.sch_off[base];
+        const int S = prev.nfeas[base];
+        const i64 s0 = prev.s0[base];
+        const int g = chunk_group(l);
+        const int s_begin = (int)(c - task_chunk0[task]) * g;
+        const int s_end = min(S, s_begin + g);
         const int P = ep.onid[q], D = ep.dnid[q];
         const double clp = ep.clp[q], cld = ep.cld[q];
         const int nid = ep.veh_nid[v], load = ep.veh_load[v], cap = ep.cap;
         const double t0 = ep.veh_t[v];
-        const int items = S * (l + 1);
+        const int items = (s_end - s_begin) * (l + 1);
+        int dead_s = -1, cnt_total = 0;
+        i64 row_base = MODE == 1 ? chunk_pos[c] : 0;
 
-        int trip = 0, nfeas_total = 0;
-        code_t* __restrict__ out = nullptr;
-        if (MODE == 1) {
-            trip = (int)task_trip[task];
-            nfeas_total = task_nfeas[task];
-            out = cur.sch + cur.sch_off[trip];
-        }
-        double run_min = DINF;
-        int n_rec = 0, n_non = 0, n_feas = 0, dead_s = -1;
-
-        for (int it0 = 0; it0 < items; it0 += 32) {
+        for (int it0 = 0; it0 < items; it0 += 32) {        // one step unless l+1 > 32
             const int it = it0 + lane;
             const bool valid = it < items;
-            const int s = valid ? it / (l + 1) : -1;
-            const int i = valid ? it - s * (l + 1) : 0;
-            const int s_first = it0 / (l + 1);
-            const int last_it = min(items, it0 + 32) - 1;
-            const int s_last = last_it / (l + 1);
+            const int sl = valid ? it / (l + 1) : -1;      // sub_sche within the chunk
+            const int i = valid ? it - sl * (l + 1) : 0;
+            const int sl_first = it0 / (l + 1);
+            const int sl_last = (min(items, it0 + 32) - 1) / (l + 1);
             __syncwarp();
-            if (l > 0) {   // stage the stops of sub_sches s_first..s_last (logical order -> rotated rows)
-                const int ne = (s_last - s_first + 1) * l;
+            if (l > 0) {   // stage the stops of the step's base schedules (list order -> stored row)
+                const int ne = (sl_last - sl_first + 1) * l;
                 for (int e = lane; e < ne; e += 32) {
-                    int ss = s_first + e / l, m = e - (e / l) * l;
-                    int row = ss + rot; if (row >= S) row -= S;
-                    int code = sch[(i64)row * l + m];
+                    const int ss = sl_first + e / l, m = e - (e / l) * l;
+                    const i64 row = s0 + prev.order[s0 + s_begin + ss];
+                    const int code = prev.sch[row * prev.stride + m];
                     int node, pod; double ddl;
                     stop_info(ep, v, code, node, ddl, pod);
                     st.node[e] = node; st.ddl[e] = ddl; st.pod[e] = (signed char)pod; st.code[e] = (code_t)code;
                 }
             }
             __syncwarp();
-            const int eb = valid ? (s - s_first) * l : 0;
+            const int eb = valid ? (sl - sl_first) * l : 0;
             const int* nd = st.node + eb;
             const double* ddl = st.ddl + eb;
 
             // capacity profile of the base schedule and accumulated time at the inserted pick-up
             unsigned long long fullmask = 0;
-            bool basebad = false;
+            bool basebad = false, stop3 = false, cap1 = false;
             double A = 0.0;
-            bool stop3 = false, cap1 = false;
             if (valid) {
                 int run = load;
                 if (run >= cap) fullmask |= 1ull;
@@ -147,61 +156,37 @@ k_eval(DEpoch ep, Table<TT> tt, Level prev, const int* __restrict__ len0, int n_
                 cap1 = basebad || ((fullmask >> i) & 1ull);                              // viol 1 at j = i+1
                 stop3 = !cap1 && (T + A > clp);                                          // viol 3 (scheduling.py:43)
             }
-            // viol==3 ends the i-loop of its sub_sche: later i of the same s are never evaluated
+            // viol==3 ends the i-loop of its sub_sche: later i of the same sub_sche are never evaluated
             const unsigned bal3 = __ballot_sync(FULL, stop3);
             const int lo = max(lane - i, 0);
             const unsigned same_s_lower = (lane > lo) ? (((1u << lane) - 1u) & ~((1u << lo) - 1u)) : 0u;
-            const bool dead = valid && ((bal3 & same_s_lower) != 0u || s == dead_s);
-            {   // carry to the next warp step if the last sub_sche continues there
-                const unsigned killed = __ballot_sync(FULL, valid && s == s_last && (stop3 || dead));
-                dead_s = killed ? s_last : -1;
+            const bool dead = valid && ((bal3 & same_s_lower) != 0u || sl == dead_s);
+            {   // carry to the next step if the last sub_sche continues there (only when l+1 > 32)
+                const unsigned killed = __ballot_sync(FULL, valid && sl == sl_last && (stop3 || dead));
+                dead_s = killed ? sl_last : -1;
             }
-
-            LaneOut o; o.feas = 0; o.rec = 0; o.lmin = DINF; o.evals = 0; o.lookups = 0;
             const bool live = valid && !dead;
-            if (live) {
-                if (cap1) { o.evals = 1; }
-                else if (stop3) { o.evals = 1; o.lookups = i + 1; }
-                else walk_j<TT, false>(tt, nd, ddl, l, i, A, P, D, cld, T, fullmask, 0.0, o);
-            }
+            LaneCount o; o.n = 0; o.evals = 0; o.lookups = 0;
             if (MODE == 0) {
-                acc_evals += o.evals; acc_lookups += o.lookups;
-                n_feas += __popcll(o.feas);
-                run_min = fmin(run_min, o.lmin);
-            } else {
-                // records need the minimum over everything evaluated before this lane, in loop order
-                const double incoming = fmin(run_min, warp_excl_min(o.lmin, lane));
-                LaneOut c; c.feas = 0; c.rec = 0; c.lmin = DINF; c.evals = 0; c.lookups = 0;
-                if (live && o.feas) walk_j<TT, true>(tt, nd, ddl, l, i, A, P, D, cld, T, fullmask, incoming, c);
-                const int nr = __popcll(c.rec), nn = __popcll(c.feas & ~c.rec);
-                int rec_before = n_rec + warp_excl_sum(nr, lane);
-                int non_before = n_non + warp_excl_sum(nn, lane);
-                unsigned long long f = c.feas;
-                while (f) {
-                    const int j = __ffsll((long long)f) - 1;
-                    f &= f - 1;
-                    // memory layout: non-records ascending from row 0, records descending from the last row;
-                    // the reference's list order is this rotated by n_non (see Level)
-                    const int row = ((c.rec >> j) & 1ull) ? (nfeas_total - 1 - rec_before++) : non_before++;
-                    code_t* dst = out + (i64)row * (l + 2);
-                    int w = 0;
-                    for (int m = 0; m < i; m++) dst[w++] = st.code[eb + m];
-                    dst[w++] = (code_t)(2 * q);
-                    for (int m = i; m < j - 1; m++) dst[w++] = st.code[eb + m];
-                    dst[w++] = (code_t)(2 * q + 1);
-                    for (int m = j - 1; m < l; m++) dst[w++] = st.code[eb + m];
+                if (live) {
+                    if (cap1) o.evals = 1;
+                    else if (stop3) { o.evals = 1; o.lookups = i + 1; }
+                    else walk_j<TT, false>(tt, nd, ddl, st.code + eb, l, i, A, P, D, q, cld, T, fullmask, o, 0, nullptr, nullptr, 0);
                 }
-                n_rec += warp_sum(nr);
-                n_non += warp_sum(nn);
-                run_min = fmin(run_min, warp_min(o.lmin));
+                acc_evals += o.evals; acc_lookups += o.lookups;
+                lane_cnt[(i64)c * 64 + it0 + lane] = (uint8_t)o.n;     // <= 64 items per chunk (l+1 <= 39)
+                cnt_total += o.n;
+            } else {
+                const int mine = lane_cnt[(i64)c * 64 + it0 + lane];
+                const int before = warp_excl_sum(mine, lane);
+                if (mine) walk_j<TT, true>(tt, nd, ddl, st.code + eb, l, i, A, P, D, q, cld, T, fullmask, o, row_base + before,
+                                           cur.sch, cur.sch_cost, cur.stride);
+                row_base += __shfl_sync(FULL, before + mine, 31);
             }
         }
         if (MODE == 0) {
-            n_feas = warp_sum(n_feas);
-            run_min = warp_min(run_min);
-            if (lane == 0) { task_nfeas[task] = n_feas; task_cost[task] = run_min; }
-        } else if (lane == 0) {
-            cur.rot[trip] = n_non;
+            cnt_total = warp_sum(cnt_total);
+            if (lane == 0) chunk_cnt[c] = cnt_total;
         }
     }
     if (MODE == 0) {

@@ -1,8 +1,10 @@
 // levels.cuh — everything around the insertion search: basic schedules (dispatch_osp.py:295-322),
 // reachability screen (:160 / dispatch_sba.py:59), ordered compaction of feasible tasks into the
-// next trip level, and candidate generation for trips of size k>=2 (:167-216).
+// next trip level, list-order classification (scheduling.py:31-36) and candidate generation for
+// trips of size k>=2 (:167-216).  All sizes come from the device-resident Control block.
 #pragma once
 #include "common.cuh"
+#include "eval.cuh"
 
 // ---------------------------------------------------------------------------------------------
 // Level 0: basic schedules.  One warp per vehicle.
@@ -31,11 +33,12 @@ __device__ __forceinline__ void unrank_perm(int p, int L, int* out /*positions*/
 
 template <typename TT, int MODE>
 __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32)
-k_basic(DEpoch ep, Table<TT> tt, int* __restrict__ len0, int* __restrict__ S0, int* __restrict__ words0,
-        const i64* __restrict__ sch_off, code_t* __restrict__ sch, Stats* stats) {
+k_basic(DEpoch ep, Table<TT> tt, Level lv0, int* __restrict__ len0, int* __restrict__ S0, const i64* __restrict__ s0pos,
+        const Control* __restrict__ ctl, Stats* stats) {
     const int lane = threadIdx.x & 31;
     const int v = blockIdx.x * WARPS_PER_BLOCK + (threadIdx.x >> 5);
     if (v >= ep.n_veh) return;
+    if (MODE == 1 && ctl->overflow) return;          // level-0 store overflowed
     const int s0 = ep.veh_sche_off[v], s1 = ep.veh_sche_off[v + 1];
     const int st = ep.veh_status[v];
     const bool perms = (ep.mode == AMOD_MODE_OSP) && st == 2;
@@ -43,8 +46,16 @@ k_basic(DEpoch ep, Table<TT> tt, int* __restrict__ len0, int* __restrict__ S0, i
     int L = 0;
     for (int k = s0; k < s1 && L < AMOD_MAX_STOPS; k++)
         if (!perms || ep.sche_onboard[k]) base[L++] = ep.sche_code[k];
-    code_t* out = MODE == 1 ? sch + sch_off[v] : nullptr;
-    if (MODE == 1 && lane == 0) for (int m = 0; m < L; m++) out[m] = (code_t)base[m];
+    const bool too_long = L > lv0.stride;
+    if (too_long) L = 0;
+    const i64 row0 = MODE == 1 ? s0pos[v] : 0;
+    if (MODE == 1 && lane == 0) {
+        code_t* out = lv0.sch + row0 * lv0.stride;
+        for (int m = 0; m < L; m++) out[m] = (code_t)base[m];
+        lv0.order[row0] = 0;
+        lv0.trip_veh[v] = v; lv0.nfeas[v] = S0[v]; lv0.s0[v] = row0; lv0.veh_start[v] = v;
+        if (v == 0) lv0.veh_start[ep.n_veh] = ep.n_veh;
+    }
     int count = 1;
     unsigned long long evals = 0, lookups = 0;
     if (perms && L >= 2 && L <= AMOD_MAX_CAP) {
@@ -82,25 +93,20 @@ k_basic(DEpoch ep, Table<TT> tt, int* __restrict__ len0, int* __restrict__ S0, i
             }
             const unsigned bal = __ballot_sync(FULL, ok);
             if (MODE == 1 && ok) {
-                code_t* dst = out + (i64)(count + __popc(bal & ((1u << lane) - 1u))) * L;
+                const int r = count + __popc(bal & ((1u << lane) - 1u));
+                code_t* dst = lv0.sch + (row0 + r) * lv0.stride;
                 for (int m = 0; m < L; m++) dst[m] = (code_t)base[pos[m]];
+                lv0.order[row0 + r] = r;
             }
             count += __popc(bal);
         }
     }
     if (MODE == 0) {
-        if (lane == 0) { len0[v] = L; S0[v] = count; words0[v] = count * L; }
+        if (lane == 0) { len0[v] = L; S0[v] = count; }
         evals = warp_sum(evals); lookups = warp_sum(lookups);
         if (lane == 0 && evals) { atomicAdd(&stats->n_evals, evals); atomicAdd(&stats->n_lookups, lookups); }
-        if (lane == 0 && (s1 - s0 > AMOD_MAX_STOPS || (perms && L > AMOD_MAX_CAP))) atomicOr(&stats->flags, 1ull);
+        if (lane == 0 && (too_long || s1 - s0 > AMOD_MAX_STOPS || (perms && L > AMOD_MAX_CAP))) atomicOr(&stats->flags, 1ull);
     }
-}
-
-// level-0 trip records: trip v = vehicle v
-__global__ void k_level0_finish(int n_veh, const int* __restrict__ S0, int* trip_veh, int* nfeas, int* rot, int* veh_start) {
-    int v = blockIdx.x * blockDim.x + threadIdx.x;
-    if (v < n_veh) { trip_veh[v] = v; nfeas[v] = S0[v]; rot[v] = 0; veh_start[v] = v; }
-    if (v == n_veh) veh_start[v] = n_veh;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -110,69 +116,128 @@ __global__ void k_level0_finish(int n_veh, const int* __restrict__ S0, int* trip
 // ---------------------------------------------------------------------------------------------
 template <typename TT>
 __global__ void k_screen(DEpoch ep, Table<TT> tt, uint8_t* __restrict__ flag, i64 n) {
-    i64 e = (i64)blockIdx.x * blockDim.x + threadIdx.x;
-    if (e >= n) return;
-    int v, s;
-    if (ep.mode == AMOD_MODE_SBA) { s = (int)(e / ep.n_veh); v = (int)(e - (i64)s * ep.n_veh); }
-    else { v = (int)(e / ep.n_search); s = (int)(e - (i64)v * ep.n_search); }
-    const int q = ep.search[s];
-    const double d = tt(ep.veh_nid[v], ep.onid[q]);
-    flag[e] = !(d + ep.veh_t[v] + ep.T > ep.clp[q]);
+    const i64 stride = (i64)gridDim.x * blockDim.x;
+    for (i64 e = (i64)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += stride) {
+        int v, s;
+        if (ep.mode == AMOD_MODE_SBA) { s = (int)(e / ep.n_veh); v = (int)(e - (i64)s * ep.n_veh); }
+        else { v = (int)(e / ep.n_search); s = (int)(e - (i64)v * ep.n_search); }
+        const int q = ep.search[s];
+        const double d = tt(ep.veh_nid[v], ep.onid[q]);
+        flag[e] = !(d + ep.veh_t[v] + ep.T > ep.clp[q]);
+    }
 }
 
+__device__ __forceinline__ int task_chunks(int S, int l) { const int g = chunk_group(l); return (S + g - 1) / g; }
+
 __global__ void k_tasks_from_screen(DEpoch ep, const uint8_t* __restrict__ flag, const i64* __restrict__ pos, i64 n,
-                                    int* task_veh, int* task_base, int* task_q) {
-    i64 e = (i64)blockIdx.x * blockDim.x + threadIdx.x;
-    if (e >= n || !flag[e]) return;
-    int v, s;
-    if (ep.mode == AMOD_MODE_SBA) { s = (int)(e / ep.n_veh); v = (int)(e - (i64)s * ep.n_veh); }
-    else { v = (int)(e / ep.n_search); s = (int)(e - (i64)v * ep.n_search); }
-    const i64 t = pos[e];
-    task_veh[t] = v; task_base[t] = v; task_q[t] = ep.search[s];
+                                    const Control* __restrict__ ctl, const int* __restrict__ len0, const int* __restrict__ S0,
+                                    int* task_veh, int* task_base, int* task_q, int* task_nchunk) {
+    if (ctl->n_tasks[0] == 0 || ctl->overflow) return;
+    const i64 stride = (i64)gridDim.x * blockDim.x;
+    for (i64 e = (i64)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += stride) {
+        if (!flag[e]) continue;
+        int v, s;
+        if (ep.mode == AMOD_MODE_SBA) { s = (int)(e / ep.n_veh); v = (int)(e - (i64)s * ep.n_veh); }
+        else { v = (int)(e / ep.n_search); s = (int)(e - (i64)v * ep.n_search); }
+        const i64 t = pos[e];
+        task_veh[t] = v; task_base[t] = v; task_q[t] = ep.search[s];
+        task_nchunk[t] = task_chunks(S0[v], len0[v]);
+    }
+}
+
+// chunk -> task map
+__global__ void k_expand_chunks(Control* __restrict__ ctl, int which, const i64* __restrict__ task_chunk0, int* __restrict__ chunk_task) {
+    const int n = (ctl->n_chunks && !ctl->overflow) ? ctl->n_tasks[which] : 0;
+    const int stride = gridDim.x * blockDim.x;
+    if (blockIdx.x == 0 && threadIdx.x == 0 && n) atomicAdd(&ctl->stats.n_tasks, (unsigned long long)n);   // compute_schedule calls
+    for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < n; t += stride)
+        for (i64 c = task_chunk0[t]; c < task_chunk0[t + 1]; c++) chunk_task[c] = t;
 }
 
 // ---------------------------------------------------------------------------------------------
 // Feasible tasks -> trips of the new level, order preserved (dispatch_osp.py:163-164, :217-218).
 // ---------------------------------------------------------------------------------------------
-__global__ void k_task_flags(int n_tasks, const int* __restrict__ task_nfeas, const int* __restrict__ task_veh,
-                             const int* __restrict__ len0, int k, uint8_t* flag, int* words, Stats* stats) {
-    int t = blockIdx.x * blockDim.x + threadIdx.x;
-    int nf = t < n_tasks ? task_nfeas[t] : 0;
-    if (t < n_tasks) {
-        flag[t] = nf > 0;
-        words[t] = nf * (len0[task_veh[t]] + 2 * k);   // nf <= ~1e6, len <= 40: fits int32 per task
+struct InTaskFeasible {       // scan input: 1 if the task produced at least one feasible schedule
+    const Control* ctl; int which; const i64* task_chunk0; const i64* chunk_pos;
+    __device__ __forceinline__ i64 size() const { return (ctl->n_chunks && !ctl->overflow) ? ctl->n_tasks[which] : 0; }
+    __device__ __forceinline__ i64 operator()(i64 t) const { return chunk_pos[task_chunk0[t + 1]] > chunk_pos[task_chunk0[t]]; }
+};
+
+__global__ void k_compact_trips(const Control* __restrict__ ctl, int which, const int* __restrict__ task_veh,
+                                const int* __restrict__ task_base, const int* __restrict__ task_q,
+                                const i64* __restrict__ task_chunk0, const i64* __restrict__ chunk_pos,
+                                const i64* __restrict__ trip_pos, Level prev, Level cur, Stats* stats) {
+    const int n = (ctl->n_trips[cur.k] && !ctl->overflow) ? ctl->n_tasks[which] : 0;
+    const int stride = gridDim.x * blockDim.x;
+    unsigned long long nsch = 0;
+    for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < n; t += stride) {
+        const i64 a = chunk_pos[task_chunk0[t]], b = chunk_pos[task_chunk0[t + 1]];
+        if (b == a) continue;
+        nsch += (unsigned long long)(b - a);
+        const int o = (int)trip_pos[t];
+        cur.trip_veh[o] = task_veh[t];
+        cur.nfeas[o] = (int)(b - a);
+        cur.s0[o] = a;
+        // trip = sorted(base trip + q)  (dispatch_osp.py:187)
+        const int kb = prev.k, q = task_q[t];
+        const int* bq = prev.trip_req + (i64)task_base[t] * kb;
+        int* d = cur.trip_req + (i64)o * (kb + 1);
+        int w = 0; bool put = false;
+        for (int m = 0; m < kb; m++) { if (!put && q < bq[m]) { d[w++] = q; put = true; } d[w++] = bq[m]; }
+        if (!put) d[w++] = q;
     }
-    int tot = warp_sum(nf);
-    if ((threadIdx.x & 31) == 0 && tot) atomicAdd(&stats->n_sches, (unsigned long long)tot);
+    nsch = warp_sum(nsch);
+    if ((threadIdx.x & 31) == 0 && nsch) atomicAdd(&stats->n_sches, nsch);
 }
 
-__global__ void k_compact_trips(int n_tasks, const int* __restrict__ task_nfeas, const double* __restrict__ task_cost,
-                                const int* __restrict__ task_veh, const int* __restrict__ task_base,
-                                const int* __restrict__ task_q, const i64* __restrict__ trip_pos,
-                                const i64* __restrict__ word_pos, Level prev, Level cur) {
-    int t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= n_tasks || task_nfeas[t] == 0) return;
-    const int o = (int)trip_pos[t];
-    cur.trip_veh[o] = task_veh[t];
-    cur.nfeas[o] = task_nfeas[t];
-    cur.cost[o] = task_cost[t];
-    cur.sch_off[o] = word_pos[t];
-    // trip = sorted(base trip + q)  (dispatch_osp.py:187)
-    const int kb = prev.k, q = task_q[t];
-    const int* b = prev.trip_req + (i64)task_base[t] * kb;
-    int* d = cur.trip_req + (i64)o * (kb + 1);
-    int w = 0; bool put = false;
-    for (int m = 0; m < kb; m++) { if (!put && q < b[m]) { d[w++] = q; put = true; } d[w++] = b[m]; }
-    if (!put) d[w++] = q;
-}
-
-// veh_start[v] = first trip of vehicle v (trips are vehicle-major)
-__global__ void k_veh_start(int n_trips, int n_veh, const int* __restrict__ trip_veh, int* veh_start) {
-    int t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t > n_trips) return;
-    int vprev = t == 0 ? -1 : trip_veh[t - 1];
-    int vcur = t == n_trips ? n_veh : trip_veh[t];
-    for (int u = vprev + 1; u <= vcur; u++) veh_start[u] = t;
+// ---------------------------------------------------------------------------------------------
+// List order of feasible_sches (scheduling.py:31-36): a schedule whose cost is strictly below every
+// earlier one is inserted at the front, the others are appended.  From the encounter-order costs:
+// order = [records, newest first] + [non-records in encounter order]; order[0] is the best schedule
+// (first-encountered minimum).  One warp per trip.  Also fills veh_start (trips are vehicle-major).
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(WARPS_PER_BLOCK * 32)
+k_classify(const Control* __restrict__ ctl, Level cur, int n_veh, int sba) {
+    const int lane = threadIdx.x & 31;
+    const int n = ctl->overflow ? 0 : ctl->n_trips[cur.k];
+    const int nwarps = gridDim.x * WARPS_PER_BLOCK;
+    for (int t = blockIdx.x * WARPS_PER_BLOCK + (threadIdx.x >> 5); t <= n; t += nwarps) {
+        if (!sba && lane == 0) {     // veh_start[u] = first trip of vehicle u
+            const int vprev = t == 0 ? -1 : cur.trip_veh[t - 1];
+            const int vcur = t == n ? n_veh : cur.trip_veh[t];
+            for (int u = vprev + 1; u <= vcur; u++) cur.veh_start[u] = t;
+        }
+        if (t == n) break;
+        const i64 s0 = cur.s0[t];
+        const int nf = cur.nfeas[t];
+        const double* __restrict__ cost = cur.sch_cost + s0;
+        int* __restrict__ ord = cur.order + s0;
+        // pass 1: number of records
+        double running = DINF;
+        int nrec = 0;
+        for (int b = 0; b < nf; b += 32) {
+            const double c = b + lane < nf ? cost[b + lane] : DINF;
+            const double incoming = fmin(running, warp_excl_min(c, lane));
+            nrec += __popc(__ballot_sync(FULL, c < incoming));
+            running = fmin(running, warp_min(c));
+        }
+        // pass 2: positions
+        double run2 = DINF;
+        int rec_before = 0, non_before = 0;
+        for (int b = 0; b < nf; b += 32) {
+            const bool in = b + lane < nf;
+            const double c = in ? cost[b + lane] : DINF;
+            const double incoming = fmin(run2, warp_excl_min(c, lane));
+            const bool isrec = in && c < incoming;
+            const unsigned br = __ballot_sync(FULL, isrec), bn = __ballot_sync(FULL, in && !isrec);
+            const unsigned lt = (1u << lane) - 1u;
+            if (isrec) ord[nrec - 1 - (rec_before + __popc(br & lt))] = b + lane;
+            else if (in) ord[nrec + non_before + __popc(bn & lt)] = b + lane;
+            rec_before += __popc(br); non_before += __popc(bn);
+            run2 = fmin(run2, warp_min(c));
+        }
+        if (lane == 0) cur.cost[t] = running;
+    }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -194,11 +259,13 @@ __device__ __forceinline__ unsigned hash_trip(int v, const int* r, int k, int sk
     return (unsigned)(h ^ (h >> 29));
 }
 
-__global__ void k_hash_build(Level lv, TripHash th) {
-    int t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= lv.n_trips) return;
-    unsigned h = hash_trip(lv.trip_veh[t], lv.trip_req + (i64)t * lv.k, lv.k, -1, -1) & th.mask;
-    while (atomicCAS(&th.slots[h], -1, t) != -1) h = (h + 1) & th.mask;
+__global__ void k_hash_build(const Control* __restrict__ ctl, Level lv, TripHash th) {
+    const int n = ctl->overflow ? 0 : ctl->n_trips[lv.k];
+    const int stride = gridDim.x * blockDim.x;
+    for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < n; t += stride) {
+        unsigned h = hash_trip(lv.trip_veh[t], lv.trip_req + (i64)t * lv.k, lv.k, -1, -1) & th.mask;
+        while (atomicCAS(&th.slots[h], -1, t) != -1) h = (h + 1) & th.mask;
+    }
 }
 
 // index of the trip (v, r minus r[skip] plus extra), or -1
@@ -230,64 +297,64 @@ __device__ __forceinline__ int hash_find(const Level& lv, const TripHash& th, in
 // (trip_i), inserting the one request U - trip_i, and the searches of one vehicle run in
 // (i, j) order, j = second-lowest subset index.  One warp per row (= trip_i); lanes scan the
 // vehicle's size-1 trips for the request to add.
-// MODE 0: count per row.  MODE 1: write (j, q) at row_off (ranked by j afterwards).
+// MODE 0: count per row.  MODE 1: write (j, q) at row_off, rank the row by j, emit the tasks.
 // ---------------------------------------------------------------------------------------------
 template <int MODE>
 __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32)
-k_gen(Level l1, Level prev, TripHash th, int* __restrict__ row_cnt, const i64* __restrict__ row_off,
-      int* __restrict__ tmp_j, int* __restrict__ tmp_q, int* __restrict__ tmp_row) {
+k_gen(const Control* __restrict__ ctl, int which_next, Level l1, Level prev, TripHash th, const int* __restrict__ len0,
+      int* __restrict__ row_cnt, const i64* __restrict__ row_off, int* __restrict__ tmp_j, int* __restrict__ tmp_q,
+      int* task_veh, int* task_base, int* task_q, int* task_nchunk) {
     const int lane = threadIdx.x & 31;
-    const int t = blockIdx.x * WARPS_PER_BLOCK + (threadIdx.x >> 5);
-    if (t >= prev.n_trips) return;
-    const int v = prev.trip_veh[t], k = prev.k;
-    const int a0 = l1.veh_start[v], a1 = l1.veh_start[v + 1];
-    const int* mine = prev.trip_req + (i64)t * k;
-    int cnt = 0;
-    const i64 off = MODE == 1 ? row_off[t] : 0;
-    for (int c0 = a0; c0 < a1; c0 += 32) {
-        const int c = c0 + lane;
-        int j = -1, r = -1;
-        if (c < a1) {
-            r = l1.trip_req[c];
-            if (k == 1) {
-                if (c > t) j = c;                       // all pairs i<j (dispatch_osp.py:183-186)
-            } else {
-                bool in = false;
-                for (int m = 0; m < k; m++) in |= mine[m] == r;
-                if (!in) {
-                    j = 0x7fffffff;
-                    for (int d = 0; d < k; d++) {       // every other k-subset must exist with a larger index
-                        const int u = hash_find(prev, th, v, mine, d, r);
-                        if (u <= t) { j = -1; break; }
-                        j = min(j, u);
+    const int n = ctl->overflow ? 0 : ctl->n_trips[prev.k];
+    if (MODE == 1 && ctl->n_tasks[which_next] == 0) return;
+    const int nwarps = gridDim.x * WARPS_PER_BLOCK;
+    for (int t = blockIdx.x * WARPS_PER_BLOCK + (threadIdx.x >> 5); t < n; t += nwarps) {
+        const int v = prev.trip_veh[t], k = prev.k;
+        const int a0 = l1.veh_start[v], a1 = l1.veh_start[v + 1];
+        const int* mine = prev.trip_req + (i64)t * k;
+        int cnt = 0;
+        const i64 off = MODE == 1 ? row_off[t] : 0;
+        for (int c0 = a0; c0 < a1; c0 += 32) {
+            const int c = c0 + lane;
+            int j = -1, r = -1;
+            if (c < a1) {
+                r = l1.trip_req[c];
+                if (k == 1) {
+                    if (c > t) j = c;                       // all pairs i<j (dispatch_osp.py:183-186)
+                } else {
+                    bool in = false;
+                    for (int m = 0; m < k; m++) in |= mine[m] == r;
+                    if (!in) {
+                        j = 0x7fffffff;
+                        for (int d = 0; d < k; d++) {       // every other k-subset must exist with a larger index
+                            const int u = hash_find(prev, th, v, mine, d, r);
+                            if (u <= t) { j = -1; break; }
+                            j = min(j, u);
+                        }
                     }
                 }
             }
+            const unsigned bal = __ballot_sync(FULL, j >= 0);
+            if (MODE == 1 && j >= 0) {
+                const i64 o = off + cnt + __popc(bal & ((1u << lane) - 1u));
+                tmp_j[o] = j; tmp_q[o] = r;
+            }
+            cnt += __popc(bal);
         }
-        const unsigned bal = __ballot_sync(FULL, j >= 0);
-        if (MODE == 1 && j >= 0) {
-            const i64 o = off + cnt + __popc(bal & ((1u << lane) - 1u));
-            tmp_j[o] = j; tmp_q[o] = r; tmp_row[o] = t;
+        if (MODE == 0) { if (lane == 0) row_cnt[t] = cnt; continue; }
+        __syncwarp();
+        // rank by j (k == 1 rows are already in j order) and emit the next level's tasks
+        const int l_next = len0[v] + 2 * k;
+        const int nch = task_chunks(prev.nfeas[t], l_next);
+        for (int e = lane; e < cnt; e += 32) {
+            int rank = e;
+            if (k > 1) {
+                const int j = tmp_j[off + e];
+                rank = 0;
+                for (int x = 0; x < cnt; x++) rank += tmp_j[off + x] < j;
+            }
+            const i64 o = off + rank;
+            task_veh[o] = v; task_base[o] = t; task_q[o] = tmp_q[off + e]; task_nchunk[o] = nch;
         }
-        cnt += __popc(bal);
     }
-    if (MODE == 0 && lane == 0) row_cnt[t] = cnt;
-}
-
-// rank the candidates of each row by j and emit the tasks
-__global__ void k_gen_rank(i64 n, const i64* __restrict__ row_off, const int* __restrict__ tmp_j,
-                           const int* __restrict__ tmp_q, const int* __restrict__ tmp_row, const int* __restrict__ trip_veh,
-                           int sorted_already, int* task_veh, int* task_base, int* task_q) {
-    i64 e = (i64)blockIdx.x * blockDim.x + threadIdx.x;
-    if (e >= n) return;
-    const int row = tmp_row[e];
-    i64 o = e;
-    if (!sorted_already) {
-        const i64 b = row_off[row], en = row_off[row + 1];
-        const int j = tmp_j[e];
-        int rank = 0;
-        for (i64 x = b; x < en; x++) rank += tmp_j[x] < j;
-        o = b + rank;
-    }
-    task_veh[o] = trip_veh[row]; task_base[o] = row; task_q[o] = tmp_q[e];
 }

@@ -1,5 +1,8 @@
-// scan.cuh — device-wide exclusive prefix sum (reduce-then-scan, three launches).
-// Used for every ordered compaction / CSR offset in the level-synchronous pool build.
+// scan.cuh — device-wide exclusive prefix sum whose length lives in device memory.
+// Two launches on a fixed grid: (a) every block reduces its contiguous segment, (b) every block
+// sums the partials before it and scans its segment.  The input is a functor, so flags derived
+// from other arrays are scanned without being materialised; a finishing functor receives the
+// total on one thread (it stores the count, checks the capacity of whatever the scan sizes).
 #pragma once
 #include "common.cuh"
 
@@ -27,45 +30,75 @@ __device__ __forceinline__ i64 block_excl_scan(i64 x, i64* total, i64* smem /*[S
     return r;
 }
 
-template <typename Tin>
-__global__ void __launch_bounds__(SCAN_THREADS) k_scan_reduce(const Tin* __restrict__ in, i64 n, i64* __restrict__ partial) {
+__device__ __forceinline__ void scan_segment(i64 n, i64* lo, i64* hi) {
+    i64 seg = (n + gridDim.x - 1) / gridDim.x;
+    seg = (seg + SCAN_TILE - 1) / SCAN_TILE * SCAN_TILE;
+    *lo = min(n, (i64)blockIdx.x * seg);
+    *hi = min(n, *lo + seg);
+}
+
+template <typename In>
+__global__ void __launch_bounds__(SCAN_THREADS) k_scan_a(In in, i64* __restrict__ partial) {
     __shared__ i64 smem[SCAN_THREADS / 32 + 1];
-    i64 base = (i64)blockIdx.x * SCAN_TILE + (i64)threadIdx.x * SCAN_ITEMS;
+    const i64 n = in.size();
+    i64 lo, hi;
+    scan_segment(n, &lo, &hi);
     i64 s = 0;
-#pragma unroll
-    for (int k = 0; k < SCAN_ITEMS; k++) if (base + k < n) s += (i64)in[base + k];
+    for (i64 i = lo + threadIdx.x; i < hi; i += SCAN_THREADS) s += in(i);
     i64 tot;
     block_excl_scan(s, &tot, smem);
     if (threadIdx.x == 0) partial[blockIdx.x] = tot;
 }
 
-// one block: exclusive scan of the per-tile totals (any number of tiles), grand total to *total
-__global__ void __launch_bounds__(SCAN_THREADS) k_scan_partials(i64* __restrict__ partial, int nb, i64* __restrict__ total) {
+template <typename In, typename Fin>
+__global__ void __launch_bounds__(SCAN_THREADS) k_scan_b(In in, const i64* __restrict__ partial, i64* __restrict__ out, Fin fin) {
     __shared__ i64 smem[SCAN_THREADS / 32 + 1];
-    i64 carry = 0;
-    for (int b0 = 0; b0 < nb; b0 += SCAN_THREADS) {
-        int b = b0 + threadIdx.x;
-        i64 x = b < nb ? partial[b] : 0;
+    const i64 n = in.size();
+    i64 lo, hi;
+    scan_segment(n, &lo, &hi);
+    i64 p = 0;
+    for (int b = threadIdx.x; b < (int)blockIdx.x; b += SCAN_THREADS) p += partial[b];
+    i64 carry;
+    block_excl_scan(p, &carry, smem);
+    for (i64 base = lo; base < hi; base += SCAN_TILE) {
+        const i64 i0 = base + (i64)threadIdx.x * SCAN_ITEMS;
+        i64 v[SCAN_ITEMS];
+        i64 s = 0;
+#pragma unroll
+        for (int k = 0; k < SCAN_ITEMS; k++) { v[k] = i0 + k < hi ? in(i0 + k) : 0; s += v[k]; }
         i64 tot;
-        i64 e = block_excl_scan(x, &tot, smem);
-        if (b < nb) partial[b] = carry + e;
+        i64 e = block_excl_scan(s, &tot, smem) + carry;
+#pragma unroll
+        for (int k = 0; k < SCAN_ITEMS; k++) { if (i0 + k < hi) out[i0 + k] = e; e += v[k]; }
         carry += tot;
     }
-    if (threadIdx.x == 0) *total = carry;
+    if (blockIdx.x == gridDim.x - 1 && threadIdx.x == 0) { out[n] = carry; fin(carry); }
 }
 
-template <typename Tin>
-__global__ void __launch_bounds__(SCAN_THREADS) k_scan_final(const Tin* __restrict__ in, i64 n, const i64* __restrict__ partial,
-                                                            i64* __restrict__ out) {
-    __shared__ i64 smem[SCAN_THREADS / 32 + 1];
-    i64 base = (i64)blockIdx.x * SCAN_TILE + (i64)threadIdx.x * SCAN_ITEMS;
-    i64 v[SCAN_ITEMS];
-    i64 s = 0;
-#pragma unroll
-    for (int k = 0; k < SCAN_ITEMS; k++) { v[k] = base + k < n ? (i64)in[base + k] : 0; s += v[k]; }
-    i64 tot;
-    i64 e = block_excl_scan(s, &tot, smem) + partial[blockIdx.x];
-#pragma unroll
-    for (int k = 0; k < SCAN_ITEMS; k++) { if (base + k < n) out[base + k] = e; e += v[k]; }
-    if (blockIdx.x == gridDim.x - 1 && threadIdx.x == SCAN_THREADS - 1) out[n] = e;   // out has n+1 entries
-}
+// ---- input functors ---------------------------------------------------------------------------
+template <typename T>
+struct InArray {                     // in[i], length *n (int) or fixed
+    const T* p; const int* n_ptr; i64 n_fixed;
+    __device__ __forceinline__ i64 size() const { return n_ptr ? (i64)*n_ptr : n_fixed; }
+    __device__ __forceinline__ i64 operator()(i64 i) const { return (i64)p[i]; }
+};
+
+// ---- finishing functors -----------------------------------------------------------------------
+struct FinNone { __device__ __forceinline__ void operator()(i64) const {} };
+// store min(total, cap) to *dst (int), remember the requirement, raise overflow
+struct FinCountInt {
+    int* dst; i64 cap; i64* need; unsigned long long* ovf; unsigned long long bit;
+    __device__ __forceinline__ void operator()(i64 tot) const {
+        if (tot > *need) *need = tot;
+        if (tot > cap) { atomicOr(ovf, bit); tot = 0; }
+        *dst = (int)tot;
+    }
+};
+struct FinCountI64 {
+    i64* dst; i64 cap; i64* need; unsigned long long* ovf; unsigned long long bit;
+    __device__ __forceinline__ void operator()(i64 tot) const {
+        if (tot > *need) *need = tot;
+        if (tot > cap) { atomicOr(ovf, bit); tot = 0; }
+        *dst = tot;
+    }
+};
