@@ -4,6 +4,7 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <cstdlib>
 #include <string>
 #include <type_traits>
 #include <vector>
@@ -27,11 +28,14 @@
         if (r_ != AMOD_OK) return r_; \
     } while (0)
 
+static thread_local unsigned long long g_reallocs = 0;   // bumped whenever a device buffer moves (graphs must be re-captured)
+
 struct DevBuf {
     void* p = nullptr;
     size_t cap = 0;
     cudaError_t ensure(size_t bytes) {
         if (bytes <= cap) return cudaSuccess;
+        g_reallocs++;
         if (p) cudaFree(p);
         p = nullptr; cap = 0;
         size_t want = std::max(bytes + bytes / 4, (size_t)4096);
@@ -58,6 +62,13 @@ struct amod_ctx {
     DevBuf ep_dev; void* ep_pinned = nullptr; size_t ep_pinned_cap = 0;
     // device control block + pinned host mirror
     DevBuf ctl; Control* h_ctl = nullptr;
+    DevBuf d_epoch; DEpoch* h_epoch = nullptr;          // the epoch header (sizes + array pointers) lives on the device
+    // one captured CUDA graph of the whole level loop per dispatch mode; replayed while buffers keep their addresses
+    struct GraphSlot { cudaGraphExec_t exec = nullptr; unsigned long long gen = 0; int cap = 0, base_len = 0, max_level = 0, launches = 0;
+                       size_t n_ev = 0; void* stream = nullptr; };
+    GraphSlot graphs[3];
+    unsigned long long buf_gen = 0;
+    bool use_graph = true;
     // capacities (grown from the sizes an epoch needed; persisted across epochs)
     i64 cap_tasks = 1 << 18, cap_chunks = 1 << 19, cap_ent = 1 << 18, cap_ptr = 1 << 19, cap_pst = 1 << 21;
     i64 cap_trips[MAX_LEVELS], cap_sch[MAX_LEVELS];
@@ -156,6 +167,9 @@ extern "C" int amod_create(amod_ctx** out, int device, int n_nodes, const void* 
     ctx->tt_bytes = bytes;
     for (int k = 0; k < MAX_LEVELS; k++) { ctx->cap_trips[k] = 1 << 16; ctx->cap_sch[k] = 1 << 18; }
     if ((e = cudaMallocHost((void**)&ctx->h_ctl, sizeof(Control))) != cudaSuccess) return bail("cudaMallocHost", e);
+    if ((e = cudaMallocHost((void**)&ctx->h_epoch, sizeof(DEpoch))) != cudaSuccess) return bail("cudaMallocHost", e);
+    if ((e = ctx->d_epoch.ensure(sizeof(DEpoch))) != cudaSuccess) return bail("cudaMalloc", e);
+    ctx->use_graph = getenv("AMOD_NO_GRAPH") == nullptr;
     apply_l2_policy(ctx, ctx->stream);
     cudaEventCreate(&ctx->ev0); cudaEventCreate(&ctx->ev1);
     *out = ctx;
@@ -178,6 +192,9 @@ extern "C" void amod_destroy(amod_ctx* ctx) {
     for (auto& l : ctx->lv) { l.trip_veh.release(); l.trip_req.release(); l.s0.release(); l.nfeas.release(); l.cost.release();
                               l.sch.release(); l.sch_cost.release(); l.order.release(); l.veh_start.release(); }
     if (ctx->h_ctl) cudaFreeHost(ctx->h_ctl);
+    if (ctx->h_epoch) cudaFreeHost(ctx->h_epoch);
+    ctx->d_epoch.release();
+    for (auto& g : ctx->graphs) if (g.exec) cudaGraphExecDestroy(g.exec);
     if (ctx->ep_pinned) cudaFreeHost(ctx->ep_pinned);
     if (ctx->d_tt) cudaFree(ctx->d_tt);
     for (auto e : ctx->ev_pool) cudaEventDestroy(e);
@@ -235,6 +252,8 @@ static int upload_epoch(amod_ctx* ctx, const amod_epoch* ep, int loc, DEpoch* d)
         d->veh_sche_off = ep->veh_sche_off; d->sche_code = ep->sche_code; d->sche_onboard = ep->sche_onboard;
         d->reb_node = ep->veh_reb_node; d->reb_ddl = ep->veh_reb_ddl; d->onid = ep->req_onid; d->dnid = ep->req_dnid;
         d->clp = ep->req_clp; d->cld = ep->req_cld; d->tr = ep->req_tr; d->ts = ep->req_ts; d->search = ep->search;
+        *ctx->h_epoch = *d;
+        CK(cudaMemcpyAsync(ctx->d_epoch.p, ctx->h_epoch, sizeof(DEpoch), cudaMemcpyHostToDevice, ctx->stream));
         return AMOD_OK;
     }
     CKR(validate_host_epoch(ctx, ep));
@@ -268,6 +287,8 @@ static int upload_epoch(amod_ctx* ctx, const amod_epoch* ep, int loc, DEpoch* d)
         off += (p.bytes + 15) & ~(size_t)15;
     }
     CK(cudaMemcpyAsync(ctx->ep_dev.p, ctx->ep_pinned, total, cudaMemcpyHostToDevice, ctx->stream));
+    *ctx->h_epoch = *d;
+    CK(cudaMemcpyAsync(ctx->d_epoch.p, ctx->h_epoch, sizeof(DEpoch), cudaMemcpyHostToDevice, ctx->stream));
     return AMOD_OK;
 }
 
@@ -332,10 +353,10 @@ static int ensure_buffers(amod_ctx* ctx, int V, i64 n_screen, int max_level, con
 // One attempt: enqueue the whole level-synchronous pipeline on the stream without any host
 // synchronisation; every size is produced and consumed on the device (Control block).
 template <typename TT>
-static int enqueue_build(amod_ctx* ctx, const DEpoch& d, Table<TT> tt, int max_level, const LevelSet& ls, const PoolBufs& pb,
+static int enqueue_build(amod_ctx* ctx, int mode, Table<TT> tt, int max_level, const LevelSet& ls, const PoolBufs& pb,
                          size_t* n_ev_out) {
     cudaStream_t st = ctx->stream;
-    const int V = d.n_veh, Q = d.n_search, mode = d.mode;
+    const DEpoch* d = ctx->d_epoch.as<DEpoch>();      // sizes and array pointers are read on the device
     const int sba = mode == AMOD_MODE_SBA;
     Control* ctl = ctx->ctl.as<Control>();
     Stats* dstats = &ctl->stats;
@@ -344,32 +365,26 @@ static int enqueue_build(amod_ctx* ctx, const DEpoch& d, Table<TT> tt, int max_l
     size_t n_ev = 0;
     int* len0 = ctx->len0.as<int>();
 
-    memset(ctx->h_ctl, 0, sizeof(Control));
-    ctx->h_ctl->n_trips[0] = V;
-    CK(cudaMemcpyAsync(ctl, ctx->h_ctl, sizeof(Control), cudaMemcpyHostToDevice, st));
-
     // ---- level 0: basic schedules -----------------------------------------------------------------
-    if (V > 0) {
-        k_basic<TT, 0><<<nblk(V, WARPS_PER_BLOCK), WARPS_PER_BLOCK * 32, 0, st>>>(d, tt, ls.lv[0], len0, ctx->S0.as<int>(), nullptr, ctl, dstats);
-        scan_dev(ctx, InArray<int>{ctx->S0.as<int>(), nullptr, V}, ctx->s0pos.as<i64>(),
+    {
+        k_basic<TT, 0><<<GE, WARPS_PER_BLOCK * 32, 0, st>>>(d, tt, ls.lv[0], len0, ctx->S0.as<int>(), nullptr, ctl, dstats);
+        scan_dev(ctx, InVehInt{ctx->S0.as<int>(), d}, ctx->s0pos.as<i64>(),
                  FinCountI64{&ctl->n_sch[0], ls.lv[0].cap_sch, &ctl->need_sch[0], &ctl->overflow, OVF_SCH});
-        k_basic<TT, 1><<<nblk(V, WARPS_PER_BLOCK), WARPS_PER_BLOCK * 32, 0, st>>>(d, tt, ls.lv[0], len0, ctx->S0.as<int>(),
-                                                                               ctx->s0pos.as<i64>(), ctl, dstats);
+        k_basic<TT, 1><<<GE, WARPS_PER_BLOCK * 32, 0, st>>>(d, tt, ls.lv[0], len0, ctx->S0.as<int>(), ctx->s0pos.as<i64>(), ctl, dstats);
         ctx->n_launches += 2;
     }
     // ---- level-1 tasks: reachability screen ---------------------------------------------------------
-    const i64 n_screen = (i64)V * Q;
-    if (n_screen > 0) {
-        k_screen<TT><<<std::min((i64)G * 4, (n_screen + 255) / 256), 256, 0, st>>>(d, tt, ctx->flag8.as<uint8_t>(), n_screen);
-        scan_dev(ctx, InArray<uint8_t>{ctx->flag8.as<uint8_t>(), nullptr, n_screen}, ctx->pos.as<i64>(),
+    {
+        k_screen<TT><<<G * 4, 256, 0, st>>>(d, tt, ctx->flag8.as<uint8_t>());
+        scan_dev(ctx, InScreenFlag{ctx->flag8.as<uint8_t>(), d}, ctx->pos.as<i64>(),
                  FinCountInt{&ctl->n_tasks[0], ctx->cap_tasks, &ctl->need_tasks, &ctl->overflow, OVF_TASKS});
-        k_tasks_from_screen<<<std::min((i64)G * 4, (n_screen + 255) / 256), 256, 0, st>>>(
-            d, ctx->flag8.as<uint8_t>(), ctx->pos.as<i64>(), n_screen, ctl, len0, ctx->S0.as<int>(), ctx->task_veh[0].as<int>(),
-            ctx->task_base[0].as<int>(), ctx->task_q[0].as<int>(), ctx->task_nchunk[0].as<int>());
+        k_tasks_from_screen<<<G * 4, 256, 0, st>>>(d, ctx->flag8.as<uint8_t>(), ctx->pos.as<i64>(), ctl, len0, ctx->S0.as<int>(),
+                                                  ctx->task_veh[0].as<int>(), ctx->task_base[0].as<int>(), ctx->task_q[0].as<int>(),
+                                                  ctx->task_nchunk[0].as<int>());
         ctx->n_launches += 2;
     }
     // ---- levels 1..max_level ----------------------------------------------------------------------------
-    for (int k = 1; k <= max_level && n_screen > 0; k++) {
+    for (int k = 1; k <= max_level; k++) {
         const int cur = (k - 1) & 1, nxt = k & 1;
         int* tv = ctx->task_veh[cur].as<int>(); int* tb = ctx->task_base[cur].as<int>(); int* tq = ctx->task_q[cur].as<int>();
         const Level& prev = ls.lv[k - 1];
@@ -392,7 +407,7 @@ static int enqueue_build(amod_ctx* ctx, const DEpoch& d, Table<TT> tt, int max_l
         k_eval<TT, 1><<<GE, WARPS_PER_BLOCK * 32, 0, st>>>(d, tt, prev, lv, len0, ctl, tv, tb, tq, chunk0, ctx->chunk_task.as<int>(),
                                                           ctx->chunk_cnt.as<int>(), ctx->lane_cnt.as<uint8_t>(), cpos, dstats);
         CK(cudaEventRecord(get_event(ctx, n_ev++), st));
-        k_classify<<<G, WARPS_PER_BLOCK * 32, 0, st>>>(ctl, lv, V, sba);
+        k_classify<<<G, WARPS_PER_BLOCK * 32, 0, st>>>(d, ctl, lv, sba);
         ctx->n_launches += 5;
         if (k == max_level) break;
         // ---- candidates of size k+1 ---------------------------------------------------------------------
@@ -414,12 +429,11 @@ static int enqueue_build(amod_ctx* ctx, const DEpoch& d, Table<TT> tt, int max_l
         ctx->n_launches += 2;
     }
     // ---- pool assembly --------------------------------------------------------------------------------
-    if (V > 0) {
-        LevelSet lsp = ls;
-        if (n_screen == 0) lsp.n = 1;
-        k_pool_veh_count<<<nblk(V, 256), 256, 0, st>>>(V, mode, lsp, ctl, ctx->veh_cnt.as<int>());
-        scan_dev(ctx, InArray<int>{ctx->veh_cnt.as<int>(), nullptr, V}, ctx->veh_off.as<i64>(), FinPoolEntries{ctl, pb.cap_ent, sba});
-        k_pool_meta_veh<<<nblk(V, 256), 256, 0, st>>>(d, lsp, len0, ctx->veh_off.as<i64>(), ctl, pb);
+    {
+        const LevelSet& lsp = ls;
+        k_pool_veh_count<<<G, 256, 0, st>>>(d, lsp, ctl, ctx->veh_cnt.as<int>());
+        scan_dev(ctx, InVehInt{ctx->veh_cnt.as<int>(), d}, ctx->veh_off.as<i64>(), FinPoolEntries{ctl, pb.cap_ent, sba});
+        k_pool_meta_veh<<<G, 256, 0, st>>>(d, lsp, len0, ctx->veh_off.as<i64>(), ctl, pb);
         k_pool_meta_levels<<<G, 256, 0, st>>>(d, lsp, len0, ctx->veh_off.as<i64>(), ctl, pb);
         scan_dev(ctx, InEntLen{pb.ent_tlen, ctl}, pb.trip_off, FinCountI64{&ctl->n_ptr, pb.cap_ptr, &ctl->need_ptr, &ctl->overflow, OVF_POOL});
         scan_dev(ctx, InEntLen{pb.ent_slen, ctl}, pb.sche_off, FinCountI64{&ctl->n_pst, pb.cap_pst, &ctl->need_pst, &ctl->overflow, OVF_POOL});
@@ -435,7 +449,6 @@ static int build_impl(amod_ctx* ctx, const amod_epoch* ep, int loc, amod_stats* 
     cudaStream_t st = ctx->stream;
     CK(cudaSetDevice(ctx->device));
     ctx->pool_valid = false;
-    ctx->n_launches = 0;
     DEpoch d;
     CK(cudaEventRecord(ctx->ev0, st));
     CKR(upload_epoch(ctx, ep, loc, &d));
@@ -463,8 +476,39 @@ static int build_impl(amod_ctx* ctx, const amod_epoch* ep, int loc, amod_stats* 
     int attempt = 0;
     for (;; attempt++) {
         if (attempt > 24) return ctx->fail(AMOD_E_NOMEM, "pool build did not converge after %d regrow attempts", attempt);
+        const unsigned long long r0 = g_reallocs;
         CKR(ensure_buffers(ctx, V, (i64)V * d.n_search, max_level, stride, &ls, &pb));
-        CKR(enqueue_build(ctx, d, tt, max_level, ls, pb, &n_ev));
+        if (g_reallocs != r0) ctx->buf_gen++;
+        memset(h, 0, sizeof(Control));
+        h->n_trips[0] = V;
+        CK(cudaMemcpyAsync(ctx->ctl.p, h, sizeof(Control), cudaMemcpyHostToDevice, st));
+        if (ctx->use_graph) {
+            // the whole level loop is one CUDA graph: ~150 small kernels whose sizes all live on the device,
+            // so a captured graph stays valid until a buffer moves or the dispatch mode / capacity changes
+            amod_ctx::GraphSlot& gs = ctx->graphs[mode];
+            if (!gs.exec || gs.gen != ctx->buf_gen || gs.cap != d.cap || gs.base_len != base_len || gs.max_level != max_level ||
+                gs.stream != (void*)st) {
+                if (gs.exec) { cudaGraphExecDestroy(gs.exec); gs.exec = nullptr; }
+                cudaGraph_t graph = nullptr;
+                CK(cudaStreamBeginCapture(st, cudaStreamCaptureModeRelaxed));
+                ctx->n_launches = 0;
+                int rc = enqueue_build(ctx, mode, tt, max_level, ls, pb, &n_ev);
+                cudaError_t ce = cudaStreamEndCapture(st, &graph);
+                if (rc != AMOD_OK) { if (graph) cudaGraphDestroy(graph); return rc; }
+                CK(ce);
+                ce = cudaGraphInstantiate(&gs.exec, graph, 0);
+                cudaGraphDestroy(graph);
+                CK(ce);
+                gs.gen = ctx->buf_gen; gs.cap = d.cap; gs.base_len = base_len; gs.max_level = max_level; gs.launches = ctx->n_launches;
+                gs.n_ev = n_ev; gs.stream = (void*)st;
+            }
+            n_ev = gs.n_ev;
+            ctx->n_launches = gs.launches;
+            CK(cudaGraphLaunch(gs.exec, st));
+        } else {
+            ctx->n_launches = 0;
+            CKR(enqueue_build(ctx, mode, tt, max_level, ls, pb, &n_ev));
+        }
         CK(cudaEventRecord(ctx->ev1, st));
         CK(cudaMemcpyAsync(h, ctx->ctl.p, sizeof(Control), cudaMemcpyDeviceToHost, st));
         CK(cudaStreamSynchronize(st));
@@ -479,10 +523,9 @@ static int build_impl(amod_ctx* ctx, const amod_epoch* ep, int loc, amod_stats* 
     }
     ctx->n_attempts = attempt + 1;
     if (h->stats.flags & 1ull) return ctx->fail(AMOD_E_LIMIT, "a vehicle schedule exceeds the compiled stop/capacity limits");
-    const i64 P = V > 0 ? h->n_ent : 0, NT = V > 0 ? h->n_ptr : 0, NS = V > 0 ? h->n_pst : 0;
+    const i64 P = h->n_ent, NT = h->n_ptr, NS = h->n_pst;
     ctx->pool_entries = P; ctx->pool_trip_reqs = NT; ctx->pool_stops = NS;
     ctx->pool_valid = true;
-    if (V == 0) { CK(cudaMemsetAsync(ctx->trip_off.p, 0, 8, st)); CK(cudaMemsetAsync(ctx->sche_off.p, 0, 8, st)); CK(cudaStreamSynchronize(st)); }
     int levels_done = 0;
     i64 total_tasks = 0;
     for (int k = 1; k <= max_level; k++) if (h->n_trips[k] > 0) levels_done = k;
@@ -492,7 +535,10 @@ static int build_impl(amod_ctx* ctx, const amod_epoch* ep, int loc, amod_stats* 
         cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1);
         out_stats->ms_build = ms;
         double me = 0.0;
-        for (size_t i = 0; i + 1 < n_ev; i += 2) { float x = 0.f; cudaEventElapsedTime(&x, ctx->ev_pool[i], ctx->ev_pool[i + 1]); me += x; }
+        for (size_t i = 0; i + 1 < n_ev; i += 2) {
+            float x = 0.f;
+            if (cudaEventElapsedTime(&x, ctx->ev_pool[i], ctx->ev_pool[i + 1]) == cudaSuccess) me += x; else cudaGetLastError();
+        }
         out_stats->ms_eval = me;
         out_stats->n_eval_launches = (int)(n_ev / 2);
         const i64 n_screen = (i64)V * d.n_search;

@@ -76,11 +76,12 @@ __device__ __forceinline__ void walk_j(const Table<TT>& tt, const int* __restric
 
 template <typename TT, int MODE>
 __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32)
-k_eval(DEpoch ep, Table<TT> tt, Level prev, Level cur, const int* __restrict__ len0, const Control* __restrict__ ctl,
+k_eval(const DEpoch* __restrict__ epp, Table<TT> tt, Level prev, Level cur, const int* __restrict__ len0, const Control* __restrict__ ctl,
        const int* __restrict__ task_veh, const int* __restrict__ task_base, const int* __restrict__ task_q,
        const i64* __restrict__ task_chunk0, const int* __restrict__ chunk_task,
        int* __restrict__ chunk_cnt, uint8_t* __restrict__ lane_cnt, const i64* __restrict__ chunk_pos, Stats* stats) {
     __shared__ WarpStage stage_all[WARPS_PER_BLOCK];
+    const DEpoch& ep = *epp;
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     WarpStage& st = stage_all[wib];
     const int warp0 = blockIdx.x * WARPS_PER_BLOCK + wib, nwarps = gridDim.x * WARPS_PER_BLOCK;

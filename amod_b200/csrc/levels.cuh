@@ -33,12 +33,14 @@ __device__ __forceinline__ void unrank_perm(int p, int L, int* out /*positions*/
 
 template <typename TT, int MODE>
 __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32)
-k_basic(DEpoch ep, Table<TT> tt, Level lv0, int* __restrict__ len0, int* __restrict__ S0, const i64* __restrict__ s0pos,
+k_basic(const DEpoch* __restrict__ epp, Table<TT> tt, Level lv0, int* __restrict__ len0, int* __restrict__ S0, const i64* __restrict__ s0pos,
         const Control* __restrict__ ctl, Stats* stats) {
+    const DEpoch& ep = *epp;
     const int lane = threadIdx.x & 31;
-    const int v = blockIdx.x * WARPS_PER_BLOCK + (threadIdx.x >> 5);
-    if (v >= ep.n_veh) return;
     if (MODE == 1 && ctl->overflow) return;          // level-0 store overflowed
+    unsigned long long evals = 0, lookups = 0;
+    bool bad = false;
+    for (int v = blockIdx.x * WARPS_PER_BLOCK + (threadIdx.x >> 5); v < ep.n_veh; v += gridDim.x * WARPS_PER_BLOCK) {
     const int s0 = ep.veh_sche_off[v], s1 = ep.veh_sche_off[v + 1];
     const int st = ep.veh_status[v];
     const bool perms = (ep.mode == AMOD_MODE_OSP) && st == 2;
@@ -57,7 +59,6 @@ k_basic(DEpoch ep, Table<TT> tt, Level lv0, int* __restrict__ len0, int* __restr
         if (v == 0) lv0.veh_start[ep.n_veh] = ep.n_veh;
     }
     int count = 1;
-    unsigned long long evals = 0, lookups = 0;
     if (perms && L >= 2 && L <= AMOD_MAX_CAP) {
         int nperm = 1;
         for (int a = 2; a <= L; a++) nperm *= a;
@@ -103,9 +104,13 @@ k_basic(DEpoch ep, Table<TT> tt, Level lv0, int* __restrict__ len0, int* __restr
     }
     if (MODE == 0) {
         if (lane == 0) { len0[v] = L; S0[v] = count; }
+        bad |= too_long || s1 - s0 > AMOD_MAX_STOPS || (perms && L > AMOD_MAX_CAP);
+    }
+    }
+    if (MODE == 0) {
         evals = warp_sum(evals); lookups = warp_sum(lookups);
         if (lane == 0 && evals) { atomicAdd(&stats->n_evals, evals); atomicAdd(&stats->n_lookups, lookups); }
-        if (lane == 0 && (too_long || s1 - s0 > AMOD_MAX_STOPS || (perms && L > AMOD_MAX_CAP))) atomicOr(&stats->flags, 1ull);
+        if (lane == 0 && bad) atomicOr(&stats->flags, 1ull);
     }
 }
 
@@ -115,7 +120,9 @@ k_basic(DEpoch ep, Table<TT> tt, Level lv0, int* __restrict__ len0, int* __restr
 // Flat order = task order: vehicle-major for OSP, request-major for SBA.
 // ---------------------------------------------------------------------------------------------
 template <typename TT>
-__global__ void k_screen(DEpoch ep, Table<TT> tt, uint8_t* __restrict__ flag, i64 n) {
+__global__ void k_screen(const DEpoch* __restrict__ epp, Table<TT> tt, uint8_t* __restrict__ flag) {
+    const DEpoch& ep = *epp;
+    const i64 n = (i64)ep.n_veh * ep.n_search;
     const i64 stride = (i64)gridDim.x * blockDim.x;
     for (i64 e = (i64)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += stride) {
         int v, s;
@@ -127,11 +134,24 @@ __global__ void k_screen(DEpoch ep, Table<TT> tt, uint8_t* __restrict__ flag, i6
     }
 }
 
+struct InScreenFlag {        // scan input over the V x Q screen flags
+    const uint8_t* p; const DEpoch* ep;
+    __device__ __forceinline__ i64 size() const { return (i64)ep->n_veh * ep->n_search; }
+    __device__ __forceinline__ i64 operator()(i64 i) const { return (i64)p[i]; }
+};
+struct InVehInt {            // scan input over a per-vehicle int array
+    const int* p; const DEpoch* ep;
+    __device__ __forceinline__ i64 size() const { return ep->n_veh; }
+    __device__ __forceinline__ i64 operator()(i64 i) const { return (i64)p[i]; }
+};
+
 __device__ __forceinline__ int task_chunks(int S, int l) { const int g = chunk_group(l); return (S + g - 1) / g; }
 
-__global__ void k_tasks_from_screen(DEpoch ep, const uint8_t* __restrict__ flag, const i64* __restrict__ pos, i64 n,
+__global__ void k_tasks_from_screen(const DEpoch* __restrict__ epp, const uint8_t* __restrict__ flag, const i64* __restrict__ pos,
                                     const Control* __restrict__ ctl, const int* __restrict__ len0, const int* __restrict__ S0,
                                     int* task_veh, int* task_base, int* task_q, int* task_nchunk) {
+    const DEpoch& ep = *epp;
+    const i64 n = (i64)ep.n_veh * ep.n_search;
     if (ctl->n_tasks[0] == 0 || ctl->overflow) return;
     const i64 stride = (i64)gridDim.x * blockDim.x;
     for (i64 e = (i64)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += stride) {
@@ -197,7 +217,8 @@ __global__ void k_compact_trips(const Control* __restrict__ ctl, int which, cons
 // (first-encountered minimum).  One warp per trip.  Also fills veh_start (trips are vehicle-major).
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32)
-k_classify(const Control* __restrict__ ctl, Level cur, int n_veh, int sba) {
+k_classify(const DEpoch* __restrict__ epp, const Control* __restrict__ ctl, Level cur, int sba) {
+    const int n_veh = epp->n_veh;
     const int lane = threadIdx.x & 31;
     const int n = ctl->overflow ? 0 : ctl->n_trips[cur.k];
     const int nwarps = gridDim.x * WARPS_PER_BLOCK;

@@ -16,14 +16,15 @@ struct PoolBufs {
     double* ent_cost; double* ent_delay; i64* trip_off; i64* sche_off; int* trip_req; int* sche_code;
 };
 
-__global__ void k_pool_veh_count(int n_veh, int mode, LevelSet ls, const Control* __restrict__ ctl, int* __restrict__ cnt) {
-    int v = blockIdx.x * blockDim.x + threadIdx.x;
-    if (v >= n_veh) return;
-    if (ctl->overflow) { cnt[v] = 0; return; }
-    if (mode == AMOD_MODE_SBA) { cnt[v] = 1; return; }
-    int c = 1 + (mode == AMOD_MODE_OSP ? 1 : 0);
-    for (int k = 1; k < ls.n; k++) c += ls.lv[k].veh_start[v + 1] - ls.lv[k].veh_start[v];
-    cnt[v] = c;
+__global__ void k_pool_veh_count(const DEpoch* __restrict__ epp, LevelSet ls, const Control* __restrict__ ctl, int* __restrict__ cnt) {
+    const int n_veh = epp->n_veh, mode = epp->mode;
+    for (int v = blockIdx.x * blockDim.x + threadIdx.x; v < n_veh; v += gridDim.x * blockDim.x) {
+        int c = 1 + (mode == AMOD_MODE_OSP ? 1 : 0);
+        if (ctl->overflow) c = 0;
+        else if (mode == AMOD_MODE_SBA) c = 1;
+        else for (int k = 1; k < ls.n; k++) c += ls.lv[k].veh_start[v + 1] - ls.lv[k].veh_start[v];
+        cnt[v] = c;
+    }
 }
 
 struct FinPoolEntries {   // n_ent = scan total (+ the SBA pairs, which precede the per-vehicle empties)
@@ -37,10 +38,11 @@ struct FinPoolEntries {   // n_ent = scan total (+ the SBA pairs, which precede 
 };
 
 // per-vehicle fixed entries (OSP: basic + current; SBA: the empty pair)
-__global__ void k_pool_meta_veh(DEpoch ep, LevelSet ls, const int* __restrict__ len0, const i64* __restrict__ veh_off,
+__global__ void k_pool_meta_veh(const DEpoch* __restrict__ epp, LevelSet ls, const int* __restrict__ len0, const i64* __restrict__ veh_off,
                                 Control* ctl, PoolBufs pb) {
-    int v = blockIdx.x * blockDim.x + threadIdx.x;
-    if (v >= ep.n_veh || ctl->n_ent == 0 || ctl->overflow) return;
+    const DEpoch& ep = *epp;
+    if (ctl->n_ent == 0 || ctl->overflow) return;
+    for (int v = blockIdx.x * blockDim.x + threadIdx.x; v < ep.n_veh; v += gridDim.x * blockDim.x) {
     const int cur_len = ep.veh_sche_off[v + 1] - ep.veh_sche_off[v];
     // compute_sche_cost walks of the fixed pairs (dispatch_osp.py:125,148, dispatch_sba.py:69)
     atomicAdd(&ctl->stats.n_lookups, (unsigned long long)((ep.mode == AMOD_MODE_SBA ? 0 : len0[v]) +
@@ -49,7 +51,7 @@ __global__ void k_pool_meta_veh(DEpoch ep, LevelSet ls, const int* __restrict__ 
         i64 e = (i64)ctl->n_trips[1] + v;
         pb.ent_veh[e] = v; pb.ent_kind[e] = AMOD_KIND_SBA_EMPTY; pb.ent_nfeas[e] = 1; pb.ent_tlen[e] = 0; pb.ent_slen[e] = cur_len;
         pb.ent_src[e] = SRC_INPUT; pb.ent_trip[e] = v;
-        return;
+        continue;
     }
     i64 e = veh_off[v];
     pb.ent_veh[e] = v; pb.ent_kind[e] = AMOD_KIND_BASIC; pb.ent_nfeas[e] = ls.lv[0].nfeas[v]; pb.ent_tlen[e] = 0;
@@ -61,11 +63,13 @@ __global__ void k_pool_meta_veh(DEpoch ep, LevelSet ls, const int* __restrict__ 
         pb.ent_veh[e] = v; pb.ent_kind[e] = AMOD_KIND_CURRENT; pb.ent_nfeas[e] = 1; pb.ent_tlen[e] = np; pb.ent_slen[e] = cur_len;
         pb.ent_src[e] = SRC_INPUT; pb.ent_trip[e] = v;
     }
+    }
 }
 
 // trip entries of every level
-__global__ void k_pool_meta_levels(DEpoch ep, LevelSet ls, const int* __restrict__ len0, const i64* __restrict__ veh_off,
+__global__ void k_pool_meta_levels(const DEpoch* __restrict__ epp, LevelSet ls, const int* __restrict__ len0, const i64* __restrict__ veh_off,
                                    const Control* __restrict__ ctl, PoolBufs pb) {
+    const DEpoch& ep = *epp;
     if (ctl->n_ent == 0 || ctl->overflow) return;
     const int stride = gridDim.x * blockDim.x;
     for (int k = 1; k < ls.n; k++) {
@@ -93,7 +97,8 @@ struct InEntLen {   // scan input over pool entries
 };
 
 template <typename TT>
-__global__ void k_pool_payload(DEpoch ep, Table<TT> tt, LevelSet ls, const Control* __restrict__ ctl, PoolBufs pb) {
+__global__ void k_pool_payload(const DEpoch* __restrict__ epp, Table<TT> tt, LevelSet ls, const Control* __restrict__ ctl, PoolBufs pb) {
+    const DEpoch& ep = *epp;
     const i64 n_ent = ctl->overflow ? 0 : ctl->n_ent;
     const i64 stride = (i64)gridDim.x * blockDim.x;
     for (i64 e = (i64)blockIdx.x * blockDim.x + threadIdx.x; e < n_ent; e += stride) {

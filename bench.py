@@ -184,7 +184,8 @@ def main():
     tt = synth.make_road_graph(seed=0).tt
     snaps = load_snapshots()
     b = PoolBuilder(tt, device=local)
-    stream = torch.cuda.current_stream()
+    stream = torch.cuda.Stream(device=dev)
+    torch.cuda.set_stream(stream)
     b.set_stream(stream.cuda_stream)          # CUDA events below bracket the stream the kernels run on
 
     # per-rank slice of the (tiled) fleet, resident in HBM before the timed region
