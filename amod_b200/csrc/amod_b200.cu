@@ -60,6 +60,7 @@ struct amod_ctx {
     std::string err;
     // staging of host epochs
     DevBuf ep_dev; void* ep_pinned = nullptr; size_t ep_pinned_cap = 0;
+    void* fetch_pinned = nullptr; size_t fetch_pinned_cap = 0;
     // device control block + pinned host mirror
     DevBuf ctl; Control* h_ctl = nullptr;
     DevBuf d_epoch; DEpoch* h_epoch = nullptr;          // the epoch header (sizes + array pointers) lives on the device
@@ -193,6 +194,7 @@ extern "C" void amod_destroy(amod_ctx* ctx) {
                               l.sch.release(); l.sch_cost.release(); l.order.release(); l.veh_start.release(); }
     if (ctx->h_ctl) cudaFreeHost(ctx->h_ctl);
     if (ctx->h_epoch) cudaFreeHost(ctx->h_epoch);
+    if (ctx->fetch_pinned) cudaFreeHost(ctx->fetch_pinned);
     ctx->d_epoch.release();
     for (auto& g : ctx->graphs) if (g.exec) cudaGraphExecDestroy(g.exec);
     if (ctx->ep_pinned) cudaFreeHost(ctx->ep_pinned);
@@ -594,20 +596,40 @@ extern "C" int amod_pool_fetch(amod_ctx* ctx, amod_pool* o, int loc) {
     if (o->cap_entries < P || o->cap_trip_reqs < NT || o->cap_stops < NS)
         return ctx->fail(AMOD_E_CAPACITY, "pool buffers too small: need %lld entries, %lld trip requests, %lld stops", P, NT, NS);
     CK(cudaSetDevice(ctx->device));
-    cudaMemcpyKind kind = loc == AMOD_LOC_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost;
     cudaStream_t st = ctx->stream;
-    if (P > 0) {
-        CK(cudaMemcpyAsync(o->ent_veh, ctx->ent_veh.p, 4 * (size_t)P, kind, st));
-        CK(cudaMemcpyAsync(o->ent_kind, ctx->ent_kind.p, 4 * (size_t)P, kind, st));
-        CK(cudaMemcpyAsync(o->ent_nfeas, ctx->ent_nfeas.p, 4 * (size_t)P, kind, st));
-        CK(cudaMemcpyAsync(o->ent_cost, ctx->ent_cost.p, 8 * (size_t)P, kind, st));
-        CK(cudaMemcpyAsync(o->ent_delay, ctx->ent_delay.p, 8 * (size_t)P, kind, st));
+    struct Part { void* dst; const void* src; size_t bytes; };
+    Part parts[] = {
+        {o->ent_veh, ctx->ent_veh.p, 4 * (size_t)P}, {o->ent_kind, ctx->ent_kind.p, 4 * (size_t)P},
+        {o->ent_nfeas, ctx->ent_nfeas.p, 4 * (size_t)P}, {o->ent_cost, ctx->ent_cost.p, 8 * (size_t)P},
+        {o->ent_delay, ctx->ent_delay.p, 8 * (size_t)P}, {o->ent_trip_off, ctx->trip_off.p, 8 * (size_t)(P + 1)},
+        {o->ent_sche_off, ctx->sche_off.p, 8 * (size_t)(P + 1)}, {o->trip_req, ctx->trip_req.p, 4 * (size_t)NT},
+        {o->sche_code, ctx->sche_code.p, 4 * (size_t)NS},
+    };
+    if (loc == AMOD_LOC_DEVICE) {
+        for (auto& p : parts) if (p.bytes) CK(cudaMemcpyAsync(p.dst, p.src, p.bytes, cudaMemcpyDeviceToDevice, st));
+        CK(cudaStreamSynchronize(st));
+        return AMOD_OK;
     }
-    CK(cudaMemcpyAsync(o->ent_trip_off, ctx->trip_off.p, 8 * (size_t)(P + 1), kind, st));
-    CK(cudaMemcpyAsync(o->ent_sche_off, ctx->sche_off.p, 8 * (size_t)(P + 1), kind, st));
-    if (NT > 0) CK(cudaMemcpyAsync(o->trip_req, ctx->trip_req.p, 4 * (size_t)NT, kind, st));
-    if (NS > 0) CK(cudaMemcpyAsync(o->sche_code, ctx->sche_code.p, 4 * (size_t)NS, kind, st));
+    // host buffers are pageable: DMA everything into one pinned staging area, then memcpy
+    size_t total = 0;
+    for (auto& p : parts) total += (p.bytes + 63) & ~(size_t)63;
+    if (total > ctx->fetch_pinned_cap) {
+        if (ctx->fetch_pinned) cudaFreeHost(ctx->fetch_pinned);
+        ctx->fetch_pinned = nullptr; ctx->fetch_pinned_cap = 0;
+        CK(cudaMallocHost(&ctx->fetch_pinned, total + total / 2));
+        ctx->fetch_pinned_cap = total + total / 2;
+    }
+    size_t off = 0;
+    for (auto& p : parts) {
+        if (p.bytes) CK(cudaMemcpyAsync((char*)ctx->fetch_pinned + off, p.src, p.bytes, cudaMemcpyDeviceToHost, st));
+        off += (p.bytes + 63) & ~(size_t)63;
+    }
     CK(cudaStreamSynchronize(st));
+    off = 0;
+    for (auto& p : parts) {
+        if (p.bytes) memcpy(p.dst, (char*)ctx->fetch_pinned + off, p.bytes);
+        off += (p.bytes + 63) & ~(size_t)63;
+    }
     return AMOD_OK;
 }
 

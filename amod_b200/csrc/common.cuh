@@ -31,6 +31,7 @@ struct Table {
     __device__ __forceinline__ double operator()(int o, int d) const {
         return (double)__ldg(p + (size_t)(o - 1) * (size_t)n + (size_t)(d - 1));
     }
+    __device__ __forceinline__ TT raw(int o, int d) const { return __ldg(p + (size_t)(o - 1) * (size_t)n + (size_t)(d - 1)); }
 };
 
 // One trip-size level of the per-vehicle feasible-trip table (FEASIBLE_TRIP_TABLE[veh][k-1],

@@ -16,10 +16,18 @@
 #include "common.cuh"
 
 #define STAGE_SLOTS 96    // stops staged per warp step: nsub*l <= 32 (whole schedules) or l <= 38
+#define LEG_SLOTS 200     // travel times staged per warp step: nsub*(5l+2) <= 192
 
+// Per base schedule of length l the insertion search only ever needs 5l+2 distinct table entries
+// (+ tt[P][D]): the base legs, and the legs into / out of the inserted pick-up P and drop-off D at
+// every position.  They are gathered once per warp step, all lanes in parallel (one L2 round trip),
+// and the sequential walks then read shared memory.  Values are the table's own elements, converted
+// to float64 at use, so the arithmetic is unchanged.
+template <typename TT>
 struct WarpStage {
     double ddl[STAGE_SLOTS];
     int node[STAGE_SLOTS];
+    TT leg[LEG_SLOTS];        // per schedule: g[l] | toP[l+1] | fromP[l] | toD[l+1] | fromD[l]
     code_t code[STAGE_SLOTS];
     signed char pod[STAGE_SLOTS];
 };
@@ -31,25 +39,26 @@ struct LaneCount { int n, evals, lookups; };
 // Walk j = i+1 .. for one (sub_sche, i).  `A` = accumulated time at the inserted pick-up.
 // WRITE: emit each feasible schedule (codes + cost) to consecutive rows starting at `row`.
 template <typename TT, bool WRITE>
-__device__ __forceinline__ void walk_j(const Table<TT>& tt, const int* __restrict__ nd, const double* __restrict__ ddl,
-                                       const code_t* __restrict__ codes, int l, int i, double A, int P, int D, int q,
+__device__ __forceinline__ void walk_j(const TT* __restrict__ lg, double PD, const double* __restrict__ ddl,
+                                       const code_t* __restrict__ codes, int l, int i, double A, int q,
                                        double cld, double T, unsigned long long fullmask, LaneCount& o, i64 row,
                                        code_t* __restrict__ out_sch, double* __restrict__ out_cost, int stride) {
+    const TT* __restrict__ g = lg;                       // g[m]     = tt[stop m-1 (or vehicle)][stop m]
+    const TT* __restrict__ fromP = lg + 2 * l + 1;       // fromP[m] = tt[P][stop m]
+    const TT* __restrict__ toD = lg + 3 * l + 1;         // toD[m]   = tt[stop m-1 (or vehicle)][D]
+    const TT* __restrict__ fromD = lg + 4 * l + 2;       // fromD[m] = tt[D][stop m]
     // capacity (scheduling.py:74-77): (i,j) is over capacity iff fullmask has a bit in [i, j-1]
     unsigned long long hi = fullmask >> (i + 1);
     const int b = hi ? (i + __ffsll((long long)hi)) : 64;     // lowest set bit above i; j <= b is capacity-feasible
     double B = A;
-    int nodeB = P;
     for (int j = i + 1;; j++) {
         o.evals++;
-        double C = B + tt(nodeB, D);
+        double C = B + (j == i + 1 ? PD : (double)toD[j - 1]);
         if (T + C > cld) { o.lookups += j + 1; break; }              // viol 2 -> break (scheduling.py:41)
-        int node = D;
         bool ok = true;
         for (int m = j - 1; m < l; m++) {
-            C += tt(node, nd[m]);
+            C += (double)(m == j - 1 ? fromD[m] : g[m]);
             if (T + C > ddl[m]) { ok = false; o.lookups += m + 3; break; }   // viol 0: infeasible, keep going
-            node = nd[m];
         }
         if (ok) {
             o.lookups += l + 2;
@@ -68,8 +77,7 @@ __device__ __forceinline__ void walk_j(const Table<TT>& tt, const int* __restric
         }
         if (j == l + 1) break;
         if (j == b) { o.evals++; break; }                           // next j is over capacity: viol 1 -> break
-        B += tt(nodeB, nd[j - 1]);                                  // extend the pick-up side over base stop j-1
-        nodeB = nd[j - 1];
+        B += (double)(j == i + 1 ? fromP[j - 1] : g[j - 1]);        // extend the pick-up side over base stop j-1
         if (T + B > ddl[j - 1]) { o.evals++; o.lookups += j + 1; break; }   // viol 4 at (i, j+1) -> break
     }
 }
@@ -80,10 +88,10 @@ k_eval(const DEpoch* __restrict__ epp, Table<TT> tt, Level prev, Level cur, cons
        const int* __restrict__ task_veh, const int* __restrict__ task_base, const int* __restrict__ task_q,
        const i64* __restrict__ task_chunk0, const int* __restrict__ chunk_task,
        int* __restrict__ chunk_cnt, uint8_t* __restrict__ lane_cnt, const i64* __restrict__ chunk_pos, Stats* stats) {
-    __shared__ WarpStage stage_all[WARPS_PER_BLOCK];
+    __shared__ WarpStage<TT> stage_all[WARPS_PER_BLOCK];
     const DEpoch& ep = *epp;
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-    WarpStage& st = stage_all[wib];
+    WarpStage<TT>& st = stage_all[wib];
     const int warp0 = blockIdx.x * WARPS_PER_BLOCK + wib, nwarps = gridDim.x * WARPS_PER_BLOCK;
     unsigned long long acc_evals = 0, acc_lookups = 0;
     const double T = ep.T;
@@ -110,6 +118,7 @@ k_eval(const DEpoch* __restrict__ epp, Table<TT> tt, Level prev, Level cur, cons
         const double clp = ep.clp[q], cld = ep.cld[q];
         const int nid = ep.veh_nid[v], load = ep.veh_load[v], cap = ep.cap;
         const double t0 = ep.veh_t[v];
+        const double PD = tt(P, D);
         const int items = (s_end - s_begin) * (l + 1);
         int dead_s = -1, cnt_total = 0;
         i64 row_base = MODE == 1 ? chunk_pos[c] : 0;
@@ -134,9 +143,25 @@ k_eval(const DEpoch* __restrict__ epp, Table<TT> tt, Level prev, Level cur, cons
                 }
             }
             __syncwarp();
+            const int W = 5 * l + 2;
+            {   // gather the 5l+2 travel times of every staged base schedule: independent loads, all lanes
+                const int ne = (sl_last - sl_first + 1) * W;
+                for (int e = lane; e < ne; e += 32) {
+                    const int sub = e / W, r = e - sub * W;
+                    const int* n = st.node + sub * l;
+                    int a, b, m;
+                    if (r < l) { m = r; a = m ? n[m - 1] : nid; b = n[m]; }
+                    else if (r < 2 * l + 1) { m = r - l; a = m ? n[m - 1] : nid; b = P; }
+                    else if (r < 3 * l + 1) { m = r - (2 * l + 1); a = P; b = n[m]; }
+                    else if (r < 4 * l + 2) { m = r - (3 * l + 1); a = m ? n[m - 1] : nid; b = D; }
+                    else { m = r - (4 * l + 2); a = D; b = n[m]; }
+                    st.leg[e] = tt.raw(a, b);
+                }
+            }
+            __syncwarp();
             const int eb = valid ? (sl - sl_first) * l : 0;
-            const int* nd = st.node + eb;
             const double* ddl = st.ddl + eb;
+            const TT* lg = st.leg + (valid ? (sl - sl_first) * W : 0);
 
             // capacity profile of the base schedule and accumulated time at the inserted pick-up
             unsigned long long fullmask = 0;
@@ -151,9 +176,8 @@ k_eval(const DEpoch* __restrict__ epp, Table<TT> tt, Level prev, Level cur, cons
                     if (run >= cap) fullmask |= 1ull << (m + 1);
                 }
                 double acc = t0;
-                int node = nid;
-                for (int m = 0; m < i; m++) { acc += tt(node, nd[m]); node = nd[m]; }   // trusted prefix (no checks)
-                A = acc + tt(node, P);
+                for (int m = 0; m < i; m++) acc += (double)lg[m];                        // trusted prefix (no checks)
+                A = acc + (double)lg[l + i];                                             // toP[i]
                 cap1 = basebad || ((fullmask >> i) & 1ull);                              // viol 1 at j = i+1
                 stop3 = !cap1 && (T + A > clp);                                          // viol 3 (scheduling.py:43)
             }
@@ -172,7 +196,7 @@ k_eval(const DEpoch* __restrict__ epp, Table<TT> tt, Level prev, Level cur, cons
                 if (live) {
                     if (cap1) o.evals = 1;
                     else if (stop3) { o.evals = 1; o.lookups = i + 1; }
-                    else walk_j<TT, false>(tt, nd, ddl, st.code + eb, l, i, A, P, D, q, cld, T, fullmask, o, 0, nullptr, nullptr, 0);
+                    else walk_j<TT, false>(lg, PD, ddl, st.code + eb, l, i, A, q, cld, T, fullmask, o, 0, nullptr, nullptr, 0);
                 }
                 acc_evals += o.evals; acc_lookups += o.lookups;
                 lane_cnt[(i64)c * 64 + it0 + lane] = (uint8_t)o.n;     // <= 64 items per chunk (l+1 <= 39)
@@ -180,7 +204,7 @@ k_eval(const DEpoch* __restrict__ epp, Table<TT> tt, Level prev, Level cur, cons
             } else {
                 const int mine = lane_cnt[(i64)c * 64 + it0 + lane];
                 const int before = warp_excl_sum(mine, lane);
-                if (mine) walk_j<TT, true>(tt, nd, ddl, st.code + eb, l, i, A, P, D, q, cld, T, fullmask, o, row_base + before,
+                if (mine) walk_j<TT, true>(lg, PD, ddl, st.code + eb, l, i, A, q, cld, T, fullmask, o, row_base + before,
                                            cur.sch, cur.sch_cost, cur.stride);
                 row_base += __shfl_sync(FULL, before + mine, 31);
             }
