@@ -75,7 +75,7 @@ struct amod_ctx {
     i64 cap_trips[MAX_LEVELS], cap_sch[MAX_LEVELS];
     // workspace
     DevBuf len0, S0, s0pos, flag8, pos, partial, task_veh[2], task_base[2], task_q[2], task_nchunk[2], task_chunk0, trip_pos,
-        chunk_task, chunk_cnt, lane_cnt, chunk_pos, hash, row_cnt, row_off, tmp_j, tmp_q;
+        chunk_desc, chunk_cnt, lane_cnt, chunk_pos, hash, row_cnt, row_off, tmp_j, tmp_q;
     LevelBufs lv[MAX_LEVELS];
     // pool
     DevBuf veh_cnt, veh_off, ent_veh, ent_kind, ent_nfeas, ent_tlen, ent_slen, ent_src, ent_trip, ent_cost, ent_delay,
@@ -183,7 +183,7 @@ extern "C" void amod_destroy(amod_ctx* ctx) {
     cudaDeviceSynchronize();
     DevBuf* all[] = {&ctx->ep_dev, &ctx->ctl, &ctx->len0, &ctx->S0, &ctx->s0pos, &ctx->flag8, &ctx->pos, &ctx->partial,
                      &ctx->task_veh[0], &ctx->task_veh[1], &ctx->task_base[0], &ctx->task_base[1], &ctx->task_q[0], &ctx->task_q[1],
-                     &ctx->task_nchunk[0], &ctx->task_nchunk[1], &ctx->task_chunk0, &ctx->trip_pos, &ctx->chunk_task, &ctx->chunk_cnt,
+                     &ctx->task_nchunk[0], &ctx->task_nchunk[1], &ctx->task_chunk0, &ctx->trip_pos, &ctx->chunk_desc, &ctx->chunk_cnt,
                      &ctx->lane_cnt, &ctx->chunk_pos, &ctx->hash, &ctx->row_cnt, &ctx->row_off, &ctx->tmp_j, &ctx->tmp_q,
                      &ctx->veh_cnt, &ctx->veh_off, &ctx->ent_veh, &ctx->ent_kind, &ctx->ent_nfeas, &ctx->ent_tlen, &ctx->ent_slen,
                      &ctx->ent_src, &ctx->ent_trip, &ctx->ent_cost, &ctx->ent_delay, &ctx->trip_off, &ctx->sche_off, &ctx->trip_req,
@@ -313,7 +313,7 @@ static int ensure_buffers(amod_ctx* ctx, int V, i64 n_screen, int max_level, con
         CK(ctx->task_nchunk[w].ensure(4 * T));
     }
     CK(ctx->task_chunk0.ensure(8 * (T + 2))); CK(ctx->trip_pos.ensure(8 * (T + 2)));
-    CK(ctx->chunk_task.ensure(4 * C)); CK(ctx->chunk_cnt.ensure(4 * C)); CK(ctx->lane_cnt.ensure(64 * C)); CK(ctx->chunk_pos.ensure(8 * (C + 2)));
+    CK(ctx->chunk_desc.ensure(sizeof(ChunkDesc) * C)); CK(ctx->chunk_cnt.ensure(4 * C)); CK(ctx->lane_cnt.ensure(64 * C)); CK(ctx->chunk_pos.ensure(8 * (C + 2)));
     CK(ctx->tmp_j.ensure(4 * T)); CK(ctx->tmp_q.ensure(4 * T));
     size_t max_trips = 1;
     memset(ls, 0, sizeof *ls);
@@ -395,10 +395,10 @@ static int enqueue_build(amod_ctx* ctx, int mode, Table<TT> tt, int max_level, c
         i64* cpos = ctx->chunk_pos.as<i64>();
         scan_dev(ctx, InArray<int>{ctx->task_nchunk[cur].as<int>(), &ctl->n_tasks[cur], 0}, chunk0,
                  FinCountInt{&ctl->n_chunks, ctx->cap_chunks, &ctl->need_chunks, &ctl->overflow, OVF_CHUNKS});
-        k_expand_chunks<<<G, 256, 0, st>>>(ctl, cur, chunk0, ctx->chunk_task.as<int>());
+        k_expand_chunks<<<GE, 256, 0, st>>>(ctl, cur, prev, len0, tv, tb, tq, chunk0, ctx->chunk_desc.as<ChunkDesc>());
         CK(cudaEventRecord(get_event(ctx, n_ev++), st));
-        k_eval<TT, 0><<<GE, WARPS_PER_BLOCK * 32, 0, st>>>(d, tt, prev, lv, len0, ctl, tv, tb, tq, chunk0, ctx->chunk_task.as<int>(),
-                                                          ctx->chunk_cnt.as<int>(), ctx->lane_cnt.as<uint8_t>(), nullptr, dstats);
+        k_eval<TT, 0><<<GE, WARPS_PER_BLOCK * 32, 0, st>>>(d, tt, prev, lv, ctl, ctx->chunk_desc.as<ChunkDesc>(), ctx->chunk_cnt.as<int>(),
+                                                          ctx->lane_cnt.as<uint8_t>(), nullptr, dstats);
         CK(cudaEventRecord(get_event(ctx, n_ev++), st));
         scan_dev(ctx, InArray<int>{ctx->chunk_cnt.as<int>(), &ctl->n_chunks, 0}, cpos,
                  FinCountI64{&ctl->n_sch[k], lv.cap_sch, &ctl->need_sch[k], &ctl->overflow, OVF_SCH});
@@ -406,8 +406,8 @@ static int enqueue_build(amod_ctx* ctx, int mode, Table<TT> tt, int max_level, c
                  FinCountInt{&ctl->n_trips[k], (i64)lv.cap_trips, &ctl->need_trips[k], &ctl->overflow, OVF_TRIPS});
         k_compact_trips<<<G, 256, 0, st>>>(ctl, cur, tv, tb, tq, chunk0, cpos, ctx->trip_pos.as<i64>(), prev, lv, dstats);
         CK(cudaEventRecord(get_event(ctx, n_ev++), st));
-        k_eval<TT, 1><<<GE, WARPS_PER_BLOCK * 32, 0, st>>>(d, tt, prev, lv, len0, ctl, tv, tb, tq, chunk0, ctx->chunk_task.as<int>(),
-                                                          ctx->chunk_cnt.as<int>(), ctx->lane_cnt.as<uint8_t>(), cpos, dstats);
+        k_eval<TT, 1><<<GE, WARPS_PER_BLOCK * 32, 0, st>>>(d, tt, prev, lv, ctl, ctx->chunk_desc.as<ChunkDesc>(), ctx->chunk_cnt.as<int>(),
+                                                          ctx->lane_cnt.as<uint8_t>(), cpos, dstats);
         CK(cudaEventRecord(get_event(ctx, n_ev++), st));
         k_classify<<<G, WARPS_PER_BLOCK * 32, 0, st>>>(d, ctl, lv, sba);
         ctx->n_launches += 5;

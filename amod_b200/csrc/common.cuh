@@ -83,6 +83,13 @@ struct Control {
     Stats stats;
 };
 
+// One unit of insertion-search work: a group of whole base schedules of one task (32 B, one load).
+struct __align__(16) ChunkDesc {
+    int v, q, s_begin, n_sub;     // vehicle, inserted request, first base schedule (list position), how many
+    i64 s0;                       // first schedule row of the base trip in the previous level
+    int l, task;                  // base schedule length, owning task
+};
+
 __device__ __forceinline__ void stop_info(const DEpoch& ep, int v, int code, int& node, double& ddl, int& pod) {
     if (code < 0) { node = ep.reb_node[v]; ddl = ep.reb_ddl[v]; pod = 0; return; }
     int r = code >> 1;

@@ -83,25 +83,30 @@ __device__ __forceinline__ void walk_j(const TT* __restrict__ lg, double PD, con
 }
 
 template <typename TT, int MODE>
-__global__ void __launch_bounds__(WARPS_PER_BLOCK * 32)
-k_eval(const DEpoch* __restrict__ epp, Table<TT> tt, Level prev, Level cur, const int* __restrict__ len0, const Control* __restrict__ ctl,
-       const int* __restrict__ task_veh, const int* __restrict__ task_base, const int* __restrict__ task_q,
-       const i64* __restrict__ task_chunk0, const int* __restrict__ chunk_task,
-       int* __restrict__ chunk_cnt, uint8_t* __restrict__ lane_cnt, const i64* __restrict__ chunk_pos, Stats* stats) {
+__global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, 3)
+k_eval(const DEpoch* __restrict__ epp, Table<TT> tt, Level prev, Level cur, const Control* __restrict__ ctl,
+       const ChunkDesc* __restrict__ desc, int* __restrict__ chunk_cnt, uint8_t* __restrict__ lane_cnt,
+       const i64* __restrict__ chunk_pos, Stats* stats) {
     __shared__ WarpStage<TT> stage_all[WARPS_PER_BLOCK];
-    const DEpoch& ep = *epp;
+    __shared__ DEpoch s_ep;       // the epoch header once per block: array pointers without a second indirection
+    if (threadIdx.x < sizeof(DEpoch) / 4) ((int*)&s_ep)[threadIdx.x] = ((const int*)epp)[threadIdx.x];
+    __syncthreads();
+    const DEpoch& ep = s_ep;
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     WarpStage<TT>& st = stage_all[wib];
     const int warp0 = blockIdx.x * WARPS_PER_BLOCK + wib, nwarps = gridDim.x * WARPS_PER_BLOCK;
     unsigned long long acc_evals = 0, acc_lookups = 0;
     const double T = ep.T;
     const int n_chunks = ctl->overflow ? 0 : ctl->n_chunks;
+    const int cap = ep.cap;
 
+    ChunkDesc nxt;
+    if (warp0 < n_chunks) nxt = desc[warp0];
     for (int c = warp0; c < n_chunks; c += nwarps) {
+        const ChunkDesc cd = nxt;
+        if (c + nwarps < n_chunks) nxt = desc[c + nwarps];        // prefetch the next descriptor
         if (MODE == 1 && chunk_cnt[c] == 0) continue;
-        const int task = chunk_task[c];
-        const int v = task_veh[task], base = task_base[task], q = task_q[task];
-        const int l = len0[v] + 2 * prev.k;
+        const int v = cd.v, q = cd.q, l = cd.l;
         if (l + 2 > MAXS || l + 2 > cur.stride) {   // compiled stop limit: reported as AMOD_E_LIMIT by the host
             if (MODE == 0) {
                 if (lane == 0) { atomicOr(&stats->flags, 1ull); chunk_cnt[c] = 0; }
@@ -109,17 +114,14 @@ k_eval(const DEpoch* __restrict__ epp, Table<TT> tt, Level prev, Level cur, cons
             }
             continue;
         }
-        const int S = prev.nfeas[base];
-        const i64 s0 = prev.s0[base];
-        const int g = chunk_group(l);
-        const int s_begin = (int)(c - task_chunk0[task]) * g;
-        const int s_end = min(S, s_begin + g);
+        const i64 s0 = cd.s0;
+        const int s_begin = cd.s_begin;
         const int P = ep.onid[q], D = ep.dnid[q];
         const double clp = ep.clp[q], cld = ep.cld[q];
-        const int nid = ep.veh_nid[v], load = ep.veh_load[v], cap = ep.cap;
+        const int nid = ep.veh_nid[v], load = ep.veh_load[v];
         const double t0 = ep.veh_t[v];
         const double PD = tt(P, D);
-        const int items = (s_end - s_begin) * (l + 1);
+        const int items = cd.n_sub * (l + 1);
         int dead_s = -1, cnt_total = 0;
         i64 row_base = MODE == 1 ? chunk_pos[c] : 0;
 

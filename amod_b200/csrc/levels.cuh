@@ -165,13 +165,28 @@ __global__ void k_tasks_from_screen(const DEpoch* __restrict__ epp, const uint8_
     }
 }
 
-// chunk -> task map
-__global__ void k_expand_chunks(Control* __restrict__ ctl, int which, const i64* __restrict__ task_chunk0, int* __restrict__ chunk_task) {
+// chunk descriptors: one warp per task, lanes over the task's chunks
+__global__ void __launch_bounds__(256)
+k_expand_chunks(Control* __restrict__ ctl, int which, Level prev, const int* __restrict__ len0, const int* __restrict__ task_veh,
+                const int* __restrict__ task_base, const int* __restrict__ task_q, const i64* __restrict__ task_chunk0,
+                ChunkDesc* __restrict__ desc) {
     const int n = (ctl->n_chunks && !ctl->overflow) ? ctl->n_tasks[which] : 0;
-    const int stride = gridDim.x * blockDim.x;
+    const int lane = threadIdx.x & 31;
+    const int nwarps = gridDim.x * (blockDim.x >> 5);
     if (blockIdx.x == 0 && threadIdx.x == 0 && n) atomicAdd(&ctl->stats.n_tasks, (unsigned long long)n);   // compute_schedule calls
-    for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < n; t += stride)
-        for (i64 c = task_chunk0[t]; c < task_chunk0[t + 1]; c++) chunk_task[c] = t;
+    for (int t = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); t < n; t += nwarps) {
+        const int v = task_veh[t], base = task_base[t], q = task_q[t];
+        const int l = len0[v] + 2 * prev.k;
+        const int S = prev.nfeas[base];
+        const i64 s0 = prev.s0[base];
+        const int g = chunk_group(l);
+        const i64 c0 = task_chunk0[t], c1 = task_chunk0[t + 1];
+        for (i64 c = c0 + lane; c < c1; c += 32) {
+            ChunkDesc d;
+            d.v = v; d.q = q; d.s_begin = (int)(c - c0) * g; d.n_sub = min(S - d.s_begin, g); d.s0 = s0; d.l = l; d.task = t;
+            desc[c] = d;
+        }
+    }
 }
 
 // ---------------------------------------------------------------------------------------------
