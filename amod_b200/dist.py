@@ -69,3 +69,33 @@ def allgather_pool(local: Pool, sel: np.ndarray, n_veh: int, mode_sba: bool = Fa
     sels = gather(np.asarray(sel, dtype=np.int64), mx[3], 3)
     parts = [(Pool(**{f: fields[f][r] for f in Pool.FIELDS}), sels[r]) for r in range(world)]
     return (merge_sba if mode_sba else merge_vehicle_major)(parts, n_veh)
+
+
+def merge_vehicle_major_torch(rank_pools: list[dict], world: int) -> dict:
+    """Device-side version of merge_vehicle_major for interleaved sharding (vehicle v lives on rank
+    v % world as local vehicle v // world).  rank_pools[r] maps Pool field name -> torch tensor
+    (already trimmed to the rank's sizes) on one device; returns the merged pool tensors in the
+    reference's vehicle-major order (dispatch_osp.py:107).  Pure torch indexing: plumbing."""
+    import torch
+
+    veh = torch.cat([p["ent_veh"].to(torch.int64) * world + r for r, p in enumerate(rank_pools)])
+    order = torch.argsort(veh, stable=True)
+    out = {"ent_veh": veh[order].to(torch.int32)}
+    for f in ("ent_kind", "ent_cost", "ent_delay", "ent_nfeas"):
+        out[f] = torch.cat([p[f] for p in rank_pools])[order]
+    for off_name, data_name in (("ent_trip_off", "trip_req"), ("ent_sche_off", "sche_code")):
+        lens, starts, base = [], [], 0
+        for p in rank_pools:
+            o = p[off_name]
+            lens.append(o[1:] - o[:-1])
+            starts.append(o[:-1] + base)
+            base += int(p[data_name].numel())
+        lens = torch.cat(lens)[order]
+        starts = torch.cat(starts)[order]
+        new_off = torch.zeros(lens.numel() + 1, dtype=torch.int64, device=lens.device)
+        torch.cumsum(lens, 0, out=new_off[1:])
+        data = torch.cat([p[data_name] for p in rank_pools])
+        idx = torch.repeat_interleave(starts - new_off[:-1], lens) + torch.arange(int(new_off[-1]), device=lens.device)
+        out[off_name] = new_off
+        out[data_name] = data[idx]
+    return out

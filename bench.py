@@ -94,11 +94,19 @@ class ClockSampler(threading.Thread):
                 "reasons": reasons, "samples": len(sm)}
 
 
+def host_threads() -> int:
+    """All host threads this process may use (torchrun pins OMP_NUM_THREADS=1; the CPU arm must not inherit that)."""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except Exception:
+        return max(1, os.cpu_count() or 1)
+
+
 def cpu_leg(snaps, tt, budget_s=12.0):
     """Oracle (the C port of the reference's path) on the host cores, bounded sample."""
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import oracle
-    threads = oracle.max_threads()
+    threads = host_threads()
     name, ep, n_evals, _ = snaps[0]
     # calibrate on every 64th vehicle, then size the vehicle stride for ~budget_s
     t = time.perf_counter()
@@ -126,7 +134,7 @@ def run_reference(args):
     import oracle
     tt = synth.make_road_graph(seed=0).tt
     snaps = load_snapshots()
-    threads = oracle.max_threads()
+    threads = host_threads()
     name, ep, n_evals, _ = snaps[0]
     t = time.perf_counter()
     p = oracle.osp_build(ep, tt, n_threads=threads, veh_step=64)
@@ -210,29 +218,40 @@ def main():
     gather_bufs = {}
 
     def allgather_pool():
-        """NCCL all-gather of the rank pools (padded), payload stays on the device."""
+        """One NCCL all-gather of the rank pools (sizes, then one packed padded payload straight from
+        the device-resident pool), then the on-device permutation back to vehicle-major order."""
+        from amod_b200 import dist as adist
         P, NT, NS = b.pool_sizes()
         sizes = torch.tensor([P, NT, NS], dtype=torch.int64, device=dev)
         all_sizes = torch.empty(world * 3, dtype=torch.int64, device=dev)
         dist.all_gather_into_tensor(all_sizes, sizes)
-        mx = all_sizes.view(world, 3).max(dim=0).values.tolist()
+        all_sizes = all_sizes.view(world, 3).cpu()
+        mx = [1 << int(np.ceil(np.log2(max(int(x), 1) + 1))) for x in all_sizes.max(dim=0).values.tolist()]   # pow2: buffers get reused
         o = capi.AmodPool()
         o.cap_entries, o.cap_trip_reqs, o.cap_stops = mx[0], mx[1], mx[2]
-        bufs = {}
+        layout, off = {}, 0
         for fname, dt, key in capi.POOL_FIELDS:
             n = {"e": mx[0], "e1": mx[0] + 1, "t": mx[1], "s": mx[2]}[key]
-            tdt = {np.int32: torch.int32, np.int64: torch.int64, np.float64: torch.float64}[dt]
-            k = (fname, n)
-            if k not in gather_bufs:
-                gather_bufs[k] = (torch.empty(max(n, 1), dtype=tdt, device=dev), torch.empty(world * max(n, 1), dtype=tdt, device=dev))
-            bufs[fname] = gather_bufs[k]
-            setattr(o, fname, bufs[fname][0].data_ptr())
+            layout[fname] = (off, n, dt)
+            off += (n * np.dtype(dt).itemsize + 15) // 16 * 16
+        key = tuple(mx)
+        if key not in gather_bufs:
+            gather_bufs[key] = (torch.empty(off, dtype=torch.uint8, device=dev), torch.empty(world * off, dtype=torch.uint8, device=dev))
+        src, dst = gather_bufs[key]
+        for fname, (o_, n, dt) in layout.items():
+            setattr(o, fname, src.data_ptr() + o_)
         b._check(b.lib.amod_pool_fetch(b.h, o, capi.LOC_DEVICE))
-        nbytes = 0
-        for fname, (src, dst) in bufs.items():
-            dist.all_gather_into_tensor(dst, src)
-            nbytes += dst.numel() * dst.element_size()
-        return nbytes
+        dist.all_gather_into_tensor(dst, src)
+        tdt = {np.int32: torch.int32, np.int64: torch.int64, np.float64: torch.float64}
+        rank_pools = []
+        for r in range(world):
+            Pr, NTr, NSr = (int(x) for x in all_sizes[r])
+            cnt = {"e": Pr, "e1": Pr + 1, "t": NTr, "s": NSr}
+            base = r * off
+            rank_pools.append({fname: dst[base + o_: base + o_ + cnt[key_] * np.dtype(dt).itemsize].view(tdt[dt])
+                               for (fname, dt, key_), (o_, n, _d) in zip(capi.POOL_FIELDS, layout.values())})
+        merged = adist.merge_vehicle_major_torch(rank_pools, world)
+        return dst.numel(), merged
 
     ptr_of = lambda t: t.data_ptr()
 
@@ -251,11 +270,11 @@ def main():
     # ---- device-resident arm (value) ---------------------------------------------------------------
     for i in range(args.warmup):
         step_resident(i)
-    barrier()
     sampler = ClockSampler(local) if rank == 0 else None
     if sampler:
         sampler.start()
         time.sleep(0.25)
+    barrier()                       # every rank enters the timed region together
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     evals = lookups_eval = launches = 0
     ms_eval = 0.0

@@ -95,3 +95,20 @@ def test_shard_and_merge_is_vehicle_major():
     merged = dist.merge_vehicle_major(parts, ep.n_veh)
     ok, why = marshal.pools_equal(merged, gold, check_kind=True)
     assert ok, why
+
+
+def test_torch_merge_matches_numpy_merge():
+    import torch
+    from amod_b200 import dist
+    tt, cases = load_golden("rand_real_osp_cap4")
+    ep, gold = cases[2]
+    world = 3
+    rank_pools = []
+    for rank in range(world):
+        sub, sel = ep.shard(rank, world)
+        p = oracle.osp_build(sub, tt)
+        rank_pools.append({f: torch.from_numpy(np.ascontiguousarray(getattr(p, f))) for f in marshal.Pool.FIELDS})
+    m = dist.merge_vehicle_major_torch(rank_pools, world)
+    got = marshal.Pool(**{f: m[f].numpy() for f in marshal.Pool.FIELDS})
+    ok, why = marshal.pools_equal(got, gold, check_kind=True)
+    assert ok, why
