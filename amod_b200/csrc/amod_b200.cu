@@ -246,7 +246,7 @@ static int validate_host_epoch(amod_ctx* ctx, const amod_epoch* ep) {
 static int upload_epoch(amod_ctx* ctx, const amod_epoch* ep, int loc, DEpoch* d) {
     if (ep->n_veh < 0 || ep->n_req < 0 || ep->n_search < 0) return ctx->fail(AMOD_E_BADARG, "negative size");
     if (ep->cap < 1 || ep->cap > AMOD_MAX_CAP) return ctx->fail(AMOD_E_LIMIT, "capacity %d outside 1..%d", ep->cap, AMOD_MAX_CAP);
-    if (ep->n_req > 16383) return ctx->fail(AMOD_E_LIMIT, "more than 16383 live requests in one epoch");
+    if (ep->n_req > (1 << 29)) return ctx->fail(AMOD_E_LIMIT, "too many live requests in one epoch");
     d->n_veh = ep->n_veh; d->n_req = ep->n_req; d->n_search = ep->n_search; d->cap = ep->cap; d->mode = ep->mode;
     d->T = (double)ep->T;
     if (loc == AMOD_LOC_DEVICE) {

@@ -10,7 +10,7 @@
 #define FULL 0xffffffffu
 
 typedef long long i64;
-typedef int16_t code_t;  // stop code: 2*req + (0 pick | 1 drop), -1 = rebalancing stop
+typedef int32_t code_t;  // stop code: 2*req + (0 pick | 1 drop), -1 = rebalancing stop
 
 // Device view of one epoch (include/amod_b200.h: struct amod_epoch).
 struct DEpoch {

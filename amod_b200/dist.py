@@ -71,7 +71,7 @@ def allgather_pool(local: Pool, sel: np.ndarray, n_veh: int, mode_sba: bool = Fa
     return (merge_sba if mode_sba else merge_vehicle_major)(parts, n_veh)
 
 
-def merge_vehicle_major_torch(rank_pools: list[dict], world: int) -> dict:
+def merge_vehicle_major_torch(rank_pools: list[dict], world: int, totals: dict | None = None) -> dict:
     """Device-side version of merge_vehicle_major for interleaved sharding (vehicle v lives on rank
     v % world as local vehicle v // world).  rank_pools[r] maps Pool field name -> torch tensor
     (already trimmed to the rank's sizes) on one device; returns the merged pool tensors in the
@@ -95,7 +95,8 @@ def merge_vehicle_major_torch(rank_pools: list[dict], world: int) -> dict:
         new_off = torch.zeros(lens.numel() + 1, dtype=torch.int64, device=lens.device)
         torch.cumsum(lens, 0, out=new_off[1:])
         data = torch.cat([p[data_name] for p in rank_pools])
-        idx = torch.repeat_interleave(starts - new_off[:-1], lens) + torch.arange(int(new_off[-1]), device=lens.device)
+        total = int(totals[data_name]) if totals is not None else int(data.numel())   # known on the host: no device sync
+        idx = torch.repeat_interleave(starts - new_off[:-1], lens, output_size=total) + torch.arange(total, device=lens.device)
         out[off_name] = new_off
         out[data_name] = data[idx]
     return out

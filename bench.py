@@ -186,6 +186,7 @@ def main():
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
+        os.environ["NCCL_DEBUG"] = "WARN"        # keep stdout to the one JSON line
         dist.init_process_group("nccl", device_id=dev)
     assert world == args.gpus or world == 1
 
@@ -250,7 +251,8 @@ def main():
             base = r * off
             rank_pools.append({fname: dst[base + o_: base + o_ + cnt[key_] * np.dtype(dt).itemsize].view(tdt[dt])
                                for (fname, dt, key_), (o_, n, _d) in zip(capi.POOL_FIELDS, layout.values())})
-        merged = adist.merge_vehicle_major_torch(rank_pools, world)
+        totals = {"trip_req": int(all_sizes[:, 1].sum()), "sche_code": int(all_sizes[:, 2].sum())}
+        merged = adist.merge_vehicle_major_torch(rank_pools, world, totals)
         return dst.numel(), merged
 
     ptr_of = lambda t: t.data_ptr()

@@ -148,3 +148,25 @@ def test_seam_functions_return_reference_style_records():
     for e, (veh, trip, sche, cost, score) in enumerate(recs):
         assert veh is vehs[gold.ent_veh[e]] and cost == gold.ent_cost[e]
     assert np.array_equal(recs.delays, gold.ent_delay)
+
+
+def test_cuda_sba_and_npo_at_peak_epoch_scale():
+    """BASELINE.json configs[4]: SBA matrix + NPO match at 20k vehicles x 5k pending requests."""
+    import oracle
+    tt = _grid()
+    b = builder_for(tt)
+    ep = synth.random_epoch(tt, n_veh=20000, n_pending=5000, cap=4, mode=marshal.MODE_SBA, seed=5, wait_sec=420, near=True,
+                            frac_new=1.0, T=5000)
+    assert ep.n_veh * ep.n_search == 100_000_000
+    ref = oracle.sba_build(ep, tt, n_threads=oracle.max_threads())
+    got = b.build_pool(ep)
+    ok, why = marshal.pools_equal(got, ref, rtol=0.0, check_kind=True)
+    assert ok, why
+    assert got.stats["n_evals"] == ref.stats["n_evals"] and got.stats["n_screens"] == 100_000_000
+    # NPO: idle vehicles x pending requests of the same epoch (rebalancing_npo.py:26-59)
+    idle = ep.veh_nid[ep.veh_status == marshal.ST_IDLE][:6000]
+    pend = ep.req_onid[ep.search][:1500]
+    a = oracle.npo_match(tt, idle, pend)
+    g = b.npo_match(idle, pend)
+    for x, y in zip(a, g):
+        assert np.array_equal(x, y)
