@@ -70,6 +70,7 @@ struct amod_ctx {
     GraphSlot graphs[3];
     unsigned long long buf_gen = 0;
     bool use_graph = true;
+    int level_hint[3] = {0, 0, 0};   // deepest non-empty trip level seen so far (+1 is searched before looking further)
     // capacities (grown from the sizes an epoch needed; persisted across epochs)
     i64 cap_tasks = 1 << 18, cap_chunks = 1 << 19, cap_ent = 1 << 18, cap_ptr = 1 << 19, cap_pst = 1 << 21;
     i64 cap_trips[MAX_LEVELS], cap_sch[MAX_LEVELS];
@@ -432,7 +433,8 @@ static int enqueue_build(amod_ctx* ctx, int mode, Table<TT> tt, int max_level, c
     }
     // ---- pool assembly --------------------------------------------------------------------------------
     {
-        const LevelSet& lsp = ls;
+        LevelSet lsp = ls;
+        lsp.n = max_level + 1;          // only the levels searched this epoch hold current data
         k_pool_veh_count<<<G, 256, 0, st>>>(d, lsp, ctl, ctx->veh_cnt.as<int>());
         scan_dev(ctx, InVehInt{ctx->veh_cnt.as<int>(), d}, ctx->veh_off.as<i64>(), FinPoolEntries{ctl, pb.cap_ent, sba});
         k_pool_meta_veh<<<G, 256, 0, st>>>(d, lsp, len0, ctx->veh_off.as<i64>(), ctl, pb);
@@ -476,6 +478,9 @@ static int build_impl(amod_ctx* ctx, const amod_epoch* ep, int loc, amod_stats* 
     size_t n_ev = 0;
     Control* h = ctx->h_ctl;
     int attempt = 0;
+    // Trip levels above the deepest feasible one are empty: search one level past what the previous epoch
+    // reached and look further only if that level still produced trips (then the epoch is rerun deeper).
+    int run_levels = mode == AMOD_MODE_SBA ? 1 : std::min(max_level, std::max(2, ctx->level_hint[mode] + 1));
     for (;; attempt++) {
         if (attempt > 24) return ctx->fail(AMOD_E_NOMEM, "pool build did not converge after %d regrow attempts", attempt);
         const unsigned long long r0 = g_reallocs;
@@ -488,20 +493,20 @@ static int build_impl(amod_ctx* ctx, const amod_epoch* ep, int loc, amod_stats* 
             // the whole level loop is one CUDA graph: ~150 small kernels whose sizes all live on the device,
             // so a captured graph stays valid until a buffer moves or the dispatch mode / capacity changes
             amod_ctx::GraphSlot& gs = ctx->graphs[mode];
-            if (!gs.exec || gs.gen != ctx->buf_gen || gs.cap != d.cap || gs.base_len != base_len || gs.max_level != max_level ||
+            if (!gs.exec || gs.gen != ctx->buf_gen || gs.cap != d.cap || gs.base_len != base_len || gs.max_level != run_levels ||
                 gs.stream != (void*)st) {
                 if (gs.exec) { cudaGraphExecDestroy(gs.exec); gs.exec = nullptr; }
                 cudaGraph_t graph = nullptr;
                 CK(cudaStreamBeginCapture(st, cudaStreamCaptureModeRelaxed));
                 ctx->n_launches = 0;
-                int rc = enqueue_build(ctx, mode, tt, max_level, ls, pb, &n_ev);
+                int rc = enqueue_build(ctx, mode, tt, run_levels, ls, pb, &n_ev);
                 cudaError_t ce = cudaStreamEndCapture(st, &graph);
                 if (rc != AMOD_OK) { if (graph) cudaGraphDestroy(graph); return rc; }
                 CK(ce);
                 ce = cudaGraphInstantiate(&gs.exec, graph, 0);
                 cudaGraphDestroy(graph);
                 CK(ce);
-                gs.gen = ctx->buf_gen; gs.cap = d.cap; gs.base_len = base_len; gs.max_level = max_level; gs.launches = ctx->n_launches;
+                gs.gen = ctx->buf_gen; gs.cap = d.cap; gs.base_len = base_len; gs.max_level = run_levels; gs.launches = ctx->n_launches;
                 gs.n_ev = n_ev; gs.stream = (void*)st;
             }
             n_ev = gs.n_ev;
@@ -509,13 +514,16 @@ static int build_impl(amod_ctx* ctx, const amod_epoch* ep, int loc, amod_stats* 
             CK(cudaGraphLaunch(gs.exec, st));
         } else {
             ctx->n_launches = 0;
-            CKR(enqueue_build(ctx, mode, tt, max_level, ls, pb, &n_ev));
+            CKR(enqueue_build(ctx, mode, tt, run_levels, ls, pb, &n_ev));
         }
         CK(cudaEventRecord(ctx->ev1, st));
         CK(cudaMemcpyAsync(h, ctx->ctl.p, sizeof(Control), cudaMemcpyDeviceToHost, st));
         CK(cudaStreamSynchronize(st));
         CK(cudaGetLastError());
-        if (!h->overflow) break;
+        if (!h->overflow) {
+            if (run_levels < max_level && h->n_trips[run_levels] > 0) { run_levels = std::min(max_level, run_levels + 2); continue; }
+            break;
+        }
         // regrow exactly what overflowed (with headroom) and rerun the epoch
         auto grow = [](i64& cap, i64 need) { if (need > cap) cap = need + need / 2 + 1024; };
         grow(ctx->cap_tasks, h->need_tasks); grow(ctx->cap_chunks, h->need_chunks);
@@ -524,13 +532,18 @@ static int build_impl(amod_ctx* ctx, const amod_epoch* ep, int loc, amod_stats* 
         if (ctx->cap_tasks > 0x7ffffff0 || ctx->cap_chunks > 0x7ffffff0) return ctx->fail(AMOD_E_LIMIT, "more than 2^31 candidates in one level");
     }
     ctx->n_attempts = attempt + 1;
+    {
+        int deepest = 0;
+        for (int k = 1; k <= run_levels; k++) if (h->n_trips[k] > 0) deepest = k;
+        ctx->level_hint[mode] = std::max(ctx->level_hint[mode], deepest);   // monotone: a captured graph is reused, never thrashed
+    }
     if (h->stats.flags & 1ull) return ctx->fail(AMOD_E_LIMIT, "a vehicle schedule exceeds the compiled stop/capacity limits");
     const i64 P = h->n_ent, NT = h->n_ptr, NS = h->n_pst;
     ctx->pool_entries = P; ctx->pool_trip_reqs = NT; ctx->pool_stops = NS;
     ctx->pool_valid = true;
     int levels_done = 0;
     i64 total_tasks = 0;
-    for (int k = 1; k <= max_level; k++) if (h->n_trips[k] > 0) levels_done = k;
+    for (int k = 1; k <= run_levels; k++) if (h->n_trips[k] > 0) levels_done = k;
     if (out_stats) {
         memset(out_stats, 0, sizeof *out_stats);
         float ms = 0.f;
@@ -557,7 +570,7 @@ static int build_impl(amod_ctx* ctx, const amod_epoch* ep, int loc, amod_stats* 
         out_stats->reserved = ctx->n_attempts;
     }
     (void)total_tasks;
-    if (mode != AMOD_MODE_SBA && h->n_trips[max_level] > 0)
+    if (mode != AMOD_MODE_SBA && run_levels == max_level && h->n_trips[max_level] > 0)
         return ctx->fail(AMOD_E_LEVELS, "a feasible trip of size cap+4=%d exists; the reference raises IndexError here "
                                         "(dispatch_osp.py:8,226)", max_level);
     return AMOD_OK;

@@ -31,6 +31,7 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
+print_json = None
 METRIC = "schedules evaluated/sec; OSP pool-build ms/epoch (2000 veh cap4)"
 UNIT = "schedules/s"
 
@@ -159,7 +160,7 @@ def run_reference(args):
                              "sample": f"every {step}th vehicle of each snapshot, {args.steps} steps, oracle/amod_oracle.c (OpenMP); "
                                        f"the Python reference itself measured 45-71k schedules/s/core (BASELINE.md)"},
             "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line))
+    print_json(line)
 
 
 def main():
@@ -170,6 +171,11 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     args = ap.parse_args()
+    # stdout carries exactly one JSON line: everything else (NCCL banner, warnings) goes to stderr
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+    global print_json
+    print_json = lambda obj: os.write(real_stdout, (json.dumps(obj) + "\n").encode())
     if args.impl == "reference":
         return run_reference(args)
 
@@ -186,7 +192,6 @@ def main():
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
-        os.environ["NCCL_DEBUG"] = "WARN"        # keep stdout to the one JSON line
         dist.init_process_group("nccl", device_id=dev)
     assert world == args.gpus or world == 1
 
@@ -381,7 +386,7 @@ def main():
             "gpu_launches": int(launches_all), "clocks": clocks, "roofline": roofline}
     if cpu:
         line["cpu_baseline"] = cpu
-    print(json.dumps(line))
+    print_json(line)
     if world > 1:
         dist.destroy_process_group()
 
