@@ -15,6 +15,9 @@
 #pragma once
 #include "common.cuh"
 
+#ifndef EVAL_BLOCKS_PER_SM
+#define EVAL_BLOCKS_PER_SM 4
+#endif
 #define STAGE_SLOTS 96    // stops staged per warp step: nsub*l <= 32 (whole schedules) or l <= 38
 #define LEG_SLOTS 200     // travel times staged per warp step: nsub*(5l+2) <= 192
 
@@ -83,7 +86,7 @@ __device__ __forceinline__ void walk_j(const TT* __restrict__ lg, double PD, con
 }
 
 template <typename TT, int MODE>
-__global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, 3)
+__global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, EVAL_BLOCKS_PER_SM)
 k_eval(const DEpoch* __restrict__ epp, Table<TT> tt, Level prev, Level cur, const Control* __restrict__ ctl,
        const ChunkDesc* __restrict__ desc, int* __restrict__ chunk_cnt, uint8_t* __restrict__ lane_cnt,
        const i64* __restrict__ chunk_pos, Stats* stats) {
