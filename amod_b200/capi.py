@@ -74,7 +74,8 @@ def epoch_struct(ep, ptr_of=None) -> AmodEpoch:
 
 EXPORTS = ("amod_create", "amod_destroy", "amod_last_error", "amod_version", "amod_set_stream",
            "amod_osp_build", "amod_sba_build", "amod_pool_fetch", "amod_pool_view", "amod_npo_match",
-           "amod_gather_bench")
+           "amod_gather_bench", "amod_gpool_create", "amod_gpool_open_peers", "amod_pool_veh_counts", "amod_gpool_scatter",
+           "amod_gpool_view", "amod_gpool_fetch")
 
 _lib = None
 
@@ -113,6 +114,18 @@ def load_library(path: str | None = None) -> C.CDLL:
     lib.amod_gather_bench.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int,
                                       C.POINTER(C.c_double)]
     lib.amod_gather_bench.restype = C.c_int
+    lib.amod_gpool_create.argtypes = [C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_int32, C.c_void_p]
+    lib.amod_gpool_create.restype = C.c_int
+    lib.amod_gpool_open_peers.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p]
+    lib.amod_gpool_open_peers.restype = C.c_int
+    lib.amod_pool_veh_counts.argtypes = [C.c_void_p, C.c_void_p]
+    lib.amod_pool_veh_counts.restype = C.c_int
+    lib.amod_gpool_scatter.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32]
+    lib.amod_gpool_scatter.restype = C.c_int
+    lib.amod_gpool_view.argtypes = [C.c_void_p, C.POINTER(AmodPool)]
+    lib.amod_gpool_view.restype = C.c_int
+    lib.amod_gpool_fetch.argtypes = [C.c_void_p, C.POINTER(AmodPool)]
+    lib.amod_gpool_fetch.restype = C.c_int
     if path is None:
         _lib = lib
     return lib

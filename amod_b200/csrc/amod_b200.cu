@@ -11,6 +11,7 @@
 
 #include "common.cuh"
 #include "eval.cuh"
+#include "gpool.cuh"
 #include "levels.cuh"
 #include "npo.cuh"
 #include "pool.cuh"
@@ -84,6 +85,9 @@ struct amod_ctx {
     i64 pool_entries = 0, pool_trip_reqs = 0, pool_stops = 0;
     bool pool_valid = false;
     int n_attempts = 0;
+    // multi-GPU global pool (peer-mapped)
+    char* gp_base = nullptr; GPoolLayout gp_layout; GPoolPeers gp_peers; bool gp_open = false; int gp_max_veh = 0;
+    DevBuf gp_off, gp_tot; void* gp_peer_ptr[GPOOL_MAX_WORLD] = {nullptr};
     // npo
     DevBuf npo_in, npo_vm, npo_rm, npo_rb, npo_vb, npo_rdt, npo_mdt, npo_cnt;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
@@ -196,6 +200,9 @@ extern "C" void amod_destroy(amod_ctx* ctx) {
     if (ctx->h_ctl) cudaFreeHost(ctx->h_ctl);
     if (ctx->h_epoch) cudaFreeHost(ctx->h_epoch);
     if (ctx->fetch_pinned) cudaFreeHost(ctx->fetch_pinned);
+    for (int r = 0; r < GPOOL_MAX_WORLD; r++) if (ctx->gp_peer_ptr[r]) cudaIpcCloseMemHandle(ctx->gp_peer_ptr[r]);
+    if (ctx->gp_base) cudaFree(ctx->gp_base);
+    ctx->gp_off.release(); ctx->gp_tot.release();
     ctx->d_epoch.release();
     for (auto& g : ctx->graphs) if (g.exec) cudaGraphExecDestroy(g.exec);
     if (ctx->ep_pinned) cudaFreeHost(ctx->ep_pinned);
@@ -628,6 +635,9 @@ extern "C" int amod_pool_fetch(amod_ctx* ctx, amod_pool* o, int loc) {
     for (auto& p : parts) total += (p.bytes + 63) & ~(size_t)63;
     if (total > ctx->fetch_pinned_cap) {
         if (ctx->fetch_pinned) cudaFreeHost(ctx->fetch_pinned);
+    for (int r = 0; r < GPOOL_MAX_WORLD; r++) if (ctx->gp_peer_ptr[r]) cudaIpcCloseMemHandle(ctx->gp_peer_ptr[r]);
+    if (ctx->gp_base) cudaFree(ctx->gp_base);
+    ctx->gp_off.release(); ctx->gp_tot.release();
         ctx->fetch_pinned = nullptr; ctx->fetch_pinned_cap = 0;
         CK(cudaMallocHost(&ctx->fetch_pinned, total + total / 2));
         ctx->fetch_pinned_cap = total + total / 2;
@@ -643,6 +653,147 @@ extern "C" int amod_pool_fetch(amod_ctx* ctx, amod_pool* o, int loc) {
         if (p.bytes) memcpy(p.dst, (char*)ctx->fetch_pinned + off, p.bytes);
         off += (p.bytes + 63) & ~(size_t)63;
     }
+    return AMOD_OK;
+}
+
+
+// ------------------------------------------------------------------------------------------------
+// multi-GPU: global pool in peer-mapped memory
+// ------------------------------------------------------------------------------------------------
+static GPoolLayout gpool_layout(i64 ce, i64 ct, i64 cs) {
+    GPoolLayout L; memset(&L, 0, sizeof L);
+    L.cap_ent = ce; L.cap_ptr = ct; L.cap_pst = cs;
+    i64 o = 0;
+    auto take = [&](i64 bytes) { i64 at = o; o += (bytes + 255) / 256 * 256; return at; };
+    L.o_hdr = take(64); L.o_veh = take(4 * ce); L.o_kind = take(4 * ce); L.o_nfeas = take(4 * ce); L.o_cost = take(8 * ce);
+    L.o_delay = take(8 * ce); L.o_toff = take(8 * (ce + 1)); L.o_soff = take(8 * (ce + 1)); L.o_treq = take(4 * ct); L.o_scode = take(4 * cs);
+    L.bytes = o;
+    return L;
+}
+
+extern "C" int amod_gpool_create(amod_ctx* ctx, int64_t cap_entries, int64_t cap_trip_reqs, int64_t cap_stops, int32_t max_veh_total,
+                                 void* ipc_handle_out) {
+    if (!ctx || !ipc_handle_out || cap_entries <= 0 || cap_trip_reqs <= 0 || cap_stops <= 0 || max_veh_total <= 0) return AMOD_E_BADARG;
+    static_assert(sizeof(cudaIpcMemHandle_t) == AMOD_IPC_HANDLE_BYTES, "ipc handle size");
+    CK(cudaSetDevice(ctx->device));
+    if (ctx->gp_base) return ctx->fail(AMOD_E_BADARG, "global pool already created on this context");
+    ctx->gp_layout = gpool_layout(cap_entries, cap_trip_reqs, cap_stops);
+    CK(cudaMalloc((void**)&ctx->gp_base, (size_t)ctx->gp_layout.bytes));
+    CK(cudaMemset(ctx->gp_base, 0, 64));
+    ctx->gp_max_veh = max_veh_total;
+    CK(ctx->gp_off.ensure(8 * 3 * ((size_t)max_veh_total + 2)));
+    CK(ctx->gp_tot.ensure(8 * 4));
+    cudaIpcMemHandle_t h;
+    CK(cudaIpcGetMemHandle(&h, ctx->gp_base));
+    memcpy(ipc_handle_out, &h, sizeof h);
+    return AMOD_OK;
+}
+
+extern "C" int amod_gpool_open_peers(amod_ctx* ctx, int32_t world, int32_t rank, const void* handles) {
+    if (!ctx || !handles || world < 1 || world > GPOOL_MAX_WORLD || rank < 0 || rank >= world) return AMOD_E_BADARG;
+    if (!ctx->gp_base) return ctx->fail(AMOD_E_BADARG, "amod_gpool_create first");
+    CK(cudaSetDevice(ctx->device));
+    memset(&ctx->gp_peers, 0, sizeof ctx->gp_peers);
+    ctx->gp_peers.world = world; ctx->gp_peers.rank = rank;
+    for (int r = 0; r < world; r++) {
+        if (r == rank) { ctx->gp_peers.base[r] = ctx->gp_base; continue; }
+        cudaIpcMemHandle_t h;
+        memcpy(&h, (const char*)handles + (size_t)r * AMOD_IPC_HANDLE_BYTES, sizeof h);
+        void* p = nullptr;
+        CK(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+        ctx->gp_peer_ptr[r] = p;
+        ctx->gp_peers.base[r] = (char*)p;
+    }
+    ctx->gp_open = true;
+    return AMOD_OK;
+}
+
+static PoolBufs pool_bufs_of(amod_ctx* ctx) {
+    PoolBufs pb; memset(&pb, 0, sizeof pb);
+    pb.cap_ent = ctx->cap_ent; pb.cap_ptr = ctx->cap_ptr; pb.cap_pst = ctx->cap_pst;
+    pb.ent_veh = ctx->ent_veh.as<int>(); pb.ent_kind = ctx->ent_kind.as<int>(); pb.ent_nfeas = ctx->ent_nfeas.as<int>();
+    pb.ent_tlen = ctx->ent_tlen.as<int>(); pb.ent_slen = ctx->ent_slen.as<int>(); pb.ent_src = ctx->ent_src.as<int>();
+    pb.ent_trip = ctx->ent_trip.as<int>(); pb.ent_cost = ctx->ent_cost.as<double>(); pb.ent_delay = ctx->ent_delay.as<double>();
+    pb.trip_off = ctx->trip_off.as<i64>(); pb.sche_off = ctx->sche_off.as<i64>(); pb.trip_req = ctx->trip_req.as<int>();
+    pb.sche_code = ctx->sche_code.as<int>();
+    return pb;
+}
+
+extern "C" int amod_pool_veh_counts(amod_ctx* ctx, int32_t* counts_dev) {
+    if (!ctx || !counts_dev) return AMOD_E_BADARG;
+    if (!ctx->pool_valid) return ctx->fail(AMOD_E_BADARG, "no pool has been built on this context");
+    if (ctx->h_epoch->mode == AMOD_MODE_SBA) return ctx->fail(AMOD_E_BADARG, "per-vehicle counts need a vehicle-major (OSP) pool");
+    CK(cudaSetDevice(ctx->device));
+    k_veh_counts<<<ctx->n_sm * 2, 256, 0, ctx->stream>>>(ctx->d_epoch.as<DEpoch>(), ctx->veh_off.as<i64>(), ctx->ctl.as<Control>(),
+                                                       pool_bufs_of(ctx), counts_dev);
+    CK(cudaGetLastError());
+    return AMOD_OK;
+}
+
+extern "C" int amod_gpool_scatter(amod_ctx* ctx, const int32_t* counts_all_dev, int32_t veh_per_rank_max, int32_t n_veh_total) {
+    if (!ctx || !counts_all_dev) return AMOD_E_BADARG;
+    if (!ctx->gp_open) return ctx->fail(AMOD_E_BADARG, "amod_gpool_open_peers first");
+    if (!ctx->pool_valid) return ctx->fail(AMOD_E_BADARG, "no pool has been built on this context");
+    if (n_veh_total > ctx->gp_max_veh) return ctx->fail(AMOD_E_CAPACITY, "global pool was created for at most %d vehicles", ctx->gp_max_veh);
+    CK(cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    const int world = ctx->gp_peers.world;
+    i64* off = ctx->gp_off.as<i64>();
+    const size_t stride = (size_t)ctx->gp_max_veh + 2;
+    i64* tot = ctx->gp_tot.as<i64>();
+    CK(cudaMemsetAsync(tot + 3, 0, 8, st));
+    for (int c = 0; c < 3; c++)
+        scan_dev(ctx, InGlobalVeh{counts_all_dev, world, veh_per_rank_max, c, n_veh_total}, off + c * stride, FinStore{tot + c});
+    k_gpool_scatter<<<ctx->n_sm * 4, 256, 0, st>>>(ctx->d_epoch.as<DEpoch>(), ctx->veh_off.as<i64>(), pool_bufs_of(ctx), ctx->gp_layout,
+                                                 ctx->gp_peers, off, off + stride, off + 2 * stride, tot, n_veh_total,
+                                                 (unsigned long long*)(tot + 3));
+    i64 h[4];
+    CK(cudaMemcpyAsync(h, tot, sizeof h, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    CK(cudaGetLastError());
+    if (h[3]) return ctx->fail(AMOD_E_CAPACITY, "global pool too small: need %lld entries, %lld trip requests, %lld stops", h[0], h[1], h[2]);
+    return AMOD_OK;
+}
+
+extern "C" int amod_gpool_view(amod_ctx* ctx, amod_pool* v) {
+    if (!ctx || !v) return AMOD_E_BADARG;
+    if (!ctx->gp_base) return ctx->fail(AMOD_E_BADARG, "amod_gpool_create first");
+    CK(cudaSetDevice(ctx->device));
+    i64 h[3];
+    CK(cudaMemcpyAsync(h, ctx->gp_base + ctx->gp_layout.o_hdr, sizeof h, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    const GPoolLayout& L = ctx->gp_layout;
+    char* B = ctx->gp_base;
+    v->cap_entries = L.cap_ent; v->cap_trip_reqs = L.cap_ptr; v->cap_stops = L.cap_pst;
+    v->n_entries = h[0]; v->n_trip_reqs = h[1]; v->n_stops = h[2];
+    v->ent_veh = (int32_t*)(B + L.o_veh); v->ent_kind = (int32_t*)(B + L.o_kind); v->ent_nfeas = (int32_t*)(B + L.o_nfeas);
+    v->ent_cost = (double*)(B + L.o_cost); v->ent_delay = (double*)(B + L.o_delay); v->ent_trip_off = (int64_t*)(B + L.o_toff);
+    v->ent_sche_off = (int64_t*)(B + L.o_soff); v->trip_req = (int32_t*)(B + L.o_treq); v->sche_code = (int32_t*)(B + L.o_scode);
+    return AMOD_OK;
+}
+
+extern "C" int amod_gpool_fetch(amod_ctx* ctx, amod_pool* o) {
+    if (!ctx || !o) return AMOD_E_BADARG;
+    amod_pool v;
+    CKR(amod_gpool_view(ctx, &v));
+    o->n_entries = v.n_entries; o->n_trip_reqs = v.n_trip_reqs; o->n_stops = v.n_stops;
+    if (o->cap_entries < v.n_entries || o->cap_trip_reqs < v.n_trip_reqs || o->cap_stops < v.n_stops)
+        return ctx->fail(AMOD_E_CAPACITY, "pool buffers too small: need %lld entries, %lld trip requests, %lld stops",
+                         (long long)v.n_entries, (long long)v.n_trip_reqs, (long long)v.n_stops);
+    const size_t P = (size_t)v.n_entries, NT = (size_t)v.n_trip_reqs, NS = (size_t)v.n_stops;
+    cudaStream_t st = ctx->stream;
+    if (P) {
+        CK(cudaMemcpyAsync(o->ent_veh, v.ent_veh, 4 * P, cudaMemcpyDeviceToHost, st));
+        CK(cudaMemcpyAsync(o->ent_kind, v.ent_kind, 4 * P, cudaMemcpyDeviceToHost, st));
+        CK(cudaMemcpyAsync(o->ent_nfeas, v.ent_nfeas, 4 * P, cudaMemcpyDeviceToHost, st));
+        CK(cudaMemcpyAsync(o->ent_cost, v.ent_cost, 8 * P, cudaMemcpyDeviceToHost, st));
+        CK(cudaMemcpyAsync(o->ent_delay, v.ent_delay, 8 * P, cudaMemcpyDeviceToHost, st));
+    }
+    CK(cudaMemcpyAsync(o->ent_trip_off, v.ent_trip_off, 8 * (P + 1), cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(o->ent_sche_off, v.ent_sche_off, 8 * (P + 1), cudaMemcpyDeviceToHost, st));
+    if (NT) CK(cudaMemcpyAsync(o->trip_req, v.trip_req, 4 * NT, cudaMemcpyDeviceToHost, st));
+    if (NS) CK(cudaMemcpyAsync(o->sche_code, v.sche_code, 4 * NS, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
     return AMOD_OK;
 }
 

@@ -1,0 +1,72 @@
+// gpool.cuh — multi-GPU assembly of the vehicle-major pool with peer stores over NVLink.
+// Each rank scatters its own vehicles' entries into every rank's global pool (cudaIpc-mapped), at the
+// positions given by a prefix sum over the all-gathered per-vehicle counts (dispatch_osp.py:107 order).
+#pragma once
+#include "common.cuh"
+#include "pool.cuh"
+
+#define GPOOL_MAX_WORLD 16
+
+struct GPoolLayout {         // one contiguous allocation per rank; identical layout on every rank
+    i64 cap_ent, cap_ptr, cap_pst;
+    i64 o_hdr, o_veh, o_kind, o_nfeas, o_cost, o_delay, o_toff, o_soff, o_treq, o_scode, bytes;
+};
+struct GPoolPeers { char* base[GPOOL_MAX_WORLD]; int world, rank; };
+
+// per local vehicle: entries, trip requests, stops of the local (vehicle-major) pool
+__global__ void k_veh_counts(const DEpoch* __restrict__ epp, const i64* __restrict__ veh_off, const Control* __restrict__ ctl,
+                             PoolBufs pb, int* __restrict__ out) {
+    const int n = epp->n_veh;
+    for (int v = blockIdx.x * blockDim.x + threadIdx.x; v < n; v += gridDim.x * blockDim.x) {
+        const i64 e0 = veh_off[v], e1 = veh_off[v + 1];
+        out[3 * v + 0] = (int)(e1 - e0);
+        out[3 * v + 1] = (int)(pb.trip_off[e1] - pb.trip_off[e0]);
+        out[3 * v + 2] = (int)(pb.sche_off[e1] - pb.sche_off[e0]);
+    }
+}
+
+struct InGlobalVeh {         // counts in global vehicle order: vehicle v = local v / world of rank v % world
+    const int* all; int world, vmax, comp, n_total;
+    __device__ __forceinline__ i64 size() const { return n_total; }
+    __device__ __forceinline__ i64 operator()(i64 v) const { return all[((v % world) * (i64)vmax + v / world) * 3 + comp]; }
+};
+struct FinStore { i64* dst; __device__ __forceinline__ void operator()(i64 tot) const { *dst = tot; } };
+
+// one warp per local vehicle: copy its entries + payload to every rank's global pool
+__global__ void __launch_bounds__(256)
+k_gpool_scatter(const DEpoch* __restrict__ epp, const i64* __restrict__ veh_off, PoolBufs pb, GPoolLayout L, GPoolPeers peers,
+                const i64* __restrict__ goff_e, const i64* __restrict__ goff_t, const i64* __restrict__ goff_s,
+                const i64* __restrict__ totals /*[3]*/, int n_veh_total, unsigned long long* err) {
+    const int lane = threadIdx.x & 31;
+    const int nwarps = gridDim.x * (blockDim.x >> 5);
+    const int n_local = epp->n_veh;
+    const bool fits = totals[0] <= L.cap_ent && totals[1] <= L.cap_ptr && totals[2] <= L.cap_pst;
+    if (!fits) { if (blockIdx.x == 0 && threadIdx.x == 0) atomicOr(err, 1ull); return; }
+    if (blockIdx.x == 0 && threadIdx.x < 3) {    // header of OUR pool: global sizes (every rank computes the same totals)
+        ((i64*)(peers.base[peers.rank] + L.o_hdr))[threadIdx.x] = totals[threadIdx.x];
+    }
+    for (int u = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); u < n_local; u += nwarps) {
+        const int v = u * peers.world + peers.rank;
+        const i64 e0 = veh_off[u], e1 = veh_off[u + 1];
+        const i64 E0 = goff_e[v], T0 = goff_t[v], S0 = goff_s[v];
+        const i64 t0 = pb.trip_off[e0], s0 = pb.sche_off[e0];
+        const i64 nt = pb.trip_off[e1] - t0, ns = pb.sche_off[e1] - s0;
+        const bool last = v == n_veh_total - 1;
+        for (int d = 0; d < peers.world; d++) {
+            char* B = peers.base[d];
+            int* g_veh = (int*)(B + L.o_veh); int* g_kind = (int*)(B + L.o_kind); int* g_nfeas = (int*)(B + L.o_nfeas);
+            double* g_cost = (double*)(B + L.o_cost); double* g_delay = (double*)(B + L.o_delay);
+            i64* g_toff = (i64*)(B + L.o_toff); i64* g_soff = (i64*)(B + L.o_soff);
+            int* g_treq = (int*)(B + L.o_treq); int* g_scode = (int*)(B + L.o_scode);
+            for (i64 e = e0 + lane; e < e1; e += 32) {
+                const i64 E = E0 + (e - e0);
+                g_veh[E] = v; g_kind[E] = pb.ent_kind[e]; g_nfeas[E] = pb.ent_nfeas[e];
+                g_cost[E] = pb.ent_cost[e]; g_delay[E] = pb.ent_delay[e];
+                g_toff[E] = T0 + (pb.trip_off[e] - t0); g_soff[E] = S0 + (pb.sche_off[e] - s0);
+            }
+            for (i64 x = lane; x < nt; x += 32) g_treq[T0 + x] = pb.trip_req[t0 + x];
+            for (i64 x = lane; x < ns; x += 32) g_scode[S0 + x] = pb.sche_code[s0 + x];
+            if (last && lane == 0) { g_toff[totals[0]] = totals[1]; g_soff[totals[0]] = totals[2]; }   // CSR end sentinels
+        }
+    }
+}

@@ -100,3 +100,68 @@ def merge_vehicle_major_torch(rank_pools: list[dict], world: int, totals: dict |
         out[off_name] = new_off
         out[data_name] = data[idx]
     return out
+
+
+class PeerPool:
+    """Vehicle-major pool of the whole fleet assembled on every rank by peer stores over NVLink
+    (include/amod_b200.h, amod_gpool_*): the only collectives are the all-gather of per-vehicle
+    counts and a barrier.  OSP modes; vehicles interleaved v % world."""
+
+    def __init__(self, builder, world: int, rank: int, n_veh_total: int, cap_entries: int, cap_trip_reqs: int,
+                 cap_stops: int, device):
+        import ctypes as C
+
+        import torch
+        import torch.distributed as dist
+        self.b, self.world, self.rank, self.n_veh_total, self.device = builder, world, rank, n_veh_total, device
+        self.vmax = (n_veh_total + world - 1) // world
+        handle = C.create_string_buffer(64)
+        builder._check(builder.lib.amod_gpool_create(builder.h, cap_entries, cap_trip_reqs, cap_stops, n_veh_total, handle))
+        handles = [None] * world
+        dist.all_gather_object(handles, bytes(handle.raw))
+        blob = C.create_string_buffer(b"".join(handles), 64 * world)
+        builder._check(builder.lib.amod_gpool_open_peers(builder.h, world, rank, blob))
+        self.counts = torch.zeros(self.vmax * 3, dtype=torch.int32, device=device)
+        self.counts_all = torch.zeros(world * self.vmax * 3, dtype=torch.int32, device=device)
+        self.nccl = dist.get_backend() == "nccl"
+        dist.barrier()
+
+    def assemble(self):
+        """Call after builder.build(...) of this rank's slice.  Returns nothing; the pool is in this
+        rank's global pool (view()/fetch())."""
+        import torch
+        import torch.distributed as dist
+        b = self.b
+        self.counts.zero_()
+        b._check(b.lib.amod_pool_veh_counts(b.h, self.counts.data_ptr()))
+        if self.nccl:
+            dist.all_gather_into_tensor(self.counts_all, self.counts)
+        else:   # CPU collectives (tests on one GPU): stage through the host
+            torch.cuda.current_stream().synchronize()
+            parts = [torch.zeros(self.vmax * 3, dtype=torch.int32) for _ in range(self.world)]
+            dist.all_gather(parts, self.counts.cpu())
+            self.counts_all.copy_(torch.cat(parts))
+            torch.cuda.current_stream().synchronize()
+        b._check(b.lib.amod_gpool_scatter(b.h, self.counts_all.data_ptr(), self.vmax, self.n_veh_total))
+        dist.barrier()        # every rank's peer stores have landed before anyone reads
+
+    def view(self):
+        from . import capi
+        import ctypes as C
+        v = capi.AmodPool()
+        self.b._check(self.b.lib.amod_gpool_view(self.b.h, C.byref(v)))
+        return v
+
+    def fetch(self) -> Pool:
+        import ctypes as C
+
+        from . import capi
+        v = self.view()
+        n = {"e": v.n_entries, "e1": v.n_entries + 1, "t": v.n_trip_reqs, "s": v.n_stops}
+        arrs = {name: np.empty(max(int(n[key]), 1), dtype=dt) for name, dt, key in capi.POOL_FIELDS}
+        o = capi.AmodPool()
+        o.cap_entries, o.cap_trip_reqs, o.cap_stops = v.n_entries, v.n_trip_reqs, v.n_stops
+        for name, _dt, _key in capi.POOL_FIELDS:
+            setattr(o, name, arrs[name].ctypes.data)
+        self.b._check(self.b.lib.amod_gpool_fetch(self.b.h, C.byref(o)))
+        return Pool(**{name: arrs[name][:int(n[key])] for name, _dt, key in capi.POOL_FIELDS})

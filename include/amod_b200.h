@@ -140,6 +140,26 @@ int amod_pool_fetch(amod_ctx* ctx, amod_pool* out, int loc);
 /* Device pointers of the last built pool (valid until the next build on ctx). */
 int amod_pool_view(amod_ctx* ctx, amod_pool* view);
 
+/* ---- multi-GPU pool assembly over NVLink peer memory (one process per GPU) ----------
+ * Vehicles are interleaved over ranks (global vehicle v lives on rank v % world as local vehicle
+ * v / world).  Every rank owns one "global pool" buffer; after its local build each rank writes its
+ * vehicles' entries straight into EVERY rank's global pool at their final vehicle-major positions
+ * with peer stores (cudaIpc-mapped memory), so the only collectives left are the all-gather of the
+ * per-vehicle entry counts (a few KB) and a barrier.  OSP modes only (SBA order is request-major). */
+#define AMOD_IPC_HANDLE_BYTES 64
+int amod_gpool_create(amod_ctx* ctx, int64_t cap_entries, int64_t cap_trip_reqs, int64_t cap_stops,
+                      int32_t max_veh_total, void* ipc_handle_out /* AMOD_IPC_HANDLE_BYTES */);
+int amod_gpool_open_peers(amod_ctx* ctx, int32_t world, int32_t rank, const void* handles /* world x 64 B */);
+/* (entries, trip requests, stops) of every local vehicle of the last built pool -> counts_dev[n_veh*3] */
+int amod_pool_veh_counts(amod_ctx* ctx, int32_t* counts_dev);
+/* counts_all_dev[world][veh_per_rank_max][3] = the all-gathered counts.  Writes this rank's entries
+ * into all peers' global pools.  The caller must run a barrier before any rank reads its pool. */
+int amod_gpool_scatter(amod_ctx* ctx, const int32_t* counts_all_dev, int32_t veh_per_rank_max, int32_t n_veh_total);
+/* device pointers + sizes of this rank's global pool (valid after the barrier) */
+int amod_gpool_view(amod_ctx* ctx, amod_pool* view);
+/* copy this rank's global pool into caller-owned HOST buffers (AMOD_E_CAPACITY reports the sizes needed) */
+int amod_gpool_fetch(amod_ctx* ctx, amod_pool* out_host);
+
 /* B3: NPO matching (rebalancing_npo.py:26-59).  idle_nid[i] = node of the i-th IDLE vehicle
  * in fleet order, pend_onid[j] = origin of the j-th PENDING request in id order.  Writes
  * min(n_idle,n_pend) matches in the reference's selection order. */

@@ -1,0 +1,69 @@
+"""Multi-rank pool assembly over peer-mapped memory (amod_gpool_*): two ranks (two GPUs when the box
+has them, otherwise two processes sharing GPU 0 — cudaIpc works either way), each builds its
+interleaved vehicle slice and scatters it into every rank's global pool; both must hold the
+reference's full vehicle-major pool.  The tiny collectives use gloo here so the test also runs on
+one GPU; bench.py uses NCCL."""
+import os
+import socket
+import sys
+
+import numpy as np
+import pytest
+import torch
+import torch.multiprocessing as mp
+
+from conftest import ROOT
+
+pytestmark = pytest.mark.gpu
+
+
+def _free_port():
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); p = s.getsockname()[1]; s.close()
+    return p
+
+
+def _worker(rank, world, port, out_dir):
+    sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "oracle")); sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"; os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    import oracle
+    from amod_b200 import dist as adist, marshal, synth
+    from amod_b200.pool import PoolBuilder
+    dev_index = rank % torch.cuda.device_count()
+    torch.cuda.set_device(dev_index)
+    dev = torch.device("cuda", dev_index)
+    stream = torch.cuda.Stream(device=dev)
+    torch.cuda.set_stream(stream)
+    tt = synth.make_road_graph(900, seed=4).tt
+    b = PoolBuilder(tt, device=dev_index)
+    b.set_stream(stream.cuda_stream)
+    ok = True
+    why = ""
+    pp = None
+    for seed in (1, 2, 3):
+        ep = synth.random_epoch(tt, n_veh=101, n_pending=50, cap=4, mode=marshal.MODE_OSP, seed=seed, wait_sec=300, near=True, T=4000)
+        ref = oracle.osp_build(ep, tt)
+        sub, _sel = ep.shard(rank, world)
+        b.build(sub)
+        if pp is None:
+            pp = adist.PeerPool(b, world, rank, ep.n_veh, 4 * ref.n_entries, 4 * ref.trip_req.size + 64, 4 * ref.sche_code.size + 64, dev)
+        pp.assemble()
+        got = pp.fetch()
+        o, w = marshal.pools_equal(got, ref, rtol=0.0, check_kind=True)
+        ok &= o
+        why = why or w
+        dist.barrier()    # nobody starts the next epoch's scatter while a peer still reads
+    np.save(os.path.join(out_dir, f"ok{rank}.npy"), np.array([int(ok)]))
+    if not ok:
+        open(os.path.join(out_dir, f"why{rank}.txt"), "w").write(why)
+    dist.destroy_process_group()
+
+
+def test_two_ranks_scatter_over_peer_memory(tmp_path):
+    world = 2
+    mp.spawn(_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
+    for r in range(world):
+        ok = int(np.load(tmp_path / f"ok{r}.npy")[0])
+        why = (tmp_path / f"why{r}.txt").read_text() if not ok else ""
+        assert ok, f"rank {r}: {why}"
