@@ -635,9 +635,6 @@ extern "C" int amod_pool_fetch(amod_ctx* ctx, amod_pool* o, int loc) {
     for (auto& p : parts) total += (p.bytes + 63) & ~(size_t)63;
     if (total > ctx->fetch_pinned_cap) {
         if (ctx->fetch_pinned) cudaFreeHost(ctx->fetch_pinned);
-    for (int r = 0; r < GPOOL_MAX_WORLD; r++) if (ctx->gp_peer_ptr[r]) cudaIpcCloseMemHandle(ctx->gp_peer_ptr[r]);
-    if (ctx->gp_base) cudaFree(ctx->gp_base);
-    ctx->gp_off.release(); ctx->gp_tot.release();
         ctx->fetch_pinned = nullptr; ctx->fetch_pinned_cap = 0;
         CK(cudaMallocHost(&ctx->fetch_pinned, total + total / 2));
         ctx->fetch_pinned_cap = total + total / 2;

@@ -221,44 +221,18 @@ def main():
             setattr(d, f, t)
         return d
 
-    gather_bufs = {}
+    peer = {}
 
     def allgather_pool():
-        """One NCCL all-gather of the rank pools (sizes, then one packed padded payload straight from
-        the device-resident pool), then the on-device permutation back to vehicle-major order."""
+        """Assemble the fleet-wide vehicle-major pool on every rank: NCCL all-gather of the per-vehicle
+        counts (a few KB), then each rank's scatter kernel writes its entries into all ranks' global pools
+        with peer stores over NVLink, then a barrier (amod_b200/dist.py PeerPool)."""
         from amod_b200 import dist as adist
-        P, NT, NS = b.pool_sizes()
-        sizes = torch.tensor([P, NT, NS], dtype=torch.int64, device=dev)
-        all_sizes = torch.empty(world * 3, dtype=torch.int64, device=dev)
-        dist.all_gather_into_tensor(all_sizes, sizes)
-        all_sizes = all_sizes.view(world, 3).cpu()
-        mx = [1 << int(np.ceil(np.log2(max(int(x), 1) + 1))) for x in all_sizes.max(dim=0).values.tolist()]   # pow2: buffers get reused
-        o = capi.AmodPool()
-        o.cap_entries, o.cap_trip_reqs, o.cap_stops = mx[0], mx[1], mx[2]
-        layout, off = {}, 0
-        for fname, dt, key in capi.POOL_FIELDS:
-            n = {"e": mx[0], "e1": mx[0] + 1, "t": mx[1], "s": mx[2]}[key]
-            layout[fname] = (off, n, dt)
-            off += (n * np.dtype(dt).itemsize + 15) // 16 * 16
-        key = tuple(mx)
-        if key not in gather_bufs:
-            gather_bufs[key] = (torch.empty(off, dtype=torch.uint8, device=dev), torch.empty(world * off, dtype=torch.uint8, device=dev))
-        src, dst = gather_bufs[key]
-        for fname, (o_, n, dt) in layout.items():
-            setattr(o, fname, src.data_ptr() + o_)
-        b._check(b.lib.amod_pool_fetch(b.h, o, capi.LOC_DEVICE))
-        dist.all_gather_into_tensor(dst, src)
-        tdt = {np.int32: torch.int32, np.int64: torch.int64, np.float64: torch.float64}
-        rank_pools = []
-        for r in range(world):
-            Pr, NTr, NSr = (int(x) for x in all_sizes[r])
-            cnt = {"e": Pr, "e1": Pr + 1, "t": NTr, "s": NSr}
-            base = r * off
-            rank_pools.append({fname: dst[base + o_: base + o_ + cnt[key_] * np.dtype(dt).itemsize].view(tdt[dt])
-                               for (fname, dt, key_), (o_, n, _d) in zip(capi.POOL_FIELDS, layout.values())})
-        totals = {"trip_req": int(all_sizes[:, 1].sum()), "sche_code": int(all_sizes[:, 2].sum())}
-        merged = adist.merge_vehicle_major_torch(rank_pools, world, totals)
-        return dst.numel(), merged
+        if "pp" not in peer:
+            P, NT, NS = b.pool_sizes()
+            peer["pp"] = adist.PeerPool(b, world, rank, work[0]["n_veh_full"], 3 * world * P, 3 * world * NT + 1024,
+                                        3 * world * NS + 1024, dev)
+        peer["pp"].assemble()
 
     ptr_of = lambda t: t.data_ptr()
 
@@ -377,7 +351,7 @@ def main():
             "config": {"workload": f"OSP pool build (cut-off disabled), {work[0]['n_veh_full']} veh cap {work[0]['host'].cap}, "
                                    f"Manhattan-scale synthetic epoch snapshots x{len(work)} (bench_data/cfg2_*), 4091-node fp32 table",
                        "fleet": work[0]["n_veh_full"], "requests_considered": int(np.mean([w["host"].n_search for w in work])),
-                       "parallelism": f"vehicles interleaved over {world} rank(s)" + (", NCCL all-gather of the pool" if world > 1 else ""),
+                       "parallelism": f"vehicles interleaved over {world} rank(s)" + (", NCCL all-gather of per-vehicle counts + peer-store scatter of the pool over NVLink" if world > 1 else ""),
                        "l2_policy": "inputs differ every step (8 snapshots cycled); table deliberately L2-resident (67 MB persisting window)",
                        "pool_entries_per_step": entries_all / args.steps, "schedules_per_step": evals_all / args.steps},
             "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": e_h2d // args.steps, "d2h_bytes_per_step": e_d2h // args.steps,
