@@ -53,7 +53,8 @@ class AmodStats(C.Structure):
     _fields_ = [("n_screens", C.c_int64), ("n_evals", C.c_int64), ("n_lookups", C.c_int64),
                 ("n_entries", C.c_int64), ("n_sches_stored", C.c_int64), ("n_tasks", C.c_int64),
                 ("n_levels", C.c_int32), ("n_kernel_launches", C.c_int32), ("ms_build", C.c_double),
-                ("ms_eval", C.c_double), ("n_eval_launches", C.c_int32), ("reserved", C.c_int32)]
+                ("ms_eval", C.c_double), ("n_eval_launches", C.c_int32), ("n_attempts", C.c_int32),
+                ("n_chunks", C.c_int64), ("n_items", C.c_int64)]
 
     def as_dict(self):
         return {f: getattr(self, f) for f, _ in self._fields_ if f != "reserved"}

@@ -73,11 +73,11 @@ struct amod_ctx {
     bool use_graph = true;
     int level_hint[3] = {0, 0, 0};   // deepest non-empty trip level seen so far (+1 is searched before looking further)
     // capacities (grown from the sizes an epoch needed; persisted across epochs)
-    i64 cap_tasks = 1 << 18, cap_chunks = 1 << 19, cap_ent = 1 << 18, cap_ptr = 1 << 19, cap_pst = 1 << 21;
+    i64 cap_tasks = 1 << 18, cap_chunks = 1 << 18, cap_rows = 1 << 19, cap_ent = 1 << 18, cap_ptr = 1 << 19, cap_pst = 1 << 21;
     i64 cap_trips[MAX_LEVELS], cap_sch[MAX_LEVELS];
     // workspace
     DevBuf len0, S0, s0pos, flag8, pos, partial, task_veh[2], task_base[2], task_q[2], task_nchunk[2], task_chunk0, trip_pos,
-        chunk_desc, chunk_cnt, lane_cnt, chunk_pos, hash, row_cnt, row_off, tmp_j, tmp_q;
+        row_desc, task_nfeas, chunk_cnt, lane_cnt, chunk_pos, hash, row_cnt, row_off, tmp_j, tmp_q;
     LevelBufs lv[MAX_LEVELS];
     // pool
     DevBuf veh_cnt, veh_off, ent_veh, ent_kind, ent_nfeas, ent_tlen, ent_slen, ent_src, ent_trip, ent_cost, ent_delay,
@@ -188,7 +188,7 @@ extern "C" void amod_destroy(amod_ctx* ctx) {
     cudaDeviceSynchronize();
     DevBuf* all[] = {&ctx->ep_dev, &ctx->ctl, &ctx->len0, &ctx->S0, &ctx->s0pos, &ctx->flag8, &ctx->pos, &ctx->partial,
                      &ctx->task_veh[0], &ctx->task_veh[1], &ctx->task_base[0], &ctx->task_base[1], &ctx->task_q[0], &ctx->task_q[1],
-                     &ctx->task_nchunk[0], &ctx->task_nchunk[1], &ctx->task_chunk0, &ctx->trip_pos, &ctx->chunk_desc, &ctx->chunk_cnt,
+                     &ctx->task_nchunk[0], &ctx->task_nchunk[1], &ctx->task_chunk0, &ctx->trip_pos, &ctx->row_desc, &ctx->task_nfeas, &ctx->chunk_cnt,
                      &ctx->lane_cnt, &ctx->chunk_pos, &ctx->hash, &ctx->row_cnt, &ctx->row_off, &ctx->tmp_j, &ctx->tmp_q,
                      &ctx->veh_cnt, &ctx->veh_off, &ctx->ent_veh, &ctx->ent_kind, &ctx->ent_nfeas, &ctx->ent_tlen, &ctx->ent_slen,
                      &ctx->ent_src, &ctx->ent_trip, &ctx->ent_cost, &ctx->ent_delay, &ctx->trip_off, &ctx->sche_off, &ctx->trip_req,
@@ -321,7 +321,7 @@ static int ensure_buffers(amod_ctx* ctx, int V, i64 n_screen, int max_level, con
         CK(ctx->task_nchunk[w].ensure(4 * T));
     }
     CK(ctx->task_chunk0.ensure(8 * (T + 2))); CK(ctx->trip_pos.ensure(8 * (T + 2)));
-    CK(ctx->chunk_desc.ensure(sizeof(ChunkDesc) * C)); CK(ctx->chunk_cnt.ensure(4 * C)); CK(ctx->lane_cnt.ensure(64 * C)); CK(ctx->chunk_pos.ensure(8 * (C + 2)));
+    CK(ctx->row_desc.ensure(sizeof(RowDesc) * (size_t)ctx->cap_rows)); CK(ctx->task_nfeas.ensure(4 * T)); CK(ctx->chunk_cnt.ensure(4 * C)); CK(ctx->lane_cnt.ensure(64 * C)); CK(ctx->chunk_pos.ensure(8 * (C + 2)));
     CK(ctx->tmp_j.ensure(4 * T)); CK(ctx->tmp_q.ensure(4 * T));
     size_t max_trips = 1;
     memset(ls, 0, sizeof *ls);
@@ -399,23 +399,27 @@ static int enqueue_build(amod_ctx* ctx, int mode, Table<TT> tt, int max_level, c
         int* tv = ctx->task_veh[cur].as<int>(); int* tb = ctx->task_base[cur].as<int>(); int* tq = ctx->task_q[cur].as<int>();
         const Level& prev = ls.lv[k - 1];
         const Level& lv = ls.lv[k];
-        i64* chunk0 = ctx->task_chunk0.as<i64>();
+        i64* row0 = ctx->task_chunk0.as<i64>();
         i64* cpos = ctx->chunk_pos.as<i64>();
-        scan_dev(ctx, InArray<int>{ctx->task_nchunk[cur].as<int>(), &ctl->n_tasks[cur], 0}, chunk0,
-                 FinCountInt{&ctl->n_chunks, ctx->cap_chunks, &ctl->need_chunks, &ctl->overflow, OVF_CHUNKS});
-        k_expand_chunks<<<GE, 256, 0, st>>>(ctl, cur, prev, len0, tv, tb, tq, chunk0, ctx->chunk_desc.as<ChunkDesc>());
+        const int Gk = std::max(1, 32 / (prev.stride + 1));      // rows per chunk: Gk * (longest schedule + 1) <= 32 lanes
+        RowDesc* rows = ctx->row_desc.as<RowDesc>();
+        int* tnf = ctx->task_nfeas.as<int>();
+        scan_dev(ctx, InArray<int>{ctx->task_nchunk[cur].as<int>(), &ctl->n_tasks[cur], 0}, row0,
+                 FinRows{ctl, ctx->cap_rows, ctx->cap_chunks, Gk});
+        k_expand_rows<<<GE, 256, 0, st>>>(ctl, cur, prev, len0, tv, tb, tq, row0, rows, tnf);
         CK(cudaEventRecord(get_event(ctx, n_ev++), st));
-        k_eval<TT, 0><<<GE, WARPS_PER_BLOCK * 32, 0, st>>>(d, tt, prev, lv, ctl, ctx->chunk_desc.as<ChunkDesc>(), ctx->chunk_cnt.as<int>(),
-                                                          ctx->lane_cnt.as<uint8_t>(), nullptr, dstats);
+        k_eval<TT, 0><<<GE, WARPS_PER_BLOCK * 32, 0, st>>>(d, tt, prev, lv, ctl, Gk, rows, ctx->chunk_cnt.as<int>(),
+                                                          ctx->lane_cnt.as<uint8_t>(), nullptr, tnf, dstats);
         CK(cudaEventRecord(get_event(ctx, n_ev++), st));
         scan_dev(ctx, InArray<int>{ctx->chunk_cnt.as<int>(), &ctl->n_chunks, 0}, cpos,
                  FinCountI64{&ctl->n_sch[k], lv.cap_sch, &ctl->need_sch[k], &ctl->overflow, OVF_SCH});
-        scan_dev(ctx, InTaskFeasible{ctl, cur, chunk0, cpos}, ctx->trip_pos.as<i64>(),
+        scan_dev(ctx, InTaskFeasible{ctl, cur, tnf}, ctx->trip_pos.as<i64>(),
                  FinCountInt{&ctl->n_trips[k], (i64)lv.cap_trips, &ctl->need_trips[k], &ctl->overflow, OVF_TRIPS});
-        k_compact_trips<<<G, 256, 0, st>>>(ctl, cur, tv, tb, tq, chunk0, cpos, ctx->trip_pos.as<i64>(), prev, lv, dstats);
+        k_compact_trips<<<G, 256, 0, st>>>(ctl, cur, tv, tb, tq, row0, tnf, Gk, rows, ctx->lane_cnt.as<uint8_t>(), cpos,
+                                          ctx->trip_pos.as<i64>(), prev, lv, dstats);
         CK(cudaEventRecord(get_event(ctx, n_ev++), st));
-        k_eval<TT, 1><<<GE, WARPS_PER_BLOCK * 32, 0, st>>>(d, tt, prev, lv, ctl, ctx->chunk_desc.as<ChunkDesc>(), ctx->chunk_cnt.as<int>(),
-                                                          ctx->lane_cnt.as<uint8_t>(), cpos, dstats);
+        k_eval<TT, 1><<<GE, WARPS_PER_BLOCK * 32, 0, st>>>(d, tt, prev, lv, ctl, Gk, rows, ctx->chunk_cnt.as<int>(),
+                                                          ctx->lane_cnt.as<uint8_t>(), cpos, tnf, dstats);
         CK(cudaEventRecord(get_event(ctx, n_ev++), st));
         k_classify<<<G, WARPS_PER_BLOCK * 32, 0, st>>>(d, ctl, lv, sba);
         ctx->n_launches += 5;
@@ -533,7 +537,7 @@ static int build_impl(amod_ctx* ctx, const amod_epoch* ep, int loc, amod_stats* 
         }
         // regrow exactly what overflowed (with headroom) and rerun the epoch
         auto grow = [](i64& cap, i64 need) { if (need > cap) cap = need + need / 2 + 1024; };
-        grow(ctx->cap_tasks, h->need_tasks); grow(ctx->cap_chunks, h->need_chunks);
+        grow(ctx->cap_tasks, h->need_tasks); grow(ctx->cap_chunks, h->need_chunks); grow(ctx->cap_rows, h->need_rows);
         for (int k = 0; k <= max_level; k++) { grow(ctx->cap_trips[k], h->need_trips[k]); grow(ctx->cap_sch[k], h->need_sch[k]); }
         grow(ctx->cap_ent, h->need_ent); grow(ctx->cap_ptr, h->need_ptr); grow(ctx->cap_pst, h->need_pst);
         if (ctx->cap_tasks > 0x7ffffff0 || ctx->cap_chunks > 0x7ffffff0) return ctx->fail(AMOD_E_LIMIT, "more than 2^31 candidates in one level");
@@ -574,7 +578,9 @@ static int build_impl(amod_ctx* ctx, const amod_epoch* ep, int loc, amod_stats* 
         out_stats->n_levels = levels_done;
         out_stats->n_kernel_launches = ctx->n_launches;
         out_stats->n_sches_stored = (int64_t)h->stats.n_sches;
-        out_stats->reserved = ctx->n_attempts;
+        out_stats->n_attempts = ctx->n_attempts;
+        out_stats->n_chunks = (int64_t)h->stats.n_chunks;
+        out_stats->n_items = (int64_t)h->stats.n_items;
     }
     (void)total_tasks;
     if (mode != AMOD_MODE_SBA && run_levels == max_level && h->n_trips[max_level] > 0)

@@ -59,7 +59,7 @@ struct Level {
 #define MAX_LEVELS (AMOD_MAX_TRIP + 1)
 
 struct Stats {            // device counters
-    unsigned long long n_screens, n_evals, n_lookups, n_sches, n_tasks, flags;
+    unsigned long long n_screens, n_evals, n_lookups, n_sches, n_tasks, flags, n_chunks, n_items;
 };
 
 // Device-resident control block: every size the level-synchronous pipeline produces lives here, so
@@ -70,24 +70,28 @@ struct Stats {            // device counters
 #define OVF_TRIPS 4ull
 #define OVF_SCH 8ull
 #define OVF_POOL 16ull
+#define OVF_ROWS 32ull
 struct Control {
     int n_tasks[2];
     int n_chunks;
+    int n_rows;
+    int pad0;
     int n_trips[MAX_LEVELS];
     i64 n_sch[MAX_LEVELS];
     i64 n_ent, n_ptr, n_pst;
     unsigned long long overflow;
+    i64 need_rows;
     i64 need_tasks, need_chunks, need_trips[MAX_LEVELS], need_sch[MAX_LEVELS], need_ent, need_ptr, need_pst;
     int max_level_nonempty;
     int pad;
     Stats stats;
 };
 
-// One unit of insertion-search work: a group of whole base schedules of one task (32 B, one load).
-struct __align__(16) ChunkDesc {
-    int v, q, s_begin, n_sub;     // vehicle, inserted request, first base schedule (list position), how many
+// One base schedule of one task = one "row" of insertion-search work (l+1 lanes).  32 B, one load.
+struct __align__(16) RowDesc {
+    int v, q, s, l;               // vehicle, inserted request, list position of the base schedule, its length
     i64 s0;                       // first schedule row of the base trip in the previous level
-    int l, task;                  // base schedule length, owning task
+    int task, pad;
 };
 
 __device__ __forceinline__ void stop_info(const DEpoch& ep, int v, int code, int& node, double& ddl, int& pod) {

@@ -35,7 +35,6 @@ struct WarpStage {
     signed char pod[STAGE_SLOTS];
 };
 
-__device__ __forceinline__ int chunk_group(int l) { return l + 1 >= 32 ? 1 : 32 / (l + 1); }   // base schedules per chunk
 
 struct LaneCount { int n, evals, lookups; };
 
@@ -85,11 +84,13 @@ __device__ __forceinline__ void walk_j(const TT* __restrict__ lg, double PD, con
     }
 }
 
+// A chunk = G consecutive rows (base schedules) of the level's global row list, whatever task or
+// vehicle they belong to; G is chosen per level so that G * (longest schedule + 1) <= 32 lanes.
 template <typename TT, int MODE>
 __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, EVAL_BLOCKS_PER_SM)
-k_eval(const DEpoch* __restrict__ epp, Table<TT> tt, Level prev, Level cur, const Control* __restrict__ ctl,
-       const ChunkDesc* __restrict__ desc, int* __restrict__ chunk_cnt, uint8_t* __restrict__ lane_cnt,
-       const i64* __restrict__ chunk_pos, Stats* stats) {
+k_eval(const DEpoch* __restrict__ epp, Table<TT> tt, Level prev, Level cur, const Control* __restrict__ ctl, int G,
+       const RowDesc* __restrict__ rows, int* __restrict__ chunk_cnt, uint8_t* __restrict__ lane_cnt,
+       const i64* __restrict__ chunk_pos, int* __restrict__ task_nfeas, Stats* stats) {
     __shared__ WarpStage<TT> stage_all[WARPS_PER_BLOCK];
     __shared__ DEpoch s_ep;       // the epoch header once per block: array pointers without a second indirection
     if (threadIdx.x < sizeof(DEpoch) / 4) ((int*)&s_ep)[threadIdx.x] = ((const int*)epp)[threadIdx.x];
@@ -100,73 +101,100 @@ k_eval(const DEpoch* __restrict__ epp, Table<TT> tt, Level prev, Level cur, cons
     const int warp0 = blockIdx.x * WARPS_PER_BLOCK + wib, nwarps = gridDim.x * WARPS_PER_BLOCK;
     unsigned long long acc_evals = 0, acc_lookups = 0;
     const double T = ep.T;
+    const int n_rows = ctl->overflow ? 0 : ctl->n_rows;
     const int n_chunks = ctl->overflow ? 0 : ctl->n_chunks;
     const int cap = ep.cap;
 
-    ChunkDesc nxt;
-    if (warp0 < n_chunks) nxt = desc[warp0];
+    RowDesc nxt; nxt.l = 0; nxt.v = 0; nxt.q = 0; nxt.s = 0; nxt.s0 = 0; nxt.task = 0;
+    if (warp0 < n_chunks && lane < G && warp0 * G + lane < n_rows) nxt = rows[(i64)warp0 * G + lane];
     for (int c = warp0; c < n_chunks; c += nwarps) {
-        const ChunkDesc cd = nxt;
-        if (c + nwarps < n_chunks) nxt = desc[c + nwarps];        // prefetch the next descriptor
+        const RowDesc rd = nxt;                                   // lane j < nr owns row j of the chunk
+        const int nr = min(G, n_rows - c * G);
+        {
+            const i64 cn = (i64)c + nwarps;
+            if (cn < n_chunks && lane < G && cn * G + lane < n_rows) nxt = rows[cn * G + lane];   // prefetch
+        }
         if (MODE == 1 && chunk_cnt[c] == 0) continue;
-        const int v = cd.v, q = cd.q, l = cd.l;
-        if (l + 2 > MAXS || l + 2 > cur.stride) {   // compiled stop limit: reported as AMOD_E_LIMIT by the host
+        const bool own = lane < nr;
+        // per-row parameters live in the owner lane's registers and are read by shuffle
+        int o_l = own ? rd.l : 0;
+        const bool too_long = own && (o_l + 2 > MAXS || o_l + 2 > cur.stride);
+        if (__any_sync(FULL, too_long)) {   // compiled stop limit: reported as AMOD_E_LIMIT by the host
             if (MODE == 0) {
                 if (lane == 0) { atomicOr(&stats->flags, 1ull); chunk_cnt[c] = 0; }
                 lane_cnt[(i64)c * 64 + lane] = 0; lane_cnt[(i64)c * 64 + 32 + lane] = 0;
             }
             continue;
         }
-        const i64 s0 = cd.s0;
-        const int s_begin = cd.s_begin;
-        const int P = ep.onid[q], D = ep.dnid[q];
-        const double clp = ep.clp[q], cld = ep.cld[q];
-        const int nid = ep.veh_nid[v], load = ep.veh_load[v];
-        const double t0 = ep.veh_t[v];
-        const double PD = tt(P, D);
-        const int items = cd.n_sub * (l + 1);
+        int o_P = 1, o_D = 1, o_nid = 1, o_load = 0;
+        double o_clp = 0, o_cld = 0, o_t0 = 0, o_PD = 0;
+        i64 o_src = 0;
+        if (own) {
+            o_P = ep.onid[rd.q]; o_D = ep.dnid[rd.q]; o_clp = ep.clp[rd.q]; o_cld = ep.cld[rd.q];
+            o_nid = ep.veh_nid[rd.v]; o_load = ep.veh_load[rd.v]; o_t0 = ep.veh_t[rd.v];
+            o_src = rd.s0 + prev.order[rd.s0 + rd.s];             // stored row of the base schedule (list order -> row)
+            o_PD = tt(o_P, o_D);
+        }
+        const int o_w = own ? o_l + 1 : 0;
+        const int o_woff = warp_excl_sum(o_w, lane);              // first lane of the row
+        const int o_soff = warp_excl_sum(o_l, lane);              // first staged stop of the row
+        const int o_goff = warp_excl_sum(own ? 5 * o_l + 2 : 0, lane);   // first staged leg of the row
+        const int items = __shfl_sync(FULL, o_woff + o_w, 31);
+        const int tot_stops = __shfl_sync(FULL, o_soff + o_l, 31);
+        const int tot_legs = __shfl_sync(FULL, o_goff + (own ? 5 * o_l + 2 : 0), 31);
+
+        __syncwarp();
+        for (int e0 = 0; e0 < tot_stops; e0 += 32) {              // stage the stops of all rows (uniform trip count:
+            const int e = e0 + lane;                               //  every lane takes part in the shuffles)
+            int r = 0;
+            for (int j = 1; j < nr; j++) if (e >= __shfl_sync(FULL, o_soff, j)) r = j;
+            const int m = e - __shfl_sync(FULL, o_soff, r);
+            const i64 src = __shfl_sync(FULL, o_src, r);
+            const int vv = __shfl_sync(FULL, rd.v, r);
+            if (e < tot_stops) {
+                const int code = prev.sch[src * prev.stride + m];
+                int node, pod; double ddl;
+                stop_info(ep, vv, code, node, ddl, pod);
+                st.node[e] = node; st.ddl[e] = ddl; st.pod[e] = (signed char)pod; st.code[e] = (code_t)code;
+            }
+        }
+        __syncwarp();
+        for (int e0 = 0; e0 < tot_legs; e0 += 32) {               // gather the 5l+2 travel times of every row
+            const int e = e0 + lane;
+            int r = 0;
+            for (int j = 1; j < nr; j++) if (e >= __shfl_sync(FULL, o_goff, j)) r = j;
+            const int x = e - __shfl_sync(FULL, o_goff, r);
+            const int l = __shfl_sync(FULL, o_l, r);
+            const int* n = st.node + __shfl_sync(FULL, o_soff, r);
+            const int P = __shfl_sync(FULL, o_P, r), D = __shfl_sync(FULL, o_D, r), nid = __shfl_sync(FULL, o_nid, r);
+            if (e < tot_legs) {
+                int a, b, m;
+                if (x < l) { m = x; a = m ? n[m - 1] : nid; b = n[m]; }
+                else if (x < 2 * l + 1) { m = x - l; a = m ? n[m - 1] : nid; b = P; }
+                else if (x < 3 * l + 1) { m = x - (2 * l + 1); a = P; b = n[m]; }
+                else if (x < 4 * l + 2) { m = x - (3 * l + 1); a = m ? n[m - 1] : nid; b = D; }
+                else { m = x - (4 * l + 2); a = D; b = n[m]; }
+                st.leg[e] = tt.raw(a, b);
+            }
+        }
+        __syncwarp();
+
         int dead_s = -1, cnt_total = 0;
         i64 row_base = MODE == 1 ? chunk_pos[c] : 0;
-
-        for (int it0 = 0; it0 < items; it0 += 32) {        // one step unless l+1 > 32
+        for (int it0 = 0; it0 < items; it0 += 32) {               // one step unless a single schedule has > 31 stops
             const int it = it0 + lane;
             const bool valid = it < items;
-            const int sl = valid ? it / (l + 1) : -1;      // sub_sche within the chunk
-            const int i = valid ? it - sl * (l + 1) : 0;
-            const int sl_first = it0 / (l + 1);
-            const int sl_last = (min(items, it0 + 32) - 1) / (l + 1);
-            __syncwarp();
-            if (l > 0) {   // stage the stops of the step's base schedules (list order -> stored row)
-                const int ne = (sl_last - sl_first + 1) * l;
-                for (int e = lane; e < ne; e += 32) {
-                    const int ss = sl_first + e / l, m = e - (e / l) * l;
-                    const i64 row = s0 + prev.order[s0 + s_begin + ss];
-                    const int code = prev.sch[row * prev.stride + m];
-                    int node, pod; double ddl;
-                    stop_info(ep, v, code, node, ddl, pod);
-                    st.node[e] = node; st.ddl[e] = ddl; st.pod[e] = (signed char)pod; st.code[e] = (code_t)code;
-                }
-            }
-            __syncwarp();
-            const int W = 5 * l + 2;
-            {   // gather the 5l+2 travel times of every staged base schedule: independent loads, all lanes
-                const int ne = (sl_last - sl_first + 1) * W;
-                for (int e = lane; e < ne; e += 32) {
-                    const int sub = e / W, r = e - sub * W;
-                    const int* n = st.node + sub * l;
-                    int a, b, m;
-                    if (r < l) { m = r; a = m ? n[m - 1] : nid; b = n[m]; }
-                    else if (r < 2 * l + 1) { m = r - l; a = m ? n[m - 1] : nid; b = P; }
-                    else if (r < 3 * l + 1) { m = r - (2 * l + 1); a = P; b = n[m]; }
-                    else if (r < 4 * l + 2) { m = r - (3 * l + 1); a = m ? n[m - 1] : nid; b = D; }
-                    else { m = r - (4 * l + 2); a = D; b = n[m]; }
-                    st.leg[e] = tt.raw(a, b);
-                }
-            }
-            __syncwarp();
-            const int eb = valid ? (sl - sl_first) * l : 0;
-            const double* ddl = st.ddl + eb;
-            const TT* lg = st.leg + (valid ? (sl - sl_first) * W : 0);
+            int r = 0;
+            for (int j = 1; j < nr; j++) if (it >= __shfl_sync(FULL, o_woff, j)) r = j;
+            const int i = it - __shfl_sync(FULL, o_woff, r);
+            const int l = __shfl_sync(FULL, o_l, r);
+            const int soff = __shfl_sync(FULL, o_soff, r), goff = __shfl_sync(FULL, o_goff, r);
+            const int q = __shfl_sync(FULL, rd.q, r), task = __shfl_sync(FULL, rd.task, r);
+            const int load = __shfl_sync(FULL, o_load, r);
+            const double clp = __shfl_sync(FULL, o_clp, r), cld = __shfl_sync(FULL, o_cld, r);
+            const double t0 = __shfl_sync(FULL, o_t0, r), PD = __shfl_sync(FULL, o_PD, r);
+            const double* ddl = st.ddl + soff;
+            const TT* lg = st.leg + goff;
 
             // capacity profile of the base schedule and accumulated time at the inserted pick-up
             unsigned long long fullmask = 0;
@@ -176,7 +204,7 @@ k_eval(const DEpoch* __restrict__ epp, Table<TT> tt, Level prev, Level cur, cons
                 int run = load;
                 if (run >= cap) fullmask |= 1ull;
                 for (int m = 0; m < l; m++) {
-                    run += st.pod[eb + m];
+                    run += st.pod[soff + m];
                     if (run > cap) basebad = true;
                     if (run >= cap) fullmask |= 1ull << (m + 1);
                 }
@@ -186,14 +214,14 @@ k_eval(const DEpoch* __restrict__ epp, Table<TT> tt, Level prev, Level cur, cons
                 cap1 = basebad || ((fullmask >> i) & 1ull);                              // viol 1 at j = i+1
                 stop3 = !cap1 && (T + A > clp);                                          // viol 3 (scheduling.py:43)
             }
-            // viol==3 ends the i-loop of its sub_sche: later i of the same sub_sche are never evaluated
+            // viol==3 ends the i-loop of its base schedule: later i of the same row are never evaluated
             const unsigned bal3 = __ballot_sync(FULL, stop3);
             const int lo = max(lane - i, 0);
             const unsigned same_s_lower = (lane > lo) ? (((1u << lane) - 1u) & ~((1u << lo) - 1u)) : 0u;
-            const bool dead = valid && ((bal3 & same_s_lower) != 0u || sl == dead_s);
-            {   // carry to the next step if the last sub_sche continues there (only when l+1 > 32)
-                const unsigned killed = __ballot_sync(FULL, valid && sl == sl_last && (stop3 || dead));
-                dead_s = killed ? sl_last : -1;
+            const bool dead = valid && ((bal3 & same_s_lower) != 0u || dead_s == 0);
+            {   // carry to the second step of a > 31-stop schedule (then the chunk is that single row)
+                const unsigned killed = __ballot_sync(FULL, valid && (stop3 || dead));
+                dead_s = (items > 32 && killed) ? 0 : -1;
             }
             const bool live = valid && !dead;
             LaneCount o; o.n = 0; o.evals = 0; o.lookups = 0;
@@ -201,20 +229,22 @@ k_eval(const DEpoch* __restrict__ epp, Table<TT> tt, Level prev, Level cur, cons
                 if (live) {
                     if (cap1) o.evals = 1;
                     else if (stop3) { o.evals = 1; o.lookups = i + 1; }
-                    else walk_j<TT, false>(lg, PD, ddl, st.code + eb, l, i, A, q, cld, T, fullmask, o, 0, nullptr, nullptr, 0);
+                    else walk_j<TT, false>(lg, PD, ddl, st.code + soff, l, i, A, q, cld, T, fullmask, o, 0, nullptr, nullptr, 0);
                 }
                 acc_evals += o.evals; acc_lookups += o.lookups;
-                lane_cnt[(i64)c * 64 + it0 + lane] = (uint8_t)o.n;     // <= 64 items per chunk (l+1 <= 39)
+                lane_cnt[(i64)c * 64 + it0 + lane] = (uint8_t)o.n;     // <= 64 items per chunk
+                if (o.n) atomicAdd(&task_nfeas[task], o.n);
                 cnt_total += o.n;
             } else {
                 const int mine = lane_cnt[(i64)c * 64 + it0 + lane];
                 const int before = warp_excl_sum(mine, lane);
-                if (mine) walk_j<TT, true>(lg, PD, ddl, st.code + eb, l, i, A, q, cld, T, fullmask, o, row_base + before,
+                if (mine) walk_j<TT, true>(lg, PD, ddl, st.code + soff, l, i, A, q, cld, T, fullmask, o, row_base + before,
                                            cur.sch, cur.sch_cost, cur.stride);
                 row_base += __shfl_sync(FULL, before + mine, 31);
             }
         }
         if (MODE == 0) {
+            if (items <= 32) lane_cnt[(i64)c * 64 + 32 + lane] = 0;
             cnt_total = warp_sum(cnt_total);
             if (lane == 0) chunk_cnt[c] = cnt_total;
         }

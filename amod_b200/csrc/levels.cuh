@@ -145,11 +145,9 @@ struct InVehInt {            // scan input over a per-vehicle int array
     __device__ __forceinline__ i64 operator()(i64 i) const { return (i64)p[i]; }
 };
 
-__device__ __forceinline__ int task_chunks(int S, int l) { const int g = chunk_group(l); return (S + g - 1) / g; }
-
 __global__ void k_tasks_from_screen(const DEpoch* __restrict__ epp, const uint8_t* __restrict__ flag, const i64* __restrict__ pos,
                                     const Control* __restrict__ ctl, const int* __restrict__ len0, const int* __restrict__ S0,
-                                    int* task_veh, int* task_base, int* task_q, int* task_nchunk) {
+                                    int* task_veh, int* task_base, int* task_q, int* task_S) {
     const DEpoch& ep = *epp;
     const i64 n = (i64)ep.n_veh * ep.n_search;
     if (ctl->n_tasks[0] == 0 || ctl->overflow) return;
@@ -161,58 +159,86 @@ __global__ void k_tasks_from_screen(const DEpoch* __restrict__ epp, const uint8_
         else { v = (int)(e / ep.n_search); s = (int)(e - (i64)v * ep.n_search); }
         const i64 t = pos[e];
         task_veh[t] = v; task_base[t] = v; task_q[t] = ep.search[s];
-        task_nchunk[t] = task_chunks(S0[v], len0[v]);
+        task_S[t] = S0[v];                     // rows (base schedules) of the task
     }
 }
 
-// chunk descriptors: one warp per task, lanes over the task's chunks
+// scan finisher for the row count of a level: rows, and chunks of G rows
+struct FinRows {
+    Control* ctl; i64 cap_rows, cap_chunks; int G;
+    __device__ __forceinline__ void operator()(i64 tot) const {
+        i64 nch = (tot + G - 1) / G;
+        if (tot > ctl->need_rows) ctl->need_rows = tot;
+        if (nch > ctl->need_chunks) ctl->need_chunks = nch;
+        if (tot > cap_rows) { atomicOr(&ctl->overflow, OVF_ROWS); tot = 0; nch = 0; }
+        if (nch > cap_chunks) { atomicOr(&ctl->overflow, OVF_CHUNKS); tot = 0; nch = 0; }
+        ctl->n_rows = (int)tot; ctl->n_chunks = (int)nch;
+        ctl->stats.n_chunks += (unsigned long long)nch;
+    }
+};
+
+// row descriptors: one warp per task, lanes over the task's base schedules
 __global__ void __launch_bounds__(256)
-k_expand_chunks(Control* __restrict__ ctl, int which, Level prev, const int* __restrict__ len0, const int* __restrict__ task_veh,
-                const int* __restrict__ task_base, const int* __restrict__ task_q, const i64* __restrict__ task_chunk0,
-                ChunkDesc* __restrict__ desc) {
-    const int n = (ctl->n_chunks && !ctl->overflow) ? ctl->n_tasks[which] : 0;
+k_expand_rows(Control* __restrict__ ctl, int which, Level prev, const int* __restrict__ len0, const int* __restrict__ task_veh,
+              const int* __restrict__ task_base, const int* __restrict__ task_q, const i64* __restrict__ task_row0,
+              RowDesc* __restrict__ rows, int* __restrict__ task_nfeas) {
+    const int n = (ctl->n_rows && !ctl->overflow) ? ctl->n_tasks[which] : 0;
     const int lane = threadIdx.x & 31;
     const int nwarps = gridDim.x * (blockDim.x >> 5);
     if (blockIdx.x == 0 && threadIdx.x == 0 && n) atomicAdd(&ctl->stats.n_tasks, (unsigned long long)n);   // compute_schedule calls
+    unsigned long long items = 0;
     for (int t = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); t < n; t += nwarps) {
         const int v = task_veh[t], base = task_base[t], q = task_q[t];
         const int l = len0[v] + 2 * prev.k;
-        const int S = prev.nfeas[base];
         const i64 s0 = prev.s0[base];
-        const int g = chunk_group(l);
-        const i64 c0 = task_chunk0[t], c1 = task_chunk0[t + 1];
-        for (i64 c = c0 + lane; c < c1; c += 32) {
-            ChunkDesc d;
-            d.v = v; d.q = q; d.s_begin = (int)(c - c0) * g; d.n_sub = min(S - d.s_begin, g); d.s0 = s0; d.l = l; d.task = t;
-            desc[c] = d;
+        const i64 r0 = task_row0[t], r1 = task_row0[t + 1];
+        if (lane == 0) { task_nfeas[t] = 0; items += (unsigned long long)(r1 - r0) * (l + 1); }
+        for (i64 r = r0 + lane; r < r1; r += 32) {
+            RowDesc d;
+            d.v = v; d.q = q; d.s = (int)(r - r0); d.l = l; d.s0 = s0; d.task = t; d.pad = 0;
+            rows[r] = d;
         }
     }
+    if (lane == 0 && items) atomicAdd(&ctl->stats.n_items, items);
+}
+
+// schedule position (encounter order) of the first feasible insertion of row r
+__device__ __forceinline__ i64 row_position(i64 r, int G, const RowDesc* __restrict__ rows, const uint8_t* __restrict__ lane_cnt,
+                                            const i64* __restrict__ chunk_pos) {
+    const i64 c = r / G;
+    int lanes_before = 0;
+    for (i64 x = c * G; x < r; x++) lanes_before += rows[x].l + 1;
+    i64 p = chunk_pos[c];
+    for (int x = 0; x < lanes_before; x++) p += lane_cnt[c * 64 + x];
+    return p;
 }
 
 // ---------------------------------------------------------------------------------------------
 // Feasible tasks -> trips of the new level, order preserved (dispatch_osp.py:163-164, :217-218).
 // ---------------------------------------------------------------------------------------------
 struct InTaskFeasible {       // scan input: 1 if the task produced at least one feasible schedule
-    const Control* ctl; int which; const i64* task_chunk0; const i64* chunk_pos;
+    const Control* ctl; int which; const int* task_nfeas;
     __device__ __forceinline__ i64 size() const { return (ctl->n_chunks && !ctl->overflow) ? ctl->n_tasks[which] : 0; }
-    __device__ __forceinline__ i64 operator()(i64 t) const { return chunk_pos[task_chunk0[t + 1]] > chunk_pos[task_chunk0[t]]; }
+    __device__ __forceinline__ i64 operator()(i64 t) const { return task_nfeas[t] > 0; }
 };
 
 __global__ void k_compact_trips(const Control* __restrict__ ctl, int which, const int* __restrict__ task_veh,
                                 const int* __restrict__ task_base, const int* __restrict__ task_q,
-                                const i64* __restrict__ task_chunk0, const i64* __restrict__ chunk_pos,
-                                const i64* __restrict__ trip_pos, Level prev, Level cur, Stats* stats) {
+                                const i64* __restrict__ task_row0, const int* __restrict__ task_nfeas, int G,
+                                const RowDesc* __restrict__ rows, const uint8_t* __restrict__ lane_cnt,
+                                const i64* __restrict__ chunk_pos, const i64* __restrict__ trip_pos, Level prev, Level cur,
+                                Stats* stats) {
     const int n = (ctl->n_trips[cur.k] && !ctl->overflow) ? ctl->n_tasks[which] : 0;
     const int stride = gridDim.x * blockDim.x;
     unsigned long long nsch = 0;
     for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < n; t += stride) {
-        const i64 a = chunk_pos[task_chunk0[t]], b = chunk_pos[task_chunk0[t + 1]];
-        if (b == a) continue;
-        nsch += (unsigned long long)(b - a);
+        const int nf = task_nfeas[t];
+        if (nf == 0) continue;
+        nsch += (unsigned long long)nf;
         const int o = (int)trip_pos[t];
         cur.trip_veh[o] = task_veh[t];
-        cur.nfeas[o] = (int)(b - a);
-        cur.s0[o] = a;
+        cur.nfeas[o] = nf;
+        cur.s0[o] = row_position(task_row0[t], G, rows, lane_cnt, chunk_pos);
         // trip = sorted(base trip + q)  (dispatch_osp.py:187)
         const int kb = prev.k, q = task_q[t];
         const int* bq = prev.trip_req + (i64)task_base[t] * kb;
@@ -339,7 +365,7 @@ template <int MODE>
 __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32)
 k_gen(const Control* __restrict__ ctl, int which_next, Level l1, Level prev, TripHash th, const int* __restrict__ len0,
       int* __restrict__ row_cnt, const i64* __restrict__ row_off, int* __restrict__ tmp_j, int* __restrict__ tmp_q,
-      int* task_veh, int* task_base, int* task_q, int* task_nchunk) {
+      int* task_veh, int* task_base, int* task_q, int* task_S) {
     const int lane = threadIdx.x & 31;
     const int n = ctl->overflow ? 0 : ctl->n_trips[prev.k];
     if (MODE == 1 && ctl->n_tasks[which_next] == 0) return;
@@ -380,8 +406,7 @@ k_gen(const Control* __restrict__ ctl, int which_next, Level l1, Level prev, Tri
         if (MODE == 0) { if (lane == 0) row_cnt[t] = cnt; continue; }
         __syncwarp();
         // rank by j (k == 1 rows are already in j order) and emit the next level's tasks
-        const int l_next = len0[v] + 2 * k;
-        const int nch = task_chunks(prev.nfeas[t], l_next);
+        const int S_next = prev.nfeas[t];       // every task inserting into trip t walks all of its schedules
         for (int e = lane; e < cnt; e += 32) {
             int rank = e;
             if (k > 1) {
@@ -390,7 +415,7 @@ k_gen(const Control* __restrict__ ctl, int which_next, Level l1, Level prev, Tri
                 for (int x = 0; x < cnt; x++) rank += tmp_j[off + x] < j;
             }
             const i64 o = off + rank;
-            task_veh[o] = v; task_base[o] = t; task_q[o] = tmp_q[off + e]; task_nchunk[o] = nch;
+            task_veh[o] = v; task_base[o] = t; task_q[o] = tmp_q[off + e]; task_S[o] = S_next;
         }
     }
 }

@@ -114,7 +114,9 @@ typedef struct amod_stats {
     double  ms_build;       /* device time of the whole build (CUDA events)                          */
     double  ms_eval;        /* device time inside the insertion-search kernels                       */
     int32_t n_eval_launches;
-    int32_t reserved;
+    int32_t n_attempts;     /* 1 unless a device buffer had to be regrown and the epoch rerun                */
+    int64_t n_chunks;       /* warp work units of the insertion search                                       */
+    int64_t n_items;        /* (base schedule, pick-up index) lanes inside them (<= 32 per chunk)            */
 } amod_stats;
 
 /* Upload the travel-time table (row = origin, col = destination; route_functions.py:22-25). */

@@ -22,7 +22,8 @@ SRC = os.path.join(_HERE, "amod_oracle.c")
 
 
 def build(force: bool = False) -> str:
-    if force or not os.path.exists(LIB) or os.path.getmtime(LIB) < os.path.getmtime(SRC):
+    hdr = os.path.join(os.path.dirname(_HERE), "include", "amod_b200.h")     # struct layouts are shared with the product ABI
+    if force or not os.path.exists(LIB) or os.path.getmtime(LIB) < max(os.path.getmtime(SRC), os.path.getmtime(hdr)):
         subprocess.check_call(["gcc", "-O2", "-fopenmp", "-shared", "-fPIC", "-o", LIB, SRC, "-lm"])
     return LIB
 
