@@ -170,3 +170,20 @@ def test_cuda_sba_and_npo_at_peak_epoch_scale():
     g = b.npo_match(idle, pend)
     for x, y in zip(a, g):
         assert np.array_equal(x, y)
+
+
+def test_cuda_long_schedules_take_two_warp_steps(mode=marshal.MODE_SBA):
+    """Base schedules with more than 31 stops (a row wider than a warp): SBA inserts into the vehicle's
+    full current schedule (dispatch_sba.py:62)."""
+    import oracle
+    tt = synth.random_table(40, 21, "real", np.float32)
+    b = builder_for(tt)
+    ep = synth.random_epoch(tt, n_veh=60, n_pending=40, cap=10, mode=mode, seed=9, wait_sec=3000, near=True, max_picking=13,
+                            frac_new=0.9, T=9000)
+    assert np.diff(ep.veh_sche_off).max() >= 32
+    ref = (oracle.sba_build if mode == marshal.MODE_SBA else oracle.osp_build)(ep, tt)
+    assert ref.error == 0
+    got = b.build_pool(ep)
+    ok, why = marshal.pools_equal(got, ref, rtol=0.0, check_kind=True)
+    assert ok, why
+    assert got.stats["n_evals"] == ref.stats["n_evals"] and got.stats["n_lookups"] == ref.stats["n_lookups"]
