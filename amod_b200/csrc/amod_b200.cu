@@ -113,6 +113,14 @@ static int dispatch_tt(amod_ctx* ctx, F&& f) {
 static inline int nblk(i64 n, int per) { return (int)((n + per - 1) / per); }
 
 // exclusive scan (length and result sizes live on the device; no synchronisation)
+template <typename InA, typename FinA, typename InB, typename FinB>
+static void scan_dev2(amod_ctx* ctx, InA a, i64* outa, FinA fa, InB b, i64* outb, FinB fb) {
+    const int g = (ctx->n_sm / 2) * 2;
+    k_scan2_a<InA, InB><<<g, SCAN_THREADS, 0, ctx->stream>>>(a, b, ctx->partial.as<i64>());
+    k_scan2_b<InA, FinA, InB, FinB><<<g, SCAN_THREADS, 0, ctx->stream>>>(a, fa, outa, b, fb, outb, ctx->partial.as<i64>());
+    ctx->n_launches += 2;
+}
+
 template <typename In, typename Fin>
 static void scan_dev(amod_ctx* ctx, In in, i64* out, Fin fin) {
     const int g = ctx->n_sm;
@@ -386,11 +394,12 @@ static int enqueue_build(amod_ctx* ctx, int mode, Table<TT> tt, int max_level, c
     // ---- level-1 tasks: reachability screen ---------------------------------------------------------
     {
         k_screen<TT><<<G * 4, 256, 0, st>>>(d, tt, ctx->flag8.as<uint8_t>());
-        scan_dev(ctx, InScreenFlag{ctx->flag8.as<uint8_t>(), d}, ctx->pos.as<i64>(),
-                 FinCountInt{&ctl->n_tasks[0], ctx->cap_tasks, &ctl->need_tasks, &ctl->overflow, OVF_TASKS});
+        const int G1 = std::max(1, 32 / (ls.lv[0].stride + 1));
+        scan_dev(ctx, InScreenPacked{ctx->flag8.as<uint8_t>(), ctx->S0.as<int>(), d}, ctx->pos.as<i64>(),
+                 FinTasksRows{ctl, 0, ctx->cap_tasks, ctx->cap_rows, ctx->cap_chunks, G1});
         k_tasks_from_screen<<<G * 4, 256, 0, st>>>(d, ctx->flag8.as<uint8_t>(), ctx->pos.as<i64>(), ctl, len0, ctx->S0.as<int>(),
                                                   ctx->task_veh[0].as<int>(), ctx->task_base[0].as<int>(), ctx->task_q[0].as<int>(),
-                                                  ctx->task_nchunk[0].as<int>());
+                                                  ctx->task_nchunk[0].as<int>(), ctx->task_chunk0.as<i64>());
         ctx->n_launches += 2;
     }
     // ---- levels 1..max_level ----------------------------------------------------------------------------
@@ -404,17 +413,15 @@ static int enqueue_build(amod_ctx* ctx, int mode, Table<TT> tt, int max_level, c
         const int Gk = std::max(1, 32 / (prev.stride + 1));      // rows per chunk: Gk * (longest schedule + 1) <= 32 lanes
         RowDesc* rows = ctx->row_desc.as<RowDesc>();
         int* tnf = ctx->task_nfeas.as<int>();
-        scan_dev(ctx, InArray<int>{ctx->task_nchunk[cur].as<int>(), &ctl->n_tasks[cur], 0}, row0,
-                 FinRows{ctl, ctx->cap_rows, ctx->cap_chunks, Gk});
-        k_expand_rows<<<GE, 256, 0, st>>>(ctl, cur, prev, len0, tv, tb, tq, row0, rows, tnf);
+        k_expand_rows<<<GE, 256, 0, st>>>(ctl, cur, prev, len0, tv, tb, tq, ctx->task_nchunk[cur].as<int>(), row0, rows, tnf);
         CK(cudaEventRecord(get_event(ctx, n_ev++), st));
         k_eval<TT, 0><<<GE, WARPS_PER_BLOCK * 32, 0, st>>>(d, tt, prev, lv, ctl, Gk, rows, ctx->chunk_cnt.as<int>(),
                                                           ctx->lane_cnt.as<uint8_t>(), nullptr, tnf, dstats);
         CK(cudaEventRecord(get_event(ctx, n_ev++), st));
-        scan_dev(ctx, InArray<int>{ctx->chunk_cnt.as<int>(), &ctl->n_chunks, 0}, cpos,
-                 FinCountI64{&ctl->n_sch[k], lv.cap_sch, &ctl->need_sch[k], &ctl->overflow, OVF_SCH});
-        scan_dev(ctx, InTaskFeasible{ctl, cur, tnf}, ctx->trip_pos.as<i64>(),
-                 FinCountInt{&ctl->n_trips[k], (i64)lv.cap_trips, &ctl->need_trips[k], &ctl->overflow, OVF_TRIPS});
+        scan_dev2(ctx, InArray<int>{ctx->chunk_cnt.as<int>(), &ctl->n_chunks, 0}, cpos,
+                  FinCountI64{&ctl->n_sch[k], lv.cap_sch, &ctl->need_sch[k], &ctl->overflow, OVF_SCH},
+                  InTaskFeasible{ctl, cur, tnf}, ctx->trip_pos.as<i64>(),
+                  FinCountInt{&ctl->n_trips[k], (i64)lv.cap_trips, &ctl->need_trips[k], &ctl->overflow, OVF_TRIPS});
         k_compact_trips<<<G, 256, 0, st>>>(ctl, cur, tv, tb, tq, row0, tnf, Gk, rows, ctx->lane_cnt.as<uint8_t>(), cpos,
                                           ctx->trip_pos.as<i64>(), prev, lv, dstats);
         CK(cudaEventRecord(get_event(ctx, n_ev++), st));
@@ -434,12 +441,13 @@ static int enqueue_build(amod_ctx* ctx, int mode, Table<TT> tt, int max_level, c
             ctx->n_launches++;
         }
         k_gen<0><<<GE, WARPS_PER_BLOCK * 32, 0, st>>>(ctl, nxt, ls.lv[1], lv, th, len0, ctx->row_cnt.as<int>(), nullptr, nullptr, nullptr,
-                                                     nullptr, nullptr, nullptr, nullptr);
-        scan_dev(ctx, InArray<int>{ctx->row_cnt.as<int>(), &ctl->n_trips[k], 0}, ctx->row_off.as<i64>(),
-                 FinCountInt{&ctl->n_tasks[nxt], ctx->cap_tasks, &ctl->need_tasks, &ctl->overflow, OVF_TASKS});
+                                                     nullptr, nullptr, nullptr, nullptr, nullptr);
+        scan_dev(ctx, InRowCntPacked{ctx->row_cnt.as<int>(), lv.nfeas, &ctl->n_trips[k], ctl}, ctx->row_off.as<i64>(),
+                 FinTasksRows{ctl, nxt, ctx->cap_tasks, ctx->cap_rows, ctx->cap_chunks, std::max(1, 32 / (lv.stride + 1))});
         k_gen<1><<<GE, WARPS_PER_BLOCK * 32, 0, st>>>(ctl, nxt, ls.lv[1], lv, th, len0, nullptr, ctx->row_off.as<i64>(), ctx->tmp_j.as<int>(),
                                                      ctx->tmp_q.as<int>(), ctx->task_veh[nxt].as<int>(), ctx->task_base[nxt].as<int>(),
-                                                     ctx->task_q[nxt].as<int>(), ctx->task_nchunk[nxt].as<int>());
+                                                     ctx->task_q[nxt].as<int>(), ctx->task_nchunk[nxt].as<int>(),
+                                                     ctx->task_chunk0.as<i64>());
         ctx->n_launches += 2;
     }
     // ---- pool assembly --------------------------------------------------------------------------------

@@ -134,10 +134,39 @@ __global__ void k_screen(const DEpoch* __restrict__ epp, Table<TT> tt, uint8_t* 
     }
 }
 
-struct InScreenFlag {        // scan input over the V x Q screen flags
-    const uint8_t* p; const DEpoch* ep;
+// Packed two-component scans: low 32 bits count tasks, high 32 bits count their rows (base schedules),
+// so one prefix sum yields both the task index and the task's first row (both totals < 2^31).
+#define PACK_LO(x) ((i64)((x) & 0xffffffffll))
+#define PACK_HI(x) ((i64)((x) >> 32))
+struct InScreenPacked {      // over the V x Q screen flags: a surviving (vehicle, request) pair is a task of S0[v] rows
+    const uint8_t* p; const int* S0; const DEpoch* ep;
     __device__ __forceinline__ i64 size() const { return (i64)ep->n_veh * ep->n_search; }
-    __device__ __forceinline__ i64 operator()(i64 i) const { return (i64)p[i]; }
+    __device__ __forceinline__ i64 operator()(i64 e) const {
+        if (!p[e]) return 0;
+        const int v = ep->mode == AMOD_MODE_SBA ? (int)(e % ep->n_veh) : (int)(e / ep->n_search);
+        return 1ll | ((i64)S0[v] << 32);
+    }
+};
+struct InRowCntPacked {      // over the trips of a level: row t spawns row_cnt[t] tasks of nfeas[t] rows each
+    const int* row_cnt; const int* nfeas; const int* n_ptr; const Control* ctl;
+    __device__ __forceinline__ i64 size() const { return ctl->overflow ? 0 : (i64)*n_ptr; }
+    __device__ __forceinline__ i64 operator()(i64 t) const { const i64 c = row_cnt[t]; return c | ((c * nfeas[t]) << 32); }
+};
+// finisher: task count of buffer `which`, row count and chunk count (G rows per chunk) of the next level
+struct FinTasksRows {
+    Control* ctl; int which; i64 cap_tasks, cap_rows, cap_chunks; int G;
+    __device__ __forceinline__ void operator()(i64 packed) const {
+        i64 nt = PACK_LO(packed), nr = PACK_HI(packed), nch = (nr + G - 1) / G;
+        if (nt > ctl->need_tasks) ctl->need_tasks = nt;
+        if (nr > ctl->need_rows) ctl->need_rows = nr;
+        if (nch > ctl->need_chunks) ctl->need_chunks = nch;
+        if (nt > cap_tasks) { atomicOr(&ctl->overflow, OVF_TASKS); nt = 0; }
+        if (nr > cap_rows) { atomicOr(&ctl->overflow, OVF_ROWS); nt = 0; }
+        if (nch > cap_chunks) { atomicOr(&ctl->overflow, OVF_CHUNKS); nt = 0; }
+        if (nt == 0) { nr = 0; nch = 0; }
+        ctl->n_tasks[which] = (int)nt; ctl->n_rows = (int)nr; ctl->n_chunks = (int)nch;
+        ctl->stats.n_chunks += (unsigned long long)nch;
+    }
 };
 struct InVehInt {            // scan input over a per-vehicle int array
     const int* p; const DEpoch* ep;
@@ -147,7 +176,7 @@ struct InVehInt {            // scan input over a per-vehicle int array
 
 __global__ void k_tasks_from_screen(const DEpoch* __restrict__ epp, const uint8_t* __restrict__ flag, const i64* __restrict__ pos,
                                     const Control* __restrict__ ctl, const int* __restrict__ len0, const int* __restrict__ S0,
-                                    int* task_veh, int* task_base, int* task_q, int* task_S) {
+                                    int* task_veh, int* task_base, int* task_q, int* task_S, i64* task_row0) {
     const DEpoch& ep = *epp;
     const i64 n = (i64)ep.n_veh * ep.n_search;
     if (ctl->n_tasks[0] == 0 || ctl->overflow) return;
@@ -157,31 +186,18 @@ __global__ void k_tasks_from_screen(const DEpoch* __restrict__ epp, const uint8_
         int v, s;
         if (ep.mode == AMOD_MODE_SBA) { s = (int)(e / ep.n_veh); v = (int)(e - (i64)s * ep.n_veh); }
         else { v = (int)(e / ep.n_search); s = (int)(e - (i64)v * ep.n_search); }
-        const i64 t = pos[e];
+        const i64 t = PACK_LO(pos[e]);
         task_veh[t] = v; task_base[t] = v; task_q[t] = ep.search[s];
         task_S[t] = S0[v];                     // rows (base schedules) of the task
+        task_row0[t] = PACK_HI(pos[e]);
     }
 }
-
-// scan finisher for the row count of a level: rows, and chunks of G rows
-struct FinRows {
-    Control* ctl; i64 cap_rows, cap_chunks; int G;
-    __device__ __forceinline__ void operator()(i64 tot) const {
-        i64 nch = (tot + G - 1) / G;
-        if (tot > ctl->need_rows) ctl->need_rows = tot;
-        if (nch > ctl->need_chunks) ctl->need_chunks = nch;
-        if (tot > cap_rows) { atomicOr(&ctl->overflow, OVF_ROWS); tot = 0; nch = 0; }
-        if (nch > cap_chunks) { atomicOr(&ctl->overflow, OVF_CHUNKS); tot = 0; nch = 0; }
-        ctl->n_rows = (int)tot; ctl->n_chunks = (int)nch;
-        ctl->stats.n_chunks += (unsigned long long)nch;
-    }
-};
 
 // row descriptors: one warp per task, lanes over the task's base schedules
 __global__ void __launch_bounds__(256)
 k_expand_rows(Control* __restrict__ ctl, int which, Level prev, const int* __restrict__ len0, const int* __restrict__ task_veh,
-              const int* __restrict__ task_base, const int* __restrict__ task_q, const i64* __restrict__ task_row0,
-              RowDesc* __restrict__ rows, int* __restrict__ task_nfeas) {
+              const int* __restrict__ task_base, const int* __restrict__ task_q, const int* __restrict__ task_S,
+              const i64* __restrict__ task_row0, RowDesc* __restrict__ rows, int* __restrict__ task_nfeas) {
     const int n = (ctl->n_rows && !ctl->overflow) ? ctl->n_tasks[which] : 0;
     const int lane = threadIdx.x & 31;
     const int nwarps = gridDim.x * (blockDim.x >> 5);
@@ -191,7 +207,7 @@ k_expand_rows(Control* __restrict__ ctl, int which, Level prev, const int* __res
         const int v = task_veh[t], base = task_base[t], q = task_q[t];
         const int l = len0[v] + 2 * prev.k;
         const i64 s0 = prev.s0[base];
-        const i64 r0 = task_row0[t], r1 = task_row0[t + 1];
+        const i64 r0 = task_row0[t], r1 = r0 + task_S[t];
         if (lane == 0) { task_nfeas[t] = 0; items += (unsigned long long)(r1 - r0) * (l + 1); }
         for (i64 r = r0 + lane; r < r1; r += 32) {
             RowDesc d;
@@ -365,7 +381,7 @@ template <int MODE>
 __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32)
 k_gen(const Control* __restrict__ ctl, int which_next, Level l1, Level prev, TripHash th, const int* __restrict__ len0,
       int* __restrict__ row_cnt, const i64* __restrict__ row_off, int* __restrict__ tmp_j, int* __restrict__ tmp_q,
-      int* task_veh, int* task_base, int* task_q, int* task_S) {
+      int* task_veh, int* task_base, int* task_q, int* task_S, i64* task_row0) {
     const int lane = threadIdx.x & 31;
     const int n = ctl->overflow ? 0 : ctl->n_trips[prev.k];
     if (MODE == 1 && ctl->n_tasks[which_next] == 0) return;
@@ -375,7 +391,8 @@ k_gen(const Control* __restrict__ ctl, int which_next, Level l1, Level prev, Tri
         const int a0 = l1.veh_start[v], a1 = l1.veh_start[v + 1];
         const int* mine = prev.trip_req + (i64)t * k;
         int cnt = 0;
-        const i64 off = MODE == 1 ? row_off[t] : 0;
+        const i64 off = MODE == 1 ? PACK_LO(row_off[t]) : 0;
+        const i64 rbase = MODE == 1 ? PACK_HI(row_off[t]) : 0;
         for (int c0 = a0; c0 < a1; c0 += 32) {
             const int c = c0 + lane;
             int j = -1, r = -1;
@@ -416,6 +433,7 @@ k_gen(const Control* __restrict__ ctl, int which_next, Level l1, Level prev, Tri
             }
             const i64 o = off + rank;
             task_veh[o] = v; task_base[o] = t; task_q[o] = tmp_q[off + e]; task_S[o] = S_next;
+            task_row0[o] = rbase + (i64)rank * S_next;
         }
     }
 }

@@ -30,34 +30,33 @@ __device__ __forceinline__ i64 block_excl_scan(i64 x, i64* total, i64* smem /*[S
     return r;
 }
 
-__device__ __forceinline__ void scan_segment(i64 n, i64* lo, i64* hi) {
-    i64 seg = (n + gridDim.x - 1) / gridDim.x;
+__device__ __forceinline__ void scan_segment(i64 n, int vb, int vg, i64* lo, i64* hi) {   // block vb of vg
+    i64 seg = (n + vg - 1) / vg;
     seg = (seg + SCAN_TILE - 1) / SCAN_TILE * SCAN_TILE;
-    *lo = min(n, (i64)blockIdx.x * seg);
+    *lo = min(n, (i64)vb * seg);
     *hi = min(n, *lo + seg);
 }
 
 template <typename In>
-__global__ void __launch_bounds__(SCAN_THREADS) k_scan_a(In in, i64* __restrict__ partial) {
-    __shared__ i64 smem[SCAN_THREADS / 32 + 1];
+__device__ __forceinline__ void scan_phase_a(const In& in, int vb, int vg, i64* __restrict__ partial, i64* smem) {
     const i64 n = in.size();
     i64 lo, hi;
-    scan_segment(n, &lo, &hi);
+    scan_segment(n, vb, vg, &lo, &hi);
     i64 s = 0;
     for (i64 i = lo + threadIdx.x; i < hi; i += SCAN_THREADS) s += in(i);
     i64 tot;
     block_excl_scan(s, &tot, smem);
-    if (threadIdx.x == 0) partial[blockIdx.x] = tot;
+    if (threadIdx.x == 0) partial[vb] = tot;
 }
 
 template <typename In, typename Fin>
-__global__ void __launch_bounds__(SCAN_THREADS) k_scan_b(In in, const i64* __restrict__ partial, i64* __restrict__ out, Fin fin) {
-    __shared__ i64 smem[SCAN_THREADS / 32 + 1];
+__device__ __forceinline__ void scan_phase_b(const In& in, int vb, int vg, const i64* __restrict__ partial, i64* __restrict__ out,
+                                             const Fin& fin, i64* smem) {
     const i64 n = in.size();
     i64 lo, hi;
-    scan_segment(n, &lo, &hi);
+    scan_segment(n, vb, vg, &lo, &hi);
     i64 p = 0;
-    for (int b = threadIdx.x; b < (int)blockIdx.x; b += SCAN_THREADS) p += partial[b];
+    for (int b = threadIdx.x; b < vb; b += SCAN_THREADS) p += partial[b];
     i64 carry;
     block_excl_scan(p, &carry, smem);
     for (i64 base = lo; base < hi; base += SCAN_TILE) {
@@ -72,7 +71,37 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_scan_b(In in, const i64* __res
         for (int k = 0; k < SCAN_ITEMS; k++) { if (i0 + k < hi) out[i0 + k] = e; e += v[k]; }
         carry += tot;
     }
-    if (blockIdx.x == gridDim.x - 1 && threadIdx.x == 0) { out[n] = carry; fin(carry); }
+    if (vb == vg - 1 && threadIdx.x == 0) { out[n] = carry; fin(carry); }
+}
+
+template <typename In>
+__global__ void __launch_bounds__(SCAN_THREADS) k_scan_a(In in, i64* __restrict__ partial) {
+    __shared__ i64 smem[SCAN_THREADS / 32 + 1];
+    scan_phase_a(in, blockIdx.x, gridDim.x, partial, smem);
+}
+
+template <typename In, typename Fin>
+__global__ void __launch_bounds__(SCAN_THREADS) k_scan_b(In in, const i64* __restrict__ partial, i64* __restrict__ out, Fin fin) {
+    __shared__ i64 smem[SCAN_THREADS / 32 + 1];
+    scan_phase_b(in, blockIdx.x, gridDim.x, partial, out, fin, smem);
+}
+
+// two independent scans in one launch pair: the first half of the grid does A, the second half B
+template <typename InA, typename InB>
+__global__ void __launch_bounds__(SCAN_THREADS) k_scan2_a(InA a, InB b, i64* __restrict__ partial) {
+    __shared__ i64 smem[SCAN_THREADS / 32 + 1];
+    const int half = gridDim.x >> 1;
+    if ((int)blockIdx.x < half) scan_phase_a(a, blockIdx.x, half, partial, smem);
+    else scan_phase_a(b, blockIdx.x - half, half, partial + half, smem);
+}
+
+template <typename InA, typename FinA, typename InB, typename FinB>
+__global__ void __launch_bounds__(SCAN_THREADS) k_scan2_b(InA a, FinA fa, i64* __restrict__ outa, InB b, FinB fb, i64* __restrict__ outb,
+                                                          const i64* __restrict__ partial) {
+    __shared__ i64 smem[SCAN_THREADS / 32 + 1];
+    const int half = gridDim.x >> 1;
+    if ((int)blockIdx.x < half) scan_phase_b(a, blockIdx.x, half, partial, outa, fa, smem);
+    else scan_phase_b(b, blockIdx.x - half, half, partial + half, outb, fb, smem);
 }
 
 // ---- input functors ---------------------------------------------------------------------------

@@ -262,7 +262,7 @@ def pool_to_records(pool: Pool, ep: Epoch, vehs, req_objs) -> PoolRecords:
     soff = pool.ent_sche_off.tolist()
     treq = pool.trip_req.tolist()
     scode = pool.sche_code.tolist()
-    cost = pool.ent_cost  # keep numpy float64 scalars like the reference (np.float64 costs)
+    cost = pool.ent_cost.copy()  # keep numpy float64 scalars like the reference (np.float64 costs)
     for e in range(len(ent_veh)):
         vi = ent_veh[e]
         veh = vehs[vi]
@@ -275,7 +275,7 @@ def pool_to_records(pool: Pool, ep: Epoch, vehs, req_objs) -> PoolRecords:
             else:
                 sche.append(drop[c >> 1] if c & 1 else pick[c >> 1])
         out.append([veh, [req_objs[i] for i in treq[toff[e]:toff[e + 1]]], sche, cost[e], 0.0])
-    out.delays = pool.ent_delay
+    out.delays = pool.ent_delay.copy()      # the pool arrays may be views of reused host buffers
     out.stats = pool.stats
     return out
 

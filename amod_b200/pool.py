@@ -85,11 +85,22 @@ class PoolBuilder:
         self._check(self.lib.amod_pool_view(self.h, C.byref(v)))
         return v
 
-    def fetch(self) -> Pool:
-        """Copy the device pool into fresh numpy arrays."""
+    def fetch(self, reuse: bool = False) -> Pool:
+        """Copy the device pool into numpy arrays.  With reuse=True the arrays are views of grow-only
+        host buffers owned by the builder (no page faults per epoch); they are overwritten by the next
+        fetch, which is fine for the seams (records are materialised immediately)."""
         P, NT, NS = self.pool_sizes()
         n = {"e": P, "e1": P + 1, "t": NT, "s": NS}
-        arrs = {name: np.empty(max(n[key], 1), dtype=dt) for name, dt, key in capi.POOL_FIELDS}
+        if reuse:
+            bufs = getattr(self, "_host_bufs", None)
+            if bufs is None or any(bufs[name].size < max(n[key], 1) for name, _dt, key in capi.POOL_FIELDS):
+                bufs = {name: np.empty(max(int(1.5 * n[key]) + 1024, 1), dtype=dt) for name, dt, key in capi.POOL_FIELDS}
+                for a in bufs.values():
+                    a.fill(0)      # touch the pages once
+                self._host_bufs = bufs
+            arrs = bufs
+        else:
+            arrs = {name: np.empty(max(n[key], 1), dtype=dt) for name, dt, key in capi.POOL_FIELDS}
         o = capi.AmodPool()
         o.cap_entries, o.cap_trip_reqs, o.cap_stops = P, NT, NS
         for name, _dt, _key in capi.POOL_FIELDS:
@@ -97,9 +108,9 @@ class PoolBuilder:
         self._check(self.lib.amod_pool_fetch(self.h, C.byref(o), capi.LOC_HOST))
         return Pool(stats=dict(self.last_stats), **{name: arrs[name][:n[key]] for name, _dt, key in capi.POOL_FIELDS})
 
-    def build_pool(self, ep: Epoch) -> Pool:
+    def build_pool(self, ep: Epoch, reuse: bool = False) -> Pool:
         self.build(ep)
-        return self.fetch()
+        return self.fetch(reuse)
 
     def npo_match(self, idle_nid, pend_onid):
         idle_nid = np.ascontiguousarray(idle_nid, dtype=np.int32)
@@ -125,7 +136,7 @@ class PoolBuilder:
         cap = capacity if capacity is not None else _capacity_of(vehs)
         mode = MODE_OSP if enable_reoptimization else MODE_OSP_NR
         ep, req_objs = marshal.marshal_epoch(reqs, vehs, considered_rids, system_time_sec, cap, mode)
-        pool = self.build_pool(ep)
+        pool = self.build_pool(ep, reuse=True)
         return marshal.pool_to_records(pool, ep, vehs, req_objs)
 
     def compute_candidate_veh_req_pairs(self, new_received_rids, reqs, vehs, system_time_sec,
@@ -133,7 +144,7 @@ class PoolBuilder:
         """B2."""
         cap = capacity if capacity is not None else _capacity_of(vehs)
         ep, req_objs = marshal.marshal_epoch(reqs, vehs, new_received_rids, system_time_sec, cap, MODE_SBA)
-        pool = self.build_pool(ep)
+        pool = self.build_pool(ep, reuse=True)
         return marshal.pool_to_records(pool, ep, vehs, req_objs)
 
     def reposition_idle_vehicles_to_nearest_pending_orders(self, reqs, vehs, system_time_sec, num_of_new_reqs,

@@ -282,7 +282,7 @@ def main():
     # ---- end-to-end arm: C-ABI call with HOST buffers, H2D + D2H inside the timed region ------------
     def step_e2e(i):
         w = work[i % len(work)]
-        pool = b.build_pool(w["host"])
+        pool = b.build_pool(w["host"], reuse=True)
         if world > 1:
             allgather_pool()
         h2d = sum(getattr(w["host"], f).nbytes for f in capi.EPOCH_PTR_FIELDS)
