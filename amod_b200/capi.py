@@ -54,7 +54,7 @@ class AmodStats(C.Structure):
                 ("n_entries", C.c_int64), ("n_sches_stored", C.c_int64), ("n_tasks", C.c_int64),
                 ("n_levels", C.c_int32), ("n_kernel_launches", C.c_int32), ("ms_build", C.c_double),
                 ("ms_eval", C.c_double), ("n_eval_launches", C.c_int32), ("n_attempts", C.c_int32),
-                ("n_chunks", C.c_int64), ("n_items", C.c_int64)]
+                ("n_chunks", C.c_int64), ("n_items", C.c_int64), ("n_lookups_eval", C.c_int64)]
 
     def as_dict(self):
         return {f: getattr(self, f) for f, _ in self._fields_ if f != "reserved"}
@@ -76,7 +76,7 @@ def epoch_struct(ep, ptr_of=None) -> AmodEpoch:
 EXPORTS = ("amod_create", "amod_destroy", "amod_last_error", "amod_version", "amod_set_stream",
            "amod_osp_build", "amod_sba_build", "amod_pool_fetch", "amod_pool_view", "amod_npo_match",
            "amod_gather_bench", "amod_gpool_create", "amod_gpool_open_peers", "amod_pool_veh_counts", "amod_gpool_scatter",
-           "amod_gpool_view", "amod_gpool_fetch")
+           "amod_gpool_view", "amod_gpool_fetch", "amod_set_graph")
 
 _lib = None
 
@@ -127,6 +127,8 @@ def load_library(path: str | None = None) -> C.CDLL:
     lib.amod_gpool_view.restype = C.c_int
     lib.amod_gpool_fetch.argtypes = [C.c_void_p, C.POINTER(AmodPool)]
     lib.amod_gpool_fetch.restype = C.c_int
+    lib.amod_set_graph.argtypes = [C.c_void_p, C.c_int]
+    lib.amod_set_graph.restype = C.c_int
     if path is None:
         _lib = lib
     return lib

@@ -17,6 +17,13 @@
 #include "pool.cuh"
 #include "scan.cuh"
 
+#ifndef GRID_ELEM_PER_SM
+#define GRID_ELEM_PER_SM 2
+#endif
+#ifndef GRID_WARP_PER_SM
+#define GRID_WARP_PER_SM 8
+#endif
+
 #define CK(call)                                                                                         \
     do {                                                                                                 \
         cudaError_t e_ = (call);                                                                         \
@@ -76,7 +83,7 @@ struct amod_ctx {
     i64 cap_tasks = 1 << 18, cap_chunks = 1 << 18, cap_rows = 1 << 19, cap_ent = 1 << 18, cap_ptr = 1 << 19, cap_pst = 1 << 21;
     i64 cap_trips[MAX_LEVELS], cap_sch[MAX_LEVELS];
     // workspace
-    DevBuf len0, S0, s0pos, flag8, pos, partial, task_veh[2], task_base[2], task_q[2], task_nchunk[2], task_chunk0, trip_pos,
+    DevBuf len0, S0, s0pos, flag8, pos, major_off, partial, task_veh[2], task_base[2], task_q[2], task_nchunk[2], task_chunk0, trip_pos,
         row_desc, task_nfeas, chunk_cnt, lane_cnt, chunk_pos, hash, row_cnt, row_off, tmp_j, tmp_q;
     LevelBufs lv[MAX_LEVELS];
     // pool
@@ -194,7 +201,7 @@ extern "C" void amod_destroy(amod_ctx* ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     cudaDeviceSynchronize();
-    DevBuf* all[] = {&ctx->ep_dev, &ctx->ctl, &ctx->len0, &ctx->S0, &ctx->s0pos, &ctx->flag8, &ctx->pos, &ctx->partial,
+    DevBuf* all[] = {&ctx->ep_dev, &ctx->ctl, &ctx->len0, &ctx->S0, &ctx->s0pos, &ctx->flag8, &ctx->pos, &ctx->major_off, &ctx->partial,
                      &ctx->task_veh[0], &ctx->task_veh[1], &ctx->task_base[0], &ctx->task_base[1], &ctx->task_q[0], &ctx->task_q[1],
                      &ctx->task_nchunk[0], &ctx->task_nchunk[1], &ctx->task_chunk0, &ctx->trip_pos, &ctx->row_desc, &ctx->task_nfeas, &ctx->chunk_cnt,
                      &ctx->lane_cnt, &ctx->chunk_pos, &ctx->hash, &ctx->row_cnt, &ctx->row_off, &ctx->tmp_j, &ctx->tmp_q,
@@ -220,6 +227,12 @@ extern "C" void amod_destroy(amod_ctx* ctx) {
     if (ctx->ev1) cudaEventDestroy(ctx->ev1);
     if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
+}
+
+extern "C" int amod_set_graph(amod_ctx* ctx, int enable) {
+    if (!ctx) return AMOD_E_BADARG;
+    ctx->use_graph = enable != 0;
+    return AMOD_OK;
 }
 
 extern "C" int amod_set_stream(amod_ctx* ctx, void* cuda_stream) {
@@ -322,7 +335,12 @@ static int ensure_buffers(amod_ctx* ctx, int V, i64 n_screen, int max_level, con
     const size_t T = (size_t)ctx->cap_tasks, C = (size_t)ctx->cap_chunks;
     CK(ctx->ctl.ensure(sizeof(Control)));
     CK(ctx->len0.ensure(4 * (size_t)(V + 1))); CK(ctx->S0.ensure(4 * (size_t)(V + 1))); CK(ctx->s0pos.ensure(8 * (size_t)(V + 2)));
-    CK(ctx->flag8.ensure((size_t)std::max(n_screen, (i64)1))); CK(ctx->pos.ensure(8 * (size_t)(n_screen + 2)));
+    {   // screen: survivor bitmask (one word per 32 minors of each major) + per-major packed counts / offsets
+        const size_t Qs = V > 0 ? (size_t)(n_screen / V) : 0;
+        const size_t words = std::max((size_t)V * ((Qs + 31) / 32), Qs * (((size_t)V + 31) / 32)) + 1;
+        const size_t majors = std::max((size_t)V, Qs) + 2;
+        CK(ctx->flag8.ensure(4 * words)); CK(ctx->pos.ensure(8 * majors)); CK(ctx->major_off.ensure(8 * majors));
+    }
     CK(ctx->partial.ensure(8 * (size_t)(ctx->n_sm + 1)));
     for (int w = 0; w < 2; w++) {
         CK(ctx->task_veh[w].ensure(4 * T)); CK(ctx->task_base[w].ensure(4 * T)); CK(ctx->task_q[w].ensure(4 * T));
@@ -378,8 +396,8 @@ static int enqueue_build(amod_ctx* ctx, int mode, Table<TT> tt, int max_level, c
     const int sba = mode == AMOD_MODE_SBA;
     Control* ctl = ctx->ctl.as<Control>();
     Stats* dstats = &ctl->stats;
-    const int G = ctx->n_sm * 2;                 // elementwise kernels: grid-stride on a fixed grid
-    const int GE = ctx->n_sm * 8;                // warp-per-item kernels
+    const int G = ctx->n_sm * GRID_ELEM_PER_SM;   // elementwise kernels: grid-stride on a fixed grid
+    const int GE = ctx->n_sm * GRID_WARP_PER_SM;   // warp-per-item kernels
     size_t n_ev = 0;
     int* len0 = ctx->len0.as<int>();
 
@@ -393,13 +411,13 @@ static int enqueue_build(amod_ctx* ctx, int mode, Table<TT> tt, int max_level, c
     }
     // ---- level-1 tasks: reachability screen ---------------------------------------------------------
     {
-        k_screen<TT><<<G * 4, 256, 0, st>>>(d, tt, ctx->flag8.as<uint8_t>());
         const int G1 = std::max(1, 32 / (ls.lv[0].stride + 1));
-        scan_dev(ctx, InScreenPacked{ctx->flag8.as<uint8_t>(), ctx->S0.as<int>(), d}, ctx->pos.as<i64>(),
+        k_screen_count<TT><<<GE, WARPS_PER_BLOCK * 32, 0, st>>>(d, tt, ctx->S0.as<int>(), ctx->flag8.as<unsigned>(), ctx->pos.as<i64>());
+        scan_dev(ctx, InMajorPacked{ctx->pos.as<i64>(), d}, ctx->major_off.as<i64>(),
                  FinTasksRows{ctl, 0, ctx->cap_tasks, ctx->cap_rows, ctx->cap_chunks, G1});
-        k_tasks_from_screen<<<G * 4, 256, 0, st>>>(d, ctx->flag8.as<uint8_t>(), ctx->pos.as<i64>(), ctl, len0, ctx->S0.as<int>(),
-                                                  ctx->task_veh[0].as<int>(), ctx->task_base[0].as<int>(), ctx->task_q[0].as<int>(),
-                                                  ctx->task_nchunk[0].as<int>(), ctx->task_chunk0.as<i64>());
+        k_screen_fill<<<GE, WARPS_PER_BLOCK * 32, 0, st>>>(d, ctl, ctx->S0.as<int>(), ctx->flag8.as<unsigned>(), ctx->major_off.as<i64>(),
+                                                          ctx->task_veh[0].as<int>(), ctx->task_base[0].as<int>(), ctx->task_q[0].as<int>(),
+                                                          ctx->task_nchunk[0].as<int>(), ctx->task_chunk0.as<i64>());
         ctx->n_launches += 2;
     }
     // ---- levels 1..max_level ----------------------------------------------------------------------------
@@ -428,7 +446,9 @@ static int enqueue_build(amod_ctx* ctx, int mode, Table<TT> tt, int max_level, c
         k_eval<TT, 1><<<GE, WARPS_PER_BLOCK * 32, 0, st>>>(d, tt, prev, lv, ctl, Gk, rows, ctx->chunk_cnt.as<int>(),
                                                           ctx->lane_cnt.as<uint8_t>(), cpos, tnf, dstats);
         CK(cudaEventRecord(get_event(ctx, n_ev++), st));
-        k_classify<<<G, WARPS_PER_BLOCK * 32, 0, st>>>(d, ctl, lv, sba);
+        unsigned hash_sz = 0;       // the level's trip lookup table is cleared by the classify kernel that precedes its build
+        if (k >= 2 && k < max_level) { hash_sz = 64; while (hash_sz < 2u * (unsigned)lv.cap_trips + 2u) hash_sz <<= 1; }
+        k_classify<<<G, WARPS_PER_BLOCK * 32, 0, st>>>(d, ctl, lv, sba, ctx->hash.as<int>(), hash_sz);
         ctx->n_launches += 5;
         if (k == max_level) break;
         // ---- candidates of size k+1 ---------------------------------------------------------------------
@@ -436,7 +456,6 @@ static int enqueue_build(amod_ctx* ctx, int mode, Table<TT> tt, int max_level, c
         if (k >= 2) {
             unsigned sz = 64; while (sz < 2u * (unsigned)lv.cap_trips + 2u) sz <<= 1;
             th.mask = sz - 1;
-            CK(cudaMemsetAsync(ctx->hash.p, 0xff, 4 * (size_t)sz, st));
             k_hash_build<<<G, 256, 0, st>>>(ctl, lv, th);
             ctx->n_launches++;
         }
@@ -454,14 +473,13 @@ static int enqueue_build(amod_ctx* ctx, int mode, Table<TT> tt, int max_level, c
     {
         LevelSet lsp = ls;
         lsp.n = max_level + 1;          // only the levels searched this epoch hold current data
-        k_pool_veh_count<<<G, 256, 0, st>>>(d, lsp, ctl, ctx->veh_cnt.as<int>());
-        scan_dev(ctx, InVehInt{ctx->veh_cnt.as<int>(), d}, ctx->veh_off.as<i64>(), FinPoolEntries{ctl, pb.cap_ent, sba});
+        scan_dev(ctx, InVehEntries{d, lsp, ctl}, ctx->veh_off.as<i64>(), FinPoolEntries{ctl, pb.cap_ent, sba});
         k_pool_meta_veh<<<G, 256, 0, st>>>(d, lsp, len0, ctx->veh_off.as<i64>(), ctl, pb);
         k_pool_meta_levels<<<G, 256, 0, st>>>(d, lsp, len0, ctx->veh_off.as<i64>(), ctl, pb);
-        scan_dev(ctx, InEntLen{pb.ent_tlen, ctl}, pb.trip_off, FinCountI64{&ctl->n_ptr, pb.cap_ptr, &ctl->need_ptr, &ctl->overflow, OVF_POOL});
-        scan_dev(ctx, InEntLen{pb.ent_slen, ctl}, pb.sche_off, FinCountI64{&ctl->n_pst, pb.cap_pst, &ctl->need_pst, &ctl->overflow, OVF_POOL});
+        scan_dev2(ctx, InEntLen{pb.ent_tlen, ctl}, pb.trip_off, FinCountI64{&ctl->n_ptr, pb.cap_ptr, &ctl->need_ptr, &ctl->overflow, OVF_POOL},
+                  InEntLen{pb.ent_slen, ctl}, pb.sche_off, FinCountI64{&ctl->n_pst, pb.cap_pst, &ctl->need_pst, &ctl->overflow, OVF_POOL});
         k_pool_payload<TT><<<G * 2, 128, 0, st>>>(d, tt, lsp, ctl, pb);
-        ctx->n_launches += 4;
+        ctx->n_launches += 3;
     }
     *n_ev_out = n_ev;
     return AMOD_OK;
@@ -589,6 +607,7 @@ static int build_impl(amod_ctx* ctx, const amod_epoch* ep, int loc, amod_stats* 
         out_stats->n_attempts = ctx->n_attempts;
         out_stats->n_chunks = (int64_t)h->stats.n_chunks;
         out_stats->n_items = (int64_t)h->stats.n_items;
+        out_stats->n_lookups_eval = (int64_t)h->stats.n_lookups_eval;
     }
     (void)total_tasks;
     if (mode != AMOD_MODE_SBA && run_levels == max_level && h->n_trips[max_level] > 0)

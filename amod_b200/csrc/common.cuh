@@ -59,7 +59,7 @@ struct Level {
 #define MAX_LEVELS (AMOD_MAX_TRIP + 1)
 
 struct Stats {            // device counters
-    unsigned long long n_screens, n_evals, n_lookups, n_sches, n_tasks, flags, n_chunks, n_items;
+    unsigned long long n_screens, n_evals, n_lookups, n_sches, n_tasks, flags, n_chunks, n_items, n_lookups_eval;
 };
 
 // Device-resident control block: every size the level-synchronous pipeline produces lives here, so

@@ -255,6 +255,7 @@ k_eval(const DEpoch* __restrict__ epp, Table<TT> tt, Level prev, Level cur, cons
         if (lane == 0 && (acc_evals | acc_lookups)) {
             atomicAdd(&stats->n_evals, acc_evals);
             atomicAdd(&stats->n_lookups, acc_lookups);
+            atomicAdd(&stats->n_lookups_eval, acc_lookups);
         }
     }
 }

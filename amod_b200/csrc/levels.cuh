@@ -117,35 +117,62 @@ k_basic(const DEpoch* __restrict__ epp, Table<TT> tt, Level lv0, int* __restrict
 // ---------------------------------------------------------------------------------------------
 // Screen: tt[veh.nid][req.onid] + veh.t_to_nid + T > req.Clp -> skip (dispatch_osp.py:160,
 // dispatch_sba.py:59; note the association differs from the in-schedule check).
-// Flat order = task order: vehicle-major for OSP, request-major for SBA.
+// Task order is the reference's loop order: vehicle-major for OSP, request-major for SBA.  One warp per
+// "major" (vehicle resp. request) walks the minors 32 at a time: pass 1 keeps a survivor bitmask and the
+// (task, row) counts of the major, a prefix sum over the majors gives its offsets, pass 2 expands the
+// bitmask into tasks in order.  (No V x Q intermediate except the bitmask.)
 // ---------------------------------------------------------------------------------------------
-template <typename TT>
-__global__ void k_screen(const DEpoch* __restrict__ epp, Table<TT> tt, uint8_t* __restrict__ flag) {
-    const DEpoch& ep = *epp;
-    const i64 n = (i64)ep.n_veh * ep.n_search;
-    const i64 stride = (i64)gridDim.x * blockDim.x;
-    for (i64 e = (i64)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += stride) {
-        int v, s;
-        if (ep.mode == AMOD_MODE_SBA) { s = (int)(e / ep.n_veh); v = (int)(e - (i64)s * ep.n_veh); }
-        else { v = (int)(e / ep.n_search); s = (int)(e - (i64)v * ep.n_search); }
-        const int q = ep.search[s];
-        const double d = tt(ep.veh_nid[v], ep.onid[q]);
-        flag[e] = !(d + ep.veh_t[v] + ep.T > ep.clp[q]);
-    }
-}
-
 // Packed two-component scans: low 32 bits count tasks, high 32 bits count their rows (base schedules),
 // so one prefix sum yields both the task index and the task's first row (both totals < 2^31).
 #define PACK_LO(x) ((i64)((x) & 0xffffffffll))
 #define PACK_HI(x) ((i64)((x) >> 32))
-struct InScreenPacked {      // over the V x Q screen flags: a surviving (vehicle, request) pair is a task of S0[v] rows
-    const uint8_t* p; const int* S0; const DEpoch* ep;
-    __device__ __forceinline__ i64 size() const { return (i64)ep->n_veh * ep->n_search; }
-    __device__ __forceinline__ i64 operator()(i64 e) const {
-        if (!p[e]) return 0;
-        const int v = ep->mode == AMOD_MODE_SBA ? (int)(e % ep->n_veh) : (int)(e / ep->n_search);
-        return 1ll | ((i64)S0[v] << 32);
+
+template <typename TT>
+__global__ void __launch_bounds__(WARPS_PER_BLOCK * 32)
+k_screen_count(const DEpoch* __restrict__ epp, Table<TT> tt, const int* __restrict__ S0, unsigned* __restrict__ bits,
+               i64* __restrict__ major_cnt) {
+    const DEpoch& ep = *epp;
+    const int lane = threadIdx.x & 31;
+    const bool sba = ep.mode == AMOD_MODE_SBA;
+    const int n_major = sba ? ep.n_search : ep.n_veh, n_minor = sba ? ep.n_veh : ep.n_search;
+    const int wpm = (n_minor + 31) >> 5;
+    const int nwarps = gridDim.x * WARPS_PER_BLOCK;
+    for (int mj = blockIdx.x * WARPS_PER_BLOCK + (threadIdx.x >> 5); mj < n_major; mj += nwarps) {
+        int cnt = 0, rows = 0;
+        // the major's own parameters
+        const int vq = sba ? ep.search[mj] : 0;
+        const int m_node = sba ? ep.onid[vq] : ep.veh_nid[mj];
+        const double m_a = sba ? ep.clp[vq] : ep.veh_t[mj];
+        for (int w = 0; w < wpm; w++) {
+            const int mn = w * 32 + lane;
+            bool ok = false;
+            int S = 0;
+            if (mn < n_minor) {
+                if (sba) {   // major = request, minor = vehicle
+                    const double d = tt(ep.veh_nid[mn], m_node);
+                    ok = !(d + ep.veh_t[mn] + ep.T > m_a);
+                    S = S0[mn];
+                } else {     // major = vehicle, minor = searched request
+                    const int q = ep.search[mn];
+                    const double d = tt(m_node, ep.onid[q]);
+                    ok = !(d + m_a + ep.T > ep.clp[q]);
+                    S = S0[mj];
+                }
+            }
+            const unsigned bal = __ballot_sync(FULL, ok);
+            if (lane == 0) bits[(i64)mj * wpm + w] = bal;
+            cnt += __popc(bal);
+            rows += ok ? S : 0;
+        }
+        rows = warp_sum(rows);
+        if (lane == 0) major_cnt[mj] = (i64)cnt | ((i64)rows << 32);
     }
+}
+
+struct InMajorPacked {       // scan input over the majors of the screen
+    const i64* p; const DEpoch* ep;
+    __device__ __forceinline__ i64 size() const { return ep->mode == AMOD_MODE_SBA ? ep->n_search : ep->n_veh; }
+    __device__ __forceinline__ i64 operator()(i64 i) const { return p[i]; }
 };
 struct InRowCntPacked {      // over the trips of a level: row t spawns row_cnt[t] tasks of nfeas[t] rows each
     const int* row_cnt; const int* nfeas; const int* n_ptr; const Control* ctl;
@@ -174,22 +201,36 @@ struct InVehInt {            // scan input over a per-vehicle int array
     __device__ __forceinline__ i64 operator()(i64 i) const { return (i64)p[i]; }
 };
 
-__global__ void k_tasks_from_screen(const DEpoch* __restrict__ epp, const uint8_t* __restrict__ flag, const i64* __restrict__ pos,
-                                    const Control* __restrict__ ctl, const int* __restrict__ len0, const int* __restrict__ S0,
-                                    int* task_veh, int* task_base, int* task_q, int* task_S, i64* task_row0) {
+__global__ void __launch_bounds__(WARPS_PER_BLOCK * 32)
+k_screen_fill(const DEpoch* __restrict__ epp, const Control* __restrict__ ctl, const int* __restrict__ S0,
+              const unsigned* __restrict__ bits, const i64* __restrict__ major_off, int* task_veh, int* task_base, int* task_q,
+              int* task_S, i64* task_row0) {
     const DEpoch& ep = *epp;
-    const i64 n = (i64)ep.n_veh * ep.n_search;
     if (ctl->n_tasks[0] == 0 || ctl->overflow) return;
-    const i64 stride = (i64)gridDim.x * blockDim.x;
-    for (i64 e = (i64)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += stride) {
-        if (!flag[e]) continue;
-        int v, s;
-        if (ep.mode == AMOD_MODE_SBA) { s = (int)(e / ep.n_veh); v = (int)(e - (i64)s * ep.n_veh); }
-        else { v = (int)(e / ep.n_search); s = (int)(e - (i64)v * ep.n_search); }
-        const i64 t = PACK_LO(pos[e]);
-        task_veh[t] = v; task_base[t] = v; task_q[t] = ep.search[s];
-        task_S[t] = S0[v];                     // rows (base schedules) of the task
-        task_row0[t] = PACK_HI(pos[e]);
+    const int lane = threadIdx.x & 31;
+    const bool sba = ep.mode == AMOD_MODE_SBA;
+    const int n_major = sba ? ep.n_search : ep.n_veh, n_minor = sba ? ep.n_veh : ep.n_search;
+    const int wpm = (n_minor + 31) >> 5;
+    const int nwarps = gridDim.x * WARPS_PER_BLOCK;
+    for (int mj = blockIdx.x * WARPS_PER_BLOCK + (threadIdx.x >> 5); mj < n_major; mj += nwarps) {
+        i64 t0 = PACK_LO(major_off[mj]), r0 = PACK_HI(major_off[mj]);
+        if (PACK_LO(major_off[mj + 1]) == t0) continue;
+        for (int w = 0; w < wpm; w++) {
+            const unsigned word = bits[(i64)mj * wpm + w];
+            if (!word) continue;
+            const int mn = w * 32 + lane;
+            const bool ok = (word >> lane) & 1u;
+            const int v = sba ? mn : mj;
+            const int S = ok ? S0[v] : 0;
+            const int rpre = warp_excl_sum(S, lane);
+            if (ok) {
+                const i64 t = t0 + __popc(word & ((1u << lane) - 1u));
+                task_veh[t] = v; task_base[t] = v; task_q[t] = ep.search[sba ? mj : mn];
+                task_S[t] = S; task_row0[t] = r0 + rpre;
+            }
+            t0 += __popc(word);
+            r0 += __shfl_sync(FULL, rpre + S, 31);
+        }
     }
 }
 
@@ -274,8 +315,10 @@ __global__ void k_compact_trips(const Control* __restrict__ ctl, int which, cons
 // (first-encountered minimum).  One warp per trip.  Also fills veh_start (trips are vehicle-major).
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32)
-k_classify(const DEpoch* __restrict__ epp, const Control* __restrict__ ctl, Level cur, int sba) {
+k_classify(const DEpoch* __restrict__ epp, const Control* __restrict__ ctl, Level cur, int sba, int* __restrict__ hash_slots,
+           unsigned hash_size) {
     const int n_veh = epp->n_veh;
+    for (unsigned x = blockIdx.x * blockDim.x + threadIdx.x; x < hash_size; x += gridDim.x * blockDim.x) hash_slots[x] = -1;
     const int lane = threadIdx.x & 31;
     const int n = ctl->overflow ? 0 : ctl->n_trips[cur.k];
     const int nwarps = gridDim.x * WARPS_PER_BLOCK;

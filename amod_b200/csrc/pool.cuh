@@ -27,6 +27,19 @@ __global__ void k_pool_veh_count(const DEpoch* __restrict__ epp, LevelSet ls, co
     }
 }
 
+struct InVehEntries {       // scan input: pool entries of vehicle v (dispatch_osp.py:113-125) / one empty pair (dispatch_sba.py:68)
+    const DEpoch* ep; LevelSet ls; const Control* ctl;
+    __device__ __forceinline__ i64 size() const { return ep->n_veh; }
+    __device__ __forceinline__ i64 operator()(i64 v) const {
+        if (ctl->overflow) return 0;
+        const int mode = ep->mode;
+        if (mode == AMOD_MODE_SBA) return 1;
+        i64 c = 1 + (mode == AMOD_MODE_OSP ? 1 : 0);
+        for (int k = 1; k < ls.n; k++) c += ls.lv[k].veh_start[v + 1] - ls.lv[k].veh_start[v];
+        return c;
+    }
+};
+
 struct FinPoolEntries {   // n_ent = scan total (+ the SBA pairs, which precede the per-vehicle empties)
     Control* ctl; i64 cap; int sba;
     __device__ __forceinline__ void operator()(i64 tot) const {

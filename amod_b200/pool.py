@@ -60,6 +60,9 @@ class PoolBuilder:
         if rc != capi.OK:
             raise AmodError(rc, self.lib.amod_last_error(self.h).decode())
 
+    def set_graph(self, enable: bool):
+        self._check(self.lib.amod_set_graph(self.h, int(bool(enable))))
+
     def set_stream(self, cuda_stream: int):
         self._check(self.lib.amod_set_stream(self.h, C.c_void_p(cuda_stream)))
 

@@ -117,6 +117,7 @@ typedef struct amod_stats {
     int32_t n_attempts;     /* 1 unless a device buffer had to be regrown and the epoch rerun                */
     int64_t n_chunks;       /* warp work units of the insertion search                                       */
     int64_t n_items;        /* (base schedule, pick-up index) lanes inside them (<= 32 per chunk)            */
+    int64_t n_lookups_eval; /* the part of n_lookups performed inside insertion-search evaluations           */
 } amod_stats;
 
 /* Upload the travel-time table (row = origin, col = destination; route_functions.py:22-25). */
@@ -124,6 +125,10 @@ int amod_create(amod_ctx** out, int device, int n_nodes, const void* tt_host, in
 void amod_destroy(amod_ctx* ctx);
 const char* amod_last_error(amod_ctx* ctx);
 const char* amod_version(void);
+
+/* Replay the level loop as one captured CUDA graph (default 1).  0 = plain stream launches, which also
+ * brackets every insertion-search kernel with CUDA events (amod_stats.ms_eval) for profiling. */
+int amod_set_graph(amod_ctx* ctx, int enable);
 
 /* Use an existing CUDA stream (cudaStream_t) for all work of this context; 0 = own stream. */
 int amod_set_stream(amod_ctx* ctx, void* cuda_stream);
