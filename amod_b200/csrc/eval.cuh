@@ -137,11 +137,20 @@ k_eval(const DEpoch* __restrict__ epp, Table<TT> tt, Level prev, Level cur, cons
         }
         const int o_w = own ? o_l + 1 : 0;
         const int o_woff = warp_excl_sum(o_w, lane);              // first lane of the row
-        const int o_soff = warp_excl_sum(o_l, lane);              // first staged stop of the row
-        const int o_goff = warp_excl_sum(own ? 5 * o_l + 2 : 0, lane);   // first staged leg of the row
         const int items = __shfl_sync(FULL, o_woff + o_w, 31);
-        const int tot_stops = __shfl_sync(FULL, o_soff + o_l, 31);
-        const int tot_legs = __shfl_sync(FULL, o_goff + (own ? 5 * o_l + 2 : 0), 31);
+        // fill pass: only rows in which some lane found a feasible insertion are staged again
+        bool o_act = own;
+        if (MODE == 1 && items <= 32) {
+            const unsigned hit = __ballot_sync(FULL, lane_cnt[(i64)c * 64 + lane] != 0);
+            const unsigned span = o_w >= 32 ? FULL : (((1u << o_w) - 1u) << o_woff);
+            o_act = own && (hit & span) != 0u;
+        }
+        const int o_sl = o_act ? o_l : 0;
+        const int o_gl = o_act ? 5 * o_l + 2 : 0;
+        const int o_soff = warp_excl_sum(o_sl, lane);             // first staged stop of the row
+        const int o_goff = warp_excl_sum(o_gl, lane);             // first staged leg of the row
+        const int tot_stops = __shfl_sync(FULL, o_soff + o_sl, 31);
+        const int tot_legs = __shfl_sync(FULL, o_goff + o_gl, 31);
 
         __syncwarp();
         for (int e0 = 0; e0 < tot_stops; e0 += 32) {              // stage the stops of all rows (uniform trip count:
@@ -200,7 +209,9 @@ k_eval(const DEpoch* __restrict__ epp, Table<TT> tt, Level prev, Level cur, cons
             unsigned long long fullmask = 0;
             bool basebad = false, stop3 = false, cap1 = false;
             double A = 0.0;
-            if (valid) {
+            int mine = 0;
+            if (MODE == 1) mine = lane_cnt[(i64)c * 64 + it0 + lane];
+            if (MODE == 0 ? valid : (mine != 0)) {
                 int run = load;
                 if (run >= cap) fullmask |= 1ull;
                 for (int m = 0; m < l; m++) {
@@ -214,18 +225,18 @@ k_eval(const DEpoch* __restrict__ epp, Table<TT> tt, Level prev, Level cur, cons
                 cap1 = basebad || ((fullmask >> i) & 1ull);                              // viol 1 at j = i+1
                 stop3 = !cap1 && (T + A > clp);                                          // viol 3 (scheduling.py:43)
             }
-            // viol==3 ends the i-loop of its base schedule: later i of the same row are never evaluated
-            const unsigned bal3 = __ballot_sync(FULL, stop3);
-            const int lo = max(lane - i, 0);
-            const unsigned same_s_lower = (lane > lo) ? (((1u << lane) - 1u) & ~((1u << lo) - 1u)) : 0u;
-            const bool dead = valid && ((bal3 & same_s_lower) != 0u || dead_s == 0);
-            {   // carry to the second step of a > 31-stop schedule (then the chunk is that single row)
-                const unsigned killed = __ballot_sync(FULL, valid && (stop3 || dead));
-                dead_s = (items > 32 && killed) ? 0 : -1;
-            }
-            const bool live = valid && !dead;
             LaneCount o; o.n = 0; o.evals = 0; o.lookups = 0;
             if (MODE == 0) {
+                // viol==3 ends the i-loop of its base schedule: later i of the same row are never evaluated
+                const unsigned bal3 = __ballot_sync(FULL, stop3);
+                const int lo = max(lane - i, 0);
+                const unsigned same_s_lower = (lane > lo) ? (((1u << lane) - 1u) & ~((1u << lo) - 1u)) : 0u;
+                const bool dead = valid && ((bal3 & same_s_lower) != 0u || dead_s == 0);
+                {   // carry to the second step of a > 31-stop schedule (then the chunk is that single row)
+                    const unsigned killed = __ballot_sync(FULL, valid && (stop3 || dead));
+                    dead_s = (items > 32 && killed) ? 0 : -1;
+                }
+                const bool live = valid && !dead;
                 if (live) {
                     if (cap1) o.evals = 1;
                     else if (stop3) { o.evals = 1; o.lookups = i + 1; }
@@ -236,7 +247,6 @@ k_eval(const DEpoch* __restrict__ epp, Table<TT> tt, Level prev, Level cur, cons
                 if (o.n) atomicAdd(&task_nfeas[task], o.n);
                 cnt_total += o.n;
             } else {
-                const int mine = lane_cnt[(i64)c * 64 + it0 + lane];
                 const int before = warp_excl_sum(mine, lane);
                 if (mine) walk_j<TT, true>(lg, PD, ddl, st.code + soff, l, i, A, q, cld, T, fullmask, o, row_base + before,
                                            cur.sch, cur.sch_cost, cur.stride);
