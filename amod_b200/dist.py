@@ -115,6 +115,10 @@ class PeerPool:
         import torch.distributed as dist
         self.b, self.world, self.rank, self.n_veh_total, self.device = builder, world, rank, n_veh_total, device
         self.vmax = (n_veh_total + world - 1) // world
+        # every rank must use the SAME capacities: the buffer layout is computed from them on each side
+        caps = [None] * world
+        dist.all_gather_object(caps, (int(cap_entries), int(cap_trip_reqs), int(cap_stops)))
+        cap_entries, cap_trip_reqs, cap_stops = (max(c[i] for c in caps) for i in range(3))
         handle = C.create_string_buffer(64)
         builder._check(builder.lib.amod_gpool_create(builder.h, cap_entries, cap_trip_reqs, cap_stops, n_veh_total, handle))
         handles = [None] * world
