@@ -95,6 +95,7 @@ struct amod_ctx {
     // multi-GPU global pool (peer-mapped)
     char* gp_base = nullptr; GPoolLayout gp_layout; GPoolPeers gp_peers; bool gp_open = false; int gp_max_veh = 0;
     DevBuf gp_off, gp_tot; void* gp_peer_ptr[GPOOL_MAX_WORLD] = {nullptr};
+    unsigned long long gp_epoch = 0;
     // npo
     DevBuf npo_in, npo_vm, npo_rm, npo_rb, npo_vb, npo_rdt, npo_mdt, npo_cnt;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
@@ -690,13 +691,15 @@ extern "C" int amod_pool_fetch(amod_ctx* ctx, amod_pool* o, int loc) {
 // ------------------------------------------------------------------------------------------------
 // multi-GPU: global pool in peer-mapped memory
 // ------------------------------------------------------------------------------------------------
-static GPoolLayout gpool_layout(i64 ce, i64 ct, i64 cs) {
+static GPoolLayout gpool_layout(i64 ce, i64 ct, i64 cs, i64 max_veh = 0) {
     GPoolLayout L; memset(&L, 0, sizeof L);
     L.cap_ent = ce; L.cap_ptr = ct; L.cap_pst = cs;
     i64 o = 0;
     auto take = [&](i64 bytes) { i64 at = o; o += (bytes + 255) / 256 * 256; return at; };
+    L.o_flags = take(8 * 2 * GPOOL_MAX_WORLD); L.o_counts = 0;
     L.o_hdr = take(64); L.o_veh = take(4 * ce); L.o_kind = take(4 * ce); L.o_nfeas = take(4 * ce); L.o_cost = take(8 * ce);
     L.o_delay = take(8 * ce); L.o_toff = take(8 * (ce + 1)); L.o_soff = take(8 * (ce + 1)); L.o_treq = take(4 * ct); L.o_scode = take(4 * cs);
+    L.o_counts = take(4 * 3 * (max_veh + GPOOL_MAX_WORLD));     // [world][ceil(max_veh/world)][3] fits for any world
     L.bytes = o;
     return L;
 }
@@ -707,12 +710,12 @@ extern "C" int amod_gpool_create(amod_ctx* ctx, int64_t cap_entries, int64_t cap
     static_assert(sizeof(cudaIpcMemHandle_t) == AMOD_IPC_HANDLE_BYTES, "ipc handle size");
     CK(cudaSetDevice(ctx->device));
     if (ctx->gp_base) return ctx->fail(AMOD_E_BADARG, "global pool already created on this context");
-    ctx->gp_layout = gpool_layout(cap_entries, cap_trip_reqs, cap_stops);
+    ctx->gp_layout = gpool_layout(cap_entries, cap_trip_reqs, cap_stops, max_veh_total);
     CK(cudaMalloc((void**)&ctx->gp_base, (size_t)ctx->gp_layout.bytes));
-    CK(cudaMemset(ctx->gp_base, 0, 64));
+    CK(cudaMemset(ctx->gp_base, 0, (size_t)ctx->gp_layout.o_veh));      // flags + header start at zero
     ctx->gp_max_veh = max_veh_total;
     CK(ctx->gp_off.ensure(8 * 3 * ((size_t)max_veh_total + 2)));
-    CK(ctx->gp_tot.ensure(8 * 4));
+    CK(ctx->gp_tot.ensure(8 * 8));
     cudaIpcMemHandle_t h;
     CK(cudaIpcGetMemHandle(&h, ctx->gp_base));
     memcpy(ipc_handle_out, &h, sizeof h);
@@ -782,6 +785,45 @@ extern "C" int amod_gpool_scatter(amod_ctx* ctx, const int32_t* counts_all_dev, 
     CK(cudaStreamSynchronize(st));
     CK(cudaGetLastError());
     if (h[3]) return ctx->fail(AMOD_E_CAPACITY, "global pool too small: need %lld entries, %lld trip requests, %lld stops", h[0], h[1], h[2]);
+    return AMOD_OK;
+}
+
+extern "C" int amod_gpool_assemble(amod_ctx* ctx, int32_t n_veh_total) {
+    if (!ctx) return AMOD_E_BADARG;
+    if (!ctx->gp_open) return ctx->fail(AMOD_E_BADARG, "amod_gpool_open_peers first");
+    if (!ctx->pool_valid) return ctx->fail(AMOD_E_BADARG, "no pool has been built on this context");
+    if (ctx->h_epoch->mode == AMOD_MODE_SBA) return ctx->fail(AMOD_E_BADARG, "peer assembly needs a vehicle-major (OSP) pool");
+    if (n_veh_total > ctx->gp_max_veh) return ctx->fail(AMOD_E_CAPACITY, "global pool was created for at most %d vehicles", ctx->gp_max_veh);
+    CK(cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    const int world = ctx->gp_peers.world;
+    const int vmax = (n_veh_total + world - 1) / world;
+    const GPoolLayout& L = ctx->gp_layout;
+    const unsigned long long epoch = ++ctx->gp_epoch;
+    i64* off = ctx->gp_off.as<i64>();
+    const size_t stride = (size_t)ctx->gp_max_veh + 2;
+    i64* tot = ctx->gp_tot.as<i64>();
+    unsigned long long* err = (unsigned long long*)(tot + 3);
+    unsigned* ticket = (unsigned*)(tot + 4);
+    if (epoch == 1) CK(cudaMemsetAsync(tot + 3, 0, 16, st)); else CK(cudaMemsetAsync(tot + 3, 0, 8, st));
+    const DEpoch* d = ctx->d_epoch.as<DEpoch>();
+    const PoolBufs pb = pool_bufs_of(ctx);
+    // K1: counts to every rank + flag;  K2: wait for everyone's counts;  scans;  K3: payload to every rank + flag;  K4: wait
+    k_gp_push_counts<<<std::max(1, (vmax + 255) / 256), 256, 0, st>>>(d, ctx->veh_off.as<i64>(), pb, L, ctx->gp_peers, vmax, epoch, ticket);
+    k_gp_wait<<<1, 32, 0, st>>>(ctx->gp_base, L, world, 0, epoch, err);
+    const int* counts_all = (const int*)(ctx->gp_base + L.o_counts);
+    for (int c = 0; c < 3; c++)
+        scan_dev(ctx, InGlobalVeh{counts_all, world, vmax, c, n_veh_total}, off + c * stride, FinStore{tot + c});
+    k_gpool_scatter<<<ctx->n_sm * 4, 256, 0, st>>>(d, ctx->veh_off.as<i64>(), pb, L, ctx->gp_peers, off, off + stride, off + 2 * stride, tot,
+                                                 n_veh_total, err);
+    k_gp_signal_done<<<1, 32, 0, st>>>(L, ctx->gp_peers, epoch);
+    k_gp_wait<<<1, 32, 0, st>>>(ctx->gp_base, L, world, 1, epoch, err);
+    i64 h[4];
+    CK(cudaMemcpyAsync(h, tot, sizeof h, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    CK(cudaGetLastError());
+    if (h[3] & 2) return ctx->fail(AMOD_E_CUDA, "peer assembly timed out waiting for another rank");
+    if (h[3] & 1) return ctx->fail(AMOD_E_CAPACITY, "global pool too small: need %lld entries, %lld trip requests, %lld stops", h[0], h[1], h[2]);
     return AMOD_OK;
 }
 

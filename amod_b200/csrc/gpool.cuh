@@ -9,6 +9,7 @@
 
 struct GPoolLayout {         // one contiguous allocation per rank; identical layout on every rank
     i64 cap_ent, cap_ptr, cap_pst;
+    i64 o_flags, o_counts;   // peer-written: 2*GPOOL_MAX_WORLD epoch flags; all ranks' per-vehicle counts [world][vmax][3]
     i64 o_hdr, o_veh, o_kind, o_nfeas, o_cost, o_delay, o_toff, o_soff, o_treq, o_scode, bytes;
 };
 struct GPoolPeers { char* base[GPOOL_MAX_WORLD]; int world, rank; };
@@ -68,5 +69,66 @@ k_gpool_scatter(const DEpoch* __restrict__ epp, const i64* __restrict__ veh_off,
             for (i64 x = lane; x < ns; x += 32) g_scode[S0 + x] = pb.sche_code[s0 + x];
             if (last && lane == 0) { g_toff[totals[0]] = totals[1]; g_soff[totals[0]] = totals[2]; }   // CSR end sentinels
         }
+    }
+    __threadfence_system();      // peer stores are performed before the kernel (and the flag that follows it) completes
+}
+
+
+// ---- assembly without host collectives: flags in peer memory ---------------------------------------
+__device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v) {
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long* p) {
+    unsigned long long v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+
+// K1: my per-vehicle counts into every rank's counts table; the last block to finish raises my flag on every rank
+__global__ void __launch_bounds__(256)
+k_gp_push_counts(const DEpoch* __restrict__ epp, const i64* __restrict__ veh_off, PoolBufs pb, GPoolLayout L, GPoolPeers peers,
+                 int vmax, unsigned long long epoch, unsigned* ticket) {
+    const int n = epp->n_veh;
+    for (int v = blockIdx.x * blockDim.x + threadIdx.x; v < vmax; v += gridDim.x * blockDim.x) {
+        int c0 = 0, c1 = 0, c2 = 0;
+        if (v < n) {
+            const i64 e0 = veh_off[v], e1 = veh_off[v + 1];
+            c0 = (int)(e1 - e0); c1 = (int)(pb.trip_off[e1] - pb.trip_off[e0]); c2 = (int)(pb.sche_off[e1] - pb.sche_off[e0]);
+        }
+        for (int d = 0; d < peers.world; d++) {
+            int* dst = (int*)(peers.base[d] + L.o_counts) + ((i64)peers.rank * vmax + v) * 3;
+            dst[0] = c0; dst[1] = c1; dst[2] = c2;
+        }
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0 && atomicAdd(ticket, 1u) == gridDim.x - 1) {
+        *ticket = 0;
+        __threadfence_system();
+        for (int d = 0; d < peers.world; d++)
+            st_release_sys((unsigned long long*)(peers.base[d] + L.o_flags) + peers.rank, epoch);
+    }
+}
+
+// K2 / K4: wait until every rank's flag in MY pool has reached `epoch` (bounded spin)
+__global__ void k_gp_wait(const char* __restrict__ my_base, GPoolLayout L, int world, int which, unsigned long long epoch,
+                          unsigned long long* err) {
+    const int r = threadIdx.x;
+    if (r >= world) return;
+    const unsigned long long* f = (const unsigned long long*)(my_base + L.o_flags) + which * GPOOL_MAX_WORLD + r;
+    const long long t0 = clock64();
+    while (ld_acquire_sys(f) < epoch) {
+        if (clock64() - t0 > 6000000000ll) { atomicOr(err, 2ull); break; }   // ~3 s: a rank never arrived
+        __nanosleep(200);
+    }
+    __threadfence_system();
+}
+
+// K3 epilogue: raise my "payload written" flag on every rank (after all scatter blocks have fenced)
+__global__ void k_gp_signal_done(GPoolLayout L, GPoolPeers peers, unsigned long long epoch) {
+    if (threadIdx.x == 0) {
+        __threadfence_system();
+        for (int d = 0; d < peers.world; d++)
+            st_release_sys((unsigned long long*)(peers.base[d] + L.o_flags) + GPOOL_MAX_WORLD + peers.rank, epoch);
     }
 }

@@ -128,6 +128,8 @@ class PeerPool:
         self.counts = torch.zeros(self.vmax * 3, dtype=torch.int32, device=device)
         self.counts_all = torch.zeros(world * self.vmax * 3, dtype=torch.int32, device=device)
         self.nccl = dist.get_backend() == "nccl"
+        # one GPU per rank -> counts, barriers and payload all go through peer memory (no host collective)
+        self.fused = self.nccl
         dist.barrier()
 
     def assemble(self):
@@ -136,6 +138,9 @@ class PeerPool:
         import torch
         import torch.distributed as dist
         b = self.b
+        if self.fused:
+            b._check(b.lib.amod_gpool_assemble(b.h, self.n_veh_total))
+            return
         self.counts.zero_()
         b._check(b.lib.amod_pool_veh_counts(b.h, self.counts.data_ptr()))
         if self.nccl:

@@ -162,6 +162,11 @@ int amod_pool_veh_counts(amod_ctx* ctx, int32_t* counts_dev);
 /* counts_all_dev[world][veh_per_rank_max][3] = the all-gathered counts.  Writes this rank's entries
  * into all peers' global pools.  The caller must run a barrier before any rank reads its pool. */
 int amod_gpool_scatter(amod_ctx* ctx, const int32_t* counts_all_dev, int32_t veh_per_rank_max, int32_t n_veh_total);
+/* The same assembly with NO host-side collective: counts exchange, both barriers and the payload all go
+ * through peer memory (flags + system-scope fences) inside four small kernels per rank.  Requires one
+ * GPU per rank (kernels of different ranks wait on each other).  Returns after the local stream has
+ * drained, i.e. when every rank's stores into this rank's pool have been observed. */
+int amod_gpool_assemble(amod_ctx* ctx, int32_t n_veh_total);
 /* device pointers + sizes of this rank's global pool (valid after the barrier) */
 int amod_gpool_view(amod_ctx* ctx, amod_pool* view);
 /* copy this rank's global pool into caller-owned HOST buffers (AMOD_E_CAPACITY reports the sizes needed) */

@@ -26,6 +26,7 @@ def _worker(rank, world, port, out_dir):
     sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "oracle")); sys.path.insert(0, os.path.join(ROOT, "tests"))
     import torch.distributed as dist
     os.environ["MASTER_ADDR"] = "127.0.0.1"; os.environ["MASTER_PORT"] = str(port)
+    two_gpus = torch.cuda.device_count() >= world
     dist.init_process_group("gloo", rank=rank, world_size=world)
     import oracle
     from amod_b200 import dist as adist, marshal, synth
@@ -48,6 +49,10 @@ def _worker(rank, world, port, out_dir):
         b.build(sub)
         if pp is None:
             pp = adist.PeerPool(b, world, rank, ep.n_veh, 4 * ref.n_entries, 4 * ref.trip_req.size + 64, 4 * ref.sche_code.size + 64, dev)
+            # with one GPU per rank also exercise the flag-based assembly (kernels of different ranks wait on each
+            # other, which must never be done by two processes sharing one GPU)
+            pp.fused = two_gpus and seed >= 2
+        pp.fused = two_gpus and seed >= 2
         pp.assemble()
         got = pp.fetch()
         o, w = marshal.pools_equal(got, ref, rtol=0.0, check_kind=True)
