@@ -115,7 +115,7 @@ def load_library(path: str | None = None) -> C.CDLL:
     lib.amod_gather_bench.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int,
                                       C.POINTER(C.c_double)]
     lib.amod_gather_bench.restype = C.c_int
-    lib.amod_gpool_create.argtypes = [C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_int32, C.c_void_p]
+    lib.amod_gpool_create.argtypes = [C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_int32, C.c_int32, C.c_void_p]
     lib.amod_gpool_create.restype = C.c_int
     lib.amod_gpool_open_peers.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p]
     lib.amod_gpool_open_peers.restype = C.c_int

@@ -94,6 +94,7 @@ struct amod_ctx {
     int n_attempts = 0;
     // multi-GPU global pool (peer-mapped)
     char* gp_base = nullptr; GPoolLayout gp_layout; GPoolPeers gp_peers; bool gp_open = false; int gp_max_veh = 0;
+    GSlotLayout gp_slot; i64 gp_o_stage = 0; int gp_world = 0;
     DevBuf gp_off, gp_tot; void* gp_peer_ptr[GPOOL_MAX_WORLD] = {nullptr};
     unsigned long long gp_epoch = 0;
     // npo
@@ -704,14 +705,31 @@ static GPoolLayout gpool_layout(i64 ce, i64 ct, i64 cs, i64 max_veh = 0) {
     return L;
 }
 
+static GSlotLayout gslot_layout(i64 cv, i64 ce, i64 ct, i64 cs) {
+    GSlotLayout S; memset(&S, 0, sizeof S);
+    S.cap_veh = cv; S.cap_ent = ce; S.cap_ptr = ct; S.cap_pst = cs;
+    i64 o = 0;
+    auto take = [&](i64 bytes) { i64 at = o; o += (bytes + 255) / 256 * 256; return at; };
+    S.o_hdr = take(64); S.o_vehoff = take(8 * (cv + 1)); S.o_kind = take(4 * ce); S.o_nfeas = take(4 * ce); S.o_cost = take(8 * ce);
+    S.o_delay = take(8 * ce); S.o_toff = take(8 * (ce + 1)); S.o_soff = take(8 * (ce + 1)); S.o_treq = take(4 * ct); S.o_scode = take(4 * cs);
+    S.bytes = o;
+    return S;
+}
+
 extern "C" int amod_gpool_create(amod_ctx* ctx, int64_t cap_entries, int64_t cap_trip_reqs, int64_t cap_stops, int32_t max_veh_total,
-                                 void* ipc_handle_out) {
-    if (!ctx || !ipc_handle_out || cap_entries <= 0 || cap_trip_reqs <= 0 || cap_stops <= 0 || max_veh_total <= 0) return AMOD_E_BADARG;
+                                 int32_t world, void* ipc_handle_out) {
+    if (!ctx || !ipc_handle_out || cap_entries <= 0 || cap_trip_reqs <= 0 || cap_stops <= 0 || max_veh_total <= 0 || world < 1 ||
+        world > GPOOL_MAX_WORLD) return AMOD_E_BADARG;
     static_assert(sizeof(cudaIpcMemHandle_t) == AMOD_IPC_HANDLE_BYTES, "ipc handle size");
     CK(cudaSetDevice(ctx->device));
     if (ctx->gp_base) return ctx->fail(AMOD_E_BADARG, "global pool already created on this context");
     ctx->gp_layout = gpool_layout(cap_entries, cap_trip_reqs, cap_stops, max_veh_total);
-    CK(cudaMalloc((void**)&ctx->gp_base, (size_t)ctx->gp_layout.bytes));
+    // staging: one slot per rank, each able to hold twice an even share of the global pool
+    ctx->gp_world = world;
+    ctx->gp_slot = gslot_layout((max_veh_total + world - 1) / world + 1, 2 * (cap_entries / world) + 1024, 2 * (cap_trip_reqs / world) + 1024,
+                                2 * (cap_stops / world) + 1024);
+    ctx->gp_o_stage = ctx->gp_layout.bytes;
+    CK(cudaMalloc((void**)&ctx->gp_base, (size_t)(ctx->gp_layout.bytes + (i64)world * ctx->gp_slot.bytes)));
     CK(cudaMemset(ctx->gp_base, 0, (size_t)ctx->gp_layout.o_veh));      // flags + header start at zero
     ctx->gp_max_veh = max_veh_total;
     CK(ctx->gp_off.ensure(8 * 3 * ((size_t)max_veh_total + 2)));
@@ -794,11 +812,12 @@ extern "C" int amod_gpool_assemble(amod_ctx* ctx, int32_t n_veh_total) {
     if (!ctx->pool_valid) return ctx->fail(AMOD_E_BADARG, "no pool has been built on this context");
     if (ctx->h_epoch->mode == AMOD_MODE_SBA) return ctx->fail(AMOD_E_BADARG, "peer assembly needs a vehicle-major (OSP) pool");
     if (n_veh_total > ctx->gp_max_veh) return ctx->fail(AMOD_E_CAPACITY, "global pool was created for at most %d vehicles", ctx->gp_max_veh);
+    const int world = ctx->gp_peers.world;
+    if (world != ctx->gp_world) return ctx->fail(AMOD_E_BADARG, "world size differs from amod_gpool_create");
     CK(cudaSetDevice(ctx->device));
     cudaStream_t st = ctx->stream;
-    const int world = ctx->gp_peers.world;
-    const int vmax = (n_veh_total + world - 1) / world;
     const GPoolLayout& L = ctx->gp_layout;
+    const GSlotLayout& S = ctx->gp_slot;
     const unsigned long long epoch = ++ctx->gp_epoch;
     i64* off = ctx->gp_off.as<i64>();
     const size_t stride = (size_t)ctx->gp_max_veh + 2;
@@ -806,24 +825,28 @@ extern "C" int amod_gpool_assemble(amod_ctx* ctx, int32_t n_veh_total) {
     unsigned long long* err = (unsigned long long*)(tot + 3);
     unsigned* ticket = (unsigned*)(tot + 4);
     if (epoch == 1) CK(cudaMemsetAsync(tot + 3, 0, 16, st)); else CK(cudaMemsetAsync(tot + 3, 0, 8, st));
-    const DEpoch* d = ctx->d_epoch.as<DEpoch>();
-    const PoolBufs pb = pool_bufs_of(ctx);
-    // K1: counts to every rank + flag;  K2: wait for everyone's counts;  scans;  K3: payload to every rank + flag;  K4: wait
-    k_gp_push_counts<<<std::max(1, (vmax + 255) / 256), 256, 0, st>>>(d, ctx->veh_off.as<i64>(), pb, L, ctx->gp_peers, vmax, epoch, ticket);
+    // every peer must have finished reading my slot of the previous epoch before I overwrite it
+    if (epoch > 1) k_gp_wait<<<1, 32, 0, st>>>(ctx->gp_base, L, world, 1, epoch - 1, err);
+    GPush P; memset(&P, 0, sizeof P);
+    const void* srcs[10] = {nullptr, ctx->veh_off.p, ctx->ent_kind.p, ctx->ent_nfeas.p, ctx->ent_cost.p, ctx->ent_delay.p, ctx->trip_off.p,
+                            ctx->sche_off.p, ctx->trip_req.p, ctx->sche_code.p};
+    const i64 dsts[10] = {S.o_hdr, S.o_vehoff, S.o_kind, S.o_nfeas, S.o_cost, S.o_delay, S.o_toff, S.o_soff, S.o_treq, S.o_scode};
+    for (int g = 0; g < 10; g++) { P.seg[g].src = (const char*)srcs[g]; P.seg[g].dst_off = dsts[g]; P.seg[g].bytes = 0; }
+    P.n = 10;
+    k_gp_push_bulk<<<ctx->n_sm * 2, 256, 0, st>>>(P, L, S, ctx->gp_o_stage, ctx->gp_peers, ctx->d_epoch.as<DEpoch>(), ctx->ctl.as<Control>(),
+                                                epoch, ticket, err);
     k_gp_wait<<<1, 32, 0, st>>>(ctx->gp_base, L, world, 0, epoch, err);
-    const int* counts_all = (const int*)(ctx->gp_base + L.o_counts);
+    const char* stage = ctx->gp_base + ctx->gp_o_stage;
     for (int c = 0; c < 3; c++)
-        scan_dev(ctx, InGlobalVeh{counts_all, world, vmax, c, n_veh_total}, off + c * stride, FinStore{tot + c});
-    k_gpool_scatter<<<ctx->n_sm * 4, 256, 0, st>>>(d, ctx->veh_off.as<i64>(), pb, L, ctx->gp_peers, off, off + stride, off + 2 * stride, tot,
-                                                 n_veh_total, err);
-    k_gp_signal_done<<<1, 32, 0, st>>>(L, ctx->gp_peers, epoch);
-    k_gp_wait<<<1, 32, 0, st>>>(ctx->gp_base, L, world, 1, epoch, err);
+        scan_dev(ctx, InStagedVeh{stage, S, world, c, n_veh_total}, off + c * stride, FinStore{tot + c});
+    k_gp_merge<<<ctx->n_sm * 8, 256, 0, st>>>(stage, S, ctx->gp_base, L, world, off, off + stride, off + 2 * stride, tot, n_veh_total, err);
+    k_gp_signal_done<<<1, 32, 0, st>>>(L, ctx->gp_peers, epoch);      // "I have read everyone's slot of this epoch"
     i64 h[4];
     CK(cudaMemcpyAsync(h, tot, sizeof h, cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
     CK(cudaGetLastError());
     if (h[3] & 2) return ctx->fail(AMOD_E_CUDA, "peer assembly timed out waiting for another rank");
-    if (h[3] & 1) return ctx->fail(AMOD_E_CAPACITY, "global pool too small: need %lld entries, %lld trip requests, %lld stops", h[0], h[1], h[2]);
+    if (h[3] & 1) return ctx->fail(AMOD_E_CAPACITY, "global pool or staging slot too small (need %lld entries, %lld trip requests, %lld stops)", h[0], h[1], h[2]);
     return AMOD_OK;
 }
 

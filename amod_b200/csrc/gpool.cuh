@@ -132,3 +132,107 @@ __global__ void k_gp_signal_done(GPoolLayout L, GPoolPeers peers, unsigned long 
             st_release_sys((unsigned long long*)(peers.base[d] + L.o_flags) + GPOOL_MAX_WORLD + peers.rank, epoch);
     }
 }
+
+
+// ---- bulk variant: whole rank slices travel as coalesced peer stores, the interleave is done locally --------
+// Every rank has one staging slot per peer.  A rank pushes its local pool arrays (contiguous, 16 B stores) into
+// its slot on every rank, raises a flag, waits for all slots in its own memory, prefix-sums the per-vehicle
+// counts in global vehicle order and merges the staged slices into its own vehicle-major pool.  Peer traffic is
+// bulk; the small scattered copies are local.
+struct GSlotLayout {        // one staging slot (offsets inside the slot); identical on every rank
+    i64 cap_veh, cap_ent, cap_ptr, cap_pst;
+    i64 o_hdr, o_vehoff, o_kind, o_nfeas, o_cost, o_delay, o_toff, o_soff, o_treq, o_scode, bytes;
+};
+struct GSeg { const char* src; i64 dst_off; i64 bytes; };
+struct GPush { GSeg seg[10]; int n; };
+
+__global__ void __launch_bounds__(256)
+k_gp_push_bulk(GPush P, GPoolLayout L, GSlotLayout S, i64 o_stage, GPoolPeers peers, const DEpoch* __restrict__ epp,
+               const Control* __restrict__ ctl, unsigned long long epoch, unsigned* ticket, unsigned long long* err) {
+    const i64 n_veh = epp->n_veh, n_ent = ctl->n_ent, n_ptr = ctl->n_ptr, n_pst = ctl->n_pst;
+    const bool fits = n_veh <= S.cap_veh && n_ent <= S.cap_ent && n_ptr <= S.cap_ptr && n_pst <= S.cap_pst;
+    if (!fits && blockIdx.x == 0 && threadIdx.x == 0) atomicOr(err, 1ull);
+    const i64 tid = (i64)blockIdx.x * blockDim.x + threadIdx.x, nth = (i64)gridDim.x * blockDim.x;
+    if (!fits && tid == 0)      // tell every reader that this slot holds nothing usable
+        for (int d = 0; d < peers.world; d++) ((i64*)(peers.base[d] + o_stage + (i64)peers.rank * S.bytes + S.o_hdr))[0] = -1;
+    if (fits) {
+        // live sizes of the segments (the host passes capacities; trim to what this epoch produced)
+        const i64 live[10] = {32, 8 * (n_veh + 1), 4 * n_ent, 4 * n_ent, 8 * n_ent, 8 * n_ent, 8 * (n_ent + 1), 8 * (n_ent + 1),
+                              4 * n_ptr, 4 * n_pst};
+        for (int d = 0; d < peers.world; d++) {
+            char* slot = peers.base[d] + o_stage + (i64)peers.rank * S.bytes;
+            if (tid == 0) { i64* h = (i64*)(slot + S.o_hdr); h[0] = n_veh; h[1] = n_ent; h[2] = n_ptr; h[3] = n_pst; }
+            for (int g = 1; g < P.n; g++) {
+                const i64 bytes = live[g];
+                const int4* src = (const int4*)P.seg[g].src;
+                int4* dst = (int4*)(slot + P.seg[g].dst_off);
+                const i64 n16 = bytes >> 4;
+                for (i64 x = tid; x < n16; x += nth) dst[x] = src[x];
+                const i64 done = n16 << 4;
+                for (i64 x = done + tid * 4; x < bytes; x += nth * 4) *(int*)((char*)dst + x) = *(const int*)((const char*)src + x);
+            }
+        }
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0 && atomicAdd(ticket, 1u) == gridDim.x - 1) {
+        *ticket = 0;
+        __threadfence_system();
+        for (int d = 0; d < peers.world; d++)
+            st_release_sys((unsigned long long*)(peers.base[d] + L.o_flags) + peers.rank, epoch);
+    }
+}
+
+struct InStagedVeh {        // counts of global vehicle v read from the staged slices (vehicle v = local v / world of rank v % world)
+    const char* stage; GSlotLayout S; int world, comp, n_total;
+    __device__ __forceinline__ i64 size() const { return n_total; }
+    __device__ __forceinline__ i64 operator()(i64 v) const {
+        const char* slot = stage + (v % world) * S.bytes;
+        const i64 u = v / world;
+        if (((const i64*)(slot + S.o_hdr))[0] <= u) return 0;        // slot unusable (its rank overflowed) or short
+        const i64* vo = (const i64*)(slot + S.o_vehoff);
+        const i64 e0 = vo[u], e1 = vo[u + 1];
+        if (comp == 0) return e1 - e0;
+        const i64* off = (const i64*)(slot + (comp == 1 ? S.o_toff : S.o_soff));
+        return off[e1] - off[e0];
+    }
+};
+
+// one warp per GLOBAL vehicle: staged slice of its rank -> my vehicle-major pool (all local memory)
+__global__ void __launch_bounds__(256)
+k_gp_merge(const char* __restrict__ stage, GSlotLayout S, char* __restrict__ B, GPoolLayout L, int world,
+           const i64* __restrict__ goff_e, const i64* __restrict__ goff_t, const i64* __restrict__ goff_s,
+           const i64* __restrict__ totals, int n_veh_total, unsigned long long* err) {
+    const int lane = threadIdx.x & 31;
+    const int nwarps = gridDim.x * (blockDim.x >> 5);
+    const bool fits = totals[0] <= L.cap_ent && totals[1] <= L.cap_ptr && totals[2] <= L.cap_pst;
+    if (!fits) { if (blockIdx.x == 0 && threadIdx.x == 0) atomicOr(err, 1ull); return; }
+    for (int r = 0; r < world; r++)
+        if (((const i64*)(stage + (i64)r * S.bytes + S.o_hdr))[0] < 0) { if (blockIdx.x == 0 && threadIdx.x == 0) atomicOr(err, 1ull); return; }
+    if (blockIdx.x == 0 && threadIdx.x < 3) ((i64*)(B + L.o_hdr))[threadIdx.x] = totals[threadIdx.x];
+    int* g_veh = (int*)(B + L.o_veh); int* g_kind = (int*)(B + L.o_kind); int* g_nfeas = (int*)(B + L.o_nfeas);
+    double* g_cost = (double*)(B + L.o_cost); double* g_delay = (double*)(B + L.o_delay);
+    i64* g_toff = (i64*)(B + L.o_toff); i64* g_soff = (i64*)(B + L.o_soff);
+    int* g_treq = (int*)(B + L.o_treq); int* g_scode = (int*)(B + L.o_scode);
+    for (int v = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); v < n_veh_total; v += nwarps) {
+        const char* slot = stage + (i64)(v % world) * S.bytes;
+        const i64 u = v / world;
+        const i64* vo = (const i64*)(slot + S.o_vehoff);
+        const int* s_kind = (const int*)(slot + S.o_kind); const int* s_nfeas = (const int*)(slot + S.o_nfeas);
+        const double* s_cost = (const double*)(slot + S.o_cost); const double* s_delay = (const double*)(slot + S.o_delay);
+        const i64* s_toff = (const i64*)(slot + S.o_toff); const i64* s_soff = (const i64*)(slot + S.o_soff);
+        const int* s_treq = (const int*)(slot + S.o_treq); const int* s_scode = (const int*)(slot + S.o_scode);
+        const i64 e0 = vo[u], e1 = vo[u + 1];
+        const i64 E0 = goff_e[v], T0 = goff_t[v], S0 = goff_s[v];
+        const i64 t0 = s_toff[e0], s0 = s_soff[e0];
+        const i64 nt = s_toff[e1] - t0, ns = s_soff[e1] - s0;
+        for (i64 e = e0 + lane; e < e1; e += 32) {
+            const i64 E = E0 + (e - e0);
+            g_veh[E] = v; g_kind[E] = s_kind[e]; g_nfeas[E] = s_nfeas[e]; g_cost[E] = s_cost[e]; g_delay[E] = s_delay[e];
+            g_toff[E] = T0 + (s_toff[e] - t0); g_soff[E] = S0 + (s_soff[e] - s0);
+        }
+        for (i64 x = lane; x < nt; x += 32) g_treq[T0 + x] = s_treq[t0 + x];
+        for (i64 x = lane; x < ns; x += 32) g_scode[S0 + x] = s_scode[s0 + x];
+        if (v == n_veh_total - 1 && lane == 0) { g_toff[totals[0]] = totals[1]; g_soff[totals[0]] = totals[2]; }
+    }
+}

@@ -120,7 +120,7 @@ class PeerPool:
         dist.all_gather_object(caps, (int(cap_entries), int(cap_trip_reqs), int(cap_stops)))
         cap_entries, cap_trip_reqs, cap_stops = (max(c[i] for c in caps) for i in range(3))
         handle = C.create_string_buffer(64)
-        builder._check(builder.lib.amod_gpool_create(builder.h, cap_entries, cap_trip_reqs, cap_stops, n_veh_total, handle))
+        builder._check(builder.lib.amod_gpool_create(builder.h, cap_entries, cap_trip_reqs, cap_stops, n_veh_total, world, handle))
         handles = [None] * world
         dist.all_gather_object(handles, bytes(handle.raw))
         blob = C.create_string_buffer(b"".join(handles), 64 * world)

@@ -155,17 +155,19 @@ int amod_pool_view(amod_ctx* ctx, amod_pool* view);
  * per-vehicle entry counts (a few KB) and a barrier.  OSP modes only (SBA order is request-major). */
 #define AMOD_IPC_HANDLE_BYTES 64
 int amod_gpool_create(amod_ctx* ctx, int64_t cap_entries, int64_t cap_trip_reqs, int64_t cap_stops,
-                      int32_t max_veh_total, void* ipc_handle_out /* AMOD_IPC_HANDLE_BYTES */);
+                      int32_t max_veh_total, int32_t world, void* ipc_handle_out /* AMOD_IPC_HANDLE_BYTES */);
 int amod_gpool_open_peers(amod_ctx* ctx, int32_t world, int32_t rank, const void* handles /* world x 64 B */);
 /* (entries, trip requests, stops) of every local vehicle of the last built pool -> counts_dev[n_veh*3] */
 int amod_pool_veh_counts(amod_ctx* ctx, int32_t* counts_dev);
 /* counts_all_dev[world][veh_per_rank_max][3] = the all-gathered counts.  Writes this rank's entries
  * into all peers' global pools.  The caller must run a barrier before any rank reads its pool. */
 int amod_gpool_scatter(amod_ctx* ctx, const int32_t* counts_all_dev, int32_t veh_per_rank_max, int32_t n_veh_total);
-/* The same assembly with NO host-side collective: counts exchange, both barriers and the payload all go
- * through peer memory (flags + system-scope fences) inside four small kernels per rank.  Requires one
- * GPU per rank (kernels of different ranks wait on each other).  Returns after the local stream has
- * drained, i.e. when every rank's stores into this rank's pool have been observed. */
+/* The same assembly with NO host-side collective.  Each rank pushes its whole local pool (contiguous arrays,
+ * 16 B peer stores) into its staging slot on every rank and raises an epoch flag there (st.release.sys); it
+ * then waits for all slots in its own memory (ld.acquire.sys, bounded spin), prefix-sums the per-vehicle
+ * counts in global vehicle order and merges the staged slices into its own vehicle-major pool locally.
+ * Requires one GPU per rank (kernels of different ranks wait on each other).  On return this rank's pool is
+ * complete; a rank starts pushing the next epoch only after every peer has finished reading the previous one. */
 int amod_gpool_assemble(amod_ctx* ctx, int32_t n_veh_total);
 /* device pointers + sizes of this rank's global pool (valid after the barrier) */
 int amod_gpool_view(amod_ctx* ctx, amod_pool* view);
