@@ -1,0 +1,80 @@
+"""Drop-in check of the seam plumbing against the LIVE reference simulator (runs only where the
+reference tree exists, i.e. in the build container; skipped on the GPU box).
+
+The reference simulator is run twice on the same synthetic day: (a) unmodified, (b) with the three
+seams rebound exactly as amod_b200.install does, except that the array-level pool build / NPO match
+is served by the oracle instead of the CUDA library (there is no GPU here).  Everything else on the
+replacement path is the product's own code: marshal_epoch, pool_to_records, the scorer using device
+delays, the NPO host wrapper.  Per-request outcomes must be identical."""
+import multiprocessing as mp
+import os
+import sys
+
+import numpy as np
+import pytest
+
+from conftest import ROOT
+
+sys.path.insert(0, os.path.join(ROOT, "oracle"))
+import ref_harness as rh  # noqa: E402
+
+pytestmark = pytest.mark.skipif(not rh.reference_available(), reason="reference tree not present")
+
+
+def _run(dispatcher: str, patched: bool, q):
+    from amod_b200 import install as inst, marshal, pool as pool_mod, synth
+    import oracle
+    graph = synth.make_road_graph(400, seed=3, with_paths=True)
+    t0 = 18 * 3600 + 30 * 60
+    on, dn, tm = synth.make_request_stream(graph, 1500, t0, t0 + 40 * 60, seed=1, mean_trip_sec=420.0)
+    ref = rh.setup_reference(f"/tmp/amod_ref_dropin_{dispatcher}_{int(patched)}", graph, on, dn, tm, fleet_size=30, capacity=4,
+                             dispatcher=dispatcher, warmup_min=5, main_min=12, winddown_min=4)
+    # both runs must search exhaustively: disable the wall-clock cut-off of the unmodified seam as well
+    orig = ref.dispatch_osp.compute_candidate_veh_trip_pairs
+    ref.dispatch_osp.compute_candidate_veh_trip_pairs = lambda n, c, r, v, T, cutoff, reopt, fast: orig(n, c, r, v, T, 1e9, reopt, fast)
+    if patched:
+        tt = graph.tt
+
+        class OracleBackedBuilder(pool_mod.PoolBuilder):       # test double for the CUDA library only
+            def __init__(self):
+                self.last_stats = {}
+
+            def build_pool(self, ep, reuse=False):
+                return (oracle.sba_build if ep.mode == marshal.MODE_SBA else oracle.osp_build)(ep, tt)
+
+            def npo_match(self, idle_nid, pend_onid):
+                return oracle.npo_match(tt, np.asarray(idle_nid, dtype=np.int32), np.asarray(pend_onid, dtype=np.int32))
+
+            def close(self):
+                pass
+
+        b = OracleBackedBuilder()
+        ref.dispatch_osp.compute_candidate_veh_trip_pairs = b.compute_candidate_veh_trip_pairs
+        ref.dispatch_sba.compute_candidate_veh_req_pairs = b.compute_candidate_veh_req_pairs
+        ref.dispatch_osp.score_vt_pairs_with_num_of_orders_and_sche_cost = pool_mod.score_vt_pairs_with_num_of_orders_and_sche_cost
+        ref.dispatch_sba.score_vt_pairs_with_num_of_orders_and_sche_cost = pool_mod.score_vt_pairs_with_num_of_orders_and_sche_cost
+        ref.platform.reposition_idle_vehicles_to_nearest_pending_orders = b.reposition_idle_vehicles_to_nearest_pending_orders
+    pf = rh.make_platform(ref)
+    for e in range(0, pf.system_shutdown_time_sec, 30):
+        pf.run_cycle(e)
+    pf.create_report(show=False)
+    out = [(r.id, r.status.value, float(r.Tp), float(r.Td)) for r in pf.reqs]
+    veh = [(v.id, v.nid, float(v.t_to_nid), v.load, v.status.value, float(v.Ds)) for v in pf.vehs]
+    q.put((pf.main_sim_result, out, veh))
+
+
+@pytest.mark.parametrize("dispatcher", ["OSP", "SBA"])
+def test_simulation_outcome_identical_with_seams_replaced(dispatcher):
+    ctx = mp.get_context("spawn")          # the reference freezes its config at import: one process per run
+    res = []
+    for patched in (False, True):
+        q = ctx.Queue()
+        p = ctx.Process(target=_run, args=(dispatcher, patched, q))
+        p.start()
+        res.append(q.get(timeout=600))
+        p.join()
+    (r0, reqs0, veh0), (r1, reqs1, veh1) = res
+    assert r0 == r1
+    assert len(reqs0) > 300 and r0[0] > 10
+    assert reqs0 == reqs1
+    assert veh0 == veh1
