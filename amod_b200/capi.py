@@ -76,7 +76,7 @@ def epoch_struct(ep, ptr_of=None) -> AmodEpoch:
 EXPORTS = ("amod_create", "amod_destroy", "amod_last_error", "amod_version", "amod_set_stream",
            "amod_osp_build", "amod_sba_build", "amod_pool_fetch", "amod_pool_view", "amod_npo_match",
            "amod_gather_bench", "amod_gpool_create", "amod_gpool_open_peers", "amod_pool_veh_counts", "amod_gpool_scatter",
-           "amod_gpool_view", "amod_gpool_fetch", "amod_set_graph", "amod_gpool_assemble")
+           "amod_gpool_view", "amod_gpool_fetch", "amod_set_graph", "amod_gpool_assemble", "amod_greedy_assign")
 
 _lib = None
 
@@ -127,6 +127,8 @@ def load_library(path: str | None = None) -> C.CDLL:
     lib.amod_gpool_view.restype = C.c_int
     lib.amod_gpool_fetch.argtypes = [C.c_void_p, C.POINTER(AmodPool)]
     lib.amod_gpool_fetch.restype = C.c_int
+    lib.amod_greedy_assign.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_int32), C.c_int, C.POINTER(C.c_int32)]
+    lib.amod_greedy_assign.restype = C.c_int
     lib.amod_gpool_assemble.argtypes = [C.c_void_p, C.c_int32]
     lib.amod_gpool_assemble.restype = C.c_int
     lib.amod_set_graph.argtypes = [C.c_void_p, C.c_int]

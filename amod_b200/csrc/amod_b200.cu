@@ -10,6 +10,7 @@
 #include <vector>
 
 #include "common.cuh"
+#include "assign.cuh"
 #include "eval.cuh"
 #include "gpool.cuh"
 #include "levels.cuh"
@@ -97,6 +98,8 @@ struct amod_ctx {
     GSlotLayout gp_slot; i64 gp_o_stage = 0; int gp_world = 0;
     DevBuf gp_off, gp_tot; void* gp_peer_ptr[GPOOL_MAX_WORLD] = {nullptr};
     unsigned long long gp_epoch = 0;
+    // greedy assignment
+    DevBuf ga_pos, ga_rank, ga_order, ga_state, ga_bv, ga_br, ga_tv, ga_tr, ga_sel, ga_cnt;
     // npo
     DevBuf npo_in, npo_vm, npo_rm, npo_rb, npo_vb, npo_rdt, npo_mdt, npo_cnt;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
@@ -209,7 +212,8 @@ extern "C" void amod_destroy(amod_ctx* ctx) {
                      &ctx->lane_cnt, &ctx->chunk_pos, &ctx->hash, &ctx->row_cnt, &ctx->row_off, &ctx->tmp_j, &ctx->tmp_q,
                      &ctx->veh_cnt, &ctx->veh_off, &ctx->ent_veh, &ctx->ent_kind, &ctx->ent_nfeas, &ctx->ent_tlen, &ctx->ent_slen,
                      &ctx->ent_src, &ctx->ent_trip, &ctx->ent_cost, &ctx->ent_delay, &ctx->trip_off, &ctx->sche_off, &ctx->trip_req,
-                     &ctx->sche_code, &ctx->npo_in, &ctx->npo_vm, &ctx->npo_rm, &ctx->npo_rb, &ctx->npo_vb, &ctx->npo_rdt,
+                     &ctx->sche_code, &ctx->ga_pos, &ctx->ga_rank, &ctx->ga_order, &ctx->ga_state, &ctx->ga_bv, &ctx->ga_br, &ctx->ga_tv, &ctx->ga_tr,
+                     &ctx->ga_sel, &ctx->ga_cnt, &ctx->npo_in, &ctx->npo_vm, &ctx->npo_rm, &ctx->npo_rb, &ctx->npo_vb, &ctx->npo_rdt,
                      &ctx->npo_mdt, &ctx->npo_cnt};
     for (DevBuf* b : all) b->release();
     for (auto& l : ctx->lv) { l.trip_veh.release(); l.trip_req.release(); l.s0.release(); l.nfeas.release(); l.cost.release();
@@ -889,6 +893,73 @@ extern "C" int amod_gpool_fetch(amod_ctx* ctx, amod_pool* o) {
     if (NT) CK(cudaMemcpyAsync(o->trip_req, v.trip_req, 4 * NT, cudaMemcpyDeviceToHost, st));
     if (NS) CK(cudaMemcpyAsync(o->sche_code, v.sche_code, 4 * NS, cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
+    return AMOD_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// greedy assignment over the device-resident pool (next row)
+// ------------------------------------------------------------------------------------------------
+extern "C" int amod_greedy_assign(amod_ctx* ctx, int32_t* order_out, int32_t* sel_out, int32_t* n_sel, int loc, int32_t* n_rounds) {
+    if (!ctx || !order_out || !sel_out || !n_sel) return AMOD_E_BADARG;
+    if (!ctx->pool_valid) return ctx->fail(AMOD_E_BADARG, "no pool has been built on this context");
+    CK(cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    const i64 P = ctx->pool_entries;
+    const int V = ctx->h_epoch->n_veh, R = ctx->h_epoch->n_req;
+    *n_sel = 0;
+    if (n_rounds) *n_rounds = 0;
+    if (P == 0) return AMOD_OK;
+    if (P > 0x7ffffff0) return ctx->fail(AMOD_E_LIMIT, "pool too large for 32-bit ranks");
+    Control* ctl = ctx->ctl.as<Control>();
+    const PoolBufs pb = pool_bufs_of(ctx);
+    const size_t Pz = (size_t)P;
+    CK(ctx->ga_pos.ensure(8 * (GA_BUCKETS * Pz + 2))); CK(ctx->ga_rank.ensure(4 * Pz)); CK(ctx->ga_order.ensure(4 * Pz));
+    CK(ctx->ga_state.ensure(Pz)); CK(ctx->ga_bv.ensure(4 * (size_t)(V + 1))); CK(ctx->ga_br.ensure(4 * (size_t)(R + 1)));
+    CK(ctx->ga_tv.ensure((size_t)V + 1)); CK(ctx->ga_tr.ensure((size_t)R + 1)); CK(ctx->ga_sel.ensure(4 * Pz)); CK(ctx->ga_cnt.ensure(32));
+    CK(ctx->partial.ensure(8 * (size_t)(ctx->n_sm + 1)));
+    const int G = ctx->n_sm * 2;
+    i64* pos = ctx->ga_pos.as<i64>();
+    unsigned long long* err = (unsigned long long*)(ctx->ga_cnt.as<char>() + 8);
+    i64* tot = (i64*)(ctx->ga_cnt.as<char>() + 16);
+    int* n_left = ctx->ga_cnt.as<int>();
+    CK(cudaMemsetAsync(ctx->ga_cnt.p, 0, 32, st));
+    // 1. rank = position after the stable sort by -score (counting sort through one prefix sum)
+    scan_dev(ctx, InScoreBucket{pb.ent_tlen, ctl}, pos, FinNone{});
+    k_ga_init<<<G, 256, 0, st>>>(ctl, pb.ent_tlen, pos, ctx->ga_rank.as<int>(), ctx->ga_order.as<int>(), ctx->ga_state.as<uint8_t>(),
+                                ctx->ga_bv.as<int>(), V, ctx->ga_br.as<int>(), R, ctx->ga_tv.as<uint8_t>(), ctx->ga_tr.as<uint8_t>(), err);
+    // 2. rounds
+    int rounds = 0;
+    for (;;) {
+        for (int rep = 0; rep < 4; rep++) {       // four rounds per host check
+            if (rep == 3) CK(cudaMemsetAsync(n_left, 0, 4, st));
+            k_ga_min<<<G, 256, 0, st>>>(ctl, pb, ctx->ga_rank.as<int>(), ctx->ga_state.as<uint8_t>(), ctx->ga_bv.as<int>(), ctx->ga_br.as<int>());
+            k_ga_keep<<<G, 256, 0, st>>>(ctl, pb, ctx->ga_rank.as<int>(), ctx->ga_state.as<uint8_t>(), ctx->ga_bv.as<int>(), ctx->ga_br.as<int>(),
+                                        ctx->ga_tv.as<uint8_t>(), ctx->ga_tr.as<uint8_t>());
+            k_ga_drop<<<G, 256, 0, st>>>(ctl, pb, ctx->ga_state.as<uint8_t>(), ctx->ga_tv.as<uint8_t>(), ctx->ga_tr.as<uint8_t>(),
+                                        ctx->ga_bv.as<int>(), V, ctx->ga_br.as<int>(), R, n_left);
+            rounds++;
+        }
+        int left = 0;
+        CK(cudaMemcpyAsync(&left, n_left, 4, cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        if (left == 0) break;
+        if (rounds > 4 * (V + 8)) return ctx->fail(AMOD_E_CUDA, "greedy assignment did not converge");
+    }
+    // 3. selected positions in the sorted list, ascending
+    scan_dev(ctx, InKeptByRank{ctx->ga_order.as<int>(), ctx->ga_state.as<uint8_t>(), ctl}, pos, FinStore{tot});
+    k_ga_emit<<<G, 256, 0, st>>>(ctl, ctx->ga_order.as<int>(), ctx->ga_state.as<uint8_t>(), pos, ctx->ga_sel.as<int>());
+    i64 h[2] = {0, 0};
+    CK(cudaMemcpyAsync(&h[0], tot, 8, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(&h[1], err, 8, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    if (h[1]) return ctx->fail(AMOD_E_LIMIT, "a pair score is outside 0..%d", GA_BUCKETS - 1);
+    const cudaMemcpyKind kind = loc == AMOD_LOC_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost;
+    CK(cudaMemcpyAsync(order_out, ctx->ga_order.p, 4 * Pz, kind, st));
+    if (h[0]) CK(cudaMemcpyAsync(sel_out, ctx->ga_sel.p, 4 * (size_t)h[0], kind, st));
+    CK(cudaStreamSynchronize(st));
+    CK(cudaGetLastError());
+    *n_sel = (int32_t)h[0];
+    if (n_rounds) *n_rounds = rounds;
     return AMOD_OK;
 }
 

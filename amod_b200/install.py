@@ -15,7 +15,7 @@ from . import pool as _pool
 
 
 def install(mean_travel_time_table, dispatch_osp=None, dispatch_sba=None, platform=None, device: int = 0,
-            table_dtype=np.float32, use_device_delays: bool = True) -> _pool.PoolBuilder:
+            table_dtype=np.float32, use_device_delays: bool = True, greedy_on_gpu: bool = False) -> _pool.PoolBuilder:
     """`table_dtype=np.float32` is the north-star layout (67 MB, L2-resident) and is exact when the
     table's values are fp32-representable; pass np.float64 for bit-exact results on arbitrary tables."""
     tt = np.ascontiguousarray(mean_travel_time_table, dtype=table_dtype)
@@ -30,6 +30,12 @@ def install(mean_travel_time_table, dispatch_osp=None, dispatch_sba=None, platfo
         dispatch_sba.compute_candidate_veh_req_pairs = b.compute_candidate_veh_req_pairs
         if use_device_delays:
             dispatch_sba.score_vt_pairs_with_num_of_orders_and_sche_cost = _pool.score_vt_pairs_with_num_of_orders_and_sche_cost
+    if greedy_on_gpu:                 # next row: the README-sanctioned greedy assigner (ilp_assign.py:101-130) on the device pool
+        ga = lambda pairs, rids=None, reqs=None, vehs=None, ensure=True: b.greedy_assignment(pairs)
+        for mod in (dispatch_osp, dispatch_sba):
+            if mod is not None:
+                mod.ilp_assignment = ga           # dispatch_osp.py:62, dispatch_sba.py:23 look the name up in their own module
+                mod.greedy_assignment = b.greedy_assignment
     if platform is not None:          # B3 was imported by name into the platform module (platform.py:9-11)
         platform.reposition_idle_vehicles_to_nearest_pending_orders = b.reposition_idle_vehicles_to_nearest_pending_orders
     return b

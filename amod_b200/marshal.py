@@ -248,6 +248,7 @@ class PoolRecords(list):
     device-computed delays so the scorer pass can be skipped."""
     delays: np.ndarray | None = None
     stats: dict | None = None
+    builder_token: object | None = None
 
 
 def pool_to_records(pool: Pool, ep: Epoch, vehs, req_objs) -> PoolRecords:

@@ -128,6 +128,30 @@ class PoolBuilder:
         k = n_out.value
         return oi[:k], op[:k], od[:k]
 
+    def greedy_assign(self):
+        """greedy_assignment (ilp_assign.py:101-130) over the pool of the last build, scored len(trip) as the
+        reference's scorer leaves it.  Returns (order, selected): order[i] = pool entry at position i of the
+        stably re-sorted list, selected = positions in that list."""
+        P, _nt, _ns = self.pool_sizes()
+        order, sel = np.empty(max(P, 1), np.int32), np.empty(max(P, 1), np.int32)
+        n_sel, n_rounds = C.c_int32(0), C.c_int32(0)
+        self._check(self.lib.amod_greedy_assign(self.h, order.ctypes.data, sel.ctypes.data, C.byref(n_sel), capi.LOC_HOST,
+                                                C.byref(n_rounds)))
+        self.last_greedy_rounds = n_rounds.value
+        return order[:P], sel[:n_sel.value]
+
+    def greedy_assignment(self, veh_trip_pairs):
+        """Drop-in for ilp_assign.greedy_assignment when `veh_trip_pairs` is the record list of this builder's
+        last build, scored by the reference's scorer (pair[4] = len(trip)): sorts the list in place exactly as
+        the reference does (ilp_assign.py:109) and returns the selected indices."""
+        if getattr(veh_trip_pairs, "builder_token", None) != getattr(self, "_pool_token", object()):
+            raise RuntimeError("greedy_assignment: the pairs are not this builder's last pool")
+        if any(pair[4] != len(pair[1]) for pair in veh_trip_pairs):
+            raise RuntimeError("greedy_assignment: only the reference's default scoring (len(trip)) is supported on the GPU")
+        order, sel = self.greedy_assign()
+        veh_trip_pairs[:] = [veh_trip_pairs[i] for i in order.tolist()]
+        return sel.tolist()
+
     # ---- the reference's seams ---------------------------------------------------------------
     def compute_candidate_veh_trip_pairs(self, new_received_rids, considered_rids, reqs, vehs, system_time_sec,
                                          cutoff_time_for_a_size_k_trip_search_per_veh_sec, enable_reoptimization,
@@ -140,7 +164,12 @@ class PoolBuilder:
         mode = MODE_OSP if enable_reoptimization else MODE_OSP_NR
         ep, req_objs = marshal.marshal_epoch(reqs, vehs, considered_rids, system_time_sec, cap, mode)
         pool = self.build_pool(ep, reuse=True)
-        return marshal.pool_to_records(pool, ep, vehs, req_objs)
+        return self._tag(marshal.pool_to_records(pool, ep, vehs, req_objs))
+
+    def _tag(self, records):
+        self._pool_token = object()
+        records.builder_token = self._pool_token
+        return records
 
     def compute_candidate_veh_req_pairs(self, new_received_rids, reqs, vehs, system_time_sec,
                                         capacity: int | None = None):
@@ -148,7 +177,7 @@ class PoolBuilder:
         cap = capacity if capacity is not None else _capacity_of(vehs)
         ep, req_objs = marshal.marshal_epoch(reqs, vehs, new_received_rids, system_time_sec, cap, MODE_SBA)
         pool = self.build_pool(ep, reuse=True)
-        return marshal.pool_to_records(pool, ep, vehs, req_objs)
+        return self._tag(marshal.pool_to_records(pool, ep, vehs, req_objs))
 
     def reposition_idle_vehicles_to_nearest_pending_orders(self, reqs, vehs, system_time_sec, num_of_new_reqs,
                                                            value_func, detour_sec: int = 240):

@@ -174,6 +174,12 @@ int amod_gpool_view(amod_ctx* ctx, amod_pool* view);
 /* copy this rank's global pool into caller-owned HOST buffers (AMOD_E_CAPACITY reports the sizes needed) */
 int amod_gpool_fetch(amod_ctx* ctx, amod_pool* out_host);
 
+/* SURVEY.md §8f rank 1 (the consumer of the pool): greedy_assignment (ilp_assign.py:101-130) over the last
+ * built pool, scored as the reference's scorer leaves it (score = len(trip), scheduling.py:160-161).
+ * order_out[i] = pool entry at position i of the stably re-sorted list (n_entries values); sel_out = the
+ * selected positions IN THAT SORTED LIST, ascending (what the reference returns); buffers host or device. */
+int amod_greedy_assign(amod_ctx* ctx, int32_t* order_out, int32_t* sel_out, int32_t* n_sel, int loc, int32_t* n_rounds);
+
 /* B3: NPO matching (rebalancing_npo.py:26-59).  idle_nid[i] = node of the i-th IDLE vehicle
  * in fleet order, pend_onid[j] = origin of the j-th PENDING request in id order.  Writes
  * min(n_idle,n_pend) matches in the reference's selection order. */

@@ -549,3 +549,38 @@ int oracle_test_constraints(const amod_epoch* ep, const void* tt, int tt_dtype, 
     *cost = INFINITY;
     return test_constraints(&c, v, sche, len, new_req, idx_p, idx_d, cost);
 }
+
+/* ---- next row: greedy assignment over the pool, ilp_assign.py:101-130 --------------
+ * list.sort(key=-score) is stable; then one pass keeps a pair iff its vehicle and all its requests are
+ * still free.  order_out = pool indices in sorted order; sel_out = positions IN THE SORTED LIST (that is
+ * what the reference returns, because it sorts the caller's list in place, ilp_assign.py:109). */
+typedef struct { double neg_score; int64_t idx; } ga_key;
+static int cmp_ga(const void* a, const void* b) {
+    const ga_key* x = (const ga_key*)a; const ga_key* y = (const ga_key*)b;
+    if (x->neg_score < y->neg_score) return -1;
+    if (x->neg_score > y->neg_score) return 1;
+    return (x->idx > y->idx) - (x->idx < y->idx);
+}
+int oracle_greedy_assign(const amod_pool* p, const double* score, int n_veh, int n_req, int32_t* order_out, int32_t* sel_out) {
+    int64_t P = p->n_entries;
+    if (P == 0) return 0;
+    ga_key* k = (ga_key*)malloc(sizeof(ga_key) * (size_t)P);
+    for (int64_t e = 0; e < P; e++) { k[e].neg_score = -score[e]; k[e].idx = e; }
+    qsort(k, (size_t)P, sizeof(ga_key), cmp_ga);
+    char* vu = (char*)calloc((size_t)n_veh + 1, 1);
+    char* ru = (char*)calloc((size_t)n_req + 1, 1);
+    int m = 0;
+    for (int64_t i = 0; i < P; i++) {
+        int64_t e = k[i].idx;
+        order_out[i] = (int32_t)e;
+        if (vu[p->ent_veh[e]]) continue;                                   /* :116-117 */
+        int clash = 0;
+        for (int64_t t = p->ent_trip_off[e]; t < p->ent_trip_off[e + 1]; t++) clash |= ru[p->trip_req[t]];   /* :119-120 */
+        if (clash) continue;
+        vu[p->ent_veh[e]] = 1;
+        for (int64_t t = p->ent_trip_off[e]; t < p->ent_trip_off[e + 1]; t++) ru[p->trip_req[t]] = 1;
+        sel_out[m++] = (int32_t)i;
+    }
+    free(k); free(vu); free(ru);
+    return m;
+}

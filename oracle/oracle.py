@@ -53,6 +53,8 @@ def lib():
         _lib.oracle_test_constraints.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p,
                                                  C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_double)]
         _lib.oracle_max_threads.restype = C.c_int
+        _lib.oracle_greedy_assign.restype = C.c_int
+        _lib.oracle_greedy_assign.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
     return _lib
 
 
@@ -118,3 +120,18 @@ def test_constraints(ep, tt: np.ndarray, v: int, sche_codes, new_req: int, idx_p
     viol = lib().oracle_test_constraints(C.addressof(s), a, d, n, v, sc.ctypes.data, sc.size, new_req, idx_p, idx_d,
                                          C.byref(cost))
     return viol, cost.value
+
+
+def greedy_assign(pool, n_veh: int, n_req: int, score=None):
+    """ilp_assign.greedy_assignment restated: returns (order, selected) where order[i] is the pool entry at
+    position i of the stably re-sorted list and `selected` are positions in that list."""
+    score = np.ascontiguousarray(np.diff(pool.ent_trip_off) if score is None else score, dtype=np.float64)
+    keep = {name: np.ascontiguousarray(getattr(pool, name), dtype=dt) for name, dt, _k in POOL_FIELDS}
+    s = AmodPool()
+    s.n_entries, s.n_trip_reqs, s.n_stops = pool.n_entries, keep["trip_req"].size, keep["sche_code"].size
+    for name in keep:
+        setattr(s, name, keep[name].ctypes.data)
+    order = np.zeros(max(pool.n_entries, 1), np.int32)
+    sel = np.zeros(max(pool.n_entries, 1), np.int32)
+    m = lib().oracle_greedy_assign(C.addressof(s), score.ctypes.data, n_veh, n_req, order.ctypes.data, sel.ctypes.data)
+    return order[:pool.n_entries], sel[:m]

@@ -187,3 +187,26 @@ def test_cuda_long_schedules_take_two_warp_steps(mode=marshal.MODE_SBA):
     ok, why = marshal.pools_equal(got, ref, rtol=0.0, check_kind=True)
     assert ok, why
     assert got.stats["n_evals"] == ref.stats["n_evals"] and got.stats["n_lookups"] == ref.stats["n_lookups"]
+
+
+def test_cuda_greedy_assignment_matches_reference_and_oracle():
+    """Next row: greedy_assignment over the device-resident pool."""
+    import oracle
+    z = np.load(os.path.join(GOLDEN, "greedy.npz"))
+    for g in range(int(z["n"])):
+        tt, cases = load_golden(str(z[f"g{g}_family"]))
+        ep, _pool = cases[int(z[f"g{g}_case"])]
+        b = builder_for(tt)
+        b.build(ep)
+        order, sel = b.greedy_assign()
+        assert np.array_equal(order, z[f"g{g}_order"]), g
+        assert np.array_equal(sel, z[f"g{g}_sel"]), g
+    # larger: cfg2-like random epoch against the oracle
+    tt = _grid()
+    b = builder_for(tt)
+    ep = synth.random_epoch(tt, n_veh=600, n_pending=300, cap=4, mode=marshal.MODE_OSP, seed=11, wait_sec=300, near=True, T=5000)
+    pool = b.build_pool(ep)
+    order, sel = b.greedy_assign()
+    o2, s2 = oracle.greedy_assign(pool, ep.n_veh, ep.n_req)
+    assert np.array_equal(order, o2) and np.array_equal(sel, s2)
+    assert sel.size == ep.n_veh          # every vehicle keeps exactly one pair (its empty pair at worst)

@@ -76,3 +76,14 @@ def test_oracle_thread_count_does_not_change_result():
     ok, why = marshal.pools_equal(a, b, check_kind=True)
     assert ok, why
     assert a.stats["n_evals"] == b.stats["n_evals"] and a.stats["n_lookups"] == b.stats["n_lookups"]
+
+
+def test_oracle_greedy_assignment_matches_reference():
+    z = np.load(os.path.join(GOLDEN, "greedy.npz"))
+    assert int(z["n"]) > 0
+    for g in range(int(z["n"])):
+        _tt, cases = load_golden(str(z[f"g{g}_family"]))
+        ep, pool = cases[int(z[f"g{g}_case"])]
+        order, sel = oracle.greedy_assign(pool, ep.n_veh, ep.n_req)
+        assert np.array_equal(order, z[f"g{g}_order"])
+        assert np.array_equal(sel, z[f"g{g}_sel"])
