@@ -32,7 +32,10 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 print_json = None
-METRIC = "schedules evaluated/sec; OSP pool-build ms/epoch (2000 veh cap4)"
+try:
+    METRIC = json.load(open(os.path.join(ROOT, "BASELINE.json")))["metric"]
+except Exception:
+    METRIC = "schedules evaluated/sec; OSP pool-build ms/epoch (2000 veh cap4) at 1/2/4/8 B200"
 UNIT = "schedules/s"
 
 
