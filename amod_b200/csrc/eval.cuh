@@ -152,56 +152,53 @@ k_eval(const DEpoch* __restrict__ epp, Table<TT> tt, Level prev, Level cur, cons
         const int tot_stops = __shfl_sync(FULL, o_soff + o_sl, 31);
         const int tot_legs = __shfl_sync(FULL, o_goff + o_gl, 31);
 
-        __syncwarp();
-        for (int e0 = 0; e0 < tot_stops; e0 += 32) {              // stage the stops of all rows (uniform trip count:
-            const int e = e0 + lane;                               //  every lane takes part in the shuffles)
-            int r = 0;
-            for (int j = 1; j < nr; j++) if (e >= __shfl_sync(FULL, o_soff, j)) r = j;
-            const int m = e - __shfl_sync(FULL, o_soff, r);
+        // lane -> (row, pick-up index): found once, by shuffles over the few owner lanes
+        int r = 0;
+        for (int j = 1; j < nr; j++) if (lane >= __shfl_sync(FULL, o_woff, j)) r = j;
+        const int i_first = lane - __shfl_sync(FULL, o_woff, r);
+        const int l = __shfl_sync(FULL, o_l, r);
+        const int soff = __shfl_sync(FULL, o_soff, r), goff = __shfl_sync(FULL, o_goff, r);
+        const int q = __shfl_sync(FULL, rd.q, r), task = __shfl_sync(FULL, rd.task, r);
+        const int load = __shfl_sync(FULL, o_load, r);
+        const double clp = __shfl_sync(FULL, o_clp, r), cld = __shfl_sync(FULL, o_cld, r);
+        const double t0 = __shfl_sync(FULL, o_t0, r), PD = __shfl_sync(FULL, o_PD, r);
+        {   // every row is staged by its own lanes: stops first, then the 5l+2 travel times it can ever need
+            const int P = __shfl_sync(FULL, o_P, r), D = __shfl_sync(FULL, o_D, r), nid = __shfl_sync(FULL, o_nid, r);
             const i64 src = __shfl_sync(FULL, o_src, r);
             const int vv = __shfl_sync(FULL, rd.v, r);
-            if (e < tot_stops) {
-                const int code = prev.sch[src * prev.stride + m];
-                int node, pod; double ddl;
-                stop_info(ep, vv, code, node, ddl, pod);
-                st.node[e] = node; st.ddl[e] = ddl; st.pod[e] = (signed char)pod; st.code[e] = (code_t)code;
+            const int row_act = __shfl_sync(FULL, (int)o_act, r);   // (shuffle outside the &&: every lane must take part)
+            const bool stage = lane < items && row_act;
+            const int wl = min(l + 1, 32);                       // lanes this row has in the first step
+            __syncwarp();
+            if (stage)
+                for (int m = i_first; m < l; m += wl) {
+                    const int code = prev.sch[src * prev.stride + m];
+                    int node, pod; double ddl;
+                    stop_info(ep, vv, code, node, ddl, pod);
+                    st.node[soff + m] = node; st.ddl[soff + m] = ddl; st.pod[soff + m] = (signed char)pod; st.code[soff + m] = (code_t)code;
+                }
+            __syncwarp();
+            if (stage) {
+                const int* n = st.node + soff;
+                for (int x = i_first; x < 5 * l + 2; x += wl) {
+                    int a, b, m;
+                    if (x < l) { m = x; a = m ? n[m - 1] : nid; b = n[m]; }
+                    else if (x < 2 * l + 1) { m = x - l; a = m ? n[m - 1] : nid; b = P; }
+                    else if (x < 3 * l + 1) { m = x - (2 * l + 1); a = P; b = n[m]; }
+                    else if (x < 4 * l + 2) { m = x - (3 * l + 1); a = m ? n[m - 1] : nid; b = D; }
+                    else { m = x - (4 * l + 2); a = D; b = n[m]; }
+                    st.leg[goff + x] = tt.raw(a, b);
+                }
             }
+            __syncwarp();
         }
-        __syncwarp();
-        for (int e0 = 0; e0 < tot_legs; e0 += 32) {               // gather the 5l+2 travel times of every row
-            const int e = e0 + lane;
-            int r = 0;
-            for (int j = 1; j < nr; j++) if (e >= __shfl_sync(FULL, o_goff, j)) r = j;
-            const int x = e - __shfl_sync(FULL, o_goff, r);
-            const int l = __shfl_sync(FULL, o_l, r);
-            const int* n = st.node + __shfl_sync(FULL, o_soff, r);
-            const int P = __shfl_sync(FULL, o_P, r), D = __shfl_sync(FULL, o_D, r), nid = __shfl_sync(FULL, o_nid, r);
-            if (e < tot_legs) {
-                int a, b, m;
-                if (x < l) { m = x; a = m ? n[m - 1] : nid; b = n[m]; }
-                else if (x < 2 * l + 1) { m = x - l; a = m ? n[m - 1] : nid; b = P; }
-                else if (x < 3 * l + 1) { m = x - (2 * l + 1); a = P; b = n[m]; }
-                else if (x < 4 * l + 2) { m = x - (3 * l + 1); a = m ? n[m - 1] : nid; b = D; }
-                else { m = x - (4 * l + 2); a = D; b = n[m]; }
-                st.leg[e] = tt.raw(a, b);
-            }
-        }
-        __syncwarp();
 
         int dead_s = -1, cnt_total = 0;
         i64 row_base = MODE == 1 ? chunk_pos[c] : 0;
         for (int it0 = 0; it0 < items; it0 += 32) {               // one step unless a single schedule has > 31 stops
             const int it = it0 + lane;
             const bool valid = it < items;
-            int r = 0;
-            for (int j = 1; j < nr; j++) if (it >= __shfl_sync(FULL, o_woff, j)) r = j;
-            const int i = it - __shfl_sync(FULL, o_woff, r);
-            const int l = __shfl_sync(FULL, o_l, r);
-            const int soff = __shfl_sync(FULL, o_soff, r), goff = __shfl_sync(FULL, o_goff, r);
-            const int q = __shfl_sync(FULL, rd.q, r), task = __shfl_sync(FULL, rd.task, r);
-            const int load = __shfl_sync(FULL, o_load, r);
-            const double clp = __shfl_sync(FULL, o_clp, r), cld = __shfl_sync(FULL, o_cld, r);
-            const double t0 = __shfl_sync(FULL, o_t0, r), PD = __shfl_sync(FULL, o_PD, r);
+            const int i = it0 + i_first;                          // (a second step only exists for a single-row chunk)
             const double* ddl = st.ddl + soff;
             const TT* lg = st.leg + goff;
 
