@@ -418,7 +418,7 @@ static int enqueue_build(amod_ctx* ctx, int mode, Table<TT> tt, int max_level, c
     // ---- level-1 tasks: reachability screen ---------------------------------------------------------
     {
         const int G1 = std::max(1, 32 / (ls.lv[0].stride + 1));
-        k_screen_count<TT><<<GE, WARPS_PER_BLOCK * 32, 0, st>>>(d, tt, ctx->S0.as<int>(), ctx->flag8.as<unsigned>(), ctx->pos.as<i64>());
+        k_screen_count<TT><<<ctx->n_sm * 16, SCREEN_WARPS * 32, 0, st>>>(d, tt, ctx->S0.as<int>(), ctx->flag8.as<unsigned>(), ctx->pos.as<i64>());
         scan_dev(ctx, InMajorPacked{ctx->pos.as<i64>(), d}, ctx->major_off.as<i64>(),
                  FinTasksRows{ctl, 0, ctx->cap_tasks, ctx->cap_rows, ctx->cap_chunks, G1});
         k_screen_fill<<<GE, WARPS_PER_BLOCK * 32, 0, st>>>(d, ctl, ctx->S0.as<int>(), ctx->flag8.as<unsigned>(), ctx->major_off.as<i64>(),

@@ -127,23 +127,24 @@ k_basic(const DEpoch* __restrict__ epp, Table<TT> tt, Level lv0, int* __restrict
 #define PACK_LO(x) ((i64)((x) & 0xffffffffll))
 #define PACK_HI(x) ((i64)((x) >> 32))
 
+#define SCREEN_WARPS 4      // warps sharing one major (vehicle / request)
+
 template <typename TT>
-__global__ void __launch_bounds__(WARPS_PER_BLOCK * 32)
+__global__ void __launch_bounds__(SCREEN_WARPS * 32)
 k_screen_count(const DEpoch* __restrict__ epp, Table<TT> tt, const int* __restrict__ S0, unsigned* __restrict__ bits,
                i64* __restrict__ major_cnt) {
+    __shared__ int s_cnt[SCREEN_WARPS], s_rows[SCREEN_WARPS];
     const DEpoch& ep = *epp;
-    const int lane = threadIdx.x & 31;
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const bool sba = ep.mode == AMOD_MODE_SBA;
     const int n_major = sba ? ep.n_search : ep.n_veh, n_minor = sba ? ep.n_veh : ep.n_search;
     const int wpm = (n_minor + 31) >> 5;
-    const int nwarps = gridDim.x * WARPS_PER_BLOCK;
-    for (int mj = blockIdx.x * WARPS_PER_BLOCK + (threadIdx.x >> 5); mj < n_major; mj += nwarps) {
+    for (int mj = blockIdx.x; mj < n_major; mj += gridDim.x) {      // one block per major, its warps interleave the words
         int cnt = 0, rows = 0;
-        // the major's own parameters
         const int vq = sba ? ep.search[mj] : 0;
         const int m_node = sba ? ep.onid[vq] : ep.veh_nid[mj];
         const double m_a = sba ? ep.clp[vq] : ep.veh_t[mj];
-        for (int w = 0; w < wpm; w++) {
+        for (int w = wib; w < wpm; w += SCREEN_WARPS) {
             const int mn = w * 32 + lane;
             bool ok = false;
             int S = 0;
@@ -165,7 +166,14 @@ k_screen_count(const DEpoch* __restrict__ epp, Table<TT> tt, const int* __restri
             rows += ok ? S : 0;
         }
         rows = warp_sum(rows);
-        if (lane == 0) major_cnt[mj] = (i64)cnt | ((i64)rows << 32);
+        if (lane == 0) { s_cnt[wib] = cnt; s_rows[wib] = rows; }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            int c = 0, r = 0;
+            for (int x = 0; x < SCREEN_WARPS; x++) { c += s_cnt[x]; r += s_rows[x]; }
+            major_cnt[mj] = (i64)c | ((i64)r << 32);
+        }
+        __syncthreads();
     }
 }
 
