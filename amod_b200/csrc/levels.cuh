@@ -252,18 +252,41 @@ k_expand_rows(Control* __restrict__ ctl, int which, Level prev, const int* __res
     const int nwarps = gridDim.x * (blockDim.x >> 5);
     if (blockIdx.x == 0 && threadIdx.x == 0 && n) atomicAdd(&ctl->stats.n_tasks, (unsigned long long)n);   // compute_schedule calls
     unsigned long long items = 0;
-    for (int t = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); t < n; t += nwarps) {
-        const int v = task_veh[t], base = task_base[t], q = task_q[t];
-        const int l = len0[v] + 2 * prev.k;
-        const i64 s0 = prev.s0[base];
-        const i64 r0 = task_row0[t], r1 = r0 + task_S[t];
-        if (lane == 0) { task_nfeas[t] = 0; items += (unsigned long long)(r1 - r0) * (l + 1); }
-        for (i64 r = r0 + lane; r < r1; r += 32) {
-            RowDesc d;
-            d.v = v; d.q = q; d.s = (int)(r - r0); d.l = l; d.s0 = s0; d.task = t; d.pad = 0;
-            rows[r] = d;
+    // a lane per task (most tasks have a handful of base schedules); tasks with many rows are shared by the warp
+    for (int t0 = (blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * 32; t0 < n; t0 += nwarps * 32) {
+        const int t = t0 + lane;
+        int v = 0, q = 0, l = 0, S = 0;
+        i64 s0 = 0, r0 = 0;
+        if (t < n) {
+            v = task_veh[t]; q = task_q[t];
+            l = len0[v] + 2 * prev.k;
+            s0 = prev.s0[task_base[t]];
+            r0 = task_row0[t]; S = task_S[t];
+            task_nfeas[t] = 0;
+            items += (unsigned long long)S * (l + 1);
+        }
+        const bool big = S > 64;
+        if (!big)
+            for (int x = 0; x < S; x++) {
+                RowDesc d;
+                d.v = v; d.q = q; d.s = x; d.l = l; d.s0 = s0; d.task = t; d.pad = 0;
+                rows[r0 + x] = d;
+            }
+        unsigned todo = __ballot_sync(FULL, big);
+        while (todo) {
+            const int src = __ffs(todo) - 1;
+            todo &= todo - 1;
+            const int bv = __shfl_sync(FULL, v, src), bq = __shfl_sync(FULL, q, src), bl = __shfl_sync(FULL, l, src);
+            const int bS = __shfl_sync(FULL, S, src);
+            const i64 bs0 = __shfl_sync(FULL, s0, src), br0 = __shfl_sync(FULL, r0, src);
+            for (int x = lane; x < bS; x += 32) {
+                RowDesc d;
+                d.v = bv; d.q = bq; d.s = x; d.l = bl; d.s0 = bs0; d.task = t0 + src; d.pad = 0;
+                rows[br0 + x] = d;
+            }
         }
     }
+    items = warp_sum(items);
     if (lane == 0 && items) atomicAdd(&ctl->stats.n_items, items);
 }
 
@@ -341,6 +364,20 @@ k_classify(const DEpoch* __restrict__ epp, const Control* __restrict__ ctl, Leve
         const int nf = cur.nfeas[t];
         const double* __restrict__ cost = cur.sch_cost + s0;
         int* __restrict__ ord = cur.order + s0;
+        if (nf <= 32) {     // the common case: one warp step decides everything
+            const bool in = lane < nf;
+            const double c = in ? cost[lane] : DINF;
+            const double before = warp_excl_min(c, lane);      // (outside the &&: every lane takes part in the shuffles)
+            const bool isrec = in && c < before;
+            const unsigned br = __ballot_sync(FULL, isrec), bn = __ballot_sync(FULL, in && !isrec);
+            const unsigned lt = (1u << lane) - 1u;
+            const int nrec1 = __popc(br);
+            if (isrec) ord[nrec1 - 1 - __popc(br & lt)] = lane;
+            else if (in) ord[nrec1 + __popc(bn & lt)] = lane;
+            const double best = warp_min(c);
+            if (lane == 0) cur.cost[t] = best;
+            continue;
+        }
         // pass 1: number of records
         double running = DINF;
         int nrec = 0;

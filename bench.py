@@ -272,7 +272,6 @@ def main():
     ev1.record(stream)
     barrier()
     ms = ev0.elapsed_time(ev1)
-    clocks = sampler.stop() if sampler else None
     # dominant-kernel time: the same steps once more with plain stream launches, where every k_eval launch is
     # bracketed by CUDA events on the build stream (a captured graph cannot be timed per node)
     b.set_graph(False)
@@ -317,6 +316,7 @@ def main():
         dist.all_reduce(t_e, op=dist.ReduceOp.MAX)
         dist.all_reduce(tot_e, op=dist.ReduceOp.SUM)
     e2e_val = float(tot_e.item()) / float(t_e.item())
+    clocks = sampler.stop() if sampler else None       # sampled across both timed regions (resident and end-to-end)
 
     if rank != 0:
         if world > 1:
