@@ -210,3 +210,29 @@ def test_cuda_greedy_assignment_matches_reference_and_oracle():
     o2, s2 = oracle.greedy_assign(pool, ep.n_veh, ep.n_req)
     assert np.array_equal(order, o2) and np.array_equal(sel, s2)
     assert sel.size == ep.n_veh          # every vehicle keeps exactly one pair (its empty pair at worst)
+
+
+@pytest.mark.parametrize("tag", ["cfg2", "cfg3"])
+def test_cuda_pool_matches_oracle_on_full_size_simulator_snapshots(tag):
+    """BASELINE.json configs[1] / configs[2] at full size: 2,000 vehicles, capacity 4 / 8, epoch states recorded
+    inside the reference simulator (bench_data/make_snapshots.py).  Bit-exact pool, stats equal."""
+    import glob
+    import oracle
+    from conftest import ROOT
+    files = sorted(glob.glob(os.path.join(ROOT, "bench_data", f"{tag}_epoch*.npz")))
+    assert files, f"no {tag} snapshots"
+    tt = _grid()
+    b = builder_for(tt)
+    for f in files[:4]:
+        ep = marshal.Epoch.from_npz_dict(np.load(f), "ep_")
+        assert ep.n_veh == 2000 and ep.cap == (4 if tag == "cfg2" else 8)
+        ref = oracle.osp_build(ep, tt, n_threads=oracle.max_threads())
+        assert ref.error == 0
+        got = b.build_pool(ep)
+        ok, why = marshal.pools_equal(got, ref, rtol=0.0, check_kind=True)
+        assert ok, f"{os.path.basename(f)}: {why}"
+        for key in ("n_evals", "n_lookups", "n_tasks", "n_sches_stored"):
+            assert got.stats[key] == ref.stats[key], (f, key)
+        order, sel = b.greedy_assign()
+        o2, s2 = oracle.greedy_assign(got, ep.n_veh, ep.n_req)
+        assert np.array_equal(order, o2) and np.array_equal(sel, s2)
