@@ -81,10 +81,10 @@ struct amod_ctx {
     bool use_graph = true;
     int level_hint[3] = {0, 0, 0};   // deepest non-empty trip level seen so far (+1 is searched before looking further)
     // capacities (grown from the sizes an epoch needed; persisted across epochs)
-    i64 cap_tasks = 1 << 18, cap_chunks = 1 << 18, cap_rows = 1 << 19, cap_ent = 1 << 18, cap_ptr = 1 << 19, cap_pst = 1 << 21;
+    i64 cap_tasks = 1 << 18, cap_chunks = 1 << 18, cap_rows = 1 << 19, cap_items = 1 << 16, cap_ent = 1 << 18, cap_ptr = 1 << 19, cap_pst = 1 << 21;
     i64 cap_trips[MAX_LEVELS], cap_sch[MAX_LEVELS];
     // workspace
-    DevBuf len0, S0, s0pos, flag8, pos, major_off, partial, task_veh[2], task_base[2], task_q[2], task_nchunk[2], task_chunk0, trip_pos,
+    DevBuf len0, S0, s0pos, perm_base, perm_nitems, perm_off, perm_cnt, perm_pos, flag8, pos, major_off, partial, task_veh[2], task_base[2], task_q[2], task_nchunk[2], task_chunk0, trip_pos,
         row_desc, task_nfeas, chunk_cnt, lane_cnt, chunk_pos, hash, row_cnt, row_off, tmp_j, tmp_q;
     LevelBufs lv[MAX_LEVELS];
     // pool
@@ -206,7 +206,8 @@ extern "C" void amod_destroy(amod_ctx* ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     cudaDeviceSynchronize();
-    DevBuf* all[] = {&ctx->ep_dev, &ctx->ctl, &ctx->len0, &ctx->S0, &ctx->s0pos, &ctx->flag8, &ctx->pos, &ctx->major_off, &ctx->partial,
+    DevBuf* all[] = {&ctx->ep_dev, &ctx->ctl, &ctx->len0, &ctx->S0, &ctx->s0pos, &ctx->perm_base, &ctx->perm_nitems, &ctx->perm_off, &ctx->perm_cnt, &ctx->perm_pos, &ctx->flag8, &ctx->pos, &ctx->major_off,
+                     &ctx->partial,
                      &ctx->task_veh[0], &ctx->task_veh[1], &ctx->task_base[0], &ctx->task_base[1], &ctx->task_q[0], &ctx->task_q[1],
                      &ctx->task_nchunk[0], &ctx->task_nchunk[1], &ctx->task_chunk0, &ctx->trip_pos, &ctx->row_desc, &ctx->task_nfeas, &ctx->chunk_cnt,
                      &ctx->lane_cnt, &ctx->chunk_pos, &ctx->hash, &ctx->row_cnt, &ctx->row_off, &ctx->tmp_j, &ctx->tmp_q,
@@ -341,6 +342,8 @@ static int ensure_buffers(amod_ctx* ctx, int V, i64 n_screen, int max_level, con
     const size_t T = (size_t)ctx->cap_tasks, C = (size_t)ctx->cap_chunks;
     CK(ctx->ctl.ensure(sizeof(Control)));
     CK(ctx->len0.ensure(4 * (size_t)(V + 1))); CK(ctx->S0.ensure(4 * (size_t)(V + 1))); CK(ctx->s0pos.ensure(8 * (size_t)(V + 2)));
+    CK(ctx->perm_base.ensure(4 * (size_t)(V + 1) * AMOD_MAX_CAP)); CK(ctx->perm_nitems.ensure(4 * (size_t)(V + 1)));
+    CK(ctx->perm_off.ensure(8 * (size_t)(V + 2))); CK(ctx->perm_cnt.ensure(4 * (size_t)ctx->cap_items)); CK(ctx->perm_pos.ensure(8 * ((size_t)ctx->cap_items + 2)));
     {   // screen: survivor bitmask (one word per 32 minors of each major) + per-major packed counts / offsets
         const size_t Qs = V > 0 ? (size_t)(n_screen / V) : 0;
         const size_t words = std::max((size_t)V * ((Qs + 31) / 32), Qs * (((size_t)V + 31) / 32)) + 1;
@@ -395,7 +398,7 @@ static int ensure_buffers(amod_ctx* ctx, int V, i64 n_screen, int max_level, con
 // One attempt: enqueue the whole level-synchronous pipeline on the stream without any host
 // synchronisation; every size is produced and consumed on the device (Control block).
 template <typename TT>
-static int enqueue_build(amod_ctx* ctx, int mode, Table<TT> tt, int max_level, const LevelSet& ls, const PoolBufs& pb,
+static int enqueue_build(amod_ctx* ctx, int mode, int cap, Table<TT> tt, int max_level, const LevelSet& ls, const PoolBufs& pb,
                          size_t* n_ev_out) {
     cudaStream_t st = ctx->stream;
     const DEpoch* d = ctx->d_epoch.as<DEpoch>();      // sizes and array pointers are read on the device
@@ -408,12 +411,23 @@ static int enqueue_build(amod_ctx* ctx, int mode, Table<TT> tt, int max_level, c
     int* len0 = ctx->len0.as<int>();
 
     // ---- level 0: basic schedules -----------------------------------------------------------------
-    {
+    if (cap <= 5) {      // at most 120 orderings per vehicle: one warp per vehicle is enough
         k_basic<TT, 0><<<GE, WARPS_PER_BLOCK * 32, 0, st>>>(d, tt, ls.lv[0], len0, ctx->S0.as<int>(), nullptr, ctl, dstats);
         scan_dev(ctx, InVehInt{ctx->S0.as<int>(), d}, ctx->s0pos.as<i64>(),
                  FinCountI64{&ctl->n_sch[0], ls.lv[0].cap_sch, &ctl->need_sch[0], &ctl->overflow, OVF_SCH});
         k_basic<TT, 1><<<GE, WARPS_PER_BLOCK * 32, 0, st>>>(d, tt, ls.lv[0], len0, ctx->S0.as<int>(), ctx->s0pos.as<i64>(), ctl, dstats);
         ctx->n_launches += 2;
+    } else {             // up to cap! orderings: 32 permutation ranks per warp work item, spread over the GPU
+        k_perm_prep<<<G, 256, 0, st>>>(d, ls.lv[0], len0, ctx->perm_base.as<int>(), ctx->perm_nitems.as<int>(), dstats);
+        scan_dev(ctx, InVehInt{ctx->perm_nitems.as<int>(), d}, ctx->perm_off.as<i64>(), FinPermItems{ctl, ctx->cap_items});
+        k_perm_items<TT, 0><<<GE, WARPS_PER_BLOCK * 32, 0, st>>>(d, tt, ls.lv[0], ctl, len0, ctx->perm_base.as<int>(), ctx->perm_off.as<i64>(),
+                                                                ctx->perm_cnt.as<int>(), nullptr, dstats);
+        scan_dev(ctx, InArray<int>{ctx->perm_cnt.as<int>(), &ctl->n_perm_items, 0}, ctx->perm_pos.as<i64>(),
+                 FinBasicRows{ctl, d, ls.lv[0].cap_sch});
+        k_perm_items<TT, 1><<<GE, WARPS_PER_BLOCK * 32, 0, st>>>(d, tt, ls.lv[0], ctl, len0, ctx->perm_base.as<int>(), ctx->perm_off.as<i64>(),
+                                                                ctx->perm_cnt.as<int>(), ctx->perm_pos.as<i64>(), dstats);
+        k_perm_rows<<<G, 256, 0, st>>>(d, ls.lv[0], ctl, len0, ctx->S0.as<int>(), ctx->perm_off.as<i64>(), ctx->perm_pos.as<i64>());
+        ctx->n_launches += 4;
     }
     // ---- level-1 tasks: reachability screen ---------------------------------------------------------
     {
@@ -542,7 +556,7 @@ static int build_impl(amod_ctx* ctx, const amod_epoch* ep, int loc, amod_stats* 
                 cudaGraph_t graph = nullptr;
                 CK(cudaStreamBeginCapture(st, cudaStreamCaptureModeRelaxed));
                 ctx->n_launches = 0;
-                int rc = enqueue_build(ctx, mode, tt, run_levels, ls, pb, &n_ev);
+                int rc = enqueue_build(ctx, mode, d.cap, tt, run_levels, ls, pb, &n_ev);
                 cudaError_t ce = cudaStreamEndCapture(st, &graph);
                 if (rc != AMOD_OK) { if (graph) cudaGraphDestroy(graph); return rc; }
                 CK(ce);
@@ -557,7 +571,7 @@ static int build_impl(amod_ctx* ctx, const amod_epoch* ep, int loc, amod_stats* 
             CK(cudaGraphLaunch(gs.exec, st));
         } else {
             ctx->n_launches = 0;
-            CKR(enqueue_build(ctx, mode, tt, run_levels, ls, pb, &n_ev));
+            CKR(enqueue_build(ctx, mode, d.cap, tt, run_levels, ls, pb, &n_ev));
         }
         CK(cudaEventRecord(ctx->ev1, st));
         CK(cudaMemcpyAsync(h, ctx->ctl.p, sizeof(Control), cudaMemcpyDeviceToHost, st));
@@ -569,7 +583,7 @@ static int build_impl(amod_ctx* ctx, const amod_epoch* ep, int loc, amod_stats* 
         }
         // regrow exactly what overflowed (with headroom) and rerun the epoch
         auto grow = [](i64& cap, i64 need) { if (need > cap) cap = need + need / 2 + 1024; };
-        grow(ctx->cap_tasks, h->need_tasks); grow(ctx->cap_chunks, h->need_chunks); grow(ctx->cap_rows, h->need_rows);
+        grow(ctx->cap_tasks, h->need_tasks); grow(ctx->cap_chunks, h->need_chunks); grow(ctx->cap_rows, h->need_rows); grow(ctx->cap_items, h->need_perm_items);
         for (int k = 0; k <= max_level; k++) { grow(ctx->cap_trips[k], h->need_trips[k]); grow(ctx->cap_sch[k], h->need_sch[k]); }
         grow(ctx->cap_ent, h->need_ent); grow(ctx->cap_ptr, h->need_ptr); grow(ctx->cap_pst, h->need_pst);
         if (ctx->cap_tasks > 0x7ffffff0 || ctx->cap_chunks > 0x7ffffff0) return ctx->fail(AMOD_E_LIMIT, "more than 2^31 candidates in one level");

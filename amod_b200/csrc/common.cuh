@@ -71,16 +71,18 @@ struct Stats {            // device counters
 #define OVF_SCH 8ull
 #define OVF_POOL 16ull
 #define OVF_ROWS 32ull
+#define OVF_ITEMS 64ull
 struct Control {
     int n_tasks[2];
     int n_chunks;
     int n_rows;
-    int pad0;
+    int n_perm_items;     // warp work units of the basic-schedule permutation search (capacity > 5)
     int n_trips[MAX_LEVELS];
     i64 n_sch[MAX_LEVELS];
     i64 n_ent, n_ptr, n_pst;
     unsigned long long overflow;
     i64 need_rows;
+    i64 need_perm_items;
     i64 need_tasks, need_chunks, need_trips[MAX_LEVELS], need_sch[MAX_LEVELS], need_ent, need_ptr, need_pst;
     int max_level_nonempty;
     int pad;

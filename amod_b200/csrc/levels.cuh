@@ -115,6 +115,131 @@ k_basic(const DEpoch* __restrict__ epp, Table<TT> tt, Level lv0, int* __restrict
 }
 
 // ---------------------------------------------------------------------------------------------
+// Level 0 for large capacities: the permutation search spread over the whole GPU.  A loaded vehicle has up to
+// cap! orderings of its drop-offs (40,320 at capacity 8, dispatch_osp.py:315); one warp per vehicle would
+// serialise them.  Work item = 32 consecutive permutation ranks of one vehicle; count -> prefix sum -> fill
+// keeps the itertools order.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ int factorial(int L) { int f = 1; for (int a = 2; a <= L; a++) f *= a; return f; }
+
+// test_constraints_get_cost(veh_params, perm, 0, 0, 0, T) (dispatch_osp.py:318): flag only; counts the lookups done
+template <typename TT>
+__device__ __forceinline__ bool perm_feasible(const DEpoch& ep, const Table<TT>& tt, int v, const int* base, int L, const int* pos,
+                                              unsigned long long& lookups) {
+    int n = ep.veh_load[v];
+    for (int m = 0; m < L; m++) {
+        int node, pod; double ddl;
+        stop_info(ep, v, base[pos[m]], node, ddl, pod);
+        n += pod;
+        if (n > ep.cap) return false;
+    }
+    double acc = ep.veh_t[v];
+    int nid = ep.veh_nid[v];
+    for (int m = 0; m < L; m++) {
+        int node, pod; double ddl;
+        stop_info(ep, v, base[pos[m]], node, ddl, pod);
+        acc += tt(nid, node);
+        lookups++;
+        if (ep.T + acc > ddl) return false;
+        nid = node;
+    }
+    return true;
+}
+
+__global__ void k_perm_prep(const DEpoch* __restrict__ epp, Level lv0, int* __restrict__ len0, int* __restrict__ perm_base,
+                            int* __restrict__ n_items, Stats* stats) {
+    const DEpoch& ep = *epp;
+    for (int v = blockIdx.x * blockDim.x + threadIdx.x; v < ep.n_veh; v += gridDim.x * blockDim.x) {
+        const int s0 = ep.veh_sche_off[v], s1 = ep.veh_sche_off[v + 1];
+        const bool perms = (ep.mode == AMOD_MODE_OSP) && ep.veh_status[v] == 2;
+        int L = 0;
+        for (int k = s0; k < s1; k++)
+            if (!perms || ep.sche_onboard[k]) { if (perms && L < AMOD_MAX_CAP) perm_base[v * AMOD_MAX_CAP + L] = ep.sche_code[k]; L++; }
+        bool bad = L > lv0.stride || s1 - s0 > AMOD_MAX_STOPS || (perms && L > AMOD_MAX_CAP);
+        if (bad) { atomicOr(&stats->flags, 1ull); L = 0; }
+        len0[v] = L;
+        n_items[v] = (perms && L >= 2) ? (factorial(L) - 1 + 31) / 32 : 0;
+    }
+}
+
+struct FinPermItems {
+    Control* ctl; i64 cap;
+    __device__ __forceinline__ void operator()(i64 tot) const {
+        if (tot > ctl->need_perm_items) ctl->need_perm_items = tot;
+        if (tot > cap) { atomicOr(&ctl->overflow, OVF_ITEMS); tot = 0; }
+        ctl->n_perm_items = (int)tot;
+    }
+};
+struct FinBasicRows {       // level-0 rows = one identity row per vehicle + the feasible permutations
+    Control* ctl; const DEpoch* ep; i64 cap;
+    __device__ __forceinline__ void operator()(i64 tot) const {
+        tot += ep->n_veh;
+        if (tot > ctl->need_sch[0]) ctl->need_sch[0] = tot;
+        if (tot > cap) { atomicOr(&ctl->overflow, OVF_SCH); tot = 0; }
+        ctl->n_sch[0] = tot;
+    }
+};
+
+template <typename TT, int MODE>
+__global__ void __launch_bounds__(WARPS_PER_BLOCK * 32)
+k_perm_items(const DEpoch* __restrict__ epp, Table<TT> tt, Level lv0, const Control* __restrict__ ctl, const int* __restrict__ len0,
+             const int* __restrict__ perm_base, const i64* __restrict__ item_off, int* __restrict__ item_cnt,
+             const i64* __restrict__ item_pos, Stats* stats) {
+    const DEpoch& ep = *epp;
+    const int lane = threadIdx.x & 31;
+    const int n = ctl->overflow ? 0 : ctl->n_perm_items;
+    const int nwarps = gridDim.x * WARPS_PER_BLOCK;
+    unsigned long long evals = 0, lookups = 0;
+    for (int it = blockIdx.x * WARPS_PER_BLOCK + (threadIdx.x >> 5); it < n; it += nwarps) {
+        int lo = 0, hi = ep.n_veh;                      // vehicle of the item: last v with item_off[v] <= it
+        while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (item_off[mid] <= it) lo = mid; else hi = mid; }
+        const int v = lo, L = len0[v];
+        const int* base = perm_base + v * AMOD_MAX_CAP;
+        const int p = 1 + (int)(it - item_off[v]) * 32 + lane;
+        bool ok = false;
+        int pos[AMOD_MAX_CAP];
+        if (p < factorial(L)) {
+            unrank_perm(p, L, pos);
+            evals++;
+            ok = perm_feasible(ep, tt, v, base, L, pos, lookups);
+        }
+        const unsigned bal = __ballot_sync(FULL, ok);
+        if (MODE == 0) { if (lane == 0) item_cnt[it] = __popc(bal); }
+        else if (ok) {
+            const i64 first = v + item_pos[item_off[v]];               // the vehicle's identity row
+            const i64 row = v + 1 + item_pos[it] + __popc(bal & ((1u << lane) - 1u));
+            code_t* dst = lv0.sch + row * lv0.stride;
+            for (int m = 0; m < L; m++) dst[m] = (code_t)base[pos[m]];
+            lv0.order[row] = (int)(row - first);
+        }
+    }
+    if (MODE == 0) {
+        evals = warp_sum(evals); lookups = warp_sum(lookups);
+        if (lane == 0 && evals) { atomicAdd(&stats->n_evals, evals); atomicAdd(&stats->n_lookups, lookups); }
+    }
+}
+
+// identity rows and the level-0 trip records
+__global__ void k_perm_rows(const DEpoch* __restrict__ epp, Level lv0, const Control* __restrict__ ctl, const int* __restrict__ len0,
+                            int* __restrict__ S0, const i64* __restrict__ item_off, const i64* __restrict__ item_pos) {
+    const DEpoch& ep = *epp;
+    if (ctl->overflow) return;
+    for (int v = blockIdx.x * blockDim.x + threadIdx.x; v < ep.n_veh; v += gridDim.x * blockDim.x) {
+        const i64 row0 = v + item_pos[item_off[v]];
+        const int nf = 1 + (int)(item_pos[item_off[v + 1]] - item_pos[item_off[v]]);
+        const bool perms = (ep.mode == AMOD_MODE_OSP) && ep.veh_status[v] == 2;
+        code_t* out = lv0.sch + row0 * lv0.stride;
+        int L = 0;
+        for (int k = ep.veh_sche_off[v]; k < ep.veh_sche_off[v + 1] && L < len0[v]; k++)
+            if (!perms || ep.sche_onboard[k]) out[L++] = (code_t)ep.sche_code[k];
+        lv0.order[row0] = 0;
+        lv0.trip_veh[v] = v; lv0.nfeas[v] = nf; lv0.s0[v] = row0; lv0.veh_start[v] = v;
+        S0[v] = nf;
+        if (v == 0) lv0.veh_start[ep.n_veh] = ep.n_veh;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
 // Screen: tt[veh.nid][req.onid] + veh.t_to_nid + T > req.Clp -> skip (dispatch_osp.py:160,
 // dispatch_sba.py:59; note the association differs from the in-schedule check).
 // Task order is the reference's loop order: vehicle-major for OSP, request-major for SBA.  One warp per
