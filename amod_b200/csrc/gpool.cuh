@@ -236,3 +236,40 @@ k_gp_merge(const char* __restrict__ stage, GSlotLayout S, char* __restrict__ B, 
         if (v == n_veh_total - 1 && lane == 0) { g_toff[totals[0]] = totals[1]; g_soff[totals[0]] = totals[2]; }
     }
 }
+
+
+// all three prefix sums (entries, trip requests, stops) over the global vehicle order in ONE single-block launch
+// (a fleet has at most a few 10^4 vehicles): thread = contiguous range of vehicles
+__global__ void __launch_bounds__(1024)
+k_gp_offsets(const char* __restrict__ stage, GSlotLayout S, int world, int n_total, i64* __restrict__ goff_e, i64* __restrict__ goff_t,
+             i64* __restrict__ goff_s, i64* __restrict__ totals) {
+    __shared__ i64 sm[3][32];
+    const int per = (n_total + 1023) / 1024;
+    const int v0 = min(n_total, (int)threadIdx.x * per), v1 = min(n_total, v0 + per);
+    i64 a[3] = {0, 0, 0};
+    for (int v = v0; v < v1; v++)
+        for (int c = 0; c < 3; c++) a[c] += InStagedVeh{stage, S, world, c, n_total}(v);
+    // block exclusive scan of the three running sums
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    i64 ex[3];
+    for (int c = 0; c < 3; c++) {
+        i64 y = a[c];
+        for (int o = 1; o < 32; o <<= 1) { i64 t = __shfl_up_sync(FULL, y, o); if (lane >= o) y += t; }
+        if (lane == 31) sm[c][w] = y;
+        ex[c] = y - a[c];
+    }
+    __syncthreads();
+    if (w == 0)
+        for (int c = 0; c < 3; c++) {
+            i64 z = sm[c][lane], y = z;
+            for (int o = 1; o < 32; o <<= 1) { i64 t = __shfl_up_sync(FULL, y, o); if (lane >= o) y += t; }
+            sm[c][lane] = y - z;
+            if (lane == 31) totals[c] = y;
+        }
+    __syncthreads();
+    i64 run[3] = {ex[0] + sm[0][w], ex[1] + sm[1][w], ex[2] + sm[2][w]};
+    for (int v = v0; v < v1; v++) {
+        goff_e[v] = run[0]; goff_t[v] = run[1]; goff_s[v] = run[2];
+        for (int c = 0; c < 3; c++) run[c] += InStagedVeh{stage, S, world, c, n_total}(v);
+    }
+}
