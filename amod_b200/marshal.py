@@ -253,32 +253,109 @@ class PoolRecords(list):
 
 def pool_to_records(pool: Pool, ep: Epoch, vehs, req_objs) -> PoolRecords:
     """Pool arrays -> the reference's record list with live Veh/Req references and a
-    fresh mutable list of 4-tuples per schedule (vehicle.py:234-245 pops from it)."""
-    pick = [(r.id, 1, r.onid, r.Clp) for r in req_objs]
-    drop = [(r.id, -1, r.dnid, r.Cld) for r in req_objs]
-    reb = {}
+    fresh mutable list of 4-tuples per schedule (vehicle.py:234-245 pops from it).
+    Vectorised: one object-array gather turns all stop codes into tuples, then plain slicing."""
+    n_req = len(req_objs)
+    n = pool.n_entries
     out = PoolRecords()
-    ent_veh = pool.ent_veh.tolist()
-    toff = pool.ent_trip_off.tolist()
-    soff = pool.ent_sche_off.tolist()
-    treq = pool.trip_req.tolist()
-    scode = pool.sche_code.tolist()
-    cost = pool.ent_cost.copy()  # keep numpy float64 scalars like the reference (np.float64 costs)
-    for e in range(len(ent_veh)):
-        vi = ent_veh[e]
-        veh = vehs[vi]
-        sche = []
-        for c in scode[soff[e]:soff[e + 1]]:
-            if c < 0:
-                if vi not in reb:
-                    reb[vi] = next(s for s in veh.sche if s[0] == -1)
-                sche.append(reb[vi])
-            else:
-                sche.append(drop[c >> 1] if c & 1 else pick[c >> 1])
-        out.append([veh, [req_objs[i] for i in treq[toff[e]:toff[e + 1]]], sche, cost[e], 0.0])
-    out.delays = pool.ent_delay.copy()      # the pool arrays may be views of reused host buffers
+    if n:
+        # stop tuples: [pick-up of request i | drop-off of request i | rebalancing stop of vehicle v]
+        lut = np.empty(2 * n_req + len(vehs), dtype=object)
+        for i, r in enumerate(req_objs):
+            lut[2 * i] = (r.id, 1, r.onid, r.Clp)
+            lut[2 * i + 1] = (r.id, -1, r.dnid, r.Cld)
+        soff = pool.ent_sche_off.astype(np.int64)
+        scode = pool.sche_code.astype(np.int64)
+        reb = np.flatnonzero(scode < 0)
+        if reb.size:
+            stop_ent = np.searchsorted(soff, reb, side="right") - 1        # entry of each rebalancing stop
+            veh_of = pool.ent_veh[stop_ent]
+            for v in np.unique(veh_of).tolist():
+                lut[2 * n_req + v] = next(s for s in vehs[v].sche if s[0] == -1)
+            scode = scode.copy()
+            scode[reb] = 2 * n_req + veh_of
+        stops = lut[scode].tolist()
+        req_lut = np.empty(max(n_req, 1), dtype=object)
+        for i, r in enumerate(req_objs):
+            req_lut[i] = r
+        trips = req_lut[pool.trip_req].tolist() if pool.trip_req.size else []
+        veh_lut = np.empty(len(vehs), dtype=object)
+        for i, v in enumerate(vehs):
+            veh_lut[i] = v
+        ent_vehs = veh_lut[pool.ent_veh].tolist()
+        so = soff.tolist()
+        to = pool.ent_trip_off.tolist()
+        cost = pool.ent_cost.copy()      # numpy float64 scalars like the reference; the arrays may be views of reused buffers
+        out.extend([ent_vehs[e], trips[to[e]:to[e + 1]], stops[so[e]:so[e + 1]], cost[e], 0.0] for e in range(n))
+    out.delays = pool.ent_delay.copy()
     out.stats = pool.stats
     return out
+
+
+class LazyPoolRecords:
+    """Sequence view of the pool that materialises a record only when it is indexed.  For the pipeline
+    scorer(GPU delays) -> greedy assignment on the GPU -> upd_schedule_for_vehicles_in_selected_vt_pairs
+    (scheduling.py:110-119) only the <= n_veh selected pairs are ever touched, so the 10^4-10^6 other
+    records are never built.  Any other consumer (iteration, sort) still works: it materialises everything."""
+
+    def __init__(self, pool: Pool, ep: Epoch, vehs, req_objs):
+        self._pool = Pool(stats=pool.stats, **{f: np.array(getattr(pool, f)) for f in Pool.FIELDS})   # own copy
+        self._vehs, self._reqs = vehs, req_objs
+        self._perm = None              # position -> pool entry after an in-place "sort"
+        self._cache = {}
+        self._full = None
+        self.delays = self._pool.ent_delay
+        self.stats = pool.stats
+        self.builder_token = None
+        self.scored = False
+
+    def __len__(self):
+        return self._pool.n_entries
+
+    def _entry(self, e: int):
+        rec = self._cache.get(e)
+        if rec is None:
+            p = self._pool
+            veh = self._vehs[int(p.ent_veh[e])]
+            sche = []
+            for c in p.sche_code[p.ent_sche_off[e]:p.ent_sche_off[e + 1]].tolist():
+                if c < 0:
+                    sche.append(next(s for s in veh.sche if s[0] == -1))
+                else:
+                    r = self._reqs[c >> 1]
+                    sche.append((r.id, -1, r.dnid, r.Cld) if c & 1 else (r.id, 1, r.onid, r.Clp))
+            trip = [self._reqs[i] for i in p.trip_req[p.ent_trip_off[e]:p.ent_trip_off[e + 1]].tolist()]
+            if self.scored:      # what the reference's scorer leaves behind (scheduling.py:145,161)
+                rec = [veh, trip, sche, p.ent_delay[e], len(trip)]
+            else:
+                rec = [veh, trip, sche, p.ent_cost[e], 0.0]
+            self._cache[e] = rec
+        return rec
+
+    def __getitem__(self, i):
+        if self._full is not None:
+            return self._full[i]
+        if isinstance(i, slice):
+            return [self[j] for j in range(*i.indices(len(self)))]
+        if i < 0:
+            i += len(self)
+        return self._entry(int(self._perm[i]) if self._perm is not None else i)
+
+    def apply_order(self, order: np.ndarray):
+        """The in-place stable sort the reference's assigner performs (ilp_assign.py:109), as a permutation."""
+        order = np.asarray(order)
+        self._perm = order if self._perm is None else self._perm[order]
+
+    def materialise(self) -> list:
+        if self._full is None:
+            self._full = [self[i] for i in range(len(self))]
+        return self._full
+
+    def __iter__(self):
+        return iter(self.materialise())
+
+    def sort(self, key=None, reverse=False):
+        self.materialise().sort(key=key, reverse=reverse)
 
 
 def pools_equal(a: Pool, b: Pool, rtol: float = 0.0, check_delay: bool = True, check_nfeas: bool = True,

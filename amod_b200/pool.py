@@ -41,6 +41,7 @@ class PoolBuilder:
             raise AmodError(rc, self.lib.amod_last_error(None).decode())
         self.h = h
         self.last_stats: dict = {}
+        self.lazy_records = False      # seams return LazyPoolRecords (see install(greedy_on_gpu=True))
 
     def close(self):
         if getattr(self, "h", None):
@@ -146,10 +147,17 @@ class PoolBuilder:
         the reference does (ilp_assign.py:109) and returns the selected indices."""
         if getattr(veh_trip_pairs, "builder_token", None) != getattr(self, "_pool_token", object()):
             raise RuntimeError("greedy_assignment: the pairs are not this builder's last pool")
-        if any(pair[4] != len(pair[1]) for pair in veh_trip_pairs):
+        lazy = isinstance(veh_trip_pairs, marshal.LazyPoolRecords)
+        if lazy:
+            if not veh_trip_pairs.scored:
+                raise RuntimeError("greedy_assignment: score the pairs first (score_vt_pairs_with_num_of_orders_and_sche_cost)")
+        elif any(pair[4] != len(pair[1]) for pair in veh_trip_pairs):
             raise RuntimeError("greedy_assignment: only the reference's default scoring (len(trip)) is supported on the GPU")
         order, sel = self.greedy_assign()
-        veh_trip_pairs[:] = [veh_trip_pairs[i] for i in order.tolist()]
+        if lazy:
+            veh_trip_pairs.apply_order(order)
+        else:
+            veh_trip_pairs[:] = [veh_trip_pairs[i] for i in order.tolist()]
         return sel.tolist()
 
     # ---- the reference's seams ---------------------------------------------------------------
@@ -164,7 +172,12 @@ class PoolBuilder:
         mode = MODE_OSP if enable_reoptimization else MODE_OSP_NR
         ep, req_objs = marshal.marshal_epoch(reqs, vehs, considered_rids, system_time_sec, cap, mode)
         pool = self.build_pool(ep, reuse=True)
-        return self._tag(marshal.pool_to_records(pool, ep, vehs, req_objs))
+        return self._tag(self._records(pool, ep, vehs, req_objs))
+
+    def _records(self, pool, ep, vehs, req_objs):
+        if getattr(self, "lazy_records", False):
+            return marshal.LazyPoolRecords(pool, ep, vehs, req_objs)
+        return marshal.pool_to_records(pool, ep, vehs, req_objs)
 
     def _tag(self, records):
         self._pool_token = object()
@@ -177,7 +190,7 @@ class PoolBuilder:
         cap = capacity if capacity is not None else _capacity_of(vehs)
         ep, req_objs = marshal.marshal_epoch(reqs, vehs, new_received_rids, system_time_sec, cap, MODE_SBA)
         pool = self.build_pool(ep, reuse=True)
-        return self._tag(marshal.pool_to_records(pool, ep, vehs, req_objs))
+        return self._tag(self._records(pool, ep, vehs, req_objs))
 
     def reposition_idle_vehicles_to_nearest_pending_orders(self, reqs, vehs, system_time_sec, num_of_new_reqs,
                                                            value_func, detour_sec: int = 240):
@@ -207,6 +220,9 @@ def score_vt_pairs_with_num_of_orders_and_sche_cost(veh_trip_pairs, reqs, system
     """Drop-in for scheduling.py:140-161 when the pool came from PoolBuilder: pair[3] := delay
     (computed on the GPU in the pool pass), pair[4] := len(trip).  Falls back to nothing: a
     pool without device delays is an error."""
+    if isinstance(veh_trip_pairs, marshal.LazyPoolRecords):
+        veh_trip_pairs.scored = True       # records are built with pair[3] = delay, pair[4] = len(trip)
+        return
     delays = getattr(veh_trip_pairs, "delays", None)
     if delays is None or len(delays) != len(veh_trip_pairs):
         raise RuntimeError("pool was not produced by amod_b200 (no device delays attached)")

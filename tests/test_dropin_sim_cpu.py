@@ -21,14 +21,15 @@ import ref_harness as rh  # noqa: E402
 pytestmark = pytest.mark.skipif(not rh.reference_available(), reason="reference tree not present")
 
 
-def _run(dispatcher: str, patched: bool, q):
+def _run(dispatcher: str, patched, q):
     from amod_b200 import install as inst, marshal, pool as pool_mod, synth
     import oracle
     graph = synth.make_road_graph(400, seed=3, with_paths=True)
     t0 = 18 * 3600 + 30 * 60
     on, dn, tm = synth.make_request_stream(graph, 1500, t0, t0 + 40 * 60, seed=1, mean_trip_sec=420.0)
-    ref = rh.setup_reference(f"/tmp/amod_ref_dropin_{dispatcher}_{int(patched)}", graph, on, dn, tm, fleet_size=30, capacity=4,
+    ref = rh.setup_reference(f"/tmp/amod_ref_dropin_{dispatcher}_{patched}", graph, on, dn, tm, fleet_size=30, capacity=4,
                              dispatcher=dispatcher, warmup_min=5, main_min=12, winddown_min=4)
+    patched_tag = str(patched)
     # both runs must search exhaustively: disable the wall-clock cut-off of the unmodified seam as well
     orig = ref.dispatch_osp.compute_candidate_veh_trip_pairs
     ref.dispatch_osp.compute_candidate_veh_trip_pairs = lambda n, c, r, v, T, cutoff, reopt, fast: orig(n, c, r, v, T, 1e9, reopt, fast)
@@ -48,7 +49,21 @@ def _run(dispatcher: str, patched: bool, q):
             def close(self):
                 pass
 
+            # doubles for the device calls behind greedy_assignment (patched == "lazy")
+            def build_pool(self, ep, reuse=False):          # noqa: F811  (keeps the last pool for greedy_assign)
+                self._last = ((oracle.sba_build if ep.mode == marshal.MODE_SBA else oracle.osp_build)(ep, tt), ep)
+                return self._last[0]
+
+            def greedy_assign(self):
+                pool, ep = self._last
+                return oracle.greedy_assign(pool, ep.n_veh, ep.n_req)
+
         b = OracleBackedBuilder()
+        if patched == "lazy":       # the install(greedy_on_gpu=True) wiring: lazy records + greedy on the "device"
+            b.lazy_records = True
+            ga = lambda pairs, rids=None, reqs=None, vehs=None, ensure=True: b.greedy_assignment(pairs)
+            ref.dispatch_osp.ilp_assignment = ga
+            ref.dispatch_sba.ilp_assignment = ga
         ref.dispatch_osp.compute_candidate_veh_trip_pairs = b.compute_candidate_veh_trip_pairs
         ref.dispatch_sba.compute_candidate_veh_req_pairs = b.compute_candidate_veh_req_pairs
         ref.dispatch_osp.score_vt_pairs_with_num_of_orders_and_sche_cost = pool_mod.score_vt_pairs_with_num_of_orders_and_sche_cost
@@ -67,14 +82,15 @@ def _run(dispatcher: str, patched: bool, q):
 def test_simulation_outcome_identical_with_seams_replaced(dispatcher):
     ctx = mp.get_context("spawn")          # the reference freezes its config at import: one process per run
     res = []
-    for patched in (False, True):
+    for patched in (False, True, "lazy"):
         q = ctx.Queue()
         p = ctx.Process(target=_run, args=(dispatcher, patched, q))
         p.start()
         res.append(q.get(timeout=600))
         p.join()
-    (r0, reqs0, veh0), (r1, reqs1, veh1) = res
-    assert r0 == r1
+    (r0, reqs0, veh0) = res[0]
     assert len(reqs0) > 300 and r0[0] > 10
-    assert reqs0 == reqs1
-    assert veh0 == veh1
+    for (r1, reqs1, veh1) in res[1:]:
+        assert r0 == r1
+        assert reqs0 == reqs1
+        assert veh0 == veh1

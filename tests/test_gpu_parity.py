@@ -236,3 +236,34 @@ def test_cuda_pool_matches_oracle_on_full_size_simulator_snapshots(tag):
         order, sel = b.greedy_assign()
         o2, s2 = oracle.greedy_assign(got, ep.n_veh, ep.n_req)
         assert np.array_equal(order, o2) and np.array_equal(sel, s2)
+
+
+def test_lazy_records_with_gpu_greedy_select_the_same_pairs():
+    """install(greedy_on_gpu=True) wiring: lazy records, device delays as scores' companion, greedy on the GPU."""
+    from test_marshal_cpu import _objects
+    from amod_b200 import pool as pool_mod
+    import oracle
+    tt, cases = load_golden("sim_osp_cap4")
+    b = builder_for(tt)
+    ep, gold = cases[2]
+    reqs, objs, vehs = _objects(ep)
+    rids = [int(ep.req_id[i]) for i in ep.search]
+    # eager reference-style path
+    b.lazy_records = False
+    eager = b.compute_candidate_veh_trip_pairs(rids, rids, reqs, vehs, ep.T, 0.1, True, False)
+    pool_mod.score_vt_pairs_with_num_of_orders_and_sche_cost(eager, reqs, ep.T)
+    sel_e = b.greedy_assignment(eager)
+    picked_e = [(eager[i][0].id, [r.id for r in eager[i][1]], eager[i][2], eager[i][3], eager[i][4]) for i in sel_e]
+    # lazy path
+    b.lazy_records = True
+    try:
+        lazy = b.compute_candidate_veh_trip_pairs(rids, rids, reqs, vehs, ep.T, 0.1, True, False)
+        pool_mod.score_vt_pairs_with_num_of_orders_and_sche_cost(lazy, reqs, ep.T)
+        sel_l = b.greedy_assignment(lazy)
+        picked_l = [(lazy[i][0].id, [r.id for r in lazy[i][1]], lazy[i][2], lazy[i][3], lazy[i][4]) for i in sel_l]
+        assert len(lazy._cache) <= ep.n_veh           # only the selected pairs were ever built
+    finally:
+        b.lazy_records = False
+    assert sel_e == sel_l and picked_e == picked_l
+    order, sel = oracle.greedy_assign(gold, ep.n_veh, ep.n_req)
+    assert sel.tolist() == sel_e
