@@ -96,61 +96,62 @@ class Epoch:
 def marshal_epoch(reqs, vehs, search_rids, T: int, cap: int, mode: int, check: bool = True):
     """Veh/Req objects -> Epoch.  `search_rids` is considered_rids (OSP, dispatch_osp.py:33-39)
     or new_received_rids (SBA, dispatch_sba.py:56).  Returns (epoch, req_objs) where
-    req_objs[i] is the Req behind request index i."""
-    rid_set = set(int(r) for r in search_rids)
-    for veh in vehs:
-        for stop in veh.sche:
-            if stop[0] >= 0:
-                rid_set.add(int(stop[0]))
-    rids = sorted(rid_set)
-    index_of = {rid: i for i, rid in enumerate(rids)}
-    req_objs = [reqs[rid] for rid in rids]
-    nr = len(rids)
-    req_id = np.fromiter(rids, dtype=np.int32, count=nr)
+    req_objs[i] is the Req behind request index i.  One pass over the objects, the rest is numpy."""
+    nv = len(vehs)
+    lens = np.fromiter((len(v.sche) for v in vehs), dtype=np.int64, count=nv)
+    off = np.zeros(nv + 1, dtype=np.int32)
+    np.cumsum(lens, out=off[1:])
+    ns = int(off[-1])
+    flat = [s for v in vehs for s in v.sche]
+    stops = np.array(flat, dtype=np.float64).reshape(ns, 4) if ns else np.zeros((0, 4))
+    s_rid = stops[:, 0].astype(np.int64)
+    s_pod = stops[:, 1].astype(np.int64)
+    s_node = stops[:, 2].astype(np.int64)
+    s_ddl = stops[:, 3]
+    s_veh = np.repeat(np.arange(nv, dtype=np.int64), lens)
+    is_reb = s_rid < 0
+    search_arr = np.fromiter((int(r) for r in search_rids), dtype=np.int64, count=len(search_rids))
+    rids = np.unique(np.concatenate([search_arr, s_rid[~is_reb]]))
+    req_objs = [reqs[r] for r in rids.tolist()]
+    nr = len(req_objs)
     req_onid = np.fromiter((r.onid for r in req_objs), dtype=np.int32, count=nr)
     req_dnid = np.fromiter((r.dnid for r in req_objs), dtype=np.int32, count=nr)
     req_clp = np.fromiter((r.Clp for r in req_objs), dtype=np.float64, count=nr)
     req_cld = np.fromiter((r.Cld for r in req_objs), dtype=np.float64, count=nr)
     req_tr = np.fromiter((r.Tr for r in req_objs), dtype=np.float64, count=nr)
     req_ts = np.fromiter((r.Ts for r in req_objs), dtype=np.float64, count=nr)
-    search = np.fromiter((index_of[int(r)] for r in search_rids), dtype=np.int32, count=len(search_rids))
+    search = np.searchsorted(rids, search_arr).astype(np.int32)
 
-    nv = len(vehs)
+    idx = np.searchsorted(rids, np.where(is_reb, rids[0] if nr else 0, s_rid)) if ns else np.zeros(0, dtype=np.int64)
+    code = np.where(is_reb, -1, 2 * idx + (s_pod == -1)).astype(np.int32)
+    # onboard flag: (vehicle, rid) pairs of veh.onboard_rids
+    big = int(rids[-1]) + 2 if nr else 2
+    onb = np.fromiter((vi * big + rid for vi, v in enumerate(vehs) for rid in v.onboard_rids), dtype=np.int64)
+    onboard = (np.isin(s_veh * big + s_rid, onb) & ~is_reb).astype(np.uint8) if ns else np.zeros(0, dtype=np.uint8)
+    reb_node = np.zeros(nv, dtype=np.int32)
+    reb_ddl = np.zeros(nv, dtype=np.float64)
+    reb_node[s_veh[is_reb]] = s_node[is_reb]
+    reb_ddl[s_veh[is_reb]] = s_ddl[is_reb]
+    if check and ns:
+        bad_reb = is_reb & ~((s_rid == -1) & (s_pod == 0))
+        if bad_reb.any():
+            k = int(np.flatnonzero(bad_reb)[0])
+            raise ValueError(f"vehicle {int(s_veh[k])}: unexpected stop {flat[k]}")
+        req = ~is_reb
+        pick = s_pod == 1
+        exp_node = np.where(pick, req_onid[idx], req_dnid[idx])
+        exp_ddl = np.where(pick, req_clp[idx], req_cld[idx])
+        bad = req & (~np.isin(s_pod, (1, -1)) | (s_node != exp_node) | (s_ddl != exp_ddl))
+        if bad.any():
+            k = int(np.flatnonzero(bad)[0])
+            raise ValueError(f"vehicle {int(s_veh[k])}: stop {flat[k]} does not match its request")
     veh_nid = np.fromiter((v.nid for v in vehs), dtype=np.int32, count=nv)
     veh_t = np.fromiter((v.t_to_nid for v in vehs), dtype=np.float64, count=nv)
     veh_load = np.fromiter((v.load for v in vehs), dtype=np.int32, count=nv)
     veh_status = np.fromiter((_status_value(v.status) for v in vehs), dtype=np.int32, count=nv)
-    off = np.zeros(nv + 1, dtype=np.int32)
-    np.cumsum(np.fromiter((len(v.sche) for v in vehs), dtype=np.int32, count=nv), out=off[1:])
-    ns = int(off[-1])
-    code = np.empty(ns, dtype=np.int32)
-    onboard = np.zeros(ns, dtype=np.uint8)
-    reb_node = np.zeros(nv, dtype=np.int32)
-    reb_ddl = np.zeros(nv, dtype=np.float64)
-    k = 0
-    for vi, veh in enumerate(vehs):
-        ob = veh.onboard_rids
-        for (rid, pod, tnid, ddl) in veh.sche:
-            if rid < 0:
-                if check and not (rid == -1 and pod == 0):
-                    raise ValueError(f"vehicle {vi}: unexpected stop {(rid, pod, tnid, ddl)}")
-                code[k] = -1
-                reb_node[vi] = tnid
-                reb_ddl[vi] = ddl
-            else:
-                i = index_of[int(rid)]
-                code[k] = 2 * i + (1 if pod == -1 else 0)
-                if rid in ob:
-                    onboard[k] = 1
-                if check:
-                    r = req_objs[i]
-                    exp = (r.onid, r.Clp) if pod == 1 else (r.dnid, r.Cld)
-                    if pod not in (1, -1) or tnid != exp[0] or ddl != exp[1]:
-                        raise ValueError(f"vehicle {vi}: stop {(rid, pod, tnid, ddl)} does not match its request")
-            k += 1
     ep = Epoch(T=T, cap=cap, mode=mode, veh_nid=veh_nid, veh_t_to_nid=veh_t, veh_load=veh_load,
                veh_status=veh_status, veh_sche_off=off, sche_code=code, sche_onboard=onboard,
-               veh_reb_node=reb_node, veh_reb_ddl=reb_ddl, req_id=req_id, req_onid=req_onid,
+               veh_reb_node=reb_node, veh_reb_ddl=reb_ddl, req_id=rids.astype(np.int32), req_onid=req_onid,
                req_dnid=req_dnid, req_clp=req_clp, req_cld=req_cld, req_tr=req_tr, req_ts=req_ts,
                search=search)
     return ep, req_objs
