@@ -79,6 +79,7 @@ struct amod_ctx {
     GraphSlot graphs[3];
     unsigned long long buf_gen = 0;
     bool use_graph = true;
+    int heavy_min = -1;            // AMOD_HEAVY_MIN overrides the block-per-trip classification threshold (tests)
     int level_hint[3] = {0, 0, 0};   // deepest non-empty trip level seen so far (+1 is searched before looking further)
     // capacities (grown from the sizes an epoch needed; persisted across epochs)
     i64 cap_tasks = 1 << 18, cap_chunks = 1 << 18, cap_rows = 1 << 19, cap_items = 1 << 16, cap_ent = 1 << 18, cap_ptr = 1 << 19, cap_pst = 1 << 21;
@@ -196,6 +197,7 @@ extern "C" int amod_create(amod_ctx** out, int device, int n_nodes, const void* 
     if ((e = cudaMallocHost((void**)&ctx->h_epoch, sizeof(DEpoch))) != cudaSuccess) return bail("cudaMallocHost", e);
     if ((e = ctx->d_epoch.ensure(sizeof(DEpoch))) != cudaSuccess) return bail("cudaMalloc", e);
     ctx->use_graph = getenv("AMOD_NO_GRAPH") == nullptr;
+    if (const char* hm = getenv("AMOD_HEAVY_MIN")) ctx->heavy_min = atoi(hm);
     apply_l2_policy(ctx, ctx->stream);
     cudaEventCreate(&ctx->ev0); cudaEventCreate(&ctx->ev1);
     *out = ctx;
@@ -468,7 +470,9 @@ static int enqueue_build(amod_ctx* ctx, int mode, int cap, Table<TT> tt, int max
         CK(cudaEventRecord(get_event(ctx, n_ev++), st));
         unsigned hash_sz = 0;       // the level's trip lookup table is cleared by the classify kernel that precedes its build
         if (k >= 2 && k < max_level) { hash_sz = 64; while (hash_sz < 2u * (unsigned)lv.cap_trips + 2u) hash_sz <<= 1; }
-        k_classify<<<G, WARPS_PER_BLOCK * 32, 0, st>>>(d, ctl, lv, sba, ctx->hash.as<int>(), hash_sz);
+        const int heavy_min = ctx->heavy_min >= 0 ? ctx->heavy_min : (cap > 5 ? 2048 : 0);   // large capacities: trips with 10^3..10^5 schedules
+        k_classify<<<GE, WARPS_PER_BLOCK * 32, 0, st>>>(d, ctl, lv, sba, ctx->hash.as<int>(), hash_sz, heavy_min, ctx->row_cnt.as<int>());
+        if (heavy_min) { k_classify_heavy<<<ctx->n_sm * 2, HEAVY_THREADS, 0, st>>>(ctl, lv, ctx->row_cnt.as<int>()); ctx->n_launches++; }
         ctx->n_launches += 5;
         if (k == max_level) break;
         // ---- candidates of size k+1 ---------------------------------------------------------------------

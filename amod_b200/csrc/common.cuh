@@ -86,6 +86,8 @@ struct Control {
     i64 need_tasks, need_chunks, need_trips[MAX_LEVELS], need_sch[MAX_LEVELS], need_ent, need_ptr, need_pst;
     int max_level_nonempty;
     int pad;
+    int n_heavy[MAX_LEVELS];  // trips with very many feasible schedules, classified by a whole block each
+    int pad2;
     Stats stats;
 };
 

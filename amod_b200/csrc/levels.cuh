@@ -471,8 +471,8 @@ __global__ void k_compact_trips(const Control* __restrict__ ctl, int which, cons
 // (first-encountered minimum).  One warp per trip.  Also fills veh_start (trips are vehicle-major).
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32)
-k_classify(const DEpoch* __restrict__ epp, const Control* __restrict__ ctl, Level cur, int sba, int* __restrict__ hash_slots,
-           unsigned hash_size) {
+k_classify(const DEpoch* __restrict__ epp, Control* __restrict__ ctl, Level cur, int sba, int* __restrict__ hash_slots,
+           unsigned hash_size, int heavy_min, int* __restrict__ heavy_list) {
     const int n_veh = epp->n_veh;
     for (unsigned x = blockIdx.x * blockDim.x + threadIdx.x; x < hash_size; x += gridDim.x * blockDim.x) hash_slots[x] = -1;
     const int lane = threadIdx.x & 31;
@@ -489,6 +489,10 @@ k_classify(const DEpoch* __restrict__ epp, const Control* __restrict__ ctl, Leve
         const int nf = cur.nfeas[t];
         const double* __restrict__ cost = cur.sch_cost + s0;
         int* __restrict__ ord = cur.order + s0;
+        if (heavy_min > 0 && nf >= heavy_min) {      // left to k_classify_heavy (one block per such trip)
+            if (lane == 0) heavy_list[atomicAdd(&ctl->n_heavy[cur.k], 1)] = t;
+            continue;
+        }
         if (nf <= 32) {     // the common case: one warp step decides everything
             const bool in = lane < nf;
             const double c = in ? cost[lane] : DINF;
@@ -528,6 +532,58 @@ k_classify(const DEpoch* __restrict__ epp, const Control* __restrict__ ctl, Leve
             run2 = fmin(run2, warp_min(c));
         }
         if (lane == 0) cur.cost[t] = running;
+    }
+}
+
+// Trips with thousands of feasible schedules (large capacities): one block per trip, every thread owns a
+// contiguous segment of the encounter-order costs and walks it sequentially; the segments are stitched with
+// two block-wide scans (running minimum entering each segment, record / non-record counts before it).
+#define HEAVY_THREADS 512
+__global__ void __launch_bounds__(HEAVY_THREADS)
+k_classify_heavy(const Control* __restrict__ ctl, Level cur, const int* __restrict__ heavy_list) {
+    __shared__ double s_min[HEAVY_THREADS];
+    __shared__ int s_rec[HEAVY_THREADS], s_non[HEAVY_THREADS];
+    const int n = ctl->overflow ? 0 : ctl->n_heavy[cur.k];
+    const int tid = threadIdx.x;
+    for (int h = blockIdx.x; h < n; h += gridDim.x) {
+        const int t = heavy_list[h];
+        const i64 s0 = cur.s0[t];
+        const int nf = cur.nfeas[t];
+        const double* __restrict__ cost = cur.sch_cost + s0;
+        int* __restrict__ ord = cur.order + s0;
+        const int seg = (nf + HEAVY_THREADS - 1) / HEAVY_THREADS;
+        const int a = min(nf, tid * seg), b = min(nf, a + seg);
+        double m = DINF;
+        for (int x = a; x < b; x++) m = fmin(m, cost[x]);
+        s_min[tid] = m;
+        __syncthreads();
+        if (tid == 0) {      // exclusive prefix-min over the segments (512 values: one thread is enough)
+            double run = DINF;
+            for (int x = 0; x < HEAVY_THREADS; x++) { const double v = s_min[x]; s_min[x] = run; run = fmin(run, v); }
+            cur.cost[t] = run;
+        }
+        __syncthreads();
+        const double incoming = s_min[tid];
+        double run = incoming;
+        int nrec = 0;
+        for (int x = a; x < b; x++) { const double c = cost[x]; if (c < run) { run = c; nrec++; } }
+        s_rec[tid] = nrec; s_non[tid] = (b - a) - nrec;
+        __syncthreads();
+        if (tid == 0) {      // exclusive prefix sums of both counts; the total record count goes to s_rec[0] slot after use
+            int r = 0, q = 0;
+            for (int x = 0; x < HEAVY_THREADS; x++) { const int vr = s_rec[x], vq = s_non[x]; s_rec[x] = r; s_non[x] = q; r += vr; q += vq; }
+            s_min[0] = (double)r;      // total number of records
+        }
+        __syncthreads();
+        const int total_rec = (int)s_min[0];
+        int rb = s_rec[tid], nb = s_non[tid];
+        run = incoming;
+        for (int x = a; x < b; x++) {
+            const double c = cost[x];
+            if (c < run) { run = c; ord[total_rec - 1 - rb++] = x; }
+            else ord[total_rec + nb++] = x;
+        }
+        __syncthreads();
     }
 }
 

@@ -267,3 +267,16 @@ def test_lazy_records_with_gpu_greedy_select_the_same_pairs():
     assert sel_e == sel_l and picked_e == picked_l
     order, sel = oracle.greedy_assign(gold, ep.n_veh, ep.n_req)
     assert sel.tolist() == sel_e
+
+
+def test_block_per_trip_classification_path(monkeypatch):
+    """Force the heavy-trip list order classification (one block per trip) onto ordinary trips."""
+    import oracle
+    monkeypatch.setenv("AMOD_HEAVY_MIN", "40")
+    tt, cases = load_golden("rand_real_osp_cap4")
+    b = PoolBuilder(tt)          # a fresh context reads the override
+    for ep, gold in cases[:3]:
+        assert gold.ent_nfeas.max() >= 40
+        ok, why = marshal.pools_equal(b.build_pool(ep), gold, rtol=0.0, check_kind=True)
+        assert ok, why
+    b.close()
