@@ -145,12 +145,12 @@ k_eval(const DEpoch* __restrict__ epp, Table<TT> tt, Level prev, Level cur, cons
             const unsigned span = o_w >= 32 ? FULL : (((1u << o_w) - 1u) << o_woff);
             o_act = own && (hit & span) != 0u;
         }
+        // staged stops and legs of the rows before this one: one packed scan (stops < 2^12 | legs << 12)
         const int o_sl = o_act ? o_l : 0;
         const int o_gl = o_act ? 5 * o_l + 2 : 0;
-        const int o_soff = warp_excl_sum(o_sl, lane);             // first staged stop of the row
-        const int o_goff = warp_excl_sum(o_gl, lane);             // first staged leg of the row
-        const int tot_stops = __shfl_sync(FULL, o_soff + o_sl, 31);
-        const int tot_legs = __shfl_sync(FULL, o_goff + o_gl, 31);
+        const int o_pk = warp_excl_sum(o_sl | (o_gl << 12), lane);
+        const int o_soff = o_pk & 0xfff;                          // first staged stop of the row
+        const int o_goff = o_pk >> 12;                            // first staged leg of the row
 
         // lane -> (row, pick-up index): found once, by shuffles over the few owner lanes
         int r = 0;
@@ -179,15 +179,17 @@ k_eval(const DEpoch* __restrict__ epp, Table<TT> tt, Level prev, Level cur, cons
                 }
             __syncwarp();
             if (stage) {
+                // the lane at position m fetches the five legs that touch position m, branch-free and
+                // back to back (one L2 round trip): g[m], toP[m], fromP[m], toD[m], fromD[m]
                 const int* n = st.node + soff;
-                for (int x = i_first; x < 5 * l + 2; x += wl) {
-                    int a, b, m;
-                    if (x < l) { m = x; a = m ? n[m - 1] : nid; b = n[m]; }
-                    else if (x < 2 * l + 1) { m = x - l; a = m ? n[m - 1] : nid; b = P; }
-                    else if (x < 3 * l + 1) { m = x - (2 * l + 1); a = P; b = n[m]; }
-                    else if (x < 4 * l + 2) { m = x - (3 * l + 1); a = m ? n[m - 1] : nid; b = D; }
-                    else { m = x - (4 * l + 2); a = D; b = n[m]; }
-                    st.leg[goff + x] = tt.raw(a, b);
+                TT* lg = st.leg + goff;
+                for (int m = i_first; m <= l; m += wl) {
+                    const bool in = m < l;
+                    const int a = m ? n[m - 1] : nid;
+                    const int b = in ? n[m] : P;
+                    const TT g = tt.raw(a, b), toP = tt.raw(a, P), frP = tt.raw(P, b), toD = tt.raw(a, D), frD = tt.raw(D, b);
+                    lg[l + m] = toP; lg[3 * l + 1 + m] = toD;
+                    if (in) { lg[m] = g; lg[2 * l + 1 + m] = frP; lg[4 * l + 2 + m] = frD; }
                 }
             }
             __syncwarp();
@@ -208,13 +210,28 @@ k_eval(const DEpoch* __restrict__ epp, Table<TT> tt, Level prev, Level cur, cons
             double A = 0.0;
             int mine = 0;
             if (MODE == 1) mine = lane_cnt[(i64)c * 64 + it0 + lane];
+            if (items <= 32) {
+                // occupancy after every base stop by a prefix sum over the row's own lanes, shared by ballot
+                const bool at = valid && i < l;
+                int run = at ? (int)st.pod[soff + i] : 0;
+                for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(FULL, run, o); if (i >= o) run += t; }
+                run += load;
+                const unsigned bal_full = __ballot_sync(FULL, at && run >= cap);
+                const unsigned bal_over = __ballot_sync(FULL, at && run > cap);
+                const unsigned rowbits = l >= 31 ? FULL : ((2u << l) - 1u);
+                const int woff = lane - i;
+                fullmask = ((unsigned long long)((bal_full >> woff) & rowbits) << 1) | (load >= cap ? 1ull : 0ull);
+                basebad = ((bal_over >> woff) & rowbits) != 0u;
+            }
             if (MODE == 0 ? valid : (mine != 0)) {
-                int run = load;
-                if (run >= cap) fullmask |= 1ull;
-                for (int m = 0; m < l; m++) {
-                    run += st.pod[soff + m];
-                    if (run > cap) basebad = true;
-                    if (run >= cap) fullmask |= 1ull << (m + 1);
+                if (items > 32) {
+                    int run = load;
+                    if (run >= cap) fullmask |= 1ull;
+                    for (int m = 0; m < l; m++) {
+                        run += st.pod[soff + m];
+                        if (run > cap) basebad = true;
+                        if (run >= cap) fullmask |= 1ull << (m + 1);
+                    }
                 }
                 double acc = t0;
                 for (int m = 0; m < i; m++) acc += (double)lg[m];                        // trusted prefix (no checks)
