@@ -86,7 +86,7 @@ struct amod_ctx {
     i64 cap_trips[MAX_LEVELS], cap_sch[MAX_LEVELS];
     // workspace
     DevBuf len0, S0, s0pos, perm_base, perm_nitems, perm_off, perm_cnt, perm_pos, flag8, pos, major_off, partial, task_veh[2], task_base[2], task_q[2], task_nchunk[2], task_chunk0, trip_pos,
-        row_desc, task_nfeas, chunk_cnt, lane_cnt, chunk_pos, hash, row_cnt, row_off, tmp_j, tmp_q;
+        row_desc, task_nfeas, chunk_cnt, lane_cnt, chunk_pos, hash, row_cnt, row_off, tmp_j, tmp_q, heavy_list;
     LevelBufs lv[MAX_LEVELS];
     // pool
     DevBuf veh_cnt, veh_off, ent_veh, ent_kind, ent_nfeas, ent_tlen, ent_slen, ent_src, ent_trip, ent_cost, ent_delay,
@@ -105,6 +105,8 @@ struct amod_ctx {
     DevBuf npo_in, npo_vm, npo_rm, npo_rb, npo_vb, npo_rdt, npo_mdt, npo_cnt;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     std::vector<cudaEvent_t> ev_pool;
+    cudaStream_t side = nullptr;             // second branch of the epoch graph (next level's candidates)
+    std::vector<cudaEvent_t> sync_pool;      // fork / join edges between the two branches
     int n_launches = 0;
 
     int fail(int code, const char* fmt, ...) {
@@ -135,10 +137,12 @@ static void scan_dev2(amod_ctx* ctx, InA a, i64* outa, FinA fa, InB b, i64* outb
 }
 
 template <typename In, typename Fin>
-static void scan_dev(amod_ctx* ctx, In in, i64* out, Fin fin) {
+static void scan_dev(amod_ctx* ctx, In in, i64* out, Fin fin, bool on_side = false) {
     const int g = ctx->n_sm;
-    k_scan_a<In><<<g, SCAN_THREADS, 0, ctx->stream>>>(in, ctx->partial.as<i64>());
-    k_scan_b<In, Fin><<<g, SCAN_THREADS, 0, ctx->stream>>>(in, ctx->partial.as<i64>(), out, fin);
+    cudaStream_t st = on_side ? ctx->side : ctx->stream;
+    i64* partial = ctx->partial.as<i64>() + (on_side ? g + 1 : 0);     // one set of block partials per graph branch
+    k_scan_a<In><<<g, SCAN_THREADS, 0, st>>>(in, partial);
+    k_scan_b<In, Fin><<<g, SCAN_THREADS, 0, st>>>(in, partial, out, fin);
     ctx->n_launches += 2;
 }
 
@@ -186,6 +190,7 @@ extern "C" int amod_create(amod_ctx** out, int device, int n_nodes, const void* 
     };
     if ((e = cudaSetDevice(device)) != cudaSuccess) return bail("cudaSetDevice", e);
     if ((e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking)) != cudaSuccess) return bail("stream", e);
+    if ((e = cudaStreamCreateWithFlags(&ctx->side, cudaStreamNonBlocking)) != cudaSuccess) return bail("stream", e);
     ctx->own_stream = true;
     cudaDeviceGetAttribute(&ctx->n_sm, cudaDevAttrMultiProcessorCount, device);
     size_t bytes = (size_t)n_nodes * n_nodes * (tt_dtype == AMOD_TT_F64 ? 8 : 4);
@@ -212,7 +217,7 @@ extern "C" void amod_destroy(amod_ctx* ctx) {
                      &ctx->partial,
                      &ctx->task_veh[0], &ctx->task_veh[1], &ctx->task_base[0], &ctx->task_base[1], &ctx->task_q[0], &ctx->task_q[1],
                      &ctx->task_nchunk[0], &ctx->task_nchunk[1], &ctx->task_chunk0, &ctx->trip_pos, &ctx->row_desc, &ctx->task_nfeas, &ctx->chunk_cnt,
-                     &ctx->lane_cnt, &ctx->chunk_pos, &ctx->hash, &ctx->row_cnt, &ctx->row_off, &ctx->tmp_j, &ctx->tmp_q,
+                     &ctx->lane_cnt, &ctx->chunk_pos, &ctx->hash, &ctx->row_cnt, &ctx->row_off, &ctx->tmp_j, &ctx->tmp_q, &ctx->heavy_list,
                      &ctx->veh_cnt, &ctx->veh_off, &ctx->ent_veh, &ctx->ent_kind, &ctx->ent_nfeas, &ctx->ent_tlen, &ctx->ent_slen,
                      &ctx->ent_src, &ctx->ent_trip, &ctx->ent_cost, &ctx->ent_delay, &ctx->trip_off, &ctx->sche_off, &ctx->trip_req,
                      &ctx->sche_code, &ctx->ga_pos, &ctx->ga_rank, &ctx->ga_order, &ctx->ga_state, &ctx->ga_bv, &ctx->ga_br, &ctx->ga_tv, &ctx->ga_tr,
@@ -232,6 +237,8 @@ extern "C" void amod_destroy(amod_ctx* ctx) {
     if (ctx->ep_pinned) cudaFreeHost(ctx->ep_pinned);
     if (ctx->d_tt) cudaFree(ctx->d_tt);
     for (auto e : ctx->ev_pool) cudaEventDestroy(e);
+    for (auto e : ctx->sync_pool) cudaEventDestroy(e);
+    if (ctx->side) cudaStreamDestroy(ctx->side);
     if (ctx->ev0) cudaEventDestroy(ctx->ev0);
     if (ctx->ev1) cudaEventDestroy(ctx->ev1);
     if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
@@ -335,6 +342,11 @@ static int upload_epoch(amod_ctx* ctx, const amod_epoch* ep, int loc, DEpoch* d)
 // ------------------------------------------------------------------------------------------------
 // the build
 // ------------------------------------------------------------------------------------------------
+static cudaEvent_t get_sync_event(amod_ctx* ctx, size_t i) {
+    while (ctx->sync_pool.size() <= i) { cudaEvent_t e; cudaEventCreateWithFlags(&e, cudaEventDisableTiming); ctx->sync_pool.push_back(e); }
+    return ctx->sync_pool[i];
+}
+
 static cudaEvent_t get_event(amod_ctx* ctx, size_t i) {
     while (ctx->ev_pool.size() <= i) { cudaEvent_t e; cudaEventCreate(&e); ctx->ev_pool.push_back(e); }
     return ctx->ev_pool[i];
@@ -352,13 +364,13 @@ static int ensure_buffers(amod_ctx* ctx, int V, i64 n_screen, int max_level, con
         const size_t majors = std::max((size_t)V, Qs) + 2;
         CK(ctx->flag8.ensure(4 * words)); CK(ctx->pos.ensure(8 * majors)); CK(ctx->major_off.ensure(8 * majors));
     }
-    CK(ctx->partial.ensure(8 * (size_t)(ctx->n_sm + 1)));
+    CK(ctx->partial.ensure(2 * 8 * (size_t)(ctx->n_sm + 1)));
     for (int w = 0; w < 2; w++) {
         CK(ctx->task_veh[w].ensure(4 * T)); CK(ctx->task_base[w].ensure(4 * T)); CK(ctx->task_q[w].ensure(4 * T));
         CK(ctx->task_nchunk[w].ensure(4 * T));
     }
     CK(ctx->task_chunk0.ensure(8 * (T + 2))); CK(ctx->trip_pos.ensure(8 * (T + 2)));
-    CK(ctx->row_desc.ensure(sizeof(RowDesc) * (size_t)ctx->cap_rows)); CK(ctx->task_nfeas.ensure(4 * T)); CK(ctx->chunk_cnt.ensure(4 * C)); CK(ctx->lane_cnt.ensure(64 * C)); CK(ctx->chunk_pos.ensure(8 * (C + 2)));
+    CK(ctx->row_desc.ensure(2 * sizeof(RowDesc) * (size_t)ctx->cap_rows)); CK(ctx->task_nfeas.ensure(4 * T)); CK(ctx->chunk_cnt.ensure(4 * C)); CK(ctx->lane_cnt.ensure(64 * C)); CK(ctx->chunk_pos.ensure(8 * (C + 2)));
     CK(ctx->tmp_j.ensure(4 * T)); CK(ctx->tmp_q.ensure(4 * T));
     size_t max_trips = 1;
     memset(ls, 0, sizeof *ls);
@@ -379,7 +391,7 @@ static int ensure_buffers(amod_ctx* ctx, int V, i64 n_screen, int max_level, con
         lv.veh_start = b.veh_start.as<int>();
     }
     ls->n = max_level + 1;
-    CK(ctx->row_cnt.ensure(4 * max_trips)); CK(ctx->row_off.ensure(8 * (max_trips + 2)));
+    CK(ctx->row_cnt.ensure(4 * max_trips)); CK(ctx->row_off.ensure(8 * (max_trips + 2))); CK(ctx->heavy_list.ensure(4 * max_trips));
     unsigned hsz = 64; while (hsz < 2u * (unsigned)max_trips + 2u) hsz <<= 1;
     CK(ctx->hash.ensure(4 * (size_t)hsz));
     CK(ctx->veh_cnt.ensure(4 * (size_t)(V + 1))); CK(ctx->veh_off.ensure(8 * (size_t)(V + 2)));
@@ -443,55 +455,77 @@ static int enqueue_build(amod_ctx* ctx, int mode, int cap, Table<TT> tt, int max
         ctx->n_launches += 2;
     }
     // ---- levels 1..max_level ----------------------------------------------------------------------------
+    // Two branches per level once the schedule offsets are known (fork after the scans):
+    //   main: k_eval<fill> -> k_classify                     (writes the level's schedules, orders them)
+    //   side: k_compact_trips -> k_trip_index -> k_gen<count> -> scan -> k_gen<fill> -> k_expand_rows
+    //         (names the level's trips and prepares level k+1's tasks and rows; touches no schedule)
+    // They meet again before k_eval<count> of level k+1.  Buffers both branches touch at once are doubled
+    // (task lists, row descriptors, Control::n_rows / n_chunks, scan partials).
+    cudaStream_t sd = ctx->side;
+    size_t n_sync = 0;
+    auto edge = [&](cudaStream_t from, cudaStream_t to) -> cudaError_t {
+        cudaEvent_t e = get_sync_event(ctx, n_sync++);
+        cudaError_t ce = cudaEventRecord(e, from);
+        return ce != cudaSuccess ? ce : cudaStreamWaitEvent(to, e, 0);
+    };
+    auto hash_size_of = [&](int k) -> unsigned {   // trips of level k are looked up by the candidates of level k+1
+        if (k < 2 || k >= max_level) return 0u;
+        unsigned sz = 64; while (sz < 2u * (unsigned)ls.lv[k].cap_trips + 2u) sz <<= 1;
+        return sz;
+    };
+    RowDesc* rows_buf[2] = {ctx->row_desc.as<RowDesc>(), ctx->row_desc.as<RowDesc>() + ctx->cap_rows};
+    i64* row0 = ctx->task_chunk0.as<i64>();
+    i64* cpos = ctx->chunk_pos.as<i64>();
+    int* tnf = ctx->task_nfeas.as<int>();
+    k_expand_rows<<<GE, 256, 0, st>>>(ctl, 0, ls.lv[0], len0, ctx->task_veh[0].as<int>(), ctx->task_base[0].as<int>(), ctx->task_q[0].as<int>(),
+                                      ctx->task_nchunk[0].as<int>(), row0, rows_buf[0], tnf, ctx->hash.as<int>(), hash_size_of(1));
+    ctx->n_launches++;
     for (int k = 1; k <= max_level; k++) {
         const int cur = (k - 1) & 1, nxt = k & 1;
         int* tv = ctx->task_veh[cur].as<int>(); int* tb = ctx->task_base[cur].as<int>(); int* tq = ctx->task_q[cur].as<int>();
         const Level& prev = ls.lv[k - 1];
         const Level& lv = ls.lv[k];
-        i64* row0 = ctx->task_chunk0.as<i64>();
-        i64* cpos = ctx->chunk_pos.as<i64>();
         const int Gk = std::max(1, 32 / (prev.stride + 1));      // rows per chunk: Gk * (longest schedule + 1) <= 32 lanes
-        RowDesc* rows = ctx->row_desc.as<RowDesc>();
-        int* tnf = ctx->task_nfeas.as<int>();
-        k_expand_rows<<<GE, 256, 0, st>>>(ctl, cur, prev, len0, tv, tb, tq, ctx->task_nchunk[cur].as<int>(), row0, rows, tnf);
+        RowDesc* rows = rows_buf[cur];
         CK(cudaEventRecord(get_event(ctx, n_ev++), st));
-        k_eval<TT, 0><<<GE, WARPS_PER_BLOCK * 32, 0, st>>>(d, tt, prev, lv, ctl, Gk, rows, ctx->chunk_cnt.as<int>(),
+        k_eval<TT, 0><<<GE, WARPS_PER_BLOCK * 32, 0, st>>>(d, tt, prev, lv, ctl, cur, Gk, rows, ctx->chunk_cnt.as<int>(),
                                                           ctx->lane_cnt.as<uint8_t>(), nullptr, tnf, dstats);
         CK(cudaEventRecord(get_event(ctx, n_ev++), st));
-        scan_dev2(ctx, InArray<int>{ctx->chunk_cnt.as<int>(), &ctl->n_chunks, 0}, cpos,
+        scan_dev2(ctx, InArray<int>{ctx->chunk_cnt.as<int>(), &ctl->n_chunks[cur], 0}, cpos,
                   FinCountI64{&ctl->n_sch[k], lv.cap_sch, &ctl->need_sch[k], &ctl->overflow, OVF_SCH},
                   InTaskFeasible{ctl, cur, tnf}, ctx->trip_pos.as<i64>(),
                   FinCountInt{&ctl->n_trips[k], (i64)lv.cap_trips, &ctl->need_trips[k], &ctl->overflow, OVF_TRIPS});
-        k_compact_trips<<<G, 256, 0, st>>>(ctl, cur, tv, tb, tq, row0, tnf, Gk, rows, ctx->lane_cnt.as<uint8_t>(), cpos,
+        CK(edge(st, sd));                                         // fork
+        k_compact_trips<<<G, 256, 0, sd>>>(ctl, cur, tv, tb, tq, row0, tnf, Gk, rows, ctx->lane_cnt.as<uint8_t>(), cpos,
                                           ctx->trip_pos.as<i64>(), prev, lv, dstats);
+        cudaEvent_t named = get_sync_event(ctx, n_sync++);        // the level's trips have their rows (s0, nfeas)
+        CK(cudaEventRecord(named, sd));
         CK(cudaEventRecord(get_event(ctx, n_ev++), st));
-        k_eval<TT, 1><<<GE, WARPS_PER_BLOCK * 32, 0, st>>>(d, tt, prev, lv, ctl, Gk, rows, ctx->chunk_cnt.as<int>(),
+        k_eval<TT, 1><<<GE, WARPS_PER_BLOCK * 32, 0, st>>>(d, tt, prev, lv, ctl, cur, Gk, rows, ctx->chunk_cnt.as<int>(),
                                                           ctx->lane_cnt.as<uint8_t>(), cpos, tnf, dstats);
         CK(cudaEventRecord(get_event(ctx, n_ev++), st));
-        unsigned hash_sz = 0;       // the level's trip lookup table is cleared by the classify kernel that precedes its build
-        if (k >= 2 && k < max_level) { hash_sz = 64; while (hash_sz < 2u * (unsigned)lv.cap_trips + 2u) hash_sz <<= 1; }
+        CK(cudaStreamWaitEvent(st, named, 0));
         const int heavy_min = ctx->heavy_min >= 0 ? ctx->heavy_min : (cap > 5 ? 2048 : 0);   // large capacities: trips with 10^3..10^5 schedules
-        k_classify<<<GE, WARPS_PER_BLOCK * 32, 0, st>>>(d, ctl, lv, sba, ctx->hash.as<int>(), hash_sz, heavy_min, ctx->row_cnt.as<int>());
-        if (heavy_min) { k_classify_heavy<<<ctx->n_sm * 2, HEAVY_THREADS, 0, st>>>(ctl, lv, ctx->row_cnt.as<int>()); ctx->n_launches++; }
-        ctx->n_launches += 5;
-        if (k == max_level) break;
-        // ---- candidates of size k+1 ---------------------------------------------------------------------
-        TripHash th; th.slots = ctx->hash.as<int>(); th.mask = 0;
-        if (k >= 2) {
-            unsigned sz = 64; while (sz < 2u * (unsigned)lv.cap_trips + 2u) sz <<= 1;
-            th.mask = sz - 1;
-            k_hash_build<<<G, 256, 0, st>>>(ctl, lv, th);
-            ctx->n_launches++;
+        k_classify<<<GE, WARPS_PER_BLOCK * 32, 0, st>>>(ctl, lv, heavy_min, ctx->heavy_list.as<int>());
+        if (heavy_min) { k_classify_heavy<<<ctx->n_sm * 2, HEAVY_THREADS, 0, st>>>(ctl, lv, ctx->heavy_list.as<int>()); ctx->n_launches++; }
+        TripHash th; th.slots = ctx->hash.as<int>(); th.mask = hash_size_of(k) ? hash_size_of(k) - 1 : 0;
+        k_trip_index<<<G, 256, 0, sd>>>(d, ctl, lv, sba, th);
+        ctx->n_launches += 6;
+        if (k < max_level) {
+            // ---- candidates of size k+1 (dispatch_osp.py:183-216) and their rows ---------------------------
+            k_gen<0><<<GE, WARPS_PER_BLOCK * 32, 0, sd>>>(ctl, nxt, ls.lv[1], lv, th, len0, ctx->row_cnt.as<int>(), nullptr, nullptr, nullptr,
+                                                         nullptr, nullptr, nullptr, nullptr, nullptr);
+            scan_dev(ctx, InRowCntPacked{ctx->row_cnt.as<int>(), lv.nfeas, &ctl->n_trips[k], ctl}, ctx->row_off.as<i64>(),
+                     FinTasksRows{ctl, nxt, ctx->cap_tasks, ctx->cap_rows, ctx->cap_chunks, std::max(1, 32 / (lv.stride + 1))}, true);
+            k_gen<1><<<GE, WARPS_PER_BLOCK * 32, 0, sd>>>(ctl, nxt, ls.lv[1], lv, th, len0, nullptr, ctx->row_off.as<i64>(), ctx->tmp_j.as<int>(),
+                                                         ctx->tmp_q.as<int>(), ctx->task_veh[nxt].as<int>(), ctx->task_base[nxt].as<int>(),
+                                                         ctx->task_q[nxt].as<int>(), ctx->task_nchunk[nxt].as<int>(), row0);
+            k_expand_rows<<<GE, 256, 0, sd>>>(ctl, nxt, lv, len0, ctx->task_veh[nxt].as<int>(), ctx->task_base[nxt].as<int>(),
+                                              ctx->task_q[nxt].as<int>(), ctx->task_nchunk[nxt].as<int>(), row0, rows_buf[nxt], tnf,
+                                              ctx->hash.as<int>(), hash_size_of(k + 1));
+            ctx->n_launches += 3;
         }
-        k_gen<0><<<GE, WARPS_PER_BLOCK * 32, 0, st>>>(ctl, nxt, ls.lv[1], lv, th, len0, ctx->row_cnt.as<int>(), nullptr, nullptr, nullptr,
-                                                     nullptr, nullptr, nullptr, nullptr, nullptr);
-        scan_dev(ctx, InRowCntPacked{ctx->row_cnt.as<int>(), lv.nfeas, &ctl->n_trips[k], ctl}, ctx->row_off.as<i64>(),
-                 FinTasksRows{ctl, nxt, ctx->cap_tasks, ctx->cap_rows, ctx->cap_chunks, std::max(1, 32 / (lv.stride + 1))});
-        k_gen<1><<<GE, WARPS_PER_BLOCK * 32, 0, st>>>(ctl, nxt, ls.lv[1], lv, th, len0, nullptr, ctx->row_off.as<i64>(), ctx->tmp_j.as<int>(),
-                                                     ctx->tmp_q.as<int>(), ctx->task_veh[nxt].as<int>(), ctx->task_base[nxt].as<int>(),
-                                                     ctx->task_q[nxt].as<int>(), ctx->task_nchunk[nxt].as<int>(),
-                                                     ctx->task_chunk0.as<i64>());
-        ctx->n_launches += 2;
+        CK(edge(sd, st));                                         // join
     }
     // ---- pool assembly --------------------------------------------------------------------------------
     {
@@ -947,7 +981,7 @@ extern "C" int amod_greedy_assign(amod_ctx* ctx, int32_t* order_out, int32_t* se
     CK(ctx->ga_pos.ensure(8 * (GA_BUCKETS * Pz + 2))); CK(ctx->ga_rank.ensure(4 * Pz)); CK(ctx->ga_order.ensure(4 * Pz));
     CK(ctx->ga_state.ensure(Pz)); CK(ctx->ga_bv.ensure(4 * (size_t)(V + 1))); CK(ctx->ga_br.ensure(4 * (size_t)(R + 1)));
     CK(ctx->ga_tv.ensure((size_t)V + 1)); CK(ctx->ga_tr.ensure((size_t)R + 1)); CK(ctx->ga_sel.ensure(4 * Pz)); CK(ctx->ga_cnt.ensure(32));
-    CK(ctx->partial.ensure(8 * (size_t)(ctx->n_sm + 1)));
+    CK(ctx->partial.ensure(2 * 8 * (size_t)(ctx->n_sm + 1)));
     const int G = ctx->n_sm * 2;
     i64* pos = ctx->ga_pos.as<i64>();
     unsigned long long* err = (unsigned long long*)(ctx->ga_cnt.as<char>() + 8);

@@ -74,8 +74,8 @@ struct Stats {            // device counters
 #define OVF_ITEMS 64ull
 struct Control {
     int n_tasks[2];
-    int n_chunks;
-    int n_rows;
+    int n_chunks[2];      // rows / chunks of the task buffer with the same index: level k+1 is prepared while
+    int n_rows[2];        // level k's schedules are still being written (two branches of the epoch graph)
     int n_perm_items;     // warp work units of the basic-schedule permutation search (capacity > 5)
     int n_trips[MAX_LEVELS];
     i64 n_sch[MAX_LEVELS];

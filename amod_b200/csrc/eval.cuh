@@ -88,7 +88,7 @@ __device__ __forceinline__ void walk_j(const TT* __restrict__ lg, double PD, con
 // vehicle they belong to; G is chosen per level so that G * (longest schedule + 1) <= 32 lanes.
 template <typename TT, int MODE>
 __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, EVAL_BLOCKS_PER_SM)
-k_eval(const DEpoch* __restrict__ epp, Table<TT> tt, Level prev, Level cur, const Control* __restrict__ ctl, int G,
+k_eval(const DEpoch* __restrict__ epp, Table<TT> tt, Level prev, Level cur, const Control* __restrict__ ctl, int which, int G,
        const RowDesc* __restrict__ rows, int* __restrict__ chunk_cnt, uint8_t* __restrict__ lane_cnt,
        const i64* __restrict__ chunk_pos, int* __restrict__ task_nfeas, Stats* stats) {
     __shared__ WarpStage<TT> stage_all[WARPS_PER_BLOCK];
@@ -101,8 +101,8 @@ k_eval(const DEpoch* __restrict__ epp, Table<TT> tt, Level prev, Level cur, cons
     const int warp0 = blockIdx.x * WARPS_PER_BLOCK + wib, nwarps = gridDim.x * WARPS_PER_BLOCK;
     unsigned long long acc_evals = 0, acc_lookups = 0;
     const double T = ep.T;
-    const int n_rows = ctl->overflow ? 0 : ctl->n_rows;
-    const int n_chunks = ctl->overflow ? 0 : ctl->n_chunks;
+    const int n_rows = ctl->overflow ? 0 : ctl->n_rows[which];
+    const int n_chunks = ctl->overflow ? 0 : ctl->n_chunks[which];
     const int cap = ep.cap;
 
     RowDesc nxt; nxt.l = 0; nxt.v = 0; nxt.q = 0; nxt.s = 0; nxt.s0 = 0; nxt.task = 0;

@@ -324,7 +324,7 @@ struct FinTasksRows {
         if (nr > cap_rows) { atomicOr(&ctl->overflow, OVF_ROWS); nt = 0; }
         if (nch > cap_chunks) { atomicOr(&ctl->overflow, OVF_CHUNKS); nt = 0; }
         if (nt == 0) { nr = 0; nch = 0; }
-        ctl->n_tasks[which] = (int)nt; ctl->n_rows = (int)nr; ctl->n_chunks = (int)nch;
+        ctl->n_tasks[which] = (int)nt; ctl->n_rows[which] = (int)nr; ctl->n_chunks[which] = (int)nch;
         ctl->stats.n_chunks += (unsigned long long)nch;
     }
 };
@@ -371,8 +371,11 @@ k_screen_fill(const DEpoch* __restrict__ epp, const Control* __restrict__ ctl, c
 __global__ void __launch_bounds__(256)
 k_expand_rows(Control* __restrict__ ctl, int which, Level prev, const int* __restrict__ len0, const int* __restrict__ task_veh,
               const int* __restrict__ task_base, const int* __restrict__ task_q, const int* __restrict__ task_S,
-              const i64* __restrict__ task_row0, RowDesc* __restrict__ rows, int* __restrict__ task_nfeas) {
-    const int n = (ctl->n_rows && !ctl->overflow) ? ctl->n_tasks[which] : 0;
+              const i64* __restrict__ task_row0, RowDesc* __restrict__ rows, int* __restrict__ task_nfeas,
+              int* __restrict__ hash_slots, unsigned hash_size) {
+    // the level's trip lookup table is free here (the candidates that used the previous one are out): clear it
+    for (unsigned x = blockIdx.x * blockDim.x + threadIdx.x; x < hash_size; x += gridDim.x * blockDim.x) hash_slots[x] = -1;
+    const int n = (ctl->n_rows[which] && !ctl->overflow) ? ctl->n_tasks[which] : 0;
     const int lane = threadIdx.x & 31;
     const int nwarps = gridDim.x * (blockDim.x >> 5);
     if (blockIdx.x == 0 && threadIdx.x == 0 && n) atomicAdd(&ctl->stats.n_tasks, (unsigned long long)n);   // compute_schedule calls
@@ -431,7 +434,7 @@ __device__ __forceinline__ i64 row_position(i64 r, int G, const RowDesc* __restr
 // ---------------------------------------------------------------------------------------------
 struct InTaskFeasible {       // scan input: 1 if the task produced at least one feasible schedule
     const Control* ctl; int which; const int* task_nfeas;
-    __device__ __forceinline__ i64 size() const { return (ctl->n_chunks && !ctl->overflow) ? ctl->n_tasks[which] : 0; }
+    __device__ __forceinline__ i64 size() const { return (ctl->n_chunks[which] && !ctl->overflow) ? ctl->n_tasks[which] : 0; }
     __device__ __forceinline__ i64 operator()(i64 t) const { return task_nfeas[t] > 0; }
 };
 
@@ -471,20 +474,11 @@ __global__ void k_compact_trips(const Control* __restrict__ ctl, int which, cons
 // (first-encountered minimum).  One warp per trip.  Also fills veh_start (trips are vehicle-major).
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32)
-k_classify(const DEpoch* __restrict__ epp, Control* __restrict__ ctl, Level cur, int sba, int* __restrict__ hash_slots,
-           unsigned hash_size, int heavy_min, int* __restrict__ heavy_list) {
-    const int n_veh = epp->n_veh;
-    for (unsigned x = blockIdx.x * blockDim.x + threadIdx.x; x < hash_size; x += gridDim.x * blockDim.x) hash_slots[x] = -1;
+k_classify(Control* __restrict__ ctl, Level cur, int heavy_min, int* __restrict__ heavy_list) {
     const int lane = threadIdx.x & 31;
     const int n = ctl->overflow ? 0 : ctl->n_trips[cur.k];
     const int nwarps = gridDim.x * WARPS_PER_BLOCK;
-    for (int t = blockIdx.x * WARPS_PER_BLOCK + (threadIdx.x >> 5); t <= n; t += nwarps) {
-        if (!sba && lane == 0) {     // veh_start[u] = first trip of vehicle u
-            const int vprev = t == 0 ? -1 : cur.trip_veh[t - 1];
-            const int vcur = t == n ? n_veh : cur.trip_veh[t];
-            for (int u = vprev + 1; u <= vcur; u++) cur.veh_start[u] = t;
-        }
-        if (t == n) break;
+    for (int t = blockIdx.x * WARPS_PER_BLOCK + (threadIdx.x >> 5); t < n; t += nwarps) {
         const i64 s0 = cur.s0[t];
         const int nf = cur.nfeas[t];
         const double* __restrict__ cost = cur.sch_cost + s0;
@@ -606,10 +600,19 @@ __device__ __forceinline__ unsigned hash_trip(int v, const int* r, int k, int sk
     return (unsigned)(h ^ (h >> 29));
 }
 
-__global__ void k_hash_build(const Control* __restrict__ ctl, Level lv, TripHash th) {
+// Index of a freshly compacted level: veh_start (trips are vehicle-major; OSP modes) and, when the next
+// level will look its trips up (th.mask != 0; the table was cleared by this level's k_expand_rows), the hash.
+__global__ void k_trip_index(const DEpoch* __restrict__ epp, const Control* __restrict__ ctl, Level lv, int sba, TripHash th) {
     const int n = ctl->overflow ? 0 : ctl->n_trips[lv.k];
+    const int n_veh = epp->n_veh;
     const int stride = gridDim.x * blockDim.x;
-    for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < n; t += stride) {
+    for (int t = blockIdx.x * blockDim.x + threadIdx.x; t <= n; t += stride) {
+        if (!sba) {                  // veh_start[u] = first trip of vehicle u
+            const int vprev = t == 0 ? -1 : lv.trip_veh[t - 1];
+            const int vcur = t == n ? n_veh : lv.trip_veh[t];
+            for (int u = vprev + 1; u <= vcur; u++) lv.veh_start[u] = t;
+        }
+        if (t == n || th.mask == 0) continue;
         unsigned h = hash_trip(lv.trip_veh[t], lv.trip_req + (i64)t * lv.k, lv.k, -1, -1) & th.mask;
         while (atomicCAS(&th.slots[h], -1, t) != -1) h = (h + 1) & th.mask;
     }
