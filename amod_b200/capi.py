@@ -15,7 +15,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "csrc", "libamod_b200.so")
 
 OK, E_BADARG, E_CUDA, E_CAPACITY, E_LEVELS, E_NOMEM, E_LIMIT = 0, -1, -2, -3, -4, -5, -6
-LOC_HOST, LOC_DEVICE = 0, 1
+LOC_HOST, LOC_DEVICE, LOC_PINNED = 0, 1, 2
 TT_F32, TT_F64 = 0, 1
 
 _i32p, _f64p, _u8p, _i64p = C.POINTER(C.c_int32), C.POINTER(C.c_double), C.POINTER(C.c_uint8), C.POINTER(C.c_int64)
@@ -74,7 +74,8 @@ def epoch_struct(ep, ptr_of=None) -> AmodEpoch:
 
 
 EXPORTS = ("amod_create", "amod_destroy", "amod_last_error", "amod_version", "amod_set_stream",
-           "amod_osp_build", "amod_sba_build", "amod_pool_fetch", "amod_pool_view", "amod_npo_match",
+           "amod_osp_build", "amod_sba_build", "amod_pool_fetch", "amod_host_register", "amod_host_unregister",
+           "amod_pool_view", "amod_npo_match",
            "amod_gather_bench", "amod_gpool_create", "amod_gpool_open_peers", "amod_pool_veh_counts", "amod_gpool_scatter",
            "amod_gpool_view", "amod_gpool_fetch", "amod_set_graph", "amod_gpool_assemble", "amod_greedy_assign")
 
@@ -107,6 +108,10 @@ def load_library(path: str | None = None) -> C.CDLL:
         fn.restype = C.c_int
     lib.amod_pool_fetch.argtypes = [C.c_void_p, C.POINTER(AmodPool), C.c_int]
     lib.amod_pool_fetch.restype = C.c_int
+    lib.amod_host_register.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t]
+    lib.amod_host_register.restype = C.c_int
+    lib.amod_host_unregister.argtypes = [C.c_void_p, C.c_void_p]
+    lib.amod_host_unregister.restype = C.c_int
     lib.amod_pool_view.argtypes = [C.c_void_p, C.POINTER(AmodPool)]
     lib.amod_pool_view.restype = C.c_int
     lib.amod_npo_match.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_int,

@@ -721,6 +721,11 @@ extern "C" int amod_pool_fetch(amod_ctx* ctx, amod_pool* o, int loc) {
         CK(cudaStreamSynchronize(st));
         return AMOD_OK;
     }
+    if (loc == AMOD_LOC_PINNED) {      // page-locked host buffers: straight DMA
+        for (auto& p : parts) if (p.bytes) CK(cudaMemcpyAsync(p.dst, p.src, p.bytes, cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        return AMOD_OK;
+    }
     // host buffers are pageable: DMA everything into one pinned staging area, then memcpy
     size_t total = 0;
     for (auto& p : parts) total += (p.bytes + 63) & ~(size_t)63;
@@ -744,6 +749,19 @@ extern "C" int amod_pool_fetch(amod_ctx* ctx, amod_pool* o, int loc) {
     return AMOD_OK;
 }
 
+extern "C" int amod_host_register(amod_ctx* ctx, void* p, size_t bytes) {
+    if (!ctx || !p || !bytes) return AMOD_E_BADARG;
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaHostRegister(p, bytes, cudaHostRegisterDefault));
+    return AMOD_OK;
+}
+
+extern "C" int amod_host_unregister(amod_ctx* ctx, void* p) {
+    if (!ctx || !p) return AMOD_E_BADARG;
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaHostUnregister(p));
+    return AMOD_OK;
+}
 
 // ------------------------------------------------------------------------------------------------
 // multi-GPU: global pool in peer-mapped memory

@@ -43,8 +43,16 @@ class PoolBuilder:
         self.last_stats: dict = {}
         self.lazy_records = False      # seams return LazyPoolRecords (see install(greedy_on_gpu=True))
 
+    def _release_host_bufs(self):
+        bufs = getattr(self, "_host_bufs", None)
+        if bufs and getattr(self, "h", None):
+            for a in bufs.values():
+                self.lib.amod_host_unregister(self.h, a.ctypes.data)
+        self._host_bufs = None
+
     def close(self):
         if getattr(self, "h", None):
+            self._release_host_bufs()
             self.lib.amod_destroy(self.h)
             self.h = None
 
@@ -98,9 +106,11 @@ class PoolBuilder:
         if reuse:
             bufs = getattr(self, "_host_bufs", None)
             if bufs is None or any(bufs[name].size < max(n[key], 1) for name, _dt, key in capi.POOL_FIELDS):
+                self._release_host_bufs()
                 bufs = {name: np.empty(max(int(1.5 * n[key]) + 1024, 1), dtype=dt) for name, dt, key in capi.POOL_FIELDS}
                 for a in bufs.values():
-                    a.fill(0)      # touch the pages once
+                    a.fill(0)      # touch the pages once, then page-lock them: the fetch is straight DMA
+                    self._check(self.lib.amod_host_register(self.h, a.ctypes.data, a.nbytes))
                 self._host_bufs = bufs
             arrs = bufs
         else:
@@ -109,7 +119,7 @@ class PoolBuilder:
         o.cap_entries, o.cap_trip_reqs, o.cap_stops = P, NT, NS
         for name, _dt, _key in capi.POOL_FIELDS:
             setattr(o, name, arrs[name].ctypes.data)
-        self._check(self.lib.amod_pool_fetch(self.h, C.byref(o), capi.LOC_HOST))
+        self._check(self.lib.amod_pool_fetch(self.h, C.byref(o), capi.LOC_PINNED if reuse else capi.LOC_HOST))
         return Pool(stats=dict(self.last_stats), **{name: arrs[name][:n[key]] for name, _dt, key in capi.POOL_FIELDS})
 
     def build_pool(self, ep: Epoch, reuse: bool = False) -> Pool:

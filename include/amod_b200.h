@@ -16,6 +16,7 @@
 #ifndef AMOD_B200_H
 #define AMOD_B200_H
 
+#include <stddef.h>
 #include <stdint.h>
 
 #ifdef __cplusplus
@@ -33,6 +34,8 @@ extern "C" {
 
 #define AMOD_LOC_HOST 0      /* pointers in the struct are host memory   */
 #define AMOD_LOC_DEVICE 1    /* pointers are device memory of ctx's GPU  */
+#define AMOD_LOC_PINNED 2    /* host memory that is page-locked (amod_host_register, cudaHostAlloc, a pinned torch
+                              * tensor): amod_pool_fetch copies into it by DMA, without the staging copy */
 
 #define AMOD_TT_F32 0        /* travel-time table element type */
 #define AMOD_TT_F64 1
@@ -143,6 +146,11 @@ int amod_sba_build(amod_ctx* ctx, const amod_epoch* ep, int loc, amod_stats* sta
 /* Copy the last built pool into caller-owned buffers (host or device).  Returns
  * AMOD_E_CAPACITY with the required n_* filled if a buffer is too small. */
 int amod_pool_fetch(amod_ctx* ctx, amod_pool* out, int loc);
+
+/* Page-lock / release a caller-owned host buffer so that it can be passed as AMOD_LOC_PINNED
+ * (thin wrappers over cudaHostRegister / cudaHostUnregister: the host side needs no CUDA binding). */
+int amod_host_register(amod_ctx* ctx, void* p, size_t bytes);
+int amod_host_unregister(amod_ctx* ctx, void* p);
 
 /* Device pointers of the last built pool (valid until the next build on ctx). */
 int amod_pool_view(amod_ctx* ctx, amod_pool* view);

@@ -280,3 +280,30 @@ def test_block_per_trip_classification_path(monkeypatch):
         ok, why = marshal.pools_equal(b.build_pool(ep), gold, rtol=0.0, check_kind=True)
         assert ok, why
     b.close()
+
+
+def test_pinned_fetch_and_repeated_builds_are_identical():
+    """fetch(reuse=True) lands in page-locked builder-owned buffers by DMA (AMOD_LOC_PINNED); the result is the
+    staged fetch's.  The same epoch built many times in a row (graph replay, both graph branches racing freely)
+    gives the same pool every time."""
+    import glob
+    from conftest import ROOT
+    files = sorted(glob.glob(os.path.join(ROOT, "bench_data", "cfg2_epoch*.npz")))
+    tt = _grid()
+    b = PoolBuilder(tt)
+    eps = [marshal.Epoch.from_npz_dict(np.load(f), "ep_") for f in files[:3]]
+    firsts = []
+    for ep in eps:
+        b.build(ep)
+        staged = b.fetch(reuse=False)
+        pinned = b.fetch(reuse=True)
+        ok, why = marshal.pools_equal(pinned, staged, rtol=0.0, check_kind=True)
+        assert ok, why
+        firsts.append(staged)
+    for rep in range(12):
+        for ep, first in zip(eps, firsts):
+            again = b.build_pool(ep, reuse=True)
+            ok, why = marshal.pools_equal(again, first, rtol=0.0, check_kind=True)
+            assert ok, f"repeat {rep}: {why}"
+            assert again.stats["n_evals"] == first.stats["n_evals"]
+    b.close()
