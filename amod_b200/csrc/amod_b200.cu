@@ -86,7 +86,7 @@ struct amod_ctx {
     i64 cap_trips[MAX_LEVELS], cap_sch[MAX_LEVELS];
     // workspace
     DevBuf len0, S0, s0pos, perm_base, perm_nitems, perm_off, perm_cnt, perm_pos, flag8, pos, major_off, partial, task_veh[2], task_base[2], task_q[2], task_nchunk[2], task_chunk0, trip_pos,
-        row_desc, task_nfeas, chunk_cnt, lane_cnt, chunk_pos, hash, row_cnt, row_off, tmp_j, tmp_q, heavy_list;
+        row_desc, task_nfeas, chunk_cnt, lane_cnt, chunk_pos, hash, row_cnt, row_off, tmp_j, tmp_q, heavy_list, gen_partial;
     LevelBufs lv[MAX_LEVELS];
     // pool
     DevBuf veh_cnt, veh_off, ent_veh, ent_kind, ent_nfeas, ent_tlen, ent_slen, ent_src, ent_trip, ent_cost, ent_delay,
@@ -108,6 +108,7 @@ struct amod_ctx {
     cudaStream_t side = nullptr;             // second branch of the epoch graph (next level's candidates)
     std::vector<cudaEvent_t> sync_pool;      // fork / join edges between the two branches
     int n_launches = 0;
+    unsigned hash_slots = 0;                 // slots per trip lookup table (two tables in `hash`)
 
     int fail(int code, const char* fmt, ...) {
         char buf[512];
@@ -217,7 +218,7 @@ extern "C" void amod_destroy(amod_ctx* ctx) {
                      &ctx->partial,
                      &ctx->task_veh[0], &ctx->task_veh[1], &ctx->task_base[0], &ctx->task_base[1], &ctx->task_q[0], &ctx->task_q[1],
                      &ctx->task_nchunk[0], &ctx->task_nchunk[1], &ctx->task_chunk0, &ctx->trip_pos, &ctx->row_desc, &ctx->task_nfeas, &ctx->chunk_cnt,
-                     &ctx->lane_cnt, &ctx->chunk_pos, &ctx->hash, &ctx->row_cnt, &ctx->row_off, &ctx->tmp_j, &ctx->tmp_q, &ctx->heavy_list,
+                     &ctx->lane_cnt, &ctx->chunk_pos, &ctx->hash, &ctx->row_cnt, &ctx->row_off, &ctx->tmp_j, &ctx->tmp_q, &ctx->heavy_list, &ctx->gen_partial,
                      &ctx->veh_cnt, &ctx->veh_off, &ctx->ent_veh, &ctx->ent_kind, &ctx->ent_nfeas, &ctx->ent_tlen, &ctx->ent_slen,
                      &ctx->ent_src, &ctx->ent_trip, &ctx->ent_cost, &ctx->ent_delay, &ctx->trip_off, &ctx->sche_off, &ctx->trip_req,
                      &ctx->sche_code, &ctx->ga_pos, &ctx->ga_rank, &ctx->ga_order, &ctx->ga_state, &ctx->ga_bv, &ctx->ga_br, &ctx->ga_tv, &ctx->ga_tr,
@@ -393,7 +394,9 @@ static int ensure_buffers(amod_ctx* ctx, int V, i64 n_screen, int max_level, con
     ls->n = max_level + 1;
     CK(ctx->row_cnt.ensure(4 * max_trips)); CK(ctx->row_off.ensure(8 * (max_trips + 2))); CK(ctx->heavy_list.ensure(4 * max_trips));
     unsigned hsz = 64; while (hsz < 2u * (unsigned)max_trips + 2u) hsz <<= 1;
-    CK(ctx->hash.ensure(4 * (size_t)hsz));
+    CK(ctx->hash.ensure(2 * 4 * (size_t)hsz));      // two tables: level k+1's is cleared while level k's is read
+    ctx->hash_slots = hsz;
+    CK(ctx->gen_partial.ensure(8 * (size_t)ctx->n_sm * GRID_WARP_PER_SM));
     CK(ctx->veh_cnt.ensure(4 * (size_t)(V + 1))); CK(ctx->veh_off.ensure(8 * (size_t)(V + 2)));
     const size_t E = (size_t)ctx->cap_ent, PT = (size_t)ctx->cap_ptr, PS = (size_t)ctx->cap_pst;
     CK(ctx->ent_veh.ensure(4 * E)); CK(ctx->ent_kind.ensure(4 * E)); CK(ctx->ent_nfeas.ensure(4 * E)); CK(ctx->ent_tlen.ensure(4 * E));
@@ -457,8 +460,8 @@ static int enqueue_build(amod_ctx* ctx, int mode, int cap, Table<TT> tt, int max
     // ---- levels 1..max_level ----------------------------------------------------------------------------
     // Two branches per level once the schedule offsets are known (fork after the scans):
     //   main: k_eval<fill> -> k_classify                     (writes the level's schedules, orders them)
-    //   side: k_compact_trips -> k_trip_index -> k_gen<count> -> scan -> k_gen<fill> -> k_expand_rows
-    //         (names the level's trips and prepares level k+1's tasks and rows; touches no schedule)
+    //   side: k_compact_trips -> k_gen_count -> k_gen_emit
+    //         (names and indexes the level's trips, prepares level k+1's tasks and rows; touches no schedule)
     // They meet again before k_eval<count> of level k+1.  Buffers both branches touch at once are doubled
     // (task lists, row descriptors, Control::n_rows / n_chunks, scan partials).
     cudaStream_t sd = ctx->side;
@@ -473,12 +476,17 @@ static int enqueue_build(amod_ctx* ctx, int mode, int cap, Table<TT> tt, int max
         unsigned sz = 64; while (sz < 2u * (unsigned)ls.lv[k].cap_trips + 2u) sz <<= 1;
         return sz;
     };
+    auto hash_of = [&](int k) -> TripHash {        // two tables by level parity: k+1's is cleared while k's is read
+        TripHash th; th.slots = ctx->hash.as<int>() + (size_t)(k & 1) * ctx->hash_slots;
+        th.mask = hash_size_of(k) ? hash_size_of(k) - 1 : 0;
+        return th;
+    };
     RowDesc* rows_buf[2] = {ctx->row_desc.as<RowDesc>(), ctx->row_desc.as<RowDesc>() + ctx->cap_rows};
     i64* row0 = ctx->task_chunk0.as<i64>();
     i64* cpos = ctx->chunk_pos.as<i64>();
     int* tnf = ctx->task_nfeas.as<int>();
     k_expand_rows<<<GE, 256, 0, st>>>(ctl, 0, ls.lv[0], len0, ctx->task_veh[0].as<int>(), ctx->task_base[0].as<int>(), ctx->task_q[0].as<int>(),
-                                      ctx->task_nchunk[0].as<int>(), row0, rows_buf[0], tnf, ctx->hash.as<int>(), hash_size_of(1));
+                                      ctx->task_nchunk[0].as<int>(), row0, rows_buf[0], tnf);
     ctx->n_launches++;
     for (int k = 1; k <= max_level; k++) {
         const int cur = (k - 1) & 1, nxt = k & 1;
@@ -496,8 +504,9 @@ static int enqueue_build(amod_ctx* ctx, int mode, int cap, Table<TT> tt, int max
                   InTaskFeasible{ctl, cur, tnf}, ctx->trip_pos.as<i64>(),
                   FinCountInt{&ctl->n_trips[k], (i64)lv.cap_trips, &ctl->need_trips[k], &ctl->overflow, OVF_TRIPS});
         CK(edge(st, sd));                                         // fork
+        const TripHash th = hash_of(k);
         k_compact_trips<<<G, 256, 0, sd>>>(ctl, cur, tv, tb, tq, row0, tnf, Gk, rows, ctx->lane_cnt.as<uint8_t>(), cpos,
-                                          ctx->trip_pos.as<i64>(), prev, lv, dstats);
+                                          ctx->trip_pos.as<i64>(), prev, lv, th, dstats);
         cudaEvent_t named = get_sync_event(ctx, n_sync++);        // the level's trips have their rows (s0, nfeas)
         CK(cudaEventRecord(named, sd));
         CK(cudaEventRecord(get_event(ctx, n_ev++), st));
@@ -508,22 +517,22 @@ static int enqueue_build(amod_ctx* ctx, int mode, int cap, Table<TT> tt, int max
         const int heavy_min = ctx->heavy_min >= 0 ? ctx->heavy_min : (cap > 5 ? 2048 : 0);   // large capacities: trips with 10^3..10^5 schedules
         k_classify<<<GE, WARPS_PER_BLOCK * 32, 0, st>>>(ctl, lv, heavy_min, ctx->heavy_list.as<int>());
         if (heavy_min) { k_classify_heavy<<<ctx->n_sm * 2, HEAVY_THREADS, 0, st>>>(ctl, lv, ctx->heavy_list.as<int>()); ctx->n_launches++; }
-        TripHash th; th.slots = ctx->hash.as<int>(); th.mask = hash_size_of(k) ? hash_size_of(k) - 1 : 0;
-        k_trip_index<<<G, 256, 0, sd>>>(d, ctl, lv, sba, th);
-        ctx->n_launches += 6;
+        ctx->n_launches += 4;       // k_eval x2, k_compact_trips, k_classify (the scans count themselves)
+        if (!sba && (k == 1 || k == max_level)) { k_veh_start<<<G, 256, 0, sd>>>(d, ctl, lv); ctx->n_launches++; }
         if (k < max_level) {
-            // ---- candidates of size k+1 (dispatch_osp.py:183-216) and their rows ---------------------------
-            k_gen<0><<<GE, WARPS_PER_BLOCK * 32, 0, sd>>>(ctl, nxt, ls.lv[1], lv, th, len0, ctx->row_cnt.as<int>(), nullptr, nullptr, nullptr,
-                                                         nullptr, nullptr, nullptr, nullptr, nullptr);
-            scan_dev(ctx, InRowCntPacked{ctx->row_cnt.as<int>(), lv.nfeas, &ctl->n_trips[k], ctl}, ctx->row_off.as<i64>(),
-                     FinTasksRows{ctl, nxt, ctx->cap_tasks, ctx->cap_rows, ctx->cap_chunks, std::max(1, 32 / (lv.stride + 1))}, true);
-            k_gen<1><<<GE, WARPS_PER_BLOCK * 32, 0, sd>>>(ctl, nxt, ls.lv[1], lv, th, len0, nullptr, ctx->row_off.as<i64>(), ctx->tmp_j.as<int>(),
-                                                         ctx->tmp_q.as<int>(), ctx->task_veh[nxt].as<int>(), ctx->task_base[nxt].as<int>(),
-                                                         ctx->task_q[nxt].as<int>(), ctx->task_nchunk[nxt].as<int>(), row0);
-            k_expand_rows<<<GE, 256, 0, sd>>>(ctl, nxt, lv, len0, ctx->task_veh[nxt].as<int>(), ctx->task_base[nxt].as<int>(),
-                                              ctx->task_q[nxt].as<int>(), ctx->task_nchunk[nxt].as<int>(), row0, rows_buf[nxt], tnf,
-                                              ctx->hash.as<int>(), hash_size_of(k + 1));
-            ctx->n_launches += 3;
+            // ---- candidates of size k+1 (dispatch_osp.py:183-216), their tasks and rows ----------------------
+            const TripHash thn = hash_of(k + 1);
+            k_gen_count<<<GE, WARPS_PER_BLOCK * 32, 0, sd>>>(d, ctl, ls.lv[1], lv, th, ctx->row_cnt.as<int>(),
+                                                            ctx->gen_partial.as<unsigned long long>(), thn.slots, thn.mask ? thn.mask + 1 : 0u);
+            GenOut go;
+            go.tmp_j = ctx->tmp_j.as<int>(); go.tmp_q = ctx->tmp_q.as<int>();
+            go.task_veh = ctx->task_veh[nxt].as<int>(); go.task_base = ctx->task_base[nxt].as<int>(); go.task_q = ctx->task_q[nxt].as<int>();
+            go.task_row0 = row0; go.rows = rows_buf[nxt]; go.task_nfeas = tnf;
+            go.cap_tasks = ctx->cap_tasks; go.cap_rows = ctx->cap_rows; go.cap_chunks = ctx->cap_chunks;
+            go.G_next = std::max(1, 32 / (lv.stride + 1));
+            k_gen_emit<<<GE, WARPS_PER_BLOCK * 32, 0, sd>>>(ctl, nxt, ls.lv[1], lv, th, len0, ctx->row_cnt.as<int>(),
+                                                           ctx->gen_partial.as<unsigned long long>(), go);
+            ctx->n_launches += 2;
         }
         CK(edge(sd, st));                                         // join
     }

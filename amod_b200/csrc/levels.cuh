@@ -5,6 +5,7 @@
 #pragma once
 #include "common.cuh"
 #include "eval.cuh"
+#include "scan.cuh"
 
 // ---------------------------------------------------------------------------------------------
 // Level 0: basic schedules.  One warp per vehicle.
@@ -371,10 +372,7 @@ k_screen_fill(const DEpoch* __restrict__ epp, const Control* __restrict__ ctl, c
 __global__ void __launch_bounds__(256)
 k_expand_rows(Control* __restrict__ ctl, int which, Level prev, const int* __restrict__ len0, const int* __restrict__ task_veh,
               const int* __restrict__ task_base, const int* __restrict__ task_q, const int* __restrict__ task_S,
-              const i64* __restrict__ task_row0, RowDesc* __restrict__ rows, int* __restrict__ task_nfeas,
-              int* __restrict__ hash_slots, unsigned hash_size) {
-    // the level's trip lookup table is free here (the candidates that used the previous one are out): clear it
-    for (unsigned x = blockIdx.x * blockDim.x + threadIdx.x; x < hash_size; x += gridDim.x * blockDim.x) hash_slots[x] = -1;
+              const i64* __restrict__ task_row0, RowDesc* __restrict__ rows, int* __restrict__ task_nfeas) {
     const int n = (ctl->n_rows[which] && !ctl->overflow) ? ctl->n_tasks[which] : 0;
     const int lane = threadIdx.x & 31;
     const int nwarps = gridDim.x * (blockDim.x >> 5);
@@ -430,6 +428,60 @@ __device__ __forceinline__ i64 row_position(i64 r, int G, const RowDesc* __restr
 }
 
 // ---------------------------------------------------------------------------------------------
+// Trip lookup table of one level: (vehicle, ascending request tuple) -> trip index.
+// Replaces the reference's `list in list` scans (dispatch_osp.py:194,202).
+// ---------------------------------------------------------------------------------------------
+struct TripHash { int* slots; unsigned mask; };
+
+__device__ __forceinline__ unsigned hash_trip(int v, const int* r, int k, int skip, int extra) {
+    // hash of the ascending tuple (r minus element `skip`, plus `extra` merged in order)
+    unsigned long long h = 0x9E3779B97F4A7C15ull ^ (unsigned long long)(unsigned)v * 0xD6E8FEB86659FD93ull;
+    bool put = extra < 0;
+    for (int m = 0; m < k; m++) {
+        if (m == skip) continue;
+        if (!put && extra < r[m]) { h = (h ^ (unsigned)extra) * 0xFF51AFD7ED558CCDull; h ^= h >> 32; put = true; }
+        h = (h ^ (unsigned)r[m]) * 0xFF51AFD7ED558CCDull; h ^= h >> 32;
+    }
+    if (!put) { h = (h ^ (unsigned)extra) * 0xFF51AFD7ED558CCDull; h ^= h >> 32; }
+    return (unsigned)(h ^ (h >> 29));
+}
+
+// veh_start[u] = first trip of vehicle u (trips are vehicle-major; OSP modes): levels whose candidates are
+// not generated by k_gen_count (level 1 before its own candidates, the last level searched)
+__global__ void k_veh_start(const DEpoch* __restrict__ epp, const Control* __restrict__ ctl, Level lv) {
+    const int n = ctl->overflow ? 0 : ctl->n_trips[lv.k];
+    const int n_veh = epp->n_veh;
+    for (int u = blockIdx.x * blockDim.x + threadIdx.x; u <= n_veh; u += gridDim.x * blockDim.x) {
+        int a = 0, b = n;
+        while (a < b) { const int m = (a + b) >> 1; if (lv.trip_veh[m] < u) a = m + 1; else b = m; }
+        lv.veh_start[u] = a;
+    }
+}
+
+// index of the trip (v, r minus r[skip] plus extra), or -1
+__device__ __forceinline__ int hash_find(const Level& lv, const TripHash& th, int v, const int* r, int skip, int extra) {
+    const int k = lv.k;
+    unsigned h = hash_trip(v, r, k, skip, extra) & th.mask;
+    for (;;) {
+        const int t = th.slots[h];
+        if (t < 0) return -1;
+        if (lv.trip_veh[t] == v) {
+            const int* c = lv.trip_req + (i64)t * k;
+            bool same = true, put = false;
+            int w = 0;
+            for (int m = 0; m < k && same; m++) {
+                if (m == skip) continue;
+                if (!put && extra < r[m]) { same = c[w++] == extra; put = true; if (!same) break; }
+                same = c[w++] == r[m];
+            }
+            if (same && !put) same = c[w++] == extra;
+            if (same) return t;
+        }
+        h = (h + 1) & th.mask;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
 // Feasible tasks -> trips of the new level, order preserved (dispatch_osp.py:163-164, :217-218).
 // ---------------------------------------------------------------------------------------------
 struct InTaskFeasible {       // scan input: 1 if the task produced at least one feasible schedule
@@ -443,7 +495,7 @@ __global__ void k_compact_trips(const Control* __restrict__ ctl, int which, cons
                                 const i64* __restrict__ task_row0, const int* __restrict__ task_nfeas, int G,
                                 const RowDesc* __restrict__ rows, const uint8_t* __restrict__ lane_cnt,
                                 const i64* __restrict__ chunk_pos, const i64* __restrict__ trip_pos, Level prev, Level cur,
-                                Stats* stats) {
+                                TripHash th, Stats* stats) {
     const int n = (ctl->n_trips[cur.k] && !ctl->overflow) ? ctl->n_tasks[which] : 0;
     const int stride = gridDim.x * blockDim.x;
     unsigned long long nsch = 0;
@@ -462,6 +514,10 @@ __global__ void k_compact_trips(const Control* __restrict__ ctl, int which, cons
         int w = 0; bool put = false;
         for (int m = 0; m < kb; m++) { if (!put && q < bq[m]) { d[w++] = q; put = true; } d[w++] = bq[m]; }
         if (!put) d[w++] = q;
+        if (th.mask) {        // the next level looks this one's trips up (table cleared two kernels back, by k_gen_count)
+            unsigned h = hash_trip(task_veh[t], d, kb + 1, -1, -1) & th.mask;
+            while (atomicCAS(&th.slots[h], -1, o) != -1) h = (h + 1) & th.mask;
+        }
     }
     nsch = warp_sum(nsch);
     if ((threadIdx.x & 31) == 0 && nsch) atomicAdd(&stats->n_sches, nsch);
@@ -582,130 +638,169 @@ k_classify_heavy(const Control* __restrict__ ctl, Level cur, const int* __restri
 }
 
 // ---------------------------------------------------------------------------------------------
-// Trip lookup table of one level: (vehicle, ascending request tuple) -> trip index.
-// Replaces the reference's `list in list` scans (dispatch_osp.py:194,202).
-// ---------------------------------------------------------------------------------------------
-struct TripHash { int* slots; unsigned mask; };
-
-__device__ __forceinline__ unsigned hash_trip(int v, const int* r, int k, int skip, int extra) {
-    // hash of the ascending tuple (r minus element `skip`, plus `extra` merged in order)
-    unsigned long long h = 0x9E3779B97F4A7C15ull ^ (unsigned long long)(unsigned)v * 0xD6E8FEB86659FD93ull;
-    bool put = extra < 0;
-    for (int m = 0; m < k; m++) {
-        if (m == skip) continue;
-        if (!put && extra < r[m]) { h = (h ^ (unsigned)extra) * 0xFF51AFD7ED558CCDull; h ^= h >> 32; put = true; }
-        h = (h ^ (unsigned)r[m]) * 0xFF51AFD7ED558CCDull; h ^= h >> 32;
-    }
-    if (!put) { h = (h ^ (unsigned)extra) * 0xFF51AFD7ED558CCDull; h ^= h >> 32; }
-    return (unsigned)(h ^ (h >> 29));
-}
-
-// Index of a freshly compacted level: veh_start (trips are vehicle-major; OSP modes) and, when the next
-// level will look its trips up (th.mask != 0; the table was cleared by this level's k_expand_rows), the hash.
-__global__ void k_trip_index(const DEpoch* __restrict__ epp, const Control* __restrict__ ctl, Level lv, int sba, TripHash th) {
-    const int n = ctl->overflow ? 0 : ctl->n_trips[lv.k];
-    const int n_veh = epp->n_veh;
-    const int stride = gridDim.x * blockDim.x;
-    for (int t = blockIdx.x * blockDim.x + threadIdx.x; t <= n; t += stride) {
-        if (!sba) {                  // veh_start[u] = first trip of vehicle u
-            const int vprev = t == 0 ? -1 : lv.trip_veh[t - 1];
-            const int vcur = t == n ? n_veh : lv.trip_veh[t];
-            for (int u = vprev + 1; u <= vcur; u++) lv.veh_start[u] = t;
-        }
-        if (t == n || th.mask == 0) continue;
-        unsigned h = hash_trip(lv.trip_veh[t], lv.trip_req + (i64)t * lv.k, lv.k, -1, -1) & th.mask;
-        while (atomicCAS(&th.slots[h], -1, t) != -1) h = (h + 1) & th.mask;
-    }
-}
-
-// index of the trip (v, r minus r[skip] plus extra), or -1
-__device__ __forceinline__ int hash_find(const Level& lv, const TripHash& th, int v, const int* r, int skip, int extra) {
-    const int k = lv.k;
-    unsigned h = hash_trip(v, r, k, skip, extra) & th.mask;
-    for (;;) {
-        const int t = th.slots[h];
-        if (t < 0) return -1;
-        if (lv.trip_veh[t] == v) {
-            const int* c = lv.trip_req + (i64)t * k;
-            bool same = true, put = false;
-            int w = 0;
-            for (int m = 0; m < k && same; m++) {
-                if (m == skip) continue;
-                if (!put && extra < r[m]) { same = c[w++] == extra; put = true; if (!same) break; }
-                same = c[w++] == r[m];
-            }
-            if (same && !put) same = c[w++] == extra;
-            if (same) return t;
-        }
-        h = (h + 1) & th.mask;
-    }
-}
-
-// ---------------------------------------------------------------------------------------------
 // Candidates of size k+1 from level k (dispatch_osp.py:183-216) in closed form: a (k+1)-set U is
 // searched iff all its k-subsets are feasible; it is searched from its lowest-index subset
 // (trip_i), inserting the one request U - trip_i, and the searches of one vehicle run in
 // (i, j) order, j = second-lowest subset index.  One warp per row (= trip_i); lanes scan the
 // vehicle's size-1 trips for the request to add.
-// MODE 0: count per row.  MODE 1: write (j, q) at row_off, rank the row by j, emit the tasks.
+//
+// Two launches, no scan kernel in between: every block owns a contiguous segment of trips.
+// MODE 0 counts per row and leaves one packed (tasks | rows << 32) sum per block.
+// MODE 1 adds up the sums of the blocks before it, scans its own segment in shared memory, writes
+// (j, q) per row, ranks the row by j and emits the next level's tasks AND their row descriptors (one per
+// base schedule the task walks); the last block publishes the level's task / row / chunk counts.
 // ---------------------------------------------------------------------------------------------
+struct GenOut {
+    int* tmp_j; int* tmp_q;
+    int* task_veh; int* task_base; int* task_q; i64* task_row0;
+    RowDesc* rows; int* task_nfeas;
+    i64 cap_tasks, cap_rows, cap_chunks; int G_next;
+};
+
+__device__ __forceinline__ void gen_segment(int n, int* lo, int* hi) {
+    const int seg = (n + (int)gridDim.x - 1) / (int)gridDim.x;
+    *lo = min(n, (int)blockIdx.x * seg);
+    *hi = min(n, *lo + seg);
+}
+
+// candidates of row t: count them (MODE 0) or store (j, q) at tmp[off..] (MODE 1); returns the count
 template <int MODE>
-__global__ void __launch_bounds__(WARPS_PER_BLOCK * 32)
-k_gen(const Control* __restrict__ ctl, int which_next, Level l1, Level prev, TripHash th, const int* __restrict__ len0,
-      int* __restrict__ row_cnt, const i64* __restrict__ row_off, int* __restrict__ tmp_j, int* __restrict__ tmp_q,
-      int* task_veh, int* task_base, int* task_q, int* task_S, i64* task_row0) {
-    const int lane = threadIdx.x & 31;
-    const int n = ctl->overflow ? 0 : ctl->n_trips[prev.k];
-    if (MODE == 1 && ctl->n_tasks[which_next] == 0) return;
-    const int nwarps = gridDim.x * WARPS_PER_BLOCK;
-    for (int t = blockIdx.x * WARPS_PER_BLOCK + (threadIdx.x >> 5); t < n; t += nwarps) {
-        const int v = prev.trip_veh[t], k = prev.k;
-        const int a0 = l1.veh_start[v], a1 = l1.veh_start[v + 1];
-        const int* mine = prev.trip_req + (i64)t * k;
-        int cnt = 0;
-        const i64 off = MODE == 1 ? PACK_LO(row_off[t]) : 0;
-        const i64 rbase = MODE == 1 ? PACK_HI(row_off[t]) : 0;
-        for (int c0 = a0; c0 < a1; c0 += 32) {
-            const int c = c0 + lane;
-            int j = -1, r = -1;
-            if (c < a1) {
-                r = l1.trip_req[c];
-                if (k == 1) {
-                    if (c > t) j = c;                       // all pairs i<j (dispatch_osp.py:183-186)
-                } else {
-                    bool in = false;
-                    for (int m = 0; m < k; m++) in |= mine[m] == r;
-                    if (!in) {
-                        j = 0x7fffffff;
-                        for (int d = 0; d < k; d++) {       // every other k-subset must exist with a larger index
-                            const int u = hash_find(prev, th, v, mine, d, r);
-                            if (u <= t) { j = -1; break; }
-                            j = min(j, u);
-                        }
+__device__ __forceinline__ int gen_row(const Level& l1, const Level& prev, const TripHash& th, int t, int lane, i64 off,
+                                       int* __restrict__ tmp_j, int* __restrict__ tmp_q) {
+    const int v = prev.trip_veh[t], k = prev.k;
+    const int a0 = l1.veh_start[v], a1 = l1.veh_start[v + 1];
+    const int* mine = prev.trip_req + (i64)t * k;
+    int cnt = 0;
+    for (int c0 = a0; c0 < a1; c0 += 32) {
+        const int c = c0 + lane;
+        int j = -1, r = -1;
+        if (c < a1) {
+            r = l1.trip_req[c];
+            if (k == 1) {
+                if (c > t) j = c;                       // all pairs i<j (dispatch_osp.py:183-186)
+            } else {
+                bool in = false;
+                for (int m = 0; m < k; m++) in |= mine[m] == r;
+                if (!in) {
+                    j = 0x7fffffff;
+                    for (int d = 0; d < k; d++) {       // every other k-subset must exist with a larger index
+                        const int u = hash_find(prev, th, v, mine, d, r);
+                        if (u <= t) { j = -1; break; }
+                        j = min(j, u);
                     }
                 }
             }
-            const unsigned bal = __ballot_sync(FULL, j >= 0);
-            if (MODE == 1 && j >= 0) {
-                const i64 o = off + cnt + __popc(bal & ((1u << lane) - 1u));
-                tmp_j[o] = j; tmp_q[o] = r;
-            }
-            cnt += __popc(bal);
         }
-        if (MODE == 0) { if (lane == 0) row_cnt[t] = cnt; continue; }
-        __syncwarp();
-        // rank by j (k == 1 rows are already in j order) and emit the next level's tasks
-        const int S_next = prev.nfeas[t];       // every task inserting into trip t walks all of its schedules
-        for (int e = lane; e < cnt; e += 32) {
-            int rank = e;
-            if (k > 1) {
-                const int j = tmp_j[off + e];
-                rank = 0;
-                for (int x = 0; x < cnt; x++) rank += tmp_j[off + x] < j;
-            }
-            const i64 o = off + rank;
-            task_veh[o] = v; task_base[o] = t; task_q[o] = tmp_q[off + e]; task_S[o] = S_next;
-            task_row0[o] = rbase + (i64)rank * S_next;
+        const unsigned bal = __ballot_sync(FULL, j >= 0);
+        if (MODE == 1 && j >= 0) {
+            const i64 o = off + cnt + __popc(bal & ((1u << lane) - 1u));
+            tmp_j[o] = j; tmp_q[o] = r;
         }
+        cnt += __popc(bal);
+    }
+    return cnt;
+}
+
+__global__ void __launch_bounds__(WARPS_PER_BLOCK * 32)
+k_gen_count(const DEpoch* __restrict__ epp, const Control* __restrict__ ctl, Level l1, Level prev, TripHash th,
+            int* __restrict__ row_cnt, unsigned long long* __restrict__ blk_partial, int* __restrict__ next_hash, unsigned next_hash_size) {
+    __shared__ unsigned long long s_sum;
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const int n = ctl->overflow ? 0 : ctl->n_trips[prev.k];
+    const unsigned gtid = blockIdx.x * blockDim.x + threadIdx.x, gsz = gridDim.x * blockDim.x;
+    // the lookup table the NEXT level will build into (the other buffer; its last readers are two kernels back)
+    for (unsigned x = gtid; x < next_hash_size; x += gsz) next_hash[x] = -1;
+    if (prev.k >= 2) {     // veh_start[u] = first trip of vehicle u (trips are vehicle-major); level 1 has its own kernel
+        const int n_veh = epp->n_veh;
+        for (int u = (int)gtid; u <= n_veh; u += (int)gsz) {
+            int a = 0, b = n;
+            while (a < b) { const int m = (a + b) >> 1; if (prev.trip_veh[m] < u) a = m + 1; else b = m; }
+            prev.veh_start[u] = a;
+        }
+    }
+    if (threadIdx.x == 0) s_sum = 0ull;
+    __syncthreads();
+    int lo, hi;
+    gen_segment(n, &lo, &hi);
+    unsigned long long mine = 0ull;
+    for (int t = lo + wib; t < hi; t += WARPS_PER_BLOCK) {
+        const int cnt = gen_row<0>(l1, prev, th, t, lane, 0, nullptr, nullptr);
+        if (lane == 0) {
+            row_cnt[t] = cnt;
+            mine += (unsigned long long)cnt | ((unsigned long long)cnt * (unsigned long long)prev.nfeas[t]) << 32;
+        }
+    }
+    if (lane == 0 && mine) atomicAdd(&s_sum, mine);
+    __syncthreads();
+    if (threadIdx.x == 0) blk_partial[blockIdx.x] = s_sum;
+}
+
+__global__ void __launch_bounds__(WARPS_PER_BLOCK * 32)
+k_gen_emit(Control* __restrict__ ctl, int which_next, Level l1, Level prev, TripHash th, const int* __restrict__ len0,
+           const int* __restrict__ row_cnt, const unsigned long long* __restrict__ blk_partial, GenOut o) {
+    __shared__ i64 s_scan[SCAN_THREADS / 32 + 1];
+    __shared__ i64 s_off[WARPS_PER_BLOCK * 32];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const int n = ctl->overflow ? 0 : ctl->n_trips[prev.k];
+    int lo, hi;
+    gen_segment(n, &lo, &hi);
+    const bool last = blockIdx.x == gridDim.x - 1;
+    if (lo >= hi && !last) return;
+    // packed (tasks | rows << 32) total of the blocks before this one
+    i64 p = 0;
+    for (int b = threadIdx.x; b < (int)blockIdx.x; b += blockDim.x) p += (i64)blk_partial[b];
+    i64 carry;
+    block_excl_scan(p, &carry, s_scan);
+    unsigned long long n_tasks = 0, n_items = 0;
+    for (int base = lo; base < hi; base += WARPS_PER_BLOCK * 32) {
+        const int tt = base + threadIdx.x;
+        i64 x = 0;
+        if (tt < hi) { const i64 c = row_cnt[tt]; x = c | ((c * (i64)prev.nfeas[tt]) << 32); }
+        i64 tile_tot;
+        s_off[threadIdx.x] = block_excl_scan(x, &tile_tot, s_scan) + carry;
+        __syncthreads();
+        for (int i = wib; i < WARPS_PER_BLOCK * 32 && base + i < hi; i += WARPS_PER_BLOCK) {
+            const int t = base + i;
+            const i64 off = PACK_LO(s_off[i]), rbase = PACK_HI(s_off[i]);
+            const int cnt = row_cnt[t];
+            const int S = prev.nfeas[t];          // every task inserting into trip t walks all of its schedules
+            if (cnt == 0) continue;
+            if (off + cnt > o.cap_tasks || rbase + (i64)cnt * S > o.cap_rows) continue;   // reported by the last block; the epoch is rerun
+            gen_row<1>(l1, prev, th, t, lane, off, o.tmp_j, o.tmp_q);
+            __syncwarp();
+            const int v = prev.trip_veh[t], k = prev.k;
+            const int l = len0[v] + 2 * k;
+            const i64 s0 = prev.s0[t];
+            // rank by j (k == 1 rows are already in j order) and emit the next level's tasks
+            for (int e = lane; e < cnt; e += 32) {
+                int rank = e;
+                if (k > 1) {
+                    const int j = o.tmp_j[off + e];
+                    rank = 0;
+                    for (int y = 0; y < cnt; y++) rank += o.tmp_j[off + y] < j;
+                }
+                const i64 w = off + rank;
+                o.task_veh[w] = v; o.task_base[w] = t; o.task_q[w] = o.tmp_q[off + e];
+                o.task_row0[w] = rbase + (i64)rank * S;
+                o.task_nfeas[w] = 0;
+            }
+            __syncwarp();
+            // ... and one row descriptor per (task, base schedule): task `off + e` owns rows rbase + e*S ..
+            const i64 n_rows = (i64)cnt * S;
+            for (i64 idx = lane; idx < n_rows; idx += 32) {
+                const int e = (int)(idx / S), xs = (int)(idx - (i64)e * S);
+                RowDesc d;
+                d.v = v; d.q = o.task_q[off + e]; d.s = xs; d.l = l; d.s0 = s0; d.task = (int)(off + e); d.pad = 0;
+                o.rows[rbase + idx] = d;
+            }
+            if (lane == 0) { n_tasks += (unsigned long long)cnt; n_items += (unsigned long long)n_rows * (unsigned long long)(l + 1); }
+        }
+        carry += tile_tot;
+        __syncthreads();
+    }
+    if (lane == 0 && n_tasks) { atomicAdd(&ctl->stats.n_tasks, n_tasks); atomicAdd(&ctl->stats.n_items, n_items); }
+    if (last && threadIdx.x == 0) {
+        FinTasksRows fin{ctl, which_next, o.cap_tasks, o.cap_rows, o.cap_chunks, o.G_next};
+        fin(carry);
     }
 }
