@@ -85,7 +85,7 @@ struct amod_ctx {
     i64 cap_tasks = 1 << 18, cap_chunks = 1 << 18, cap_rows = 1 << 19, cap_items = 1 << 16, cap_ent = 1 << 18, cap_ptr = 1 << 19, cap_pst = 1 << 21;
     i64 cap_trips[MAX_LEVELS], cap_sch[MAX_LEVELS];
     // workspace
-    DevBuf len0, S0, s0pos, perm_base, perm_nitems, perm_off, perm_cnt, perm_pos, flag8, pos, major_off, partial, task_veh[2], task_base[2], task_q[2], task_nchunk[2], task_chunk0, trip_pos,
+    DevBuf len0, S0, s0pos, perm_base, perm_nitems, perm_off, perm_cnt, perm_pos, flag8, pos, major_off, partial, scan_sites, task_veh[2], task_base[2], task_q[2], task_nchunk[2], task_chunk0, trip_pos,
         row_desc, task_nfeas, chunk_cnt, lane_cnt, chunk_pos, hash, row_cnt, row_off, tmp_j, tmp_q, heavy_list, gen_partial;
     LevelBufs lv[MAX_LEVELS];
     // pool
@@ -145,6 +145,20 @@ static void scan_dev(amod_ctx* ctx, In in, i64* out, Fin fin, bool on_side = fal
     k_scan_a<In><<<g, SCAN_THREADS, 0, st>>>(in, partial);
     k_scan_b<In, Fin><<<g, SCAN_THREADS, 0, st>>>(in, partial, out, fin);
     ctx->n_launches += 2;
+}
+
+// phase (b) only: the producer kernel left the block sums in `partial` (zeroed before the epoch; see scan_seg_len)
+template <typename InA, typename FinA, typename InB, typename FinB>
+static void scan_fin2(amod_ctx* ctx, InA a, i64* outa, FinA fa, InB b, i64* outb, FinB fb, i64* partial) {
+    const int g = (ctx->n_sm / 2) * 2;
+    k_scan2_b<InA, FinA, InB, FinB><<<g, SCAN_THREADS, 0, ctx->stream>>>(a, fa, outa, b, fb, outb, partial);
+    ctx->n_launches += 1;
+}
+
+template <typename In, typename Fin>
+static void scan_fin(amod_ctx* ctx, In in, i64* out, Fin fin, i64* partial) {
+    k_scan_b<In, Fin><<<ctx->n_sm, SCAN_THREADS, 0, ctx->stream>>>(in, partial, out, fin);
+    ctx->n_launches += 1;
 }
 
 // Keep the travel-time table resident in L2 (126 MB on B200; 67 MB as fp32): persisting
@@ -215,7 +229,7 @@ extern "C" void amod_destroy(amod_ctx* ctx) {
     cudaSetDevice(ctx->device);
     cudaDeviceSynchronize();
     DevBuf* all[] = {&ctx->ep_dev, &ctx->ctl, &ctx->len0, &ctx->S0, &ctx->s0pos, &ctx->perm_base, &ctx->perm_nitems, &ctx->perm_off, &ctx->perm_cnt, &ctx->perm_pos, &ctx->flag8, &ctx->pos, &ctx->major_off,
-                     &ctx->partial,
+                     &ctx->partial, &ctx->scan_sites,
                      &ctx->task_veh[0], &ctx->task_veh[1], &ctx->task_base[0], &ctx->task_base[1], &ctx->task_q[0], &ctx->task_q[1],
                      &ctx->task_nchunk[0], &ctx->task_nchunk[1], &ctx->task_chunk0, &ctx->trip_pos, &ctx->row_desc, &ctx->task_nfeas, &ctx->chunk_cnt,
                      &ctx->lane_cnt, &ctx->chunk_pos, &ctx->hash, &ctx->row_cnt, &ctx->row_off, &ctx->tmp_j, &ctx->tmp_q, &ctx->heavy_list, &ctx->gen_partial,
@@ -343,6 +357,11 @@ static int upload_epoch(amod_ctx* ctx, const amod_epoch* ep, int loc, DEpoch* d)
 // ------------------------------------------------------------------------------------------------
 // the build
 // ------------------------------------------------------------------------------------------------
+// Block sums left by producer kernels, one zeroed array per scan of the epoch (levels, basic schedules, screen, pool)
+#define SCAN_SITES (MAX_LEVELS + 4)
+static size_t scan_sites_bytes(const amod_ctx* ctx) { return (size_t)SCAN_SITES * 8 * (size_t)(ctx->n_sm + 2); }
+static unsigned long long* scan_site(amod_ctx* ctx, int i) { return ctx->scan_sites.as<unsigned long long>() + (size_t)i * (size_t)(ctx->n_sm + 2); }
+
 static cudaEvent_t get_sync_event(amod_ctx* ctx, size_t i) {
     while (ctx->sync_pool.size() <= i) { cudaEvent_t e; cudaEventCreateWithFlags(&e, cudaEventDisableTiming); ctx->sync_pool.push_back(e); }
     return ctx->sync_pool[i];
@@ -366,6 +385,7 @@ static int ensure_buffers(amod_ctx* ctx, int V, i64 n_screen, int max_level, con
         CK(ctx->flag8.ensure(4 * words)); CK(ctx->pos.ensure(8 * majors)); CK(ctx->major_off.ensure(8 * majors));
     }
     CK(ctx->partial.ensure(2 * 8 * (size_t)(ctx->n_sm + 1)));
+    CK(ctx->scan_sites.ensure(scan_sites_bytes(ctx)));
     for (int w = 0; w < 2; w++) {
         CK(ctx->task_veh[w].ensure(4 * T)); CK(ctx->task_base[w].ensure(4 * T)); CK(ctx->task_q[w].ensure(4 * T));
         CK(ctx->task_nchunk[w].ensure(4 * T));
@@ -429,10 +449,12 @@ static int enqueue_build(amod_ctx* ctx, int mode, int cap, Table<TT> tt, int max
 
     // ---- level 0: basic schedules -----------------------------------------------------------------
     if (cap <= 5) {      // at most 120 orderings per vehicle: one warp per vehicle is enough
-        k_basic<TT, 0><<<GE, WARPS_PER_BLOCK * 32, 0, st>>>(d, tt, ls.lv[0], len0, ctx->S0.as<int>(), nullptr, ctl, dstats);
-        scan_dev(ctx, InVehInt{ctx->S0.as<int>(), d}, ctx->s0pos.as<i64>(),
-                 FinCountI64{&ctl->n_sch[0], ls.lv[0].cap_sch, &ctl->need_sch[0], &ctl->overflow, OVF_SCH});
-        k_basic<TT, 1><<<GE, WARPS_PER_BLOCK * 32, 0, st>>>(d, tt, ls.lv[0], len0, ctx->S0.as<int>(), ctx->s0pos.as<i64>(), ctl, dstats);
+        k_basic<TT, 0><<<GE, WARPS_PER_BLOCK * 32, 0, st>>>(d, tt, ls.lv[0], len0, ctx->S0.as<int>(), nullptr, ctl, dstats,
+                                                            scan_site(ctx, MAX_LEVELS), ctx->n_sm);
+        scan_fin(ctx, InVehInt{ctx->S0.as<int>(), d}, ctx->s0pos.as<i64>(),
+                 FinCountI64{&ctl->n_sch[0], ls.lv[0].cap_sch, &ctl->need_sch[0], &ctl->overflow, OVF_SCH}, (i64*)scan_site(ctx, MAX_LEVELS));
+        k_basic<TT, 1><<<GE, WARPS_PER_BLOCK * 32, 0, st>>>(d, tt, ls.lv[0], len0, ctx->S0.as<int>(), ctx->s0pos.as<i64>(), ctl, dstats,
+                                                            nullptr, ctx->n_sm);
         ctx->n_launches += 2;
     } else {             // up to cap! orderings: 32 permutation ranks per warp work item, spread over the GPU
         k_perm_prep<<<G, 256, 0, st>>>(d, ls.lv[0], len0, ctx->perm_base.as<int>(), ctx->perm_nitems.as<int>(), dstats);
@@ -449,9 +471,10 @@ static int enqueue_build(amod_ctx* ctx, int mode, int cap, Table<TT> tt, int max
     // ---- level-1 tasks: reachability screen ---------------------------------------------------------
     {
         const int G1 = std::max(1, 32 / (ls.lv[0].stride + 1));
-        k_screen_count<TT><<<ctx->n_sm * 16, SCREEN_WARPS * 32, 0, st>>>(d, tt, ctx->S0.as<int>(), ctx->flag8.as<unsigned>(), ctx->pos.as<i64>());
-        scan_dev(ctx, InMajorPacked{ctx->pos.as<i64>(), d}, ctx->major_off.as<i64>(),
-                 FinTasksRows{ctl, 0, ctx->cap_tasks, ctx->cap_rows, ctx->cap_chunks, G1});
+        k_screen_count<TT><<<ctx->n_sm * 16, SCREEN_WARPS * 32, 0, st>>>(d, tt, ctx->S0.as<int>(), ctx->flag8.as<unsigned>(), ctx->pos.as<i64>(),
+                                                                         scan_site(ctx, MAX_LEVELS + 1), ctx->n_sm);
+        scan_fin(ctx, InMajorPacked{ctx->pos.as<i64>(), d}, ctx->major_off.as<i64>(),
+                 FinTasksRows{ctl, 0, ctx->cap_tasks, ctx->cap_rows, ctx->cap_chunks, G1}, (i64*)scan_site(ctx, MAX_LEVELS + 1));
         k_screen_fill<<<GE, WARPS_PER_BLOCK * 32, 0, st>>>(d, ctl, ctx->S0.as<int>(), ctx->flag8.as<unsigned>(), ctx->major_off.as<i64>(),
                                                           ctx->task_veh[0].as<int>(), ctx->task_base[0].as<int>(), ctx->task_q[0].as<int>(),
                                                           ctx->task_nchunk[0].as<int>(), ctx->task_chunk0.as<i64>());
@@ -465,6 +488,7 @@ static int enqueue_build(amod_ctx* ctx, int mode, int cap, Table<TT> tt, int max
     // They meet again before k_eval<count> of level k+1.  Buffers both branches touch at once are doubled
     // (task lists, row descriptors, Control::n_rows / n_chunks, scan partials).
     cudaStream_t sd = ctx->side;
+    const int half = ctx->n_sm / 2;            // blocks per scan of the pair scan (k_scan2_b)
     size_t n_sync = 0;
     auto edge = [&](cudaStream_t from, cudaStream_t to) -> cudaError_t {
         cudaEvent_t e = get_sync_event(ctx, n_sync++);
@@ -497,12 +521,12 @@ static int enqueue_build(amod_ctx* ctx, int mode, int cap, Table<TT> tt, int max
         RowDesc* rows = rows_buf[cur];
         CK(cudaEventRecord(get_event(ctx, n_ev++), st));
         k_eval<TT, 0><<<GE, WARPS_PER_BLOCK * 32, 0, st>>>(d, tt, prev, lv, ctl, cur, Gk, rows, ctx->chunk_cnt.as<int>(),
-                                                          ctx->lane_cnt.as<uint8_t>(), nullptr, tnf, dstats);
+                                                          ctx->lane_cnt.as<uint8_t>(), nullptr, tnf, dstats, scan_site(ctx, k), half);
         CK(cudaEventRecord(get_event(ctx, n_ev++), st));
-        scan_dev2(ctx, InArray<int>{ctx->chunk_cnt.as<int>(), &ctl->n_chunks[cur], 0}, cpos,
+        scan_fin2(ctx, InArray<int>{ctx->chunk_cnt.as<int>(), &ctl->n_chunks[cur], 0}, cpos,
                   FinCountI64{&ctl->n_sch[k], lv.cap_sch, &ctl->need_sch[k], &ctl->overflow, OVF_SCH},
                   InTaskFeasible{ctl, cur, tnf}, ctx->trip_pos.as<i64>(),
-                  FinCountInt{&ctl->n_trips[k], (i64)lv.cap_trips, &ctl->need_trips[k], &ctl->overflow, OVF_TRIPS});
+                  FinCountInt{&ctl->n_trips[k], (i64)lv.cap_trips, &ctl->need_trips[k], &ctl->overflow, OVF_TRIPS}, (i64*)scan_site(ctx, k));
         CK(edge(st, sd));                                         // fork
         const TripHash th = hash_of(k);
         k_compact_trips<<<G, 256, 0, sd>>>(ctl, cur, tv, tb, tq, row0, tnf, Gk, rows, ctx->lane_cnt.as<uint8_t>(), cpos,
@@ -511,7 +535,7 @@ static int enqueue_build(amod_ctx* ctx, int mode, int cap, Table<TT> tt, int max
         CK(cudaEventRecord(named, sd));
         CK(cudaEventRecord(get_event(ctx, n_ev++), st));
         k_eval<TT, 1><<<GE, WARPS_PER_BLOCK * 32, 0, st>>>(d, tt, prev, lv, ctl, cur, Gk, rows, ctx->chunk_cnt.as<int>(),
-                                                          ctx->lane_cnt.as<uint8_t>(), cpos, tnf, dstats);
+                                                          ctx->lane_cnt.as<uint8_t>(), cpos, tnf, dstats, nullptr, half);
         CK(cudaEventRecord(get_event(ctx, n_ev++), st));
         CK(cudaStreamWaitEvent(st, named, 0));
         const int heavy_min = ctx->heavy_min >= 0 ? ctx->heavy_min : (cap > 5 ? 2048 : 0);   // large capacities: trips with 10^3..10^5 schedules
@@ -540,13 +564,12 @@ static int enqueue_build(amod_ctx* ctx, int mode, int cap, Table<TT> tt, int max
     {
         LevelSet lsp = ls;
         lsp.n = max_level + 1;          // only the levels searched this epoch hold current data
-        scan_dev(ctx, InVehEntries{d, lsp, ctl}, ctx->veh_off.as<i64>(), FinPoolEntries{ctl, pb.cap_ent, sba});
-        k_pool_meta_veh<<<G, 256, 0, st>>>(d, lsp, len0, ctx->veh_off.as<i64>(), ctl, pb);
-        k_pool_meta_levels<<<G, 256, 0, st>>>(d, lsp, len0, ctx->veh_off.as<i64>(), ctl, pb);
-        scan_dev2(ctx, InEntLen{pb.ent_tlen, ctl}, pb.trip_off, FinCountI64{&ctl->n_ptr, pb.cap_ptr, &ctl->need_ptr, &ctl->overflow, OVF_POOL},
-                  InEntLen{pb.ent_slen, ctl}, pb.sche_off, FinCountI64{&ctl->n_pst, pb.cap_pst, &ctl->need_pst, &ctl->overflow, OVF_POOL});
+        k_pool_meta<<<G, 256, 0, st>>>(d, lsp, len0, ctx->veh_off.as<i64>(), ctl, pb, scan_site(ctx, MAX_LEVELS + 2), half);
+        scan_fin2(ctx, InEntLen{pb.ent_tlen, ctl}, pb.trip_off, FinCountI64{&ctl->n_ptr, pb.cap_ptr, &ctl->need_ptr, &ctl->overflow, OVF_POOL},
+                  InEntLen{pb.ent_slen, ctl}, pb.sche_off, FinCountI64{&ctl->n_pst, pb.cap_pst, &ctl->need_pst, &ctl->overflow, OVF_POOL},
+                  (i64*)scan_site(ctx, MAX_LEVELS + 2));
         k_pool_payload<TT><<<G * 2, 128, 0, st>>>(d, tt, lsp, ctl, pb);
-        ctx->n_launches += 3;
+        ctx->n_launches += 2;
     }
     *n_ev_out = n_ev;
     return AMOD_OK;
@@ -593,6 +616,7 @@ static int build_impl(amod_ctx* ctx, const amod_epoch* ep, int loc, amod_stats* 
         memset(h, 0, sizeof(Control));
         h->n_trips[0] = V;
         CK(cudaMemcpyAsync(ctx->ctl.p, h, sizeof(Control), cudaMemcpyHostToDevice, st));
+        CK(cudaMemsetAsync(ctx->scan_sites.p, 0, scan_sites_bytes(ctx), st));     // block sums the producer kernels add into
         if (ctx->use_graph) {
             // the whole level loop is one CUDA graph: ~150 small kernels whose sizes all live on the device,
             // so a captured graph stays valid until a buffer moves or the dispatch mode / capacity changes

@@ -14,6 +14,7 @@
 // MODE 1 re-walks only lanes that found something and writes schedules + costs in encounter order.
 #pragma once
 #include "common.cuh"
+#include "scan.cuh"
 
 #ifndef EVAL_BLOCKS_PER_SM
 #define EVAL_BLOCKS_PER_SM 4
@@ -90,7 +91,7 @@ template <typename TT, int MODE>
 __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, EVAL_BLOCKS_PER_SM)
 k_eval(const DEpoch* __restrict__ epp, Table<TT> tt, Level prev, Level cur, const Control* __restrict__ ctl, int which, int G,
        const RowDesc* __restrict__ rows, int* __restrict__ chunk_cnt, uint8_t* __restrict__ lane_cnt,
-       const i64* __restrict__ chunk_pos, int* __restrict__ task_nfeas, Stats* stats) {
+       const i64* __restrict__ chunk_pos, int* __restrict__ task_nfeas, Stats* stats, unsigned long long* __restrict__ part, int part_vg) {
     __shared__ WarpStage<TT> stage_all[WARPS_PER_BLOCK];
     __shared__ DEpoch s_ep;       // the epoch header once per block: array pointers without a second indirection
     if (threadIdx.x < sizeof(DEpoch) / 4) ((int*)&s_ep)[threadIdx.x] = ((const int*)epp)[threadIdx.x];
@@ -104,6 +105,8 @@ k_eval(const DEpoch* __restrict__ epp, Table<TT> tt, Level prev, Level cur, cons
     const int n_rows = ctl->overflow ? 0 : ctl->n_rows[which];
     const int n_chunks = ctl->overflow ? 0 : ctl->n_chunks[which];
     const int cap = ep.cap;
+    // MODE 0 leaves the block sums of the two scans that follow (schedules per chunk, feasible tasks) as it goes
+    const int seg_chunks = (int)scan_seg_len(n_chunks, part_vg), seg_tasks = (int)scan_seg_len(ctl->n_tasks[which], part_vg);
 
     RowDesc nxt; nxt.l = 0; nxt.v = 0; nxt.q = 0; nxt.s = 0; nxt.s0 = 0; nxt.task = 0;
     if (warp0 < n_chunks && lane < G && warp0 * G + lane < n_rows) nxt = rows[(i64)warp0 * G + lane];
@@ -258,7 +261,7 @@ k_eval(const DEpoch* __restrict__ epp, Table<TT> tt, Level prev, Level cur, cons
                 }
                 acc_evals += o.evals; acc_lookups += o.lookups;
                 lane_cnt[(i64)c * 64 + it0 + lane] = (uint8_t)o.n;     // <= 64 items per chunk
-                if (o.n) atomicAdd(&task_nfeas[task], o.n);
+                if (o.n && atomicAdd(&task_nfeas[task], o.n) == 0) atomicAdd(&part[part_vg + task / seg_tasks], 1ull);   // first feasible insertion of the task
                 cnt_total += o.n;
             } else {
                 const int before = warp_excl_sum(mine, lane);
@@ -270,7 +273,7 @@ k_eval(const DEpoch* __restrict__ epp, Table<TT> tt, Level prev, Level cur, cons
         if (MODE == 0) {
             if (items <= 32) lane_cnt[(i64)c * 64 + 32 + lane] = 0;
             cnt_total = warp_sum(cnt_total);
-            if (lane == 0) chunk_cnt[c] = cnt_total;
+            if (lane == 0) { chunk_cnt[c] = cnt_total; if (cnt_total) atomicAdd(&part[c / seg_chunks], (unsigned long long)cnt_total); }
         }
     }
     if (MODE == 0) {

@@ -35,10 +35,11 @@ __device__ __forceinline__ void unrank_perm(int p, int L, int* out /*positions*/
 template <typename TT, int MODE>
 __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32)
 k_basic(const DEpoch* __restrict__ epp, Table<TT> tt, Level lv0, int* __restrict__ len0, int* __restrict__ S0, const i64* __restrict__ s0pos,
-        const Control* __restrict__ ctl, Stats* stats) {
+        const Control* __restrict__ ctl, Stats* stats, unsigned long long* __restrict__ part, int part_vg) {
     const DEpoch& ep = *epp;
     const int lane = threadIdx.x & 31;
     if (MODE == 1 && ctl->overflow) return;          // level-0 store overflowed
+    const int seg_veh = (int)scan_seg_len(ep.n_veh, part_vg);     // MODE 0 leaves the block sums of the scan over S0
     unsigned long long evals = 0, lookups = 0;
     bool bad = false;
     for (int v = blockIdx.x * WARPS_PER_BLOCK + (threadIdx.x >> 5); v < ep.n_veh; v += gridDim.x * WARPS_PER_BLOCK) {
@@ -104,7 +105,7 @@ k_basic(const DEpoch* __restrict__ epp, Table<TT> tt, Level lv0, int* __restrict
         }
     }
     if (MODE == 0) {
-        if (lane == 0) { len0[v] = L; S0[v] = count; }
+        if (lane == 0) { len0[v] = L; S0[v] = count; if (count) atomicAdd(&part[v / seg_veh], (unsigned long long)count); }
         bad |= too_long || s1 - s0 > AMOD_MAX_STOPS || (perms && L > AMOD_MAX_CAP);
     }
     }
@@ -258,13 +259,14 @@ __global__ void k_perm_rows(const DEpoch* __restrict__ epp, Level lv0, const Con
 template <typename TT>
 __global__ void __launch_bounds__(SCREEN_WARPS * 32)
 k_screen_count(const DEpoch* __restrict__ epp, Table<TT> tt, const int* __restrict__ S0, unsigned* __restrict__ bits,
-               i64* __restrict__ major_cnt) {
+               i64* __restrict__ major_cnt, unsigned long long* __restrict__ part, int part_vg) {
     __shared__ int s_cnt[SCREEN_WARPS], s_rows[SCREEN_WARPS];
     const DEpoch& ep = *epp;
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const bool sba = ep.mode == AMOD_MODE_SBA;
     const int n_major = sba ? ep.n_search : ep.n_veh, n_minor = sba ? ep.n_veh : ep.n_search;
     const int wpm = (n_minor + 31) >> 5;
+    const int seg_major = (int)scan_seg_len(n_major, part_vg);      // block sums of the scan over the majors, left as we go
     for (int mj = blockIdx.x; mj < n_major; mj += gridDim.x) {      // one block per major, its warps interleave the words
         int cnt = 0, rows = 0;
         const int vq = sba ? ep.search[mj] : 0;
@@ -298,6 +300,7 @@ k_screen_count(const DEpoch* __restrict__ epp, Table<TT> tt, const int* __restri
             int c = 0, r = 0;
             for (int x = 0; x < SCREEN_WARPS; x++) { c += s_cnt[x]; r += s_rows[x]; }
             major_cnt[mj] = (i64)c | ((i64)r << 32);
+            if (c) atomicAdd(&part[mj / seg_major], (unsigned long long)c | ((unsigned long long)r << 32));
         }
         __syncthreads();
     }

@@ -5,6 +5,7 @@
 //                                   empty pair per vehicle
 #pragma once
 #include "common.cuh"
+#include "scan.cuh"
 
 struct LevelSet { Level lv[MAX_LEVELS]; int n; };   // lv[0] = basic schedules, lv[k] = trips of size k
 
@@ -16,89 +17,102 @@ struct PoolBufs {
     double* ent_cost; double* ent_delay; i64* trip_off; i64* sche_off; int* trip_req; int* sche_code;
 };
 
-__global__ void k_pool_veh_count(const DEpoch* __restrict__ epp, LevelSet ls, const Control* __restrict__ ctl, int* __restrict__ cnt) {
-    const int n_veh = epp->n_veh, mode = epp->mode;
-    for (int v = blockIdx.x * blockDim.x + threadIdx.x; v < n_veh; v += gridDim.x * blockDim.x) {
-        int c = 1 + (mode == AMOD_MODE_OSP ? 1 : 0);
-        if (ctl->overflow) c = 0;
-        else if (mode == AMOD_MODE_SBA) c = 1;
-        else for (int k = 1; k < ls.n; k++) c += ls.lv[k].veh_start[v + 1] - ls.lv[k].veh_start[v];
-        cnt[v] = c;
+// First pool entry of vehicle v.  The per-level veh_start arrays already are prefix sums over vehicles, so the
+// vehicle-major entry offsets need no scan: (fixed entries per vehicle) * v + sum over levels of veh_start_k[v].
+__device__ __forceinline__ i64 pool_veh_off(const LevelSet& ls, int mode, int v) {
+    if (mode == AMOD_MODE_SBA) return v;
+    i64 e = (i64)v * (1 + (mode == AMOD_MODE_OSP ? 1 : 0));
+    for (int k = 1; k < ls.n; k++) e += ls.lv[k].veh_start[v];
+    return e;
+}
+
+// adds (tlen, slen) of one entry per lane to the block sums of the two scans over the entries; one atomic pair
+// per warp when all its entries fall into the same scan segment (the common case: lanes hold consecutive entries)
+__device__ __forceinline__ void pool_len_partials(unsigned long long* __restrict__ part, int vg, i64 seg, bool valid, i64 e, int tlen, int slen,
+                                                  int lane) {
+    const unsigned vm = __ballot_sync(FULL, valid);
+    if (!vm) return;
+    const int sg = valid ? (int)(e / seg) : -1;
+    const int lead = __ffs(vm) - 1;
+    const int sg0 = __shfl_sync(FULL, sg, lead);
+    const bool uni = __all_sync(FULL, !valid || sg == sg0);
+    if (uni) {
+        const int t = warp_sum(valid ? tlen : 0), sl = warp_sum(valid ? slen : 0);
+        if (lane == lead) { atomicAdd(&part[sg0], (unsigned long long)t); atomicAdd(&part[vg + sg0], (unsigned long long)sl); }
+    } else if (valid) {
+        atomicAdd(&part[sg], (unsigned long long)tlen); atomicAdd(&part[vg + sg], (unsigned long long)slen);
     }
 }
 
-struct InVehEntries {       // scan input: pool entries of vehicle v (dispatch_osp.py:113-125) / one empty pair (dispatch_sba.py:68)
-    const DEpoch* ep; LevelSet ls; const Control* ctl;
-    __device__ __forceinline__ i64 size() const { return ep->n_veh; }
-    __device__ __forceinline__ i64 operator()(i64 v) const {
-        if (ctl->overflow) return 0;
-        const int mode = ep->mode;
-        if (mode == AMOD_MODE_SBA) return 1;
-        i64 c = 1 + (mode == AMOD_MODE_OSP ? 1 : 0);
-        for (int k = 1; k < ls.n; k++) c += ls.lv[k].veh_start[v + 1] - ls.lv[k].veh_start[v];
-        return c;
-    }
-};
-
-struct FinPoolEntries {   // n_ent = scan total (+ the SBA pairs, which precede the per-vehicle empties)
-    Control* ctl; i64 cap; int sba;
-    __device__ __forceinline__ void operator()(i64 tot) const {
-        if (sba) tot += ctl->n_trips[1];
-        if (tot > ctl->need_ent) ctl->need_ent = tot;
-        if (tot > cap) { atomicOr(&ctl->overflow, OVF_POOL); tot = 0; }
-        ctl->n_ent = tot;
-    }
-};
-
-// per-vehicle fixed entries (OSP: basic + current; SBA: the empty pair)
-__global__ void k_pool_meta_veh(const DEpoch* __restrict__ epp, LevelSet ls, const int* __restrict__ len0, const i64* __restrict__ veh_off,
-                                Control* ctl, PoolBufs pb) {
+// Entry metadata: the per-vehicle fixed entries (OSP: basic + current; SBA: the empty pair) and the trip entries
+// of every level; publishes the entry count, the per-vehicle offsets (multi-GPU assembly reads them) and the block
+// sums of the two scans that follow (trip lengths, schedule lengths).
+__global__ void __launch_bounds__(256)
+k_pool_meta(const DEpoch* __restrict__ epp, LevelSet ls, const int* __restrict__ len0, i64* __restrict__ veh_off, Control* ctl, PoolBufs pb,
+            unsigned long long* __restrict__ part, int part_vg) {
     const DEpoch& ep = *epp;
-    if (ctl->n_ent == 0 || ctl->overflow) return;
-    for (int v = blockIdx.x * blockDim.x + threadIdx.x; v < ep.n_veh; v += gridDim.x * blockDim.x) {
-    const int cur_len = ep.veh_sche_off[v + 1] - ep.veh_sche_off[v];
-    // compute_sche_cost walks of the fixed pairs (dispatch_osp.py:125,148, dispatch_sba.py:69)
-    atomicAdd(&ctl->stats.n_lookups, (unsigned long long)((ep.mode == AMOD_MODE_SBA ? 0 : len0[v]) +
-                                                          (ep.mode == AMOD_MODE_OSP_NR ? 0 : cur_len)));
-    if (ep.mode == AMOD_MODE_SBA) {
-        i64 e = (i64)ctl->n_trips[1] + v;
-        pb.ent_veh[e] = v; pb.ent_kind[e] = AMOD_KIND_SBA_EMPTY; pb.ent_nfeas[e] = 1; pb.ent_tlen[e] = 0; pb.ent_slen[e] = cur_len;
-        pb.ent_src[e] = SRC_INPUT; pb.ent_trip[e] = v;
-        continue;
+    const int mode = ep.mode, n_veh = ep.n_veh;
+    const bool sba = mode == AMOD_MODE_SBA;
+    const int lane = threadIdx.x & 31;
+    i64 n_ent = 0;
+    if (!ctl->overflow) n_ent = sba ? (i64)ctl->n_trips[1] + n_veh : pool_veh_off(ls, mode, n_veh);
+    const bool over = n_ent > pb.cap_ent;
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        if (n_ent > ctl->need_ent) ctl->need_ent = n_ent;
+        if (over) atomicOr(&ctl->overflow, OVF_POOL);
+        ctl->n_ent = over ? 0 : n_ent;
     }
-    i64 e = veh_off[v];
-    pb.ent_veh[e] = v; pb.ent_kind[e] = AMOD_KIND_BASIC; pb.ent_nfeas[e] = ls.lv[0].nfeas[v]; pb.ent_tlen[e] = 0;
-    pb.ent_slen[e] = len0[v]; pb.ent_src[e] = 0; pb.ent_trip[e] = v;
-    if (ep.mode == AMOD_MODE_OSP) {
-        e = veh_off[v + 1] - 1;
-        int np = 0;
-        for (int k = ep.veh_sche_off[v]; k < ep.veh_sche_off[v + 1]; k++) np += ep.sche_code[k] >= 0 && !(ep.sche_code[k] & 1);
-        pb.ent_veh[e] = v; pb.ent_kind[e] = AMOD_KIND_CURRENT; pb.ent_nfeas[e] = 1; pb.ent_tlen[e] = np; pb.ent_slen[e] = cur_len;
-        pb.ent_src[e] = SRC_INPUT; pb.ent_trip[e] = v;
+    if (over || n_ent == 0) return;
+    const i64 seg = scan_seg_len(n_ent, part_vg);
+    const int gtid = blockIdx.x * blockDim.x + threadIdx.x, stride = gridDim.x * blockDim.x;
+    for (int v = gtid; v <= n_veh; v += stride) {
+        const i64 e0 = pool_veh_off(ls, mode, v);
+        veh_off[v] = e0;
+        if (v == n_veh) break;
+        const int cur_len = ep.veh_sche_off[v + 1] - ep.veh_sche_off[v];
+        // compute_sche_cost walks of the fixed pairs (dispatch_osp.py:125,148, dispatch_sba.py:69)
+        atomicAdd(&ctl->stats.n_lookups, (unsigned long long)((sba ? 0 : len0[v]) + (mode == AMOD_MODE_OSP_NR ? 0 : cur_len)));
+        if (sba) {
+            const i64 e = (i64)ctl->n_trips[1] + v;
+            pb.ent_veh[e] = v; pb.ent_kind[e] = AMOD_KIND_SBA_EMPTY; pb.ent_nfeas[e] = 1; pb.ent_tlen[e] = 0; pb.ent_slen[e] = cur_len;
+            pb.ent_src[e] = SRC_INPUT; pb.ent_trip[e] = v;
+            atomicAdd(&part[part_vg + e / seg], (unsigned long long)cur_len);
+            continue;
+        }
+        i64 e = e0;
+        pb.ent_veh[e] = v; pb.ent_kind[e] = AMOD_KIND_BASIC; pb.ent_nfeas[e] = ls.lv[0].nfeas[v]; pb.ent_tlen[e] = 0;
+        pb.ent_slen[e] = len0[v]; pb.ent_src[e] = 0; pb.ent_trip[e] = v;
+        atomicAdd(&part[part_vg + e / seg], (unsigned long long)len0[v]);
+        if (mode == AMOD_MODE_OSP) {
+            e = pool_veh_off(ls, mode, v + 1) - 1;
+            int np = 0;
+            for (int k = ep.veh_sche_off[v]; k < ep.veh_sche_off[v + 1]; k++) np += ep.sche_code[k] >= 0 && !(ep.sche_code[k] & 1);
+            pb.ent_veh[e] = v; pb.ent_kind[e] = AMOD_KIND_CURRENT; pb.ent_nfeas[e] = 1; pb.ent_tlen[e] = np; pb.ent_slen[e] = cur_len;
+            pb.ent_src[e] = SRC_INPUT; pb.ent_trip[e] = v;
+            atomicAdd(&part[e / seg], (unsigned long long)np); atomicAdd(&part[part_vg + e / seg], (unsigned long long)cur_len);
+        }
     }
-    }
-}
-
-// trip entries of every level
-__global__ void k_pool_meta_levels(const DEpoch* __restrict__ epp, LevelSet ls, const int* __restrict__ len0, const i64* __restrict__ veh_off,
-                                   const Control* __restrict__ ctl, PoolBufs pb) {
-    const DEpoch& ep = *epp;
-    if (ctl->n_ent == 0 || ctl->overflow) return;
-    const int stride = gridDim.x * blockDim.x;
     for (int k = 1; k < ls.n; k++) {
         const Level& lv = ls.lv[k];
         const int n = ctl->n_trips[k];
-        for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < n; t += stride) {
-            const int v = lv.trip_veh[t];
-            i64 e;
-            if (ep.mode == AMOD_MODE_SBA) e = t;
-            else {
-                e = veh_off[v] + 1 + (t - lv.veh_start[v]);
-                for (int kk = 1; kk < k; kk++) e += ls.lv[kk].veh_start[v + 1] - ls.lv[kk].veh_start[v];
+        for (int base = blockIdx.x * blockDim.x; base < n; base += stride) {      // (whole warps iterate together)
+            const int t = base + threadIdx.x;
+            const bool valid = t < n;
+            i64 e = 0;
+            int slen = 0;
+            if (valid) {
+                const int v = lv.trip_veh[t];
+                if (sba) e = t;
+                else {
+                    e = pool_veh_off(ls, mode, v) + 1 + (t - lv.veh_start[v]);
+                    for (int kk = 1; kk < k; kk++) e += ls.lv[kk].veh_start[v + 1] - ls.lv[kk].veh_start[v];
+                }
+                slen = len0[v] + 2 * k;
+                pb.ent_veh[e] = v; pb.ent_kind[e] = sba ? AMOD_KIND_SBA_PAIR : AMOD_KIND_TRIP;
+                pb.ent_nfeas[e] = lv.nfeas[t]; pb.ent_tlen[e] = k; pb.ent_slen[e] = slen;
+                pb.ent_src[e] = k; pb.ent_trip[e] = t;
             }
-            pb.ent_veh[e] = v; pb.ent_kind[e] = ep.mode == AMOD_MODE_SBA ? AMOD_KIND_SBA_PAIR : AMOD_KIND_TRIP;
-            pb.ent_nfeas[e] = lv.nfeas[t]; pb.ent_tlen[e] = k; pb.ent_slen[e] = len0[v] + 2 * k;
-            pb.ent_src[e] = k; pb.ent_trip[e] = t;
+            pool_len_partials(part, part_vg, seg, valid, e, k, slen, lane);
         }
     }
 }

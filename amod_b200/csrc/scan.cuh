@@ -37,6 +37,14 @@ __device__ __forceinline__ void scan_segment(i64 n, int vb, int vg, i64* lo, i64
     *hi = min(n, *lo + seg);
 }
 
+// A producer kernel can leave the per-block sums itself (atomicAdd into a zeroed array as it writes element i);
+// then only phase (b) is launched.  `seg` = scan_seg_len(n, blocks of the scan).
+__device__ __forceinline__ i64 scan_seg_len(i64 n, int vg) {
+    i64 seg = (n + vg - 1) / vg;
+    seg = (seg + SCAN_TILE - 1) / SCAN_TILE * SCAN_TILE;
+    return seg > 0 ? seg : SCAN_TILE;
+}
+
 template <typename In>
 __device__ __forceinline__ void scan_phase_a(const In& in, int vb, int vg, i64* __restrict__ partial, i64* smem) {
     const i64 n = in.size();
