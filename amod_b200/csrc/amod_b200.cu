@@ -156,8 +156,8 @@ static void scan_fin2(amod_ctx* ctx, InA a, i64* outa, FinA fa, InB b, i64* outb
 }
 
 template <typename In, typename Fin>
-static void scan_fin(amod_ctx* ctx, In in, i64* out, Fin fin, i64* partial) {
-    k_scan_b<In, Fin><<<ctx->n_sm, SCAN_THREADS, 0, ctx->stream>>>(in, partial, out, fin);
+static void scan_fin(amod_ctx* ctx, In in, i64* out, Fin fin, i64* partial, cudaStream_t st = nullptr) {
+    k_scan_b<In, Fin><<<ctx->n_sm, SCAN_THREADS, 0, st ? st : ctx->stream>>>(in, partial, out, fin);
     ctx->n_launches += 1;
 }
 
@@ -447,13 +447,23 @@ static int enqueue_build(amod_ctx* ctx, int mode, int cap, Table<TT> tt, int max
     size_t n_ev = 0;
     int* len0 = ctx->len0.as<int>();
 
+    cudaStream_t sd = ctx->side;
+    const int half = ctx->n_sm / 2;            // blocks per scan of the pair scan (k_scan2_b)
+    size_t n_sync = 0;
+    auto edge = [&](cudaStream_t from, cudaStream_t to) -> cudaError_t {
+        cudaEvent_t e = get_sync_event(ctx, n_sync++);
+        cudaError_t ce = cudaEventRecord(e, from);
+        return ce != cudaSuccess ? ce : cudaStreamWaitEvent(to, e, 0);
+    };
     // ---- level 0: basic schedules -----------------------------------------------------------------
     if (cap <= 5) {      // at most 120 orderings per vehicle: one warp per vehicle is enough
         k_basic<TT, 0><<<GE, WARPS_PER_BLOCK * 32, 0, st>>>(d, tt, ls.lv[0], len0, ctx->S0.as<int>(), nullptr, ctl, dstats,
                                                             scan_site(ctx, MAX_LEVELS), ctx->n_sm);
+        // the level-0 store is written beside the reachability screen, which only needs the counts (S0)
+        CK(edge(st, sd));
         scan_fin(ctx, InVehInt{ctx->S0.as<int>(), d}, ctx->s0pos.as<i64>(),
-                 FinCountI64{&ctl->n_sch[0], ls.lv[0].cap_sch, &ctl->need_sch[0], &ctl->overflow, OVF_SCH}, (i64*)scan_site(ctx, MAX_LEVELS));
-        k_basic<TT, 1><<<GE, WARPS_PER_BLOCK * 32, 0, st>>>(d, tt, ls.lv[0], len0, ctx->S0.as<int>(), ctx->s0pos.as<i64>(), ctl, dstats,
+                 FinCountI64{&ctl->n_sch[0], ls.lv[0].cap_sch, &ctl->need_sch[0], &ctl->overflow, OVF_SCH}, (i64*)scan_site(ctx, MAX_LEVELS), sd);
+        k_basic<TT, 1><<<GE, WARPS_PER_BLOCK * 32, 0, sd>>>(d, tt, ls.lv[0], len0, ctx->S0.as<int>(), ctx->s0pos.as<i64>(), ctl, dstats,
                                                             nullptr, ctx->n_sm);
         ctx->n_launches += 2;
     } else {             // up to cap! orderings: 32 permutation ranks per warp work item, spread over the GPU
@@ -466,6 +476,7 @@ static int enqueue_build(amod_ctx* ctx, int mode, int cap, Table<TT> tt, int max
         k_perm_items<TT, 1><<<GE, WARPS_PER_BLOCK * 32, 0, st>>>(d, tt, ls.lv[0], ctl, len0, ctx->perm_base.as<int>(), ctx->perm_off.as<i64>(),
                                                                 ctx->perm_cnt.as<int>(), ctx->perm_pos.as<i64>(), dstats);
         k_perm_rows<<<G, 256, 0, st>>>(d, ls.lv[0], ctl, len0, ctx->S0.as<int>(), ctx->perm_off.as<i64>(), ctx->perm_pos.as<i64>());
+        CK(edge(st, sd));     // (the side branch joins the graph here; it has nothing to do before the levels)
         ctx->n_launches += 4;
     }
     // ---- level-1 tasks: reachability screen ---------------------------------------------------------
@@ -487,14 +498,6 @@ static int enqueue_build(amod_ctx* ctx, int mode, int cap, Table<TT> tt, int max
     //         (names and indexes the level's trips, prepares level k+1's tasks and rows; touches no schedule)
     // They meet again before k_eval<count> of level k+1.  Buffers both branches touch at once are doubled
     // (task lists, row descriptors, Control::n_rows / n_chunks, scan partials).
-    cudaStream_t sd = ctx->side;
-    const int half = ctx->n_sm / 2;            // blocks per scan of the pair scan (k_scan2_b)
-    size_t n_sync = 0;
-    auto edge = [&](cudaStream_t from, cudaStream_t to) -> cudaError_t {
-        cudaEvent_t e = get_sync_event(ctx, n_sync++);
-        cudaError_t ce = cudaEventRecord(e, from);
-        return ce != cudaSuccess ? ce : cudaStreamWaitEvent(to, e, 0);
-    };
     auto hash_size_of = [&](int k) -> unsigned {   // trips of level k are looked up by the candidates of level k+1
         if (k < 2 || k >= max_level) return 0u;
         unsigned sz = 64; while (sz < 2u * (unsigned)ls.lv[k].cap_trips + 2u) sz <<= 1;
@@ -509,6 +512,7 @@ static int enqueue_build(amod_ctx* ctx, int mode, int cap, Table<TT> tt, int max
     i64* row0 = ctx->task_chunk0.as<i64>();
     i64* cpos = ctx->chunk_pos.as<i64>();
     int* tnf = ctx->task_nfeas.as<int>();
+    CK(edge(sd, st));     // level 0 is stored
     k_expand_rows<<<GE, 256, 0, st>>>(ctl, 0, ls.lv[0], len0, ctx->task_veh[0].as<int>(), ctx->task_base[0].as<int>(), ctx->task_q[0].as<int>(),
                                       ctx->task_nchunk[0].as<int>(), row0, rows_buf[0], tnf);
     ctx->n_launches++;

@@ -272,26 +272,34 @@ k_screen_count(const DEpoch* __restrict__ epp, Table<TT> tt, const int* __restri
         const int vq = sba ? ep.search[mj] : 0;
         const int m_node = sba ? ep.onid[vq] : ep.veh_nid[mj];
         const double m_a = sba ? ep.clp[vq] : ep.veh_t[mj];
-        for (int w = wib; w < wpm; w += SCREEN_WARPS) {
-            const int mn = w * 32 + lane;
-            bool ok = false;
-            int S = 0;
-            if (mn < n_minor) {
-                if (sba) {   // major = request, minor = vehicle
-                    const double d = tt(ep.veh_nid[mn], m_node);
-                    ok = !(d + ep.veh_t[mn] + ep.T > m_a);
-                    S = S0[mn];
-                } else {     // major = vehicle, minor = searched request
-                    const int q = ep.search[mn];
-                    const double d = tt(m_node, ep.onid[q]);
-                    ok = !(d + m_a + ep.T > ep.clp[q]);
-                    S = S0[mj];
+        for (int w0 = wib; w0 < wpm; w0 += SCREEN_WARPS * 4) {     // four words per round: their lookups are in flight together
+            bool ok[4];
+            int S[4];
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+                const int mn = (w0 + u * SCREEN_WARPS) * 32 + lane;
+                ok[u] = false; S[u] = 0;
+                if (mn < n_minor) {
+                    if (sba) {   // major = request, minor = vehicle
+                        const double d = tt(ep.veh_nid[mn], m_node);
+                        ok[u] = !(d + ep.veh_t[mn] + ep.T > m_a);
+                        S[u] = S0[mn];
+                    } else {     // major = vehicle, minor = searched request
+                        const int q = ep.search[mn];
+                        const double d = tt(m_node, ep.onid[q]);
+                        ok[u] = !(d + m_a + ep.T > ep.clp[q]);
+                        S[u] = S0[mj];
+                    }
                 }
             }
-            const unsigned bal = __ballot_sync(FULL, ok);
-            if (lane == 0) bits[(i64)mj * wpm + w] = bal;
-            cnt += __popc(bal);
-            rows += ok ? S : 0;
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+                const int w = w0 + u * SCREEN_WARPS;
+                const unsigned bal = __ballot_sync(FULL, ok[u]);
+                if (lane == 0 && w < wpm) bits[(i64)mj * wpm + w] = bal;
+                cnt += __popc(bal);
+                rows += ok[u] ? S[u] : 0;
+            }
         }
         rows = warp_sum(rows);
         if (lane == 0) { s_cnt[wib] = cnt; s_rows[wib] = rows; }
@@ -352,21 +360,29 @@ k_screen_fill(const DEpoch* __restrict__ epp, const Control* __restrict__ ctl, c
     for (int mj = blockIdx.x * WARPS_PER_BLOCK + (threadIdx.x >> 5); mj < n_major; mj += nwarps) {
         i64 t0 = PACK_LO(major_off[mj]), r0 = PACK_HI(major_off[mj]);
         if (PACK_LO(major_off[mj + 1]) == t0) continue;
-        for (int w = 0; w < wpm; w++) {
-            const unsigned word = bits[(i64)mj * wpm + w];
-            if (!word) continue;
-            const int mn = w * 32 + lane;
-            const bool ok = (word >> lane) & 1u;
-            const int v = sba ? mn : mj;
-            const int S = ok ? S0[v] : 0;
-            const int rpre = warp_excl_sum(S, lane);
-            if (ok) {
-                const i64 t = t0 + __popc(word & ((1u << lane) - 1u));
-                task_veh[t] = v; task_base[t] = v; task_q[t] = ep.search[sba ? mj : mn];
-                task_S[t] = S; task_row0[t] = r0 + rpre;
+        // a lane per 32-pair word (the masks are sparse): count, scan over the lanes, then each lane writes its own tasks
+        for (int w0 = 0; w0 < wpm; w0 += 32) {
+            const int w = w0 + lane;
+            unsigned word = w < wpm ? bits[(i64)mj * wpm + w] : 0u;
+            const int S_major = sba ? 0 : S0[mj];
+            i64 mine = 0;
+            for (unsigned x = word; x; x &= x - 1) {
+                const int S = sba ? S0[w * 32 + __ffs(x) - 1] : S_major;
+                mine += 1 | ((i64)S << 32);
             }
-            t0 += __popc(word);
-            r0 += __shfl_sync(FULL, rpre + S, 31);
+            i64 incl = mine;
+            for (int o = 1; o < 32; o <<= 1) { const i64 y = __shfl_up_sync(FULL, incl, o); if (lane >= o) incl += y; }
+            i64 t = t0 + PACK_LO(incl - mine), r = r0 + PACK_HI(incl - mine);
+            for (; word; word &= word - 1) {
+                const int mn = w * 32 + __ffs(word) - 1;
+                const int v = sba ? mn : mj;
+                const int S = sba ? S0[v] : S_major;
+                task_veh[t] = v; task_base[t] = v; task_q[t] = ep.search[sba ? mj : mn];
+                task_S[t] = S; task_row0[t] = r;
+                t++; r += S;
+            }
+            const i64 tot = __shfl_sync(FULL, incl, 31);
+            t0 += PACK_LO(tot); r0 += PACK_HI(tot);
         }
     }
 }
