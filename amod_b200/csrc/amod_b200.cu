@@ -79,6 +79,7 @@ struct amod_ctx {
     GraphSlot graphs[3];
     unsigned long long buf_gen = 0;
     bool use_graph = true;
+    int gen_inline = GEN_INLINE;   // AMOD_GEN_INLINE=0 forces candidate recomputation in k_gen_emit (tests)
     int heavy_min = -1;            // AMOD_HEAVY_MIN overrides the block-per-trip classification threshold (tests)
     int level_hint[3] = {0, 0, 0};   // deepest non-empty trip level seen so far (+1 is searched before looking further)
     // capacities (grown from the sizes an epoch needed; persisted across epochs)
@@ -86,7 +87,7 @@ struct amod_ctx {
     i64 cap_trips[MAX_LEVELS], cap_sch[MAX_LEVELS];
     // workspace
     DevBuf len0, S0, s0pos, perm_base, perm_nitems, perm_off, perm_cnt, perm_pos, flag8, pos, major_off, partial, scan_sites, task_veh[2], task_base[2], task_q[2], task_nchunk[2], task_chunk0, trip_pos,
-        row_desc, task_nfeas, chunk_cnt, lane_cnt, chunk_pos, hash, row_cnt, row_off, tmp_j, tmp_q, heavy_list, gen_partial;
+        row_desc, task_nfeas, chunk_cnt, lane_cnt, chunk_pos, hash, row_cnt, row_off, tmp_j, tmp_q, heavy_list, gen_partial, gen_cache;
     LevelBufs lv[MAX_LEVELS];
     // pool
     DevBuf veh_cnt, veh_off, ent_veh, ent_kind, ent_nfeas, ent_tlen, ent_slen, ent_src, ent_trip, ent_cost, ent_delay,
@@ -218,6 +219,7 @@ extern "C" int amod_create(amod_ctx** out, int device, int n_nodes, const void* 
     if ((e = ctx->d_epoch.ensure(sizeof(DEpoch))) != cudaSuccess) return bail("cudaMalloc", e);
     ctx->use_graph = getenv("AMOD_NO_GRAPH") == nullptr;
     if (const char* hm = getenv("AMOD_HEAVY_MIN")) ctx->heavy_min = atoi(hm);
+    if (const char* gi = getenv("AMOD_GEN_INLINE")) ctx->gen_inline = std::max(0, std::min(GEN_INLINE, atoi(gi)));
     apply_l2_policy(ctx, ctx->stream);
     cudaEventCreate(&ctx->ev0); cudaEventCreate(&ctx->ev1);
     *out = ctx;
@@ -232,7 +234,7 @@ extern "C" void amod_destroy(amod_ctx* ctx) {
                      &ctx->partial, &ctx->scan_sites,
                      &ctx->task_veh[0], &ctx->task_veh[1], &ctx->task_base[0], &ctx->task_base[1], &ctx->task_q[0], &ctx->task_q[1],
                      &ctx->task_nchunk[0], &ctx->task_nchunk[1], &ctx->task_chunk0, &ctx->trip_pos, &ctx->row_desc, &ctx->task_nfeas, &ctx->chunk_cnt,
-                     &ctx->lane_cnt, &ctx->chunk_pos, &ctx->hash, &ctx->row_cnt, &ctx->row_off, &ctx->tmp_j, &ctx->tmp_q, &ctx->heavy_list, &ctx->gen_partial,
+                     &ctx->lane_cnt, &ctx->chunk_pos, &ctx->hash, &ctx->row_cnt, &ctx->row_off, &ctx->tmp_j, &ctx->tmp_q, &ctx->heavy_list, &ctx->gen_partial, &ctx->gen_cache,
                      &ctx->veh_cnt, &ctx->veh_off, &ctx->ent_veh, &ctx->ent_kind, &ctx->ent_nfeas, &ctx->ent_tlen, &ctx->ent_slen,
                      &ctx->ent_src, &ctx->ent_trip, &ctx->ent_cost, &ctx->ent_delay, &ctx->trip_off, &ctx->sche_off, &ctx->trip_req,
                      &ctx->sche_code, &ctx->ga_pos, &ctx->ga_rank, &ctx->ga_order, &ctx->ga_state, &ctx->ga_bv, &ctx->ga_br, &ctx->ga_tv, &ctx->ga_tr,
@@ -417,6 +419,7 @@ static int ensure_buffers(amod_ctx* ctx, int V, i64 n_screen, int max_level, con
     CK(ctx->hash.ensure(2 * 4 * (size_t)hsz));      // two tables: level k+1's is cleared while level k's is read
     ctx->hash_slots = hsz;
     CK(ctx->gen_partial.ensure(8 * (size_t)ctx->n_sm * GRID_WARP_PER_SM));
+    CK(ctx->gen_cache.ensure(sizeof(int2) * GEN_INLINE * max_trips));
     CK(ctx->veh_cnt.ensure(4 * (size_t)(V + 1))); CK(ctx->veh_off.ensure(8 * (size_t)(V + 2)));
     const size_t E = (size_t)ctx->cap_ent, PT = (size_t)ctx->cap_ptr, PS = (size_t)ctx->cap_pst;
     CK(ctx->ent_veh.ensure(4 * E)); CK(ctx->ent_kind.ensure(4 * E)); CK(ctx->ent_nfeas.ensure(4 * E)); CK(ctx->ent_tlen.ensure(4 * E));
@@ -550,7 +553,7 @@ static int enqueue_build(amod_ctx* ctx, int mode, int cap, Table<TT> tt, int max
         if (k < max_level) {
             // ---- candidates of size k+1 (dispatch_osp.py:183-216), their tasks and rows ----------------------
             const TripHash thn = hash_of(k + 1);
-            k_gen_count<<<GE, WARPS_PER_BLOCK * 32, 0, sd>>>(d, ctl, ls.lv[1], lv, th, ctx->row_cnt.as<int>(),
+            k_gen_count<<<GE, WARPS_PER_BLOCK * 32, 0, sd>>>(d, ctl, ls.lv[1], lv, th, ctx->row_cnt.as<int>(), ctx->gen_cache.as<int2>(),
                                                             ctx->gen_partial.as<unsigned long long>(), thn.slots, thn.mask ? thn.mask + 1 : 0u);
             GenOut go;
             go.tmp_j = ctx->tmp_j.as<int>(); go.tmp_q = ctx->tmp_q.as<int>();
@@ -558,8 +561,8 @@ static int enqueue_build(amod_ctx* ctx, int mode, int cap, Table<TT> tt, int max
             go.task_row0 = row0; go.rows = rows_buf[nxt]; go.task_nfeas = tnf;
             go.cap_tasks = ctx->cap_tasks; go.cap_rows = ctx->cap_rows; go.cap_chunks = ctx->cap_chunks;
             go.G_next = std::max(1, 32 / (lv.stride + 1));
-            k_gen_emit<<<GE, WARPS_PER_BLOCK * 32, 0, sd>>>(ctl, nxt, ls.lv[1], lv, th, len0, ctx->row_cnt.as<int>(),
-                                                           ctx->gen_partial.as<unsigned long long>(), go);
+            k_gen_emit<<<GE, WARPS_PER_BLOCK * 32, 0, sd>>>(ctl, nxt, ls.lv[1], lv, th, len0, ctx->row_cnt.as<int>(), ctx->gen_cache.as<int2>(),
+                                                           ctx->gen_partial.as<unsigned long long>(), go, ctx->gen_inline);
             ctx->n_launches += 2;
         }
         CK(edge(sd, st));                                         // join

@@ -682,10 +682,16 @@ __device__ __forceinline__ void gen_segment(int n, int* lo, int* hi) {
     *hi = min(n, *lo + seg);
 }
 
-// candidates of row t: count them (MODE 0) or store (j, q) at tmp[off..] (MODE 1); returns the count
+#define GEN_INLINE 8      // (j, q) pairs a row hands from the count pass to the emit pass without recomputing them
+
+// Candidates of row t, in the order of the vehicle's size-1 trips.  MODE 0 counts them and keeps the first
+// GEN_INLINE (j, q) pairs in `cache`; MODE 1 stores all of them at tmp[off..] (rows that did not fit the cache).
+// The k lookups of a candidate are not walked one after the other: every lane first tries the subset without
+// mine[0]; the (few) survivors' remaining k-1 lookups are then spread over the lanes, one lookup deep.
 template <int MODE>
 __device__ __forceinline__ int gen_row(const Level& l1, const Level& prev, const TripHash& th, int t, int lane, i64 off,
-                                       int* __restrict__ tmp_j, int* __restrict__ tmp_q) {
+                                       int* __restrict__ tmp_j, int* __restrict__ tmp_q, int* __restrict__ s_j /*[32], this warp's*/,
+                                       int2* __restrict__ cache) {
     const int v = prev.trip_veh[t], k = prev.k;
     const int a0 = l1.veh_start[v], a1 = l1.veh_start[v + 1];
     const int* mine = prev.trip_req + (i64)t * k;
@@ -700,20 +706,37 @@ __device__ __forceinline__ int gen_row(const Level& l1, const Level& prev, const
             } else {
                 bool in = false;
                 for (int m = 0; m < k; m++) in |= mine[m] == r;
-                if (!in) {
-                    j = 0x7fffffff;
-                    for (int d = 0; d < k; d++) {       // every other k-subset must exist with a larger index
-                        const int u = hash_find(prev, th, v, mine, d, r);
-                        if (u <= t) { j = -1; break; }
-                        j = min(j, u);
-                    }
+                if (!in) {                              // every other k-subset must exist with a larger index
+                    const int u = hash_find(prev, th, v, mine, 0, r);
+                    if (u > t) j = u;
                 }
             }
         }
+        if (k > 1) {
+            const unsigned surv = __ballot_sync(FULL, j >= 0);
+            __syncwarp();
+            s_j[lane] = j;
+            __syncwarp();
+            const int items = __popc(surv) * (k - 1);
+            for (int it0 = 0; it0 < items; it0 += 32) {
+                const int it = it0 + lane;
+                const bool valid = it < items;
+                const int si = valid ? it / (k - 1) : 0, d = 1 + (valid ? it % (k - 1) : 0);
+                const int src = __fns(surv, 0, si + 1);          // lane of the si-th survivor
+                const int rr = __shfl_sync(FULL, r, src);
+                if (valid) {
+                    const int u = hash_find(prev, th, v, mine, d, rr);
+                    atomicMin(&s_j[src], u > t ? u : -1);        // j = lowest subset index; any subset missing or not above t: rejected
+                }
+            }
+            __syncwarp();
+            j = s_j[lane];
+        }
         const unsigned bal = __ballot_sync(FULL, j >= 0);
-        if (MODE == 1 && j >= 0) {
-            const i64 o = off + cnt + __popc(bal & ((1u << lane) - 1u));
-            tmp_j[o] = j; tmp_q[o] = r;
+        if (j >= 0) {
+            const int p = cnt + __popc(bal & ((1u << lane) - 1u));
+            if (MODE == 1) { tmp_j[off + p] = j; tmp_q[off + p] = r; }
+            else if (p < GEN_INLINE) cache[p] = make_int2(j, r);
         }
         cnt += __popc(bal);
     }
@@ -722,8 +745,10 @@ __device__ __forceinline__ int gen_row(const Level& l1, const Level& prev, const
 
 __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32)
 k_gen_count(const DEpoch* __restrict__ epp, const Control* __restrict__ ctl, Level l1, Level prev, TripHash th,
-            int* __restrict__ row_cnt, unsigned long long* __restrict__ blk_partial, int* __restrict__ next_hash, unsigned next_hash_size) {
+            int* __restrict__ row_cnt, int2* __restrict__ row_cache, unsigned long long* __restrict__ blk_partial,
+            int* __restrict__ next_hash, unsigned next_hash_size) {
     __shared__ unsigned long long s_sum;
+    __shared__ int s_j[WARPS_PER_BLOCK][32];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const int n = ctl->overflow ? 0 : ctl->n_trips[prev.k];
     const unsigned gtid = blockIdx.x * blockDim.x + threadIdx.x, gsz = gridDim.x * blockDim.x;
@@ -743,7 +768,7 @@ k_gen_count(const DEpoch* __restrict__ epp, const Control* __restrict__ ctl, Lev
     gen_segment(n, &lo, &hi);
     unsigned long long mine = 0ull;
     for (int t = lo + wib; t < hi; t += WARPS_PER_BLOCK) {
-        const int cnt = gen_row<0>(l1, prev, th, t, lane, 0, nullptr, nullptr);
+        const int cnt = gen_row<0>(l1, prev, th, t, lane, 0, nullptr, nullptr, s_j[wib], row_cache + (i64)t * GEN_INLINE);
         if (lane == 0) {
             row_cnt[t] = cnt;
             mine += (unsigned long long)cnt | ((unsigned long long)cnt * (unsigned long long)prev.nfeas[t]) << 32;
@@ -756,7 +781,9 @@ k_gen_count(const DEpoch* __restrict__ epp, const Control* __restrict__ ctl, Lev
 
 __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32)
 k_gen_emit(Control* __restrict__ ctl, int which_next, Level l1, Level prev, TripHash th, const int* __restrict__ len0,
-           const int* __restrict__ row_cnt, const unsigned long long* __restrict__ blk_partial, GenOut o) {
+           const int* __restrict__ row_cnt, const int2* __restrict__ row_cache, const unsigned long long* __restrict__ blk_partial,
+           GenOut o, int inline_max /* <= GEN_INLINE; 0 forces the recompute path (tests) */) {
+    __shared__ int s_j[WARPS_PER_BLOCK][32];
     __shared__ i64 s_scan[SCAN_THREADS / 32 + 1];
     __shared__ i64 s_off[WARPS_PER_BLOCK * 32];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
@@ -785,23 +812,36 @@ k_gen_emit(Control* __restrict__ ctl, int which_next, Level l1, Level prev, Trip
             const int S = prev.nfeas[t];          // every task inserting into trip t walks all of its schedules
             if (cnt == 0) continue;
             if (off + cnt > o.cap_tasks || rbase + (i64)cnt * S > o.cap_rows) continue;   // reported by the last block; the epoch is rerun
-            gen_row<1>(l1, prev, th, t, lane, off, o.tmp_j, o.tmp_q);
-            __syncwarp();
             const int v = prev.trip_veh[t], k = prev.k;
             const int l = len0[v] + 2 * k;
             const i64 s0 = prev.s0[t];
             // rank by j (k == 1 rows are already in j order) and emit the next level's tasks
-            for (int e = lane; e < cnt; e += 32) {
-                int rank = e;
-                if (k > 1) {
-                    const int j = o.tmp_j[off + e];
-                    rank = 0;
-                    for (int y = 0; y < cnt; y++) rank += o.tmp_j[off + y] < j;
+            if (cnt <= inline_max) {                   // the count pass left the (j, q) pairs
+                const int2* cc = row_cache + (i64)t * GEN_INLINE;
+                if (lane < cnt) {
+                    const int2 me = cc[lane];
+                    int rank = lane;
+                    if (k > 1) { rank = 0; for (int y = 0; y < cnt; y++) rank += cc[y].x < me.x; }
+                    const i64 w = off + rank;
+                    o.task_veh[w] = v; o.task_base[w] = t; o.task_q[w] = me.y;
+                    o.task_row0[w] = rbase + (i64)rank * S;
+                    o.task_nfeas[w] = 0;
                 }
-                const i64 w = off + rank;
-                o.task_veh[w] = v; o.task_base[w] = t; o.task_q[w] = o.tmp_q[off + e];
-                o.task_row0[w] = rbase + (i64)rank * S;
-                o.task_nfeas[w] = 0;
+            } else {
+                gen_row<1>(l1, prev, th, t, lane, off, o.tmp_j, o.tmp_q, s_j[wib], nullptr);
+                __syncwarp();
+                for (int e = lane; e < cnt; e += 32) {
+                    int rank = e;
+                    if (k > 1) {
+                        const int j = o.tmp_j[off + e];
+                        rank = 0;
+                        for (int y = 0; y < cnt; y++) rank += o.tmp_j[off + y] < j;
+                    }
+                    const i64 w = off + rank;
+                    o.task_veh[w] = v; o.task_base[w] = t; o.task_q[w] = o.tmp_q[off + e];
+                    o.task_row0[w] = rbase + (i64)rank * S;
+                    o.task_nfeas[w] = 0;
+                }
             }
             __syncwarp();
             // ... and one row descriptor per (task, base schedule): task `off + e` owns rows rbase + e*S ..

@@ -307,3 +307,18 @@ def test_pinned_fetch_and_repeated_builds_are_identical():
             assert ok, f"repeat {rep}: {why}"
             assert again.stats["n_evals"] == first.stats["n_evals"]
     b.close()
+
+
+def test_candidate_recompute_path(monkeypatch):
+    """k_gen_emit normally takes a row's (j, q) candidates from the count pass (first GEN_INLINE of them); rows with
+    more recompute them.  Force every row onto the recompute path and compare with the reference goldens."""
+    monkeypatch.setenv("AMOD_GEN_INLINE", "0")
+    for family in ("rand_real_osp_cap4", "rand_ties_osp_cap8"):
+        if family not in golden_families(("rand_",)):
+            continue
+        tt, cases = load_golden(family)
+        b = PoolBuilder(tt)          # a fresh context reads the override
+        for ep, gold in cases[:3]:
+            ok, why = marshal.pools_equal(b.build_pool(ep), gold, rtol=0.0, check_kind=True)
+            assert ok, f"{family}: {why}"
+        b.close()
