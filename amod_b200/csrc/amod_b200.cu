@@ -826,6 +826,7 @@ static GSlotLayout gslot_layout(i64 cv, i64 ce, i64 ct, i64 cs) {
     auto take = [&](i64 bytes) { i64 at = o; o += (bytes + 255) / 256 * 256; return at; };
     S.o_hdr = take(64); S.o_vehoff = take(8 * (cv + 1)); S.o_kind = take(4 * ce); S.o_nfeas = take(4 * ce); S.o_cost = take(8 * ce);
     S.o_delay = take(8 * ce); S.o_toff = take(8 * (ce + 1)); S.o_soff = take(8 * (ce + 1)); S.o_treq = take(4 * ct); S.o_scode = take(4 * cs);
+    S.o_cnt = take(4 * 3 * cv);
     S.bytes = o;
     return S;
 }

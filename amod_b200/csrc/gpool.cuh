@@ -142,6 +142,7 @@ __global__ void k_gp_signal_done(GPoolLayout L, GPoolPeers peers, unsigned long 
 struct GSlotLayout {        // one staging slot (offsets inside the slot); identical on every rank
     i64 cap_veh, cap_ent, cap_ptr, cap_pst;
     i64 o_hdr, o_vehoff, o_kind, o_nfeas, o_cost, o_delay, o_toff, o_soff, o_treq, o_scode, bytes;
+    i64 o_cnt;            // int32 [3][cap_veh]: entries / trip requests / stops of each local vehicle (so readers need no dependent loads)
 };
 struct GSeg { const char* src; i64 dst_off; i64 bytes; };
 struct GPush { GSeg seg[10]; int n; };
@@ -172,6 +173,16 @@ k_gp_push_bulk(GPush P, GPoolLayout L, GSlotLayout S, i64 o_stage, GPoolPeers pe
                 for (i64 x = done + tid * 4; x < bytes; x += nth * 4) *(int*)((char*)dst + x) = *(const int*)((const char*)src + x);
             }
         }
+        // per-vehicle (entries, trip requests, stops), so that the readers' prefix sums are plain array reads
+        const i64* vo = (const i64*)P.seg[1].src; const i64* toff = (const i64*)P.seg[6].src; const i64* soff = (const i64*)P.seg[7].src;
+        for (i64 u = tid; u < n_veh; u += nth) {
+            const i64 e0 = vo[u], e1 = vo[u + 1];
+            const int ce = (int)(e1 - e0), ct = (int)(toff[e1] - toff[e0]), cs = (int)(soff[e1] - soff[e0]);
+            for (int d = 0; d < peers.world; d++) {
+                int* cnt = (int*)(peers.base[d] + o_stage + (i64)peers.rank * S.bytes + S.o_cnt);
+                cnt[u] = ce; cnt[S.cap_veh + u] = ct; cnt[2 * S.cap_veh + u] = cs;
+            }
+        }
     }
     __threadfence_system();
     __syncthreads();
@@ -190,56 +201,82 @@ struct InStagedVeh {        // counts of global vehicle v read from the staged s
         const char* slot = stage + (v % world) * S.bytes;
         const i64 u = v / world;
         if (((const i64*)(slot + S.o_hdr))[0] <= u) return 0;        // slot unusable (its rank overflowed) or short
-        const i64* vo = (const i64*)(slot + S.o_vehoff);
-        const i64 e0 = vo[u], e1 = vo[u + 1];
-        if (comp == 0) return e1 - e0;
-        const i64* off = (const i64*)(slot + (comp == 1 ? S.o_toff : S.o_soff));
-        return off[e1] - off[e0];
+        return ((const int*)(slot + S.o_cnt))[comp * S.cap_veh + u];
     }
 };
 
-// one warp per GLOBAL vehicle: staged slice of its rank -> my vehicle-major pool (all local memory)
+// Staged slices -> my vehicle-major pool (all local memory).  One warp per 32 consecutive GLOBAL entries: a lane
+// finds its entry's vehicle by binary search in the global entry offsets, copies the fixed fields and rebases the
+// two CSR offsets; the trip requests and stop codes of the 32 entries are one contiguous destination range, copied
+// by the whole warp (each element finds its entry among the lanes by a shuffle search).  No per-vehicle loops: a
+// vehicle with thousands of entries costs what its entries cost.
 __global__ void __launch_bounds__(256)
 k_gp_merge(const char* __restrict__ stage, GSlotLayout S, char* __restrict__ B, GPoolLayout L, int world,
            const i64* __restrict__ goff_e, const i64* __restrict__ goff_t, const i64* __restrict__ goff_s,
            const i64* __restrict__ totals, int n_veh_total, unsigned long long* err) {
     const int lane = threadIdx.x & 31;
-    const int nwarps = gridDim.x * (blockDim.x >> 5);
+    const i64 nwarps = (i64)gridDim.x * (blockDim.x >> 5);
     const bool fits = totals[0] <= L.cap_ent && totals[1] <= L.cap_ptr && totals[2] <= L.cap_pst;
     if (!fits) { if (blockIdx.x == 0 && threadIdx.x == 0) atomicOr(err, 1ull); return; }
     for (int r = 0; r < world; r++)
         if (((const i64*)(stage + (i64)r * S.bytes + S.o_hdr))[0] < 0) { if (blockIdx.x == 0 && threadIdx.x == 0) atomicOr(err, 1ull); return; }
-    if (blockIdx.x == 0 && threadIdx.x < 3) ((i64*)(B + L.o_hdr))[threadIdx.x] = totals[threadIdx.x];
     int* g_veh = (int*)(B + L.o_veh); int* g_kind = (int*)(B + L.o_kind); int* g_nfeas = (int*)(B + L.o_nfeas);
     double* g_cost = (double*)(B + L.o_cost); double* g_delay = (double*)(B + L.o_delay);
     i64* g_toff = (i64*)(B + L.o_toff); i64* g_soff = (i64*)(B + L.o_soff);
     int* g_treq = (int*)(B + L.o_treq); int* g_scode = (int*)(B + L.o_scode);
-    for (int v = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); v < n_veh_total; v += nwarps) {
-        const char* slot = stage + (i64)(v % world) * S.bytes;
-        const i64 u = v / world;
-        const i64* vo = (const i64*)(slot + S.o_vehoff);
-        const int* s_kind = (const int*)(slot + S.o_kind); const int* s_nfeas = (const int*)(slot + S.o_nfeas);
-        const double* s_cost = (const double*)(slot + S.o_cost); const double* s_delay = (const double*)(slot + S.o_delay);
-        const i64* s_toff = (const i64*)(slot + S.o_toff); const i64* s_soff = (const i64*)(slot + S.o_soff);
-        const int* s_treq = (const int*)(slot + S.o_treq); const int* s_scode = (const int*)(slot + S.o_scode);
-        const i64 e0 = vo[u], e1 = vo[u + 1];
-        const i64 E0 = goff_e[v], T0 = goff_t[v], S0 = goff_s[v];
-        const i64 t0 = s_toff[e0], s0 = s_soff[e0];
-        const i64 nt = s_toff[e1] - t0, ns = s_soff[e1] - s0;
-        for (i64 e = e0 + lane; e < e1; e += 32) {
-            const i64 E = E0 + (e - e0);
-            g_veh[E] = v; g_kind[E] = s_kind[e]; g_nfeas[E] = s_nfeas[e]; g_cost[E] = s_cost[e]; g_delay[E] = s_delay[e];
-            g_toff[E] = T0 + (s_toff[e] - t0); g_soff[E] = S0 + (s_soff[e] - s0);
+    const i64 n_ent = totals[0];
+    if (blockIdx.x == 0 && threadIdx.x < 3) ((i64*)(B + L.o_hdr))[threadIdx.x] = totals[threadIdx.x];
+    if (blockIdx.x == 0 && threadIdx.x == 0) { g_toff[n_ent] = totals[1]; g_soff[n_ent] = totals[2]; }
+    for (i64 E0 = ((i64)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * 32; E0 < n_ent; E0 += nwarps * 32) {
+        const i64 E = E0 + lane;
+        const bool valid = E < n_ent;
+        i64 dt = 0, ds = 0;                 // destination of the entry's trip requests / stop codes
+        int lt = 0, lsc = 0;                // their lengths
+        const int* pt = nullptr; const int* ps = nullptr;
+        if (valid) {
+            int a = 0, b = n_veh_total;     // last vehicle whose first entry is <= E (vehicles without entries share their successor's offset)
+            while (b - a > 1) { const int m = (a + b) >> 1; if (goff_e[m] <= E) a = m; else b = m; }
+            const int v = a;
+            const char* slot = stage + (i64)(v % world) * S.bytes;
+            const i64 u = v / world;
+            const i64* s_toff = (const i64*)(slot + S.o_toff); const i64* s_soff = (const i64*)(slot + S.o_soff);
+            const i64 e0 = ((const i64*)(slot + S.o_vehoff))[u];
+            const i64 e = e0 + (E - goff_e[v]);
+            const i64 t0 = s_toff[e0], s0 = s_soff[e0], te = s_toff[e], se = s_soff[e];
+            lt = (int)(s_toff[e + 1] - te); lsc = (int)(s_soff[e + 1] - se);
+            dt = goff_t[v] + (te - t0); ds = goff_s[v] + (se - s0);
+            pt = (const int*)(slot + S.o_treq) + te; ps = (const int*)(slot + S.o_scode) + se;
+            g_veh[E] = v; g_kind[E] = ((const int*)(slot + S.o_kind))[e]; g_nfeas[E] = ((const int*)(slot + S.o_nfeas))[e];
+            g_cost[E] = ((const double*)(slot + S.o_cost))[e]; g_delay[E] = ((const double*)(slot + S.o_delay))[e];
+            g_toff[E] = dt; g_soff[E] = ds;
         }
-        for (i64 x = lane; x < nt; x += 32) g_treq[T0 + x] = s_treq[t0 + x];
-        for (i64 x = lane; x < ns; x += 32) g_scode[S0 + x] = s_scode[s0 + x];
-        if (v == n_veh_total - 1 && lane == 0) { g_toff[totals[0]] = totals[1]; g_soff[totals[0]] = totals[2]; }
+#pragma unroll
+        for (int pass = 0; pass < 2; pass++) {
+            const i64 d0 = pass ? ds : dt;
+            const int len = pass ? lsc : lt;
+            const int* src = pass ? ps : pt;
+            int* dst = pass ? g_scode : g_treq;
+            const i64 first = __shfl_sync(FULL, d0, 0);
+            const int n_valid = __popc(__ballot_sync(FULL, valid));
+            const i64 end = __shfl_sync(FULL, d0 + len, n_valid - 1);
+            const int rel = valid ? (int)(d0 - first) : 0x7fffffff;          // monotone over the lanes
+            const int n = (int)(end - first);
+            for (int x0 = 0; x0 < n; x0 += 32) {
+                const int x = x0 + lane;
+                int own = 0;                                                  // last lane whose range starts at or before x
+#pragma unroll
+                for (int h = 16; h; h >>= 1) { const int r = __shfl_sync(FULL, rel, own + h); if (r <= x) own += h; }
+                const int* sp = (const int*)__shfl_sync(FULL, (unsigned long long)src, own);
+                const int r0 = __shfl_sync(FULL, rel, own);
+                if (x < n) dst[first + x] = sp[x - r0];
+            }
+        }
     }
 }
 
-
 // all three prefix sums (entries, trip requests, stops) over the global vehicle order in ONE single-block launch
-// (a fleet has at most a few 10^4 vehicles): thread = contiguous range of vehicles
+// (a fleet has at most a few 10^4 vehicles): thread = contiguous range of vehicles; the counts are plain arrays
+// every rank pushed with its slice
 __global__ void __launch_bounds__(1024)
 k_gp_offsets(const char* __restrict__ stage, GSlotLayout S, int world, int n_total, i64* __restrict__ goff_e, i64* __restrict__ goff_t,
              i64* __restrict__ goff_s, i64* __restrict__ totals) {
@@ -272,4 +309,5 @@ k_gp_offsets(const char* __restrict__ stage, GSlotLayout S, int world, int n_tot
         goff_e[v] = run[0]; goff_t[v] = run[1]; goff_s[v] = run[2];
         for (int c = 0; c < 3; c++) run[c] += InStagedVeh{stage, S, world, c, n_total}(v);
     }
+    if (threadIdx.x == 1023) { goff_e[n_total] = run[0]; goff_t[n_total] = run[1]; goff_s[n_total] = run[2]; }
 }

@@ -72,3 +72,41 @@ def test_two_ranks_scatter_over_peer_memory(tmp_path):
         ok = int(np.load(tmp_path / f"ok{r}.npy")[0])
         why = (tmp_path / f"why{r}.txt").read_text() if not ok else ""
         assert ok, f"rank {r}: {why}"
+
+
+def _single_rank_worker(rank, world, port, out_dir):
+    sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "oracle")); sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"; os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    import oracle
+    from amod_b200 import dist as adist, marshal, synth
+    from amod_b200.pool import PoolBuilder
+    torch.cuda.set_device(0)
+    dev = torch.device("cuda", 0)
+    tt = synth.make_road_graph(900, seed=4).tt
+    b = PoolBuilder(tt, device=0)
+    ok, why, pp = True, "", None
+    for seed in (5, 6, 7):
+        ep = synth.random_epoch(tt, n_veh=157, n_pending=60, cap=4, mode=marshal.MODE_OSP, seed=seed, wait_sec=300, near=True, T=4000)
+        ref = oracle.osp_build(ep, tt)
+        b.build(ep)
+        if pp is None:
+            pp = adist.PeerPool(b, 1, 0, ep.n_veh, 4 * ref.n_entries, 4 * ref.trip_req.size + 64, 4 * ref.sche_code.size + 64, dev)
+        pp.fused = True          # push -> flags -> offsets -> merge; with one rank no kernel waits on another process
+        pp.assemble()
+        o, w = marshal.pools_equal(pp.fetch(), ref, rtol=0.0, check_kind=True)
+        ok &= o
+        why = why or w
+    np.save(os.path.join(out_dir, "ok.npy"), np.array([int(ok)]))
+    if not ok:
+        open(os.path.join(out_dir, "why.txt"), "w").write(why)
+    dist.destroy_process_group()
+
+
+def test_flag_based_assembly_kernels_with_one_rank(tmp_path):
+    """The NVLink assembly path (bulk push, epoch flags, offsets, entry-parallel merge) run by a single rank on one
+    GPU: the same kernels bench.py uses at N > 1, checked against the oracle's full pool."""
+    mp.spawn(_single_rank_worker, args=(1, _free_port(), str(tmp_path)), nprocs=1, join=True)
+    ok = int(np.load(tmp_path / "ok.npy")[0])
+    assert ok, (tmp_path / "why.txt").read_text() if not ok else ""
