@@ -944,34 +944,30 @@ extern "C" int amod_gpool_assemble(amod_ctx* ctx, int32_t n_veh_total) {
     const bool prof = getenv("AMOD_GP_PROF") != nullptr;
     auto mark = [&](int i) { if (prof) cudaEventRecord(get_event(ctx, 64 + i), st); };
     mark(0);
-    if (epoch > 1) k_gp_wait<<<1, 32, 0, st>>>(ctx->gp_base, L, world, 1, epoch - 1, err);
-    mark(1);
     GPush P; memset(&P, 0, sizeof P);
     const void* srcs[10] = {nullptr, ctx->veh_off.p, ctx->ent_kind.p, ctx->ent_nfeas.p, ctx->ent_cost.p, ctx->ent_delay.p, ctx->trip_off.p,
                             ctx->sche_off.p, ctx->trip_req.p, ctx->sche_code.p};
     const i64 dsts[10] = {S.o_hdr, S.o_vehoff, S.o_kind, S.o_nfeas, S.o_cost, S.o_delay, S.o_toff, S.o_soff, S.o_treq, S.o_scode};
     for (int g = 0; g < 10; g++) { P.seg[g].src = (const char*)srcs[g]; P.seg[g].dst_off = dsts[g]; P.seg[g].bytes = 0; }
     P.n = 10;
+    // three launches: (wait for last epoch's readers,) push my slice + flag | wait for all slices, global offsets | merge + "read" flag
     k_gp_push_bulk<<<ctx->n_sm * 2, 256, 0, st>>>(P, L, S, ctx->gp_o_stage, ctx->gp_peers, ctx->d_epoch.as<DEpoch>(), ctx->ctl.as<Control>(),
-                                                epoch, ticket, err);
-    mark(2);
-    k_gp_wait<<<1, 32, 0, st>>>(ctx->gp_base, L, world, 0, epoch, err);
-    mark(3);
+                                                epoch, ticket, err, ctx->gp_base);
+    mark(1);
     const char* stage = ctx->gp_base + ctx->gp_o_stage;
-    k_gp_offsets<<<1, 1024, 0, st>>>(stage, S, world, n_veh_total, off, off + stride, off + 2 * stride, tot);
-    mark(4);
-    k_gp_merge<<<ctx->n_sm * 8, 256, 0, st>>>(stage, S, ctx->gp_base, L, world, off, off + stride, off + 2 * stride, tot, n_veh_total, err);
-    mark(5);
-    k_gp_signal_done<<<1, 32, 0, st>>>(L, ctx->gp_peers, epoch);      // "I have read everyone's slot of this epoch"
-    mark(6);
+    k_gp_offsets<<<1, 1024, 0, st>>>(stage, S, world, n_veh_total, off, off + stride, off + 2 * stride, tot, ctx->gp_base, L, epoch, err);
+    mark(2);
+    k_gp_merge<<<ctx->n_sm * 8, 256, 0, st>>>(stage, S, ctx->gp_base, L, world, off, off + stride, off + 2 * stride, tot, n_veh_total, err,
+                                              ctx->gp_peers, epoch, ticket + 1);
+    mark(3);
     i64 h[4];
     CK(cudaMemcpyAsync(h, tot, sizeof h, cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
     CK(cudaGetLastError());
     if (prof && (epoch % 16) == 0) {
-        float x[6];
-        for (int i = 0; i < 6; i++) cudaEventElapsedTime(&x[i], ctx->ev_pool[64 + i], ctx->ev_pool[64 + i + 1]);
-        fprintf(stderr, "[gp rank %d] wait_prev %.3f push %.3f wait_all %.3f offsets %.3f merge %.3f signal %.3f ms\n", ctx->gp_peers.rank, x[0], x[1], x[2], x[3], x[4], x[5]);
+        float x[3];
+        for (int i = 0; i < 3; i++) cudaEventElapsedTime(&x[i], ctx->ev_pool[64 + i], ctx->ev_pool[64 + i + 1]);
+        fprintf(stderr, "[gp rank %d] wait_prev+push %.3f wait_all+offsets %.3f merge+signal %.3f ms\n", ctx->gp_peers.rank, x[0], x[1], x[2]);
     }
     if (h[3] & 2) return ctx->fail(AMOD_E_CUDA, "peer assembly timed out waiting for another rank");
     if (h[3] & 1) return ctx->fail(AMOD_E_CAPACITY, "global pool or staging slot too small (need %lld entries, %lld trip requests, %lld stops)", h[0], h[1], h[2]);

@@ -84,53 +84,20 @@ __device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long
     return v;
 }
 
-// K1: my per-vehicle counts into every rank's counts table; the last block to finish raises my flag on every rank
-__global__ void __launch_bounds__(256)
-k_gp_push_counts(const DEpoch* __restrict__ epp, const i64* __restrict__ veh_off, PoolBufs pb, GPoolLayout L, GPoolPeers peers,
-                 int vmax, unsigned long long epoch, unsigned* ticket) {
-    const int n = epp->n_veh;
-    for (int v = blockIdx.x * blockDim.x + threadIdx.x; v < vmax; v += gridDim.x * blockDim.x) {
-        int c0 = 0, c1 = 0, c2 = 0;
-        if (v < n) {
-            const i64 e0 = veh_off[v], e1 = veh_off[v + 1];
-            c0 = (int)(e1 - e0); c1 = (int)(pb.trip_off[e1] - pb.trip_off[e0]); c2 = (int)(pb.sche_off[e1] - pb.sche_off[e0]);
+// Wait until every rank's flag `which` in MY pool has reached `epoch` (bounded spin); call with a whole block,
+// threads < world poll one flag each.  which 0 = "slice pushed", 1 = "slice read".
+__device__ __forceinline__ void gp_wait_flags(const char* __restrict__ my_base, const GPoolLayout& L, int world, int which,
+                                              unsigned long long epoch, unsigned long long* err) {
+    if ((int)threadIdx.x < world) {
+        const unsigned long long* f = (const unsigned long long*)(my_base + L.o_flags) + which * GPOOL_MAX_WORLD + threadIdx.x;
+        const long long t0 = clock64();
+        while (ld_acquire_sys(f) < epoch) {
+            if (clock64() - t0 > 6000000000ll) { atomicOr(err, 2ull); break; }   // ~3 s: a rank never arrived
+            __nanosleep(200);
         }
-        for (int d = 0; d < peers.world; d++) {
-            int* dst = (int*)(peers.base[d] + L.o_counts) + ((i64)peers.rank * vmax + v) * 3;
-            dst[0] = c0; dst[1] = c1; dst[2] = c2;
-        }
+        __threadfence_system();
     }
-    __threadfence_system();
     __syncthreads();
-    if (threadIdx.x == 0 && atomicAdd(ticket, 1u) == gridDim.x - 1) {
-        *ticket = 0;
-        __threadfence_system();
-        for (int d = 0; d < peers.world; d++)
-            st_release_sys((unsigned long long*)(peers.base[d] + L.o_flags) + peers.rank, epoch);
-    }
-}
-
-// K2 / K4: wait until every rank's flag in MY pool has reached `epoch` (bounded spin)
-__global__ void k_gp_wait(const char* __restrict__ my_base, GPoolLayout L, int world, int which, unsigned long long epoch,
-                          unsigned long long* err) {
-    const int r = threadIdx.x;
-    if (r >= world) return;
-    const unsigned long long* f = (const unsigned long long*)(my_base + L.o_flags) + which * GPOOL_MAX_WORLD + r;
-    const long long t0 = clock64();
-    while (ld_acquire_sys(f) < epoch) {
-        if (clock64() - t0 > 6000000000ll) { atomicOr(err, 2ull); break; }   // ~3 s: a rank never arrived
-        __nanosleep(200);
-    }
-    __threadfence_system();
-}
-
-// K3 epilogue: raise my "payload written" flag on every rank (after all scatter blocks have fenced)
-__global__ void k_gp_signal_done(GPoolLayout L, GPoolPeers peers, unsigned long long epoch) {
-    if (threadIdx.x == 0) {
-        __threadfence_system();
-        for (int d = 0; d < peers.world; d++)
-            st_release_sys((unsigned long long*)(peers.base[d] + L.o_flags) + GPOOL_MAX_WORLD + peers.rank, epoch);
-    }
 }
 
 
@@ -149,7 +116,10 @@ struct GPush { GSeg seg[10]; int n; };
 
 __global__ void __launch_bounds__(256)
 k_gp_push_bulk(GPush P, GPoolLayout L, GSlotLayout S, i64 o_stage, GPoolPeers peers, const DEpoch* __restrict__ epp,
-               const Control* __restrict__ ctl, unsigned long long epoch, unsigned* ticket, unsigned long long* err) {
+               const Control* __restrict__ ctl, unsigned long long epoch, unsigned* ticket, unsigned long long* err,
+               const char* __restrict__ my_base) {
+    // every peer must have finished reading my slot of the previous epoch before I overwrite it
+    if (epoch > 1) gp_wait_flags(my_base, L, peers.world, 1, epoch - 1, err);
     const i64 n_veh = epp->n_veh, n_ent = ctl->n_ent, n_ptr = ctl->n_ptr, n_pst = ctl->n_pst;
     const bool fits = n_veh <= S.cap_veh && n_ent <= S.cap_ent && n_ptr <= S.cap_ptr && n_pst <= S.cap_pst;
     if (!fits && blockIdx.x == 0 && threadIdx.x == 0) atomicOr(err, 1ull);
@@ -213,18 +183,18 @@ struct InStagedVeh {        // counts of global vehicle v read from the staged s
 __global__ void __launch_bounds__(256)
 k_gp_merge(const char* __restrict__ stage, GSlotLayout S, char* __restrict__ B, GPoolLayout L, int world,
            const i64* __restrict__ goff_e, const i64* __restrict__ goff_t, const i64* __restrict__ goff_s,
-           const i64* __restrict__ totals, int n_veh_total, unsigned long long* err) {
+           const i64* __restrict__ totals, int n_veh_total, unsigned long long* err, GPoolPeers peers, unsigned long long epoch,
+           unsigned* ticket) {
     const int lane = threadIdx.x & 31;
     const i64 nwarps = (i64)gridDim.x * (blockDim.x >> 5);
-    const bool fits = totals[0] <= L.cap_ent && totals[1] <= L.cap_ptr && totals[2] <= L.cap_pst;
-    if (!fits) { if (blockIdx.x == 0 && threadIdx.x == 0) atomicOr(err, 1ull); return; }
-    for (int r = 0; r < world; r++)
-        if (((const i64*)(stage + (i64)r * S.bytes + S.o_hdr))[0] < 0) { if (blockIdx.x == 0 && threadIdx.x == 0) atomicOr(err, 1ull); return; }
+    bool usable = totals[0] <= L.cap_ent && totals[1] <= L.cap_ptr && totals[2] <= L.cap_pst;
+    for (int r = 0; r < world; r++) usable &= ((const i64*)(stage + (i64)r * S.bytes + S.o_hdr))[0] >= 0;
+    if (!usable && blockIdx.x == 0 && threadIdx.x == 0) atomicOr(err, 1ull);
     int* g_veh = (int*)(B + L.o_veh); int* g_kind = (int*)(B + L.o_kind); int* g_nfeas = (int*)(B + L.o_nfeas);
     double* g_cost = (double*)(B + L.o_cost); double* g_delay = (double*)(B + L.o_delay);
     i64* g_toff = (i64*)(B + L.o_toff); i64* g_soff = (i64*)(B + L.o_soff);
     int* g_treq = (int*)(B + L.o_treq); int* g_scode = (int*)(B + L.o_scode);
-    const i64 n_ent = totals[0];
+    const i64 n_ent = usable ? totals[0] : 0;
     if (blockIdx.x == 0 && threadIdx.x < 3) ((i64*)(B + L.o_hdr))[threadIdx.x] = totals[threadIdx.x];
     if (blockIdx.x == 0 && threadIdx.x == 0) { g_toff[n_ent] = totals[1]; g_soff[n_ent] = totals[2]; }
     for (i64 E0 = ((i64)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * 32; E0 < n_ent; E0 += nwarps * 32) {
@@ -272,6 +242,17 @@ k_gp_merge(const char* __restrict__ stage, GSlotLayout S, char* __restrict__ B, 
             }
         }
     }
+    // "I have read everyone's slot of this epoch": the last block to finish raises my flag on every rank
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        if (atomicAdd(ticket, 1u) == gridDim.x - 1) {
+            *ticket = 0;
+            __threadfence_system();
+            for (int d = 0; d < peers.world; d++)
+                st_release_sys((unsigned long long*)(peers.base[d] + L.o_flags) + GPOOL_MAX_WORLD + peers.rank, epoch);
+        }
+    }
 }
 
 // all three prefix sums (entries, trip requests, stops) over the global vehicle order in ONE single-block launch
@@ -279,8 +260,10 @@ k_gp_merge(const char* __restrict__ stage, GSlotLayout S, char* __restrict__ B, 
 // every rank pushed with its slice
 __global__ void __launch_bounds__(1024)
 k_gp_offsets(const char* __restrict__ stage, GSlotLayout S, int world, int n_total, i64* __restrict__ goff_e, i64* __restrict__ goff_t,
-             i64* __restrict__ goff_s, i64* __restrict__ totals) {
+             i64* __restrict__ goff_s, i64* __restrict__ totals, const char* __restrict__ my_base, GPoolLayout L, unsigned long long epoch,
+             unsigned long long* err) {
     __shared__ i64 sm[3][32];
+    gp_wait_flags(my_base, L, world, 0, epoch, err);       // every rank's slice of this epoch has landed in my memory
     const int per = (n_total + 1023) / 1024;
     const int v0 = min(n_total, (int)threadIdx.x * per), v1 = min(n_total, v0 + per);
     i64 a[3] = {0, 0, 0};
