@@ -74,23 +74,28 @@ class Epoch:
         T, cap, mode = (int(x) for x in d[prefix + "scalars"])
         return cls(T=T, cap=cap, mode=mode, **{f: d[prefix + f] for f in cls.FIELDS})
 
-    def shard(self, rank: int, world: int) -> tuple["Epoch", np.ndarray]:
-        """Vehicles rank, rank+world, ... (interleaved: vehicle work is heavy-tailed and
-        spatially correlated with fleet order, platform.py:51-55).  Requests are replicated."""
-        sel = np.arange(rank, self.n_veh, world, dtype=np.int64)
+    def take(self, sel: np.ndarray) -> "Epoch":
+        """The epoch restricted to vehicles `sel` (in that order).  Requests are kept as they are."""
+        sel = np.asarray(sel, dtype=np.int64)
         lens = np.diff(self.veh_sche_off)[sel]
         off = np.zeros(sel.size + 1, dtype=np.int32)
         np.cumsum(lens, out=off[1:])
-        idx = np.concatenate([np.arange(self.veh_sche_off[v], self.veh_sche_off[v + 1]) for v in sel]) \
-            if sel.size else np.zeros(0, dtype=np.int64)
-        idx = idx.astype(np.int64)
+        # stop indices of the selected vehicles, vehicle by vehicle (vectorised ragged gather)
+        starts = np.repeat(self.veh_sche_off[:-1][sel].astype(np.int64) - off[:-1], lens)
+        idx = starts + np.arange(int(off[-1]), dtype=np.int64)
         kw = {f: getattr(self, f) for f in self.FIELDS}
         for f in ("veh_nid", "veh_t_to_nid", "veh_load", "veh_status", "veh_reb_node", "veh_reb_ddl"):
             kw[f] = kw[f][sel]
         kw["veh_sche_off"] = off
         kw["sche_code"] = self.sche_code[idx]
         kw["sche_onboard"] = self.sche_onboard[idx]
-        return Epoch(T=self.T, cap=self.cap, mode=self.mode, **kw), sel
+        return Epoch(T=self.T, cap=self.cap, mode=self.mode, **kw)
+
+    def shard(self, rank: int, world: int) -> tuple["Epoch", np.ndarray]:
+        """Vehicles rank, rank+world, ... (interleaved: vehicle work is heavy-tailed and
+        spatially correlated with fleet order, platform.py:51-55).  Requests are replicated."""
+        sel = np.arange(rank, self.n_veh, world, dtype=np.int64)
+        return self.take(sel), sel
 
 
 def marshal_epoch(reqs, vehs, search_rids, T: int, cap: int, mode: int, check: bool = True):

@@ -52,14 +52,17 @@ def load_snapshots(tag="cfg2"):
 
 
 def tile_fleet(ep, n):
-    """Fleet of n x V vehicles: the snapshot's fleet repeated n times (same requests)."""
+    """Fleet of n x V vehicles on the same requests: the snapshot's fleet n times, every further copy in a
+    different (seeded) vehicle order, so that an interleaved rank slice is a sample of the whole fleet and not
+    the same V/n vehicles n times over."""
     if n == 1:
         return ep
     from amod_b200.marshal import Epoch
+    parts = [ep] + [ep.take(np.random.default_rng(1000 + c).permutation(ep.n_veh)) for c in range(1, n)]
     kw = {f: getattr(ep, f) for f in Epoch.FIELDS}
     for f in ("veh_nid", "veh_t_to_nid", "veh_load", "veh_status", "veh_reb_node", "veh_reb_ddl", "sche_code", "sche_onboard"):
-        kw[f] = np.tile(kw[f], n)
-    lens = np.tile(np.diff(ep.veh_sche_off), n)
+        kw[f] = np.concatenate([getattr(p, f) for p in parts])
+    lens = np.concatenate([np.diff(p.veh_sche_off) for p in parts])
     off = np.zeros(lens.size + 1, dtype=np.int32)
     np.cumsum(lens, out=off[1:])
     kw["veh_sche_off"] = off
