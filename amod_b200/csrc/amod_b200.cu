@@ -130,21 +130,12 @@ static int dispatch_tt(amod_ctx* ctx, F&& f) {
 static inline int nblk(i64 n, int per) { return (int)((n + per - 1) / per); }
 
 // exclusive scan (length and result sizes live on the device; no synchronisation)
-template <typename InA, typename FinA, typename InB, typename FinB>
-static void scan_dev2(amod_ctx* ctx, InA a, i64* outa, FinA fa, InB b, i64* outb, FinB fb) {
-    const int g = (ctx->n_sm / 2) * 2;
-    k_scan2_a<InA, InB><<<g, SCAN_THREADS, 0, ctx->stream>>>(a, b, ctx->partial.as<i64>());
-    k_scan2_b<InA, FinA, InB, FinB><<<g, SCAN_THREADS, 0, ctx->stream>>>(a, fa, outa, b, fb, outb, ctx->partial.as<i64>());
-    ctx->n_launches += 2;
-}
-
 template <typename In, typename Fin>
-static void scan_dev(amod_ctx* ctx, In in, i64* out, Fin fin, bool on_side = false) {
+static void scan_dev(amod_ctx* ctx, In in, i64* out, Fin fin) {
     const int g = ctx->n_sm;
-    cudaStream_t st = on_side ? ctx->side : ctx->stream;
-    i64* partial = ctx->partial.as<i64>() + (on_side ? g + 1 : 0);     // one set of block partials per graph branch
-    k_scan_a<In><<<g, SCAN_THREADS, 0, st>>>(in, partial);
-    k_scan_b<In, Fin><<<g, SCAN_THREADS, 0, st>>>(in, partial, out, fin);
+    i64* partial = ctx->partial.as<i64>();
+    k_scan_a<In><<<g, SCAN_THREADS, 0, ctx->stream>>>(in, partial);
+    k_scan_b<In, Fin><<<g, SCAN_THREADS, 0, ctx->stream>>>(in, partial, out, fin);
     ctx->n_launches += 2;
 }
 

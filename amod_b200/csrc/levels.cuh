@@ -319,11 +319,6 @@ struct InMajorPacked {       // scan input over the majors of the screen
     __device__ __forceinline__ i64 size() const { return ep->mode == AMOD_MODE_SBA ? ep->n_search : ep->n_veh; }
     __device__ __forceinline__ i64 operator()(i64 i) const { return p[i]; }
 };
-struct InRowCntPacked {      // over the trips of a level: row t spawns row_cnt[t] tasks of nfeas[t] rows each
-    const int* row_cnt; const int* nfeas; const int* n_ptr; const Control* ctl;
-    __device__ __forceinline__ i64 size() const { return ctl->overflow ? 0 : (i64)*n_ptr; }
-    __device__ __forceinline__ i64 operator()(i64 t) const { const i64 c = row_cnt[t]; return c | ((c * nfeas[t]) << 32); }
-};
 // finisher: task count of buffer `which`, row count and chunk count (G rows per chunk) of the next level
 struct FinTasksRows {
     Control* ctl; int which; i64 cap_tasks, cap_rows, cap_chunks; int G;
@@ -546,7 +541,7 @@ __global__ void k_compact_trips(const Control* __restrict__ ctl, int which, cons
 // List order of feasible_sches (scheduling.py:31-36): a schedule whose cost is strictly below every
 // earlier one is inserted at the front, the others are appended.  From the encounter-order costs:
 // order = [records, newest first] + [non-records in encounter order]; order[0] is the best schedule
-// (first-encountered minimum).  One warp per trip.  Also fills veh_start (trips are vehicle-major).
+// (first-encountered minimum).  One warp per trip.
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32)
 k_classify(Control* __restrict__ ctl, Level cur, int heavy_min, int* __restrict__ heavy_list) {

@@ -1,6 +1,7 @@
 // scan.cuh — device-wide exclusive prefix sum whose length lives in device memory.
-// Two launches on a fixed grid: (a) every block reduces its contiguous segment, (b) every block
-// sums the partials before it and scans its segment.  The input is a functor, so flags derived
+// Two phases on a fixed grid: (a) every block reduces its contiguous segment, (b) every block sums the
+// partials before it and scans its segment.  Phase (a) is a launch of its own only where no producer kernel
+// can leave the block sums (scan_seg_len below).  The input is a functor, so flags derived
 // from other arrays are scanned without being materialised; a finishing functor receives the
 // total on one thread (it stores the count, checks the capacity of whatever the scan sizes).
 #pragma once
@@ -94,15 +95,8 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_scan_b(In in, const i64* __res
     scan_phase_b(in, blockIdx.x, gridDim.x, partial, out, fin, smem);
 }
 
-// two independent scans in one launch pair: the first half of the grid does A, the second half B
-template <typename InA, typename InB>
-__global__ void __launch_bounds__(SCAN_THREADS) k_scan2_a(InA a, InB b, i64* __restrict__ partial) {
-    __shared__ i64 smem[SCAN_THREADS / 32 + 1];
-    const int half = gridDim.x >> 1;
-    if ((int)blockIdx.x < half) scan_phase_a(a, blockIdx.x, half, partial, smem);
-    else scan_phase_a(b, blockIdx.x - half, half, partial + half, smem);
-}
-
+// two independent scans in one launch (their block sums come from the producer kernel): the first half of the
+// grid does A, the second half B
 template <typename InA, typename FinA, typename InB, typename FinB>
 __global__ void __launch_bounds__(SCAN_THREADS) k_scan2_b(InA a, FinA fa, i64* __restrict__ outa, InB b, FinB fb, i64* __restrict__ outb,
                                                           const i64* __restrict__ partial) {

@@ -112,3 +112,24 @@ def test_torch_merge_matches_numpy_merge():
     got = marshal.Pool(**{f: m[f].numpy() for f in marshal.Pool.FIELDS})
     ok, why = marshal.pools_equal(got, gold, check_kind=True)
     assert ok, why
+
+
+def test_take_reorders_vehicles_with_their_schedules():
+    """Epoch.take (used by shard and by bench.py's weak-scaling fleet): any vehicle order, schedules follow, and
+    building the permuted epoch gives the original pool with the vehicles renamed."""
+    tt, cases = load_golden("rand_real_osp_cap4")
+    ep = cases[0][0]
+    perm = np.random.default_rng(3).permutation(ep.n_veh)
+    pe = ep.take(perm)
+    assert pe.n_veh == ep.n_veh and pe.sche_code.size == ep.sche_code.size
+    for k in (0, ep.n_veh // 2, ep.n_veh - 1):
+        v = perm[k]
+        assert np.array_equal(pe.sche_code[pe.veh_sche_off[k]:pe.veh_sche_off[k + 1]],
+                              ep.sche_code[ep.veh_sche_off[v]:ep.veh_sche_off[v + 1]])
+        assert pe.veh_nid[k] == ep.veh_nid[v] and pe.veh_load[k] == ep.veh_load[v]
+    a, b = oracle.osp_build(ep, tt), oracle.osp_build(pe, tt)
+    assert a.n_entries == b.n_entries
+    # per-vehicle entry counts travel with the vehicles
+    ca = np.bincount(a.ent_veh, minlength=ep.n_veh)
+    cb = np.bincount(b.ent_veh, minlength=ep.n_veh)
+    assert np.array_equal(cb, ca[perm])
