@@ -15,7 +15,8 @@ from . import pool as _pool
 
 
 def install(mean_travel_time_table, dispatch_osp=None, dispatch_sba=None, platform=None, device: int = 0,
-            table_dtype=np.float32, use_device_delays: bool = True, greedy_on_gpu: bool = False) -> _pool.PoolBuilder:
+            table_dtype=np.float32, use_device_delays: bool = True, greedy_on_gpu: bool = False,
+            exact_assignment: bool = False) -> _pool.PoolBuilder:
     """`table_dtype=np.float32` is the north-star layout (67 MB, L2-resident) and is exact when the
     table's values are fp32-representable; pass np.float64 for bit-exact results on arbitrary tables."""
     tt = np.ascontiguousarray(mean_travel_time_table, dtype=table_dtype)
@@ -37,6 +38,13 @@ def install(mean_travel_time_table, dispatch_osp=None, dispatch_sba=None, platfo
             if mod is not None:
                 mod.ilp_assignment = ga           # dispatch_osp.py:62, dispatch_sba.py:23 look the name up in their own module
                 mod.greedy_assignment = b.greedy_assignment
+    if exact_assignment:              # the reference's ILP (ilp_assign.py:10-98) on HiGHS where Gurobi is absent; host-side consumer
+        if greedy_on_gpu:
+            raise ValueError("choose one assigner: greedy_on_gpu or exact_assignment")
+        from .assign_milp import milp_assignment
+        for mod in (dispatch_osp, dispatch_sba):
+            if mod is not None:
+                mod.ilp_assignment = milp_assignment
     if platform is not None:          # B3 was imported by name into the platform module (platform.py:9-11)
         platform.reposition_idle_vehicles_to_nearest_pending_orders = b.reposition_idle_vehicles_to_nearest_pending_orders
     return b

@@ -21,13 +21,13 @@ import ref_harness as rh  # noqa: E402
 pytestmark = pytest.mark.skipif(not rh.reference_available(), reason="reference tree not present")
 
 
-def _run(dispatcher: str, patched, q):
+def _run(dispatcher: str, patched, q, assigner: str = "greedy"):
     from amod_b200 import install as inst, marshal, pool as pool_mod, synth
     import oracle
     graph = synth.make_road_graph(400, seed=3, with_paths=True)
     t0 = 18 * 3600 + 30 * 60
     on, dn, tm = synth.make_request_stream(graph, 1500, t0, t0 + 40 * 60, seed=1, mean_trip_sec=420.0)
-    ref = rh.setup_reference(f"/tmp/amod_ref_dropin_{dispatcher}_{patched}", graph, on, dn, tm, fleet_size=30, capacity=4,
+    ref = rh.setup_reference(f"/tmp/amod_ref_dropin_{dispatcher}_{patched}_{assigner}", graph, on, dn, tm, fleet_size=30, capacity=4,
                              dispatcher=dispatcher, warmup_min=5, main_min=12, winddown_min=4)
     patched_tag = str(patched)
     # both runs must search exhaustively: disable the wall-clock cut-off of the unmodified seam as well
@@ -69,6 +69,10 @@ def _run(dispatcher: str, patched, q):
         ref.dispatch_osp.score_vt_pairs_with_num_of_orders_and_sche_cost = pool_mod.score_vt_pairs_with_num_of_orders_and_sche_cost
         ref.dispatch_sba.score_vt_pairs_with_num_of_orders_and_sche_cost = pool_mod.score_vt_pairs_with_num_of_orders_and_sche_cost
         ref.platform.reposition_idle_vehicles_to_nearest_pending_orders = b.reposition_idle_vehicles_to_nearest_pending_orders
+    if assigner == "milp":      # exact assignment on HiGHS in place of the Gurobi model (amod_b200/assign_milp.py)
+        from amod_b200.assign_milp import milp_assignment
+        ref.dispatch_osp.ilp_assignment = milp_assignment
+        ref.dispatch_sba.ilp_assignment = milp_assignment
     pf = rh.make_platform(ref)
     for e in range(0, pf.system_shutdown_time_sec, 30):
         pf.run_cycle(e)
@@ -94,3 +98,19 @@ def test_simulation_outcome_identical_with_seams_replaced(dispatcher):
         assert r0 == r1
         assert reqs0 == reqs1
         assert veh0 == veh1
+
+
+def test_simulation_outcome_identical_with_exact_assignment():
+    """OSP with the exact assignment model (HiGHS stand-in for the absent Gurobi): the replaced seams hand the
+    solver a bit-identical pool, so the simulated day is identical too."""
+    ctx = mp.get_context("spawn")
+    res = []
+    for patched in (False, True):
+        q = ctx.Queue()
+        p = ctx.Process(target=_run, args=("OSP", patched, q, "milp"))
+        p.start()
+        res.append(q.get(timeout=900))
+        p.join()
+    (r0, reqs0, veh0), (r1, reqs1, veh1) = res
+    assert len(reqs0) > 300 and r0[0] > 10
+    assert r0 == r1 and reqs0 == reqs1 and veh0 == veh1
