@@ -12,8 +12,10 @@ WOULD PERFORM IT; the kernels count it with the reference's early-exit semantics
 check the count against the oracle, so GPU and CPU arms share the numerator.
 
 N > 1 (torchrun, one rank per GPU): weak scaling — the fleet is N x 2,000 vehicles (the snapshot's
-fleet tiled N times against the same request set, BASELINE.json configs[3] at N=4), vehicles are
-interleaved over ranks, every rank builds its slice and an NCCL all-gather assembles the pool.
+fleet N times against the same request set, further copies in a seeded vehicle order; BASELINE.json
+configs[3] at N=4), vehicles are interleaved over ranks, every rank builds its slice and the
+vehicle-major pool is assembled on every rank over NVLink peer memory (amod_b200/dist.py PeerPool:
+bulk peer stores + epoch flags, no host-side collective in the timed region).
 """
 from __future__ import annotations
 

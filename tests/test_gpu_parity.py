@@ -322,3 +322,31 @@ def test_candidate_recompute_path(monkeypatch):
             ok, why = marshal.pools_equal(b.build_pool(ep), gold, rtol=0.0, check_kind=True)
             assert ok, f"{family}: {why}"
         b.close()
+
+
+def test_cuda_pool_at_cfg4_fleet_scale_and_sharded():
+    """BASELINE.json configs[3] scale: 8,000 vehicles (bench.py's weak-scaling fleet for N = 4), capacity 4.  The
+    whole-fleet pool is bit-exact against the oracle, and the four interleaved rank slices, built one after the
+    other on this GPU and merged vehicle-major on the host, give the same pool."""
+    import glob
+    import oracle
+    from conftest import ROOT
+    import bench
+    from amod_b200 import dist as adist
+    f = sorted(glob.glob(os.path.join(ROOT, "bench_data", "cfg2_epoch*.npz")))[2]
+    ep = bench.tile_fleet(marshal.Epoch.from_npz_dict(np.load(f), "ep_"), 4)
+    assert ep.n_veh == 8000
+    tt = _grid()
+    b = builder_for(tt)
+    ref = oracle.osp_build(ep, tt, n_threads=oracle.max_threads())
+    got = b.build_pool(ep)
+    ok, why = marshal.pools_equal(got, ref, rtol=0.0, check_kind=True)
+    assert ok, why
+    assert got.stats["n_evals"] == ref.stats["n_evals"]
+    parts = []
+    for rank in range(4):
+        sub, sel = ep.shard(rank, 4)
+        parts.append((b.build_pool(sub), sel))
+    merged = adist.merge_vehicle_major(parts, ep.n_veh)
+    ok, why = marshal.pools_equal(merged, ref, rtol=0.0, check_kind=True)
+    assert ok, why
