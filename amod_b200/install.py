@@ -25,11 +25,11 @@ def install(mean_travel_time_table, dispatch_osp=None, dispatch_sba=None, platfo
     b = _pool.PoolBuilder(tt, device=device)
     if dispatch_osp is not None:      # B1, dispatch_osp.py:48-51 looks the name up in its own module
         dispatch_osp.compute_candidate_veh_trip_pairs = b.compute_candidate_veh_trip_pairs
-        if use_device_delays or greedy_on_gpu:
+        if use_device_delays or greedy_on_gpu or exact_assignment:
             dispatch_osp.score_vt_pairs_with_num_of_orders_and_sche_cost = _pool.score_vt_pairs_with_num_of_orders_and_sche_cost
     if dispatch_sba is not None:      # B2, dispatch_sba.py:15
         dispatch_sba.compute_candidate_veh_req_pairs = b.compute_candidate_veh_req_pairs
-        if use_device_delays or greedy_on_gpu:
+        if use_device_delays or greedy_on_gpu or exact_assignment:
             dispatch_sba.score_vt_pairs_with_num_of_orders_and_sche_cost = _pool.score_vt_pairs_with_num_of_orders_and_sche_cost
     if greedy_on_gpu:                 # next row
         b.lazy_records = True         # only the selected pairs are ever materialised as Python records: the README-sanctioned greedy assigner (ilp_assign.py:101-130) on the device pool
@@ -42,6 +42,7 @@ def install(mean_travel_time_table, dispatch_osp=None, dispatch_sba=None, platfo
         if greedy_on_gpu:
             raise ValueError("choose one assigner: greedy_on_gpu or exact_assignment")
         from .assign_milp import milp_assignment
+        b.lazy_records = True         # the model is built from the pool arrays; only the selected pairs become Python records
         for mod in (dispatch_osp, dispatch_sba):
             if mod is not None:
                 mod.ilp_assignment = milp_assignment

@@ -98,7 +98,38 @@ class Epoch:
         return self.take(sel), sel
 
 
-def marshal_epoch(reqs, vehs, search_rids, T: int, cap: int, mode: int, check: bool = True):
+class ReqTable:
+    """Per-simulation table of the immutable request fields, filled the first time a request id is seen, so that
+    an epoch only reads the ~10^2 new request objects instead of all ~10^4 live ones.  Bound to one `reqs`
+    container (the platform's list, platform.py:60-65); a different container starts a new table."""
+
+    FIELDS = (("onid", np.int32), ("dnid", np.int32), ("Clp", np.float64), ("Cld", np.float64), ("Tr", np.float64), ("Ts", np.float64))
+
+    def __init__(self):
+        self._container = None
+        self._known = np.zeros(0, dtype=bool)
+        self._cols = [np.zeros(0, dtype=dt) for _f, dt in self.FIELDS]
+
+    def gather(self, reqs, rids: np.ndarray, req_objs: list):
+        if reqs is not self._container:
+            self.__init__()
+            self._container = reqs
+        top = int(rids[-1]) + 1 if rids.size else 0
+        if top > self._known.size:
+            n = max(top, 2 * self._known.size, 1024)
+            self._known = np.concatenate([self._known, np.zeros(n - self._known.size, dtype=bool)])
+            self._cols = [np.concatenate([c, np.zeros(n - c.size, dtype=c.dtype)]) for c in self._cols]
+        new = np.flatnonzero(~self._known[rids])
+        if new.size:
+            objs = [req_objs[k] for k in new.tolist()]
+            at = rids[new]
+            for c, (f, dt) in zip(self._cols, self.FIELDS):
+                c[at] = np.fromiter((getattr(r, f) for r in objs), dtype=dt, count=len(objs))
+            self._known[at] = True
+        return tuple(c[rids] for c in self._cols)
+
+
+def marshal_epoch(reqs, vehs, search_rids, T: int, cap: int, mode: int, check: bool = True, req_table: ReqTable | None = None):
     """Veh/Req objects -> Epoch.  `search_rids` is considered_rids (OSP, dispatch_osp.py:33-39)
     or new_received_rids (SBA, dispatch_sba.py:56).  Returns (epoch, req_objs) where
     req_objs[i] is the Req behind request index i.  One pass over the objects, the rest is numpy."""
@@ -119,12 +150,15 @@ def marshal_epoch(reqs, vehs, search_rids, T: int, cap: int, mode: int, check: b
     rids = np.unique(np.concatenate([search_arr, s_rid[~is_reb]]))
     req_objs = [reqs[r] for r in rids.tolist()]
     nr = len(req_objs)
-    req_onid = np.fromiter((r.onid for r in req_objs), dtype=np.int32, count=nr)
-    req_dnid = np.fromiter((r.dnid for r in req_objs), dtype=np.int32, count=nr)
-    req_clp = np.fromiter((r.Clp for r in req_objs), dtype=np.float64, count=nr)
-    req_cld = np.fromiter((r.Cld for r in req_objs), dtype=np.float64, count=nr)
-    req_tr = np.fromiter((r.Tr for r in req_objs), dtype=np.float64, count=nr)
-    req_ts = np.fromiter((r.Ts for r in req_objs), dtype=np.float64, count=nr)
+    if req_table is not None:       # a request's (onid, dnid, Clp, Cld, Tr, Ts) never change (request.py:25-41): read each object once
+        req_onid, req_dnid, req_clp, req_cld, req_tr, req_ts = req_table.gather(reqs, rids, req_objs)
+    else:
+        req_onid = np.fromiter((r.onid for r in req_objs), dtype=np.int32, count=nr)
+        req_dnid = np.fromiter((r.dnid for r in req_objs), dtype=np.int32, count=nr)
+        req_clp = np.fromiter((r.Clp for r in req_objs), dtype=np.float64, count=nr)
+        req_cld = np.fromiter((r.Cld for r in req_objs), dtype=np.float64, count=nr)
+        req_tr = np.fromiter((r.Tr for r in req_objs), dtype=np.float64, count=nr)
+        req_ts = np.fromiter((r.Ts for r in req_objs), dtype=np.float64, count=nr)
     search = np.searchsorted(rids, search_arr).astype(np.int32)
 
     idx = np.searchsorted(rids, np.where(is_reb, rids[0] if nr else 0, s_rid)) if ns else np.zeros(0, dtype=np.int64)
@@ -307,6 +341,7 @@ class LazyPoolRecords:
     def __init__(self, pool: Pool, ep: Epoch, vehs, req_objs):
         self._pool = Pool(stats=pool.stats, **{f: np.array(getattr(pool, f)) for f in Pool.FIELDS})   # own copy
         self._vehs, self._reqs = vehs, req_objs
+        self._req_id = np.asarray(ep.req_id, dtype=np.int64)     # request index -> request id (array-level consumers)
         self._perm = None              # position -> pool entry after an in-place "sort"
         self._cache = {}
         self._full = None

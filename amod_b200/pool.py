@@ -180,9 +180,15 @@ class PoolBuilder:
             raise NotImplementedError("enable_fast_compute is disabled in the reference (dispatch_osp.py:29)")
         cap = capacity if capacity is not None else _capacity_of(vehs)
         mode = MODE_OSP if enable_reoptimization else MODE_OSP_NR
-        ep, req_objs = marshal.marshal_epoch(reqs, vehs, considered_rids, system_time_sec, cap, mode)
+        ep, req_objs = marshal.marshal_epoch(reqs, vehs, considered_rids, system_time_sec, cap, mode, req_table=self._req_table())
         pool = self.build_pool(ep, reuse=True)
         return self._tag(self._records(pool, ep, vehs, req_objs))
+
+    def _req_table(self):
+        t = getattr(self, "_reqs_seen", None)
+        if t is None:
+            t = self._reqs_seen = marshal.ReqTable()
+        return t
 
     def _records(self, pool, ep, vehs, req_objs):
         if getattr(self, "lazy_records", False):
@@ -198,7 +204,7 @@ class PoolBuilder:
                                         capacity: int | None = None):
         """B2."""
         cap = capacity if capacity is not None else _capacity_of(vehs)
-        ep, req_objs = marshal.marshal_epoch(reqs, vehs, new_received_rids, system_time_sec, cap, MODE_SBA)
+        ep, req_objs = marshal.marshal_epoch(reqs, vehs, new_received_rids, system_time_sec, cap, MODE_SBA, req_table=self._req_table())
         pool = self.build_pool(ep, reuse=True)
         return self._tag(self._records(pool, ep, vehs, req_objs))
 

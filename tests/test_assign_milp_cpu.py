@@ -98,3 +98,26 @@ def test_not_worse_than_greedy_on_reference_pools():
         _order, gsel = oracle.greedy_assign(gold, ep.n_veh, ep.n_req)
         greedy = float(np.diff(gold.ent_trip_off)[_order[gsel]].sum())
         assert got >= greedy
+
+
+def test_array_path_equals_record_path():
+    """install(exact_assignment=True) hands the solver a LazyPoolRecords: the model is built from the pool arrays
+    and must be the record path's model (same rows, same order -> same solution)."""
+    tt, cases = load_golden("rand_real_osp_cap4")
+    for ep, gold in cases[:3]:
+        reqs_by_id, objs, vehs = _objects(ep)
+        for k, r in enumerate(objs):
+            r.status = OrderStatus.PENDING
+        considered = [int(ep.req_id[i]) for i in ep.search]
+        recs = marshal.pool_to_records(gold, ep, vehs, objs)
+        for p in recs:
+            p[4] = float(len(p[1]))
+        eager = milp_assignment(recs, considered, reqs_by_id, vehs, True)
+        lazy = marshal.LazyPoolRecords(gold, ep, vehs, objs)
+        lazy.scored = True
+        sel = milp_assignment(lazy, considered, reqs_by_id, vehs, True)
+        assert sel == eager
+        assert not lazy._cache                                           # nothing was materialised to build the model
+        for i in sel[:5]:
+            a, b = lazy[i], recs[i]
+            assert a[0] is b[0] and a[1] == b[1] and a[2] == b[2] and a[4] == b[4]
