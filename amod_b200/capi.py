@@ -12,7 +12,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "csrc", "libamod_b200.so")
+LIB_PATH = os.environ.get("AMOD_B200_LIB") or os.path.join(_HERE, "csrc", "libamod_b200.so")   # (override: tuning variants of the same source)
 
 OK, E_BADARG, E_CUDA, E_CAPACITY, E_LEVELS, E_NOMEM, E_LIMIT = 0, -1, -2, -3, -4, -5, -6
 LOC_HOST, LOC_DEVICE, LOC_PINNED = 0, 1, 2

@@ -22,7 +22,10 @@
 #define GRID_ELEM_PER_SM 2
 #endif
 #ifndef GRID_WARP_PER_SM
-#define GRID_WARP_PER_SM 8
+#define GRID_WARP_PER_SM 6      // swept 2..16 on the cfg2 snapshots (profiles/r01_grid_sweep.txt)
+#endif
+#ifndef GRID_EVAL_PER_SM
+#define GRID_EVAL_PER_SM EVAL_BLOCKS_PER_SM
 #endif
 
 #define CK(call)                                                                                         \
@@ -438,6 +441,7 @@ static int enqueue_build(amod_ctx* ctx, int mode, int cap, Table<TT> tt, int max
     Stats* dstats = &ctl->stats;
     const int G = ctx->n_sm * GRID_ELEM_PER_SM;   // elementwise kernels: grid-stride on a fixed grid
     const int GE = ctx->n_sm * GRID_WARP_PER_SM;   // warp-per-item kernels
+    const int GEV = ctx->n_sm * GRID_EVAL_PER_SM;  // the insertion search: exactly the resident blocks, one wave
     size_t n_ev = 0;
     int* len0 = ctx->len0.as<int>();
 
@@ -518,7 +522,7 @@ static int enqueue_build(amod_ctx* ctx, int mode, int cap, Table<TT> tt, int max
         const int Gk = std::max(1, 32 / (prev.stride + 1));      // rows per chunk: Gk * (longest schedule + 1) <= 32 lanes
         RowDesc* rows = rows_buf[cur];
         CK(cudaEventRecord(get_event(ctx, n_ev++), st));
-        k_eval<TT, 0><<<GE, WARPS_PER_BLOCK * 32, 0, st>>>(d, tt, prev, lv, ctl, cur, Gk, rows, ctx->chunk_cnt.as<int>(),
+        k_eval<TT, 0><<<GEV, WARPS_PER_BLOCK * 32, 0, st>>>(d, tt, prev, lv, ctl, cur, Gk, rows, ctx->chunk_cnt.as<int>(),
                                                           ctx->lane_cnt.as<uint8_t>(), nullptr, tnf, dstats, scan_site(ctx, k), half);
         CK(cudaEventRecord(get_event(ctx, n_ev++), st));
         scan_fin2(ctx, InArray<int>{ctx->chunk_cnt.as<int>(), &ctl->n_chunks[cur], 0}, cpos,
@@ -532,7 +536,7 @@ static int enqueue_build(amod_ctx* ctx, int mode, int cap, Table<TT> tt, int max
         cudaEvent_t named = get_sync_event(ctx, n_sync++);        // the level's trips have their rows (s0, nfeas)
         CK(cudaEventRecord(named, sd));
         CK(cudaEventRecord(get_event(ctx, n_ev++), st));
-        k_eval<TT, 1><<<GE, WARPS_PER_BLOCK * 32, 0, st>>>(d, tt, prev, lv, ctl, cur, Gk, rows, ctx->chunk_cnt.as<int>(),
+        k_eval<TT, 1><<<GEV, WARPS_PER_BLOCK * 32, 0, st>>>(d, tt, prev, lv, ctl, cur, Gk, rows, ctx->chunk_cnt.as<int>(),
                                                           ctx->lane_cnt.as<uint8_t>(), cpos, tnf, dstats, nullptr, half);
         CK(cudaEventRecord(get_event(ctx, n_ev++), st));
         CK(cudaStreamWaitEvent(st, named, 0));
