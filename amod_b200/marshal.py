@@ -12,6 +12,9 @@ stop (rid=-1, pod=0) whose node/deadline are per-vehicle (rebalancing_npo.py:37)
 """
 from __future__ import annotations
 
+import itertools
+import operator
+
 import numpy as np
 
 MODE_OSP = 0      # enable_reoptimization=True   dispatch_osp.py:301-322
@@ -25,6 +28,13 @@ ST_IDLE, ST_WORKING, ST_REBALANCING = 1, 2, 3  # types.py:18-21
 
 def _status_value(s) -> int:
     return int(getattr(s, "value", s))
+
+
+_get_sche = operator.attrgetter("sche")
+_get_onboard = operator.attrgetter("onboard_rids")
+_get_veh3 = operator.attrgetter("nid", "t_to_nid", "load")
+_get_status_value = operator.attrgetter("status.value")
+_chain = itertools.chain.from_iterable
 
 
 class Epoch:
@@ -134,20 +144,35 @@ def marshal_epoch(reqs, vehs, search_rids, T: int, cap: int, mode: int, check: b
     or new_received_rids (SBA, dispatch_sba.py:56).  Returns (epoch, req_objs) where
     req_objs[i] is the Req behind request index i.  One pass over the objects, the rest is numpy."""
     nv = len(vehs)
-    lens = np.fromiter((len(v.sche) for v in vehs), dtype=np.int64, count=nv)
+    # attribute reads at C speed (operator.attrgetter / map / chain): this loop over ~10^3-10^4 Python objects is
+    # what the seam costs per epoch once the kernels take < 1 ms
+    sches = list(map(_get_sche, vehs))
+    lens = np.fromiter(map(len, sches), dtype=np.int64, count=nv)
     off = np.zeros(nv + 1, dtype=np.int32)
     np.cumsum(lens, out=off[1:])
     ns = int(off[-1])
-    flat = [s for v in vehs for s in v.sche]
-    stops = np.array(flat, dtype=np.float64).reshape(ns, 4) if ns else np.zeros((0, 4))
+    flat = list(_chain(sches))
+    stops = np.fromiter(_chain(flat), dtype=np.float64, count=4 * ns).reshape(ns, 4) if ns else np.zeros((0, 4))
     s_rid = stops[:, 0].astype(np.int64)
     s_pod = stops[:, 1].astype(np.int64)
     s_node = stops[:, 2].astype(np.int64)
     s_ddl = stops[:, 3]
     s_veh = np.repeat(np.arange(nv, dtype=np.int64), lens)
     is_reb = s_rid < 0
-    search_arr = np.fromiter((int(r) for r in search_rids), dtype=np.int64, count=len(search_rids))
-    rids = np.unique(np.concatenate([search_arr, s_rid[~is_reb]]))
+    search_arr = np.asarray(search_rids, dtype=np.int64).reshape(-1)
+    onbs = list(map(_get_onboard, vehs))
+    onb_len = np.fromiter(map(len, onbs), dtype=np.int64, count=nv)
+    onb_rid = np.fromiter(_chain(onbs), dtype=np.int64, count=int(onb_len.sum()))
+    onb_veh = np.repeat(np.arange(nv, dtype=np.int64), onb_len)
+    vals = np.concatenate([search_arr, s_rid[~is_reb]])
+    top = int(max(vals.max() if vals.size else -1, onb_rid.max() if onb_rid.size else -1)) + 1
+    dense = 0 < top <= (1 << 22) and (vals.size == 0 or int(vals.min()) >= 0)    # request ids index the platform's list: direct tables
+    if dense:
+        present = np.zeros(top, dtype=bool)
+        present[vals] = True
+        rids = np.flatnonzero(present)
+    else:
+        rids = np.unique(vals)
     req_objs = [reqs[r] for r in rids.tolist()]
     nr = len(req_objs)
     if req_table is not None:       # a request's (onid, dnid, Clp, Cld, Tr, Ts) never change (request.py:25-41): read each object once
@@ -159,14 +184,22 @@ def marshal_epoch(reqs, vehs, search_rids, T: int, cap: int, mode: int, check: b
         req_cld = np.fromiter((r.Cld for r in req_objs), dtype=np.float64, count=nr)
         req_tr = np.fromiter((r.Tr for r in req_objs), dtype=np.float64, count=nr)
         req_ts = np.fromiter((r.Ts for r in req_objs), dtype=np.float64, count=nr)
-    search = np.searchsorted(rids, search_arr).astype(np.int32)
-
-    idx = np.searchsorted(rids, np.where(is_reb, rids[0] if nr else 0, s_rid)) if ns else np.zeros(0, dtype=np.int64)
+    s_rid0 = np.where(is_reb, rids[0] if nr else 0, s_rid)
+    if dense:
+        index_of = np.full(top, -1, dtype=np.int64)
+        index_of[rids] = np.arange(nr, dtype=np.int64)
+        search = index_of[search_arr].astype(np.int32)
+        idx = index_of[s_rid0] if ns else np.zeros(0, dtype=np.int64)
+        # onboard flag: (vehicle, rid) pairs of veh.onboard_rids; a request is on board of at most one vehicle
+        veh_of = np.full(top, -1, dtype=np.int64)
+        veh_of[onb_rid] = onb_veh
+        onboard = ((veh_of[s_rid0] == s_veh) & ~is_reb).astype(np.uint8) if ns else np.zeros(0, dtype=np.uint8)
+    else:
+        search = np.searchsorted(rids, search_arr).astype(np.int32)
+        idx = np.searchsorted(rids, s_rid0) if ns else np.zeros(0, dtype=np.int64)
+        big = int(max(rids[-1] if nr else 0, onb_rid.max() if onb_rid.size else 0)) + 2
+        onboard = (np.isin(s_veh * big + s_rid, onb_veh * big + onb_rid) & ~is_reb).astype(np.uint8) if ns else np.zeros(0, dtype=np.uint8)
     code = np.where(is_reb, -1, 2 * idx + (s_pod == -1)).astype(np.int32)
-    # onboard flag: (vehicle, rid) pairs of veh.onboard_rids
-    big = int(rids[-1]) + 2 if nr else 2
-    onb = np.fromiter((vi * big + rid for vi, v in enumerate(vehs) for rid in v.onboard_rids), dtype=np.int64)
-    onboard = (np.isin(s_veh * big + s_rid, onb) & ~is_reb).astype(np.uint8) if ns else np.zeros(0, dtype=np.uint8)
     reb_node = np.zeros(nv, dtype=np.int32)
     reb_ddl = np.zeros(nv, dtype=np.float64)
     reb_node[s_veh[is_reb]] = s_node[is_reb]
@@ -184,10 +217,14 @@ def marshal_epoch(reqs, vehs, search_rids, T: int, cap: int, mode: int, check: b
         if bad.any():
             k = int(np.flatnonzero(bad)[0])
             raise ValueError(f"vehicle {int(s_veh[k])}: stop {flat[k]} does not match its request")
-    veh_nid = np.fromiter((v.nid for v in vehs), dtype=np.int32, count=nv)
-    veh_t = np.fromiter((v.t_to_nid for v in vehs), dtype=np.float64, count=nv)
-    veh_load = np.fromiter((v.load for v in vehs), dtype=np.int32, count=nv)
-    veh_status = np.fromiter((_status_value(v.status) for v in vehs), dtype=np.int32, count=nv)
+    vcols = np.fromiter(_chain(map(_get_veh3, vehs)), dtype=np.float64, count=3 * nv).reshape(nv, 3)   # (nid, t_to_nid, load): exact in float64
+    veh_nid = vcols[:, 0].astype(np.int32)
+    veh_t = np.ascontiguousarray(vcols[:, 1])
+    veh_load = vcols[:, 2].astype(np.int32)
+    try:
+        veh_status = np.fromiter(map(_get_status_value, vehs), dtype=np.int32, count=nv)
+    except AttributeError:          # plain ints instead of the reference's enum
+        veh_status = np.fromiter((_status_value(v.status) for v in vehs), dtype=np.int32, count=nv)
     ep = Epoch(T=T, cap=cap, mode=mode, veh_nid=veh_nid, veh_t_to_nid=veh_t, veh_load=veh_load,
                veh_status=veh_status, veh_sche_off=off, sche_code=code, sche_onboard=onboard,
                veh_reb_node=reb_node, veh_reb_ddl=reb_ddl, req_id=rids.astype(np.int32), req_onid=req_onid,
