@@ -90,7 +90,7 @@ struct amod_ctx {
     i64 cap_trips[MAX_LEVELS], cap_sch[MAX_LEVELS];
     // workspace
     DevBuf len0, S0, s0pos, perm_base, perm_nitems, perm_off, perm_cnt, perm_pos, flag8, pos, major_off, partial, scan_sites, task_veh[2], task_base[2], task_q[2], task_nchunk[2], task_chunk0, trip_pos,
-        row_desc, task_nfeas, chunk_cnt, lane_cnt, chunk_pos, hash, row_cnt, row_off, tmp_j, tmp_q, heavy_list, gen_partial, gen_cache;
+        row_desc, task_nfeas, chunk_cnt, lane_cnt, chunk_pos, hash, row_cnt, row_off, tmp_j, tmp_q, heavy_list, gen_partial, gen_cache, task_first;
     LevelBufs lv[MAX_LEVELS];
     // pool
     DevBuf veh_cnt, veh_off, ent_veh, ent_kind, ent_nfeas, ent_tlen, ent_slen, ent_src, ent_trip, ent_cost, ent_delay,
@@ -228,7 +228,7 @@ extern "C" void amod_destroy(amod_ctx* ctx) {
                      &ctx->partial, &ctx->scan_sites,
                      &ctx->task_veh[0], &ctx->task_veh[1], &ctx->task_base[0], &ctx->task_base[1], &ctx->task_q[0], &ctx->task_q[1],
                      &ctx->task_nchunk[0], &ctx->task_nchunk[1], &ctx->task_chunk0, &ctx->trip_pos, &ctx->row_desc, &ctx->task_nfeas, &ctx->chunk_cnt,
-                     &ctx->lane_cnt, &ctx->chunk_pos, &ctx->hash, &ctx->row_cnt, &ctx->row_off, &ctx->tmp_j, &ctx->tmp_q, &ctx->heavy_list, &ctx->gen_partial, &ctx->gen_cache,
+                     &ctx->lane_cnt, &ctx->chunk_pos, &ctx->hash, &ctx->row_cnt, &ctx->row_off, &ctx->tmp_j, &ctx->tmp_q, &ctx->heavy_list, &ctx->gen_partial, &ctx->gen_cache, &ctx->task_first,
                      &ctx->veh_cnt, &ctx->veh_off, &ctx->ent_veh, &ctx->ent_kind, &ctx->ent_nfeas, &ctx->ent_tlen, &ctx->ent_slen,
                      &ctx->ent_src, &ctx->ent_trip, &ctx->ent_cost, &ctx->ent_delay, &ctx->trip_off, &ctx->sche_off, &ctx->trip_req,
                      &ctx->sche_code, &ctx->ga_pos, &ctx->ga_rank, &ctx->ga_order, &ctx->ga_state, &ctx->ga_bv, &ctx->ga_br, &ctx->ga_tv, &ctx->ga_tr,
@@ -413,7 +413,7 @@ static int ensure_buffers(amod_ctx* ctx, int V, i64 n_screen, int max_level, con
     CK(ctx->hash.ensure(2 * 4 * (size_t)hsz));      // two tables: level k+1's is cleared while level k's is read
     ctx->hash_slots = hsz;
     CK(ctx->gen_partial.ensure(8 * (size_t)ctx->n_sm * GRID_WARP_PER_SM));
-    CK(ctx->gen_cache.ensure(sizeof(int2) * GEN_INLINE * max_trips));
+    CK(ctx->gen_cache.ensure(sizeof(int2) * GEN_INLINE * max_trips)); CK(ctx->task_first.ensure(8 * (max_trips + 2)));
     CK(ctx->veh_cnt.ensure(4 * (size_t)(V + 1))); CK(ctx->veh_off.ensure(8 * (size_t)(V + 2)));
     const size_t E = (size_t)ctx->cap_ent, PT = (size_t)ctx->cap_ptr, PS = (size_t)ctx->cap_pst;
     CK(ctx->ent_veh.ensure(4 * E)); CK(ctx->ent_kind.ensure(4 * E)); CK(ctx->ent_nfeas.ensure(4 * E)); CK(ctx->ent_tlen.ensure(4 * E));
@@ -532,7 +532,7 @@ static int enqueue_build(amod_ctx* ctx, int mode, int cap, Table<TT> tt, int max
         CK(edge(st, sd));                                         // fork
         const TripHash th = hash_of(k);
         k_compact_trips<<<G, 256, 0, sd>>>(ctl, cur, tv, tb, tq, row0, tnf, Gk, rows, ctx->lane_cnt.as<uint8_t>(), cpos,
-                                          ctx->trip_pos.as<i64>(), prev, lv, th, dstats);
+                                          ctx->trip_pos.as<i64>(), prev, lv, th, dstats, d, sba, ctx->major_off.as<i64>(), ctx->task_first.as<i64>());
         cudaEvent_t named = get_sync_event(ctx, n_sync++);        // the level's trips have their rows (s0, nfeas)
         CK(cudaEventRecord(named, sd));
         CK(cudaEventRecord(get_event(ctx, n_ev++), st));
@@ -544,7 +544,6 @@ static int enqueue_build(amod_ctx* ctx, int mode, int cap, Table<TT> tt, int max
         k_classify<<<GE, WARPS_PER_BLOCK * 32, 0, st>>>(ctl, lv, heavy_min, ctx->heavy_list.as<int>());
         if (heavy_min) { k_classify_heavy<<<ctx->n_sm * 2, HEAVY_THREADS, 0, st>>>(ctl, lv, ctx->heavy_list.as<int>()); ctx->n_launches++; }
         ctx->n_launches += 4;       // k_eval x2, k_compact_trips, k_classify (the scans count themselves)
-        if (!sba && (k == 1 || k == max_level)) { k_veh_start<<<G, 256, 0, sd>>>(d, ctl, lv); ctx->n_launches++; }
         if (k < max_level) {
             // ---- candidates of size k+1 (dispatch_osp.py:183-216), their tasks and rows ----------------------
             const TripHash thn = hash_of(k + 1);
@@ -553,7 +552,7 @@ static int enqueue_build(amod_ctx* ctx, int mode, int cap, Table<TT> tt, int max
             GenOut go;
             go.tmp_j = ctx->tmp_j.as<int>(); go.tmp_q = ctx->tmp_q.as<int>();
             go.task_veh = ctx->task_veh[nxt].as<int>(); go.task_base = ctx->task_base[nxt].as<int>(); go.task_q = ctx->task_q[nxt].as<int>();
-            go.task_row0 = row0; go.rows = rows_buf[nxt]; go.task_nfeas = tnf;
+            go.task_row0 = row0; go.rows = rows_buf[nxt]; go.task_nfeas = tnf; go.task_first = ctx->task_first.as<i64>();
             go.cap_tasks = ctx->cap_tasks; go.cap_rows = ctx->cap_rows; go.cap_chunks = ctx->cap_chunks;
             go.G_next = std::max(1, 32 / (lv.stride + 1));
             k_gen_emit<<<GE, WARPS_PER_BLOCK * 32, 0, sd>>>(ctl, nxt, ls.lv[1], lv, th, len0, ctx->row_cnt.as<int>(), ctx->gen_cache.as<int2>(),

@@ -460,18 +460,6 @@ __device__ __forceinline__ unsigned hash_trip(int v, const int* r, int k, int sk
     return (unsigned)(h ^ (h >> 29));
 }
 
-// veh_start[u] = first trip of vehicle u (trips are vehicle-major; OSP modes): levels whose candidates are
-// not generated by k_gen_count (level 1 before its own candidates, the last level searched)
-__global__ void k_veh_start(const DEpoch* __restrict__ epp, const Control* __restrict__ ctl, Level lv) {
-    const int n = ctl->overflow ? 0 : ctl->n_trips[lv.k];
-    const int n_veh = epp->n_veh;
-    for (int u = blockIdx.x * blockDim.x + threadIdx.x; u <= n_veh; u += gridDim.x * blockDim.x) {
-        int a = 0, b = n;
-        while (a < b) { const int m = (a + b) >> 1; if (lv.trip_veh[m] < u) a = m + 1; else b = m; }
-        lv.veh_start[u] = a;
-    }
-}
-
 // index of the trip (v, r minus r[skip] plus extra), or -1
 __device__ __forceinline__ int hash_find(const Level& lv, const TripHash& th, int v, const int* r, int skip, int extra) {
     const int k = lv.k;
@@ -509,9 +497,20 @@ __global__ void k_compact_trips(const Control* __restrict__ ctl, int which, cons
                                 const i64* __restrict__ task_row0, const int* __restrict__ task_nfeas, int G,
                                 const RowDesc* __restrict__ rows, const uint8_t* __restrict__ lane_cnt,
                                 const i64* __restrict__ chunk_pos, const i64* __restrict__ trip_pos, Level prev, Level cur,
-                                TripHash th, Stats* stats) {
+                                TripHash th, Stats* stats, const DEpoch* __restrict__ epp, int sba,
+                                const i64* __restrict__ major_off, const i64* __restrict__ task_first) {
     const int n = (ctl->n_trips[cur.k] && !ctl->overflow) ? ctl->n_tasks[which] : 0;
     const int stride = gridDim.x * blockDim.x;
+    if (!sba && !ctl->overflow) {
+        // veh_start[v] = first trip of vehicle v (trips are vehicle-major, like the tasks they come from): the
+        // trip position of the vehicle's first task.  Level 1 tasks start at the screen's per-vehicle offsets;
+        // level k tasks of v start where the candidates of v's first level-(k-1) trip start.
+        const int n_veh = epp->n_veh;
+        for (int v = blockIdx.x * blockDim.x + threadIdx.x; v <= n_veh; v += stride) {
+            const i64 ft = cur.k == 1 ? PACK_LO(major_off[v]) : task_first[prev.veh_start[v]];
+            cur.veh_start[v] = (int)trip_pos[ft];
+        }
+    }
     unsigned long long nsch = 0;
     for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < n; t += stride) {
         const int nf = task_nfeas[t];
@@ -668,6 +667,7 @@ struct GenOut {
     int* tmp_j; int* tmp_q;
     int* task_veh; int* task_base; int* task_q; i64* task_row0;
     RowDesc* rows; int* task_nfeas;
+    i64* task_first;          // [trips of the level + 1] first task spawned by each trip (-> veh_start of the next level)
     i64 cap_tasks, cap_rows, cap_chunks; int G_next;
 };
 
@@ -749,14 +749,6 @@ k_gen_count(const DEpoch* __restrict__ epp, const Control* __restrict__ ctl, Lev
     const unsigned gtid = blockIdx.x * blockDim.x + threadIdx.x, gsz = gridDim.x * blockDim.x;
     // the lookup table the NEXT level will build into (the other buffer; its last readers are two kernels back)
     for (unsigned x = gtid; x < next_hash_size; x += gsz) next_hash[x] = -1;
-    if (prev.k >= 2) {     // veh_start[u] = first trip of vehicle u (trips are vehicle-major); level 1 has its own kernel
-        const int n_veh = epp->n_veh;
-        for (int u = (int)gtid; u <= n_veh; u += (int)gsz) {
-            int a = 0, b = n;
-            while (a < b) { const int m = (a + b) >> 1; if (prev.trip_veh[m] < u) a = m + 1; else b = m; }
-            prev.veh_start[u] = a;
-        }
-    }
     if (threadIdx.x == 0) s_sum = 0ull;
     __syncthreads();
     int lo, hi;
@@ -805,6 +797,7 @@ k_gen_emit(Control* __restrict__ ctl, int which_next, Level l1, Level prev, Trip
             const i64 off = PACK_LO(s_off[i]), rbase = PACK_HI(s_off[i]);
             const int cnt = row_cnt[t];
             const int S = prev.nfeas[t];          // every task inserting into trip t walks all of its schedules
+            if (lane == 0) o.task_first[t] = off;
             if (cnt == 0) continue;
             if (off + cnt > o.cap_tasks || rbase + (i64)cnt * S > o.cap_rows) continue;   // reported by the last block; the epoch is rerun
             const int v = prev.trip_veh[t], k = prev.k;
@@ -854,6 +847,7 @@ k_gen_emit(Control* __restrict__ ctl, int which_next, Level l1, Level prev, Trip
     }
     if (lane == 0 && n_tasks) { atomicAdd(&ctl->stats.n_tasks, n_tasks); atomicAdd(&ctl->stats.n_items, n_items); }
     if (last && threadIdx.x == 0) {
+        o.task_first[n] = PACK_LO(carry);
         FinTasksRows fin{ctl, which_next, o.cap_tasks, o.cap_rows, o.cap_chunks, o.G_next};
         fin(carry);
     }
