@@ -12,6 +12,7 @@ stop (rid=-1, pod=0) whose node/deadline are per-vehicle (rebalancing_npo.py:37)
 """
 from __future__ import annotations
 
+import gc
 import itertools
 import operator
 
@@ -335,6 +336,21 @@ def pool_to_records(pool: Pool, ep: Epoch, vehs, req_objs) -> PoolRecords:
     n_req = len(req_objs)
     n = pool.n_entries
     out = PoolRecords()
+    # ~10^5 container objects are born here and none of them is garbage: without this the cyclic collector runs
+    # a generation pass every few hundred allocations and takes 3/4 of the time
+    gc_was_on = gc.isenabled()
+    gc.disable()
+    try:
+        _fill_records(out, pool, ep, vehs, req_objs, n_req, n)
+    finally:
+        if gc_was_on:
+            gc.enable()
+    out.delays = pool.ent_delay.copy()
+    out.stats = pool.stats
+    return out
+
+
+def _fill_records(out, pool, ep, vehs, req_objs, n_req, n):
     if n:
         # stop tuples: [pick-up of request i | drop-off of request i | rebalancing stop of vehicle v]
         lut = np.empty(2 * n_req + len(vehs), dtype=object)
@@ -364,9 +380,6 @@ def pool_to_records(pool: Pool, ep: Epoch, vehs, req_objs) -> PoolRecords:
         to = pool.ent_trip_off.tolist()
         cost = pool.ent_cost.copy()      # numpy float64 scalars like the reference; the arrays may be views of reused buffers
         out.extend([ent_vehs[e], trips[to[e]:to[e + 1]], stops[so[e]:so[e + 1]], cost[e], 0.0] for e in range(n))
-    out.delays = pool.ent_delay.copy()
-    out.stats = pool.stats
-    return out
 
 
 class LazyPoolRecords:
