@@ -619,7 +619,7 @@ static int build_impl(amod_ctx* ctx, const amod_epoch* ep, int loc, amod_stats* 
         CK(cudaMemcpyAsync(ctx->ctl.p, h, sizeof(Control), cudaMemcpyHostToDevice, st));
         CK(cudaMemsetAsync(ctx->scan_sites.p, 0, scan_sites_bytes(ctx), st));     // block sums the producer kernels add into
         if (ctx->use_graph) {
-            // the whole level loop is one CUDA graph: ~150 small kernels whose sizes all live on the device,
+            // the whole level loop is one CUDA graph (two branches, ~60-90 kernel nodes) whose sizes all live on the device,
             // so a captured graph stays valid until a buffer moves or the dispatch mode / capacity changes
             amod_ctx::GraphSlot& gs = ctx->graphs[mode];
             if (!gs.exec || gs.gen != ctx->buf_gen || gs.cap != d.cap || gs.base_len != base_len || gs.max_level != run_levels ||
