@@ -133,3 +133,33 @@ def test_take_reorders_vehicles_with_their_schedules():
     ca = np.bincount(a.ent_veh, minlength=ep.n_veh)
     cb = np.bincount(b.ent_veh, minlength=ep.n_veh)
     assert np.array_equal(cb, ca[perm])
+
+
+def test_request_table_and_index_paths_agree():
+    """marshal_epoch with the per-simulation request table, without it, and with request ids too sparse for the
+    direct index tables must produce the same epoch; a different `reqs` container starts a fresh table."""
+    tt, cases = load_golden("rand_real_osp_cap4")
+    ep = cases[0][0]
+    reqs, objs, vehs = _objects(ep)
+    search = [int(ep.req_id[i]) for i in ep.search]
+    plain, _ = marshal.marshal_epoch(reqs, vehs, search, ep.T, ep.cap, ep.mode)
+    table = marshal.ReqTable()
+    for _ in range(2):                                   # second call: every request already known
+        cached, _ = marshal.marshal_epoch(reqs, vehs, search, ep.T, ep.cap, ep.mode, req_table=table)
+        for f in marshal.Epoch.FIELDS:
+            assert np.array_equal(getattr(plain, f), getattr(cached, f)) and getattr(plain, f).dtype == getattr(cached, f).dtype, f
+    # same ids, different request data, different container: the table must not serve the old values
+    reqs2 = {rid: types.SimpleNamespace(**{**r.__dict__, "Clp": r.Clp + 7.0, "Cld": r.Cld + 9.0}) for rid, r in reqs.items()}
+    vehs2 = [types.SimpleNamespace(**{**v.__dict__, "sche": [(s[0], s[1], s[2], s[3] + (0.0 if s[0] < 0 else (7.0 if s[1] == 1 else 9.0)))
+                                                           for s in v.sche]}) for v in vehs]
+    shifted, _ = marshal.marshal_epoch(reqs2, vehs2, search, ep.T, ep.cap, ep.mode, req_table=table)
+    assert np.array_equal(shifted.req_clp, plain.req_clp + 7.0) and np.array_equal(shifted.req_cld, plain.req_cld + 9.0)
+    # ids beyond the direct-table limit take the sort-based path
+    big = 1 << 23
+    reqs3 = {rid + big: types.SimpleNamespace(**{**r.__dict__, "id": rid + big}) for rid, r in reqs.items()}
+    vehs3 = [types.SimpleNamespace(**{**v.__dict__, "sche": [(s[0] + big if s[0] >= 0 else s[0], s[1], s[2], s[3]) for s in v.sche],
+                                      "onboard_rids": [x + big for x in v.onboard_rids]}) for v in vehs]
+    sparse, _ = marshal.marshal_epoch(reqs3, vehs3, [r + big for r in search], ep.T, ep.cap, ep.mode)
+    for f in marshal.Epoch.FIELDS:
+        want = getattr(plain, f) + (big if f == "req_id" else 0)
+        assert np.array_equal(want, getattr(sparse, f)), f
