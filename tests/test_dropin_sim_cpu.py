@@ -21,14 +21,20 @@ import ref_harness as rh  # noqa: E402
 pytestmark = pytest.mark.skipif(not rh.reference_available(), reason="reference tree not present")
 
 
-def _run(dispatcher: str, patched, q, assigner: str = "greedy"):
+def _run(dispatcher: str, patched, q, assigner: str = "greedy", scale: str = "small"):
     from amod_b200 import install as inst, marshal, pool as pool_mod, synth
     import oracle
-    graph = synth.make_road_graph(400, seed=3, with_paths=True)
     t0 = 18 * 3600 + 30 * 60
-    on, dn, tm = synth.make_request_stream(graph, 1500, t0, t0 + 40 * 60, seed=1, mean_trip_sec=420.0)
-    ref = rh.setup_reference(f"/tmp/amod_ref_dropin_{dispatcher}_{patched}_{assigner}", graph, on, dn, tm, fleet_size=30, capacity=4,
-                             dispatcher=dispatcher, warmup_min=5, main_min=12, winddown_min=4)
+    if scale == "cfg1":     # BASELINE.json configs[0]: 100 vehicles cap 4, 1 h main horizon, the full-size 4,091-node table
+        graph = synth.make_road_graph(seed=0, with_paths=True)
+        on, dn, tm = synth.make_request_stream(graph, 1700, t0, t0 + 135 * 60, seed=1, mean_trip_sec=600.0)
+        horizon = dict(fleet_size=100, warmup_min=30, main_min=60, winddown_min=39)
+    else:
+        graph = synth.make_road_graph(400, seed=3, with_paths=True)
+        on, dn, tm = synth.make_request_stream(graph, 1500, t0, t0 + 40 * 60, seed=1, mean_trip_sec=420.0)
+        horizon = dict(fleet_size=30, warmup_min=5, main_min=12, winddown_min=4)
+    ref = rh.setup_reference(f"/tmp/amod_ref_dropin_{dispatcher}_{patched}_{assigner}_{scale}", graph, on, dn, tm, capacity=4,
+                             dispatcher=dispatcher, **horizon)
     patched_tag = str(patched)
     # both runs must search exhaustively: disable the wall-clock cut-off of the unmodified seam as well
     orig = ref.dispatch_osp.compute_candidate_veh_trip_pairs
@@ -113,5 +119,24 @@ def test_simulation_outcome_identical_with_exact_assignment():
         p.join()
     (r0, reqs0, veh0) = res[0]
     assert len(reqs0) > 300 and r0[0] > 10
+    for (r1, reqs1, veh1) in res[1:]:
+        assert r0 == r1 and reqs0 == reqs1 and veh0 == veh1
+
+
+def test_cfg1_simulated_hour_identical_with_seams_replaced():
+    """BASELINE.json configs[0] at full size — SBA + greedy assignment, 100 vehicles of capacity 4, 30 + 60 + 39
+    simulated minutes (258 epochs) on the 4,091-node synthetic table: per-request outcomes, per-vehicle end states
+    and the report are identical for the unmodified reference, the replaced seams with eager records and the
+    replaced seams with lazy records + the greedy assigner on the (stand-in) device."""
+    ctx = mp.get_context("spawn")
+    res = []
+    for patched in (False, True, "lazy"):
+        q = ctx.Queue()
+        p = ctx.Process(target=_run, args=("SBA", patched, q, "greedy", "cfg1"))
+        p.start()
+        res.append(q.get(timeout=900))
+        p.join()
+    (r0, reqs0, veh0) = res[0]
+    assert len(reqs0) > 1200 and len(veh0) == 100 and r0[0] > 300
     for (r1, reqs1, veh1) in res[1:]:
         assert r0 == r1 and reqs0 == reqs1 and veh0 == veh1
