@@ -12,6 +12,8 @@ from __future__ import annotations
 
 import ctypes as C
 
+import operator
+
 import numpy as np
 
 from . import capi, marshal
@@ -212,11 +214,12 @@ class PoolBuilder:
                                                            value_func, detour_sec: int = 240):
         """B3: candidates, sort and greedy selection on the GPU; veh.build_route stays host
         (rebalancing_npo.py:62)."""
-        pending = [r for r in reqs if _status_value(r.status) == 1]          # OrderStatus.PENDING (:13-16)
-        idle = [v for v in vehs if _status_value(v.status) == marshal.ST_IDLE]   # (:29-31)
+        pending = _with_status(reqs, 1)                      # OrderStatus.PENDING (:13-16), in id order
+        idle = _with_status(vehs, marshal.ST_IDLE)           # (:29-31), in fleet order
         if not pending or not idle:
             return
-        oi, op, od = self.npo_match([v.nid for v in idle], [r.onid for r in pending])
+        oi, op, od = self.npo_match(np.fromiter(map(_get_nid, idle), dtype=np.int32, count=len(idle)),
+                                    np.fromiter(map(_get_onid, pending), dtype=np.int32, count=len(pending)))
         tt_type = np.float64
         for vi, ri, dt in zip(oi.tolist(), op.tolist(), od):
             req = pending[ri]
@@ -225,6 +228,22 @@ class PoolBuilder:
 
 def _status_value(s) -> int:
     return int(getattr(s, "value", s))
+
+
+_get_status_value = operator.attrgetter("status.value")
+_get_nid = operator.attrgetter("nid")
+_get_onid = operator.attrgetter("onid")
+
+
+def _with_status(objs, value: int) -> list:
+    """Objects whose status equals `value`, in order.  The reference scans every request of the day each epoch
+    (rebalancing_npo.py:13-16); the scan stays, at C speed."""
+    objs = objs if isinstance(objs, list) else list(objs)
+    try:
+        st = np.fromiter(map(_get_status_value, objs), dtype=np.int64, count=len(objs))
+    except AttributeError:      # plain ints instead of the reference's enums
+        st = np.fromiter((_status_value(o.status) for o in objs), dtype=np.int64, count=len(objs))
+    return [objs[i] for i in np.flatnonzero(st == value).tolist()]
 
 
 def _capacity_of(vehs) -> int:
