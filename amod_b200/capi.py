@@ -54,10 +54,11 @@ class AmodStats(C.Structure):
                 ("n_entries", C.c_int64), ("n_sches_stored", C.c_int64), ("n_tasks", C.c_int64),
                 ("n_levels", C.c_int32), ("n_kernel_launches", C.c_int32), ("ms_build", C.c_double),
                 ("ms_eval", C.c_double), ("n_eval_launches", C.c_int32), ("n_attempts", C.c_int32),
-                ("n_chunks", C.c_int64), ("n_items", C.c_int64), ("n_lookups_eval", C.c_int64)]
+                ("n_chunks", C.c_int64), ("n_items", C.c_int64), ("n_lookups_eval", C.c_int64),
+                ("evals_level", C.c_int64 * 16), ("lookups_level", C.c_int64 * 16), ("ms_screen", C.c_double)]
 
     def as_dict(self):
-        return {f: getattr(self, f) for f, _ in self._fields_ if f != "reserved"}
+        return {f: (list(getattr(self, f)) if f.endswith("_level") else getattr(self, f)) for f, _ in self._fields_}
 
 
 def epoch_struct(ep, ptr_of=None) -> AmodEpoch:

@@ -113,6 +113,8 @@ struct amod_ctx {
     std::vector<cudaEvent_t> sync_pool;      // fork / join edges between the two branches
     int n_launches = 0;
     unsigned hash_slots = 0;                 // slots per trip lookup table (two tables in `hash`)
+    cudaAccessPolicyWindow l2_window; bool l2_window_valid = false, l2_on = false;
+    int base_len_hint[3] = {0, 0, 0};        // longest current schedule seen so far per mode (SBA / OSP_NR): keeps graph + strides stable
 
     int fail(int code, const char* fmt, ...) {
         char buf[512];
@@ -157,21 +159,49 @@ static void scan_fin(amod_ctx* ctx, In in, i64* out, Fin fin, i64* partial, cuda
 }
 
 // Keep the travel-time table resident in L2 (126 MB on B200; 67 MB as fp32): persisting
-// access-policy window on the stream the kernels run on.
+// access-policy window on the streams the kernels run on AND on every kernel node of the captured
+// epoch graph (graph kernel nodes carry their own launch attributes).  AMOD_NO_L2_POLICY=1 switches
+// it off (A/B evidence: profiles/r02_l2_policy_ab.txt).
 static void apply_l2_policy(amod_ctx* ctx, cudaStream_t stream) {
-    int max_win = 0, max_persist = 0;
-    cudaDeviceGetAttribute(&max_win, cudaDevAttrMaxAccessPolicyWindowSize, ctx->device);
-    cudaDeviceGetAttribute(&max_persist, cudaDevAttrMaxPersistingL2CacheSize, ctx->device);
-    if (max_win <= 0 || max_persist <= 0 || !ctx->d_tt) return;
-    size_t win = std::min(ctx->tt_bytes, (size_t)max_win);
-    cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, std::min((size_t)max_persist, win));
+    if (!ctx->l2_window_valid) {
+        ctx->l2_on = false;
+        if (getenv("AMOD_NO_L2_POLICY")) return;
+        int max_win = 0, max_persist = 0;
+        cudaDeviceGetAttribute(&max_win, cudaDevAttrMaxAccessPolicyWindowSize, ctx->device);
+        cudaDeviceGetAttribute(&max_persist, cudaDevAttrMaxPersistingL2CacheSize, ctx->device);
+        if (max_win <= 0 || max_persist <= 0 || !ctx->d_tt) return;
+        size_t win = std::min(ctx->tt_bytes, (size_t)max_win);
+        cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, std::min((size_t)max_persist, win));
+        memset(&ctx->l2_window, 0, sizeof ctx->l2_window);
+        ctx->l2_window.base_ptr = ctx->d_tt;
+        ctx->l2_window.num_bytes = win;
+        ctx->l2_window.hitRatio = (float)std::min(1.0, (double)max_persist / (double)win);
+        ctx->l2_window.hitProp = cudaAccessPropertyPersisting;
+        ctx->l2_window.missProp = cudaAccessPropertyStreaming;
+        ctx->l2_window_valid = true;
+        ctx->l2_on = true;
+    }
+    if (!ctx->l2_on) return;
     cudaStreamAttrValue av; memset(&av, 0, sizeof av);
-    av.accessPolicyWindow.base_ptr = ctx->d_tt;
-    av.accessPolicyWindow.num_bytes = win;
-    av.accessPolicyWindow.hitRatio = (float)std::min(1.0, (double)max_persist / (double)win);
-    av.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
-    av.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+    av.accessPolicyWindow = ctx->l2_window;
     cudaStreamSetAttribute(stream, cudaStreamAttributeAccessPolicyWindow, &av);
+    cudaGetLastError();
+}
+
+// the same window on every kernel node of a captured graph (before instantiation)
+static void apply_l2_policy_to_graph(amod_ctx* ctx, cudaGraph_t graph) {
+    if (!ctx->l2_on) return;
+    size_t n = 0;
+    if (cudaGraphGetNodes(graph, nullptr, &n) != cudaSuccess || n == 0) { cudaGetLastError(); return; }
+    std::vector<cudaGraphNode_t> nodes(n);
+    if (cudaGraphGetNodes(graph, nodes.data(), &n) != cudaSuccess) { cudaGetLastError(); return; }
+    cudaKernelNodeAttrValue av; memset(&av, 0, sizeof av);
+    av.accessPolicyWindow = ctx->l2_window;
+    for (size_t i = 0; i < n; i++) {
+        cudaGraphNodeType ty;
+        if (cudaGraphNodeGetType(nodes[i], &ty) != cudaSuccess || ty != cudaGraphNodeTypeKernel) continue;
+        cudaGraphKernelNodeSetAttribute(nodes[i], cudaKernelNodeAttributeAccessPolicyWindow, &av);
+    }
     cudaGetLastError();
 }
 
@@ -215,6 +245,7 @@ extern "C" int amod_create(amod_ctx** out, int device, int n_nodes, const void* 
     if (const char* hm = getenv("AMOD_HEAVY_MIN")) ctx->heavy_min = atoi(hm);
     if (const char* gi = getenv("AMOD_GEN_INLINE")) ctx->gen_inline = std::max(0, std::min(GEN_INLINE, atoi(gi)));
     apply_l2_policy(ctx, ctx->stream);
+    apply_l2_policy(ctx, ctx->side);         // k_basic<fill>, candidate generation: the side branch looks travel times up too
     cudaEventCreate(&ctx->ev0); cudaEventCreate(&ctx->ev1);
     *out = ctx;
     return AMOD_OK;
@@ -363,6 +394,7 @@ static cudaEvent_t get_sync_event(amod_ctx* ctx, size_t i) {
     return ctx->sync_pool[i];
 }
 
+#define EV_SCREEN 100     // ev_pool slots: [0, 64) insertion-search launches, 64.. peer-assembly profiling, 100/101 the screen
 static cudaEvent_t get_event(amod_ctx* ctx, size_t i) {
     while (ctx->ev_pool.size() <= i) { cudaEvent_t e; cudaEventCreate(&e); ctx->ev_pool.push_back(e); }
     return ctx->ev_pool[i];
@@ -480,6 +512,7 @@ static int enqueue_build(amod_ctx* ctx, int mode, int cap, Table<TT> tt, int max
     // ---- level-1 tasks: reachability screen ---------------------------------------------------------
     {
         const int G1 = std::max(1, 32 / (ls.lv[0].stride + 1));
+        CK(cudaEventRecord(get_event(ctx, EV_SCREEN), st));
         k_screen_count<TT><<<ctx->n_sm * 16, SCREEN_WARPS * 32, 0, st>>>(d, tt, ctx->S0.as<int>(), ctx->flag8.as<unsigned>(), ctx->pos.as<i64>(),
                                                                          scan_site(ctx, MAX_LEVELS + 1), ctx->n_sm);
         scan_fin(ctx, InMajorPacked{ctx->pos.as<i64>(), d}, ctx->major_off.as<i64>(),
@@ -487,6 +520,7 @@ static int enqueue_build(amod_ctx* ctx, int mode, int cap, Table<TT> tt, int max
         k_screen_fill<<<GE, WARPS_PER_BLOCK * 32, 0, st>>>(d, ctl, ctx->S0.as<int>(), ctx->flag8.as<unsigned>(), ctx->major_off.as<i64>(),
                                                           ctx->task_veh[0].as<int>(), ctx->task_base[0].as<int>(), ctx->task_q[0].as<int>(),
                                                           ctx->task_nchunk[0].as<int>(), ctx->task_chunk0.as<i64>());
+        CK(cudaEventRecord(get_event(ctx, EV_SCREEN + 1), st));
         ctx->n_launches += 2;
     }
     // ---- levels 1..max_level ----------------------------------------------------------------------------
@@ -599,6 +633,10 @@ static int build_impl(amod_ctx* ctx, const amod_epoch* ep, int loc, amod_stats* 
             for (int v = 0; v < V; v++) base_len = std::max(base_len, off[v + 1] - off[v]);
         }
     }
+    if (mode != AMOD_MODE_OSP) {     // monotone per mode: the captured graph and the level strides stay put once the fleet's longest schedule was seen
+        base_len = std::max(base_len, ctx->base_len_hint[mode]);
+        ctx->base_len_hint[mode] = base_len;
+    }
     int stride[MAX_LEVELS];
     for (int k = 0; k < MAX_LEVELS; k++) stride[k] = std::max(1, std::min(MAXS, base_len + 2 * k));
 
@@ -632,6 +670,7 @@ static int build_impl(amod_ctx* ctx, const amod_epoch* ep, int loc, amod_stats* 
                 cudaError_t ce = cudaStreamEndCapture(st, &graph);
                 if (rc != AMOD_OK) { if (graph) cudaGraphDestroy(graph); return rc; }
                 CK(ce);
+                apply_l2_policy_to_graph(ctx, graph);
                 ce = cudaGraphInstantiate(&gs.exec, graph, 0);
                 cudaGraphDestroy(graph);
                 CK(ce);
@@ -658,7 +697,8 @@ static int build_impl(amod_ctx* ctx, const amod_epoch* ep, int loc, amod_stats* 
         grow(ctx->cap_tasks, h->need_tasks); grow(ctx->cap_chunks, h->need_chunks); grow(ctx->cap_rows, h->need_rows); grow(ctx->cap_items, h->need_perm_items);
         for (int k = 0; k <= max_level; k++) { grow(ctx->cap_trips[k], h->need_trips[k]); grow(ctx->cap_sch[k], h->need_sch[k]); }
         grow(ctx->cap_ent, h->need_ent); grow(ctx->cap_ptr, h->need_ptr); grow(ctx->cap_pst, h->need_pst);
-        if (ctx->cap_tasks > 0x7ffffff0 || ctx->cap_chunks > 0x7ffffff0) return ctx->fail(AMOD_E_LIMIT, "more than 2^31 candidates in one level");
+        if (ctx->cap_tasks > 0x7ffffff0 || ctx->cap_chunks > 0x7ffffff0 || ctx->cap_rows > 0x7ffffff0)
+            return ctx->fail(AMOD_E_LIMIT, "more than 2^31 candidates or base-schedule rows in one level");
     }
     ctx->n_attempts = attempt + 1;
     {
@@ -684,6 +724,10 @@ static int build_impl(amod_ctx* ctx, const amod_epoch* ep, int loc, amod_stats* 
             if (cudaEventElapsedTime(&x, ctx->ev_pool[i], ctx->ev_pool[i + 1]) == cudaSuccess) me += x; else cudaGetLastError();
         }
         out_stats->ms_eval = me;
+        if (!ctx->use_graph && ctx->ev_pool.size() > EV_SCREEN + 1) {
+            float x = 0.f;
+            if (cudaEventElapsedTime(&x, ctx->ev_pool[EV_SCREEN], ctx->ev_pool[EV_SCREEN + 1]) == cudaSuccess) out_stats->ms_screen = x; else cudaGetLastError();
+        }
         out_stats->n_eval_launches = (int)(n_ev / 2);
         const i64 n_screen = (i64)V * d.n_search;
         out_stats->n_screens = n_screen;
@@ -700,6 +744,10 @@ static int build_impl(amod_ctx* ctx, const amod_epoch* ep, int loc, amod_stats* 
         out_stats->n_chunks = (int64_t)h->stats.n_chunks;
         out_stats->n_items = (int64_t)h->stats.n_items;
         out_stats->n_lookups_eval = (int64_t)h->stats.n_lookups_eval;
+        for (int k = 0; k < 16 && k <= MAX_LEVELS; k++) {
+            out_stats->evals_level[k] = (int64_t)h->stats.lvl_evals[k];
+            out_stats->lookups_level[k] = (int64_t)h->stats.lvl_lookups[k];
+        }
     }
     (void)total_tasks;
     if (mode != AMOD_MODE_SBA && run_levels == max_level && h->n_trips[max_level] > 0)

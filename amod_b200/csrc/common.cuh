@@ -12,6 +12,8 @@
 typedef long long i64;
 typedef int32_t code_t;  // stop code: 2*req + (0 pick | 1 drop), -1 = rebalancing stop
 
+#define MAX_LEVELS (AMOD_MAX_TRIP + 1)
+
 // Device view of one epoch (include/amod_b200.h: struct amod_epoch).
 struct DEpoch {
     int n_veh, n_req, n_search, cap, mode;
@@ -56,10 +58,9 @@ struct Level {
     int* veh_start;      // [n_veh+1] trips of vehicle v are [veh_start[v], veh_start[v+1])  (OSP modes)
 };
 
-#define MAX_LEVELS (AMOD_MAX_TRIP + 1)
-
 struct Stats {            // device counters
     unsigned long long n_screens, n_evals, n_lookups, n_sches, n_tasks, flags, n_chunks, n_items, n_lookups_eval;
+    unsigned long long lvl_evals[MAX_LEVELS + 1], lvl_lookups[MAX_LEVELS + 1];   // insertion-search work per trip level (one k_eval launch pair each)
 };
 
 // Device-resident control block: every size the level-synchronous pipeline produces lives here, so

@@ -283,6 +283,8 @@ k_eval(const DEpoch* __restrict__ epp, Table<TT> tt, Level prev, Level cur, cons
             atomicAdd(&stats->n_evals, acc_evals);
             atomicAdd(&stats->n_lookups, acc_lookups);
             atomicAdd(&stats->n_lookups_eval, acc_lookups);
+            atomicAdd(&stats->lvl_evals[cur.k], acc_evals);
+            atomicAdd(&stats->lvl_lookups[cur.k], acc_lookups);
         }
     }
 }

@@ -323,7 +323,9 @@ struct InMajorPacked {       // scan input over the majors of the screen
 struct FinTasksRows {
     Control* ctl; int which; i64 cap_tasks, cap_rows, cap_chunks; int G;
     __device__ __forceinline__ void operator()(i64 packed) const {
-        i64 nt = PACK_LO(packed), nr = PACK_HI(packed), nch = (nr + G - 1) / G;
+        i64 nt = PACK_LO(packed), nr = PACK_HI(packed);
+        if (packed < 0 || nr > 0x7ffffff0ll) nr = 0x7fffffffll;     // the packed row sum left 31 bits: reported as need_rows, the host fails with AMOD_E_LIMIT
+        i64 nch = (nr + G - 1) / G;
         if (nt > ctl->need_tasks) ctl->need_tasks = nt;
         if (nr > ctl->need_rows) ctl->need_rows = nr;
         if (nch > ctl->need_chunks) ctl->need_chunks = nch;

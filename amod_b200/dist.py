@@ -23,9 +23,11 @@ def merge_vehicle_major(parts: list[tuple[Pool, np.ndarray]], n_veh: int) -> Poo
     return cat.take(order)
 
 
-def merge_sba(parts: list[tuple[Pool, np.ndarray]], n_veh: int) -> Pool:
-    """SBA order is request-major then one empty pair per vehicle (dispatch_sba.py:56-69):
-    pairs sort by (request position, vehicle), the empty pairs by vehicle."""
+def merge_sba(parts: list[tuple[Pool, np.ndarray]], n_veh: int, search: np.ndarray | None = None) -> Pool:
+    """SBA order is request-major then one empty pair per vehicle (dispatch_sba.py:56-69): pairs sort by
+    (position of the request in new_received_rids, vehicle), the empty pairs by vehicle.  `search` is the epoch's
+    search array (request indices in the reference's loop order, dispatch_sba.py:56); without it the request
+    index itself is taken as the position (true when the simulator hands ascending rids)."""
     pools = []
     for pool, sel in parts:
         p = Pool(stats=pool.stats, **{f: getattr(pool, f) for f in Pool.FIELDS})
@@ -33,13 +35,18 @@ def merge_sba(parts: list[tuple[Pool, np.ndarray]], n_veh: int) -> Pool:
         pools.append(p)
     cat = concat_pools(pools)
     is_empty = (cat.ent_trip_off[1:] - cat.ent_trip_off[:-1]) == 0
-    req = np.where(is_empty, np.iinfo(np.int32).max, cat.trip_req[np.minimum(cat.ent_trip_off[:-1], max(cat.trip_req.size - 1, 0))]
-                   if cat.trip_req.size else 0)
+    req = cat.trip_req[np.minimum(cat.ent_trip_off[:-1], max(cat.trip_req.size - 1, 0))] if cat.trip_req.size else np.zeros(cat.n_entries, dtype=np.int64)
+    if search is not None and req.size:
+        search = np.asarray(search, dtype=np.int64)
+        pos_of = np.full(int(max(search.max(initial=-1), req.max(initial=-1))) + 1, np.iinfo(np.int32).max, dtype=np.int64)
+        pos_of[search[::-1]] = np.arange(search.size - 1, -1, -1)      # first position of a request in the loop
+        req = pos_of[req]
+    req = np.where(is_empty, np.iinfo(np.int64).max, req)
     order = np.lexsort((cat.ent_veh, req))
     return cat.take(order)
 
 
-def allgather_pool(local: Pool, sel: np.ndarray, n_veh: int, mode_sba: bool = False, device=None) -> Pool:
+def allgather_pool(local: Pool, sel: np.ndarray, n_veh: int, mode_sba: bool = False, device=None, search=None) -> Pool:
     """All-gather the rank-local pools (torch.distributed; NCCL over NVLink when `device` is a
     CUDA device, gloo on CPU) and return the full vehicle-major pool on every rank."""
     import torch
@@ -68,7 +75,9 @@ def allgather_pool(local: Pool, sel: np.ndarray, n_veh: int, mode_sba: bool = Fa
         fields[f] = gather(getattr(local, f), mx[col], col, extra)
     sels = gather(np.asarray(sel, dtype=np.int64), mx[3], 3)
     parts = [(Pool(**{f: fields[f][r] for f in Pool.FIELDS}), sels[r]) for r in range(world)]
-    return (merge_sba if mode_sba else merge_vehicle_major)(parts, n_veh)
+    if mode_sba:
+        return merge_sba(parts, n_veh, search)
+    return merge_vehicle_major(parts, n_veh)
 
 
 def merge_vehicle_major_torch(rank_pools: list[dict], world: int, totals: dict | None = None) -> dict:
@@ -161,16 +170,36 @@ class PeerPool:
         self.b._check(self.b.lib.amod_gpool_view(self.b.h, C.byref(v)))
         return v
 
-    def fetch(self) -> Pool:
+    def fetch(self, reuse: bool = False) -> Pool:
+        """This rank's assembled pool as numpy arrays.  reuse=True: views of grow-only page-locked buffers owned by
+        this object (straight DMA, overwritten by the next fetch), like PoolBuilder.fetch(reuse=True)."""
         import ctypes as C
 
         from . import capi
         v = self.view()
-        n = {"e": v.n_entries, "e1": v.n_entries + 1, "t": v.n_trip_reqs, "s": v.n_stops}
-        arrs = {name: np.empty(max(int(n[key]), 1), dtype=dt) for name, dt, key in capi.POOL_FIELDS}
+        n = {"e": int(v.n_entries), "e1": int(v.n_entries) + 1, "t": int(v.n_trip_reqs), "s": int(v.n_stops)}
+        if reuse:
+            bufs = getattr(self, "_host_bufs", None)
+            if bufs is None or any(bufs[name].size < max(n[key], 1) for name, _dt, key in capi.POOL_FIELDS):
+                self._release_host_bufs()
+                bufs = {name: np.empty(max(int(1.5 * n[key]) + 1024, 1), dtype=dt) for name, dt, key in capi.POOL_FIELDS}
+                for a in bufs.values():
+                    a.fill(0)
+                    self.b._check(self.b.lib.amod_host_register(self.b.h, a.ctypes.data, a.nbytes))
+                self._host_bufs = bufs
+            arrs = bufs
+        else:
+            arrs = {name: np.empty(max(n[key], 1), dtype=dt) for name, dt, key in capi.POOL_FIELDS}
         o = capi.AmodPool()
         o.cap_entries, o.cap_trip_reqs, o.cap_stops = v.n_entries, v.n_trip_reqs, v.n_stops
         for name, _dt, _key in capi.POOL_FIELDS:
             setattr(o, name, arrs[name].ctypes.data)
         self.b._check(self.b.lib.amod_gpool_fetch(self.b.h, C.byref(o)))
-        return Pool(**{name: arrs[name][:int(n[key])] for name, _dt, key in capi.POOL_FIELDS})
+        return Pool(**{name: arrs[name][:n[key]] for name, _dt, key in capi.POOL_FIELDS})
+
+    def _release_host_bufs(self):
+        bufs = getattr(self, "_host_bufs", None)
+        if bufs and getattr(self.b, "h", None):
+            for a in bufs.values():
+                self.b.lib.amod_host_unregister(self.b.h, a.ctypes.data)
+        self._host_bufs = None

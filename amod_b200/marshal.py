@@ -398,7 +398,24 @@ class LazyPoolRecords:
         self.delays = self._pool.ent_delay
         self.stats = pool.stats
         self.builder_token = None
-        self.scored = False
+        self._scored = False
+        self.user_sorted = False       # list.sort() by a consumer: the GPU assigner's permutation no longer applies
+
+    @property
+    def scored(self) -> bool:
+        return self._scored
+
+    @scored.setter
+    def scored(self, value: bool):
+        """The scorer (scheduling.py:140-161) overwrites pair[3] with the delay and pair[4] with len(trip): records
+        built before the flag flips carry cost / 0.0 and are rewritten in place (identity of the lists is kept)."""
+        value = bool(value)
+        if value and not self._scored:
+            p = self._pool
+            for e, rec in self._cache.items():      # every record ever built lives in the cache, keyed by pool entry
+                rec[3] = p.ent_delay[e]
+                rec[4] = len(rec[1])
+        self._scored = value
 
     def __len__(self):
         return self._pool.n_entries
@@ -433,9 +450,16 @@ class LazyPoolRecords:
         return self._entry(int(self._perm[i]) if self._perm is not None else i)
 
     def apply_order(self, order: np.ndarray):
-        """The in-place stable sort the reference's assigner performs (ilp_assign.py:109), as a permutation."""
+        """The in-place stable sort the reference's assigner performs (ilp_assign.py:109), as a permutation:
+        order[i] = pool entry (in the builder's order) that stands at position i of the sorted list.  If something
+        already iterated the list (records materialised), the materialised list is permuted in place as well, so
+        positions mean "index in the sorted list" either way."""
+        if self.user_sorted:
+            raise RuntimeError("the pair list was re-sorted by the caller: positions no longer refer to the builder's pool order")
         order = np.asarray(order)
-        self._perm = order if self._perm is None else self._perm[order]
+        if self._full is not None:
+            self._full[:] = [self._cache[e] for e in order.tolist()]
+        self._perm = order
 
     def materialise(self) -> list:
         if self._full is None:
@@ -447,6 +471,23 @@ class LazyPoolRecords:
 
     def sort(self, key=None, reverse=False):
         self.materialise().sort(key=key, reverse=reverse)
+        self.user_sorted = True
+
+
+def pool_digest(pool: Pool) -> str:
+    """Order-sensitive fingerprint of a pool: entry count, vehicle / kind / CSR offsets / trip requests / stop
+    codes, and the float64 BITS of costs and delays.  Two pools share a digest iff they are bit-identical in
+    every field the parity tests compare (pools_equal with rtol=0, check_kind=True)."""
+    import hashlib
+    h = hashlib.blake2b(digest_size=16)
+    h.update(np.int64(pool.n_entries).tobytes())
+    for f, dt in (("ent_veh", "<i4"), ("ent_kind", "<i4"), ("ent_trip_off", "<i8"), ("ent_sche_off", "<i8"), ("trip_req", "<i4"),
+                  ("sche_code", "<i4"), ("ent_nfeas", "<i4"), ("ent_cost", "<f8"), ("ent_delay", "<f8")):
+        a = np.ascontiguousarray(getattr(pool, f), dtype=np.dtype(dt))
+        h.update(f.encode())
+        h.update(np.int64(a.size).tobytes())
+        h.update(a.tobytes())
+    return h.hexdigest()
 
 
 def pools_equal(a: Pool, b: Pool, rtol: float = 0.0, check_delay: bool = True, check_nfeas: bool = True,

@@ -228,3 +228,21 @@ def random_epoch(tt: np.ndarray, n_veh: int, n_pending: int, cap: int, mode: int
                  veh_status=status, veh_sche_off=off, sche_code=code, sche_onboard=onb, veh_reb_node=reb_node,
                  veh_reb_ddl=reb_ddl, req_id=gid, req_onid=on[perm], req_dnid=dn[perm], req_clp=clp[perm],
                  req_cld=cld[perm], req_tr=tr[perm], req_ts=ts[perm], search=search)
+
+
+def tile_fleet(ep, n: int):
+    """Fleet of n x V vehicles on the same requests: the snapshot's fleet n times, every further copy in a
+    different (seeded) vehicle order, so that an interleaved rank slice is a sample of the whole fleet and not
+    the same V/n vehicles n times over.  (bench.py's weak-scaling and size-sweep workloads.)"""
+    if n == 1:
+        return ep
+    from .marshal import Epoch
+    parts = [ep] + [ep.take(np.random.default_rng(1000 + c).permutation(ep.n_veh)) for c in range(1, n)]
+    kw = {f: getattr(ep, f) for f in Epoch.FIELDS}
+    for f in ("veh_nid", "veh_t_to_nid", "veh_load", "veh_status", "veh_reb_node", "veh_reb_ddl", "sche_code", "sche_onboard"):
+        kw[f] = np.concatenate([getattr(p, f) for p in parts])
+    lens = np.concatenate([np.diff(p.veh_sche_off) for p in parts])
+    off = np.zeros(lens.size + 1, dtype=np.int32)
+    np.cumsum(lens, out=off[1:])
+    kw["veh_sche_off"] = off
+    return Epoch(T=ep.T, cap=ep.cap, mode=ep.mode, **kw)

@@ -3,19 +3,30 @@
 pool-build ms/epoch, 2,000 vehicles, capacity 4, Manhattan-scale synthetic demand, 30 s epochs).
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+                    [--config cfg2|cfg3|cfg4|cfg5] [--fleet-mult M] [--scaling weak|strong]
 
 A *step* is one pass of the hot path (dispatch_osp.compute_candidate_veh_trip_pairs, cut-off
-disabled) over one recorded epoch snapshot (bench_data/cfg2_epoch*.npz, produced by running the
+disabled) over one recorded epoch snapshot (bench_data/<cfg>_epoch*.npz, produced by running the
 reference simulator on the synthetic table, see bench_data/make_snapshots.py).  The unit, a
 "schedule evaluated", is one execution of scheduling.test_constraints_get_cost AS THE REFERENCE
 WOULD PERFORM IT; the kernels count it with the reference's early-exit semantics and the tests
 check the count against the oracle, so GPU and CPU arms share the numerator.
 
-N > 1 (torchrun, one rank per GPU): weak scaling — the fleet is N x 2,000 vehicles (the snapshot's
-fleet N times against the same request set, further copies in a seeded vehicle order; BASELINE.json
-configs[3] at N=4), vehicles are interleaved over ranks, every rank builds its slice and the
-vehicle-major pool is assembled on every rank over NVLink peer memory (amod_b200/dist.py PeerPool:
-bulk peer stores + epoch flags, no host-side collective in the timed region).
+Workloads (BASELINE.json configs[1..4]; configs[0] is the CPU parity run in tests/):
+  cfg2 (default)  OSP, 2,000 vehicles cap 4, 8 snapshots.  N > 1: WEAK scaling, the fleet is N x 2,000 vehicles
+                  (synth.tile_fleet) against the same requests.  --fleet-mult M fixes the fleet at M x 2,000 instead
+                  (single-GPU size sweep, or STRONG scaling with --gpus N --scaling strong).
+  cfg3            the same with capacity 8 (large permutation search).
+  cfg4            OSP, 8,000 vehicles cap 4, demand x4 (bench_data/cfg4_*): STRONG scaling, the fleet is sharded.
+  cfg5            peak epoch: SBA vehicle-request matrix 20,000 x 5,000 + NPO nearest-idle-vehicle match.
+
+N > 1 (torchrun, one rank per GPU): vehicles are sharded over the ranks, every rank builds its slice and the
+vehicle-major pool is assembled over NVLink peer memory on the rank that hosts the (unchanged) assigner
+(amod_b200/dist.py PeerPool; no host-side collective in the timed region).
+
+Parity is part of the line: before timing, every snapshot's pool (at N > 1 the ASSEMBLED pool on rank 0) is
+fingerprinted (marshal.pool_digest) and compared with the oracle's fingerprint stored in bench_data/digests.json
+(bench_data/make_digests.py) -> "parity": {"checked": true, "ok": ..., "snapshots": n}.
 """
 from __future__ import annotations
 
@@ -40,35 +51,41 @@ except Exception:
     METRIC = "schedules evaluated/sec; OSP pool-build ms/epoch (2000 veh cap4) at 1/2/4/8 B200"
 UNIT = "schedules/s"
 
+CONFIGS = {
+    "cfg2": dict(tag="cfg2", scaling="weak", what="OSP pool build (cut-off disabled), {fleet} veh cap 4, Manhattan-scale synthetic epoch "
+                 "snapshots x{n} (bench_data/cfg2_*), 4091-node fp32 table"),
+    "cfg3": dict(tag="cfg3", scaling="weak", what="OSP pool build (cut-off disabled), {fleet} veh cap 8 (large permutation search), "
+                 "synthetic epoch snapshots x{n} (bench_data/cfg3_*), 4091-node fp32 table"),
+    "cfg4": dict(tag="cfg4", scaling="strong", what="OSP scale-out, {fleet} veh cap 4, demand x4 synthetic epoch snapshots x{n} "
+                 "(bench_data/cfg4_*), vehicle-sharded, 4091-node fp32 table"),
+    "cfg5": dict(tag="cfg5", scaling="strong", what="peak epoch: SBA feasibility/cost matrix {fleet} veh x {req} new requests + NPO "
+                 "nearest-idle-vehicle match (bench_data/cfg5_*), 4091-node fp32 table"),
+}
+
+
+def load_digests():
+    try:
+        return json.load(open(os.path.join(ROOT, "bench_data", "digests.json")))
+    except Exception:
+        return {}
+
 
 def load_snapshots(tag="cfg2"):
     from amod_b200.marshal import Epoch
     files = sorted(glob.glob(os.path.join(ROOT, "bench_data", f"{tag}_epoch*.npz")))
     if not files:
-        raise SystemExit("bench_data/ holds no epoch snapshots (run bench_data/make_snapshots.py)")
+        raise SystemExit(f"bench_data/ holds no {tag} epoch snapshots (run bench_data/make_snapshots.py)")
     snaps = []
     for f in files:
         z = np.load(f)
-        snaps.append((os.path.basename(f), Epoch.from_npz_dict(z, "ep_"), int(z["n_evals"]), int(z["n_lookups"])))
+        extra = {k: z[k] for k in ("npo_idle_nid", "npo_pend_onid") if k in z.files}
+        snaps.append((os.path.basename(f), Epoch.from_npz_dict(z, "ep_"), int(z["n_evals"]), int(z["n_lookups"]), extra))
     return snaps
 
 
 def tile_fleet(ep, n):
-    """Fleet of n x V vehicles on the same requests: the snapshot's fleet n times, every further copy in a
-    different (seeded) vehicle order, so that an interleaved rank slice is a sample of the whole fleet and not
-    the same V/n vehicles n times over."""
-    if n == 1:
-        return ep
-    from amod_b200.marshal import Epoch
-    parts = [ep] + [ep.take(np.random.default_rng(1000 + c).permutation(ep.n_veh)) for c in range(1, n)]
-    kw = {f: getattr(ep, f) for f in Epoch.FIELDS}
-    for f in ("veh_nid", "veh_t_to_nid", "veh_load", "veh_status", "veh_reb_node", "veh_reb_ddl", "sche_code", "sche_onboard"):
-        kw[f] = np.concatenate([getattr(p, f) for p in parts])
-    lens = np.concatenate([np.diff(p.veh_sche_off) for p in parts])
-    off = np.zeros(lens.size + 1, dtype=np.int32)
-    np.cumsum(lens, out=off[1:])
-    kw["veh_sche_off"] = off
-    return Epoch(T=ep.T, cap=ep.cap, mode=ep.mode, **kw)
+    from amod_b200 import synth
+    return synth.tile_fleet(ep, n)
 
 
 class ClockSampler(threading.Thread):
@@ -111,66 +128,99 @@ def host_threads() -> int:
         return max(1, os.cpu_count() or 1)
 
 
-def cpu_leg(snaps, tt, budget_s=10.0):
-    """Oracle (the C port of the reference's path) on the host cores, bounded sample."""
+def _oracle_build(oracle, ep, tt, **kw):
+    from amod_b200 import marshal
+    if ep.mode == marshal.MODE_SBA:
+        kw.pop("veh_lo", None); kw.pop("veh_step", None)
+        return oracle.sba_build(ep, tt, n_threads=kw.get("n_threads", 1))
+    return oracle.osp_build(ep, tt, **kw)
+
+
+def cpu_leg(work_eps, tt, budget_s=10.0):
+    """Oracle (the C port of the reference's path) on the host cores, bounded sample of the same workload."""
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import oracle
+    from amod_b200 import marshal
     threads = host_threads()
-    # warm (thread pool, table pages), calibrate on every 16th vehicle, then whole snapshots for ~budget_s
-    t = time.perf_counter()
-    p = oracle.osp_build(snaps[0][1], tt, n_threads=threads, veh_step=16)
-    rate = max(p.stats["n_evals"], 1) / max(time.perf_counter() - t, 1e-6)
+    sba = work_eps[0].mode == marshal.MODE_SBA
+    _oracle_build(oracle, work_eps[0], tt, n_threads=threads, veh_step=16)      # warm (thread pool, table pages)
     evals, secs, n_done = 0, 0.0, 0
     while secs < budget_s and n_done < 5000:
-        name, ep, n_evals, _ = snaps[n_done % len(snaps)]
-        step = 1 if n_evals / rate < budget_s else int(np.ceil(n_evals / (rate * budget_s)))
+        ep = work_eps[n_done % len(work_eps)]
         t = time.perf_counter()
-        p = oracle.osp_build(ep, tt, n_threads=threads, veh_step=step)
+        p = _oracle_build(oracle, ep, tt, n_threads=threads)
         secs += time.perf_counter() - t
         evals += p.stats["n_evals"]
         n_done += 1
-    mean_evals = float(np.mean([s[2] for s in snaps]))
     return {"value": evals / secs, "unit": UNIT, "cores": threads, "kind": "port",
             "sample": f"{n_done} snapshot builds (all vehicles) in {secs:.2f} s, {evals} schedules, "
-                      f"oracle/amod_oracle.c with OpenMP over vehicles",
-            "ms_per_epoch": 1e3 * mean_evals / (evals / secs)}
+                      f"oracle/amod_oracle.c with OpenMP over {'requests' if sba else 'vehicles'}",
+            "ms_per_epoch": 1e3 * secs / max(n_done, 1)}
+
+
+def python_reference_leg(budget_s=20.0):
+    """The reference's OWN Python implementation (git-ignored scratch copy under baseline/_ref, shipped to the box by
+    gpurun), one core, on a bounded vehicle sample of the first snapshot; None when the copy is not there."""
+    try:
+        sys.path.insert(0, os.path.join(ROOT, "baseline"))
+        import ref_arm
+    except Exception:
+        return None
+    try:
+        return ref_arm.time_reference_python(ROOT, budget_s=budget_s)
+    except Exception as e:      # the baseline is a report, never a reason to lose the bench line
+        return {"unavailable": f"{type(e).__name__}: {e}"[:200]}
+
+
+def workload_for(args, world):
+    cfg = CONFIGS[args.config]
+    scaling = args.scaling or cfg["scaling"]
+    mult = args.fleet_mult if args.fleet_mult else (world if scaling == "weak" else 1)
+    return cfg, scaling, mult
 
 
 def run_reference(args):
-    """--impl reference: the reference's CPU path (oracle port: the Python reference cannot travel
-    to the GPU box) on all host threads, same snapshots, each step a bounded vehicle sample."""
+    """--impl reference: the reference's CPU path (oracle port; the Python reference itself is timed on one core
+    as `python_reference` inside cpu_baseline) on all host threads, same workload as our arm at this N (the same
+    tiled fleet), each step a bounded vehicle sample."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    from amod_b200 import synth
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    from amod_b200 import marshal, synth
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import oracle
+    cfg, scaling, mult = workload_for(args, max(world, args.gpus))
     tt = synth.make_road_graph(seed=0).tt
-    snaps = load_snapshots()
+    snaps = load_snapshots(cfg["tag"])
+    eps = [tile_fleet(s[1], mult) for s in snaps]
     threads = host_threads()
-    name, ep, n_evals, _ = snaps[0]
+    sba = eps[0].mode == marshal.MODE_SBA
     t = time.perf_counter()
-    p = oracle.osp_build(ep, tt, n_threads=threads, veh_step=64)
+    p = _oracle_build(oracle, eps[0], tt, n_threads=threads, veh_step=64)
     rate = max(p.stats["n_evals"], 1) / max(time.perf_counter() - t, 1e-6)
+    n_evals = snaps[0][2] * mult
     per_step_budget = max(2.0, min(20.0, 150.0 / max(args.steps + args.warmup, 1)))
-    step = int(max(1, min(64, np.ceil(n_evals / (rate * per_step_budget)))))
+    step = 1 if sba else int(max(1, min(64 * mult, np.ceil(n_evals / (rate * per_step_budget)))))
     evals, t_total = 0, 0.0
     for i in range(args.warmup + args.steps):
-        _n, e, _ne, _nl = snaps[i % len(snaps)]
+        e = eps[i % len(eps)]
         t = time.perf_counter()
-        p = oracle.osp_build(e, tt, n_threads=threads, veh_lo=i % step, veh_step=step)
+        p = _oracle_build(oracle, e, tt, n_threads=threads, veh_lo=i % step, veh_step=step)
         dt = time.perf_counter() - t
         if i >= args.warmup:
             evals += p.stats["n_evals"]; t_total += dt
     val = evals / t_total
+    fleet = eps[0].n_veh
     line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": 1e3 * t_total / args.steps, "higher_is_better": True, "scaling": "weak",
+            "warmup": args.warmup, "ms_per_step": 1e3 * t_total / args.steps, "higher_is_better": True, "scaling": scaling,
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": "OSP pool build, 2000 veh cap 4, Manhattan-scale synthetic epoch snapshots (bench_data/cfg2_*)",
+            "config": {"workload": cfg["what"].format(fleet=fleet, n=len(eps), req=eps[0].n_search), "fleet": fleet,
                        "sample": f"every {step}th vehicle per step"},
             "cpu_baseline": {"value": val, "unit": UNIT, "cores": threads, "kind": "port",
-                             "sample": f"every {step}th vehicle of each snapshot, {args.steps} steps, oracle/amod_oracle.c (OpenMP); "
-                                       f"the Python reference itself measured 45-71k schedules/s/core (BASELINE.md)"},
+                             "sample": f"every {step}th vehicle of each snapshot, {args.steps} steps, oracle/amod_oracle.c (OpenMP), the C "
+                                       f"restatement of the reference's path; the Python reference itself: see cpu_baseline.python_reference "
+                                       f"of our arm (BASELINE.md)"},
             "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print_json(line)
 
@@ -181,7 +231,11 @@ def main():
     ap.add_argument("--steps", type=int, default=64)
     ap.add_argument("--warmup", type=int, default=8)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--config", default="cfg2", choices=sorted(CONFIGS))
+    ap.add_argument("--fleet-mult", type=int, default=0, help="fleet = M x the snapshot's fleet (default: N for weak scaling, 1 for strong)")
+    ap.add_argument("--scaling", default=None, choices=["weak", "strong"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-graph", action="store_true", help="plain stream launches instead of the captured epoch graph (profiling)")
     args = ap.parse_args()
     # stdout carries exactly one JSON line: everything else (NCCL banner, warnings) goes to stderr
     real_stdout = os.dup(1)
@@ -191,9 +245,11 @@ def main():
     if args.impl == "reference":
         return run_reference(args)
 
+    import ctypes as C
+
     import torch
     import torch.distributed as dist
-    from amod_b200 import capi, synth
+    from amod_b200 import capi, marshal, synth
     from amod_b200.pool import PoolBuilder
 
     rank = int(os.environ.get("RANK", "0"))
@@ -207,20 +263,30 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
     assert world == args.gpus or world == 1
 
+    cfg, scaling, mult = workload_for(args, world)
     tt = synth.make_road_graph(seed=0).tt
-    snaps = load_snapshots()
+    snaps = load_snapshots(cfg["tag"])
+    digests = load_digests()
     b = PoolBuilder(tt, device=local)
     stream = torch.cuda.Stream(device=dev)
     torch.cuda.set_stream(stream)
     b.set_stream(stream.cuda_stream)          # CUDA events below bracket the stream the kernels run on
+    if args.no_graph:
+        b.set_graph(False)
+    sba = snaps[0][1].mode == marshal.MODE_SBA
 
     # per-rank slice of the (tiled) fleet, resident in HBM before the timed region
     work = []
-    for name, ep, n_evals, n_lookups in snaps:
-        full = tile_fleet(ep, world)
+    for name, ep, n_evals, n_lookups, extra in snaps:
+        full = tile_fleet(ep, mult)
         mine, sel = full.shard(rank, world)
         tens = {f: torch.from_numpy(getattr(mine, f)).to(dev) for f in capi.EPOCH_PTR_FIELDS}
-        work.append(dict(name=name, host=mine, dev=tens, sel=sel, n_evals_full=n_evals * world, n_veh_full=full.n_veh))
+        w = dict(name=name, host=mine, dev=tens, sel=sel, n_veh_full=full.n_veh, full=full if rank == 0 else None,
+                 digest=digests.get(f"{name}@x{mult}"))
+        if extra:        # cfg5: the NPO match of the same epoch (idle vehicles x pending requests)
+            w["npo_host"] = (np.ascontiguousarray(extra["npo_idle_nid"], dtype=np.int32), np.ascontiguousarray(extra["npo_pend_onid"], dtype=np.int32))
+            w["npo_dev"] = tuple(torch.from_numpy(a).to(dev) for a in w["npo_host"])
+        work.append(w)
 
     class DevEp:
         pass
@@ -235,10 +301,9 @@ def main():
 
     peer = {}
 
-    def allgather_pool():
-        """Assemble the fleet-wide vehicle-major pool on every rank: NCCL all-gather of the per-vehicle
-        counts (a few KB), then each rank's scatter kernel writes its entries into all ranks' global pools
-        with peer stores over NVLink, then a barrier (amod_b200/dist.py PeerPool)."""
+    def assemble():
+        """Assemble the fleet-wide pool in the reference's order on the assigner's rank (rank 0) over NVLink peer
+        memory (amod_b200/dist.py PeerPool)."""
         from amod_b200 import dist as adist
         if "pp" not in peer:
             P, NT, NS = b.pool_sizes()
@@ -247,18 +312,65 @@ def main():
         peer["pp"].assemble()
 
     ptr_of = lambda t: t.data_ptr()
+    npo_out = {}
+
+    def npo_resident(w):
+        idle, pend = w["npo_dev"]
+        m = min(idle.numel(), pend.numel())
+        if "oi" not in npo_out:
+            npo_out.update(oi=np.zeros(max(m, 1), np.int32), op=np.zeros(max(m, 1), np.int32), od=np.zeros(max(m, 1), np.float64))
+        n_out, n_rounds = C.c_int32(0), C.c_int32(0)
+        b._check(b.lib.amod_npo_match(b.h, idle.data_ptr(), idle.numel(), pend.data_ptr(), pend.numel(), capi.LOC_DEVICE,
+                                      npo_out["oi"].ctypes.data, npo_out["op"].ctypes.data, npo_out["od"].ctypes.data,
+                                      C.byref(n_out), C.byref(n_rounds)))
+        return n_out.value, n_rounds.value
 
     def step_resident(i):
         w = work[i % len(work)]
         st = b.build(dev_epoch(w), loc=capi.LOC_DEVICE, ptr_of=ptr_of)
         if world > 1:
-            allgather_pool()
+            assemble()
+        if "npo_dev" in w:
+            npo_resident(w)
         return st
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
+
+    # ---- parity (untimed): every snapshot's pool against the oracle's fingerprint ---------------------------------
+    def npo_digest(oi, op, od):
+        import hashlib
+        h = hashlib.blake2b(digest_size=16)
+        for a, dt in ((oi, "<i4"), (op, "<i4"), (od, "<f8")):
+            h.update(np.ascontiguousarray(a, dtype=np.dtype(dt)).tobytes())
+        return h.hexdigest()
+
+    parity = {"checked": True, "ok": True, "snapshots": 0, "against": "oracle fingerprints in bench_data/digests.json (entries, order, "
+              "trips, schedules, float64 cost/delay bits; n_evals)", "pool": "assembled on rank 0" if world > 1 else "local"}
+    for i, w in enumerate(work):
+        st = step_resident(i)
+        ne = torch.tensor([float(st["n_evals"])], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(ne, op=dist.ReduceOp.SUM)
+        if rank == 0:
+            got = peer["pp"].fetch() if world > 1 else b.fetch()
+            dg = w["digest"]
+            if dg is None:
+                parity["checked"] = False
+                parity.setdefault("missing", []).append(f"{w['name']}@x{mult}")
+            else:
+                ok = marshal.pool_digest(got) == dg["digest"] and got.n_entries == dg["n_entries"] and int(ne.item()) == dg["n_evals"]
+                if "npo_host" in w and "npo_digest" in dg:
+                    oi, op, od = b.npo_match(*w["npo_host"])
+                    ok = ok and npo_digest(oi, op, od) == dg["npo_digest"]
+                parity["ok"] = parity["ok"] and bool(ok)
+                if not ok:
+                    parity.setdefault("failed", []).append(w["name"])
+                parity["snapshots"] += 1
+    if not parity["checked"]:
+        parity["ok"] = None
 
     # ---- device-resident arm (value) ---------------------------------------------------------------
     for i in range(args.warmup):
@@ -280,13 +392,23 @@ def main():
     # dominant-kernel time: the same steps once more with plain stream launches, where every k_eval launch is
     # bracketed by CUDA events on the build stream (a captured graph cannot be timed per node)
     b.set_graph(False)
-    ms_eval, n_eval_launches, lookups_eval_p = 0.0, 0, 0
-    for i in range(min(args.steps, 2 * len(work))):
-        st = b.build(dev_epoch(work[(args.warmup + i) % len(work)]), loc=capi.LOC_DEVICE, ptr_of=ptr_of)
+    ms_eval, n_eval_launches, lookups_eval_p, ms_screen, screens_p, ms_npo, npo_pairs = 0.0, 0, 0, 0.0, 0, 0.0, 0
+    prof_steps = min(args.steps, 2 * len(work))
+    for i in range(prof_steps):
+        w = work[(args.warmup + i) % len(work)]
+        st = b.build(dev_epoch(w), loc=capi.LOC_DEVICE, ptr_of=ptr_of)
         ms_eval += st["ms_eval"]; n_eval_launches += st["n_eval_launches"]
         lookups_eval_p += st["n_lookups_eval"]
-    b.set_graph(True)
-    prof_steps = min(args.steps, 2 * len(work))
+        ms_screen += st.get("ms_screen", 0.0); screens_p += st["n_screens"]
+        if "npo_dev" in w:
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(stream)
+            _n, rounds = npo_resident(w)
+            e1.record(stream)
+            torch.cuda.synchronize()
+            ms_npo += e0.elapsed_time(e1)
+            npo_pairs += w["npo_dev"][0].numel() * w["npo_dev"][1].numel()
+    b.set_graph(not args.no_graph)
     t_ms = torch.tensor([ms], dtype=torch.float64, device=dev)
     tot = torch.tensor([float(evals), float(launches), float(entries)], dtype=torch.float64, device=dev)
     if world > 1:
@@ -296,14 +418,26 @@ def main():
     evals_all, launches_all, entries_all = (float(x) for x in tot.tolist())
 
     # ---- end-to-end arm: C-ABI call with HOST buffers, H2D + D2H inside the timed region ------------
+    # every rank uploads its slice from host memory; the rank hosting the assigner (rank 0) reads the result back:
+    # its local pool at N = 1, the ASSEMBLED fleet-wide pool at N > 1
     def step_e2e(i):
         w = work[i % len(work)]
-        pool = b.build_pool(w["host"], reuse=True)
-        if world > 1:
-            allgather_pool()
         h2d = sum(getattr(w["host"], f).nbytes for f in capi.EPOCH_PTR_FIELDS)
-        d2h = sum(getattr(pool, f).nbytes for f, _d, _k in capi.POOL_FIELDS)
-        return pool.stats["n_evals"], h2d, d2h
+        d2h = 0
+        if world == 1:
+            pool = b.build_pool(w["host"], reuse=True)
+            n_ev = pool.stats["n_evals"]
+            d2h = sum(getattr(pool, f).nbytes for f, _d, _k in capi.POOL_FIELDS)
+        else:
+            n_ev = b.build(w["host"])["n_evals"]
+            assemble()
+            if rank == 0:
+                pool = peer["pp"].fetch(reuse=True)
+                d2h = sum(getattr(pool, f).nbytes for f, _d, _k in capi.POOL_FIELDS)
+        if "npo_host" in w:
+            oi, _op, _od = b.npo_match(*w["npo_host"])
+            h2d += sum(a.nbytes for a in w["npo_host"]); d2h += 16 * oi.size
+        return n_ev, h2d, d2h
 
     for i in range(min(args.warmup, 2)):
         step_e2e(i)
@@ -316,11 +450,12 @@ def main():
     barrier()
     e_s = time.perf_counter() - t0
     t_e = torch.tensor([e_s], dtype=torch.float64, device=dev)
-    tot_e = torch.tensor([float(e_evals)], dtype=torch.float64, device=dev)
+    tot_e = torch.tensor([float(e_evals), float(e_h2d), float(e_d2h)], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t_e, op=dist.ReduceOp.MAX)
         dist.all_reduce(tot_e, op=dist.ReduceOp.SUM)
-    e2e_val = float(tot_e.item()) / float(t_e.item())
+    e_evals_all, e_h2d_all, e_d2h_all = (float(x) for x in tot_e.tolist())
+    e2e_val = e_evals_all / float(t_e.item())
     clocks = sampler.stop() if sampler else None       # sampled across both timed regions (resident and end-to-end)
 
     if rank != 0:
@@ -328,7 +463,7 @@ def main():
             dist.destroy_process_group()
         return
 
-    # ---- roofline of the dominant kernel (k_eval: the insertion search) -----------------------------
+    # ---- roofline of the dominant kernel ------------------------------------------------------------
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -342,40 +477,61 @@ def main():
     o_t = torch.from_numpy(rng.integers(1, tt.shape[0] + 1, size=ng).astype(np.int32)).to(dev)
     d_t = torch.from_numpy(rng.integers(1, tt.shape[0] + 1, size=ng).astype(np.int32)).to(dev)
     out_t = torch.empty(ng, dtype=torch.float32, device=dev)
-    import ctypes as C
     gms = C.c_double(0.0)
     b._check(b.lib.amod_gather_bench(b.h, o_t.data_ptr(), d_t.data_ptr(), out_t.data_ptr(), ng, 5, C.byref(gms)))
     l2_gather_gbs = ng * 32 / (gms.value * 1e-3) / 1e9
-    alg_bytes = lookups_eval_p * 32.0          # one 32 B L2 sector per reference lookup
-    achieved = alg_bytes / (ms_eval * 1e-3) / 1e9 if ms_eval > 0 else 0.0
-    traffic = None
+    traffic_info = {}
     try:
-        traffic = json.load(open(os.path.join(ROOT, "profiles", "eval_traffic.json")))["dram_bytes_per_launch"]
+        traffic_info = json.load(open(os.path.join(ROOT, "profiles", "eval_traffic.json")))
     except Exception:
         pass
-    roofline = {"bound": "hbm", "kernel": "k_eval (insertion search, count + fill launches)", "achieved": achieved,
+    step_ms = ms / args.steps
+    if sba and ms_screen > ms_eval:     # cfg5: the 10^8-pair reachability screen dominates (one lookup per pair)
+        alg_bytes, k_ms, k_launches = screens_p * 32.0, ms_screen, 2 * prof_steps
+        kname = "k_screen_count + k_screen_fill (reachability screen, dispatch_sba.py:59)"
+        traffic = None
+    else:
+        alg_bytes, k_ms, k_launches = lookups_eval_p * 32.0, ms_eval, n_eval_launches
+        kname = "k_eval (insertion search, count + fill launches)"
+        traffic = traffic_info.get(args.config, {}).get("dram_bytes_per_launch") if isinstance(traffic_info.get(args.config), dict) else None
+    achieved = alg_bytes / (k_ms * 1e-3) / 1e9 if k_ms > 0 else 0.0
+    roofline = {"bound": "hbm", "kernel": kname, "achieved": achieved,
                 "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak, "traffic": traffic, "peak_source": peak_src,
-                "algorithmic_bytes_per_launch": alg_bytes / max(n_eval_launches, 1), "launches": n_eval_launches,
-                "avg_launch_ms": ms_eval / max(n_eval_launches, 1), "kernel_share_of_step": (ms_eval / prof_steps) / (ms / args.steps),
+                "algorithmic_bytes_per_launch": alg_bytes / max(k_launches, 1), "launches": k_launches,
+                "avg_launch_ms": k_ms / max(k_launches, 1), "kernel_share_of_step": (k_ms / prof_steps) / step_ms,
                 "l2_gather_peak_gbs": l2_gather_gbs, "frac_of_l2_gather_peak": achieved / l2_gather_gbs,
-                "note": "algorithmic bytes = reference travel-time lookups inside evaluations x 32 B sector; the table is "
+                "traffic_source": traffic_info.get(args.config, {}).get("source") if isinstance(traffic_info.get(args.config), dict) else None,
+                "note": "algorithmic bytes = reference travel-time lookups inside the kernel's work x 32 B sector; the table is "
                         "L2-resident so HBM peak is the fallback bound and the measured L2 random-gather rate the real one"}
 
-    cpu = None if (args.no_cpu or world > 1) else cpu_leg(snaps, tt)
+    fleet = work[0]["n_veh_full"]
+    par = f"vehicles interleaved over {world} rank(s)"
+    if world > 1:
+        par += (", pool assembled on rank 0 over NVLink peer memory (bulk peer stores + epoch flags, no host collective; "
+                "NCCL only for start-up, barriers and the final timing reduction)")
     line = {"metric": METRIC, "value": evals_all / (ms * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+            "warmup": args.warmup, "ms_per_step": step_ms, "higher_is_better": True, "scaling": scaling,
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": f"OSP pool build (cut-off disabled), {work[0]['n_veh_full']} veh cap {work[0]['host'].cap}, "
-                                   f"Manhattan-scale synthetic epoch snapshots x{len(work)} (bench_data/cfg2_*), 4091-node fp32 table",
-                       "fleet": work[0]["n_veh_full"], "requests_considered": int(np.mean([w["host"].n_search for w in work])),
-                       "parallelism": f"vehicles interleaved over {world} rank(s)" + (", NCCL all-gather of per-vehicle counts + peer-store scatter of the pool over NVLink" if world > 1 else ""),
-                       "l2_policy": "inputs differ every step (8 snapshots cycled); table deliberately L2-resident (67 MB persisting window)",
-                       "pool_entries_per_step": entries_all / args.steps, "schedules_per_step": evals_all / args.steps},
-            "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": e_h2d // args.steps, "d2h_bytes_per_step": e_d2h // args.steps,
+            "config": {"workload": cfg["what"].format(fleet=fleet, n=len(work), req=work[0]["host"].n_search), "name": args.config,
+                       "fleet": fleet, "fleet_mult": mult, "requests_considered": int(np.mean([w["host"].n_search for w in work])),
+                       "parallelism": par,
+                       "l2_policy": f"inputs differ every step ({len(work)} snapshots cycled); table deliberately L2-resident (67 MB persisting window)",
+                       "pool_entries_per_step": entries_all / args.steps, "schedules_per_step": evals_all / args.steps,
+                       "graph": not args.no_graph},
+            "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": int(e_h2d_all // args.steps), "d2h_bytes_per_step": int(e_d2h_all // args.steps),
                     "ms_per_step": 1e3 * float(t_e.item()) / args.steps,
-                    "path": "amod_osp_build(host pointers) + amod_pool_fetch(host buffers) through ctypes"},
-            "gpu_launches": int(launches_all), "clocks": clocks, "roofline": roofline}
-    if cpu:
+                    "path": "amod_osp_build(host pointers) on every rank + " + ("amod_gpool_assemble + amod_gpool_fetch of the assembled pool on rank 0"
+                                                                                 if world > 1 else "amod_pool_fetch(host buffers)") + " through ctypes"},
+            "gpu_launches": int(launches_all), "clocks": clocks, "roofline": roofline, "parity": parity}
+    if sba:
+        line["config"].update({"sba_screens_per_step": screens_p / max(prof_steps, 1), "screen_ms_per_step": ms_screen / max(prof_steps, 1),
+                               "eval_ms_per_step": ms_eval / max(prof_steps, 1), "npo_ms_per_step": ms_npo / max(prof_steps, 1),
+                               "npo_pairs_per_step": npo_pairs / max(prof_steps, 1)})
+    if not (args.no_cpu or world > 1):
+        cpu = cpu_leg([w["host"] for w in work], tt)
+        pyref = python_reference_leg() if args.config == "cfg2" else None
+        if pyref:
+            cpu["python_reference"] = pyref
         line["cpu_baseline"] = cpu
     print_json(line)
     if world > 1:

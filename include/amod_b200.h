@@ -121,6 +121,10 @@ typedef struct amod_stats {
     int64_t n_chunks;       /* warp work units of the insertion search                                       */
     int64_t n_items;        /* (base schedule, pick-up index) lanes inside them (<= 32 per chunk)            */
     int64_t n_lookups_eval; /* the part of n_lookups performed inside insertion-search evaluations           */
+    int64_t evals_level[16];   /* insertion-search evaluations per trip level (index = trip size; one count + one fill
+                                  launch of the search kernel each): the per-launch work behind the roofline figures */
+    int64_t lookups_level[16]; /* reference lookups inside those evaluations, per trip level                         */
+    double  ms_screen;         /* device time of the reachability screen (plain stream launches only, like ms_eval)  */
 } amod_stats;
 
 /* Upload the travel-time table (row = origin, col = destination; route_functions.py:22-25). */

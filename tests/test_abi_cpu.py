@@ -26,7 +26,7 @@ def test_struct_layouts_match_header_sizes():
     # amod_epoch: 6 int32 + int64 + 16 pointers; amod_pool: 6 int64 + 9 pointers
     assert C.sizeof(capi.AmodEpoch) == 6 * 4 + 8 + 16 * 8
     assert C.sizeof(capi.AmodPool) == 6 * 8 + 9 * 8
-    assert C.sizeof(capi.AmodStats) == 6 * 8 + 2 * 4 + 2 * 8 + 2 * 4 + 3 * 8
+    assert C.sizeof(capi.AmodStats) == 6 * 8 + 2 * 4 + 2 * 8 + 2 * 4 + 3 * 8 + 2 * 16 * 8 + 8
 
 
 @pytest.mark.skipif(torch.cuda.is_available(), reason="only meaningful without a GPU")

@@ -40,7 +40,7 @@ def _worker(rank, world, port, family, case, out_dir):
     local = (oracle.sba_build if sba else oracle.osp_build)(sub, tt)
     if sba:   # a rank's SBA slice carries its own empty pairs; they merge by vehicle
         pass
-    full = adist.allgather_pool(local, sel, ep.n_veh, mode_sba=sba)
+    full = adist.allgather_pool(local, sel, ep.n_veh, mode_sba=sba, search=ep.search)
     ok, why = marshal.pools_equal(full, gold, check_kind=True)
     np.save(os.path.join(out_dir, f"ok{rank}.npy"), np.array([int(ok)]))
     if not ok:
@@ -56,3 +56,20 @@ def test_two_rank_gloo_allgather_reproduces_reference_pool(tmp_path, family, cas
         ok = int(np.load(tmp_path / f"ok{r}.npy")[0])
         why = (tmp_path / f"why{r}.txt").read_text() if not ok else ""
         assert ok, f"rank {r}: {why}"
+
+
+def test_sba_merge_follows_the_search_order_not_the_request_index():
+    """the reference's SBA pool is ordered by position in new_received_rids (dispatch_sba.py:56); a
+    non-monotone search list must merge to the single-rank pool."""
+    import oracle
+    from amod_b200 import dist as adist
+    tt, cases = load_golden("rand_ties_sba_cap4")
+    ep, _gold = cases[1]
+    ep.search = np.ascontiguousarray(ep.search[::-1])
+    whole = oracle.sba_build(ep, tt)
+    parts = []
+    for rank in range(3):
+        sub, sel = ep.shard(rank, 3)
+        parts.append((oracle.sba_build(sub, tt), sel))
+    ok, why = marshal.pools_equal(adist.merge_sba(parts, ep.n_veh, ep.search), whole, check_kind=True)
+    assert ok, why

@@ -163,3 +163,39 @@ def test_request_table_and_index_paths_agree():
     for f in marshal.Epoch.FIELDS:
         want = getattr(plain, f) + (big if f == "req_id" else 0)
         assert np.array_equal(want, getattr(sparse, f)), f
+
+
+def test_lazy_records_keep_sorted_positions_after_iteration():
+    """anything that iterates the lazy pair list between scoring and the GPU assigner materialises the
+    records; apply_order must then permute the materialised list too, records built before scoring must carry
+    delay / len(trip) afterwards, and a consumer's own sort() makes the assigner's permutation refuse to apply."""
+    import pytest
+    tt, cases = load_golden("sim_osp_cap4")
+    ep, gold = cases[2]
+    reqs, objs, vehs = _objects(ep)
+    order, sel = oracle.greedy_assign(gold, ep.n_veh, ep.n_req)
+
+    def picked(lazy):
+        return [(lazy[i][0].id, [r.id for r in lazy[i][1]], lazy[i][2], float(lazy[i][3]), lazy[i][4]) for i in sel.tolist()]
+
+    clean = marshal.LazyPoolRecords(gold, ep, vehs, objs)
+    clean.scored = True
+    clean.apply_order(order)
+    want = picked(clean)
+
+    touched = marshal.LazyPoolRecords(gold, ep, vehs, objs)
+    first = touched[0]                      # built before scoring: cost / 0.0
+    assert first[3] == gold.ent_cost[0] and first[4] == 0.0
+    n_seen = sum(1 for _pair in touched)    # a debug hook iterating the candidate list
+    assert n_seen == gold.n_entries
+    touched.scored = True
+    assert first[3] == gold.ent_delay[0] and first[4] == len(first[1])
+    touched.apply_order(order)
+    assert picked(touched) == want
+    assert touched[int(sel[0])] is touched.materialise()[int(sel[0])]
+
+    resorted = marshal.LazyPoolRecords(gold, ep, vehs, objs)
+    resorted.scored = True
+    resorted.sort(key=lambda p: p[0].id, reverse=True)
+    with pytest.raises(RuntimeError):
+        resorted.apply_order(order)
