@@ -291,7 +291,10 @@ def concat_pools(pools: list["Pool"]) -> "Pool":
     stats = {}
     for p in pools:
         for k, v in p.stats.items():
-            stats[k] = stats.get(k, 0) + v
+            if isinstance(v, (list, tuple)):      # per-level counters
+                stats[k] = [a + b for a, b in zip(stats.get(k, [0] * len(v)), v)]
+            else:
+                stats[k] = stats.get(k, 0) + v
     return Pool(stats=stats, **kw)
 
 
