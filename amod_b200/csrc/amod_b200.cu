@@ -15,6 +15,7 @@
 #include "gpool.cuh"
 #include "levels.cuh"
 #include "npo.cuh"
+#include "place.cuh"
 #include "pool.cuh"
 #include "scan.cuh"
 
@@ -59,7 +60,7 @@ struct DevBuf {
     template <typename T> T* as() { return (T*)p; }
 };
 
-struct LevelBufs { DevBuf trip_veh, trip_req, s0, nfeas, cost, sch, sch_cost, order, veh_start; };
+struct LevelBufs { DevBuf trip_veh, trip_req, s0, nfeas, cost, sch, sch_cost, final, veh_start; };
 
 struct amod_ctx {
     int device = 0;
@@ -87,10 +88,11 @@ struct amod_ctx {
     int level_hint[3] = {0, 0, 0};   // deepest non-empty trip level seen so far (+1 is searched before looking further)
     // capacities (grown from the sizes an epoch needed; persisted across epochs)
     i64 cap_tasks = 1 << 18, cap_chunks = 1 << 18, cap_rows = 1 << 19, cap_items = 1 << 16, cap_ent = 1 << 18, cap_ptr = 1 << 19, cap_pst = 1 << 21;
+    i64 cap_tuples = 1 << 20;       // feasible-insertion records of one search launch (all block regions together)
     i64 cap_trips[MAX_LEVELS], cap_sch[MAX_LEVELS];
     // workspace
     DevBuf len0, S0, s0pos, perm_base, perm_nitems, perm_off, perm_cnt, perm_pos, flag8, pos, major_off, partial, scan_sites, task_veh[2], task_base[2], task_q[2], task_nchunk[2], task_chunk0, trip_pos,
-        row_desc, task_nfeas, chunk_cnt, lane_cnt, chunk_pos, hash, row_cnt, row_off, tmp_j, tmp_q, heavy_list, gen_partial, gen_cache, task_first;
+        row_desc, task_nfeas, chunk_cnt, lane_cnt, chunk_pos, tuples, tup_cnt, tup_pos, hash, row_cnt, row_off, tmp_j, tmp_q, heavy_list, gen_partial, gen_cache, task_first;
     LevelBufs lv[MAX_LEVELS];
     // pool
     DevBuf veh_cnt, veh_off, ent_veh, ent_kind, ent_nfeas, ent_tlen, ent_slen, ent_src, ent_trip, ent_cost, ent_delay,
@@ -259,7 +261,7 @@ extern "C" void amod_destroy(amod_ctx* ctx) {
                      &ctx->partial, &ctx->scan_sites,
                      &ctx->task_veh[0], &ctx->task_veh[1], &ctx->task_base[0], &ctx->task_base[1], &ctx->task_q[0], &ctx->task_q[1],
                      &ctx->task_nchunk[0], &ctx->task_nchunk[1], &ctx->task_chunk0, &ctx->trip_pos, &ctx->row_desc, &ctx->task_nfeas, &ctx->chunk_cnt,
-                     &ctx->lane_cnt, &ctx->chunk_pos, &ctx->hash, &ctx->row_cnt, &ctx->row_off, &ctx->tmp_j, &ctx->tmp_q, &ctx->heavy_list, &ctx->gen_partial, &ctx->gen_cache, &ctx->task_first,
+                     &ctx->lane_cnt, &ctx->chunk_pos, &ctx->tuples, &ctx->tup_cnt, &ctx->tup_pos, &ctx->hash, &ctx->row_cnt, &ctx->row_off, &ctx->tmp_j, &ctx->tmp_q, &ctx->heavy_list, &ctx->gen_partial, &ctx->gen_cache, &ctx->task_first,
                      &ctx->veh_cnt, &ctx->veh_off, &ctx->ent_veh, &ctx->ent_kind, &ctx->ent_nfeas, &ctx->ent_tlen, &ctx->ent_slen,
                      &ctx->ent_src, &ctx->ent_trip, &ctx->ent_cost, &ctx->ent_delay, &ctx->trip_off, &ctx->sche_off, &ctx->trip_req,
                      &ctx->sche_code, &ctx->ga_pos, &ctx->ga_rank, &ctx->ga_order, &ctx->ga_state, &ctx->ga_bv, &ctx->ga_br, &ctx->ga_tv, &ctx->ga_tr,
@@ -267,7 +269,7 @@ extern "C" void amod_destroy(amod_ctx* ctx) {
                      &ctx->npo_mdt, &ctx->npo_cnt};
     for (DevBuf* b : all) b->release();
     for (auto& l : ctx->lv) { l.trip_veh.release(); l.trip_req.release(); l.s0.release(); l.nfeas.release(); l.cost.release();
-                              l.sch.release(); l.sch_cost.release(); l.order.release(); l.veh_start.release(); }
+                              l.sch.release(); l.sch_cost.release(); l.final.release(); l.veh_start.release(); }
     if (ctx->h_ctl) cudaFreeHost(ctx->h_ctl);
     if (ctx->h_epoch) cudaFreeHost(ctx->h_epoch);
     if (ctx->fetch_pinned) cudaFreeHost(ctx->fetch_pinned);
@@ -421,6 +423,11 @@ static int ensure_buffers(amod_ctx* ctx, int V, i64 n_screen, int max_level, con
     CK(ctx->task_chunk0.ensure(8 * (T + 2))); CK(ctx->trip_pos.ensure(8 * (T + 2)));
     CK(ctx->row_desc.ensure(2 * sizeof(RowDesc) * (size_t)ctx->cap_rows)); CK(ctx->task_nfeas.ensure(4 * T)); CK(ctx->chunk_cnt.ensure(4 * C)); CK(ctx->lane_cnt.ensure(64 * C)); CK(ctx->chunk_pos.ensure(8 * (C + 2)));
     CK(ctx->tmp_j.ensure(4 * T)); CK(ctx->tmp_q.ensure(4 * T));
+    {   // one record region per block of the search launch
+        const size_t n_regions = (size_t)ctx->n_sm * GRID_EVAL_PER_SM;
+        const size_t region = ((size_t)ctx->cap_tuples + n_regions - 1) / n_regions;
+        CK(ctx->tuples.ensure(sizeof(Tuple) * region * n_regions)); CK(ctx->tup_pos.ensure(4 * region * n_regions)); CK(ctx->tup_cnt.ensure(4 * n_regions));
+    }
     size_t max_trips = 1;
     memset(ls, 0, sizeof *ls);
     for (int k = 0; k <= max_level; k++) {
@@ -431,12 +438,12 @@ static int ensure_buffers(amod_ctx* ctx, int V, i64 n_screen, int max_level, con
         max_trips = std::max(max_trips, nt);
         CK(b.trip_veh.ensure(4 * nt)); CK(b.trip_req.ensure(4 * nt * (size_t)std::max(k, 1))); CK(b.s0.ensure(8 * nt));
         CK(b.nfeas.ensure(4 * nt)); CK(b.cost.ensure(8 * nt));
-        CK(b.sch.ensure(sizeof(code_t) * nsch * (size_t)stride[k])); CK(b.sch_cost.ensure(8 * nsch)); CK(b.order.ensure(4 * nsch));
+        CK(b.sch.ensure(sizeof(Stop) * nsch * (size_t)stride[k])); CK(b.sch_cost.ensure(8 * nsch)); CK(b.final.ensure(4 * nsch));
         CK(b.veh_start.ensure(4 * ((size_t)V + 2)));
         Level& lv = ls->lv[k];
         lv.k = k; lv.stride = stride[k]; lv.cap_trips = (int)nt; lv.cap_sch = (i64)nsch;
         lv.trip_veh = b.trip_veh.as<int>(); lv.trip_req = b.trip_req.as<int>(); lv.s0 = b.s0.as<i64>(); lv.nfeas = b.nfeas.as<int>();
-        lv.cost = b.cost.as<double>(); lv.sch = b.sch.as<code_t>(); lv.sch_cost = b.sch_cost.as<double>(); lv.order = b.order.as<int>();
+        lv.cost = b.cost.as<double>(); lv.sch = b.sch.as<Stop>(); lv.sch_cost = b.sch_cost.as<double>(); lv.final = b.final.as<int>();
         lv.veh_start = b.veh_start.as<int>();
     }
     ls->n = max_level + 1;
@@ -525,7 +532,7 @@ static int enqueue_build(amod_ctx* ctx, int mode, int cap, Table<TT> tt, int max
     }
     // ---- levels 1..max_level ----------------------------------------------------------------------------
     // Two branches per level once the schedule offsets are known (fork after the scans):
-    //   main: k_eval<fill> -> k_classify                     (writes the level's schedules, orders them)
+    //   main: k_place_cost -> k_classify -> k_place_rows     (orders the level's schedules, writes them)
     //   side: k_compact_trips -> k_gen_count -> k_gen_emit
     //         (names and indexes the level's trips, prepares level k+1's tasks and rows; touches no schedule)
     // They meet again before k_eval<count> of level k+1.  Buffers both branches touch at once are doubled
@@ -548,6 +555,11 @@ static int enqueue_build(amod_ctx* ctx, int mode, int cap, Table<TT> tt, int max
     k_expand_rows<<<GE, 256, 0, st>>>(ctl, 0, ls.lv[0], len0, ctx->task_veh[0].as<int>(), ctx->task_base[0].as<int>(), ctx->task_q[0].as<int>(),
                                       ctx->task_nchunk[0].as<int>(), row0, rows_buf[0], tnf);
     ctx->n_launches++;
+    const int n_regions = GEV;
+    const int region_cap = (int)(((size_t)ctx->cap_tuples + n_regions - 1) / n_regions);
+    Tuple* tup = ctx->tuples.as<Tuple>();
+    int* tup_cnt = ctx->tup_cnt.as<int>();
+    unsigned* tup_pos = ctx->tup_pos.as<unsigned>();
     for (int k = 1; k <= max_level; k++) {
         const int cur = (k - 1) & 1, nxt = k & 1;
         int* tv = ctx->task_veh[cur].as<int>(); int* tb = ctx->task_base[cur].as<int>(); int* tq = ctx->task_q[cur].as<int>();
@@ -556,28 +568,28 @@ static int enqueue_build(amod_ctx* ctx, int mode, int cap, Table<TT> tt, int max
         const int Gk = std::max(1, 32 / (prev.stride + 1));      // rows per chunk: Gk * (longest schedule + 1) <= 32 lanes
         RowDesc* rows = rows_buf[cur];
         CK(cudaEventRecord(get_event(ctx, n_ev++), st));
-        k_eval<TT, 0><<<GEV, WARPS_PER_BLOCK * 32, 0, st>>>(d, tt, prev, lv, ctl, cur, Gk, rows, ctx->chunk_cnt.as<int>(),
-                                                          ctx->lane_cnt.as<uint8_t>(), nullptr, tnf, dstats, scan_site(ctx, k), half);
+        k_eval<TT><<<GEV, WARPS_PER_BLOCK * 32, 0, st>>>(d, tt, prev, lv, ctl, cur, Gk, rows, ctx->chunk_cnt.as<int>(),
+                                                       ctx->lane_cnt.as<uint8_t>(), tnf, dstats, scan_site(ctx, k), half,
+                                                       tup, tup_cnt, region_cap);
         CK(cudaEventRecord(get_event(ctx, n_ev++), st));
         scan_fin2(ctx, InArray<int>{ctx->chunk_cnt.as<int>(), &ctl->n_chunks[cur], 0}, cpos,
                   FinCountI64{&ctl->n_sch[k], lv.cap_sch, &ctl->need_sch[k], &ctl->overflow, OVF_SCH},
                   InTaskFeasible{ctl, cur, tnf}, ctx->trip_pos.as<i64>(),
-                  FinCountInt{&ctl->n_trips[k], (i64)lv.cap_trips, &ctl->need_trips[k], &ctl->overflow, OVF_TRIPS}, (i64*)scan_site(ctx, k));
+                  FinTrips{&ctl->n_trips[k], (i64)lv.cap_trips, &ctl->need_trips[k], &ctl->overflow}, (i64*)scan_site(ctx, k));
         CK(edge(st, sd));                                         // fork
         const TripHash th = hash_of(k);
-        k_compact_trips<<<G, 256, 0, sd>>>(ctl, cur, tv, tb, tq, row0, tnf, Gk, rows, ctx->lane_cnt.as<uint8_t>(), cpos,
-                                          ctx->trip_pos.as<i64>(), prev, lv, th, dstats, d, sba, ctx->major_off.as<i64>(), ctx->task_first.as<i64>());
+        k_compact_trips<<<G, 256, 0, sd>>>(ctl, cur, tv, tb, tq, tnf, ctx->trip_pos.as<i64>(), prev, lv, th, dstats, d, sba,
+                                          ctx->major_off.as<i64>(), ctx->task_first.as<i64>());
         cudaEvent_t named = get_sync_event(ctx, n_sync++);        // the level's trips have their rows (s0, nfeas)
         CK(cudaEventRecord(named, sd));
-        CK(cudaEventRecord(get_event(ctx, n_ev++), st));
-        k_eval<TT, 1><<<GEV, WARPS_PER_BLOCK * 32, 0, st>>>(d, tt, prev, lv, ctl, cur, Gk, rows, ctx->chunk_cnt.as<int>(),
-                                                          ctx->lane_cnt.as<uint8_t>(), cpos, tnf, dstats, nullptr, half);
-        CK(cudaEventRecord(get_event(ctx, n_ev++), st));
+        // main: costs to their encounter positions -> list order per trip -> schedules straight into their final rows
+        k_place_cost<<<n_regions, PLACE_THREADS, 0, st>>>(ctl, tup, tup_cnt, region_cap, ctx->lane_cnt.as<uint8_t>(), cpos, lv, tup_pos);
         CK(cudaStreamWaitEvent(st, named, 0));
         const int heavy_min = ctx->heavy_min >= 0 ? ctx->heavy_min : (cap > 5 ? 2048 : 0);   // large capacities: trips with 10^3..10^5 schedules
         k_classify<<<GE, WARPS_PER_BLOCK * 32, 0, st>>>(ctl, lv, heavy_min, ctx->heavy_list.as<int>());
         if (heavy_min) { k_classify_heavy<<<ctx->n_sm * 2, HEAVY_THREADS, 0, st>>>(ctl, lv, ctx->heavy_list.as<int>()); ctx->n_launches++; }
-        ctx->n_launches += 4;       // k_eval x2, k_compact_trips, k_classify (the scans count themselves)
+        k_place_rows<<<n_regions, PLACE_THREADS, 0, st>>>(d, ctl, tup, tup_cnt, region_cap, tup_pos, rows, Gk, prev, lv);
+        ctx->n_launches += 5;       // k_eval, k_compact_trips, k_place_cost, k_classify, k_place_rows (the scans count themselves)
         if (k < max_level) {
             // ---- candidates of size k+1 (dispatch_osp.py:183-216), their tasks and rows ----------------------
             const TripHash thn = hash_of(k + 1);
@@ -697,6 +709,8 @@ static int build_impl(amod_ctx* ctx, const amod_epoch* ep, int loc, amod_stats* 
         grow(ctx->cap_tasks, h->need_tasks); grow(ctx->cap_chunks, h->need_chunks); grow(ctx->cap_rows, h->need_rows); grow(ctx->cap_items, h->need_perm_items);
         for (int k = 0; k <= max_level; k++) { grow(ctx->cap_trips[k], h->need_trips[k]); grow(ctx->cap_sch[k], h->need_sch[k]); }
         grow(ctx->cap_ent, h->need_ent); grow(ctx->cap_ptr, h->need_ptr); grow(ctx->cap_pst, h->need_pst);
+        grow(ctx->cap_tuples, h->need_tuples);
+        for (int k = 0; k <= max_level; k++) if (ctx->cap_sch[k] > 0x7ffffff0) return ctx->fail(AMOD_E_LIMIT, "more than 2^31 feasible schedules in one level");
         if (ctx->cap_tasks > 0x7ffffff0 || ctx->cap_chunks > 0x7ffffff0 || ctx->cap_rows > 0x7ffffff0)
             return ctx->fail(AMOD_E_LIMIT, "more than 2^31 candidates or base-schedule rows in one level");
     }

@@ -36,15 +36,21 @@ struct Table {
     __device__ __forceinline__ TT raw(int o, int d) const { return __ldg(p + (size_t)(o - 1) * (size_t)n + (size_t)(d - 1)); }
 };
 
+// One stop of a stored schedule: the stop code plus the node and deadline it stands for (scheduling.py:56-57), so
+// that the insertion search stages a base schedule with one 16 B load per stop and no dependent look-ups.
+struct __align__(16) Stop { int code; int node; double ddl; };
+
 // One trip-size level of the per-vehicle feasible-trip table (FEASIBLE_TRIP_TABLE[veh][k-1],
 // dispatch_osp.py:8) flattened over all vehicles.  Level 0 holds the basic schedules.
 // Feasible schedules of trip t are rows [s0[t], s0[t]+nfeas[t]) of the level's schedule store
-// (fixed `stride` codes per row), kept in ENCOUNTER order (the reference's loop order); the
-// reference's list order (running-minimum records newest-first, then the rest; scheduling.py:31-36)
-// is the permutation order[s0[t] + p] -> row offset within the trip.
+// (fixed `stride` stops per row), kept in the reference's LIST order (running-minimum records newest-first,
+// then the rest in encounter order; scheduling.py:31-36): row s0[t] is the best schedule and the next level
+// iterates the rows exactly as the reference iterates feasible_sches.  The insertion search reports its
+// results in ENCOUNTER order (the reference's loop order); `sch_cost` holds the costs in that order and
+// `final[s0 + e]` is the row the e-th encountered schedule of the trip is stored in.
 struct Level {
     int k;
-    int stride;          // codes per schedule row (>= longest schedule of this level)
+    int stride;          // stops per schedule row (>= longest schedule of this level)
     int cap_trips;
     i64 cap_sch;
     int* trip_veh;
@@ -52,9 +58,9 @@ struct Level {
     i64* s0;             // first schedule row of the trip
     int* nfeas;
     double* cost;        // min cost (scheduling.py:33)
-    code_t* sch;         // [n_sch * stride]
-    double* sch_cost;    // [n_sch] cost of each feasible schedule (encounter order)
-    int* order;          // [n_sch] list position -> encounter position within its trip
+    Stop* sch;           // [n_sch * stride] list order
+    double* sch_cost;    // [n_sch] cost of each feasible schedule, encounter order
+    int* final;          // [n_sch] encounter position -> row
     int* veh_start;      // [n_veh+1] trips of vehicle v are [veh_start[v], veh_start[v+1])  (OSP modes)
 };
 
@@ -73,6 +79,7 @@ struct Stats {            // device counters
 #define OVF_POOL 16ull
 #define OVF_ROWS 32ull
 #define OVF_ITEMS 64ull
+#define OVF_TUPLES 128ull
 struct Control {
     int n_tasks[2];
     int n_chunks[2];      // rows / chunks of the task buffer with the same index: level k+1 is prepared while
@@ -84,6 +91,7 @@ struct Control {
     unsigned long long overflow;
     i64 need_rows;
     i64 need_perm_items;
+    i64 need_tuples;      // feasible-insertion records per launch region (x regions) the search would have needed
     i64 need_tasks, need_chunks, need_trips[MAX_LEVELS], need_sch[MAX_LEVELS], need_ent, need_ptr, need_pst;
     int max_level_nonempty;
     int pad;
@@ -99,11 +107,20 @@ struct __align__(16) RowDesc {
     int task, pad;
 };
 
+__device__ __forceinline__ int pod_of(int code) { return code < 0 ? 0 : ((code & 1) ? -1 : 1); }
+
 __device__ __forceinline__ void stop_info(const DEpoch& ep, int v, int code, int& node, double& ddl, int& pod) {
     if (code < 0) { node = ep.reb_node[v]; ddl = ep.reb_ddl[v]; pod = 0; return; }
     int r = code >> 1;
     if (code & 1) { node = ep.dnid[r]; ddl = ep.cld[r]; pod = -1; }
     else          { node = ep.onid[r]; ddl = ep.clp[r]; pod = 1; }
+}
+
+__device__ __forceinline__ Stop make_stop(const DEpoch& ep, int v, int code) {
+    Stop s; int pod;
+    s.code = code;
+    stop_info(ep, v, code, s.node, s.ddl, pod);
+    return s;
 }
 
 __device__ __forceinline__ double warp_min(double x) {

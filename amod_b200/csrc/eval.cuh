@@ -10,8 +10,11 @@
 // All arithmetic is float64 accumulated left to right in the reference's order: costs and every
 // comparison are bit-identical to the reference.
 //
-// MODE 0 counts the feasible insertions of every lane (-> offsets by prefix sum);
-// MODE 1 re-walks only lanes that found something and writes schedules + costs in encounter order.
+// ONE pass: every feasible insertion is appended, as a 16 B record (cost, chunk, lane, ordinal within the lane,
+// i, j, row), to the launching block's region of a record buffer (a block-local cursor in shared memory: no
+// global atomics, no ordering between blocks).  The per-lane counts give, by one prefix sum over the chunks, the
+// record's position in the reference's encounter order; place.cuh then stores cost and schedule there.  The
+// search itself is never repeated.
 #pragma once
 #include "common.cuh"
 #include "scan.cuh"
@@ -32,20 +35,34 @@ struct WarpStage {
     double ddl[STAGE_SLOTS];
     int node[STAGE_SLOTS];
     TT leg[LEG_SLOTS];        // per schedule: g[l] | toP[l+1] | fromP[l] | toD[l+1] | fromD[l]
-    code_t code[STAGE_SLOTS];
     signed char pod[STAGE_SLOTS];
 };
 
+// One feasible insertion found by the search.  info = lane (6 bits: 0..63, the work item within the chunk)
+// | ordinal among the lane's feasible insertions << 6 | j << 12 | i << 18 | row within the chunk << 24.
+struct __align__(16) Tuple { double cost; int c; unsigned info; };
+#define TUP_LANE(x) ((int)((x) & 63u))
+#define TUP_ORD(x) ((int)(((x) >> 6) & 63u))
+#define TUP_J(x) ((int)(((x) >> 12) & 63u))
+#define TUP_I(x) ((int)(((x) >> 18) & 63u))
+#define TUP_ROW(x) ((int)(((x) >> 24) & 31u))
+
+struct TupleOut {
+    Tuple* region;      // this block's region of the record buffer
+    int cap;            // records per region
+    int* cursor;        // shared-memory cursor of the block
+    int c;              // chunk
+    unsigned tag;       // lane | i << 18 | row << 24
+};
 
 struct LaneCount { int n, evals, lookups; };
 
 // Walk j = i+1 .. for one (sub_sche, i).  `A` = accumulated time at the inserted pick-up.
-// WRITE: emit each feasible schedule (codes + cost) to consecutive rows starting at `row`.
-template <typename TT, bool WRITE>
+// Every feasible (i, j) is appended to the block's record region with its cost.
+template <typename TT>
 __device__ __forceinline__ void walk_j(const TT* __restrict__ lg, double PD, const double* __restrict__ ddl,
-                                       const code_t* __restrict__ codes, int l, int i, double A, int q,
-                                       double cld, double T, unsigned long long fullmask, LaneCount& o, i64 row,
-                                       code_t* __restrict__ out_sch, double* __restrict__ out_cost, int stride) {
+                                       int l, int i, double A, double cld, double T, unsigned long long fullmask,
+                                       LaneCount& o, const TupleOut& out) {
     const TT* __restrict__ g = lg;                       // g[m]     = tt[stop m-1 (or vehicle)][stop m]
     const TT* __restrict__ fromP = lg + 2 * l + 1;       // fromP[m] = tt[P][stop m]
     const TT* __restrict__ toD = lg + 3 * l + 1;         // toD[m]   = tt[stop m-1 (or vehicle)][D]
@@ -65,18 +82,12 @@ __device__ __forceinline__ void walk_j(const TT* __restrict__ lg, double PD, con
         }
         if (ok) {
             o.lookups += l + 2;
-            o.n++;
-            if (WRITE) {
-                code_t* dst = out_sch + row * stride;
-                int w = 0;
-                for (int m = 0; m < i; m++) dst[w++] = codes[m];
-                dst[w++] = (code_t)(2 * q);
-                for (int m = i; m < j - 1; m++) dst[w++] = codes[m];
-                dst[w++] = (code_t)(2 * q + 1);
-                for (int m = j - 1; m < l; m++) dst[w++] = codes[m];
-                out_cost[row] = C;
-                row++;
+            const int slot = atomicAdd(out.cursor, 1);
+            if (slot < out.cap) {
+                Tuple t; t.cost = C; t.c = out.c; t.info = out.tag | ((unsigned)o.n << 6) | ((unsigned)j << 12);
+                out.region[slot] = t;
             }
+            o.n++;
         }
         if (j == l + 1) break;
         if (j == b) { o.evals++; break; }                           // next j is over capacity: viol 1 -> break
@@ -87,14 +98,17 @@ __device__ __forceinline__ void walk_j(const TT* __restrict__ lg, double PD, con
 
 // A chunk = G consecutive rows (base schedules) of the level's global row list, whatever task or
 // vehicle they belong to; G is chosen per level so that G * (longest schedule + 1) <= 32 lanes.
-template <typename TT, int MODE>
+template <typename TT>
 __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, EVAL_BLOCKS_PER_SM)
-k_eval(const DEpoch* __restrict__ epp, Table<TT> tt, Level prev, Level cur, const Control* __restrict__ ctl, int which, int G,
+k_eval(const DEpoch* __restrict__ epp, Table<TT> tt, Level prev, Level cur, Control* __restrict__ ctl, int which, int G,
        const RowDesc* __restrict__ rows, int* __restrict__ chunk_cnt, uint8_t* __restrict__ lane_cnt,
-       const i64* __restrict__ chunk_pos, int* __restrict__ task_nfeas, Stats* stats, unsigned long long* __restrict__ part, int part_vg) {
+       int* __restrict__ task_nfeas, Stats* stats, unsigned long long* __restrict__ part, int part_vg,
+       Tuple* __restrict__ tup, int* __restrict__ tup_cnt, int region_cap) {
     __shared__ WarpStage<TT> stage_all[WARPS_PER_BLOCK];
     __shared__ DEpoch s_ep;       // the epoch header once per block: array pointers without a second indirection
+    __shared__ int s_cursor;      // feasible-insertion records appended by this block
     if (threadIdx.x < sizeof(DEpoch) / 4) ((int*)&s_ep)[threadIdx.x] = ((const int*)epp)[threadIdx.x];
+    if (threadIdx.x == 0) s_cursor = 0;
     __syncthreads();
     const DEpoch& ep = s_ep;
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
@@ -105,8 +119,10 @@ k_eval(const DEpoch* __restrict__ epp, Table<TT> tt, Level prev, Level cur, cons
     const int n_rows = ctl->overflow ? 0 : ctl->n_rows[which];
     const int n_chunks = ctl->overflow ? 0 : ctl->n_chunks[which];
     const int cap = ep.cap;
-    // MODE 0 leaves the block sums of the two scans that follow (schedules per chunk, feasible tasks) as it goes
+    // the block sums of the two scans that follow (schedules per chunk; feasible tasks | their schedules << 32) are left as we go
     const int seg_chunks = (int)scan_seg_len(n_chunks, part_vg), seg_tasks = (int)scan_seg_len(ctl->n_tasks[which], part_vg);
+    TupleOut out;
+    out.region = tup + (i64)blockIdx.x * region_cap; out.cap = region_cap; out.cursor = &s_cursor; out.c = 0; out.tag = 0;
 
     RowDesc nxt; nxt.l = 0; nxt.v = 0; nxt.q = 0; nxt.s = 0; nxt.s0 = 0; nxt.task = 0;
     if (warp0 < n_chunks && lane < G && warp0 * G + lane < n_rows) nxt = rows[(i64)warp0 * G + lane];
@@ -117,16 +133,13 @@ k_eval(const DEpoch* __restrict__ epp, Table<TT> tt, Level prev, Level cur, cons
             const i64 cn = (i64)c + nwarps;
             if (cn < n_chunks && lane < G && cn * G + lane < n_rows) nxt = rows[cn * G + lane];   // prefetch
         }
-        if (MODE == 1 && chunk_cnt[c] == 0) continue;
         const bool own = lane < nr;
         // per-row parameters live in the owner lane's registers and are read by shuffle
         int o_l = own ? rd.l : 0;
         const bool too_long = own && (o_l + 2 > MAXS || o_l + 2 > cur.stride);
         if (__any_sync(FULL, too_long)) {   // compiled stop limit: reported as AMOD_E_LIMIT by the host
-            if (MODE == 0) {
-                if (lane == 0) { atomicOr(&stats->flags, 1ull); chunk_cnt[c] = 0; }
-                lane_cnt[(i64)c * 64 + lane] = 0; lane_cnt[(i64)c * 64 + 32 + lane] = 0;
-            }
+            if (lane == 0) { atomicOr(&stats->flags, 1ull); chunk_cnt[c] = 0; }
+            lane_cnt[(i64)c * 64 + lane] = 0; lane_cnt[(i64)c * 64 + 32 + lane] = 0;
             continue;
         }
         int o_P = 1, o_D = 1, o_nid = 1, o_load = 0;
@@ -135,22 +148,15 @@ k_eval(const DEpoch* __restrict__ epp, Table<TT> tt, Level prev, Level cur, cons
         if (own) {
             o_P = ep.onid[rd.q]; o_D = ep.dnid[rd.q]; o_clp = ep.clp[rd.q]; o_cld = ep.cld[rd.q];
             o_nid = ep.veh_nid[rd.v]; o_load = ep.veh_load[rd.v]; o_t0 = ep.veh_t[rd.v];
-            o_src = rd.s0 + prev.order[rd.s0 + rd.s];             // stored row of the base schedule (list order -> row)
+            o_src = rd.s0 + rd.s;                                 // rows are stored in list order: row s IS feasible_sches[s]
             o_PD = tt(o_P, o_D);
         }
         const int o_w = own ? o_l + 1 : 0;
         const int o_woff = warp_excl_sum(o_w, lane);              // first lane of the row
         const int items = __shfl_sync(FULL, o_woff + o_w, 31);
-        // fill pass: only rows in which some lane found a feasible insertion are staged again
-        bool o_act = own;
-        if (MODE == 1 && items <= 32) {
-            const unsigned hit = __ballot_sync(FULL, lane_cnt[(i64)c * 64 + lane] != 0);
-            const unsigned span = o_w >= 32 ? FULL : (((1u << o_w) - 1u) << o_woff);
-            o_act = own && (hit & span) != 0u;
-        }
         // staged stops and legs of the rows before this one: one packed scan (stops < 2^12 | legs << 12)
-        const int o_sl = o_act ? o_l : 0;
-        const int o_gl = o_act ? 5 * o_l + 2 : 0;
+        const int o_sl = own ? o_l : 0;
+        const int o_gl = own ? 5 * o_l + 2 : 0;
         const int o_pk = warp_excl_sum(o_sl | (o_gl << 12), lane);
         const int o_soff = o_pk & 0xfff;                          // first staged stop of the row
         const int o_goff = o_pk >> 12;                            // first staged leg of the row
@@ -161,24 +167,20 @@ k_eval(const DEpoch* __restrict__ epp, Table<TT> tt, Level prev, Level cur, cons
         const int i_first = lane - __shfl_sync(FULL, o_woff, r);
         const int l = __shfl_sync(FULL, o_l, r);
         const int soff = __shfl_sync(FULL, o_soff, r), goff = __shfl_sync(FULL, o_goff, r);
-        const int q = __shfl_sync(FULL, rd.q, r), task = __shfl_sync(FULL, rd.task, r);
+        const int task = __shfl_sync(FULL, rd.task, r);
         const int load = __shfl_sync(FULL, o_load, r);
         const double clp = __shfl_sync(FULL, o_clp, r), cld = __shfl_sync(FULL, o_cld, r);
         const double t0 = __shfl_sync(FULL, o_t0, r), PD = __shfl_sync(FULL, o_PD, r);
         {   // every row is staged by its own lanes: stops first, then the 5l+2 travel times it can ever need
             const int P = __shfl_sync(FULL, o_P, r), D = __shfl_sync(FULL, o_D, r), nid = __shfl_sync(FULL, o_nid, r);
             const i64 src = __shfl_sync(FULL, o_src, r);
-            const int vv = __shfl_sync(FULL, rd.v, r);
-            const int row_act = __shfl_sync(FULL, (int)o_act, r);   // (shuffle outside the &&: every lane must take part)
-            const bool stage = lane < items && row_act;
+            const bool stage = lane < items;
             const int wl = min(l + 1, 32);                       // lanes this row has in the first step
             __syncwarp();
             if (stage)
                 for (int m = i_first; m < l; m += wl) {
-                    const int code = prev.sch[src * prev.stride + m];
-                    int node, pod; double ddl;
-                    stop_info(ep, vv, code, node, ddl, pod);
-                    st.node[soff + m] = node; st.ddl[soff + m] = ddl; st.pod[soff + m] = (signed char)pod; st.code[soff + m] = (code_t)code;
+                    const Stop sp = prev.sch[src * prev.stride + m];      // one 16 B load: code, node, deadline
+                    st.node[soff + m] = sp.node; st.ddl[soff + m] = sp.ddl; st.pod[soff + m] = (signed char)pod_of(sp.code);
                 }
             __syncwarp();
             if (stage) {
@@ -199,7 +201,7 @@ k_eval(const DEpoch* __restrict__ epp, Table<TT> tt, Level prev, Level cur, cons
         }
 
         int dead_s = -1, cnt_total = 0;
-        i64 row_base = MODE == 1 ? chunk_pos[c] : 0;
+        out.c = c;
         for (int it0 = 0; it0 < items; it0 += 32) {               // one step unless a single schedule has > 31 stops
             const int it = it0 + lane;
             const bool valid = it < items;
@@ -211,8 +213,6 @@ k_eval(const DEpoch* __restrict__ epp, Table<TT> tt, Level prev, Level cur, cons
             unsigned long long fullmask = 0;
             bool basebad = false, stop3 = false, cap1 = false;
             double A = 0.0;
-            int mine = 0;
-            if (MODE == 1) mine = lane_cnt[(i64)c * 64 + it0 + lane];
             if (items <= 32) {
                 // occupancy after every base stop by a prefix sum over the row's own lanes, shared by ballot
                 const bool at = valid && i < l;
@@ -226,7 +226,7 @@ k_eval(const DEpoch* __restrict__ epp, Table<TT> tt, Level prev, Level cur, cons
                 fullmask = ((unsigned long long)((bal_full >> woff) & rowbits) << 1) | (load >= cap ? 1ull : 0ull);
                 basebad = ((bal_over >> woff) & rowbits) != 0u;
             }
-            if (MODE == 0 ? valid : (mine != 0)) {
+            if (valid) {
                 if (items > 32) {
                     int run = load;
                     if (run >= cap) fullmask |= 1ull;
@@ -243,48 +243,52 @@ k_eval(const DEpoch* __restrict__ epp, Table<TT> tt, Level prev, Level cur, cons
                 stop3 = !cap1 && (T + A > clp);                                          // viol 3 (scheduling.py:43)
             }
             LaneCount o; o.n = 0; o.evals = 0; o.lookups = 0;
-            if (MODE == 0) {
-                // viol==3 ends the i-loop of its base schedule: later i of the same row are never evaluated
-                const unsigned bal3 = __ballot_sync(FULL, stop3);
-                const int lo = max(lane - i, 0);
-                const unsigned same_s_lower = (lane > lo) ? (((1u << lane) - 1u) & ~((1u << lo) - 1u)) : 0u;
-                const bool dead = valid && ((bal3 & same_s_lower) != 0u || dead_s == 0);
-                {   // carry to the second step of a > 31-stop schedule (then the chunk is that single row)
-                    const unsigned killed = __ballot_sync(FULL, valid && (stop3 || dead));
-                    dead_s = (items > 32 && killed) ? 0 : -1;
-                }
-                const bool live = valid && !dead;
-                if (live) {
-                    if (cap1) o.evals = 1;
-                    else if (stop3) { o.evals = 1; o.lookups = i + 1; }
-                    else walk_j<TT, false>(lg, PD, ddl, st.code + soff, l, i, A, q, cld, T, fullmask, o, 0, nullptr, nullptr, 0);
-                }
-                acc_evals += o.evals; acc_lookups += o.lookups;
-                lane_cnt[(i64)c * 64 + it0 + lane] = (uint8_t)o.n;     // <= 64 items per chunk
-                if (o.n && atomicAdd(&task_nfeas[task], o.n) == 0) atomicAdd(&part[part_vg + task / seg_tasks], 1ull);   // first feasible insertion of the task
-                cnt_total += o.n;
-            } else {
-                const int before = warp_excl_sum(mine, lane);
-                if (mine) walk_j<TT, true>(lg, PD, ddl, st.code + soff, l, i, A, q, cld, T, fullmask, o, row_base + before,
-                                           cur.sch, cur.sch_cost, cur.stride);
-                row_base += __shfl_sync(FULL, before + mine, 31);
+            // viol==3 ends the i-loop of its base schedule: later i of the same row are never evaluated
+            const unsigned bal3 = __ballot_sync(FULL, stop3);
+            const int lo = max(lane - i, 0);
+            const unsigned same_s_lower = (lane > lo) ? (((1u << lane) - 1u) & ~((1u << lo) - 1u)) : 0u;
+            const bool dead = valid && ((bal3 & same_s_lower) != 0u || dead_s == 0);
+            {   // carry to the second step of a > 31-stop schedule (then the chunk is that single row)
+                const unsigned killed = __ballot_sync(FULL, valid && (stop3 || dead));
+                dead_s = (items > 32 && killed) ? 0 : -1;
             }
+            const bool live = valid && !dead;
+            if (live) {
+                if (cap1) o.evals = 1;
+                else if (stop3) { o.evals = 1; o.lookups = i + 1; }
+                else {
+                    out.tag = (unsigned)it | ((unsigned)i << 18) | ((unsigned)r << 24);
+                    walk_j<TT>(lg, PD, ddl, l, i, A, cld, T, fullmask, o, out);
+                }
+            }
+            acc_evals += o.evals; acc_lookups += o.lookups;
+            lane_cnt[(i64)c * 64 + it0 + lane] = (uint8_t)o.n;     // <= 64 items per chunk
+            if (o.n) {      // block sums of the scan over tasks: (task has a feasible schedule) | (its schedules) << 32
+                const int before = atomicAdd(&task_nfeas[task], o.n);
+                atomicAdd(&part[part_vg + task / seg_tasks], (before == 0 ? 1ull : 0ull) | ((unsigned long long)o.n << 32));
+            }
+            cnt_total += o.n;
         }
-        if (MODE == 0) {
-            if (items <= 32) lane_cnt[(i64)c * 64 + 32 + lane] = 0;
-            cnt_total = warp_sum(cnt_total);
-            if (lane == 0) { chunk_cnt[c] = cnt_total; if (cnt_total) atomicAdd(&part[c / seg_chunks], (unsigned long long)cnt_total); }
-        }
+        if (items <= 32) lane_cnt[(i64)c * 64 + 32 + lane] = 0;
+        cnt_total = warp_sum(cnt_total);
+        if (lane == 0) { chunk_cnt[c] = cnt_total; if (cnt_total) atomicAdd(&part[c / seg_chunks], (unsigned long long)cnt_total); }
     }
-    if (MODE == 0) {
-        acc_evals = warp_sum(acc_evals);
-        acc_lookups = warp_sum(acc_lookups);
-        if (lane == 0 && (acc_evals | acc_lookups)) {
-            atomicAdd(&stats->n_evals, acc_evals);
-            atomicAdd(&stats->n_lookups, acc_lookups);
-            atomicAdd(&stats->n_lookups_eval, acc_lookups);
-            atomicAdd(&stats->lvl_evals[cur.k], acc_evals);
-            atomicAdd(&stats->lvl_lookups[cur.k], acc_lookups);
+    acc_evals = warp_sum(acc_evals);
+    acc_lookups = warp_sum(acc_lookups);
+    if (lane == 0 && (acc_evals | acc_lookups)) {
+        atomicAdd(&stats->n_evals, acc_evals);
+        atomicAdd(&stats->n_lookups, acc_lookups);
+        atomicAdd(&stats->n_lookups_eval, acc_lookups);
+        atomicAdd(&stats->lvl_evals[cur.k], acc_evals);
+        atomicAdd(&stats->lvl_lookups[cur.k], acc_lookups);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const int n = s_cursor;
+        tup_cnt[blockIdx.x] = min(n, region_cap);
+        if (n > region_cap) {      // the region overflowed: the host regrows the record buffer and reruns the epoch
+            atomicMax((unsigned long long*)&ctl->need_tuples, (unsigned long long)n * gridDim.x);
+            atomicOr(&ctl->overflow, OVF_TUPLES);
         }
     }
 }

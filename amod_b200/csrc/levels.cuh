@@ -54,9 +54,8 @@ k_basic(const DEpoch* __restrict__ epp, Table<TT> tt, Level lv0, int* __restrict
     if (too_long) L = 0;
     const i64 row0 = MODE == 1 ? s0pos[v] : 0;
     if (MODE == 1 && lane == 0) {
-        code_t* out = lv0.sch + row0 * lv0.stride;
-        for (int m = 0; m < L; m++) out[m] = (code_t)base[m];
-        lv0.order[row0] = 0;
+        Stop* out = lv0.sch + row0 * lv0.stride;
+        for (int m = 0; m < L; m++) out[m] = make_stop(ep, v, base[m]);
         lv0.trip_veh[v] = v; lv0.nfeas[v] = S0[v]; lv0.s0[v] = row0; lv0.veh_start[v] = v;
         if (v == 0) lv0.veh_start[ep.n_veh] = ep.n_veh;
     }
@@ -97,9 +96,8 @@ k_basic(const DEpoch* __restrict__ epp, Table<TT> tt, Level lv0, int* __restrict
             const unsigned bal = __ballot_sync(FULL, ok);
             if (MODE == 1 && ok) {
                 const int r = count + __popc(bal & ((1u << lane) - 1u));
-                code_t* dst = lv0.sch + (row0 + r) * lv0.stride;
-                for (int m = 0; m < L; m++) dst[m] = (code_t)base[pos[m]];
-                lv0.order[row0 + r] = r;
+                Stop* dst = lv0.sch + (row0 + r) * lv0.stride;       // itertools order = list order (dispatch_osp.py:315-320)
+                for (int m = 0; m < L; m++) dst[m] = make_stop(ep, v, base[pos[m]]);
             }
             count += __popc(bal);
         }
@@ -208,11 +206,9 @@ k_perm_items(const DEpoch* __restrict__ epp, Table<TT> tt, Level lv0, const Cont
         const unsigned bal = __ballot_sync(FULL, ok);
         if (MODE == 0) { if (lane == 0) item_cnt[it] = __popc(bal); }
         else if (ok) {
-            const i64 first = v + item_pos[item_off[v]];               // the vehicle's identity row
-            const i64 row = v + 1 + item_pos[it] + __popc(bal & ((1u << lane) - 1u));
-            code_t* dst = lv0.sch + row * lv0.stride;
-            for (int m = 0; m < L; m++) dst[m] = (code_t)base[pos[m]];
-            lv0.order[row] = (int)(row - first);
+            const i64 row = v + 1 + item_pos[it] + __popc(bal & ((1u << lane) - 1u));      // (row v + item_pos[item_off[v]] is the vehicle's identity row)
+            Stop* dst = lv0.sch + row * lv0.stride;
+            for (int m = 0; m < L; m++) dst[m] = make_stop(ep, v, base[pos[m]]);
         }
     }
     if (MODE == 0) {
@@ -230,11 +226,10 @@ __global__ void k_perm_rows(const DEpoch* __restrict__ epp, Level lv0, const Con
         const i64 row0 = v + item_pos[item_off[v]];
         const int nf = 1 + (int)(item_pos[item_off[v + 1]] - item_pos[item_off[v]]);
         const bool perms = (ep.mode == AMOD_MODE_OSP) && ep.veh_status[v] == 2;
-        code_t* out = lv0.sch + row0 * lv0.stride;
+        Stop* out = lv0.sch + row0 * lv0.stride;
         int L = 0;
         for (int k = ep.veh_sche_off[v]; k < ep.veh_sche_off[v + 1] && L < len0[v]; k++)
-            if (!perms || ep.sche_onboard[k]) out[L++] = (code_t)ep.sche_code[k];
-        lv0.order[row0] = 0;
+            if (!perms || ep.sche_onboard[k]) out[L++] = make_stop(ep, v, ep.sche_code[k]);
         lv0.trip_veh[v] = v; lv0.nfeas[v] = nf; lv0.s0[v] = row0; lv0.veh_start[v] = v;
         S0[v] = nf;
         if (v == 0) lv0.veh_start[ep.n_veh] = ep.n_veh;
@@ -432,17 +427,6 @@ k_expand_rows(Control* __restrict__ ctl, int which, Level prev, const int* __res
     if (lane == 0 && items) atomicAdd(&ctl->stats.n_items, items);
 }
 
-// schedule position (encounter order) of the first feasible insertion of row r
-__device__ __forceinline__ i64 row_position(i64 r, int G, const RowDesc* __restrict__ rows, const uint8_t* __restrict__ lane_cnt,
-                                            const i64* __restrict__ chunk_pos) {
-    const i64 c = r / G;
-    int lanes_before = 0;
-    for (i64 x = c * G; x < r; x++) lanes_before += rows[x].l + 1;
-    i64 p = chunk_pos[c];
-    for (int x = 0; x < lanes_before; x++) p += lane_cnt[c * 64 + x];
-    return p;
-}
-
 // ---------------------------------------------------------------------------------------------
 // Trip lookup table of one level: (vehicle, ascending request tuple) -> trip index.
 // Replaces the reference's `list in list` scans (dispatch_osp.py:194,202).
@@ -488,17 +472,26 @@ __device__ __forceinline__ int hash_find(const Level& lv, const TripHash& th, in
 // ---------------------------------------------------------------------------------------------
 // Feasible tasks -> trips of the new level, order preserved (dispatch_osp.py:163-164, :217-218).
 // ---------------------------------------------------------------------------------------------
-struct InTaskFeasible {       // scan input: 1 if the task produced at least one feasible schedule
+struct InTaskFeasible {       // scan input: (the task produced a feasible schedule) | (its feasible schedules) << 32
     const Control* ctl; int which; const int* task_nfeas;
     __device__ __forceinline__ i64 size() const { return (ctl->n_chunks[which] && !ctl->overflow) ? ctl->n_tasks[which] : 0; }
-    __device__ __forceinline__ i64 operator()(i64 t) const { return task_nfeas[t] > 0; }
+    __device__ __forceinline__ i64 operator()(i64 t) const { const i64 nf = task_nfeas[t]; return (nf > 0 ? 1 : 0) | (nf << 32); }
+};
+// finisher of that scan: the trip count of the level (low half; the high half repeats the level's schedule count)
+struct FinTrips {
+    int* dst; i64 cap; i64* need; unsigned long long* ovf;
+    __device__ __forceinline__ void operator()(i64 packed) const {
+        i64 tot = PACK_LO(packed);
+        if (tot > *need) *need = tot;
+        if (tot > cap) { atomicOr(ovf, OVF_TRIPS); tot = 0; }
+        *dst = (int)tot;
+    }
 };
 
 __global__ void k_compact_trips(const Control* __restrict__ ctl, int which, const int* __restrict__ task_veh,
                                 const int* __restrict__ task_base, const int* __restrict__ task_q,
-                                const i64* __restrict__ task_row0, const int* __restrict__ task_nfeas, int G,
-                                const RowDesc* __restrict__ rows, const uint8_t* __restrict__ lane_cnt,
-                                const i64* __restrict__ chunk_pos, const i64* __restrict__ trip_pos, Level prev, Level cur,
+                                const int* __restrict__ task_nfeas,
+                                const i64* __restrict__ trip_pos /* exclusive (trips | schedules << 32) before each task */, Level prev, Level cur,
                                 TripHash th, Stats* stats, const DEpoch* __restrict__ epp, int sba,
                                 const i64* __restrict__ major_off, const i64* __restrict__ task_first) {
     const int n = (ctl->n_trips[cur.k] && !ctl->overflow) ? ctl->n_tasks[which] : 0;
@@ -510,7 +503,7 @@ __global__ void k_compact_trips(const Control* __restrict__ ctl, int which, cons
         const int n_veh = epp->n_veh;
         for (int v = blockIdx.x * blockDim.x + threadIdx.x; v <= n_veh; v += stride) {
             const i64 ft = cur.k == 1 ? PACK_LO(major_off[v]) : task_first[prev.veh_start[v]];
-            cur.veh_start[v] = (int)trip_pos[ft];
+            cur.veh_start[v] = (int)PACK_LO(trip_pos[ft]);
         }
     }
     unsigned long long nsch = 0;
@@ -518,10 +511,11 @@ __global__ void k_compact_trips(const Control* __restrict__ ctl, int which, cons
         const int nf = task_nfeas[t];
         if (nf == 0) continue;
         nsch += (unsigned long long)nf;
-        const int o = (int)trip_pos[t];
+        const i64 tp = trip_pos[t];
+        const int o = (int)PACK_LO(tp);
         cur.trip_veh[o] = task_veh[t];
         cur.nfeas[o] = nf;
-        cur.s0[o] = row_position(task_row0[t], G, rows, lane_cnt, chunk_pos);
+        cur.s0[o] = PACK_HI(tp);            // rows are task-major: the trip's first schedule follows those of all earlier tasks
         // trip = sorted(base trip + q)  (dispatch_osp.py:187)
         const int kb = prev.k, q = task_q[t];
         const int* bq = prev.trip_req + (i64)task_base[t] * kb;
@@ -553,7 +547,8 @@ k_classify(Control* __restrict__ ctl, Level cur, int heavy_min, int* __restrict_
         const i64 s0 = cur.s0[t];
         const int nf = cur.nfeas[t];
         const double* __restrict__ cost = cur.sch_cost + s0;
-        int* __restrict__ ord = cur.order + s0;
+        int* __restrict__ fin = cur.final + s0;       // encounter position -> row (list order)
+        const int r0 = (int)s0;
         if (heavy_min > 0 && nf >= heavy_min) {      // left to k_classify_heavy (one block per such trip)
             if (lane == 0) heavy_list[atomicAdd(&ctl->n_heavy[cur.k], 1)] = t;
             continue;
@@ -566,8 +561,8 @@ k_classify(Control* __restrict__ ctl, Level cur, int heavy_min, int* __restrict_
             const unsigned br = __ballot_sync(FULL, isrec), bn = __ballot_sync(FULL, in && !isrec);
             const unsigned lt = (1u << lane) - 1u;
             const int nrec1 = __popc(br);
-            if (isrec) ord[nrec1 - 1 - __popc(br & lt)] = lane;
-            else if (in) ord[nrec1 + __popc(bn & lt)] = lane;
+            if (isrec) fin[lane] = r0 + nrec1 - 1 - __popc(br & lt);
+            else if (in) fin[lane] = r0 + nrec1 + __popc(bn & lt);
             const double best = warp_min(c);
             if (lane == 0) cur.cost[t] = best;
             continue;
@@ -591,8 +586,8 @@ k_classify(Control* __restrict__ ctl, Level cur, int heavy_min, int* __restrict_
             const bool isrec = in && c < incoming;
             const unsigned br = __ballot_sync(FULL, isrec), bn = __ballot_sync(FULL, in && !isrec);
             const unsigned lt = (1u << lane) - 1u;
-            if (isrec) ord[nrec - 1 - (rec_before + __popc(br & lt))] = b + lane;
-            else if (in) ord[nrec + non_before + __popc(bn & lt)] = b + lane;
+            if (isrec) fin[b + lane] = r0 + nrec - 1 - (rec_before + __popc(br & lt));
+            else if (in) fin[b + lane] = r0 + nrec + non_before + __popc(bn & lt);
             rec_before += __popc(br); non_before += __popc(bn);
             run2 = fmin(run2, warp_min(c));
         }
@@ -615,7 +610,8 @@ k_classify_heavy(const Control* __restrict__ ctl, Level cur, const int* __restri
         const i64 s0 = cur.s0[t];
         const int nf = cur.nfeas[t];
         const double* __restrict__ cost = cur.sch_cost + s0;
-        int* __restrict__ ord = cur.order + s0;
+        int* __restrict__ fin = cur.final + s0;
+        const int r0 = (int)s0;
         const int seg = (nf + HEAVY_THREADS - 1) / HEAVY_THREADS;
         const int a = min(nf, tid * seg), b = min(nf, a + seg);
         double m = DINF;
@@ -645,8 +641,8 @@ k_classify_heavy(const Control* __restrict__ ctl, Level cur, const int* __restri
         run = incoming;
         for (int x = a; x < b; x++) {
             const double c = cost[x];
-            if (c < run) { run = c; ord[total_rec - 1 - rb++] = x; }
-            else ord[total_rec + nb++] = x;
+            if (c < run) { run = c; fin[x] = r0 + total_rec - 1 - rb++; }
+            else fin[x] = r0 + total_rec + nb++;
         }
         __syncthreads();
     }

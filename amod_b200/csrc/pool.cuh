@@ -147,8 +147,8 @@ __global__ void k_pool_payload(const DEpoch* __restrict__ epp, Table<TT> tt, Lev
         } else {
             const Level& lv = ls.lv[src];
             const i64 s0 = lv.s0[t];
-            const code_t* in = lv.sch + (s0 + lv.order[s0]) * lv.stride;   // list element 0 = best (scheduling.py:32-34)
-            for (int m = 0; m < slen; m++) sc[m] = in[m];
+            const Stop* in = lv.sch + s0 * lv.stride;   // rows are in list order: element 0 = best (scheduling.py:32-34)
+            for (int m = 0; m < slen; m++) sc[m] = in[m].code;
             for (int m = 0; m < src; m++) tr[m] = lv.trip_req[(i64)t * src + m];
         }
         // cost walk (scheduling.py:101-107) and delay (:126-137)

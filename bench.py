@@ -492,7 +492,7 @@ def main():
         traffic = None
     else:
         alg_bytes, k_ms, k_launches = lookups_eval_p * 32.0, ms_eval, n_eval_launches
-        kname = "k_eval (insertion search, count + fill launches)"
+        kname = "k_eval (insertion search, one pass per trip level)"
         traffic = traffic_info.get(args.config, {}).get("dram_bytes_per_launch") if isinstance(traffic_info.get(args.config), dict) else None
     achieved = alg_bytes / (k_ms * 1e-3) / 1e9 if k_ms > 0 else 0.0
     roofline = {"bound": "hbm", "kernel": kname, "achieved": achieved,
