@@ -78,7 +78,8 @@ EXPORTS = ("amod_create", "amod_destroy", "amod_last_error", "amod_version", "am
            "amod_osp_build", "amod_sba_build", "amod_pool_fetch", "amod_host_register", "amod_host_unregister",
            "amod_pool_view", "amod_npo_match",
            "amod_gather_bench", "amod_gpool_create", "amod_gpool_open_peers", "amod_pool_veh_counts", "amod_gpool_scatter",
-           "amod_gpool_view", "amod_gpool_fetch", "amod_set_graph", "amod_gpool_assemble", "amod_greedy_assign")
+           "amod_gpool_view", "amod_gpool_fetch", "amod_set_graph", "amod_gpool_assemble", "amod_greedy_assign",
+           "amod_gpool_attach", "amod_gpool_detach")
 
 _lib = None
 
@@ -137,6 +138,10 @@ def load_library(path: str | None = None) -> C.CDLL:
     lib.amod_greedy_assign.restype = C.c_int
     lib.amod_gpool_assemble.argtypes = [C.c_void_p, C.c_int32]
     lib.amod_gpool_assemble.restype = C.c_int
+    lib.amod_gpool_attach.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]
+    lib.amod_gpool_attach.restype = C.c_int
+    lib.amod_gpool_detach.argtypes = [C.c_void_p]
+    lib.amod_gpool_detach.restype = C.c_int
     lib.amod_set_graph.argtypes = [C.c_void_p, C.c_int]
     lib.amod_set_graph.restype = C.c_int
     if path is None:

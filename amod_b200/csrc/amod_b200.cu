@@ -103,8 +103,11 @@ struct amod_ctx {
     // multi-GPU global pool (peer-mapped)
     char* gp_base = nullptr; GPoolLayout gp_layout; GPoolPeers gp_peers; bool gp_open = false; int gp_max_veh = 0;
     GSlotLayout gp_slot; i64 gp_o_stage = 0; int gp_world = 0;
-    DevBuf gp_off, gp_tot; void* gp_peer_ptr[GPOOL_MAX_WORLD] = {nullptr};
-    unsigned long long gp_epoch = 0;
+    DevBuf gp_off, gp_tot, gp_place; void* gp_peer_ptr[GPOOL_MAX_WORLD] = {nullptr};
+    GpState* gp_h_state = nullptr;           // pinned mirror of the device-resident assembly state
+    bool gp_attached = false;                // every build also assembles (inside the build's single synchronisation)
+    int gp_root = -1;                        // >= 0: only this rank receives and merges the slices (gather); < 0: every rank does
+    int gp_n_total = 0;
     // greedy assignment
     DevBuf ga_pos, ga_rank, ga_order, ga_state, ga_bv, ga_br, ga_tv, ga_tr, ga_sel, ga_cnt;
     // npo
@@ -136,13 +139,28 @@ static int dispatch_tt(amod_ctx* ctx, F&& f) {
 
 static inline int nblk(i64 n, int per) { return (int)((n + per - 1) / per); }
 
+// Every kernel of the epoch pipeline is launched with programmatic stream serialization (PDL): its blocks may be
+// scheduled while the previous kernel of the stream drains; the kernel itself waits for that grid's completion before
+// touching memory (pdl_enter(), common.cuh).  AMOD_NO_PDL=1 launches them plainly (A/B: profiles/r02_pdl_ab.txt).
+static bool g_pdl = getenv("AMOD_NO_PDL") == nullptr;
+template <typename... KArgs, typename... Args>
+static inline void launch_k(cudaStream_t st, int grid, int block, void (*kern)(KArgs...), Args&&... args) {
+    cudaLaunchConfig_t cfg; memset(&cfg, 0, sizeof cfg);
+    cfg.gridDim = dim3((unsigned)grid); cfg.blockDim = dim3((unsigned)block); cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at; cfg.numAttrs = g_pdl ? 1 : 0;
+    cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+}
+
 // exclusive scan (length and result sizes live on the device; no synchronisation)
 template <typename In, typename Fin>
 static void scan_dev(amod_ctx* ctx, In in, i64* out, Fin fin) {
     const int g = ctx->n_sm;
     i64* partial = ctx->partial.as<i64>();
-    k_scan_a<In><<<g, SCAN_THREADS, 0, ctx->stream>>>(in, partial);
-    k_scan_b<In, Fin><<<g, SCAN_THREADS, 0, ctx->stream>>>(in, partial, out, fin);
+    launch_k(ctx->stream, g, SCAN_THREADS, k_scan_a<In>, in, partial);
+    launch_k(ctx->stream, g, SCAN_THREADS, k_scan_b<In, Fin>, in, partial, out, fin);
     ctx->n_launches += 2;
 }
 
@@ -150,13 +168,13 @@ static void scan_dev(amod_ctx* ctx, In in, i64* out, Fin fin) {
 template <typename InA, typename FinA, typename InB, typename FinB>
 static void scan_fin2(amod_ctx* ctx, InA a, i64* outa, FinA fa, InB b, i64* outb, FinB fb, i64* partial) {
     const int g = (ctx->n_sm / 2) * 2;
-    k_scan2_b<InA, FinA, InB, FinB><<<g, SCAN_THREADS, 0, ctx->stream>>>(a, fa, outa, b, fb, outb, partial);
+    launch_k(ctx->stream, g, SCAN_THREADS, k_scan2_b<InA, FinA, InB, FinB>, a, fa, outa, b, fb, outb, partial);
     ctx->n_launches += 1;
 }
 
 template <typename In, typename Fin>
 static void scan_fin(amod_ctx* ctx, In in, i64* out, Fin fin, i64* partial, cudaStream_t st = nullptr) {
-    k_scan_b<In, Fin><<<ctx->n_sm, SCAN_THREADS, 0, st ? st : ctx->stream>>>(in, partial, out, fin);
+    launch_k(st ? st : ctx->stream, ctx->n_sm, SCAN_THREADS, k_scan_b<In, Fin>, in, partial, out, fin);
     ctx->n_launches += 1;
 }
 
@@ -275,7 +293,8 @@ extern "C" void amod_destroy(amod_ctx* ctx) {
     if (ctx->fetch_pinned) cudaFreeHost(ctx->fetch_pinned);
     for (int r = 0; r < GPOOL_MAX_WORLD; r++) if (ctx->gp_peer_ptr[r]) cudaIpcCloseMemHandle(ctx->gp_peer_ptr[r]);
     if (ctx->gp_base) cudaFree(ctx->gp_base);
-    ctx->gp_off.release(); ctx->gp_tot.release();
+    ctx->gp_off.release(); ctx->gp_tot.release(); ctx->gp_place.release();
+    if (ctx->gp_h_state) cudaFreeHost(ctx->gp_h_state);
     ctx->d_epoch.release();
     for (auto& g : ctx->graphs) if (g.exec) cudaGraphExecDestroy(g.exec);
     if (ctx->ep_pinned) cudaFreeHost(ctx->ep_pinned);
@@ -468,6 +487,9 @@ static int ensure_buffers(amod_ctx* ctx, int V, i64 n_screen, int max_level, con
     return AMOD_OK;
 }
 
+static void enqueue_gpool(amod_ctx* ctx, int run_levels, int max_level);
+static int check_gpool_state(amod_ctx* ctx);
+
 // One attempt: enqueue the whole level-synchronous pipeline on the stream without any host
 // synchronisation; every size is produced and consumed on the device (Control block).
 template <typename TT>
@@ -494,25 +516,25 @@ static int enqueue_build(amod_ctx* ctx, int mode, int cap, Table<TT> tt, int max
     };
     // ---- level 0: basic schedules -----------------------------------------------------------------
     if (cap <= 5) {      // at most 120 orderings per vehicle: one warp per vehicle is enough
-        k_basic<TT, 0><<<GE, WARPS_PER_BLOCK * 32, 0, st>>>(d, tt, ls.lv[0], len0, ctx->S0.as<int>(), nullptr, ctl, dstats,
+        launch_k(st, GE, WARPS_PER_BLOCK * 32, k_basic<TT, 0>, d, tt, ls.lv[0], len0, ctx->S0.as<int>(), nullptr, ctl, dstats,
                                                             scan_site(ctx, MAX_LEVELS), ctx->n_sm);
         // the level-0 store is written beside the reachability screen, which only needs the counts (S0)
         CK(edge(st, sd));
         scan_fin(ctx, InVehInt{ctx->S0.as<int>(), d}, ctx->s0pos.as<i64>(),
                  FinCountI64{&ctl->n_sch[0], ls.lv[0].cap_sch, &ctl->need_sch[0], &ctl->overflow, OVF_SCH}, (i64*)scan_site(ctx, MAX_LEVELS), sd);
-        k_basic<TT, 1><<<GE, WARPS_PER_BLOCK * 32, 0, sd>>>(d, tt, ls.lv[0], len0, ctx->S0.as<int>(), ctx->s0pos.as<i64>(), ctl, dstats,
+        launch_k(sd, GE, WARPS_PER_BLOCK * 32, k_basic<TT, 1>, d, tt, ls.lv[0], len0, ctx->S0.as<int>(), ctx->s0pos.as<i64>(), ctl, dstats,
                                                             nullptr, ctx->n_sm);
         ctx->n_launches += 2;
     } else {             // up to cap! orderings: 32 permutation ranks per warp work item, spread over the GPU
-        k_perm_prep<<<G, 256, 0, st>>>(d, ls.lv[0], len0, ctx->perm_base.as<int>(), ctx->perm_nitems.as<int>(), dstats);
+        launch_k(st, G, 256, k_perm_prep, d, ls.lv[0], len0, ctx->perm_base.as<int>(), ctx->perm_nitems.as<int>(), dstats);
         scan_dev(ctx, InVehInt{ctx->perm_nitems.as<int>(), d}, ctx->perm_off.as<i64>(), FinPermItems{ctl, ctx->cap_items});
-        k_perm_items<TT, 0><<<GE, WARPS_PER_BLOCK * 32, 0, st>>>(d, tt, ls.lv[0], ctl, len0, ctx->perm_base.as<int>(), ctx->perm_off.as<i64>(),
+        launch_k(st, GE, WARPS_PER_BLOCK * 32, k_perm_items<TT, 0>, d, tt, ls.lv[0], ctl, len0, ctx->perm_base.as<int>(), ctx->perm_off.as<i64>(),
                                                                 ctx->perm_cnt.as<int>(), nullptr, dstats);
         scan_dev(ctx, InArray<int>{ctx->perm_cnt.as<int>(), &ctl->n_perm_items, 0}, ctx->perm_pos.as<i64>(),
                  FinBasicRows{ctl, d, ls.lv[0].cap_sch});
-        k_perm_items<TT, 1><<<GE, WARPS_PER_BLOCK * 32, 0, st>>>(d, tt, ls.lv[0], ctl, len0, ctx->perm_base.as<int>(), ctx->perm_off.as<i64>(),
+        launch_k(st, GE, WARPS_PER_BLOCK * 32, k_perm_items<TT, 1>, d, tt, ls.lv[0], ctl, len0, ctx->perm_base.as<int>(), ctx->perm_off.as<i64>(),
                                                                 ctx->perm_cnt.as<int>(), ctx->perm_pos.as<i64>(), dstats);
-        k_perm_rows<<<G, 256, 0, st>>>(d, ls.lv[0], ctl, len0, ctx->S0.as<int>(), ctx->perm_off.as<i64>(), ctx->perm_pos.as<i64>());
+        launch_k(st, G, 256, k_perm_rows, d, ls.lv[0], ctl, len0, ctx->S0.as<int>(), ctx->perm_off.as<i64>(), ctx->perm_pos.as<i64>());
         CK(edge(st, sd));     // (the side branch joins the graph here; it has nothing to do before the levels)
         ctx->n_launches += 4;
     }
@@ -520,11 +542,11 @@ static int enqueue_build(amod_ctx* ctx, int mode, int cap, Table<TT> tt, int max
     {
         const int G1 = std::max(1, 32 / (ls.lv[0].stride + 1));
         CK(cudaEventRecord(get_event(ctx, EV_SCREEN), st));
-        k_screen_count<TT><<<ctx->n_sm * 16, SCREEN_WARPS * 32, 0, st>>>(d, tt, ctx->S0.as<int>(), ctx->flag8.as<unsigned>(), ctx->pos.as<i64>(),
+        launch_k(st, ctx->n_sm * 16, SCREEN_WARPS * 32, k_screen_count<TT>, d, tt, ctx->S0.as<int>(), ctx->flag8.as<unsigned>(), ctx->pos.as<i64>(),
                                                                          scan_site(ctx, MAX_LEVELS + 1), ctx->n_sm);
         scan_fin(ctx, InMajorPacked{ctx->pos.as<i64>(), d}, ctx->major_off.as<i64>(),
                  FinTasksRows{ctl, 0, ctx->cap_tasks, ctx->cap_rows, ctx->cap_chunks, G1}, (i64*)scan_site(ctx, MAX_LEVELS + 1));
-        k_screen_fill<<<GE, WARPS_PER_BLOCK * 32, 0, st>>>(d, ctl, ctx->S0.as<int>(), ctx->flag8.as<unsigned>(), ctx->major_off.as<i64>(),
+        launch_k(st, GE, WARPS_PER_BLOCK * 32, k_screen_fill, d, ctl, ctx->S0.as<int>(), ctx->flag8.as<unsigned>(), ctx->major_off.as<i64>(),
                                                           ctx->task_veh[0].as<int>(), ctx->task_base[0].as<int>(), ctx->task_q[0].as<int>(),
                                                           ctx->task_nchunk[0].as<int>(), ctx->task_chunk0.as<i64>());
         CK(cudaEventRecord(get_event(ctx, EV_SCREEN + 1), st));
@@ -552,7 +574,7 @@ static int enqueue_build(amod_ctx* ctx, int mode, int cap, Table<TT> tt, int max
     i64* cpos = ctx->chunk_pos.as<i64>();
     int* tnf = ctx->task_nfeas.as<int>();
     CK(edge(sd, st));     // level 0 is stored
-    k_expand_rows<<<GE, 256, 0, st>>>(ctl, 0, ls.lv[0], len0, ctx->task_veh[0].as<int>(), ctx->task_base[0].as<int>(), ctx->task_q[0].as<int>(),
+    launch_k(st, GE, 256, k_expand_rows, ctl, 0, ls.lv[0], len0, ctx->task_veh[0].as<int>(), ctx->task_base[0].as<int>(), ctx->task_q[0].as<int>(),
                                       ctx->task_nchunk[0].as<int>(), row0, rows_buf[0], tnf);
     ctx->n_launches++;
     const int n_regions = GEV;
@@ -568,7 +590,7 @@ static int enqueue_build(amod_ctx* ctx, int mode, int cap, Table<TT> tt, int max
         const int Gk = std::max(1, 32 / (prev.stride + 1));      // rows per chunk: Gk * (longest schedule + 1) <= 32 lanes
         RowDesc* rows = rows_buf[cur];
         CK(cudaEventRecord(get_event(ctx, n_ev++), st));
-        k_eval<TT><<<GEV, WARPS_PER_BLOCK * 32, 0, st>>>(d, tt, prev, lv, ctl, cur, Gk, rows, ctx->chunk_cnt.as<int>(),
+        launch_k(st, GEV, WARPS_PER_BLOCK * 32, k_eval<TT>, d, tt, prev, lv, ctl, cur, Gk, rows, ctx->chunk_cnt.as<int>(),
                                                        ctx->lane_cnt.as<uint8_t>(), tnf, dstats, scan_site(ctx, k), half,
                                                        tup, tup_cnt, region_cap);
         CK(cudaEventRecord(get_event(ctx, n_ev++), st));
@@ -578,22 +600,22 @@ static int enqueue_build(amod_ctx* ctx, int mode, int cap, Table<TT> tt, int max
                   FinTrips{&ctl->n_trips[k], (i64)lv.cap_trips, &ctl->need_trips[k], &ctl->overflow}, (i64*)scan_site(ctx, k));
         CK(edge(st, sd));                                         // fork
         const TripHash th = hash_of(k);
-        k_compact_trips<<<G, 256, 0, sd>>>(ctl, cur, tv, tb, tq, tnf, ctx->trip_pos.as<i64>(), prev, lv, th, dstats, d, sba,
+        launch_k(sd, G, 256, k_compact_trips, ctl, cur, tv, tb, tq, tnf, ctx->trip_pos.as<i64>(), prev, lv, th, dstats, d, sba,
                                           ctx->major_off.as<i64>(), ctx->task_first.as<i64>());
         cudaEvent_t named = get_sync_event(ctx, n_sync++);        // the level's trips have their rows (s0, nfeas)
         CK(cudaEventRecord(named, sd));
         // main: costs to their encounter positions -> list order per trip -> schedules straight into their final rows
-        k_place_cost<<<n_regions, PLACE_THREADS, 0, st>>>(ctl, tup, tup_cnt, region_cap, ctx->lane_cnt.as<uint8_t>(), cpos, lv, tup_pos);
+        launch_k(st, n_regions, PLACE_THREADS, k_place_cost, ctl, tup, tup_cnt, region_cap, ctx->lane_cnt.as<uint8_t>(), cpos, lv, tup_pos);
         CK(cudaStreamWaitEvent(st, named, 0));
         const int heavy_min = ctx->heavy_min >= 0 ? ctx->heavy_min : (cap > 5 ? 2048 : 0);   // large capacities: trips with 10^3..10^5 schedules
-        k_classify<<<GE, WARPS_PER_BLOCK * 32, 0, st>>>(ctl, lv, heavy_min, ctx->heavy_list.as<int>());
-        if (heavy_min) { k_classify_heavy<<<ctx->n_sm * 2, HEAVY_THREADS, 0, st>>>(ctl, lv, ctx->heavy_list.as<int>()); ctx->n_launches++; }
-        k_place_rows<<<n_regions, PLACE_THREADS, 0, st>>>(d, ctl, tup, tup_cnt, region_cap, tup_pos, rows, Gk, prev, lv);
+        launch_k(st, GE, WARPS_PER_BLOCK * 32, k_classify, ctl, lv, heavy_min, ctx->heavy_list.as<int>());
+        if (heavy_min) { launch_k(st, ctx->n_sm * 2, HEAVY_THREADS, k_classify_heavy, ctl, lv, ctx->heavy_list.as<int>()); ctx->n_launches++; }
+        launch_k(st, n_regions, PLACE_THREADS, k_place_rows, d, ctl, tup, tup_cnt, region_cap, tup_pos, rows, Gk, prev, lv);
         ctx->n_launches += 5;       // k_eval, k_compact_trips, k_place_cost, k_classify, k_place_rows (the scans count themselves)
         if (k < max_level) {
             // ---- candidates of size k+1 (dispatch_osp.py:183-216), their tasks and rows ----------------------
             const TripHash thn = hash_of(k + 1);
-            k_gen_count<<<GE, WARPS_PER_BLOCK * 32, 0, sd>>>(d, ctl, ls.lv[1], lv, th, ctx->row_cnt.as<int>(), ctx->gen_cache.as<int2>(),
+            launch_k(sd, GE, WARPS_PER_BLOCK * 32, k_gen_count, d, ctl, ls.lv[1], lv, th, ctx->row_cnt.as<int>(), ctx->gen_cache.as<int2>(),
                                                             ctx->gen_partial.as<unsigned long long>(), thn.slots, thn.mask ? thn.mask + 1 : 0u);
             GenOut go;
             go.tmp_j = ctx->tmp_j.as<int>(); go.tmp_q = ctx->tmp_q.as<int>();
@@ -601,7 +623,7 @@ static int enqueue_build(amod_ctx* ctx, int mode, int cap, Table<TT> tt, int max
             go.task_row0 = row0; go.rows = rows_buf[nxt]; go.task_nfeas = tnf; go.task_first = ctx->task_first.as<i64>();
             go.cap_tasks = ctx->cap_tasks; go.cap_rows = ctx->cap_rows; go.cap_chunks = ctx->cap_chunks;
             go.G_next = std::max(1, 32 / (lv.stride + 1));
-            k_gen_emit<<<GE, WARPS_PER_BLOCK * 32, 0, sd>>>(ctl, nxt, ls.lv[1], lv, th, len0, ctx->row_cnt.as<int>(), ctx->gen_cache.as<int2>(),
+            launch_k(sd, GE, WARPS_PER_BLOCK * 32, k_gen_emit, ctl, nxt, ls.lv[1], lv, th, len0, ctx->row_cnt.as<int>(), ctx->gen_cache.as<int2>(),
                                                            ctx->gen_partial.as<unsigned long long>(), go, ctx->gen_inline);
             ctx->n_launches += 2;
         }
@@ -611,13 +633,15 @@ static int enqueue_build(amod_ctx* ctx, int mode, int cap, Table<TT> tt, int max
     {
         LevelSet lsp = ls;
         lsp.n = max_level + 1;          // only the levels searched this epoch hold current data
-        k_pool_meta<<<G, 256, 0, st>>>(d, lsp, len0, ctx->veh_off.as<i64>(), ctl, pb, scan_site(ctx, MAX_LEVELS + 2), half);
+        launch_k(st, G, 256, k_pool_meta, d, lsp, len0, ctx->veh_off.as<i64>(), ctl, pb, scan_site(ctx, MAX_LEVELS + 2), half);
         scan_fin2(ctx, InEntLen{pb.ent_tlen, ctl}, pb.trip_off, FinCountI64{&ctl->n_ptr, pb.cap_ptr, &ctl->need_ptr, &ctl->overflow, OVF_POOL},
                   InEntLen{pb.ent_slen, ctl}, pb.sche_off, FinCountI64{&ctl->n_pst, pb.cap_pst, &ctl->need_pst, &ctl->overflow, OVF_POOL},
                   (i64*)scan_site(ctx, MAX_LEVELS + 2));
-        k_pool_payload<TT><<<G * 2, 128, 0, st>>>(d, tt, lsp, ctl, pb);
+        launch_k(st, G * 2, 128, k_pool_payload<TT>, d, tt, lsp, ctl, pb);
         ctx->n_launches += 2;
     }
+    // ---- multi-GPU: this rank's slice travels (and, on the merging ranks, the fleet-wide pool is assembled) in the same graph
+    if (ctx->gp_attached && !sba) enqueue_gpool(ctx, max_level, cap + 4);
     *n_ev_out = n_ev;
     return AMOD_OK;
 }
@@ -698,6 +722,8 @@ static int build_impl(amod_ctx* ctx, const amod_epoch* ep, int loc, amod_stats* 
         }
         CK(cudaEventRecord(ctx->ev1, st));
         CK(cudaMemcpyAsync(h, ctx->ctl.p, sizeof(Control), cudaMemcpyDeviceToHost, st));
+        const bool with_gp = ctx->gp_attached && mode != AMOD_MODE_SBA;
+        if (with_gp) CK(cudaMemcpyAsync(ctx->gp_h_state, ctx->gp_tot.p, sizeof(GpState), cudaMemcpyDeviceToHost, st));
         CK(cudaStreamSynchronize(st));
         CK(cudaGetLastError());
         if (!h->overflow) {
@@ -764,6 +790,7 @@ static int build_impl(amod_ctx* ctx, const amod_epoch* ep, int loc, amod_stats* 
         }
     }
     (void)total_tasks;
+    if (ctx->gp_attached && mode != AMOD_MODE_SBA) CKR(check_gpool_state(ctx));
     if (mode != AMOD_MODE_SBA && run_levels == max_level && h->n_trips[max_level] > 0)
         return ctx->fail(AMOD_E_LEVELS, "a feasible trip of size cap+4=%d exists; the reference raises IndexError here "
                                         "(dispatch_osp.py:8,226)", max_level);
@@ -904,7 +931,21 @@ extern "C" int amod_gpool_create(amod_ctx* ctx, int64_t cap_entries, int64_t cap
     CK(cudaMemset(ctx->gp_base, 0, (size_t)ctx->gp_layout.o_veh));      // flags + header start at zero
     ctx->gp_max_veh = max_veh_total;
     CK(ctx->gp_off.ensure(8 * 3 * ((size_t)max_veh_total + 2)));
-    CK(ctx->gp_tot.ensure(8 * 8));
+    CK(ctx->gp_tot.ensure(sizeof(GpState)));
+    CK(cudaMemset(ctx->gp_tot.p, 0, sizeof(GpState)));
+    CK(cudaMallocHost((void**)&ctx->gp_h_state, sizeof(GpState)));
+    {   // bounded spins: AMOD_GP_TIMEOUT_S seconds (default 30) of the SM clock
+        GpState init; memset(&init, 0, sizeof init);
+        const char* ts = getenv("AMOD_GP_TIMEOUT_S");
+        init.timeout_clk = (long long)((ts ? std::max(1.0, atof(ts)) : 30.0) * 1.9e9);
+        CK(cudaMemcpy(ctx->gp_tot.p, &init, sizeof init, cudaMemcpyHostToDevice));
+    }
+    {   // default placement: vehicles interleaved over the ranks (global v = local v / world of rank v % world)
+        std::vector<int> place(2 * (size_t)max_veh_total);
+        for (int v = 0; v < max_veh_total; v++) { place[v] = v % world; place[(size_t)max_veh_total + v] = v / world; }
+        CK(ctx->gp_place.ensure(4 * place.size()));
+        CK(cudaMemcpy(ctx->gp_place.p, place.data(), 4 * place.size(), cudaMemcpyHostToDevice));
+    }
     cudaIpcMemHandle_t h;
     CK(cudaIpcGetMemHandle(&h, ctx->gp_base));
     memcpy(ipc_handle_out, &h, sizeof h);
@@ -962,7 +1003,7 @@ extern "C" int amod_gpool_scatter(amod_ctx* ctx, const int32_t* counts_all_dev, 
     const int world = ctx->gp_peers.world;
     i64* off = ctx->gp_off.as<i64>();
     const size_t stride = (size_t)ctx->gp_max_veh + 2;
-    i64* tot = ctx->gp_tot.as<i64>();
+    i64* tot = ctx->gp_tot.as<i64>();       // GpState: tot[0..2], err at [3]
     CK(cudaMemsetAsync(tot + 3, 0, 8, st));
     for (int c = 0; c < 3; c++)
         scan_dev(ctx, InGlobalVeh{counts_all_dev, world, veh_per_rank_max, c, n_veh_total}, off + c * stride, FinStore{tot + c});
@@ -977,57 +1018,89 @@ extern "C" int amod_gpool_scatter(amod_ctx* ctx, const int32_t* counts_all_dev, 
     return AMOD_OK;
 }
 
-extern "C" int amod_gpool_assemble(amod_ctx* ctx, int32_t n_veh_total) {
-    if (!ctx) return AMOD_E_BADARG;
-    if (!ctx->gp_open) return ctx->fail(AMOD_E_BADARG, "amod_gpool_open_peers first");
-    if (!ctx->pool_valid) return ctx->fail(AMOD_E_BADARG, "no pool has been built on this context");
-    if (ctx->h_epoch->mode == AMOD_MODE_SBA) return ctx->fail(AMOD_E_BADARG, "peer assembly needs a vehicle-major (OSP) pool");
-    if (n_veh_total > ctx->gp_max_veh) return ctx->fail(AMOD_E_CAPACITY, "global pool was created for at most %d vehicles", ctx->gp_max_veh);
-    const int world = ctx->gp_peers.world;
-    if (world != ctx->gp_world) return ctx->fail(AMOD_E_BADARG, "world size differs from amod_gpool_create");
-    CK(cudaSetDevice(ctx->device));
+// the three assembly kernels on the build stream: push my slice (+ flag) | wait for all slices, global offsets | merge
+// (+ "read" flag).  Ranks that do not merge (gather mode, rank != root) only push.  Capturable: no per-epoch argument.
+static void enqueue_gpool(amod_ctx* ctx, int run_levels, int max_level) {
     cudaStream_t st = ctx->stream;
     const GPoolLayout& L = ctx->gp_layout;
     const GSlotLayout& S = ctx->gp_slot;
-    const unsigned long long epoch = ++ctx->gp_epoch;
+    const int world = ctx->gp_peers.world, root = ctx->gp_root, n_total = ctx->gp_n_total;
     i64* off = ctx->gp_off.as<i64>();
     const size_t stride = (size_t)ctx->gp_max_veh + 2;
-    i64* tot = ctx->gp_tot.as<i64>();
-    unsigned long long* err = (unsigned long long*)(tot + 3);
-    unsigned* ticket = (unsigned*)(tot + 4);
-    if (epoch == 1) CK(cudaMemsetAsync(tot + 3, 0, 16, st)); else CK(cudaMemsetAsync(tot + 3, 0, 8, st));
-    // every peer must have finished reading my slot of the previous epoch before I overwrite it
-    const bool prof = getenv("AMOD_GP_PROF") != nullptr;
-    auto mark = [&](int i) { if (prof) cudaEventRecord(get_event(ctx, 64 + i), st); };
-    mark(0);
+    GpState* gst = ctx->gp_tot.as<GpState>();
+    const int* vrank = ctx->gp_place.as<int>();
+    const int* vlocal = vrank + ctx->gp_max_veh;
     GPush P; memset(&P, 0, sizeof P);
     const void* srcs[10] = {nullptr, ctx->veh_off.p, ctx->ent_kind.p, ctx->ent_nfeas.p, ctx->ent_cost.p, ctx->ent_delay.p, ctx->trip_off.p,
                             ctx->sche_off.p, ctx->trip_req.p, ctx->sche_code.p};
     const i64 dsts[10] = {S.o_hdr, S.o_vehoff, S.o_kind, S.o_nfeas, S.o_cost, S.o_delay, S.o_toff, S.o_soff, S.o_treq, S.o_scode};
     for (int g = 0; g < 10; g++) { P.seg[g].src = (const char*)srcs[g]; P.seg[g].dst_off = dsts[g]; P.seg[g].bytes = 0; }
     P.n = 10;
-    // three launches: (wait for last epoch's readers,) push my slice + flag | wait for all slices, global offsets | merge + "read" flag
     k_gp_push_bulk<<<ctx->n_sm * 2, 256, 0, st>>>(P, L, S, ctx->gp_o_stage, ctx->gp_peers, ctx->d_epoch.as<DEpoch>(), ctx->ctl.as<Control>(),
-                                                epoch, ticket, err, ctx->gp_base);
-    mark(1);
+                                                gst, ctx->gp_base, root, run_levels, max_level);
+    ctx->n_launches++;
+    if (root >= 0 && root != ctx->gp_peers.rank) return;
     const char* stage = ctx->gp_base + ctx->gp_o_stage;
-    k_gp_offsets<<<1, 1024, 0, st>>>(stage, S, world, n_veh_total, off, off + stride, off + 2 * stride, tot, ctx->gp_base, L, epoch, err);
-    mark(2);
-    k_gp_merge<<<ctx->n_sm * 8, 256, 0, st>>>(stage, S, ctx->gp_base, L, world, off, off + stride, off + 2 * stride, tot, n_veh_total, err,
-                                              ctx->gp_peers, epoch, ticket + 1);
-    mark(3);
-    i64 h[4];
-    CK(cudaMemcpyAsync(h, tot, sizeof h, cudaMemcpyDeviceToHost, st));
+    k_gp_offsets<<<1, 1024, 0, st>>>(stage, S, world, n_total, off, off + stride, off + 2 * stride, gst, ctx->gp_base, L, vrank, vlocal,
+                                     ctx->ctl.as<Control>(), run_levels, max_level);
+    k_gp_merge<<<ctx->n_sm * 8, 256, 0, st>>>(stage, S, ctx->gp_base, L, world, off, off + stride, off + 2 * stride, gst, n_total,
+                                              ctx->gp_peers, vrank, vlocal, ctx->ctl.as<Control>(), run_levels, max_level);
+    ctx->n_launches += 2;
+}
+
+static int check_gpool_state(amod_ctx* ctx) {
+    GpState* h = ctx->gp_h_state;
+    if (h->err) cudaMemsetAsync(&ctx->gp_tot.as<GpState>()->err, 0, 8, ctx->stream);      // reported once
+    if (h->err & 2) return ctx->fail(AMOD_E_CUDA, "peer assembly timed out waiting for another rank (the PeerPool must be rebuilt on every rank)");
+    if (h->err & 1) return ctx->fail(AMOD_E_CAPACITY, "global pool or staging slot too small (need %lld entries, %lld trip requests, %lld stops)",
+                                     (long long)h->tot[0], (long long)h->tot[1], (long long)h->tot[2]);
+    return AMOD_OK;
+}
+
+extern "C" int amod_gpool_attach(amod_ctx* ctx, int32_t n_veh_total, int32_t root, const int32_t* veh_rank, const int32_t* veh_local) {
+    if (!ctx) return AMOD_E_BADARG;
+    if (!ctx->gp_open) return ctx->fail(AMOD_E_BADARG, "amod_gpool_open_peers first");
+    if (n_veh_total < 0 || n_veh_total > ctx->gp_max_veh) return ctx->fail(AMOD_E_CAPACITY, "global pool was created for at most %d vehicles", ctx->gp_max_veh);
+    if (root >= ctx->gp_peers.world) return ctx->fail(AMOD_E_BADARG, "root outside the world");
+    CK(cudaSetDevice(ctx->device));
+    if ((veh_rank == nullptr) != (veh_local == nullptr)) return ctx->fail(AMOD_E_BADARG, "veh_rank and veh_local come together");
+    std::vector<int> place(2 * (size_t)ctx->gp_max_veh, 0);
+    const int world = ctx->gp_peers.world;
+    for (int v = 0; v < n_veh_total; v++) {
+        const int r = veh_rank ? veh_rank[v] : v % world, u = veh_local ? veh_local[v] : v / world;
+        if (r < 0 || r >= world || u < 0 || u >= ctx->gp_slot.cap_veh) return ctx->fail(AMOD_E_BADARG, "vehicle %d: placement (%d, %d) out of range", v, r, u);
+        place[v] = r; place[(size_t)ctx->gp_max_veh + v] = u;
+    }
+    CK(cudaStreamSynchronize(ctx->stream));
+    CK(cudaMemcpy(ctx->gp_place.p, place.data(), 4 * place.size(), cudaMemcpyHostToDevice));
+    if (!ctx->gp_attached || ctx->gp_root != root || ctx->gp_n_total != n_veh_total) ctx->buf_gen++;      // the epoch graph changes
+    ctx->gp_attached = true; ctx->gp_root = root; ctx->gp_n_total = n_veh_total;
+    return AMOD_OK;
+}
+
+extern "C" int amod_gpool_detach(amod_ctx* ctx) {
+    if (!ctx) return AMOD_E_BADARG;
+    if (ctx->gp_attached) ctx->buf_gen++;
+    ctx->gp_attached = false;
+    return AMOD_OK;
+}
+
+extern "C" int amod_gpool_assemble(amod_ctx* ctx, int32_t n_veh_total) {
+    if (!ctx) return AMOD_E_BADARG;
+    if (!ctx->gp_open) return ctx->fail(AMOD_E_BADARG, "amod_gpool_open_peers first");
+    if (!ctx->pool_valid) return ctx->fail(AMOD_E_BADARG, "no pool has been built on this context");
+    if (ctx->h_epoch->mode == AMOD_MODE_SBA) return ctx->fail(AMOD_E_BADARG, "peer assembly needs a vehicle-major (OSP) pool");
+    if (n_veh_total > ctx->gp_max_veh) return ctx->fail(AMOD_E_CAPACITY, "global pool was created for at most %d vehicles", ctx->gp_max_veh);
+    if (ctx->gp_attached) return ctx->fail(AMOD_E_BADARG, "the pool is assembled by every build while attached (amod_gpool_attach)");
+    if (ctx->gp_peers.world != ctx->gp_world) return ctx->fail(AMOD_E_BADARG, "world size differs from amod_gpool_create");
+    CK(cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    ctx->gp_n_total = n_veh_total;
+    enqueue_gpool(ctx, 0, 0);          // (the build is complete: nothing to rerun)
+    CK(cudaMemcpyAsync(ctx->gp_h_state, ctx->gp_tot.p, sizeof(GpState), cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
     CK(cudaGetLastError());
-    if (prof && (epoch % 16) == 0) {
-        float x[3];
-        for (int i = 0; i < 3; i++) cudaEventElapsedTime(&x[i], ctx->ev_pool[64 + i], ctx->ev_pool[64 + i + 1]);
-        fprintf(stderr, "[gp rank %d] wait_prev+push %.3f wait_all+offsets %.3f merge+signal %.3f ms\n", ctx->gp_peers.rank, x[0], x[1], x[2]);
-    }
-    if (h[3] & 2) return ctx->fail(AMOD_E_CUDA, "peer assembly timed out waiting for another rank");
-    if (h[3] & 1) return ctx->fail(AMOD_E_CAPACITY, "global pool or staging slot too small (need %lld entries, %lld trip requests, %lld stops)", h[0], h[1], h[2]);
-    return AMOD_OK;
+    return check_gpool_state(ctx);
 }
 
 extern "C" int amod_gpool_view(amod_ctx* ctx, amod_pool* v) {

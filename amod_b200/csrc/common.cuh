@@ -107,6 +107,15 @@ struct __align__(16) RowDesc {
     int task, pad;
 };
 
+// Programmatic dependent launch (sm_90+): every kernel of the epoch pipeline is launched with
+// cudaLaunchAttributeProgrammaticStreamSerialization, so its blocks may be scheduled while the kernel before it in the
+// stream is still draining.  First statement of every such kernel: wait until the predecessor grid has completed and its
+// writes are visible, then allow the successor's launch to begin.  (A no-op for launches without the attribute.)
+__device__ __forceinline__ void pdl_enter() {
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
+
 __device__ __forceinline__ int pod_of(int code) { return code < 0 ? 0 : ((code & 1) ? -1 : 1); }
 
 __device__ __forceinline__ void stop_info(const DEpoch& ep, int v, int code, int& node, double& ddl, int& pod) {

@@ -104,6 +104,7 @@ k_eval(const DEpoch* __restrict__ epp, Table<TT> tt, Level prev, Level cur, Cont
        const RowDesc* __restrict__ rows, int* __restrict__ chunk_cnt, uint8_t* __restrict__ lane_cnt,
        int* __restrict__ task_nfeas, Stats* stats, unsigned long long* __restrict__ part, int part_vg,
        Tuple* __restrict__ tup, int* __restrict__ tup_cnt, int region_cap) {
+    pdl_enter();
     __shared__ WarpStage<TT> stage_all[WARPS_PER_BLOCK];
     __shared__ DEpoch s_ep;       // the epoch header once per block: array pointers without a second indirection
     __shared__ int s_cursor;      // feasible-insertion records appended by this block

@@ -84,20 +84,36 @@ __device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long
     return v;
 }
 
-// Wait until every rank's flag `which` in MY pool has reached `epoch` (bounded spin); call with a whole block,
-// threads < world poll one flag each.  which 0 = "slice pushed", 1 = "slice read".
+// Device-resident state of the peer assembly (one per context): the epoch counter lives on the device so that the
+// assembly kernels can be part of the captured epoch graph (no per-epoch kernel argument).
+struct GpState {
+    i64 tot[3];                     // entries, trip requests, stops of the assembled pool
+    unsigned long long err;         // 1 = capacity, 2 = a rank never arrived (time-out)
+    unsigned ticket[2];
+    unsigned long long epoch;       // assemblies completed (pushes issued) by this rank
+    long long timeout_clk;          // bounded spins give up after this many clock64 ticks
+};
+
+// Wait until the flags `which` of the ranks in `mask` in MY pool have reached `epoch` (bounded spin); call with a whole
+// block, threads < world poll one flag each.  which 0 = "slice pushed", 1 = "slices read".
 __device__ __forceinline__ void gp_wait_flags(const char* __restrict__ my_base, const GPoolLayout& L, int world, int which,
-                                              unsigned long long epoch, unsigned long long* err) {
-    if ((int)threadIdx.x < world) {
+                                              unsigned long long epoch, GpState* st, unsigned mask) {
+    if ((int)threadIdx.x < world && ((mask >> threadIdx.x) & 1u)) {
         const unsigned long long* f = (const unsigned long long*)(my_base + L.o_flags) + which * GPOOL_MAX_WORLD + threadIdx.x;
         const long long t0 = clock64();
         while (ld_acquire_sys(f) < epoch) {
-            if (clock64() - t0 > 6000000000ll) { atomicOr(err, 2ull); break; }   // ~3 s: a rank never arrived
+            if (clock64() - t0 > st->timeout_clk) { atomicOr(&st->err, 2ull); break; }   // a rank never arrived
             __nanosleep(200);
         }
         __threadfence_system();
     }
     __syncthreads();
+}
+
+// this rank's build must be complete and final for its slice to travel: an overflowed attempt or one that has to be
+// searched deeper is rerun by the host (amod_b200.cu: build_impl), and only the rerun pushes
+__device__ __forceinline__ bool gp_build_final(const Control* __restrict__ ctl, int run_levels, int max_level) {
+    return !ctl->overflow && !(run_levels < max_level && ctl->n_trips[run_levels] > 0);
 }
 
 
@@ -114,23 +130,27 @@ struct GSlotLayout {        // one staging slot (offsets inside the slot); ident
 struct GSeg { const char* src; i64 dst_off; i64 bytes; };
 struct GPush { GSeg seg[10]; int n; };
 
+// root < 0: every rank receives every slice (all-gather); root >= 0: only `root` does (gather: the rank that hosts the
+// assigner), so a rank sends its slice once instead of `world` times and only the root merges.
 __global__ void __launch_bounds__(256)
 k_gp_push_bulk(GPush P, GPoolLayout L, GSlotLayout S, i64 o_stage, GPoolPeers peers, const DEpoch* __restrict__ epp,
-               const Control* __restrict__ ctl, unsigned long long epoch, unsigned* ticket, unsigned long long* err,
-               const char* __restrict__ my_base) {
-    // every peer must have finished reading my slot of the previous epoch before I overwrite it
-    if (epoch > 1) gp_wait_flags(my_base, L, peers.world, 1, epoch - 1, err);
+               const Control* __restrict__ ctl, GpState* st, const char* __restrict__ my_base, int root, int run_levels, int max_level) {
+    if (!gp_build_final(ctl, run_levels, max_level)) return;
+    const unsigned long long epoch = st->epoch + 1;        // (every block reads it before the last block to finish advances it)
+    const int d0 = root < 0 ? 0 : root, d1 = root < 0 ? peers.world : root + 1;
+    // the readers of my slot must have finished with the previous epoch before I overwrite it
+    if (epoch > 1) gp_wait_flags(my_base, L, peers.world, 1, epoch - 1, st, root < 0 ? 0xffffffffu : (1u << root));
     const i64 n_veh = epp->n_veh, n_ent = ctl->n_ent, n_ptr = ctl->n_ptr, n_pst = ctl->n_pst;
     const bool fits = n_veh <= S.cap_veh && n_ent <= S.cap_ent && n_ptr <= S.cap_ptr && n_pst <= S.cap_pst;
-    if (!fits && blockIdx.x == 0 && threadIdx.x == 0) atomicOr(err, 1ull);
+    if (!fits && blockIdx.x == 0 && threadIdx.x == 0) atomicOr(&st->err, 1ull);
     const i64 tid = (i64)blockIdx.x * blockDim.x + threadIdx.x, nth = (i64)gridDim.x * blockDim.x;
     if (!fits && tid == 0)      // tell every reader that this slot holds nothing usable
-        for (int d = 0; d < peers.world; d++) ((i64*)(peers.base[d] + o_stage + (i64)peers.rank * S.bytes + S.o_hdr))[0] = -1;
+        for (int d = d0; d < d1; d++) ((i64*)(peers.base[d] + o_stage + (i64)peers.rank * S.bytes + S.o_hdr))[0] = -1;
     if (fits) {
         // live sizes of the segments (the host passes capacities; trim to what this epoch produced)
         const i64 live[10] = {32, 8 * (n_veh + 1), 4 * n_ent, 4 * n_ent, 8 * n_ent, 8 * n_ent, 8 * (n_ent + 1), 8 * (n_ent + 1),
                               4 * n_ptr, 4 * n_pst};
-        for (int d = 0; d < peers.world; d++) {
+        for (int d = d0; d < d1; d++) {
             char* slot = peers.base[d] + o_stage + (i64)peers.rank * S.bytes;
             if (tid == 0) { i64* h = (i64*)(slot + S.o_hdr); h[0] = n_veh; h[1] = n_ent; h[2] = n_ptr; h[3] = n_pst; }
             for (int g = 1; g < P.n; g++) {
@@ -148,7 +168,7 @@ k_gp_push_bulk(GPush P, GPoolLayout L, GSlotLayout S, i64 o_stage, GPoolPeers pe
         for (i64 u = tid; u < n_veh; u += nth) {
             const i64 e0 = vo[u], e1 = vo[u + 1];
             const int ce = (int)(e1 - e0), ct = (int)(toff[e1] - toff[e0]), cs = (int)(soff[e1] - soff[e0]);
-            for (int d = 0; d < peers.world; d++) {
+            for (int d = d0; d < d1; d++) {
                 int* cnt = (int*)(peers.base[d] + o_stage + (i64)peers.rank * S.bytes + S.o_cnt);
                 cnt[u] = ce; cnt[S.cap_veh + u] = ct; cnt[2 * S.cap_veh + u] = cs;
             }
@@ -156,20 +176,21 @@ k_gp_push_bulk(GPush P, GPoolLayout L, GSlotLayout S, i64 o_stage, GPoolPeers pe
     }
     __threadfence_system();
     __syncthreads();
-    if (threadIdx.x == 0 && atomicAdd(ticket, 1u) == gridDim.x - 1) {
-        *ticket = 0;
+    if (threadIdx.x == 0 && atomicAdd(&st->ticket[0], 1u) == gridDim.x - 1) {
+        st->ticket[0] = 0;
+        st->epoch = epoch;
         __threadfence_system();
-        for (int d = 0; d < peers.world; d++)
+        for (int d = d0; d < d1; d++)
             st_release_sys((unsigned long long*)(peers.base[d] + L.o_flags) + peers.rank, epoch);
     }
 }
 
-struct InStagedVeh {        // counts of global vehicle v read from the staged slices (vehicle v = local v / world of rank v % world)
-    const char* stage; GSlotLayout S; int world, comp, n_total;
+struct InStagedVeh {        // counts of global vehicle v read from the staged slices: vehicle v is local vehicle vlocal[v] of rank vrank[v]
+    const char* stage; GSlotLayout S; const int* vrank; const int* vlocal; int comp, n_total;
     __device__ __forceinline__ i64 size() const { return n_total; }
     __device__ __forceinline__ i64 operator()(i64 v) const {
-        const char* slot = stage + (v % world) * S.bytes;
-        const i64 u = v / world;
+        const char* slot = stage + (i64)vrank[v] * S.bytes;
+        const i64 u = vlocal[v];
         if (((const i64*)(slot + S.o_hdr))[0] <= u) return 0;        // slot unusable (its rank overflowed) or short
         return ((const int*)(slot + S.o_cnt))[comp * S.cap_veh + u];
     }
@@ -183,13 +204,16 @@ struct InStagedVeh {        // counts of global vehicle v read from the staged s
 __global__ void __launch_bounds__(256)
 k_gp_merge(const char* __restrict__ stage, GSlotLayout S, char* __restrict__ B, GPoolLayout L, int world,
            const i64* __restrict__ goff_e, const i64* __restrict__ goff_t, const i64* __restrict__ goff_s,
-           const i64* __restrict__ totals, int n_veh_total, unsigned long long* err, GPoolPeers peers, unsigned long long epoch,
-           unsigned* ticket) {
+           GpState* st, int n_veh_total, GPoolPeers peers, const int* __restrict__ vrank, const int* __restrict__ vlocal,
+           const Control* __restrict__ ctl, int run_levels, int max_level) {
+    if (!gp_build_final(ctl, run_levels, max_level)) return;
+    const i64* totals = st->tot;
+    const unsigned long long epoch = st->epoch;
     const int lane = threadIdx.x & 31;
     const i64 nwarps = (i64)gridDim.x * (blockDim.x >> 5);
-    bool usable = totals[0] <= L.cap_ent && totals[1] <= L.cap_ptr && totals[2] <= L.cap_pst;
+    bool usable = totals[0] <= L.cap_ent && totals[1] <= L.cap_ptr && totals[2] <= L.cap_pst && !(st->err & 2ull);
     for (int r = 0; r < world; r++) usable &= ((const i64*)(stage + (i64)r * S.bytes + S.o_hdr))[0] >= 0;
-    if (!usable && blockIdx.x == 0 && threadIdx.x == 0) atomicOr(err, 1ull);
+    if (!usable && blockIdx.x == 0 && threadIdx.x == 0) atomicOr(&st->err, 1ull);
     int* g_veh = (int*)(B + L.o_veh); int* g_kind = (int*)(B + L.o_kind); int* g_nfeas = (int*)(B + L.o_nfeas);
     double* g_cost = (double*)(B + L.o_cost); double* g_delay = (double*)(B + L.o_delay);
     i64* g_toff = (i64*)(B + L.o_toff); i64* g_soff = (i64*)(B + L.o_soff);
@@ -207,8 +231,8 @@ k_gp_merge(const char* __restrict__ stage, GSlotLayout S, char* __restrict__ B, 
             int a = 0, b = n_veh_total;     // last vehicle whose first entry is <= E (vehicles without entries share their successor's offset)
             while (b - a > 1) { const int m = (a + b) >> 1; if (goff_e[m] <= E) a = m; else b = m; }
             const int v = a;
-            const char* slot = stage + (i64)(v % world) * S.bytes;
-            const i64 u = v / world;
+            const char* slot = stage + (i64)vrank[v] * S.bytes;
+            const i64 u = vlocal[v];
             const i64* s_toff = (const i64*)(slot + S.o_toff); const i64* s_soff = (const i64*)(slot + S.o_soff);
             const i64 e0 = ((const i64*)(slot + S.o_vehoff))[u];
             const i64 e = e0 + (E - goff_e[v]);
@@ -246,8 +270,8 @@ k_gp_merge(const char* __restrict__ stage, GSlotLayout S, char* __restrict__ B, 
     __syncthreads();
     if (threadIdx.x == 0) {
         __threadfence();
-        if (atomicAdd(ticket, 1u) == gridDim.x - 1) {
-            *ticket = 0;
+        if (atomicAdd(&st->ticket[1], 1u) == gridDim.x - 1) {
+            st->ticket[1] = 0;
             __threadfence_system();
             for (int d = 0; d < peers.world; d++)
                 st_release_sys((unsigned long long*)(peers.base[d] + L.o_flags) + GPOOL_MAX_WORLD + peers.rank, epoch);
@@ -260,15 +284,16 @@ k_gp_merge(const char* __restrict__ stage, GSlotLayout S, char* __restrict__ B, 
 // every rank pushed with its slice
 __global__ void __launch_bounds__(1024)
 k_gp_offsets(const char* __restrict__ stage, GSlotLayout S, int world, int n_total, i64* __restrict__ goff_e, i64* __restrict__ goff_t,
-             i64* __restrict__ goff_s, i64* __restrict__ totals, const char* __restrict__ my_base, GPoolLayout L, unsigned long long epoch,
-             unsigned long long* err) {
+             i64* __restrict__ goff_s, GpState* st, const char* __restrict__ my_base, GPoolLayout L, const int* __restrict__ vrank,
+             const int* __restrict__ vlocal, const Control* __restrict__ ctl, int run_levels, int max_level) {
     __shared__ i64 sm[3][32];
-    gp_wait_flags(my_base, L, world, 0, epoch, err);       // every rank's slice of this epoch has landed in my memory
+    if (!gp_build_final(ctl, run_levels, max_level)) return;
+    gp_wait_flags(my_base, L, world, 0, st->epoch, st, 0xffffffffu);       // every rank's slice of this epoch has landed in my memory
     const int per = (n_total + 1023) / 1024;
     const int v0 = min(n_total, (int)threadIdx.x * per), v1 = min(n_total, v0 + per);
     i64 a[3] = {0, 0, 0};
     for (int v = v0; v < v1; v++)
-        for (int c = 0; c < 3; c++) a[c] += InStagedVeh{stage, S, world, c, n_total}(v);
+        for (int c = 0; c < 3; c++) a[c] += InStagedVeh{stage, S, vrank, vlocal, c, n_total}(v);
     // block exclusive scan of the three running sums
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     i64 ex[3];
@@ -284,13 +309,13 @@ k_gp_offsets(const char* __restrict__ stage, GSlotLayout S, int world, int n_tot
             i64 z = sm[c][lane], y = z;
             for (int o = 1; o < 32; o <<= 1) { i64 t = __shfl_up_sync(FULL, y, o); if (lane >= o) y += t; }
             sm[c][lane] = y - z;
-            if (lane == 31) totals[c] = y;
+            if (lane == 31) st->tot[c] = y;
         }
     __syncthreads();
     i64 run[3] = {ex[0] + sm[0][w], ex[1] + sm[1][w], ex[2] + sm[2][w]};
     for (int v = v0; v < v1; v++) {
         goff_e[v] = run[0]; goff_t[v] = run[1]; goff_s[v] = run[2];
-        for (int c = 0; c < 3; c++) run[c] += InStagedVeh{stage, S, world, c, n_total}(v);
+        for (int c = 0; c < 3; c++) run[c] += InStagedVeh{stage, S, vrank, vlocal, c, n_total}(v);
     }
     if (threadIdx.x == 1023) { goff_e[n_total] = run[0]; goff_t[n_total] = run[1]; goff_s[n_total] = run[2]; }
 }

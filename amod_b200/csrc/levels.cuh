@@ -36,6 +36,7 @@ template <typename TT, int MODE>
 __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32)
 k_basic(const DEpoch* __restrict__ epp, Table<TT> tt, Level lv0, int* __restrict__ len0, int* __restrict__ S0, const i64* __restrict__ s0pos,
         const Control* __restrict__ ctl, Stats* stats, unsigned long long* __restrict__ part, int part_vg) {
+    pdl_enter();
     const DEpoch& ep = *epp;
     const int lane = threadIdx.x & 31;
     if (MODE == 1 && ctl->overflow) return;          // level-0 store overflowed
@@ -148,6 +149,7 @@ __device__ __forceinline__ bool perm_feasible(const DEpoch& ep, const Table<TT>&
 
 __global__ void k_perm_prep(const DEpoch* __restrict__ epp, Level lv0, int* __restrict__ len0, int* __restrict__ perm_base,
                             int* __restrict__ n_items, Stats* stats) {
+    pdl_enter();
     const DEpoch& ep = *epp;
     for (int v = blockIdx.x * blockDim.x + threadIdx.x; v < ep.n_veh; v += gridDim.x * blockDim.x) {
         const int s0 = ep.veh_sche_off[v], s1 = ep.veh_sche_off[v + 1];
@@ -185,6 +187,7 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32)
 k_perm_items(const DEpoch* __restrict__ epp, Table<TT> tt, Level lv0, const Control* __restrict__ ctl, const int* __restrict__ len0,
              const int* __restrict__ perm_base, const i64* __restrict__ item_off, int* __restrict__ item_cnt,
              const i64* __restrict__ item_pos, Stats* stats) {
+    pdl_enter();
     const DEpoch& ep = *epp;
     const int lane = threadIdx.x & 31;
     const int n = ctl->overflow ? 0 : ctl->n_perm_items;
@@ -220,6 +223,7 @@ k_perm_items(const DEpoch* __restrict__ epp, Table<TT> tt, Level lv0, const Cont
 // identity rows and the level-0 trip records
 __global__ void k_perm_rows(const DEpoch* __restrict__ epp, Level lv0, const Control* __restrict__ ctl, const int* __restrict__ len0,
                             int* __restrict__ S0, const i64* __restrict__ item_off, const i64* __restrict__ item_pos) {
+    pdl_enter();
     const DEpoch& ep = *epp;
     if (ctl->overflow) return;
     for (int v = blockIdx.x * blockDim.x + threadIdx.x; v < ep.n_veh; v += gridDim.x * blockDim.x) {
@@ -255,6 +259,7 @@ template <typename TT>
 __global__ void __launch_bounds__(SCREEN_WARPS * 32)
 k_screen_count(const DEpoch* __restrict__ epp, Table<TT> tt, const int* __restrict__ S0, unsigned* __restrict__ bits,
                i64* __restrict__ major_cnt, unsigned long long* __restrict__ part, int part_vg) {
+    pdl_enter();
     __shared__ int s_cnt[SCREEN_WARPS], s_rows[SCREEN_WARPS];
     const DEpoch& ep = *epp;
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
@@ -342,6 +347,7 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32)
 k_screen_fill(const DEpoch* __restrict__ epp, const Control* __restrict__ ctl, const int* __restrict__ S0,
               const unsigned* __restrict__ bits, const i64* __restrict__ major_off, int* task_veh, int* task_base, int* task_q,
               int* task_S, i64* task_row0) {
+    pdl_enter();
     const DEpoch& ep = *epp;
     if (ctl->n_tasks[0] == 0 || ctl->overflow) return;
     const int lane = threadIdx.x & 31;
@@ -384,6 +390,7 @@ __global__ void __launch_bounds__(256)
 k_expand_rows(Control* __restrict__ ctl, int which, Level prev, const int* __restrict__ len0, const int* __restrict__ task_veh,
               const int* __restrict__ task_base, const int* __restrict__ task_q, const int* __restrict__ task_S,
               const i64* __restrict__ task_row0, RowDesc* __restrict__ rows, int* __restrict__ task_nfeas) {
+    pdl_enter();
     const int n = (ctl->n_rows[which] && !ctl->overflow) ? ctl->n_tasks[which] : 0;
     const int lane = threadIdx.x & 31;
     const int nwarps = gridDim.x * (blockDim.x >> 5);
@@ -494,6 +501,7 @@ __global__ void k_compact_trips(const Control* __restrict__ ctl, int which, cons
                                 const i64* __restrict__ trip_pos /* exclusive (trips | schedules << 32) before each task */, Level prev, Level cur,
                                 TripHash th, Stats* stats, const DEpoch* __restrict__ epp, int sba,
                                 const i64* __restrict__ major_off, const i64* __restrict__ task_first) {
+    pdl_enter();
     const int n = (ctl->n_trips[cur.k] && !ctl->overflow) ? ctl->n_tasks[which] : 0;
     const int stride = gridDim.x * blockDim.x;
     if (!sba && !ctl->overflow) {
@@ -540,6 +548,7 @@ __global__ void k_compact_trips(const Control* __restrict__ ctl, int which, cons
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32)
 k_classify(Control* __restrict__ ctl, Level cur, int heavy_min, int* __restrict__ heavy_list) {
+    pdl_enter();
     const int lane = threadIdx.x & 31;
     const int n = ctl->overflow ? 0 : ctl->n_trips[cur.k];
     const int nwarps = gridDim.x * WARPS_PER_BLOCK;
@@ -601,6 +610,7 @@ k_classify(Control* __restrict__ ctl, Level cur, int heavy_min, int* __restrict_
 #define HEAVY_THREADS 512
 __global__ void __launch_bounds__(HEAVY_THREADS)
 k_classify_heavy(const Control* __restrict__ ctl, Level cur, const int* __restrict__ heavy_list) {
+    pdl_enter();
     __shared__ double s_min[HEAVY_THREADS];
     __shared__ int s_rec[HEAVY_THREADS], s_non[HEAVY_THREADS];
     const int n = ctl->overflow ? 0 : ctl->n_heavy[cur.k];
@@ -740,6 +750,7 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32)
 k_gen_count(const DEpoch* __restrict__ epp, const Control* __restrict__ ctl, Level l1, Level prev, TripHash th,
             int* __restrict__ row_cnt, int2* __restrict__ row_cache, unsigned long long* __restrict__ blk_partial,
             int* __restrict__ next_hash, unsigned next_hash_size) {
+    pdl_enter();
     __shared__ unsigned long long s_sum;
     __shared__ int s_j[WARPS_PER_BLOCK][32];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
@@ -768,6 +779,7 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32)
 k_gen_emit(Control* __restrict__ ctl, int which_next, Level l1, Level prev, TripHash th, const int* __restrict__ len0,
            const int* __restrict__ row_cnt, const int2* __restrict__ row_cache, const unsigned long long* __restrict__ blk_partial,
            GenOut o, int inline_max /* <= GEN_INLINE; 0 forces the recompute path (tests) */) {
+    pdl_enter();
     __shared__ int s_j[WARPS_PER_BLOCK][32];
     __shared__ i64 s_scan[SCAN_THREADS / 32 + 1];
     __shared__ i64 s_off[WARPS_PER_BLOCK * 32];

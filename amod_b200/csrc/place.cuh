@@ -36,6 +36,7 @@ __device__ __forceinline__ int lanes_before(const uint8_t* __restrict__ lane_cnt
 __global__ void __launch_bounds__(PLACE_THREADS)
 k_place_cost(const Control* __restrict__ ctl, const Tuple* __restrict__ tup, const int* __restrict__ tup_cnt, int region_cap,
              const uint8_t* __restrict__ lane_cnt, const i64* __restrict__ chunk_pos, Level cur, unsigned* __restrict__ tup_pos) {
+    pdl_enter();
     if (ctl->overflow) return;
     const int n = tup_cnt[blockIdx.x];
     const i64 base = (i64)blockIdx.x * region_cap;
@@ -51,6 +52,7 @@ k_place_cost(const Control* __restrict__ ctl, const Tuple* __restrict__ tup, con
 __global__ void __launch_bounds__(PLACE_THREADS)
 k_place_rows(const DEpoch* __restrict__ epp, const Control* __restrict__ ctl, const Tuple* __restrict__ tup, const int* __restrict__ tup_cnt,
              int region_cap, const unsigned* __restrict__ tup_pos, const RowDesc* __restrict__ rows, int G, Level prev, Level cur) {
+    pdl_enter();
     if (ctl->overflow) return;
     const DEpoch& ep = *epp;
     const int n = tup_cnt[blockIdx.x];

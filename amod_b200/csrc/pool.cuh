@@ -50,6 +50,7 @@ __device__ __forceinline__ void pool_len_partials(unsigned long long* __restrict
 __global__ void __launch_bounds__(256)
 k_pool_meta(const DEpoch* __restrict__ epp, LevelSet ls, const int* __restrict__ len0, i64* __restrict__ veh_off, Control* ctl, PoolBufs pb,
             unsigned long long* __restrict__ part, int part_vg) {
+    pdl_enter();
     const DEpoch& ep = *epp;
     const int mode = ep.mode, n_veh = ep.n_veh;
     const bool sba = mode == AMOD_MODE_SBA;
@@ -125,6 +126,7 @@ struct InEntLen {   // scan input over pool entries
 
 template <typename TT>
 __global__ void k_pool_payload(const DEpoch* __restrict__ epp, Table<TT> tt, LevelSet ls, const Control* __restrict__ ctl, PoolBufs pb) {
+    pdl_enter();
     const DEpoch& ep = *epp;
     const i64 n_ent = ctl->overflow ? 0 : ctl->n_ent;
     const i64 stride = (i64)gridDim.x * blockDim.x;

@@ -85,12 +85,14 @@ __device__ __forceinline__ void scan_phase_b(const In& in, int vb, int vg, const
 
 template <typename In>
 __global__ void __launch_bounds__(SCAN_THREADS) k_scan_a(In in, i64* __restrict__ partial) {
+    pdl_enter();
     __shared__ i64 smem[SCAN_THREADS / 32 + 1];
     scan_phase_a(in, blockIdx.x, gridDim.x, partial, smem);
 }
 
 template <typename In, typename Fin>
 __global__ void __launch_bounds__(SCAN_THREADS) k_scan_b(In in, const i64* __restrict__ partial, i64* __restrict__ out, Fin fin) {
+    pdl_enter();
     __shared__ i64 smem[SCAN_THREADS / 32 + 1];
     scan_phase_b(in, blockIdx.x, gridDim.x, partial, out, fin, smem);
 }
@@ -100,6 +102,7 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_scan_b(In in, const i64* __res
 template <typename InA, typename FinA, typename InB, typename FinB>
 __global__ void __launch_bounds__(SCAN_THREADS) k_scan2_b(InA a, FinA fa, i64* __restrict__ outa, InB b, FinB fb, i64* __restrict__ outb,
                                                           const i64* __restrict__ partial) {
+    pdl_enter();
     __shared__ i64 smem[SCAN_THREADS / 32 + 1];
     const int half = gridDim.x >> 1;
     if ((int)blockIdx.x < half) scan_phase_b(a, blockIdx.x, half, partial, outa, fa, smem);

@@ -46,6 +46,33 @@ def merge_sba(parts: list[tuple[Pool, np.ndarray]], n_veh: int, search: np.ndarr
     return cat.take(order)
 
 
+def balanced_placement(cost: np.ndarray, world: int):
+    """Placement of every vehicle on a rank by its expected work (e.g. the size of its share of the previous epochs'
+    pools): longest-processing-time-first bin packing, ties towards the emptier rank.  A rank's vehicles keep their
+    global order (the assembled pool is vehicle-major, dispatch_osp.py:107).  Returns (veh_rank, veh_local, sels) where
+    sels[r] are the global indices of rank r's vehicles in local order."""
+    cost = np.asarray(cost, dtype=np.float64)
+    n = cost.size
+    order = np.argsort(-cost, kind="stable")
+    load = np.zeros(world)
+    count = np.zeros(world, dtype=np.int64)
+    veh_rank = np.zeros(n, dtype=np.int32)
+    cap = (n + world - 1) // world + 1               # a staging slot holds at most this many vehicles
+    for v in order.tolist():
+        open_ranks = np.flatnonzero(count < cap)
+        r = int(open_ranks[np.argmin(load[open_ranks])])
+        veh_rank[v] = r
+        load[r] += cost[v]
+        count[r] += 1
+    veh_local = np.zeros(n, dtype=np.int32)
+    sels = []
+    for r in range(world):
+        sel = np.flatnonzero(veh_rank == r)
+        veh_local[sel] = np.arange(sel.size, dtype=np.int32)
+        sels.append(sel.astype(np.int64))
+    return veh_rank, veh_local, sels
+
+
 def allgather_pool(local: Pool, sel: np.ndarray, n_veh: int, mode_sba: bool = False, device=None, search=None) -> Pool:
     """All-gather the rank-local pools (torch.distributed; NCCL over NVLink when `device` is a
     CUDA device, gloo on CPU) and return the full vehicle-major pool on every rank."""
@@ -141,12 +168,34 @@ class PeerPool:
         self.fused = self.nccl
         dist.barrier()
 
+    def attach(self, root: int = 0, veh_rank=None, veh_local=None):
+        """From now on every builder.build(...) of this rank's slice also assembles: the slice is pushed (to `root` only,
+        or to every rank with root < 0) and the merging ranks build the fleet-wide pool inside the build's own captured
+        graph and single host synchronisation (amod_gpool_attach).  veh_rank / veh_local: placement of every global
+        vehicle (see balanced_placement); None = interleaved."""
+        b = self.b
+        if veh_rank is None:
+            rc = b.lib.amod_gpool_attach(b.h, self.n_veh_total, root, None, None)
+        else:
+            self._vr = np.ascontiguousarray(veh_rank, dtype=np.int32)
+            self._vl = np.ascontiguousarray(veh_local, dtype=np.int32)
+            assert self._vr.size == self.n_veh_total == self._vl.size
+            rc = b.lib.amod_gpool_attach(b.h, self.n_veh_total, root, self._vr.ctypes.data, self._vl.ctypes.data)
+        b._check(rc)
+        self.attached, self.root = True, root
+
+    def detach(self):
+        self.b._check(self.b.lib.amod_gpool_detach(self.b.h))
+        self.attached = False
+
     def assemble(self):
         """Call after builder.build(...) of this rank's slice.  Returns nothing; the pool is in this
-        rank's global pool (view()/fetch())."""
+        rank's global pool (view()/fetch()).  A no-op while attached (the build already assembled)."""
         import torch
         import torch.distributed as dist
         b = self.b
+        if getattr(self, "attached", False):
+            return
         if self.fused:
             b._check(b.lib.amod_gpool_assemble(b.h, self.n_veh_total))
             return

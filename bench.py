@@ -275,18 +275,61 @@ def main():
         b.set_graph(False)
     sba = snaps[0][1].mode == marshal.MODE_SBA
 
-    # per-rank slice of the (tiled) fleet, resident in HBM before the timed region
-    work = []
-    for name, ep, n_evals, n_lookups, extra in snaps:
-        full = tile_fleet(ep, mult)
-        mine, sel = full.shard(rank, world)
-        tens = {f: torch.from_numpy(getattr(mine, f)).to(dev) for f in capi.EPOCH_PTR_FIELDS}
-        w = dict(name=name, host=mine, dev=tens, sel=sel, n_veh_full=full.n_veh, full=full if rank == 0 else None,
-                 digest=digests.get(f"{name}@x{mult}"))
-        if extra:        # cfg5: the NPO match of the same epoch (idle vehicles x pending requests)
-            w["npo_host"] = (np.ascontiguousarray(extra["npo_idle_nid"], dtype=np.int32), np.ascontiguousarray(extra["npo_pend_onid"], dtype=np.int32))
-            w["npo_dev"] = tuple(torch.from_numpy(a).to(dev) for a in w["npo_host"])
-        work.append(w)
+    if sba and world > 1:
+        raise SystemExit("cfg5 (SBA + NPO) runs on one GPU in this bench; the multi-rank SBA merge is host-side (amod_b200/dist.py merge_sba)")
+    fulls = [(name, tile_fleet(ep, mult), extra) for name, ep, _ne, _nl, extra in snaps]
+    n_veh_full = fulls[0][1].n_veh
+    peer = {}
+    placement = {"veh_rank": None, "how": "interleaved (v % N)"}
+
+    def make_work(sels):
+        """per-rank slice of the (tiled) fleet, resident in HBM before the timed region"""
+        work = []
+        for name, full, extra in fulls:
+            mine = full.take(sels[rank]) if sels is not None else full.shard(rank, world)[0]
+            tens = {f: torch.from_numpy(getattr(mine, f)).to(dev) for f in capi.EPOCH_PTR_FIELDS}
+            w = dict(name=name, host=mine, dev=tens, n_veh_full=full.n_veh, digest=digests.get(f"{name}@x{mult}"))
+            if extra:        # cfg5: the NPO match of the same epoch (idle vehicles x pending requests)
+                w["npo_host"] = (np.ascontiguousarray(extra["npo_idle_nid"], dtype=np.int32), np.ascontiguousarray(extra["npo_pend_onid"], dtype=np.int32))
+                w["npo_dev"] = tuple(torch.from_numpy(a).to(dev) for a in w["npo_host"])
+            work.append(w)
+        return work
+
+    work = make_work(None)
+    if world > 1:
+        # Load-balanced placement (SURVEY.md 8e: work per vehicle is heavy-tailed): one untimed pass with the interleaved
+        # placement measures every vehicle's share of the pool (feasible schedules behind its entries); the fleet is then
+        # placed by longest-processing-time-first bin packing on the running mean over the epochs seen so far.
+        from amod_b200 import dist as adist
+        b.build(work[0]["host"])
+        P, NT, NS = b.pool_sizes()
+        peer["pp"] = adist.PeerPool(b, world, rank, n_veh_full, 3 * world * P, 3 * world * NT + 1024, 3 * world * NS + 1024, dev)
+        peer["pp"].attach(root=0)
+        cost = np.zeros(n_veh_full)
+        for w in work:
+            b.build(w["host"])
+            if rank == 0:
+                got = peer["pp"].fetch()
+                cost += np.bincount(got.ent_veh, weights=got.ent_nfeas.astype(np.float64) + 1.0, minlength=n_veh_full)
+            dist.barrier()
+        vr = torch.zeros(n_veh_full, dtype=torch.int32, device=dev)
+        if rank == 0 and not os.environ.get("AMOD_BENCH_INTERLEAVED"):
+            veh_rank, _vl, _sels = adist.balanced_placement(cost, world)
+            vr.copy_(torch.from_numpy(veh_rank))
+        elif rank == 0:
+            vr.copy_(torch.from_numpy((np.arange(n_veh_full) % world).astype(np.int32)))
+        dist.broadcast(vr, src=0)
+        veh_rank = vr.cpu().numpy()
+        veh_local = np.zeros(n_veh_full, dtype=np.int32)
+        sels = []
+        for r in range(world):
+            sel = np.flatnonzero(veh_rank == r)
+            veh_local[sel] = np.arange(sel.size, dtype=np.int32)
+            sels.append(sel.astype(np.int64))
+        work = make_work(sels)
+        peer["pp"].attach(root=0, veh_rank=veh_rank, veh_local=veh_local)
+        if not os.environ.get("AMOD_BENCH_INTERLEAVED"):
+            placement = {"veh_rank": veh_rank, "how": "balanced: LPT bin packing on each vehicle's mean pool share over the epochs seen (untimed pass)"}
 
     class DevEp:
         pass
@@ -298,18 +341,6 @@ def main():
         for f, t in w["dev"].items():
             setattr(d, f, t)
         return d
-
-    peer = {}
-
-    def assemble():
-        """Assemble the fleet-wide pool in the reference's order on the assigner's rank (rank 0) over NVLink peer
-        memory (amod_b200/dist.py PeerPool)."""
-        from amod_b200 import dist as adist
-        if "pp" not in peer:
-            P, NT, NS = b.pool_sizes()
-            peer["pp"] = adist.PeerPool(b, world, rank, work[0]["n_veh_full"], 3 * world * P, 3 * world * NT + 1024,
-                                        3 * world * NS + 1024, dev)
-        peer["pp"].assemble()
 
     ptr_of = lambda t: t.data_ptr()
     npo_out = {}
@@ -327,9 +358,7 @@ def main():
 
     def step_resident(i):
         w = work[i % len(work)]
-        st = b.build(dev_epoch(w), loc=capi.LOC_DEVICE, ptr_of=ptr_of)
-        if world > 1:
-            assemble()
+        st = b.build(dev_epoch(w), loc=capi.LOC_DEVICE, ptr_of=ptr_of)      # (N > 1: the build also assembles, PeerPool.attach)
         if "npo_dev" in w:
             npo_resident(w)
         return st
@@ -430,7 +459,6 @@ def main():
             d2h = sum(getattr(pool, f).nbytes for f, _d, _k in capi.POOL_FIELDS)
         else:
             n_ev = b.build(w["host"])["n_evals"]
-            assemble()
             if rank == 0:
                 pool = peer["pp"].fetch(reuse=True)
                 d2h = sum(getattr(pool, f).nbytes for f, _d, _k in capi.POOL_FIELDS)
@@ -507,8 +535,9 @@ def main():
     fleet = work[0]["n_veh_full"]
     par = f"vehicles interleaved over {world} rank(s)"
     if world > 1:
-        par += (", pool assembled on rank 0 over NVLink peer memory (bulk peer stores + epoch flags, no host collective; "
-                "NCCL only for start-up, barriers and the final timing reduction)")
+        par += (", placement " + placement["how"] + "; pool gathered and merged on rank 0 over NVLink peer memory inside the build's own "
+                "graph (bulk peer stores + epoch flags, one host sync per epoch, no host collective; NCCL only for start-up, "
+                "barriers and the final timing reduction)")
     line = {"metric": METRIC, "value": evals_all / (ms * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": step_ms, "higher_is_better": True, "scaling": scaling,
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
@@ -520,7 +549,7 @@ def main():
                        "graph": not args.no_graph},
             "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": int(e_h2d_all // args.steps), "d2h_bytes_per_step": int(e_d2h_all // args.steps),
                     "ms_per_step": 1e3 * float(t_e.item()) / args.steps,
-                    "path": "amod_osp_build(host pointers) on every rank + " + ("amod_gpool_assemble + amod_gpool_fetch of the assembled pool on rank 0"
+                    "path": "amod_osp_build(host pointers) on every rank + " + ("peer assembly inside the build + amod_gpool_fetch of the assembled pool on rank 0"
                                                                                  if world > 1 else "amod_pool_fetch(host buffers)") + " through ctypes"},
             "gpu_launches": int(launches_all), "clocks": clocks, "roofline": roofline, "parity": parity}
     if sba:

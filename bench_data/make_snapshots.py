@@ -86,8 +86,25 @@ def main():
 
     state = {"epoch": 0}
 
+    sba_advance = os.environ.get("ADVANCE") == "sba"
+    probe = int(os.environ.get("PROBE_STEP", "0"))
+
     def osp(new_rids, reqs, vehs, T, value_func, is_reoptimization=True):
         considered = [r.id for r in reqs if r.status in (OS.PICKING, OS.PENDING)]   # dispatch_osp.py:33-37
+        if sba_advance:
+            # dense configs (cfg4: demand x4): an exhaustive OSP build per epoch takes the CPU oracle many minutes, so the
+            # day advances with the reference's SBA dispatcher (as it does during warm-up, platform.py:160-161) and the
+            # OSP seam inputs of the chosen epochs are recorded without being applied
+            if state["epoch"] in snap_epochs:
+                ep, _objs = marshal.marshal_epoch(reqs, vehs, considered, T, cap, marshal.MODE_OSP)
+                if probe:
+                    t = time.time()
+                    p = oracle.osp_build(ep, tt, n_threads=nthreads, veh_lo=0, veh_step=probe)
+                    print(f"  probe epoch {state['epoch']}: every {probe}th vehicle: {p.stats['n_evals']:,} evals, {p.n_entries} entries, "
+                          f"{p.stats['n_sches_stored']:,} sches in {time.time() - t:.1f}s  (V={ep.n_veh} R={ep.n_search})", flush=True)
+                np.savez_compressed(os.path.join(HERE, f"{tag}_epoch{state['epoch']:04d}.npz"), **ep.to_npz_dict("ep_"),
+                                    n_evals=0, n_lookups=0, n_entries=0)
+            return dispatch(marshal.MODE_SBA, new_rids, reqs, vehs, T, state["epoch"])
         dispatch(marshal.MODE_OSP, considered, reqs, vehs, T, state["epoch"])
 
     def sba(new_rids, reqs, vehs, T, value_func):

@@ -181,6 +181,19 @@ int amod_gpool_scatter(amod_ctx* ctx, const int32_t* counts_all_dev, int32_t veh
  * Requires one GPU per rank (kernels of different ranks wait on each other).  On return this rank's pool is
  * complete; a rank starts pushing the next epoch only after every peer has finished reading the previous one. */
 int amod_gpool_assemble(amod_ctx* ctx, int32_t n_veh_total);
+/* Assembly INSIDE the build: after this call every amod_osp_build on ctx also pushes this rank's slice and, on the
+ * merging ranks, assembles the fleet-wide pool, as part of the same captured graph and under the build's single host
+ * synchronisation (amod_gpool_assemble must not be called while attached).
+ *   root >= 0  gather: only rank `root` (the process that hosts the unchanged assigner) receives the slices and merges;
+ *              a rank sends its slice once and is done.   root < 0: every rank receives and merges (all-gather).
+ *   veh_rank / veh_local [n_veh_total] (host): placement of every global vehicle, e.g. a load-balanced sharding by the
+ *              previous epoch's per-vehicle work; NULL = interleaved (v % world, v / world).  Vehicles of one rank must
+ *              keep their global order.  May be called again at any time to change the placement.
+ * A rank whose attempt overflowed a buffer or must be searched deeper reruns its epoch and only then pushes; the
+ * others wait for it (bounded: AMOD_GP_TIMEOUT_S seconds, default 30; a time-out is AMOD_E_CUDA on the waiting rank and
+ * the global pool must then be rebuilt on every rank). */
+int amod_gpool_attach(amod_ctx* ctx, int32_t n_veh_total, int32_t root, const int32_t* veh_rank, const int32_t* veh_local);
+int amod_gpool_detach(amod_ctx* ctx);
 /* device pointers + sizes of this rank's global pool (valid after the barrier) */
 int amod_gpool_view(amod_ctx* ctx, amod_pool* view);
 /* copy this rank's global pool into caller-owned HOST buffers (AMOD_E_CAPACITY reports the sizes needed) */

@@ -110,3 +110,55 @@ def test_flag_based_assembly_kernels_with_one_rank(tmp_path):
     mp.spawn(_single_rank_worker, args=(1, _free_port(), str(tmp_path)), nprocs=1, join=True)
     ok = int(np.load(tmp_path / "ok.npy")[0])
     assert ok, (tmp_path / "why.txt").read_text() if not ok else ""
+
+
+def _attached_worker(rank, world, port, out_dir):
+    sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "oracle")); sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"; os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    import oracle
+    from amod_b200 import dist as adist, marshal, synth
+    from amod_b200.pool import PoolBuilder
+    torch.cuda.set_device(rank)
+    dev = torch.device("cuda", rank)
+    tt = synth.make_road_graph(900, seed=4).tt
+    b = PoolBuilder(tt, device=rank)
+    ok, why, pp = True, "", None
+    rng = np.random.default_rng(17)
+    for it, seed in enumerate((11, 12, 13, 14)):
+        ep = synth.random_epoch(tt, n_veh=203, n_pending=70, cap=4, mode=marshal.MODE_OSP, seed=seed, wait_sec=300, near=True, T=4000)
+        ref = oracle.osp_build(ep, tt)
+        root = it % world                                    # the gathering rank changes too
+        if it < 2:     # interleaved placement, then an arbitrary load-balanced one
+            veh_rank, veh_local, sels = None, None, [np.arange(r, ep.n_veh, world) for r in range(world)]
+        else:
+            veh_rank, veh_local, sels = adist.balanced_placement(rng.pareto(1.1, size=ep.n_veh) + 1.0, world)
+        sub = ep.take(sels[rank])
+        if pp is None:
+            b.build(sub)
+            pp = adist.PeerPool(b, world, rank, ep.n_veh, 4 * ref.n_entries, 4 * ref.trip_req.size + 64, 4 * ref.sche_code.size + 64, dev)
+        pp.attach(root=root, veh_rank=veh_rank, veh_local=veh_local)
+        for _rep in range(3):                                # graph replay: the assembly kernels are nodes of the epoch graph
+            b.build(sub)
+            if rank == root:
+                o, w = marshal.pools_equal(pp.fetch(), ref, rtol=0.0, check_kind=True)
+                ok &= o
+                why = why or w
+        dist.barrier()
+    np.save(os.path.join(out_dir, f"ok{rank}.npy"), np.array([int(ok)]))
+    if not ok:
+        open(os.path.join(out_dir, f"why{rank}.txt"), "w").write(why)
+    dist.destroy_process_group()
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs: kernels of different ranks wait on each other")
+def test_two_gpus_gather_to_root_inside_the_build_graph(tmp_path):
+    """bench.py's N > 1 path on real peers: PeerPool.attach -> every build pushes its slice to the root over NVLink and the
+    root merges, all inside the captured epoch graph; interleaved and load-balanced placements, both ranks as root."""
+    world = 2
+    mp.spawn(_attached_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
+    for r in range(world):
+        ok = int(np.load(tmp_path / f"ok{r}.npy")[0])
+        why = (tmp_path / f"why{r}.txt").read_text() if not ok else ""
+        assert ok, f"rank {r}: {why}"
