@@ -1074,14 +1074,26 @@ extern "C" int amod_gpool_attach(amod_ctx* ctx, int32_t n_veh_total, int32_t roo
     CK(cudaStreamSynchronize(ctx->stream));
     CK(cudaMemcpy(ctx->gp_place.p, place.data(), 4 * place.size(), cudaMemcpyHostToDevice));
     if (!ctx->gp_attached || ctx->gp_root != root || ctx->gp_n_total != n_veh_total) ctx->buf_gen++;      // the epoch graph changes
+    if (!ctx->gp_attached || ctx->gp_root != root) {
+        // the readers change: the ranks must have met at a host-side barrier since the last assembly; the next push does not
+        // wait for "read" flags of epochs that were read under the previous root / mode
+        GpState* gst = ctx->gp_tot.as<GpState>();
+        CK(cudaMemcpy(&gst->read_base, &gst->epoch, 8, cudaMemcpyDeviceToDevice));
+    }
     ctx->gp_attached = true; ctx->gp_root = root; ctx->gp_n_total = n_veh_total;
     return AMOD_OK;
 }
 
 extern "C" int amod_gpool_detach(amod_ctx* ctx) {
     if (!ctx) return AMOD_E_BADARG;
-    if (ctx->gp_attached) ctx->buf_gen++;
-    ctx->gp_attached = false;
+    if (ctx->gp_attached) {
+        ctx->buf_gen++;
+        GpState* gst = ctx->gp_tot.as<GpState>();
+        CK(cudaSetDevice(ctx->device));
+        CK(cudaStreamSynchronize(ctx->stream));
+        CK(cudaMemcpy(&gst->read_base, &gst->epoch, 8, cudaMemcpyDeviceToDevice));
+    }
+    ctx->gp_attached = false; ctx->gp_root = -1;
     return AMOD_OK;
 }
 

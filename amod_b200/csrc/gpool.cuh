@@ -92,6 +92,7 @@ struct GpState {
     unsigned ticket[2];
     unsigned long long epoch;       // assemblies completed (pushes issued) by this rank
     long long timeout_clk;          // bounded spins give up after this many clock64 ticks
+    unsigned long long read_base;   // epochs up to this one were read under another root / mode: their "read" flags are not waited for
 };
 
 // Wait until the flags `which` of the ranks in `mask` in MY pool have reached `epoch` (bounded spin); call with a whole
@@ -139,7 +140,7 @@ k_gp_push_bulk(GPush P, GPoolLayout L, GSlotLayout S, i64 o_stage, GPoolPeers pe
     const unsigned long long epoch = st->epoch + 1;        // (every block reads it before the last block to finish advances it)
     const int d0 = root < 0 ? 0 : root, d1 = root < 0 ? peers.world : root + 1;
     // the readers of my slot must have finished with the previous epoch before I overwrite it
-    if (epoch > 1) gp_wait_flags(my_base, L, peers.world, 1, epoch - 1, st, root < 0 ? 0xffffffffu : (1u << root));
+    if (epoch - 1 > st->read_base) gp_wait_flags(my_base, L, peers.world, 1, epoch - 1, st, root < 0 ? 0xffffffffu : (1u << root));
     const i64 n_veh = epp->n_veh, n_ent = ctl->n_ent, n_ptr = ctl->n_ptr, n_pst = ctl->n_pst;
     const bool fits = n_veh <= S.cap_veh && n_ent <= S.cap_ent && n_ptr <= S.cap_ptr && n_pst <= S.cap_pst;
     if (!fits && blockIdx.x == 0 && threadIdx.x == 0) atomicOr(&st->err, 1ull);

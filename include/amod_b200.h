@@ -188,7 +188,8 @@ int amod_gpool_assemble(amod_ctx* ctx, int32_t n_veh_total);
  *              a rank sends its slice once and is done.   root < 0: every rank receives and merges (all-gather).
  *   veh_rank / veh_local [n_veh_total] (host): placement of every global vehicle, e.g. a load-balanced sharding by the
  *              previous epoch's per-vehicle work; NULL = interleaved (v % world, v / world).  Vehicles of one rank must
- *              keep their global order.  May be called again at any time to change the placement.
+ *              keep their global order.  May be called again at any time to change the placement; changing `root`
+ *              requires that all ranks have met at a host-side barrier since their last build.
  * A rank whose attempt overflowed a buffer or must be searched deeper reruns its epoch and only then pushes; the
  * others wait for it (bounded: AMOD_GP_TIMEOUT_S seconds, default 30; a time-out is AMOD_E_CUDA on the waiting rank and
  * the global pool must then be rebuilt on every rank). */
