@@ -49,6 +49,11 @@ POOL_FIELDS = (("ent_veh", np.int32, "e"), ("ent_kind", np.int32, "e"), ("ent_tr
                ("ent_nfeas", np.int32, "e"), ("trip_req", np.int32, "t"), ("sche_code", np.int32, "s"))
 
 
+class AmodRoutes(C.Structure):
+    _fields_ = [("cap_steps", C.c_int64), ("n_steps", C.c_int64), ("leg_off", C.c_void_p), ("step_u", C.c_void_p),
+                ("step_v", C.c_void_p), ("step_t", C.c_void_p), ("step_d", C.c_void_p), ("leg_t", C.c_void_p), ("leg_d", C.c_void_p)]
+
+
 class AmodStats(C.Structure):
     _fields_ = [("n_screens", C.c_int64), ("n_evals", C.c_int64), ("n_lookups", C.c_int64),
                 ("n_entries", C.c_int64), ("n_sches_stored", C.c_int64), ("n_tasks", C.c_int64),
@@ -79,7 +84,7 @@ EXPORTS = ("amod_create", "amod_destroy", "amod_last_error", "amod_version", "am
            "amod_pool_view", "amod_npo_match",
            "amod_gather_bench", "amod_gpool_create", "amod_gpool_open_peers", "amod_pool_veh_counts", "amod_gpool_scatter",
            "amod_gpool_view", "amod_gpool_fetch", "amod_set_graph", "amod_gpool_assemble", "amod_greedy_assign",
-           "amod_gpool_attach", "amod_gpool_detach")
+           "amod_gpool_attach", "amod_gpool_detach", "amod_routes_upload", "amod_routes_build")
 
 _lib = None
 
@@ -142,6 +147,10 @@ def load_library(path: str | None = None) -> C.CDLL:
     lib.amod_gpool_attach.restype = C.c_int
     lib.amod_gpool_detach.argtypes = [C.c_void_p]
     lib.amod_gpool_detach.restype = C.c_int
+    lib.amod_routes_upload.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.amod_routes_upload.restype = C.c_int
+    lib.amod_routes_build.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int, C.POINTER(AmodRoutes)]
+    lib.amod_routes_build.restype = C.c_int
     lib.amod_set_graph.argtypes = [C.c_void_p, C.c_int]
     lib.amod_set_graph.restype = C.c_int
     if path is None:

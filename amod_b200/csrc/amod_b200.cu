@@ -17,6 +17,7 @@
 #include "npo.cuh"
 #include "place.cuh"
 #include "pool.cuh"
+#include "routes.cuh"
 #include "scan.cuh"
 
 #ifndef GRID_ELEM_PER_SM
@@ -112,6 +113,9 @@ struct amod_ctx {
     DevBuf ga_pos, ga_rank, ga_order, ga_state, ga_bv, ga_br, ga_tv, ga_tr, ga_sel, ga_cnt;
     // npo
     DevBuf npo_in, npo_vm, npo_rm, npo_rb, npo_vb, npo_rdt, npo_mdt, npo_cnt;
+    // routes (8f-2)
+    int* d_pred = nullptr; void* d_dist = nullptr;
+    DevBuf rt_in, rt_len, rt_off, rt_u, rt_v, rt_t, rt_d, rt_lt, rt_ld, rt_err;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     std::vector<cudaEvent_t> ev_pool;
     cudaStream_t side = nullptr;             // second branch of the epoch graph (next level's candidates)
@@ -226,7 +230,11 @@ static void apply_l2_policy_to_graph(amod_ctx* ctx, cudaGraph_t graph) {
 }
 
 // ------------------------------------------------------------------------------------------------
-extern "C" const char* amod_version(void) { return "amod_b200 0.1 (sm_100a)"; }
+#ifdef AMOD_BOUNDS
+extern "C" const char* amod_version(void) { return "amod_b200 0.2 (sm_100a, AMOD_BOUNDS debug build)"; }
+#else
+extern "C" const char* amod_version(void) { return "amod_b200 0.2 (sm_100a)"; }
+#endif
 
 extern "C" const char* amod_last_error(amod_ctx* ctx) { return ctx ? ctx->err.c_str() : g_err.c_str(); }
 
@@ -299,6 +307,10 @@ extern "C" void amod_destroy(amod_ctx* ctx) {
     for (auto& g : ctx->graphs) if (g.exec) cudaGraphExecDestroy(g.exec);
     if (ctx->ep_pinned) cudaFreeHost(ctx->ep_pinned);
     if (ctx->d_tt) cudaFree(ctx->d_tt);
+    if (ctx->d_pred) cudaFree(ctx->d_pred);
+    if (ctx->d_dist) cudaFree(ctx->d_dist);
+    { DevBuf* rb[] = {&ctx->rt_in, &ctx->rt_len, &ctx->rt_off, &ctx->rt_u, &ctx->rt_v, &ctx->rt_t, &ctx->rt_d, &ctx->rt_lt, &ctx->rt_ld, &ctx->rt_err};
+      for (DevBuf* b : rb) b->release(); }
     for (auto e : ctx->ev_pool) cudaEventDestroy(e);
     for (auto e : ctx->sync_pool) cudaEventDestroy(e);
     if (ctx->side) cudaStreamDestroy(ctx->side);
@@ -726,6 +738,17 @@ static int build_impl(amod_ctx* ctx, const amod_epoch* ep, int loc, amod_stats* 
         if (with_gp) CK(cudaMemcpyAsync(ctx->gp_h_state, ctx->gp_tot.p, sizeof(GpState), cudaMemcpyDeviceToHost, st));
         CK(cudaStreamSynchronize(st));
         CK(cudaGetLastError());
+#ifdef AMOD_BOUNDS
+        {   // debug build: a guarded store was out of range (common.cuh BOK): file tag * 100000 + line
+            unsigned long long hit = 0;
+            CK(cudaMemcpyFromSymbol(&hit, g_bounds_hit, sizeof hit));
+            if (hit) {
+                unsigned long long zero = 0;
+                cudaMemcpyToSymbol(g_bounds_hit, &zero, sizeof zero);
+                return ctx->fail(AMOD_E_CUDA, "AMOD_BOUNDS: guarded store out of range at site %llu (file tag * 100000 + line)", hit);
+            }
+        }
+#endif
         if (!h->overflow) {
             if (run_levels < max_level && h->n_trips[run_levels] > 0) { run_levels = std::min(max_level, run_levels + 2); continue; }
             break;
@@ -1287,6 +1310,78 @@ extern "C" int amod_npo_match(amod_ctx* ctx, const int32_t* idle_nid, int32_t n_
     return dispatch_tt(ctx, [&](auto tt) {
         return npo_impl(ctx, idle_nid, n_idle, pend_onid, n_pend, loc, out_idle_idx, out_pend_idx, out_dt, n_out, n_rounds, tt);
     });
+}
+
+// ------------------------------------------------------------------------------------------------
+// batched route construction
+// ------------------------------------------------------------------------------------------------
+extern "C" int amod_routes_upload(amod_ctx* ctx, const int32_t* path_table_host, const void* dist_table_host) {
+    if (!ctx || !path_table_host || !dist_table_host) return AMOD_E_BADARG;
+    CK(cudaSetDevice(ctx->device));
+    const size_t n2 = (size_t)ctx->n_nodes * ctx->n_nodes;
+    const size_t el = ctx->tt_dtype == AMOD_TT_F64 ? 8 : 4;
+    if (!ctx->d_pred) CK(cudaMalloc((void**)&ctx->d_pred, 4 * n2));
+    if (!ctx->d_dist) CK(cudaMalloc(&ctx->d_dist, el * n2));
+    CK(cudaMemcpy(ctx->d_pred, path_table_host, 4 * n2, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(ctx->d_dist, dist_table_host, el * n2, cudaMemcpyHostToDevice));
+    return AMOD_OK;
+}
+
+template <typename TT>
+static int routes_impl(amod_ctx* ctx, const int32_t* leg_o, const int32_t* leg_d, int n_legs, int loc, amod_routes* out, Table<TT> tt) {
+    cudaStream_t st = ctx->stream;
+    CK(cudaSetDevice(ctx->device));
+    out->n_steps = 0;
+    if (n_legs == 0) return AMOD_OK;
+    const size_t L = (size_t)n_legs;
+    const int* d_o = leg_o; const int* d_d = leg_d;
+    if (loc != AMOD_LOC_DEVICE) {
+        CK(ctx->rt_in.ensure(8 * L));
+        CK(cudaMemcpyAsync(ctx->rt_in.p, leg_o, 4 * L, cudaMemcpyHostToDevice, st));
+        CK(cudaMemcpyAsync(ctx->rt_in.as<int>() + L, leg_d, 4 * L, cudaMemcpyHostToDevice, st));
+        d_o = ctx->rt_in.as<int>(); d_d = ctx->rt_in.as<int>() + L;
+    }
+    CK(ctx->rt_len.ensure(4 * L)); CK(ctx->rt_off.ensure(8 * (L + 2))); CK(ctx->rt_lt.ensure(8 * L)); CK(ctx->rt_ld.ensure(8 * L));
+    CK(ctx->rt_err.ensure(16)); CK(ctx->partial.ensure(2 * 8 * (size_t)(ctx->n_sm + 1)));
+    CK(cudaMemsetAsync(ctx->rt_err.p, 0, 16, st));
+    RouteTables rt; rt.pred = ctx->d_pred; rt.dist = ctx->d_dist; rt.n = ctx->n_nodes;
+    unsigned long long* err = ctx->rt_err.as<unsigned long long>();
+    i64* tot = (i64*)(err + 1);
+    k_route_count<<<ctx->n_sm * 4, 256, 0, st>>>(rt, d_o, d_d, n_legs, ctx->rt_len.as<int>(), err);
+    scan_dev(ctx, InLegLen{ctx->rt_len.as<int>(), (i64)n_legs}, ctx->rt_off.as<i64>(), FinStoreI64{tot});
+    unsigned long long h[2];
+    CK(cudaMemcpyAsync(h, err, 16, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    if (h[0]) return ctx->fail(AMOD_E_BADARG, "a leg's node is out of range or the path table does not lead back to its origin");
+    const i64 n_steps = (i64)h[1];
+    out->n_steps = n_steps;
+    if (out->cap_steps < n_steps) return ctx->fail(AMOD_E_CAPACITY, "step buffers too small: need %lld steps", (long long)n_steps);
+    const size_t S = (size_t)n_steps;
+    const bool dev = loc == AMOD_LOC_DEVICE;
+    int* su = out->step_u; int* sv = out->step_v; double* stt = out->step_t; double* sdd = out->step_d;
+    double* lt = out->leg_t; double* ld = out->leg_d; i64* lo = (i64*)out->leg_off;
+    if (!dev) {
+        CK(ctx->rt_u.ensure(4 * S)); CK(ctx->rt_v.ensure(4 * S)); CK(ctx->rt_t.ensure(8 * S)); CK(ctx->rt_d.ensure(8 * S));
+        su = ctx->rt_u.as<int>(); sv = ctx->rt_v.as<int>(); stt = ctx->rt_t.as<double>(); sdd = ctx->rt_d.as<double>();
+        lt = ctx->rt_lt.as<double>(); ld = ctx->rt_ld.as<double>();
+    }
+    k_route_fill<TT><<<ctx->n_sm * 8, 256, 0, st>>>(rt, tt, d_o, d_d, n_legs, ctx->rt_off.as<i64>(), n_steps, su, sv, stt, sdd, lt, ld);
+    const cudaMemcpyKind kind = dev ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost;
+    CK(cudaMemcpyAsync(lo, ctx->rt_off.p, 8 * (L + 1), kind, st));
+    if (!dev) {
+        CK(cudaMemcpyAsync(out->step_u, su, 4 * S, kind, st)); CK(cudaMemcpyAsync(out->step_v, sv, 4 * S, kind, st));
+        CK(cudaMemcpyAsync(out->step_t, stt, 8 * S, kind, st)); CK(cudaMemcpyAsync(out->step_d, sdd, 8 * S, kind, st));
+        CK(cudaMemcpyAsync(out->leg_t, lt, 8 * L, kind, st)); CK(cudaMemcpyAsync(out->leg_d, ld, 8 * L, kind, st));
+    }
+    CK(cudaStreamSynchronize(st));
+    CK(cudaGetLastError());
+    return AMOD_OK;
+}
+
+extern "C" int amod_routes_build(amod_ctx* ctx, const int32_t* leg_o, const int32_t* leg_d, int32_t n_legs, int loc, amod_routes* out) {
+    if (!ctx || !out || n_legs < 0 || (n_legs && (!leg_o || !leg_d))) return AMOD_E_BADARG;
+    if (!ctx->d_pred) return ctx->fail(AMOD_E_BADARG, "amod_routes_upload first");
+    return dispatch_tt(ctx, [&](auto tt) { return routes_impl(ctx, leg_o, leg_d, n_legs, loc, out, tt); });
 }
 
 extern "C" int amod_gather_bench(amod_ctx* ctx, const int32_t* o_dev, const int32_t* d_dev, float* out_dev, int64_t n, int iters,

@@ -116,6 +116,21 @@ __device__ __forceinline__ void pdl_enter() {
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 }
 
+// -DAMOD_BOUNDS (debug build, libamod_b200_bounds.so): every store into a level, pool, task or record buffer is guarded by
+// BOK(index < capacity); a violated guard skips the store and records where (file tag * 100000 + line), and the host turns
+// that into an error after the epoch.  compute-sanitizer is closed on this GPU pool, so this build is what the GPU tests
+// run the golden families under.  In the release build BOK(x) is `true` and costs nothing.
+#ifdef AMOD_BOUNDS
+__device__ unsigned long long g_bounds_hit;
+__device__ __forceinline__ bool bounds_ok(bool ok, int where) {
+    if (!ok) atomicCAS(&g_bounds_hit, 0ull, (unsigned long long)where);
+    return ok;
+}
+#define BOK(cond) bounds_ok((cond), BFILE * 100000 + __LINE__)
+#else
+#define BOK(cond) true
+#endif
+
 __device__ __forceinline__ int pod_of(int code) { return code < 0 ? 0 : ((code & 1) ? -1 : 1); }
 
 __device__ __forceinline__ void stop_info(const DEpoch& ep, int v, int code, int& node, double& ddl, int& pod) {

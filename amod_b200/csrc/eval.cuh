@@ -16,6 +16,8 @@
 // record's position in the reference's encounter order; place.cuh then stores cost and schedule there.  The
 // search itself is never repeated.
 #pragma once
+#undef BFILE
+#define BFILE 1
 #include "common.cuh"
 #include "scan.cuh"
 
@@ -83,7 +85,7 @@ __device__ __forceinline__ void walk_j(const TT* __restrict__ lg, double PD, con
         if (ok) {
             o.lookups += l + 2;
             const int slot = atomicAdd(out.cursor, 1);
-            if (slot < out.cap) {
+            if (slot < out.cap && BOK(slot >= 0)) {
                 Tuple t; t.cost = C; t.c = out.c; t.info = out.tag | ((unsigned)o.n << 6) | ((unsigned)j << 12);
                 out.region[slot] = t;
             }

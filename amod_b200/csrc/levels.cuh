@@ -3,6 +3,8 @@
 // next trip level, list-order classification (scheduling.py:31-36) and candidate generation for
 // trips of size k>=2 (:167-216).  All sizes come from the device-resident Control block.
 #pragma once
+#undef BFILE
+#define BFILE 3
 #include "common.cuh"
 #include "eval.cuh"
 #include "scan.cuh"
@@ -56,7 +58,7 @@ k_basic(const DEpoch* __restrict__ epp, Table<TT> tt, Level lv0, int* __restrict
     const i64 row0 = MODE == 1 ? s0pos[v] : 0;
     if (MODE == 1 && lane == 0) {
         Stop* out = lv0.sch + row0 * lv0.stride;
-        for (int m = 0; m < L; m++) out[m] = make_stop(ep, v, base[m]);
+        for (int m = 0; m < L; m++) if (BOK(row0 < lv0.cap_sch && m < lv0.stride)) out[m] = make_stop(ep, v, base[m]);
         lv0.trip_veh[v] = v; lv0.nfeas[v] = S0[v]; lv0.s0[v] = row0; lv0.veh_start[v] = v;
         if (v == 0) lv0.veh_start[ep.n_veh] = ep.n_veh;
     }
@@ -98,7 +100,7 @@ k_basic(const DEpoch* __restrict__ epp, Table<TT> tt, Level lv0, int* __restrict
             if (MODE == 1 && ok) {
                 const int r = count + __popc(bal & ((1u << lane) - 1u));
                 Stop* dst = lv0.sch + (row0 + r) * lv0.stride;       // itertools order = list order (dispatch_osp.py:315-320)
-                for (int m = 0; m < L; m++) dst[m] = make_stop(ep, v, base[pos[m]]);
+                for (int m = 0; m < L; m++) if (BOK(row0 + r < lv0.cap_sch && m < lv0.stride)) dst[m] = make_stop(ep, v, base[pos[m]]);
             }
             count += __popc(bal);
         }
@@ -375,6 +377,7 @@ k_screen_fill(const DEpoch* __restrict__ epp, const Control* __restrict__ ctl, c
                 const int mn = w * 32 + __ffs(word) - 1;
                 const int v = sba ? mn : mj;
                 const int S = sba ? S0[v] : S_major;
+                if (!BOK(t < ctl->n_tasks[0] && r + S <= ctl->n_rows[0])) { t++; r += S; continue; }
                 task_veh[t] = v; task_base[t] = v; task_q[t] = ep.search[sba ? mj : mn];
                 task_S[t] = S; task_row0[t] = r;
                 t++; r += S;
@@ -521,6 +524,7 @@ __global__ void k_compact_trips(const Control* __restrict__ ctl, int which, cons
         nsch += (unsigned long long)nf;
         const i64 tp = trip_pos[t];
         const int o = (int)PACK_LO(tp);
+        if (!BOK(o >= 0 && o < cur.cap_trips && PACK_HI(tp) + nf <= cur.cap_sch)) continue;
         cur.trip_veh[o] = task_veh[t];
         cur.nfeas[o] = nf;
         cur.s0[o] = PACK_HI(tp);            // rows are task-major: the trip's first schedule follows those of all earlier tasks
@@ -570,6 +574,7 @@ k_classify(Control* __restrict__ ctl, Level cur, int heavy_min, int* __restrict_
             const unsigned br = __ballot_sync(FULL, isrec), bn = __ballot_sync(FULL, in && !isrec);
             const unsigned lt = (1u << lane) - 1u;
             const int nrec1 = __popc(br);
+            if (!BOK(s0 + nf <= cur.cap_sch)) continue;
             if (isrec) fin[lane] = r0 + nrec1 - 1 - __popc(br & lt);
             else if (in) fin[lane] = r0 + nrec1 + __popc(bn & lt);
             const double best = warp_min(c);
@@ -821,9 +826,11 @@ k_gen_emit(Control* __restrict__ ctl, int which_next, Level l1, Level prev, Trip
                     int rank = lane;
                     if (k > 1) { rank = 0; for (int y = 0; y < cnt; y++) rank += cc[y].x < me.x; }
                     const i64 w = off + rank;
-                    o.task_veh[w] = v; o.task_base[w] = t; o.task_q[w] = me.y;
-                    o.task_row0[w] = rbase + (i64)rank * S;
-                    o.task_nfeas[w] = 0;
+                    if (BOK(w >= 0 && w < o.cap_tasks && rank < cnt)) {
+                        o.task_veh[w] = v; o.task_base[w] = t; o.task_q[w] = me.y;
+                        o.task_row0[w] = rbase + (i64)rank * S;
+                        o.task_nfeas[w] = 0;
+                    }
                 }
             } else {
                 gen_row<1>(l1, prev, th, t, lane, off, o.tmp_j, o.tmp_q, s_j[wib], nullptr);
@@ -836,9 +843,11 @@ k_gen_emit(Control* __restrict__ ctl, int which_next, Level l1, Level prev, Trip
                         for (int y = 0; y < cnt; y++) rank += o.tmp_j[off + y] < j;
                     }
                     const i64 w = off + rank;
-                    o.task_veh[w] = v; o.task_base[w] = t; o.task_q[w] = o.tmp_q[off + e];
-                    o.task_row0[w] = rbase + (i64)rank * S;
-                    o.task_nfeas[w] = 0;
+                    if (BOK(w >= 0 && w < o.cap_tasks && rank < cnt)) {
+                        o.task_veh[w] = v; o.task_base[w] = t; o.task_q[w] = o.tmp_q[off + e];
+                        o.task_row0[w] = rbase + (i64)rank * S;
+                        o.task_nfeas[w] = 0;
+                    }
                 }
             }
             __syncwarp();
@@ -848,7 +857,7 @@ k_gen_emit(Control* __restrict__ ctl, int which_next, Level l1, Level prev, Trip
                 const int e = (int)(idx / S), xs = (int)(idx - (i64)e * S);
                 RowDesc d;
                 d.v = v; d.q = o.task_q[off + e]; d.s = xs; d.l = l; d.s0 = s0; d.task = (int)(off + e); d.pad = 0;
-                o.rows[rbase + idx] = d;
+                if (BOK(rbase + idx < o.cap_rows)) o.rows[rbase + idx] = d;
             }
             if (lane == 0) { n_tasks += (unsigned long long)cnt; n_items += (unsigned long long)n_rows * (unsigned long long)(l + 1); }
         }

@@ -11,6 +11,8 @@
 //                  into its final row: 16 B stops (code, node, deadline), eight lanes per schedule
 // Nothing here looks a travel time up: the search is not repeated.
 #pragma once
+#undef BFILE
+#define BFILE 2
 #include "common.cuh"
 #include "eval.cuh"
 
@@ -43,7 +45,7 @@ k_place_cost(const Control* __restrict__ ctl, const Tuple* __restrict__ tup, con
     for (int s = threadIdx.x; s < n; s += PLACE_THREADS) {
         const Tuple t = tup[base + s];
         const i64 pos = chunk_pos[t.c] + lanes_before(lane_cnt, t.c, TUP_LANE(t.info)) + TUP_ORD(t.info);
-        cur.sch_cost[pos] = t.cost;
+        if (BOK(pos >= 0 && pos < cur.cap_sch)) cur.sch_cost[pos] = t.cost;
         tup_pos[base + s] = (unsigned)pos;
     }
 }
@@ -70,7 +72,7 @@ k_place_rows(const DEpoch* __restrict__ epp, const Control* __restrict__ ctl, co
             if (w == i) { o.code = 2 * q; o.node = ep.onid[q]; o.ddl = ep.clp[q]; }
             else if (w == j) { o.code = 2 * q + 1; o.node = ep.dnid[q]; o.ddl = ep.cld[q]; }
             else o = src[w - (w > i ? 1 : 0) - (w > j ? 1 : 0)];
-            dst[w] = o;
+            if (BOK(w < cur.stride && cur.final[tup_pos[base + s]] >= 0 && (i64)cur.final[tup_pos[base + s]] < cur.cap_sch)) dst[w] = o;
         }
     }
 }

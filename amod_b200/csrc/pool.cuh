@@ -4,6 +4,8 @@
 //   SBA  (dispatch_sba.py:56-69):   feasible (request, vehicle) pairs request-major, then one
 //                                   empty pair per vehicle
 #pragma once
+#undef BFILE
+#define BFILE 4
 #include "common.cuh"
 #include "scan.cuh"
 
@@ -109,9 +111,12 @@ k_pool_meta(const DEpoch* __restrict__ epp, LevelSet ls, const int* __restrict__
                     for (int kk = 1; kk < k; kk++) e += ls.lv[kk].veh_start[v + 1] - ls.lv[kk].veh_start[v];
                 }
                 slen = len0[v] + 2 * k;
+                if (!BOK(e >= 0 && e < pb.cap_ent)) { e = 0; slen = 0; }
+                else {
                 pb.ent_veh[e] = v; pb.ent_kind[e] = sba ? AMOD_KIND_SBA_PAIR : AMOD_KIND_TRIP;
                 pb.ent_nfeas[e] = lv.nfeas[t]; pb.ent_tlen[e] = k; pb.ent_slen[e] = slen;
                 pb.ent_src[e] = k; pb.ent_trip[e] = t;
+                }
             }
             pool_len_partials(part, part_vg, seg, valid, e, k, slen, lane);
         }
@@ -135,6 +140,7 @@ __global__ void k_pool_payload(const DEpoch* __restrict__ epp, Table<TT> tt, Lev
         const int slen = (int)(pb.sche_off[e + 1] - pb.sche_off[e]);
         int* sc = pb.sche_code + pb.sche_off[e];
         int* tr = pb.trip_req + pb.trip_off[e];
+        if (!BOK(e < pb.cap_ent && pb.sche_off[e + 1] <= pb.cap_pst && pb.trip_off[e + 1] <= pb.cap_ptr && pb.sche_off[e] >= 0 && pb.trip_off[e] >= 0)) continue;
         if (src == SRC_INPUT) {
             const int* in = ep.sche_code + ep.veh_sche_off[v];
             int w = 0;

@@ -477,6 +477,15 @@ class LazyPoolRecords:
         self.user_sorted = True
 
 
+def pool_of_vehicles(pool: Pool, step: int, lo: int = 0) -> Pool:
+    """The entries of vehicles lo, lo+step, ... in pool order (vehicles are independent, dispatch_osp.py:107-111, so a
+    vehicle sample of the pool can be checked against the oracle's build of just those vehicles)."""
+    if step <= 1 and lo == 0:
+        return pool
+    v = pool.ent_veh.astype(np.int64)
+    return pool.take(np.flatnonzero((v >= lo) & ((v - lo) % step == 0)))
+
+
 def pool_digest(pool: Pool) -> str:
     """Order-sensitive fingerprint of a pool: entry count, vehicle / kind / CSR offsets / trip requests / stop
     codes, and the float64 BITS of costs and delays.  Two pools share a digest iff they are bit-identical in

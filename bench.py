@@ -199,7 +199,8 @@ def run_reference(args):
     t = time.perf_counter()
     p = _oracle_build(oracle, eps[0], tt, n_threads=threads, veh_step=64)
     rate = max(p.stats["n_evals"], 1) / max(time.perf_counter() - t, 1e-6)
-    n_evals = snaps[0][2] * mult
+    dg0 = load_digests().get(f"{snaps[0][0]}@x{mult}", {})
+    n_evals = dg0.get("n_evals", 0) * dg0.get("sample_step", 1) or snaps[0][2] * mult
     per_step_budget = max(2.0, min(20.0, 150.0 / max(args.steps + args.warmup, 1)))
     step = 1 if sba else int(max(1, min(64 * mult, np.ceil(n_evals / (rate * per_step_budget)))))
     evals, t_total = 0, 0.0
@@ -390,7 +391,11 @@ def main():
                 parity["checked"] = False
                 parity.setdefault("missing", []).append(f"{w['name']}@x{mult}")
             else:
-                ok = marshal.pool_digest(got) == dg["digest"] and got.n_entries == dg["n_entries"] and int(ne.item()) == dg["n_evals"]
+                step = int(dg.get("sample_step", 1))         # cfg4: the oracle built every step-th vehicle's part of the pool
+                sub = marshal.pool_of_vehicles(got, step)
+                ok = marshal.pool_digest(sub) == dg["digest"] and sub.n_entries == dg["n_entries"] and (step > 1 or int(ne.item()) == dg["n_evals"])
+                if step > 1:
+                    parity["vehicle_sample"] = f"every {step}th vehicle of the fleet ({dg.get('n_veh', 0) // step} vehicles, {dg['n_entries']} pool entries)"
                 if "npo_host" in w and "npo_digest" in dg:
                     oi, op, od = b.npo_match(*w["npo_host"])
                     ok = ok and npo_digest(oi, op, od) == dg["npo_digest"]

@@ -26,7 +26,11 @@ sys.path.insert(0, os.path.join(ROOT, "oracle"))
 from amod_b200 import marshal, synth  # noqa: E402
 import oracle  # noqa: E402
 
-TILES = {"cfg2": (1, 2, 4, 8), "cfg3": (1, 2, 4, 8), "cfg4": (1,), "cfg5": (1,)}
+TILES = {"cfg2": (1, 2, 4, 8, 16), "cfg3": (1, 2, 4, 8), "cfg4": (1,), "cfg5": (1,)}
+# cfg4 (8,000 vehicles, demand x4) is ~3.5 G schedule evaluations per epoch: hours for the CPU oracle.  Parity is stated on a
+# vehicle SAMPLE (vehicles are independent, dispatch_osp.py:107-111): the oracle builds every 80th vehicle's part of the pool
+# and bench.py fingerprints the same vehicles' entries of the GPU pool (marshal.pool_of_vehicles).
+SAMPLE = {"cfg4": 80}
 
 
 def npo_digest(oi, op, od) -> str:
@@ -38,24 +42,41 @@ def npo_digest(oi, op, od) -> str:
 
 def main():
     tt = synth.make_road_graph(seed=0).tt
+    only = set(sys.argv[1:])
+    try:
+        previous = json.load(open(os.path.join(HERE, "digests.json")))
+    except Exception:
+        previous = {}
     out = {}
     nth = oracle.max_threads()
     for f in sorted(glob.glob(os.path.join(HERE, "*_epoch*.npz"))):
         name = os.path.basename(f)
         tag = name.split("_")[0]
+        if tag not in TILES:
+            continue
+        if only and tag not in only:
+            out.update({k: v for k, v in previous.items() if k.startswith(name)})
+            continue
         z = np.load(f)
         ep = marshal.Epoch.from_npz_dict(z, "ep_")
         for n in TILES.get(tag, (1,)):
             full = synth.tile_fleet(ep, n)
-            build = oracle.sba_build if full.mode == marshal.MODE_SBA else oracle.osp_build
-            pool = build(full, tt, n_threads=nth)
+            step = SAMPLE.get(tag, 1)
+            if full.mode == marshal.MODE_SBA:
+                pool = oracle.sba_build(full, tt, n_threads=nth)
+            else:
+                pool = oracle.osp_build(full, tt, n_threads=nth, veh_lo=0, veh_step=step)
             assert pool.error == 0
-            rec = {"digest": marshal.pool_digest(pool), "n_entries": int(pool.n_entries), "n_evals": int(pool.stats["n_evals"]),
+            rec = {"digest": marshal.pool_digest(pool), "sample_step": step, "n_entries": int(pool.n_entries), "n_evals": int(pool.stats["n_evals"]),
                    "n_lookups": int(pool.stats["n_lookups"]), "n_veh": int(full.n_veh), "n_search": int(full.n_search)}
             if "npo_idle_nid" in z.files and n == 1:
                 oi, op, od = oracle.npo_match(tt, z["npo_idle_nid"], z["npo_pend_onid"])
                 rec["npo_digest"] = npo_digest(oi, op, od)
                 rec["npo_matches"] = int(oi.size)
+                # the named peak size (BASELINE.json configs[4]): EVERY vehicle's node as an idle vehicle x the 5,000 origins = 10^8 pairs
+                oi, op, od = oracle.npo_match(tt, ep.veh_nid, z["npo_pend_onid"])
+                rec["npo_full_digest"] = npo_digest(oi, op, od)
+                rec["npo_full_pairs"] = int(ep.n_veh) * int(z["npo_pend_onid"].size)
             out[f"{name}@x{n}"] = rec
             print(name, n, rec, flush=True)
     json.dump(out, open(os.path.join(HERE, "digests.json"), "w"), indent=1, sort_keys=True)

@@ -108,6 +108,11 @@ def main():
         dispatch(marshal.MODE_OSP, considered, reqs, vehs, T, state["epoch"])
 
     def sba(new_rids, reqs, vehs, T, value_func):
+        if sba_advance and state["epoch"] in snap_epochs:       # warm-up epochs of a dense run: the fleet in mixed states (cfg5's source)
+            considered = [r.id for r in reqs if r.status in (OS.PICKING, OS.PENDING)]
+            ep, _objs = marshal.marshal_epoch(reqs, vehs, considered, T, cap, marshal.MODE_OSP)
+            np.savez_compressed(os.path.join(HERE, f"{tag}_epoch{state['epoch']:04d}.npz"), **ep.to_npz_dict("ep_"),
+                                n_evals=0, n_lookups=0, n_entries=0)
         dispatch(marshal.MODE_SBA, new_rids, reqs, vehs, T, state["epoch"])
 
     ref.platform.assign_orders_through_osp = osp

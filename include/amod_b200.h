@@ -213,6 +213,29 @@ int amod_npo_match(amod_ctx* ctx, const int32_t* idle_nid, int32_t n_idle, const
                    int32_t n_pend, int loc, int32_t* out_idle_idx, int32_t* out_pend_idx, double* out_dt,
                    int32_t* n_out, int32_t* n_rounds);
 
+/* ---- batched route construction ------------------------------------------------------------------
+ * route_functions.build_route_from_origin_to_dest (route_functions.py:36-70) for a batch of legs, e.g. all legs of the
+ * schedules selected in one epoch (scheduling.py:110-119 -> vehicle.py:231-302 add_leg).
+ * amod_routes_upload: shortest_path_table (int32 [n*n], P[o-1][d-1] = 1-based predecessor of d on the best path from o,
+ * <= 0 at d == o; route_functions.py:38-43) and travel_distance_table (same element type as the travel-time table).
+ * amod_routes_build: leg g goes from leg_o[g] to leg_d[g].  Its steps are rows [leg_off[g], leg_off[g+1]) of the step
+ * arrays: (t, d, [u, v]) per consecutive node pair of the path, then the closing (0, 0, [tnid, tnid]) step (:59-61).
+ * leg_t / leg_d are the reference's left-to-right float64 sums (:56-57).  Buffers are caller-owned (host or device);
+ * AMOD_E_CAPACITY reports the n_steps needed. */
+typedef struct amod_routes {
+    int64_t cap_steps;       /* in: capacity of the step arrays */
+    int64_t n_steps;         /* out */
+    int64_t* leg_off;        /* [n_legs+1] */
+    int32_t* step_u;         /* [n_steps] */
+    int32_t* step_v;
+    double*  step_t;
+    double*  step_d;
+    double*  leg_t;          /* [n_legs] */
+    double*  leg_d;
+} amod_routes;
+int amod_routes_upload(amod_ctx* ctx, const int32_t* path_table_host, const void* dist_table_host);
+int amod_routes_build(amod_ctx* ctx, const int32_t* leg_o, const int32_t* leg_d, int32_t n_legs, int loc, amod_routes* out);
+
 /* Raw travel-time gather out[i] = tt[o[i]][d[i]] (route_functions.py:22-25): used by the
  * L2-gather roofline microbenchmark.  Device pointers.  Returns device ms in *ms. */
 int amod_gather_bench(amod_ctx* ctx, const int32_t* o_dev, const int32_t* d_dev, float* out_dev,

@@ -584,3 +584,30 @@ int oracle_greedy_assign(const amod_pool* p, const double* score, int n_veh, int
     free(k); free(vu); free(ru);
     return m;
 }
+
+/* ---- route_functions.build_route_from_origin_to_dest (route_functions.py:36-70), restated -----------
+ * Steps of the best path o -> d: (t, d, [u, v]) per consecutive node pair of the path recovered by walking the
+ * predecessor table back from d (:38-43), then the closing (0, 0, [tnid, tnid]) step (:59-61); *leg_t / *leg_d are the
+ * left-to-right sums (:56-57).  Returns the number of steps, or -(steps needed) if cap is too small, 0 on a broken table. */
+int64_t oracle_route_build(const int32_t* pred, const void* tt, const void* dist, int dtype, int n, int o, int d,
+                           int32_t* su, int32_t* sv, double* st, double* sd, int64_t cap, double* leg_t, double* leg_d) {
+    const int32_t* row = pred + (size_t)(o - 1) * (size_t)n;
+    int64_t len = 1;
+    for (int x = row[d - 1]; x > 0; x = row[x - 1]) if (++len > n) return 0;
+    if (len > cap) return -len;
+    int x = d;
+    for (int64_t p = len - 1; p >= 0; p--) { sv[p] = x; if (p > 0) x = row[x - 1]; }      /* path.reverse() */
+    for (int64_t k = 0; k < len; k++) su[k] = sv[k];
+    double duration = 0.0, distance = 0.0;
+    for (int64_t k = 0; k + 1 < len; k++) {
+        int u = su[k], v = su[k + 1];
+        size_t at = (size_t)(u - 1) * (size_t)n + (size_t)(v - 1);
+        st[k] = dtype == AMOD_TT_F64 ? ((const double*)tt)[at] : (double)((const float*)tt)[at];
+        sd[k] = dtype == AMOD_TT_F64 ? ((const double*)dist)[at] : (double)((const float*)dist)[at];
+        sv[k] = v;
+        duration += st[k]; distance += sd[k];
+    }
+    su[len - 1] = d; sv[len - 1] = d; st[len - 1] = 0.0; sd[len - 1] = 0.0;
+    *leg_t = duration; *leg_d = distance;
+    return len;
+}

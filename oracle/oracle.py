@@ -135,3 +135,34 @@ def greedy_assign(pool, n_veh: int, n_req: int, score=None):
     sel = np.zeros(max(pool.n_entries, 1), np.int32)
     m = lib().oracle_greedy_assign(C.addressof(s), score.ctypes.data, n_veh, n_req, order.ctypes.data, sel.ctypes.data)
     return order[:pool.n_entries], sel[:m]
+
+
+def routes_build(pred: np.ndarray, tt: np.ndarray, dist: np.ndarray, leg_o, leg_d):
+    """route_functions.build_route_from_origin_to_dest restated, for a batch of legs; same array layout as
+    amod_routes_build: (leg_off, step_u, step_v, step_t, step_d, leg_t, leg_d)."""
+    L = lib()
+    if not hasattr(L, "_routes_ready"):
+        L.oracle_route_build.restype = C.c_int64
+        L.oracle_route_build.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p,
+                                         C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.POINTER(C.c_double), C.POINTER(C.c_double)]
+        L._routes_ready = True
+    pred = np.ascontiguousarray(pred, dtype=np.int32)
+    assert tt.dtype == dist.dtype and tt.flags.c_contiguous and dist.flags.c_contiguous
+    n = tt.shape[0]
+    dtype = 1 if tt.dtype == np.float64 else 0
+    leg_o = np.asarray(leg_o, dtype=np.int32); leg_d = np.asarray(leg_d, dtype=np.int32)
+    cap = 4 * n
+    su, sv, st, sd = np.zeros(cap, np.int32), np.zeros(cap, np.int32), np.zeros(cap), np.zeros(cap)
+    off = [0]
+    U, V, Tt, D, LT, LD = [], [], [], [], [], []
+    for o, d in zip(leg_o.tolist(), leg_d.tolist()):
+        lt, ld = C.c_double(0.0), C.c_double(0.0)
+        k = L.oracle_route_build(pred.ctypes.data, tt.ctypes.data, dist.ctypes.data, dtype, n, o, d, su.ctypes.data, sv.ctypes.data,
+                                 st.ctypes.data, sd.ctypes.data, cap, C.byref(lt), C.byref(ld))
+        assert k > 0, (o, d, k)
+        U.append(su[:k].copy()); V.append(sv[:k].copy()); Tt.append(st[:k].copy()); D.append(sd[:k].copy())
+        LT.append(lt.value); LD.append(ld.value)
+        off.append(off[-1] + k)
+    cat = lambda xs, dt: np.concatenate(xs).astype(dt) if xs else np.zeros(0, dt)
+    return (np.asarray(off, dtype=np.int64), cat(U, np.int32), cat(V, np.int32), cat(Tt, np.float64), cat(D, np.float64),
+            np.asarray(LT, dtype=np.float64), np.asarray(LD, dtype=np.float64))

@@ -16,6 +16,7 @@ import pytest
 from conftest import ROOT
 
 sys.path.insert(0, os.path.join(ROOT, "oracle"))
+sys.path.insert(0, os.path.join(ROOT, "tests"))
 import ref_harness as rh  # noqa: E402
 
 pytestmark = pytest.mark.skipif(not rh.reference_available(), reason="reference tree not present")
@@ -39,6 +40,14 @@ def _run(dispatcher: str, patched, q, assigner: str = "greedy", scale: str = "sm
     # both runs must search exhaustively: disable the wall-clock cut-off of the unmodified seam as well
     orig = ref.dispatch_osp.compute_candidate_veh_trip_pairs
     ref.dispatch_osp.compute_candidate_veh_trip_pairs = lambda n, c, r, v, T, cutoff, reopt, fast: orig(n, c, r, v, T, 1e9, reopt, fast)
+    if patched == "routes":     # all legs of an epoch built in one batch, served to the reference's unchanged Veh.build_route
+        from amod_b200 import routes as aroutes
+        from test_routes_cpu import OracleRouteBuilder
+        import src.simulator.vehicle as vehicle_mod
+        geo = np.array([ref.route_functions.get_node_geo(n) for n in range(1, graph.n_nodes + 1)], dtype=np.float64)
+        rb = OracleRouteBuilder(graph, geo)
+        aroutes.install_routes(rb, vehicle_mod, [ref.dispatch_osp, ref.dispatch_sba])
+        patched = False
     if patched:
         tt = graph.tt
 
@@ -104,6 +113,20 @@ def test_simulation_outcome_identical_with_seams_replaced(dispatcher):
         assert r0 == r1
         assert reqs0 == reqs1
         assert veh0 == veh1
+
+
+def test_simulation_outcome_identical_with_batched_routes():
+    """Apply step (scheduling.py:110-119 -> vehicle.py:231-302) fed by batched route construction: the simulated run is
+    identical to the unmodified reference's, including every vehicle's travelled distance."""
+    ctx = mp.get_context("spawn")
+    res = []
+    for patched in (False, "routes"):
+        q = ctx.Queue()
+        p = ctx.Process(target=_run, args=("OSP", patched, q))
+        p.start()
+        res.append(q.get(timeout=600))
+        p.join()
+    assert res[0] == res[1]
 
 
 def test_simulation_outcome_identical_with_exact_assignment():

@@ -350,3 +350,31 @@ def test_cuda_pool_at_cfg4_fleet_scale_and_sharded():
     merged = adist.merge_vehicle_major(parts, ep.n_veh)
     ok, why = marshal.pools_equal(merged, ref, rtol=0.0, check_kind=True)
     assert ok, why
+
+
+def test_cuda_cfg5_peak_epoch_snapshot_sba_and_npo_at_named_size():
+    """BASELINE.json configs[4] on the committed peak-epoch snapshot (bench_data/cfg5_*: 20,000 vehicles in mixed states from a
+    demand-x4 run of the reference simulator, a 5,000-request burst): SBA pool and both NPO matches (the epoch's idle vehicles,
+    and all 20,000 x 5,000 = 10^8 pairs) against the oracle fingerprints of bench_data/digests.json."""
+    import glob
+    import hashlib
+    from conftest import ROOT
+    f = sorted(glob.glob(os.path.join(ROOT, "bench_data", "cfg5_epoch*.npz")))[0]
+    dg = json.load(open(os.path.join(ROOT, "bench_data", "digests.json")))[os.path.basename(f) + "@x1"]
+    z = np.load(f)
+    ep = marshal.Epoch.from_npz_dict(z, "ep_")
+    assert ep.n_veh == 20000 and ep.n_search == 5000 and ep.mode == marshal.MODE_SBA
+    b = builder_for(_grid())
+    got = b.build_pool(ep)
+    assert got.n_entries == dg["n_entries"] and got.stats["n_evals"] == dg["n_evals"] and got.stats["n_screens"] == 100_000_000
+    assert marshal.pool_digest(got) == dg["digest"]
+
+    def npo_digest(oi, op, od):
+        h = hashlib.blake2b(digest_size=16)
+        for a, dt in ((oi, "<i4"), (op, "<i4"), (od, "<f8")):
+            h.update(np.ascontiguousarray(a, dtype=np.dtype(dt)).tobytes())
+        return h.hexdigest()
+
+    assert npo_digest(*b.npo_match(z["npo_idle_nid"], z["npo_pend_onid"])) == dg["npo_digest"]
+    oi, op, od = b.npo_match(ep.veh_nid, z["npo_pend_onid"])          # 20,000 x 5,000
+    assert oi.size == 5000 and npo_digest(oi, op, od) == dg["npo_full_digest"]

@@ -87,3 +87,21 @@ def test_oracle_greedy_assignment_matches_reference():
         order, sel = oracle.greedy_assign(pool, ep.n_veh, ep.n_req)
         assert np.array_equal(order, z[f"g{g}_order"])
         assert np.array_equal(sel, z[f"g{g}_sel"])
+
+
+def test_bench_digests_are_the_oracles():
+    """bench.py states parity against bench_data/digests.json without executing the oracle: the stored fingerprints of the
+    plain (x1) cfg2 / cfg3 snapshots must be what the oracle produces today."""
+    import glob
+    import json
+    from conftest import ROOT
+    from amod_b200 import marshal, synth
+    import oracle
+    dg = json.load(open(os.path.join(ROOT, "bench_data", "digests.json")))
+    tt = synth.make_road_graph(seed=0).tt
+    files = sorted(glob.glob(os.path.join(ROOT, "bench_data", "cfg2_epoch*.npz")))[:3] + sorted(glob.glob(os.path.join(ROOT, "bench_data", "cfg3_epoch*.npz")))[:1]
+    for f in files:
+        ep = marshal.Epoch.from_npz_dict(np.load(f), "ep_")
+        pool = oracle.osp_build(ep, tt, n_threads=oracle.max_threads())
+        rec = dg[os.path.basename(f) + "@x1"]
+        assert marshal.pool_digest(pool) == rec["digest"] and pool.n_entries == rec["n_entries"] and pool.stats["n_evals"] == rec["n_evals"], f
