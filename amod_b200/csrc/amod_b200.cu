@@ -112,7 +112,7 @@ struct amod_ctx {
     // greedy assignment
     DevBuf ga_pos, ga_rank, ga_order, ga_state, ga_bv, ga_br, ga_tv, ga_tr, ga_sel, ga_cnt;
     // npo
-    DevBuf npo_in, npo_vm, npo_rm, npo_rb, npo_vb, npo_rdt, npo_mdt, npo_cnt;
+    DevBuf npo_in, npo_vm, npo_rm, npo_rb, npo_vb, npo_rdt, npo_mdt, npo_cnt, npo_grp, npo_rg;
     // routes (8f-2)
     int* d_pred = nullptr; void* d_dist = nullptr;
     DevBuf rt_in, rt_len, rt_off, rt_u, rt_v, rt_t, rt_d, rt_lt, rt_ld, rt_err;
@@ -292,7 +292,7 @@ extern "C" void amod_destroy(amod_ctx* ctx) {
                      &ctx->ent_src, &ctx->ent_trip, &ctx->ent_cost, &ctx->ent_delay, &ctx->trip_off, &ctx->sche_off, &ctx->trip_req,
                      &ctx->sche_code, &ctx->ga_pos, &ctx->ga_rank, &ctx->ga_order, &ctx->ga_state, &ctx->ga_bv, &ctx->ga_br, &ctx->ga_tv, &ctx->ga_tr,
                      &ctx->ga_sel, &ctx->ga_cnt, &ctx->npo_in, &ctx->npo_vm, &ctx->npo_rm, &ctx->npo_rb, &ctx->npo_vb, &ctx->npo_rdt,
-                     &ctx->npo_mdt, &ctx->npo_cnt};
+                     &ctx->npo_mdt, &ctx->npo_cnt, &ctx->npo_grp, &ctx->npo_rg};
     for (DevBuf* b : all) b->release();
     for (auto& l : ctx->lv) { l.trip_veh.release(); l.trip_req.release(); l.s0.release(); l.nfeas.release(); l.cost.release();
                               l.sch.release(); l.sch_cost.release(); l.final.release(); l.veh_start.release(); }
@@ -1268,21 +1268,44 @@ static int npo_impl(amod_ctx* ctx, const int32_t* idle_nid, int n_idle, const in
         CK(cudaMemcpyAsync(ctx->npo_in.as<int>() + n_idle, pend_onid, 4 * (size_t)n_pend, cudaMemcpyHostToDevice, st));
         d_idle = ctx->npo_in.as<int>(); d_pend = ctx->npo_in.as<int>() + n_idle;
     }
-    CK(ctx->npo_vm.ensure(4 * (size_t)n_idle)); CK(ctx->npo_rm.ensure(4 * (size_t)n_pend)); CK(ctx->npo_rb.ensure(4 * (size_t)n_pend));
-    CK(ctx->npo_vb.ensure(4 * (size_t)n_idle)); CK(ctx->npo_rdt.ensure(8 * (size_t)n_pend)); CK(ctx->npo_mdt.ensure(8 * (size_t)n_pend));
+    // groups of idle vehicles standing at the same node (npo.cuh): node, vehicles in fleet order, head pointer
+    std::vector<int> h_idle;
+    const int* hi = idle_nid;
+    if (loc == AMOD_LOC_DEVICE) {
+        h_idle.resize(n_idle);
+        CK(cudaMemcpyAsync(h_idle.data(), idle_nid, 4 * (size_t)n_idle, cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        hi = h_idle.data();
+        for (int i = 0; i < n_idle; i++) if (hi[i] < 1 || hi[i] > ctx->n_nodes) return ctx->fail(AMOD_E_BADARG, "idle node out of range");
+    }
+    std::vector<int> by_node(n_idle);
+    for (int i = 0; i < n_idle; i++) by_node[i] = i;
+    std::stable_sort(by_node.begin(), by_node.end(), [&](int a, int b) { return hi[a] < hi[b]; });
+    std::vector<int> g_node, g_start;
+    for (int i = 0; i < n_idle; i++)
+        if (i == 0 || hi[by_node[i]] != hi[by_node[i - 1]]) { g_node.push_back(hi[by_node[i]]); g_start.push_back(i); }
+    g_start.push_back(n_idle);
+    const int G = (int)g_node.size();
+    // packed upload: node[G] | start[G+1] | veh[n_idle] | head[G] (zero)
+    std::vector<int> packed((size_t)G + (size_t)G + 1 + (size_t)n_idle + (size_t)G, 0);
+    memcpy(packed.data(), g_node.data(), 4 * (size_t)G);
+    memcpy(packed.data() + G, g_start.data(), 4 * ((size_t)G + 1));
+    memcpy(packed.data() + 2 * (size_t)G + 1, by_node.data(), 4 * (size_t)n_idle);
+    CK(ctx->npo_grp.ensure(4 * packed.size()));
+    CK(cudaMemcpyAsync(ctx->npo_grp.p, packed.data(), 4 * packed.size(), cudaMemcpyHostToDevice, st));
+    NpoGroups grp;
+    grp.node = ctx->npo_grp.as<int>(); grp.start = grp.node + G; grp.veh = grp.start + G + 1;
+    grp.head = ctx->npo_grp.as<int>() + 2 * (size_t)G + 1 + (size_t)n_idle; grp.n_groups = G;
+    CK(ctx->npo_vm.ensure(4 * (size_t)n_idle)); CK(ctx->npo_rm.ensure(4 * (size_t)n_pend)); CK(ctx->npo_mdt.ensure(8 * (size_t)n_pend));
     CK(ctx->npo_cnt.ensure(4));
     CK(cudaMemsetAsync(ctx->npo_vm.p, 0xff, 4 * (size_t)n_idle, st));
     CK(cudaMemsetAsync(ctx->npo_rm.p, 0xff, 4 * (size_t)n_pend, st));
     CK(cudaMemsetAsync(ctx->npo_cnt.p, 0, 4, st));
     int matched = 0, rounds = 0;
     while (matched < target) {
-        k_npo_best<TT><<<n_pend, NPO_THREADS, 0, st>>>(tt, d_idle, n_idle, d_pend, n_pend, ctx->npo_vm.as<int>(), ctx->npo_rm.as<int>(), 0,
-                                                      ctx->npo_rb.as<int>(), ctx->npo_rdt.as<double>());
-        k_npo_best<TT><<<n_idle, NPO_THREADS, 0, st>>>(tt, d_idle, n_idle, d_pend, n_pend, ctx->npo_vm.as<int>(), ctx->npo_rm.as<int>(), 1,
-                                                      ctx->npo_vb.as<int>(), nullptr);
-        k_npo_commit<<<nblk(n_pend, 256), 256, 0, st>>>(n_pend, ctx->npo_rb.as<int>(), ctx->npo_rdt.as<double>(), ctx->npo_vb.as<int>(),
-                                                      ctx->npo_vm.as<int>(), ctx->npo_rm.as<int>(), ctx->npo_mdt.as<double>(),
-                                                      ctx->npo_cnt.as<int>());
+        // every group runs until it is exhausted or blocked by a request that prefers another group for now
+        k_npo_group_run<TT><<<G, NPO_THREADS, 0, st>>>(tt, grp, d_pend, n_pend, ctx->npo_vm.as<int>(), ctx->npo_rm.as<int>(),
+                                                      ctx->npo_mdt.as<double>(), ctx->npo_cnt.as<int>());
         rounds++;
         int prev = matched;
         CK(cudaMemcpyAsync(&matched, ctx->npo_cnt.p, 4, cudaMemcpyDeviceToHost, st));

@@ -26,8 +26,8 @@ def test_cfg1_whole_horizon_on_cuda():
 
 def test_cfg2_whole_day_samples_on_cuda():
     z = tu.load_trace("trace_cfg2day")
-    if z is None:
-        pytest.skip("tests/golden/trace_cfg2day.npz not recorded")
+    if z is None or "spec" not in z.files:
+        pytest.skip("tests/golden/trace_cfg2day.npz not recorded (or still being written)")
     b = PoolBuilder(table_from_spec(json.loads(str(z["spec"]))))
     n = tu.replay_cfg2day(b, z)
     assert n == len(z["epochs"])

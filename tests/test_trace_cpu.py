@@ -17,8 +17,8 @@ def test_cfg1_horizon_replays_through_the_seams_on_cpu():
 
 def test_cfg2_day_samples_replay_on_cpu():
     z = tu.load_trace("trace_cfg2day")
-    if z is None:
-        pytest.skip("tests/golden/trace_cfg2day.npz not recorded")
+    if z is None or "spec" not in z.files:
+        pytest.skip("tests/golden/trace_cfg2day.npz not recorded (or still being written)")
     tt = table_from_spec(json.loads(str(z["spec"])))
     epochs = z["epochs"].tolist()
     n = tu.replay_cfg2day(tu.oracle_backed_builder(tt), z, only=set(epochs[::6]))
