@@ -290,12 +290,21 @@ k_gp_offsets(const char* __restrict__ stage, GSlotLayout S, int world, int n_tot
     __shared__ i64 sm[3][32];
     if (!gp_build_final(ctl, run_levels, max_level)) return;
     gp_wait_flags(my_base, L, world, 0, st->epoch, st, 0xffffffffu);       // every rank's slice of this epoch has landed in my memory
+    // pass 1 (coalesced over vehicles, loads independent of each other): the three counts of every global vehicle, parked in the
+    // offset arrays themselves
+    for (int v = threadIdx.x; v < n_total; v += 1024) {
+        const char* slot = stage + (i64)vrank[v] * S.bytes;
+        const i64 u = vlocal[v];
+        const bool ok = ((const i64*)(slot + S.o_hdr))[0] > u;             // (a slot is unusable when its rank overflowed)
+        const int* cnt = (const int*)(slot + S.o_cnt);
+        goff_e[v] = ok ? cnt[u] : 0; goff_t[v] = ok ? cnt[S.cap_veh + u] : 0; goff_s[v] = ok ? cnt[2 * S.cap_veh + u] : 0;
+    }
+    __syncthreads();
+    // pass 2: every thread owns a contiguous range of vehicles; block-wide exclusive scan of the three running sums
     const int per = (n_total + 1023) / 1024;
     const int v0 = min(n_total, (int)threadIdx.x * per), v1 = min(n_total, v0 + per);
     i64 a[3] = {0, 0, 0};
-    for (int v = v0; v < v1; v++)
-        for (int c = 0; c < 3; c++) a[c] += InStagedVeh{stage, S, vrank, vlocal, c, n_total}(v);
-    // block exclusive scan of the three running sums
+    for (int v = v0; v < v1; v++) { a[0] += goff_e[v]; a[1] += goff_t[v]; a[2] += goff_s[v]; }
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     i64 ex[3];
     for (int c = 0; c < 3; c++) {
@@ -315,8 +324,10 @@ k_gp_offsets(const char* __restrict__ stage, GSlotLayout S, int world, int n_tot
     __syncthreads();
     i64 run[3] = {ex[0] + sm[0][w], ex[1] + sm[1][w], ex[2] + sm[2][w]};
     for (int v = v0; v < v1; v++) {
+        const i64 ce = goff_e[v], ct = goff_t[v], cs = goff_s[v];
         goff_e[v] = run[0]; goff_t[v] = run[1]; goff_s[v] = run[2];
-        for (int c = 0; c < 3; c++) run[c] += InStagedVeh{stage, S, vrank, vlocal, c, n_total}(v);
+        run[0] += ce; run[1] += ct; run[2] += cs;
     }
-    if (threadIdx.x == 1023) { goff_e[n_total] = run[0]; goff_t[n_total] = run[1]; goff_s[n_total] = run[2]; }
+    __syncthreads();
+    if (threadIdx.x == 1023) { goff_e[n_total] = st->tot[0]; goff_t[n_total] = st->tot[1]; goff_s[n_total] = st->tot[2]; }
 }
