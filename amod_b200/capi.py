@@ -84,7 +84,8 @@ EXPORTS = ("amod_create", "amod_destroy", "amod_last_error", "amod_version", "am
            "amod_pool_view", "amod_npo_match",
            "amod_gather_bench", "amod_gpool_create", "amod_gpool_open_peers", "amod_pool_veh_counts", "amod_gpool_scatter",
            "amod_gpool_view", "amod_gpool_fetch", "amod_set_graph", "amod_gpool_assemble", "amod_greedy_assign",
-           "amod_gpool_attach", "amod_gpool_detach", "amod_routes_upload", "amod_routes_build")
+           "amod_gpool_attach", "amod_gpool_detach", "amod_routes_upload", "amod_routes_build",
+           "amod_state_create", "amod_state_add_requests", "amod_state_update_vehicles", "amod_state_build", "amod_state_download")
 
 _lib = None
 
@@ -151,6 +152,16 @@ def load_library(path: str | None = None) -> C.CDLL:
     lib.amod_routes_upload.restype = C.c_int
     lib.amod_routes_build.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int, C.POINTER(AmodRoutes)]
     lib.amod_routes_build.restype = C.c_int
+    lib.amod_state_create.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_int32]
+    lib.amod_state_create.restype = C.c_int
+    lib.amod_state_add_requests.argtypes = [C.c_void_p, C.c_int32, C.c_int32] + [C.c_void_p] * 6
+    lib.amod_state_add_requests.restype = C.c_int
+    lib.amod_state_update_vehicles.argtypes = [C.c_void_p, C.c_int32] + [C.c_void_p] * 10
+    lib.amod_state_update_vehicles.restype = C.c_int
+    lib.amod_state_build.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_int64, C.c_void_p, C.c_int32, C.POINTER(AmodStats)]
+    lib.amod_state_build.restype = C.c_int
+    lib.amod_state_download.argtypes = [C.c_void_p] + [C.c_void_p] * 9
+    lib.amod_state_download.restype = C.c_int
     lib.amod_set_graph.argtypes = [C.c_void_p, C.c_int]
     lib.amod_set_graph.restype = C.c_int
     if path is None:

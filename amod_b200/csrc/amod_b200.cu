@@ -18,6 +18,7 @@
 #include "place.cuh"
 #include "pool.cuh"
 #include "routes.cuh"
+#include "state.cuh"
 #include "scan.cuh"
 
 #ifndef GRID_ELEM_PER_SM
@@ -116,6 +117,11 @@ struct amod_ctx {
     // routes (8f-2)
     int* d_pred = nullptr; void* d_dist = nullptr;
     DevBuf rt_in, rt_len, rt_off, rt_u, rt_v, rt_t, rt_d, rt_lt, rt_ld, rt_err;
+    // resident epoch state (8f-3)
+    FleetState fs; bool fs_valid = false; int fs_req_cap = 0, fs_req_n = 0, fs_max_len = 0;
+    DevBuf fs_nid, fs_t, fs_load, fs_status, fs_rnode, fs_rddl, fs_len, fs_code, fs_onb, fs_off64, fs_off32, fs_ccode, fs_conb, fs_search, fs_stage, fs_err;
+    DevBuf rq_onid, rq_dnid, rq_clp, rq_cld, rq_tr, rq_ts;
+    void* fs_pinned = nullptr; size_t fs_pinned_cap = 0;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     std::vector<cudaEvent_t> ev_pool;
     cudaStream_t side = nullptr;             // second branch of the epoch graph (next level's candidates)
@@ -307,6 +313,11 @@ extern "C" void amod_destroy(amod_ctx* ctx) {
     for (auto& g : ctx->graphs) if (g.exec) cudaGraphExecDestroy(g.exec);
     if (ctx->ep_pinned) cudaFreeHost(ctx->ep_pinned);
     if (ctx->d_tt) cudaFree(ctx->d_tt);
+    { DevBuf* sb[] = {&ctx->fs_nid, &ctx->fs_t, &ctx->fs_load, &ctx->fs_status, &ctx->fs_rnode, &ctx->fs_rddl, &ctx->fs_len, &ctx->fs_code, &ctx->fs_onb,
+                      &ctx->fs_off64, &ctx->fs_off32, &ctx->fs_ccode, &ctx->fs_conb, &ctx->fs_search, &ctx->fs_stage, &ctx->fs_err, &ctx->rq_onid, &ctx->rq_dnid,
+                      &ctx->rq_clp, &ctx->rq_cld, &ctx->rq_tr, &ctx->rq_ts};
+      for (DevBuf* b : sb) b->release(); }
+    if (ctx->fs_pinned) cudaFreeHost(ctx->fs_pinned);
     if (ctx->d_pred) cudaFree(ctx->d_pred);
     if (ctx->d_dist) cudaFree(ctx->d_dist);
     { DevBuf* rb[] = {&ctx->rt_in, &ctx->rt_len, &ctx->rt_off, &ctx->rt_u, &ctx->rt_v, &ctx->rt_t, &ctx->rt_d, &ctx->rt_lt, &ctx->rt_ld, &ctx->rt_err};
@@ -696,7 +707,7 @@ static int build_impl(amod_ctx* ctx, const amod_epoch* ep, int loc, amod_stats* 
     // reached and look further only if that level still produced trips (then the epoch is rerun deeper).
     int run_levels = mode == AMOD_MODE_SBA ? 1 : std::min(max_level, std::max(2, ctx->level_hint[mode] + 1));
     for (;; attempt++) {
-        if (attempt > 24) return ctx->fail(AMOD_E_NOMEM, "pool build did not converge after %d regrow attempts", attempt);
+        if (attempt > 48) return ctx->fail(AMOD_E_NOMEM, "pool build did not converge after %d regrow attempts", attempt);
         const unsigned long long r0 = g_reallocs;
         CKR(ensure_buffers(ctx, V, (i64)V * d.n_search, max_level, stride, &ls, &pb));
         if (g_reallocs != r0) ctx->buf_gen++;
@@ -1405,6 +1416,145 @@ extern "C" int amod_routes_build(amod_ctx* ctx, const int32_t* leg_o, const int3
     if (!ctx || !out || n_legs < 0 || (n_legs && (!leg_o || !leg_d))) return AMOD_E_BADARG;
     if (!ctx->d_pred) return ctx->fail(AMOD_E_BADARG, "amod_routes_upload first");
     return dispatch_tt(ctx, [&](auto tt) { return routes_impl(ctx, leg_o, leg_d, n_legs, loc, out, tt); });
+}
+
+// ------------------------------------------------------------------------------------------------
+// epoch state resident in HBM, updated by deltas
+// ------------------------------------------------------------------------------------------------
+extern "C" int amod_state_create(amod_ctx* ctx, int32_t n_veh, int32_t max_stops, int32_t req_cap) {
+    if (!ctx || n_veh < 0 || max_stops < 1 || max_stops > AMOD_MAX_STOPS || req_cap < 1) return AMOD_E_BADARG;
+    CK(cudaSetDevice(ctx->device));
+    const size_t V = (size_t)std::max(n_veh, 1), S = (size_t)max_stops, R = (size_t)req_cap;
+    CK(ctx->fs_nid.ensure(4 * V)); CK(ctx->fs_t.ensure(8 * V)); CK(ctx->fs_load.ensure(4 * V)); CK(ctx->fs_status.ensure(4 * V));
+    CK(ctx->fs_rnode.ensure(4 * V)); CK(ctx->fs_rddl.ensure(8 * V)); CK(ctx->fs_len.ensure(4 * V)); CK(ctx->fs_code.ensure(4 * V * S)); CK(ctx->fs_onb.ensure(V * S));
+    CK(ctx->fs_off64.ensure(8 * (V + 2))); CK(ctx->fs_off32.ensure(4 * (V + 2))); CK(ctx->fs_ccode.ensure(4 * V * S)); CK(ctx->fs_conb.ensure(V * S));
+    CK(ctx->fs_err.ensure(8));
+    CK(ctx->rq_onid.ensure(4 * R)); CK(ctx->rq_dnid.ensure(4 * R)); CK(ctx->rq_clp.ensure(8 * R)); CK(ctx->rq_cld.ensure(8 * R));
+    CK(ctx->rq_tr.ensure(8 * R)); CK(ctx->rq_ts.ensure(8 * R));
+    DevBuf* zero[] = {&ctx->fs_nid, &ctx->fs_t, &ctx->fs_load, &ctx->fs_status, &ctx->fs_rnode, &ctx->fs_rddl, &ctx->fs_len, &ctx->fs_code, &ctx->fs_onb};
+    for (DevBuf* b : zero) CK(cudaMemset(b->p, 0, b->cap));
+    FleetState& fs = ctx->fs;
+    fs.nid = ctx->fs_nid.as<int>(); fs.t = ctx->fs_t.as<double>(); fs.load = ctx->fs_load.as<int>(); fs.status = ctx->fs_status.as<int>();
+    fs.reb_node = ctx->fs_rnode.as<int>(); fs.reb_ddl = ctx->fs_rddl.as<double>(); fs.len = ctx->fs_len.as<int>(); fs.code = ctx->fs_code.as<int>();
+    fs.onboard = ctx->fs_onb.as<uint8_t>(); fs.n_veh = n_veh; fs.max_stops = max_stops;
+    ctx->fs_valid = true; ctx->fs_req_cap = req_cap; ctx->fs_req_n = 0; ctx->fs_max_len = 0;
+    ctx->buf_gen++;
+    return AMOD_OK;
+}
+
+extern "C" int amod_state_add_requests(amod_ctx* ctx, int32_t first, int32_t n, const int32_t* onid, const int32_t* dnid, const double* clp,
+                                       const double* cld, const double* tr, const double* ts) {
+    if (!ctx || n < 0 || first < 0) return AMOD_E_BADARG;
+    if (!ctx->fs_valid) return ctx->fail(AMOD_E_BADARG, "amod_state_create first");
+    if (n == 0) return AMOD_OK;
+    if ((i64)first + n > ctx->fs_req_cap) return ctx->fail(AMOD_E_CAPACITY, "request table holds %d requests", ctx->fs_req_cap);
+    for (int i = 0; i < n; i++)
+        if (onid[i] < 1 || onid[i] > ctx->n_nodes || dnid[i] < 1 || dnid[i] > ctx->n_nodes) return ctx->fail(AMOD_E_BADARG, "request %d: node id out of range", first + i);
+    CK(cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    const size_t N = (size_t)n, F = (size_t)first;
+    CK(cudaMemcpyAsync(ctx->rq_onid.as<int>() + F, onid, 4 * N, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(ctx->rq_dnid.as<int>() + F, dnid, 4 * N, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(ctx->rq_clp.as<double>() + F, clp, 8 * N, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(ctx->rq_cld.as<double>() + F, cld, 8 * N, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(ctx->rq_tr.as<double>() + F, tr, 8 * N, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(ctx->rq_ts.as<double>() + F, ts, 8 * N, cudaMemcpyHostToDevice, st));
+    CK(cudaStreamSynchronize(st));      // (the host arrays may be reused by the caller)
+    ctx->fs_req_n = std::max(ctx->fs_req_n, first + n);
+    return AMOD_OK;
+}
+
+extern "C" int amod_state_update_vehicles(amod_ctx* ctx, int32_t n, const int32_t* veh_idx, const int32_t* nid, const double* t,
+                                          const int32_t* load, const int32_t* status, const int32_t* reb_node, const double* reb_ddl,
+                                          const int32_t* sche_off, const int32_t* sche_code, const uint8_t* sche_onboard) {
+    if (!ctx || n < 0) return AMOD_E_BADARG;
+    if (!ctx->fs_valid) return ctx->fail(AMOD_E_BADARG, "amod_state_create first");
+    if (n == 0) return AMOD_OK;
+    CK(cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    const size_t N = (size_t)n, NS = (size_t)sche_off[n];
+    for (int i = 0; i < n; i++) {
+        if (nid[i] < 1 || nid[i] > ctx->n_nodes) return ctx->fail(AMOD_E_BADARG, "vehicle %d: node id out of range", veh_idx[i]);
+        if (sche_off[i + 1] - sche_off[i] > ctx->fs.max_stops) return ctx->fail(AMOD_E_LIMIT, "vehicle %d: schedule longer than the state's %d stops", veh_idx[i], ctx->fs.max_stops);
+        ctx->fs_max_len = std::max(ctx->fs_max_len, sche_off[i + 1] - sche_off[i]);      // monotone: the SBA / OSP-NR graph and strides stay put
+        for (int k = sche_off[i]; k < sche_off[i + 1]; k++) {
+            const int c = sche_code[k];
+            if (c < -1 || (c >> 1) >= ctx->fs_req_n) return ctx->fail(AMOD_E_BADARG, "vehicle %d: stop code %d names an unknown request", veh_idx[i], c);
+            if (c == -1 && (reb_node[i] < 1 || reb_node[i] > ctx->n_nodes)) return ctx->fail(AMOD_E_BADARG, "vehicle %d: rebalancing node out of range", veh_idx[i]);
+        }
+    }
+    // one packed staging buffer, one copy
+    struct Part { const void* src; size_t bytes; size_t at; };
+    Part parts[] = {{t, 8 * N, 0}, {reb_ddl, 8 * N, 0}, {veh_idx, 4 * N, 0}, {nid, 4 * N, 0}, {load, 4 * N, 0}, {status, 4 * N, 0}, {reb_node, 4 * N, 0},
+                    {sche_off, 4 * (N + 1), 0}, {sche_code, 4 * NS, 0}, {sche_onboard, NS, 0}};
+    size_t total = 0;
+    for (auto& p : parts) { p.at = total; total += (p.bytes + 15) & ~(size_t)15; }
+    if (total > ctx->fs_pinned_cap) {
+        if (ctx->fs_pinned) cudaFreeHost(ctx->fs_pinned);
+        ctx->fs_pinned = nullptr; ctx->fs_pinned_cap = 0;
+        CK(cudaMallocHost(&ctx->fs_pinned, total * 2));
+        ctx->fs_pinned_cap = total * 2;
+    }
+    CK(ctx->fs_stage.ensure(total));
+    for (auto& p : parts) if (p.bytes) memcpy((char*)ctx->fs_pinned + p.at, p.src, p.bytes);
+    CK(cudaMemcpyAsync(ctx->fs_stage.p, ctx->fs_pinned, total, cudaMemcpyHostToDevice, st));
+    const char* B = ctx->fs_stage.as<char>();
+    FleetDelta d;
+    d.t = (const double*)(B + parts[0].at); d.reb_ddl = (const double*)(B + parts[1].at); d.idx = (const int*)(B + parts[2].at);
+    d.nid = (const int*)(B + parts[3].at); d.load = (const int*)(B + parts[4].at); d.status = (const int*)(B + parts[5].at);
+    d.reb_node = (const int*)(B + parts[6].at); d.off = (const int*)(B + parts[7].at); d.code = (const int*)(B + parts[8].at);
+    d.onboard = (const uint8_t*)(B + parts[9].at); d.n = n;
+    CK(cudaMemsetAsync(ctx->fs_err.p, 0, 8, st));
+    k_state_scatter<<<std::max(1, std::min(ctx->n_sm * 4, (n + 255) / 256)), 256, 0, st>>>(ctx->fs, d, ctx->fs_err.as<unsigned long long>());
+    unsigned long long err = 0;
+    CK(cudaMemcpyAsync(&err, ctx->fs_err.p, 8, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    CK(cudaGetLastError());
+    if (err) return ctx->fail(AMOD_E_BADARG, "a vehicle index or schedule length is out of range for the resident state");
+    return AMOD_OK;
+}
+
+extern "C" int amod_state_build(amod_ctx* ctx, int32_t mode, int32_t cap, int64_t T, const int32_t* search_rids, int32_t n_search, amod_stats* stats) {
+    if (!ctx || n_search < 0 || (n_search && !search_rids)) return AMOD_E_BADARG;
+    if (!ctx->fs_valid) return ctx->fail(AMOD_E_BADARG, "amod_state_create first");
+    for (int i = 0; i < n_search; i++)
+        if (search_rids[i] < 0 || search_rids[i] >= ctx->fs_req_n) return ctx->fail(AMOD_E_BADARG, "search[%d] names an unknown request", i);
+    CK(cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    const FleetState& fs = ctx->fs;
+    CK(ctx->fs_search.ensure(4 * (size_t)std::max(n_search, 1)));
+    if (n_search) CK(cudaMemcpyAsync(ctx->fs_search.p, search_rids, 4 * (size_t)n_search, cudaMemcpyHostToDevice, st));
+    CK(ctx->partial.ensure(2 * 8 * (size_t)(ctx->n_sm + 1)));
+    scan_dev(ctx, InStateLen{fs.len, (i64)fs.n_veh}, ctx->fs_off64.as<i64>(), FinNone{});
+    k_state_csr<<<std::max(1, std::min(ctx->n_sm * 4, (fs.n_veh + 256) / 256)), 256, 0, st>>>(fs, ctx->fs_off64.as<i64>(), ctx->fs_off32.as<int>(),
+                                                                                       ctx->fs_ccode.as<int>(), ctx->fs_conb.as<uint8_t>());
+    amod_epoch ep; memset(&ep, 0, sizeof ep);
+    ep.n_veh = fs.n_veh; ep.n_req = ctx->fs_req_n; ep.n_search = n_search; ep.cap = cap; ep.mode = mode; ep.T = T;
+    ep.reserved = mode == AMOD_MODE_OSP ? 0 : std::max(ctx->fs_max_len, 1);     // longest schedule ever resident (monotone)
+    ep.veh_nid = fs.nid; ep.veh_t_to_nid = fs.t; ep.veh_load = fs.load; ep.veh_status = fs.status;
+    ep.veh_sche_off = ctx->fs_off32.as<int>(); ep.sche_code = ctx->fs_ccode.as<int>(); ep.sche_onboard = ctx->fs_conb.as<uint8_t>();
+    ep.veh_reb_node = fs.reb_node; ep.veh_reb_ddl = fs.reb_ddl;
+    ep.req_onid = ctx->rq_onid.as<int>(); ep.req_dnid = ctx->rq_dnid.as<int>(); ep.req_clp = ctx->rq_clp.as<double>(); ep.req_cld = ctx->rq_cld.as<double>();
+    ep.req_tr = ctx->rq_tr.as<double>(); ep.req_ts = ctx->rq_ts.as<double>(); ep.search = ctx->fs_search.as<int>();
+    return dispatch_tt(ctx, [&](auto tt) { return build_impl(ctx, &ep, AMOD_LOC_DEVICE, stats, tt); });
+}
+
+extern "C" int amod_state_download(amod_ctx* ctx, int32_t* nid, double* t, int32_t* load, int32_t* status, int32_t* reb_node, double* reb_ddl,
+                                   int32_t* sche_len, int32_t* sche_code, uint8_t* sche_onboard) {
+    if (!ctx) return AMOD_E_BADARG;
+    if (!ctx->fs_valid) return ctx->fail(AMOD_E_BADARG, "amod_state_create first");
+    CK(cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    const size_t V = (size_t)ctx->fs.n_veh, S = (size_t)ctx->fs.max_stops;
+    if (V == 0) return AMOD_OK;
+    CK(cudaMemcpyAsync(nid, ctx->fs.nid, 4 * V, cudaMemcpyDeviceToHost, st)); CK(cudaMemcpyAsync(t, ctx->fs.t, 8 * V, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(load, ctx->fs.load, 4 * V, cudaMemcpyDeviceToHost, st)); CK(cudaMemcpyAsync(status, ctx->fs.status, 4 * V, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(reb_node, ctx->fs.reb_node, 4 * V, cudaMemcpyDeviceToHost, st)); CK(cudaMemcpyAsync(reb_ddl, ctx->fs.reb_ddl, 8 * V, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(sche_len, ctx->fs.len, 4 * V, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(sche_code, ctx->fs.code, 4 * V * S, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(sche_onboard, ctx->fs.onboard, V * S, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    return AMOD_OK;
 }
 
 extern "C" int amod_gather_bench(amod_ctx* ctx, const int32_t* o_dev, const int32_t* d_dev, float* out_dev, int64_t n, int iters,

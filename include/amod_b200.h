@@ -236,6 +236,25 @@ typedef struct amod_routes {
 int amod_routes_upload(amod_ctx* ctx, const int32_t* path_table_host, const void* dist_table_host);
 int amod_routes_build(amod_ctx* ctx, const int32_t* leg_o, const int32_t* leg_d, int32_t n_legs, int loc, amod_routes* out);
 
+/* ---- epoch state resident in HBM, updated by deltas ----------------------------------------------------
+ * The request table is indexed by request id (request.py:25-41: a request's fields never change; the platform numbers them
+ * 0, 1, 2, ... platform.py:262) and only grows; vehicles (vehicle.py:41-70) are rows of fixed-stride device arrays.  An epoch
+ * uploads the requests that arrived and the vehicles whose row changed, then builds from the resident state; stop codes and the
+ * pool's trip_req then hold request IDS (code = 2*rid + drop-off, -1 = rebalancing stop).
+ * amod_state_update_vehicles: row i of the arrays describes vehicle veh_idx[i]; its schedule is stops [sche_off[i], sche_off[i+1])
+ * of sche_code / sche_onboard (stop codes over request ids).  All pointers are host memory. */
+int amod_state_create(amod_ctx* ctx, int32_t n_veh, int32_t max_stops_per_veh, int32_t request_capacity);
+int amod_state_add_requests(amod_ctx* ctx, int32_t first_rid, int32_t n, const int32_t* onid, const int32_t* dnid, const double* clp,
+                            const double* cld, const double* tr, const double* ts);
+int amod_state_update_vehicles(amod_ctx* ctx, int32_t n, const int32_t* veh_idx, const int32_t* nid, const double* t_to_nid,
+                               const int32_t* load, const int32_t* status, const int32_t* reb_node, const double* reb_ddl,
+                               const int32_t* sche_off, const int32_t* sche_code, const uint8_t* sche_onboard);
+/* build from the resident state: mode / cap / T as in amod_epoch, search = request ids in the reference's order (host). */
+int amod_state_build(amod_ctx* ctx, int32_t mode, int32_t cap, int64_t T, const int32_t* search_rids, int32_t n_search, amod_stats* stats);
+/* download the resident state as an amod_epoch-shaped set of host arrays (tests: parity with the host marshalling) */
+int amod_state_download(amod_ctx* ctx, int32_t* nid, double* t, int32_t* load, int32_t* status, int32_t* reb_node, double* reb_ddl,
+                        int32_t* sche_len, int32_t* sche_code /*[n_veh*max_stops]*/, uint8_t* sche_onboard);
+
 /* Raw travel-time gather out[i] = tt[o[i]][d[i]] (route_functions.py:22-25): used by the
  * L2-gather roofline microbenchmark.  Device pointers.  Returns device ms in *ms. */
 int amod_gather_bench(amod_ctx* ctx, const int32_t* o_dev, const int32_t* d_dev, float* out_dev,

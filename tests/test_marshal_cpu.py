@@ -199,3 +199,21 @@ def test_lazy_records_keep_sorted_positions_after_iteration():
     resorted.sort(key=lambda p: p[0].id, reverse=True)
     with pytest.raises(RuntimeError):
         resorted.apply_order(order)
+
+
+def test_state_rows_and_request_id_space():
+    """amod_b200/state.py host logic: fixed-stride vehicle rows over request IDS, and a pool rewritten over ids."""
+    from amod_b200 import state as astate
+    tt, cases = load_golden("sim_osp_cap4")
+    ep, gold = cases[2]
+    rows = astate.DeviceFleet.rows_of(ep, 16)
+    lens = np.diff(ep.veh_sche_off)
+    assert np.array_equal(rows["len"], lens)
+    for v in range(ep.n_veh):
+        codes = ep.sche_code[ep.veh_sche_off[v]:ep.veh_sche_off[v + 1]]
+        want = [(-1 if c < 0 else 2 * int(ep.req_id[c >> 1]) + (c & 1)) for c in codes.tolist()]
+        assert rows["code"][v, :lens[v]].tolist() == want and not rows["code"][v, lens[v]:].any()
+    p = astate.pool_in_request_ids(gold, ep)
+    assert np.array_equal(p.trip_req, ep.req_id[gold.trip_req]) and np.array_equal(p.ent_cost, gold.ent_cost)
+    back = np.where(p.sche_code < 0, -1, 2 * np.searchsorted(ep.req_id, np.maximum(p.sche_code, 0) >> 1) + (p.sche_code & 1))
+    assert np.array_equal(back, gold.sche_code)
