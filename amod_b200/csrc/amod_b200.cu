@@ -19,6 +19,7 @@
 #include "pool.cuh"
 #include "routes.cuh"
 #include "state.cuh"
+#include "sbam.cuh"
 #include "scan.cuh"
 
 #ifndef GRID_ELEM_PER_SM
@@ -105,7 +106,8 @@ struct amod_ctx {
     // multi-GPU global pool (peer-mapped)
     char* gp_base = nullptr; GPoolLayout gp_layout; GPoolPeers gp_peers; bool gp_open = false; int gp_max_veh = 0;
     GSlotLayout gp_slot; i64 gp_o_stage = 0; int gp_world = 0;
-    DevBuf gp_off, gp_tot, gp_place; void* gp_peer_ptr[GPOOL_MAX_WORLD] = {nullptr};
+    DevBuf gp_off, gp_tot, gp_place, gp_glob; void* gp_peer_ptr[GPOOL_MAX_WORLD] = {nullptr};
+    DevBuf sm_pos, sm_epos, sm_egv, sm_dest, sm_rs, sm_base, sm_slen;      // SBA merge workspace (sbam.cuh)
     GpState* gp_h_state = nullptr;           // pinned mirror of the device-resident assembly state
     bool gp_attached = false;                // every build also assembles (inside the build's single synchronisation)
     int gp_root = -1;                        // >= 0: only this rank receives and merges the slices (gather); < 0: every rank does
@@ -307,7 +309,8 @@ extern "C" void amod_destroy(amod_ctx* ctx) {
     if (ctx->fetch_pinned) cudaFreeHost(ctx->fetch_pinned);
     for (int r = 0; r < GPOOL_MAX_WORLD; r++) if (ctx->gp_peer_ptr[r]) cudaIpcCloseMemHandle(ctx->gp_peer_ptr[r]);
     if (ctx->gp_base) cudaFree(ctx->gp_base);
-    ctx->gp_off.release(); ctx->gp_tot.release(); ctx->gp_place.release();
+    ctx->gp_off.release(); ctx->gp_tot.release(); ctx->gp_place.release(); ctx->gp_glob.release();
+    { DevBuf* mb[] = {&ctx->sm_pos, &ctx->sm_epos, &ctx->sm_egv, &ctx->sm_dest, &ctx->sm_rs, &ctx->sm_base, &ctx->sm_slen}; for (DevBuf* b : mb) b->release(); }
     if (ctx->gp_h_state) cudaFreeHost(ctx->gp_h_state);
     ctx->d_epoch.release();
     for (auto& g : ctx->graphs) if (g.exec) cudaGraphExecDestroy(g.exec);
@@ -510,7 +513,7 @@ static int ensure_buffers(amod_ctx* ctx, int V, i64 n_screen, int max_level, con
     return AMOD_OK;
 }
 
-static void enqueue_gpool(amod_ctx* ctx, int run_levels, int max_level);
+static void enqueue_gpool(amod_ctx* ctx, int run_levels, int max_level, bool sba);
 static int check_gpool_state(amod_ctx* ctx);
 
 // One attempt: enqueue the whole level-synchronous pipeline on the stream without any host
@@ -664,7 +667,7 @@ static int enqueue_build(amod_ctx* ctx, int mode, int cap, Table<TT> tt, int max
         ctx->n_launches += 2;
     }
     // ---- multi-GPU: this rank's slice travels (and, on the merging ranks, the fleet-wide pool is assembled) in the same graph
-    if (ctx->gp_attached && !sba) enqueue_gpool(ctx, max_level, cap + 4);
+    if (ctx->gp_attached) enqueue_gpool(ctx, max_level, sba ? max_level : cap + 4, sba != 0);
     *n_ev_out = n_ev;
     return AMOD_OK;
 }
@@ -699,6 +702,15 @@ static int build_impl(amod_ctx* ctx, const amod_epoch* ep, int loc, amod_stats* 
     int stride[MAX_LEVELS];
     for (int k = 0; k < MAX_LEVELS; k++) stride[k] = std::max(1, std::min(MAXS, base_len + 2 * k));
 
+    if (ctx->gp_attached && mode == AMOD_MODE_SBA && (ctx->gp_root < 0 || ctx->gp_root == ctx->gp_peers.rank)) {
+        // workspace of the request-major merge on this (merging) rank
+        const unsigned long long r0 = g_reallocs;
+        const size_t W = (size_t)ctx->gp_peers.world, CE = (size_t)ctx->gp_slot.cap_ent, Q = (size_t)d.n_search;
+        CK(ctx->sm_pos.ensure(4 * ((size_t)d.n_req + 1))); CK(ctx->sm_epos.ensure(4 * W * CE)); CK(ctx->sm_egv.ensure(4 * W * CE));
+        CK(ctx->sm_dest.ensure(4 * W * CE)); CK(ctx->sm_rs.ensure(4 * W * (Q + 2))); CK(ctx->sm_base.ensure(8 * (Q + 2)));
+        CK(ctx->sm_slen.ensure(4 * ((size_t)ctx->gp_layout.cap_ent + 1))); CK(ctx->partial.ensure(2 * 8 * (size_t)(ctx->n_sm + 1)));
+        if (g_reallocs != r0) ctx->buf_gen++;
+    }
     LevelSet ls; PoolBufs pb;
     size_t n_ev = 0;
     Control* h = ctx->h_ctl;
@@ -745,7 +757,7 @@ static int build_impl(amod_ctx* ctx, const amod_epoch* ep, int loc, amod_stats* 
         }
         CK(cudaEventRecord(ctx->ev1, st));
         CK(cudaMemcpyAsync(h, ctx->ctl.p, sizeof(Control), cudaMemcpyDeviceToHost, st));
-        const bool with_gp = ctx->gp_attached && mode != AMOD_MODE_SBA;
+        const bool with_gp = ctx->gp_attached;
         if (with_gp) CK(cudaMemcpyAsync(ctx->gp_h_state, ctx->gp_tot.p, sizeof(GpState), cudaMemcpyDeviceToHost, st));
         CK(cudaStreamSynchronize(st));
         CK(cudaGetLastError());
@@ -824,7 +836,7 @@ static int build_impl(amod_ctx* ctx, const amod_epoch* ep, int loc, amod_stats* 
         }
     }
     (void)total_tasks;
-    if (ctx->gp_attached && mode != AMOD_MODE_SBA) CKR(check_gpool_state(ctx));
+    if (ctx->gp_attached) CKR(check_gpool_state(ctx));
     if (mode != AMOD_MODE_SBA && run_levels == max_level && h->n_trips[max_level] > 0)
         return ctx->fail(AMOD_E_LEVELS, "a feasible trip of size cap+4=%d exists; the reference raises IndexError here "
                                         "(dispatch_osp.py:8,226)", max_level);
@@ -944,6 +956,7 @@ static GSlotLayout gslot_layout(i64 cv, i64 ce, i64 ct, i64 cs) {
     S.o_hdr = take(64); S.o_vehoff = take(8 * (cv + 1)); S.o_kind = take(4 * ce); S.o_nfeas = take(4 * ce); S.o_cost = take(8 * ce);
     S.o_delay = take(8 * ce); S.o_toff = take(8 * (ce + 1)); S.o_soff = take(8 * (ce + 1)); S.o_treq = take(4 * ct); S.o_scode = take(4 * cs);
     S.o_cnt = take(4 * 3 * cv);
+    S.o_veh = take(4 * ce);
     S.bytes = o;
     return S;
 }
@@ -979,6 +992,11 @@ extern "C" int amod_gpool_create(amod_ctx* ctx, int64_t cap_entries, int64_t cap
         for (int v = 0; v < max_veh_total; v++) { place[v] = v % world; place[(size_t)max_veh_total + v] = v / world; }
         CK(ctx->gp_place.ensure(4 * place.size()));
         CK(cudaMemcpy(ctx->gp_place.p, place.data(), 4 * place.size(), cudaMemcpyHostToDevice));
+        const size_t cv = (size_t)ctx->gp_slot.cap_veh;
+        std::vector<int> glob((size_t)world * cv, 0);           // inverse: global vehicle of (rank, local vehicle)
+        for (int v = 0; v < max_veh_total; v++) glob[(size_t)(v % world) * cv + (size_t)(v / world)] = v;
+        CK(ctx->gp_glob.ensure(4 * glob.size()));
+        CK(cudaMemcpy(ctx->gp_glob.p, glob.data(), 4 * glob.size(), cudaMemcpyHostToDevice));
     }
     cudaIpcMemHandle_t h;
     CK(cudaIpcGetMemHandle(&h, ctx->gp_base));
@@ -1054,7 +1072,7 @@ extern "C" int amod_gpool_scatter(amod_ctx* ctx, const int32_t* counts_all_dev, 
 
 // the three assembly kernels on the build stream: push my slice (+ flag) | wait for all slices, global offsets | merge
 // (+ "read" flag).  Ranks that do not merge (gather mode, rank != root) only push.  Capturable: no per-epoch argument.
-static void enqueue_gpool(amod_ctx* ctx, int run_levels, int max_level) {
+static void enqueue_gpool(amod_ctx* ctx, int run_levels, int max_level, bool sba = false) {
     cudaStream_t st = ctx->stream;
     const GPoolLayout& L = ctx->gp_layout;
     const GSlotLayout& S = ctx->gp_slot;
@@ -1065,16 +1083,35 @@ static void enqueue_gpool(amod_ctx* ctx, int run_levels, int max_level) {
     const int* vrank = ctx->gp_place.as<int>();
     const int* vlocal = vrank + ctx->gp_max_veh;
     GPush P; memset(&P, 0, sizeof P);
-    const void* srcs[10] = {nullptr, ctx->veh_off.p, ctx->ent_kind.p, ctx->ent_nfeas.p, ctx->ent_cost.p, ctx->ent_delay.p, ctx->trip_off.p,
-                            ctx->sche_off.p, ctx->trip_req.p, ctx->sche_code.p};
-    const i64 dsts[10] = {S.o_hdr, S.o_vehoff, S.o_kind, S.o_nfeas, S.o_cost, S.o_delay, S.o_toff, S.o_soff, S.o_treq, S.o_scode};
-    for (int g = 0; g < 10; g++) { P.seg[g].src = (const char*)srcs[g]; P.seg[g].dst_off = dsts[g]; P.seg[g].bytes = 0; }
-    P.n = 10;
+    const void* srcs[11] = {nullptr, ctx->veh_off.p, ctx->ent_kind.p, ctx->ent_nfeas.p, ctx->ent_cost.p, ctx->ent_delay.p, ctx->trip_off.p,
+                            ctx->sche_off.p, ctx->trip_req.p, ctx->sche_code.p, ctx->ent_veh.p};
+    const i64 dsts[11] = {S.o_hdr, S.o_vehoff, S.o_kind, S.o_nfeas, S.o_cost, S.o_delay, S.o_toff, S.o_soff, S.o_treq, S.o_scode, S.o_veh};
+    for (int g = 0; g < 11; g++) { P.seg[g].src = (const char*)srcs[g]; P.seg[g].dst_off = dsts[g]; P.seg[g].bytes = 0; }
+    P.n = 11;
     k_gp_push_bulk<<<ctx->n_sm * 2, 256, 0, st>>>(P, L, S, ctx->gp_o_stage, ctx->gp_peers, ctx->d_epoch.as<DEpoch>(), ctx->ctl.as<Control>(),
                                                 gst, ctx->gp_base, root, run_levels, max_level);
     ctx->n_launches++;
     if (root >= 0 && root != ctx->gp_peers.rank) return;
     const char* stage = ctx->gp_base + ctx->gp_o_stage;
+    if (sba) {      // request-major merge (sbam.cuh): positions by counting, one prefix sum for the schedule offsets
+        SbaMergeBufs m;
+        m.pos_of = ctx->sm_pos.as<int>(); m.epos = ctx->sm_epos.as<int>(); m.egv = ctx->sm_egv.as<int>(); m.dest = ctx->sm_dest.as<int>();
+        m.rs = ctx->sm_rs.as<int>(); m.base = ctx->sm_base.as<i64>(); m.slen = ctx->sm_slen.as<int>(); m.glob = ctx->gp_glob.as<int>();
+        m.cap_ent_slot = S.cap_ent; m.cap_veh = (int)S.cap_veh;
+        const DEpoch* d = ctx->d_epoch.as<DEpoch>();
+        Control* ctl = ctx->ctl.as<Control>();
+        const int G = ctx->n_sm * 4;
+        k_sbam_pos<<<G, 256, 0, st>>>(d, m);
+        k_sbam_pos2<<<G, 256, 0, st>>>(d, m);
+        k_sbam_keys<<<G, 256, 0, st>>>(stage, S, world, d, m, gst, ctx->gp_base, L, ctl);
+        k_sbam_reqstart<<<G, 256, 0, st>>>(stage, S, world, d, m, ctl);
+        k_sbam_base<<<ctx->n_sm, 256, 0, st>>>(world, d, m, gst, L, n_total, ctl);
+        k_sbam_dest<<<G * 2, 256, 0, st>>>(stage, S, ctx->gp_base, L, world, d, m, gst, ctl);
+        scan_dev(ctx, InSbaSlen{m.slen, gst}, (i64*)(ctx->gp_base + L.o_soff), FinSbaStops{gst, L.cap_pst});
+        k_sbam_codes<<<G * 2, 256, 0, st>>>(stage, S, ctx->gp_base, L, world, m, gst, ctx->gp_peers, ctl);
+        ctx->n_launches += 7;
+        return;
+    }
     k_gp_offsets<<<1, 1024, 0, st>>>(stage, S, world, n_total, off, off + stride, off + 2 * stride, gst, ctx->gp_base, L, vrank, vlocal,
                                      ctx->ctl.as<Control>(), run_levels, max_level);
     k_gp_merge<<<ctx->n_sm * 8, 256, 0, st>>>(stage, S, ctx->gp_base, L, world, off, off + stride, off + 2 * stride, gst, n_total,
@@ -1107,6 +1144,12 @@ extern "C" int amod_gpool_attach(amod_ctx* ctx, int32_t n_veh_total, int32_t roo
     }
     CK(cudaStreamSynchronize(ctx->stream));
     CK(cudaMemcpy(ctx->gp_place.p, place.data(), 4 * place.size(), cudaMemcpyHostToDevice));
+    {
+        const size_t cv = (size_t)ctx->gp_slot.cap_veh;
+        std::vector<int> glob((size_t)world * cv, 0);
+        for (int v = 0; v < n_veh_total; v++) glob[(size_t)place[v] * cv + (size_t)place[(size_t)ctx->gp_max_veh + v]] = v;
+        CK(cudaMemcpy(ctx->gp_glob.p, glob.data(), 4 * glob.size(), cudaMemcpyHostToDevice));
+    }
     if (!ctx->gp_attached || ctx->gp_root != root || ctx->gp_n_total != n_veh_total) ctx->buf_gen++;      // the epoch graph changes
     if (!ctx->gp_attached || ctx->gp_root != root) {
         // the readers change: the ranks must have met at a host-side barrier since the last assembly; the next push does not
@@ -1142,7 +1185,7 @@ extern "C" int amod_gpool_assemble(amod_ctx* ctx, int32_t n_veh_total) {
     CK(cudaSetDevice(ctx->device));
     cudaStream_t st = ctx->stream;
     ctx->gp_n_total = n_veh_total;
-    enqueue_gpool(ctx, 0, 0);          // (the build is complete: nothing to rerun)
+    enqueue_gpool(ctx, 0, 0, false);   // (the build is complete: nothing to rerun)
     CK(cudaMemcpyAsync(ctx->gp_h_state, ctx->gp_tot.p, sizeof(GpState), cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
     CK(cudaGetLastError());

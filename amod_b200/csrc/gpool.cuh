@@ -127,9 +127,10 @@ struct GSlotLayout {        // one staging slot (offsets inside the slot); ident
     i64 cap_veh, cap_ent, cap_ptr, cap_pst;
     i64 o_hdr, o_vehoff, o_kind, o_nfeas, o_cost, o_delay, o_toff, o_soff, o_treq, o_scode, bytes;
     i64 o_cnt;            // int32 [3][cap_veh]: entries / trip requests / stops of each local vehicle (so readers need no dependent loads)
+    i64 o_veh;            // int32 [cap_ent]: local vehicle of every entry (the SBA merge needs it; OSP slices are vehicle-major)
 };
 struct GSeg { const char* src; i64 dst_off; i64 bytes; };
-struct GPush { GSeg seg[10]; int n; };
+struct GPush { GSeg seg[11]; int n; };
 
 // root < 0: every rank receives every slice (all-gather); root >= 0: only `root` does (gather: the rank that hosts the
 // assigner), so a rank sends its slice once instead of `world` times and only the root merges.
@@ -149,11 +150,11 @@ k_gp_push_bulk(GPush P, GPoolLayout L, GSlotLayout S, i64 o_stage, GPoolPeers pe
         for (int d = d0; d < d1; d++) ((i64*)(peers.base[d] + o_stage + (i64)peers.rank * S.bytes + S.o_hdr))[0] = -1;
     if (fits) {
         // live sizes of the segments (the host passes capacities; trim to what this epoch produced)
-        const i64 live[10] = {32, 8 * (n_veh + 1), 4 * n_ent, 4 * n_ent, 8 * n_ent, 8 * n_ent, 8 * (n_ent + 1), 8 * (n_ent + 1),
-                              4 * n_ptr, 4 * n_pst};
+        const i64 live[11] = {32, 8 * (n_veh + 1), 4 * n_ent, 4 * n_ent, 8 * n_ent, 8 * n_ent, 8 * (n_ent + 1), 8 * (n_ent + 1),
+                              4 * n_ptr, 4 * n_pst, 4 * n_ent};
         for (int d = d0; d < d1; d++) {
             char* slot = peers.base[d] + o_stage + (i64)peers.rank * S.bytes;
-            if (tid == 0) { i64* h = (i64*)(slot + S.o_hdr); h[0] = n_veh; h[1] = n_ent; h[2] = n_ptr; h[3] = n_pst; }
+            if (tid == 0) { i64* h = (i64*)(slot + S.o_hdr); h[0] = n_veh; h[1] = n_ent; h[2] = n_ptr; h[3] = n_pst; h[4] = epp->mode; }
             for (int g = 1; g < P.n; g++) {
                 const i64 bytes = live[g];
                 const int4* src = (const int4*)P.seg[g].src;

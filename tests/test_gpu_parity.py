@@ -378,3 +378,21 @@ def test_cuda_cfg5_peak_epoch_snapshot_sba_and_npo_at_named_size():
     assert npo_digest(*b.npo_match(z["npo_idle_nid"], z["npo_pend_onid"])) == dg["npo_digest"]
     oi, op, od = b.npo_match(ep.veh_nid, z["npo_pend_onid"])          # 20,000 x 5,000
     assert oi.size == 5000 and npo_digest(oi, op, od) == dg["npo_full_digest"]
+
+
+def test_cuda_dense_demand_x4_vehicle_sample():
+    """The dense reading of BASELINE.json configs[3] (8,000 vehicles, demand x4: 8,129 considered requests at epoch 62 of the
+    reference simulator, bench_data/cfg4dense_*): every 80th vehicle of the fleet, 44 M schedule evaluations and 353 k pool
+    entries for 100 vehicles, against the oracle fingerprint of exactly those vehicles (bench_data/digests.json)."""
+    import glob
+    from conftest import ROOT
+    f = sorted(glob.glob(os.path.join(ROOT, "bench_data", "cfg4dense_epoch*.npz")))[0]
+    dg = json.load(open(os.path.join(ROOT, "bench_data", "digests.json")))[os.path.basename(f) + "@x1"]
+    ep = marshal.Epoch.from_npz_dict(np.load(f), "ep_")
+    step = dg["sample_step"]
+    sub = ep.take(np.arange(0, ep.n_veh, step))
+    b = builder_for(_grid())
+    got = b.build_pool(sub)
+    got.ent_veh = (got.ent_veh.astype(np.int64) * step).astype(np.int32)      # back to fleet indices, as the oracle reports them
+    assert got.n_entries == dg["n_entries"] and got.stats["n_evals"] == dg["n_evals"] and got.stats["n_lookups"] == dg["n_lookups"]
+    assert marshal.pool_digest(got) == dg["digest"]

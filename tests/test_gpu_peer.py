@@ -146,6 +146,27 @@ def _attached_worker(rank, world, port, out_dir):
                 ok &= o
                 why = why or w
         dist.barrier()
+    # SBA on the same peers: request-major merge on the root (sbam.cuh), a non-monotone search list, OSP and SBA epochs alternating
+    for it, seed in enumerate((21, 22, 23)):
+        ep = synth.random_epoch(tt, n_veh=203, n_pending=60, cap=4, mode=marshal.MODE_SBA, seed=seed, wait_sec=400, near=True, frac_new=0.8, T=4000)
+        if it == 1:
+            ep.search = np.ascontiguousarray(ep.search[::-1])
+        ref = oracle.sba_build(ep, tt)
+        veh_rank, veh_local, sels = adist.balanced_placement(rng.pareto(1.1, size=ep.n_veh) + 1.0, world)
+        pp.attach(root=0, veh_rank=veh_rank, veh_local=veh_local)
+        b.build(ep.take(sels[rank]))
+        if rank == 0:
+            o, w = marshal.pools_equal(pp.fetch(), ref, rtol=0.0, check_kind=True)
+            ok &= o
+            why = why or ("sba: " + w if w else "")
+        dist.barrier()
+        ep2 = synth.random_epoch(tt, n_veh=203, n_pending=40, cap=4, mode=marshal.MODE_OSP, seed=seed + 100, wait_sec=300, near=True, T=4000)
+        b.build(ep2.take(sels[rank]))
+        if rank == 0:
+            o, w = marshal.pools_equal(pp.fetch(), oracle.osp_build(ep2, tt), rtol=0.0, check_kind=True)
+            ok &= o
+            why = why or ("osp after sba: " + w if w else "")
+        dist.barrier()
     np.save(os.path.join(out_dir, f"ok{rank}.npy"), np.array([int(ok)]))
     if not ok:
         open(os.path.join(out_dir, f"why{rank}.txt"), "w").write(why)
