@@ -75,7 +75,7 @@ struct amod_ctx {
     int n_sm = 148;
     std::string err;
     // staging of host epochs
-    DevBuf ep_dev; void* ep_pinned = nullptr; size_t ep_pinned_cap = 0;
+    DevBuf ep_dev, fetch_dev; void* ep_pinned = nullptr; size_t ep_pinned_cap = 0;
     void* fetch_pinned = nullptr; size_t fetch_pinned_cap = 0;
     // device control block + pinned host mirror
     DevBuf ctl; Control* h_ctl = nullptr;
@@ -291,7 +291,7 @@ extern "C" void amod_destroy(amod_ctx* ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     cudaDeviceSynchronize();
-    DevBuf* all[] = {&ctx->ep_dev, &ctx->ctl, &ctx->len0, &ctx->S0, &ctx->s0pos, &ctx->perm_base, &ctx->perm_nitems, &ctx->perm_off, &ctx->perm_cnt, &ctx->perm_pos, &ctx->flag8, &ctx->pos, &ctx->major_off,
+    DevBuf* all[] = {&ctx->ep_dev, &ctx->fetch_dev, &ctx->ctl, &ctx->len0, &ctx->S0, &ctx->s0pos, &ctx->perm_base, &ctx->perm_nitems, &ctx->perm_off, &ctx->perm_cnt, &ctx->perm_pos, &ctx->flag8, &ctx->pos, &ctx->major_off,
                      &ctx->partial, &ctx->scan_sites,
                      &ctx->task_veh[0], &ctx->task_veh[1], &ctx->task_base[0], &ctx->task_base[1], &ctx->task_q[0], &ctx->task_q[1],
                      &ctx->task_nchunk[0], &ctx->task_nchunk[1], &ctx->task_chunk0, &ctx->trip_pos, &ctx->row_desc, &ctx->task_nfeas, &ctx->chunk_cnt,
@@ -868,6 +868,35 @@ extern "C" int amod_pool_view(amod_ctx* ctx, amod_pool* v) {
     return AMOD_OK;
 }
 
+// Page-locked destinations that are laid out back to back (64 B aligned segments, the order of the parts): the live ranges
+// of the nine pool arrays are packed by one kernel and travel as ONE DMA instead of nine (each copy has a fixed latency of
+// several microseconds; PoolBuilder.fetch(reuse=True) allocates its buffers that way).
+struct PackSegs { const char* src[9]; i64 bytes[9]; i64 at[9]; };
+__global__ void k_pack_pool(PackSegs p, char* __restrict__ dst) {
+    const i64 tid = (i64)blockIdx.x * blockDim.x + threadIdx.x, nth = (i64)gridDim.x * blockDim.x;
+    for (int g = 0; g < 9; g++) {
+        const int4* s = (const int4*)p.src[g];
+        int4* d = (int4*)(dst + p.at[g]);
+        const i64 n16 = (p.bytes[g] + 15) >> 4;          // (sources are cudaMalloc'd with slack: reading the last partial 16 B is in bounds)
+        for (i64 x = tid; x < n16; x += nth) d[x] = s[x];
+    }
+}
+struct FetchPart { void* dst; const void* src; size_t bytes; };
+static bool fetch_packed(amod_ctx* ctx, const FetchPart* parts, cudaError_t* ce) {
+    size_t at[9], total = 0;
+    for (int g = 0; g < 9; g++) { at[g] = total; total += (parts[g].bytes + 63) & ~(size_t)63; }
+    for (int g = 0; g < 9; g++)
+        if ((char*)parts[g].dst != (char*)parts[0].dst + at[g] || ((uintptr_t)parts[g].src & 15)) return false;
+    *ce = ctx->fetch_dev.ensure(total + 64);
+    if (*ce != cudaSuccess) return true;
+    PackSegs p;
+    for (int g = 0; g < 9; g++) { p.src[g] = (const char*)parts[g].src; p.bytes[g] = (i64)parts[g].bytes; p.at[g] = (i64)at[g]; }
+    k_pack_pool<<<ctx->n_sm * 2, 256, 0, ctx->stream>>>(p, ctx->fetch_dev.as<char>());
+    *ce = cudaMemcpyAsync(parts[0].dst, ctx->fetch_dev.p, total, cudaMemcpyDeviceToHost, ctx->stream);
+    if (*ce == cudaSuccess) *ce = cudaStreamSynchronize(ctx->stream);
+    return true;
+}
+
 extern "C" int amod_pool_fetch(amod_ctx* ctx, amod_pool* o, int loc) {
     if (!ctx || !o) return AMOD_E_BADARG;
     if (!ctx->pool_valid) return ctx->fail(AMOD_E_BADARG, "no pool has been built on this context");
@@ -890,7 +919,13 @@ extern "C" int amod_pool_fetch(amod_ctx* ctx, amod_pool* o, int loc) {
         CK(cudaStreamSynchronize(st));
         return AMOD_OK;
     }
-    if (loc == AMOD_LOC_PINNED) {      // page-locked host buffers: straight DMA
+    if (loc == AMOD_LOC_PINNED) {      // page-locked host buffers: straight DMA (one copy when they are laid out back to back)
+        {
+            FetchPart fp[9];
+            for (int g = 0; g < 9; g++) { fp[g].dst = parts[g].dst; fp[g].src = parts[g].src; fp[g].bytes = parts[g].bytes; }
+            cudaError_t ce = cudaSuccess;
+            if (P > 0 && fetch_packed(ctx, fp, &ce)) { CK(ce); return AMOD_OK; }
+        }
         for (auto& p : parts) if (p.bytes) CK(cudaMemcpyAsync(p.dst, p.src, p.bytes, cudaMemcpyDeviceToHost, st));
         CK(cudaStreamSynchronize(st));
         return AMOD_OK;
@@ -1219,6 +1254,16 @@ extern "C" int amod_gpool_fetch(amod_ctx* ctx, amod_pool* o) {
                          (long long)v.n_entries, (long long)v.n_trip_reqs, (long long)v.n_stops);
     const size_t P = (size_t)v.n_entries, NT = (size_t)v.n_trip_reqs, NS = (size_t)v.n_stops;
     cudaStream_t st = ctx->stream;
+    if (P) {      // one DMA when the (page-locked) destinations are laid out back to back, in the order of amod_pool_fetch
+        FetchPart fp[9] = {{o->ent_veh, v.ent_veh, 4 * P}, {o->ent_kind, v.ent_kind, 4 * P}, {o->ent_nfeas, v.ent_nfeas, 4 * P},
+                           {o->ent_cost, v.ent_cost, 8 * P}, {o->ent_delay, v.ent_delay, 8 * P}, {o->ent_trip_off, v.ent_trip_off, 8 * (P + 1)},
+                           {o->ent_sche_off, v.ent_sche_off, 8 * (P + 1)}, {o->trip_req, v.trip_req, 4 * NT}, {o->sche_code, v.sche_code, 4 * NS}};
+        cudaPointerAttributes pa;
+        const bool pinned = cudaPointerGetAttributes(&pa, o->ent_veh) == cudaSuccess && pa.type == cudaMemoryTypeHost;
+        cudaGetLastError();
+        cudaError_t ce = cudaSuccess;
+        if (pinned && fetch_packed(ctx, fp, &ce)) { CK(ce); return AMOD_OK; }
+    }
     if (P) {
         CK(cudaMemcpyAsync(o->ent_veh, v.ent_veh, 4 * P, cudaMemcpyDeviceToHost, st));
         CK(cudaMemcpyAsync(o->ent_kind, v.ent_kind, 4 * P, cudaMemcpyDeviceToHost, st));

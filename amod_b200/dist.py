@@ -228,15 +228,8 @@ class PeerPool:
         v = self.view()
         n = {"e": int(v.n_entries), "e1": int(v.n_entries) + 1, "t": int(v.n_trip_reqs), "s": int(v.n_stops)}
         if reuse:
-            bufs = getattr(self, "_host_bufs", None)
-            if bufs is None or any(bufs[name].size < max(n[key], 1) for name, _dt, key in capi.POOL_FIELDS):
-                self._release_host_bufs()
-                bufs = {name: np.empty(max(int(1.5 * n[key]) + 1024, 1), dtype=dt) for name, dt, key in capi.POOL_FIELDS}
-                for a in bufs.values():
-                    a.fill(0)
-                    self.b._check(self.b.lib.amod_host_register(self.b.h, a.ctypes.data, a.nbytes))
-                self._host_bufs = bufs
-            arrs = bufs
+            from .pool import packed_pool_views
+            arrs = packed_pool_views(self, n)
         else:
             arrs = {name: np.empty(max(n[key], 1), dtype=dt) for name, dt, key in capi.POOL_FIELDS}
         o = capi.AmodPool()
@@ -247,8 +240,7 @@ class PeerPool:
         return Pool(**{name: arrs[name][:n[key]] for name, _dt, key in capi.POOL_FIELDS})
 
     def _release_host_bufs(self):
-        bufs = getattr(self, "_host_bufs", None)
-        if bufs and getattr(self.b, "h", None):
-            for a in bufs.values():
-                self.b.lib.amod_host_unregister(self.b.h, a.ctypes.data)
-        self._host_bufs = None
+        buf = getattr(self, "_host_buf", None)
+        if buf is not None and getattr(self.b, "h", None):
+            self.b.lib.amod_host_unregister(self.b.h, buf.ctypes.data)
+        self._host_buf = None

@@ -46,11 +46,10 @@ class PoolBuilder:
         self.lazy_records = False      # seams return LazyPoolRecords (see install(greedy_on_gpu=True))
 
     def _release_host_bufs(self):
-        bufs = getattr(self, "_host_bufs", None)
-        if bufs and getattr(self, "h", None):
-            for a in bufs.values():
-                self.lib.amod_host_unregister(self.h, a.ctypes.data)
-        self._host_bufs = None
+        buf = getattr(self, "_host_buf", None)
+        if buf is not None and getattr(self, "h", None):
+            self.lib.amod_host_unregister(self.h, buf.ctypes.data)
+        self._host_buf = None
 
     def close(self):
         if getattr(self, "h", None):
@@ -106,15 +105,7 @@ class PoolBuilder:
         P, NT, NS = self.pool_sizes()
         n = {"e": P, "e1": P + 1, "t": NT, "s": NS}
         if reuse:
-            bufs = getattr(self, "_host_bufs", None)
-            if bufs is None or any(bufs[name].size < max(n[key], 1) for name, _dt, key in capi.POOL_FIELDS):
-                self._release_host_bufs()
-                bufs = {name: np.empty(max(int(1.5 * n[key]) + 1024, 1), dtype=dt) for name, dt, key in capi.POOL_FIELDS}
-                for a in bufs.values():
-                    a.fill(0)      # touch the pages once, then page-lock them: the fetch is straight DMA
-                    self._check(self.lib.amod_host_register(self.h, a.ctypes.data, a.nbytes))
-                self._host_bufs = bufs
-            arrs = bufs
+            arrs = packed_pool_views(self, n)
         else:
             arrs = {name: np.empty(max(n[key], 1), dtype=dt) for name, dt, key in capi.POOL_FIELDS}
         o = capi.AmodPool()
@@ -224,6 +215,32 @@ class PoolBuilder:
         for vi, ri, dt in zip(oi.tolist(), op.tolist(), od):
             req = pending[ri]
             idle[vi].build_route([(-1, 0, req.onid, system_time_sec + tt_type(dt) + detour_sec)])   # (:37,:62)
+
+
+# order and 64 B alignment of the segments = what amod_pool_fetch / amod_gpool_fetch recognise as "back to back"
+_FETCH_ORDER = ("ent_veh", "ent_kind", "ent_nfeas", "ent_cost", "ent_delay", "ent_trip_off", "ent_sche_off", "trip_req", "sche_code")
+
+
+def packed_pool_views(owner, n: dict) -> dict:
+    """Views of ONE grow-only page-locked buffer owned by `owner` (a PoolBuilder or PeerPool), laid out so that the fetch is a
+    single DMA: segment g starts where segment g-1 ends, rounded up to 64 B.  Overwritten by the next fetch."""
+    builder = getattr(owner, "b", owner)
+    spec = {name: (dt, key) for name, dt, key in capi.POOL_FIELDS}
+    sizes = [(name, np.dtype(spec[name][0]), int(n[spec[name][1]])) for name in _FETCH_ORDER]
+    total = sum((cnt * dt.itemsize + 63) & ~63 for _nm, dt, cnt in sizes) + 64
+    buf = getattr(owner, "_host_buf", None)
+    if buf is None or buf.size < total:
+        if buf is not None:
+            builder.lib.amod_host_unregister(builder.h, buf.ctypes.data)
+        buf = np.zeros(int(1.5 * total) + 4096, dtype=np.uint8)      # touched once, then page-locked
+        builder._check(builder.lib.amod_host_register(builder.h, buf.ctypes.data, buf.nbytes))
+        owner._host_buf = buf
+    base = (-buf.ctypes.data) % 64          # 64 B aligned start
+    out, at = {}, base
+    for name, dt, cnt in sizes:
+        out[name] = buf[at:at + max(cnt, 1) * dt.itemsize].view(dt) if cnt else np.zeros(1, dtype=dt)
+        at += (cnt * dt.itemsize + 63) & ~63
+    return out
 
 
 def _status_value(s) -> int:
