@@ -46,15 +46,19 @@ def merge_sba(parts: list[tuple[Pool, np.ndarray]], n_veh: int, search: np.ndarr
     return cat.take(order)
 
 
-def balanced_placement(cost: np.ndarray, world: int):
+def balanced_placement(cost: np.ndarray, world: int, root: int | None = None, root_share: float = 1.0):
     """Placement of every vehicle on a rank by its expected work (e.g. the size of its share of the previous epochs'
     pools): longest-processing-time-first bin packing, ties towards the emptier rank.  A rank's vehicles keep their
-    global order (the assembled pool is vehicle-major, dispatch_osp.py:107).  Returns (veh_rank, veh_local, sels) where
-    sels[r] are the global indices of rank r's vehicles in local order."""
+    global order (the assembled pool is vehicle-major, dispatch_osp.py:107).  `root_share` < 1 gives the gathering rank
+    that fraction of an even share of the work: it also merges the fleet-wide pool after its own build, so a lighter
+    slice shortens the epoch.  Returns (veh_rank, veh_local, sels) where sels[r] are the global indices of rank r's
+    vehicles in local order."""
     cost = np.asarray(cost, dtype=np.float64)
     n = cost.size
     order = np.argsort(-cost, kind="stable")
     load = np.zeros(world)
+    if root is not None and world > 1 and root_share < 1.0:
+        load[root] = (1.0 - root_share) * float(cost.sum()) / world        # a head start the packing fills last
     count = np.zeros(world, dtype=np.int64)
     veh_rank = np.zeros(n, dtype=np.int32)
     cap = (n + world - 1) // world + 1               # a staging slot holds at most this many vehicles

@@ -315,7 +315,9 @@ def main():
             dist.barrier()
         vr = torch.zeros(n_veh_full, dtype=torch.int32, device=dev)
         if rank == 0 and not os.environ.get("AMOD_BENCH_INTERLEAVED"):
-            veh_rank, _vl, _sels = adist.balanced_placement(cost, world)
+            # the gathering rank also merges: it takes less than an even share of the build (measured: profiles/r02_root_share_ab.txt)
+            root_share = float(os.environ.get("AMOD_BENCH_ROOT_SHARE", {2: 0.7, 4: 0.55, 8: 0.45}.get(world, max(0.3, 1.0 - 0.63 * (world - 1) / world))))
+            veh_rank, _vl, _sels = adist.balanced_placement(cost, world, root=0, root_share=root_share)
             vr.copy_(torch.from_numpy(veh_rank))
         elif rank == 0:
             vr.copy_(torch.from_numpy((np.arange(n_veh_full) % world).astype(np.int32)))
@@ -330,7 +332,7 @@ def main():
         work = make_work(sels)
         peer["pp"].attach(root=0, veh_rank=veh_rank, veh_local=veh_local)
         if not os.environ.get("AMOD_BENCH_INTERLEAVED"):
-            placement = {"veh_rank": veh_rank, "how": "balanced: LPT bin packing on each vehicle's mean pool share over the epochs seen (untimed pass)"}
+            placement = {"veh_rank": veh_rank, "how": "balanced: LPT bin packing on each vehicle's mean pool share over the epochs seen (untimed pass); the gathering rank, which also merges, takes 0.7 / 0.55 / 0.45 of an even share at N = 2 / 4 / 8"}
 
     class DevEp:
         pass
