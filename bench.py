@@ -535,6 +535,7 @@ def main():
                 "algorithmic_bytes_per_launch": alg_bytes / max(k_launches, 1), "launches": k_launches,
                 "avg_launch_ms": k_ms / max(k_launches, 1), "kernel_share_of_step": (k_ms / prof_steps) / step_ms,
                 "l2_gather_peak_gbs": l2_gather_gbs, "frac_of_l2_gather_peak": achieved / l2_gather_gbs,
+                "measured_on": "rank 0" + (" (the gathering rank: it builds less than an even share of the fleet, so its launches are smaller than the other ranks')" if world > 1 else ""),
                 "traffic_source": traffic_info.get(args.config, {}).get("source") if isinstance(traffic_info.get(args.config), dict) else None,
                 "note": "algorithmic bytes = reference travel-time lookups inside the kernel's work x 32 B sector; the table is "
                         "L2-resident so HBM peak is the fallback bound and the measured L2 random-gather rate the real one"}
