@@ -33,7 +33,10 @@ extern "C" {
 #define AMOD_E_LIMIT (-6)    /* input exceeds a compiled limit (stops per schedule, requests)     */
 
 #define AMOD_LOC_HOST 0      /* pointers in the struct are host memory   */
-#define AMOD_LOC_DEVICE 1    /* pointers are device memory of ctx's GPU  */
+#define AMOD_LOC_DEVICE 1    /* pointers are device memory of ctx's GPU.  PRECONDITION: the arrays are well formed (node ids in
+                              * 1..n_nodes, stop codes in -1..2*n_req-1, monotone CSR offsets): host epochs are validated by
+                              * the library (AMOD_E_BADARG), device epochs are not read by the host and are trusted; the
+                              * resident state (amod_state_*) validates what it uploads */
 #define AMOD_LOC_PINNED 2    /* host memory that is page-locked (amod_host_register, cudaHostAlloc, a pinned torch
                               * tensor): amod_pool_fetch copies into it by DMA, without the staging copy */
 
