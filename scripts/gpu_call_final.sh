@@ -1,0 +1,18 @@
+#!/bin/bash
+TAG=${1:-r02final}
+mkdir -p gpurun_out
+timeout 900 python -m pytest tests -m gpu -x -q > gpurun_out/${TAG}_pytest.log 2>&1; echo "pytest rc=$?" >> gpurun_out/${TAG}_pytest.log
+tail -3 gpurun_out/${TAG}_pytest.log
+timeout 300 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/${TAG}_smoke.log 2>&1; echo "smoke rc=$?"; tail -4 gpurun_out/${TAG}_smoke.log
+timeout 300 python bench.py --impl reference --gpus 1 --steps 20 --warmup 5 > gpurun_out/${TAG}_bench_reference.json 2> gpurun_out/${TAG}_bench_reference.err; echo "ref rc=$?"
+timeout 600 python bench.py --gpus 1 --steps 20 --warmup 5 > gpurun_out/${TAG}_bench.json 2> gpurun_out/${TAG}_bench.err; echo "bench rc=$?"
+timeout 600 python bench.py > gpurun_out/${TAG}_bench_default.json 2> gpurun_out/${TAG}_bench_default.err; echo "bench default rc=$?"
+python - <<PY
+import json
+for f in ("bench", "bench_default", "bench_reference"):
+    try:
+        d = json.loads(open("gpurun_out/${TAG}_%s.json" % f).read().strip().splitlines()[-1])
+        print(f, "ms/step %.4f" % d["ms_per_step"], "value %.4g" % d["value"], "e2e", d["e2e"].get("ms_per_step"), "%.4g" % d["e2e"]["value"], "frac", (d.get("roofline") or {}).get("frac"), "traffic", (d.get("roofline") or {}).get("traffic"), "parity", (d.get("parity") or {}).get("ok"), "clocks", d.get("clocks"))
+    except Exception as e:
+        print(f, "no json", e)
+PY
