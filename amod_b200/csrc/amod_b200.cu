@@ -95,7 +95,7 @@ struct amod_ctx {
     i64 cap_trips[MAX_LEVELS], cap_sch[MAX_LEVELS];
     // workspace
     DevBuf len0, S0, s0pos, perm_base, perm_nitems, perm_off, perm_cnt, perm_pos, flag8, pos, major_off, partial, scan_sites, task_veh[2], task_base[2], task_q[2], task_nchunk[2], task_chunk0, trip_pos,
-        row_desc, task_nfeas, chunk_cnt, lane_cnt, chunk_pos, tuples, tup_cnt, tup_pos, hash, row_cnt, row_off, tmp_j, tmp_q, heavy_list, gen_partial, gen_cache, task_first;
+        row_desc, task_nfeas, chunk_cnt, lane_cnt, chunk_pos, tuples, tup_cnt, tup_pos, sq_onid, sq_clp, hash, row_cnt, row_off, tmp_j, tmp_q, heavy_list, gen_partial, gen_cache, task_first;
     LevelBufs lv[MAX_LEVELS];
     // pool
     DevBuf veh_cnt, veh_off, ent_veh, ent_kind, ent_nfeas, ent_tlen, ent_slen, ent_src, ent_trip, ent_cost, ent_delay,
@@ -130,6 +130,7 @@ struct amod_ctx {
     std::vector<cudaEvent_t> sync_pool;      // fork / join edges between the two branches
     int n_launches = 0;
     unsigned hash_slots = 0;                 // slots per trip lookup table (two tables in `hash`)
+    size_t sq_n = 0;                         // searched requests of the epoch (sizes the search cache even when the fleet is empty)
     cudaAccessPolicyWindow l2_window; bool l2_window_valid = false, l2_on = false;
     int base_len_hint[3] = {0, 0, 0};        // longest current schedule seen so far per mode (SBA / OSP_NR): keeps graph + strides stable
 
@@ -295,7 +296,7 @@ extern "C" void amod_destroy(amod_ctx* ctx) {
                      &ctx->partial, &ctx->scan_sites,
                      &ctx->task_veh[0], &ctx->task_veh[1], &ctx->task_base[0], &ctx->task_base[1], &ctx->task_q[0], &ctx->task_q[1],
                      &ctx->task_nchunk[0], &ctx->task_nchunk[1], &ctx->task_chunk0, &ctx->trip_pos, &ctx->row_desc, &ctx->task_nfeas, &ctx->chunk_cnt,
-                     &ctx->lane_cnt, &ctx->chunk_pos, &ctx->tuples, &ctx->tup_cnt, &ctx->tup_pos, &ctx->hash, &ctx->row_cnt, &ctx->row_off, &ctx->tmp_j, &ctx->tmp_q, &ctx->heavy_list, &ctx->gen_partial, &ctx->gen_cache, &ctx->task_first,
+                     &ctx->lane_cnt, &ctx->chunk_pos, &ctx->tuples, &ctx->tup_cnt, &ctx->tup_pos, &ctx->sq_onid, &ctx->sq_clp, &ctx->hash, &ctx->row_cnt, &ctx->row_off, &ctx->tmp_j, &ctx->tmp_q, &ctx->heavy_list, &ctx->gen_partial, &ctx->gen_cache, &ctx->task_first,
                      &ctx->veh_cnt, &ctx->veh_off, &ctx->ent_veh, &ctx->ent_kind, &ctx->ent_nfeas, &ctx->ent_tlen, &ctx->ent_slen,
                      &ctx->ent_src, &ctx->ent_trip, &ctx->ent_cost, &ctx->ent_delay, &ctx->trip_off, &ctx->sche_off, &ctx->trip_req,
                      &ctx->sche_code, &ctx->ga_pos, &ctx->ga_rank, &ctx->ga_order, &ctx->ga_state, &ctx->ga_bv, &ctx->ga_br, &ctx->ga_tv, &ctx->ga_tr,
@@ -461,6 +462,10 @@ static int ensure_buffers(amod_ctx* ctx, int V, i64 n_screen, int max_level, con
     }
     CK(ctx->partial.ensure(2 * 8 * (size_t)(ctx->n_sm + 1)));
     CK(ctx->scan_sites.ensure(scan_sites_bytes(ctx)));
+    {   // searched requests' origin / latest pick-up by search position (levels.cuh SearchCache)
+        const size_t Qs = V > 0 ? (size_t)(n_screen / V) : 0;
+        CK(ctx->sq_onid.ensure(4 * (std::max(Qs, ctx->sq_n) + 1))); CK(ctx->sq_clp.ensure(8 * (std::max(Qs, ctx->sq_n) + 1)));
+    }
     for (int w = 0; w < 2; w++) {
         CK(ctx->task_veh[w].ensure(4 * T)); CK(ctx->task_base[w].ensure(4 * T)); CK(ctx->task_q[w].ensure(4 * T));
         CK(ctx->task_nchunk[w].ensure(4 * T));
@@ -531,6 +536,7 @@ static int enqueue_build(amod_ctx* ctx, int mode, int cap, Table<TT> tt, int max
     const int GEV = ctx->n_sm * GRID_EVAL_PER_SM;  // the insertion search: exactly the resident blocks, one wave
     size_t n_ev = 0;
     int* len0 = ctx->len0.as<int>();
+    const SearchCache sc{ctx->sq_onid.as<int>(), ctx->sq_clp.as<double>()};
 
     cudaStream_t sd = ctx->side;
     const int half = ctx->n_sm / 2;            // blocks per scan of the pair scan (k_scan2_b)
@@ -543,16 +549,16 @@ static int enqueue_build(amod_ctx* ctx, int mode, int cap, Table<TT> tt, int max
     // ---- level 0: basic schedules -----------------------------------------------------------------
     if (cap <= 5) {      // at most 120 orderings per vehicle: one warp per vehicle is enough
         launch_k(st, GE, WARPS_PER_BLOCK * 32, k_basic<TT, 0>, d, tt, ls.lv[0], len0, ctx->S0.as<int>(), nullptr, ctl, dstats,
-                                                            scan_site(ctx, MAX_LEVELS), ctx->n_sm);
+                                                            scan_site(ctx, MAX_LEVELS), ctx->n_sm, sc);
         // the level-0 store is written beside the reachability screen, which only needs the counts (S0)
         CK(edge(st, sd));
         scan_fin(ctx, InVehInt{ctx->S0.as<int>(), d}, ctx->s0pos.as<i64>(),
                  FinCountI64{&ctl->n_sch[0], ls.lv[0].cap_sch, &ctl->need_sch[0], &ctl->overflow, OVF_SCH}, (i64*)scan_site(ctx, MAX_LEVELS), sd);
         launch_k(sd, GE, WARPS_PER_BLOCK * 32, k_basic<TT, 1>, d, tt, ls.lv[0], len0, ctx->S0.as<int>(), ctx->s0pos.as<i64>(), ctl, dstats,
-                                                            nullptr, ctx->n_sm);
+                                                            nullptr, ctx->n_sm, sc);
         ctx->n_launches += 2;
     } else {             // up to cap! orderings: 32 permutation ranks per warp work item, spread over the GPU
-        launch_k(st, G, 256, k_perm_prep, d, ls.lv[0], len0, ctx->perm_base.as<int>(), ctx->perm_nitems.as<int>(), dstats);
+        launch_k(st, G, 256, k_perm_prep, d, ls.lv[0], len0, ctx->perm_base.as<int>(), ctx->perm_nitems.as<int>(), dstats, sc);
         scan_dev(ctx, InVehInt{ctx->perm_nitems.as<int>(), d}, ctx->perm_off.as<i64>(), FinPermItems{ctl, ctx->cap_items});
         launch_k(st, GE, WARPS_PER_BLOCK * 32, k_perm_items<TT, 0>, d, tt, ls.lv[0], ctl, len0, ctx->perm_base.as<int>(), ctx->perm_off.as<i64>(),
                                                                 ctx->perm_cnt.as<int>(), nullptr, dstats);
@@ -569,7 +575,7 @@ static int enqueue_build(amod_ctx* ctx, int mode, int cap, Table<TT> tt, int max
         const int G1 = std::max(1, 32 / (ls.lv[0].stride + 1));
         CK(cudaEventRecord(get_event(ctx, EV_SCREEN), st));
         launch_k(st, ctx->n_sm * 16, SCREEN_WARPS * 32, k_screen_count<TT>, d, tt, ctx->S0.as<int>(), ctx->flag8.as<unsigned>(), ctx->pos.as<i64>(),
-                                                                         scan_site(ctx, MAX_LEVELS + 1), ctx->n_sm);
+                                                                         scan_site(ctx, MAX_LEVELS + 1), ctx->n_sm, sc);
         scan_fin(ctx, InMajorPacked{ctx->pos.as<i64>(), d}, ctx->major_off.as<i64>(),
                  FinTasksRows{ctl, 0, ctx->cap_tasks, ctx->cap_rows, ctx->cap_chunks, G1}, (i64*)scan_site(ctx, MAX_LEVELS + 1));
         launch_k(st, GE, WARPS_PER_BLOCK * 32, k_screen_fill, d, ctl, ctx->S0.as<int>(), ctx->flag8.as<unsigned>(), ctx->major_off.as<i64>(),
@@ -627,7 +633,7 @@ static int enqueue_build(amod_ctx* ctx, int mode, int cap, Table<TT> tt, int max
         CK(edge(st, sd));                                         // fork
         const TripHash th = hash_of(k);
         launch_k(sd, G, 256, k_compact_trips, ctl, cur, tv, tb, tq, tnf, ctx->trip_pos.as<i64>(), prev, lv, th, dstats, d, sba,
-                                          ctx->major_off.as<i64>(), ctx->task_first.as<i64>());
+                                          ctx->major_off.as<i64>(), ctx->task_first.as<i64>(), ctx->gen_partial.as<unsigned long long>(), GE);
         cudaEvent_t named = get_sync_event(ctx, n_sync++);        // the level's trips have their rows (s0, nfeas)
         CK(cudaEventRecord(named, sd));
         // main: costs to their encounter positions -> list order per trip -> schedules straight into their final rows
@@ -721,6 +727,7 @@ static int build_impl(amod_ctx* ctx, const amod_epoch* ep, int loc, amod_stats* 
     for (;; attempt++) {
         if (attempt > 48) return ctx->fail(AMOD_E_NOMEM, "pool build did not converge after %d regrow attempts", attempt);
         const unsigned long long r0 = g_reallocs;
+        ctx->sq_n = (size_t)d.n_search;
         CKR(ensure_buffers(ctx, V, (i64)V * d.n_search, max_level, stride, &ls, &pb));
         if (g_reallocs != r0) ctx->buf_gen++;
         memset(h, 0, sizeof(Control));

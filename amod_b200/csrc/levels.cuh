@@ -34,13 +34,25 @@ __device__ __forceinline__ void unrank_perm(int p, int L, int* out /*positions*/
     }
 }
 
+// The searched requests' origin and latest pick-up time gathered once per epoch into arrays indexed by search position, so that
+// the reachability screen (one lookup per vehicle x request) reads them coalesced instead of through search[] -> onid[] / clp[].
+struct SearchCache { int* onid; double* clp; };
+__device__ __forceinline__ void fill_search_cache(const DEpoch& ep, const SearchCache& sc) {
+    const int stride = gridDim.x * blockDim.x;
+    for (int s = blockIdx.x * blockDim.x + threadIdx.x; s < ep.n_search; s += stride) {
+        const int q = ep.search[s];
+        sc.onid[s] = ep.onid[q]; sc.clp[s] = ep.clp[q];
+    }
+}
+
 template <typename TT, int MODE>
 __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32)
 k_basic(const DEpoch* __restrict__ epp, Table<TT> tt, Level lv0, int* __restrict__ len0, int* __restrict__ S0, const i64* __restrict__ s0pos,
-        const Control* __restrict__ ctl, Stats* stats, unsigned long long* __restrict__ part, int part_vg) {
+        const Control* __restrict__ ctl, Stats* stats, unsigned long long* __restrict__ part, int part_vg, SearchCache sc) {
     pdl_enter();
     const DEpoch& ep = *epp;
     const int lane = threadIdx.x & 31;
+    if (MODE == 0) fill_search_cache(ep, sc);
     if (MODE == 1 && ctl->overflow) return;          // level-0 store overflowed
     const int seg_veh = (int)scan_seg_len(ep.n_veh, part_vg);     // MODE 0 leaves the block sums of the scan over S0
     unsigned long long evals = 0, lookups = 0;
@@ -150,9 +162,10 @@ __device__ __forceinline__ bool perm_feasible(const DEpoch& ep, const Table<TT>&
 }
 
 __global__ void k_perm_prep(const DEpoch* __restrict__ epp, Level lv0, int* __restrict__ len0, int* __restrict__ perm_base,
-                            int* __restrict__ n_items, Stats* stats) {
+                            int* __restrict__ n_items, Stats* stats, SearchCache sc) {
     pdl_enter();
     const DEpoch& ep = *epp;
+    fill_search_cache(ep, sc);
     for (int v = blockIdx.x * blockDim.x + threadIdx.x; v < ep.n_veh; v += gridDim.x * blockDim.x) {
         const int s0 = ep.veh_sche_off[v], s1 = ep.veh_sche_off[v + 1];
         const bool perms = (ep.mode == AMOD_MODE_OSP) && ep.veh_status[v] == 2;
@@ -260,7 +273,7 @@ __global__ void k_perm_rows(const DEpoch* __restrict__ epp, Level lv0, const Con
 template <typename TT>
 __global__ void __launch_bounds__(SCREEN_WARPS * 32)
 k_screen_count(const DEpoch* __restrict__ epp, Table<TT> tt, const int* __restrict__ S0, unsigned* __restrict__ bits,
-               i64* __restrict__ major_cnt, unsigned long long* __restrict__ part, int part_vg) {
+               i64* __restrict__ major_cnt, unsigned long long* __restrict__ part, int part_vg, SearchCache sc) {
     pdl_enter();
     __shared__ int s_cnt[SCREEN_WARPS], s_rows[SCREEN_WARPS];
     const DEpoch& ep = *epp;
@@ -287,9 +300,8 @@ k_screen_count(const DEpoch* __restrict__ epp, Table<TT> tt, const int* __restri
                         ok[u] = !(d + ep.veh_t[mn] + ep.T > m_a);
                         S[u] = S0[mn];
                     } else {     // major = vehicle, minor = searched request
-                        const int q = ep.search[mn];
-                        const double d = tt(m_node, ep.onid[q]);
-                        ok[u] = !(d + m_a + ep.T > ep.clp[q]);
+                        const double d = tt(m_node, sc.onid[mn]);
+                        ok[u] = !(d + m_a + ep.T > sc.clp[mn]);
                         S[u] = S0[mj];
                     }
                 }
@@ -503,8 +515,10 @@ __global__ void k_compact_trips(const Control* __restrict__ ctl, int which, cons
                                 const int* __restrict__ task_nfeas,
                                 const i64* __restrict__ trip_pos /* exclusive (trips | schedules << 32) before each task */, Level prev, Level cur,
                                 TripHash th, Stats* stats, const DEpoch* __restrict__ epp, int sba,
-                                const i64* __restrict__ major_off, const i64* __restrict__ task_first) {
+                                const i64* __restrict__ major_off, const i64* __restrict__ task_first,
+                                unsigned long long* __restrict__ gen_partial, int n_gen_partial) {
     pdl_enter();
+    for (int x = blockIdx.x * blockDim.x + threadIdx.x; x < n_gen_partial; x += gridDim.x * blockDim.x) gen_partial[x] = 0ull;   // segment sums of the candidate count that follows
     const int n = (ctl->n_trips[cur.k] && !ctl->overflow) ? ctl->n_tasks[which] : 0;
     const int stride = gridDim.x * blockDim.x;
     if (!sba && !ctl->overflow) {
@@ -756,28 +770,24 @@ k_gen_count(const DEpoch* __restrict__ epp, const Control* __restrict__ ctl, Lev
             int* __restrict__ row_cnt, int2* __restrict__ row_cache, unsigned long long* __restrict__ blk_partial,
             int* __restrict__ next_hash, unsigned next_hash_size) {
     pdl_enter();
-    __shared__ unsigned long long s_sum;
     __shared__ int s_j[WARPS_PER_BLOCK][32];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const int n = ctl->overflow ? 0 : ctl->n_trips[prev.k];
     const unsigned gtid = blockIdx.x * blockDim.x + threadIdx.x, gsz = gridDim.x * blockDim.x;
     // the lookup table the NEXT level will build into (the other buffer; its last readers are two kernels back)
     for (unsigned x = gtid; x < next_hash_size; x += gsz) next_hash[x] = -1;
-    if (threadIdx.x == 0) s_sum = 0ull;
-    __syncthreads();
-    int lo, hi;
-    gen_segment(n, &lo, &hi);
-    unsigned long long mine = 0ull;
-    for (int t = lo + wib; t < hi; t += WARPS_PER_BLOCK) {
+    // Rows are dealt out cyclically over ALL warps of the grid (a vehicle's trips are consecutive rows and a heavy vehicle's rows scan
+    // several 32-wide slices of its size-1 trips: contiguous rows per block would leave whole blocks with nothing but heavy rows); the
+    // emit pass owns contiguous segments, so every row adds its (tasks | rows << 32) to the sum of the segment it belongs to
+    // (blk_partial is zeroed by k_compact_trips, the kernel before this one on the branch).
+    const int seg = max(1, (n + (int)gridDim.x - 1) / (int)gridDim.x);
+    for (int t = blockIdx.x * WARPS_PER_BLOCK + wib; t < n; t += gridDim.x * WARPS_PER_BLOCK) {
         const int cnt = gen_row<0>(l1, prev, th, t, lane, 0, nullptr, nullptr, s_j[wib], row_cache + (i64)t * GEN_INLINE);
         if (lane == 0) {
             row_cnt[t] = cnt;
-            mine += (unsigned long long)cnt | ((unsigned long long)cnt * (unsigned long long)prev.nfeas[t]) << 32;
+            if (cnt) atomicAdd(&blk_partial[t / seg], (unsigned long long)cnt | ((unsigned long long)cnt * (unsigned long long)prev.nfeas[t]) << 32);
         }
     }
-    if (lane == 0 && mine) atomicAdd(&s_sum, mine);
-    __syncthreads();
-    if (threadIdx.x == 0) blk_partial[blockIdx.x] = s_sum;
 }
 
 __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32)
