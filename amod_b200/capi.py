@@ -85,7 +85,19 @@ EXPORTS = ("amod_create", "amod_destroy", "amod_last_error", "amod_version", "am
            "amod_gather_bench", "amod_gpool_create", "amod_gpool_open_peers", "amod_pool_veh_counts", "amod_gpool_scatter",
            "amod_gpool_view", "amod_gpool_fetch", "amod_set_graph", "amod_gpool_assemble", "amod_greedy_assign",
            "amod_gpool_attach", "amod_gpool_detach", "amod_routes_upload", "amod_routes_build",
-           "amod_state_create", "amod_state_add_requests", "amod_state_update_vehicles", "amod_state_build", "amod_state_download")
+           "amod_state_create", "amod_state_add_requests", "amod_state_update_vehicles", "amod_state_build", "amod_state_download",
+           "amod_fleet_create", "amod_fleet_add_requests", "amod_fleet_advance", "amod_fleet_events", "amod_fleet_set_status",
+           "amod_fleet_apply", "amod_fleet_apply_selected", "amod_fleet_build", "amod_fleet_array")
+
+# amod_fleet_array selectors (include/amod_b200.h enum AMOD_FLEET_*): name -> (index, dtype, shape key)
+FLEET_ARRAYS = {name: (i, dt, shape) for i, (name, dt, shape) in enumerate((
+    ("nid", "i4", "V"), ("lng", "f8", "V"), ("lat", "f8", "V"), ("t_to_nid", "f8", "V"), ("d_to_nid", "f8", "V"), ("tnid", "i4", "V"),
+    ("load", "i4", "V"), ("status", "i4", "V"), ("state_time", "f8", "V"), ("t", "f8", "V"), ("d", "f8", "V"), ("stats", "f8", "8V"),
+    ("has_step", "u1", "V"), ("step_t", "f8", "V"), ("step_d", "f8", "V"), ("step_u", "i4", "V"), ("step_v", "i4", "V"),
+    ("sche_len", "i4", "V"), ("sche_code", "i4", "VS"), ("sche_onboard", "u1", "VS"), ("reb_node", "i4", "V"), ("reb_ddl", "f8", "V"),
+    ("leg_head", "i4", "V"), ("leg_n", "i4", "V"), ("leg_rid", "i4", "VL"), ("leg_pod", "i4", "VL"), ("leg_tnid", "i4", "VL"),
+    ("leg_ddl", "f8", "VL"), ("leg_t", "f8", "VL"), ("leg_d", "f8", "VL"), ("leg_sb", "i4", "VL"), ("leg_se", "i4", "VL"),
+    ("req_status", "i4", "R"), ("req_tp", "f8", "R"), ("req_td", "f8", "R")))}
 
 _lib = None
 
@@ -164,6 +176,18 @@ def load_library(path: str | None = None) -> C.CDLL:
     lib.amod_state_download.restype = C.c_int
     lib.amod_set_graph.argtypes = [C.c_void_p, C.c_int]
     lib.amod_set_graph.restype = C.c_int
+    lib.amod_fleet_create.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.amod_fleet_add_requests.argtypes = [C.c_void_p, C.c_int32, C.c_int32] + [C.c_void_p] * 6
+    lib.amod_fleet_advance.argtypes = [C.c_void_p, C.c_int64, C.c_int32, C.POINTER(C.c_int32)]
+    lib.amod_fleet_events.argtypes = [C.c_void_p] + [C.c_void_p] * 5 + [C.c_int32]
+    lib.amod_fleet_set_status.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32]
+    lib.amod_fleet_apply.argtypes = [C.c_void_p, C.c_int32] + [C.c_void_p] * 5
+    lib.amod_fleet_apply_selected.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32]
+    lib.amod_fleet_build.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_int64, C.c_int32, C.POINTER(AmodStats), C.POINTER(C.c_int32)]
+    lib.amod_fleet_array.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_int64]
+    for name in EXPORTS:
+        if name.startswith("amod_fleet_"):
+            getattr(lib, name).restype = C.c_int
     if path is None:
         _lib = lib
     return lib

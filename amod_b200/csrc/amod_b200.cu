@@ -19,6 +19,7 @@
 #include "pool.cuh"
 #include "routes.cuh"
 #include "state.cuh"
+#include "fleet.cuh"
 #include "sbam.cuh"
 #include "scan.cuh"
 
@@ -124,6 +125,9 @@ struct amod_ctx {
     DevBuf fs_nid, fs_t, fs_load, fs_status, fs_rnode, fs_rddl, fs_len, fs_code, fs_onb, fs_off64, fs_off32, fs_ccode, fs_conb, fs_search, fs_stage, fs_err;
     DevBuf rq_onid, rq_dnid, rq_clp, rq_cld, rq_tr, rq_ts;
     void* fs_pinned = nullptr; size_t fs_pinned_cap = 0;
+    // fleet simulation state (8f-3: advance + apply on the device, fleet.cuh)
+    FleetSim fl; bool fl_valid = false; std::vector<DevBuf> fl_bufs; DevBuf fl_call, fl_pos, fl_stage, fl_rids;
+    int fl_n_events = 0; int ga_n_sel = -1;     // ga_n_sel: selected pairs of the last greedy assignment (on the device in ga_sel / ga_order)
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     std::vector<cudaEvent_t> ev_pool;
     cudaStream_t side = nullptr;             // second branch of the epoch graph (next level's candidates)
@@ -682,7 +686,7 @@ template <typename TT>
 static int build_impl(amod_ctx* ctx, const amod_epoch* ep, int loc, amod_stats* out_stats, Table<TT> tt) {
     cudaStream_t st = ctx->stream;
     CK(cudaSetDevice(ctx->device));
-    ctx->pool_valid = false;
+    ctx->pool_valid = false; ctx->ga_n_sel = -1;
     DEpoch d;
     CK(cudaEventRecord(ctx->ev0, st));
     CKR(upload_epoch(ctx, ep, loc, &d));
@@ -1349,6 +1353,7 @@ extern "C" int amod_greedy_assign(amod_ctx* ctx, int32_t* order_out, int32_t* se
     CK(cudaStreamSynchronize(st));
     CK(cudaGetLastError());
     *n_sel = (int32_t)h[0];
+    ctx->ga_n_sel = (int)h[0];
     if (n_rounds) *n_rounds = rounds;
     return AMOD_OK;
 }
@@ -1609,16 +1614,10 @@ extern "C" int amod_state_update_vehicles(amod_ctx* ctx, int32_t n, const int32_
     return AMOD_OK;
 }
 
-extern "C" int amod_state_build(amod_ctx* ctx, int32_t mode, int32_t cap, int64_t T, const int32_t* search_rids, int32_t n_search, amod_stats* stats) {
-    if (!ctx || n_search < 0 || (n_search && !search_rids)) return AMOD_E_BADARG;
-    if (!ctx->fs_valid) return ctx->fail(AMOD_E_BADARG, "amod_state_create first");
-    for (int i = 0; i < n_search; i++)
-        if (search_rids[i] < 0 || search_rids[i] >= ctx->fs_req_n) return ctx->fail(AMOD_E_BADARG, "search[%d] names an unknown request", i);
-    CK(cudaSetDevice(ctx->device));
+// the pool build over the resident rows; the searched request ids are already in ctx->fs_search (device)
+static int state_build_dev(amod_ctx* ctx, int32_t mode, int32_t cap, int64_t T, int32_t n_search, amod_stats* stats) {
     cudaStream_t st = ctx->stream;
     const FleetState& fs = ctx->fs;
-    CK(ctx->fs_search.ensure(4 * (size_t)std::max(n_search, 1)));
-    if (n_search) CK(cudaMemcpyAsync(ctx->fs_search.p, search_rids, 4 * (size_t)n_search, cudaMemcpyHostToDevice, st));
     CK(ctx->partial.ensure(2 * 8 * (size_t)(ctx->n_sm + 1)));
     scan_dev(ctx, InStateLen{fs.len, (i64)fs.n_veh}, ctx->fs_off64.as<i64>(), FinNone{});
     k_state_csr<<<std::max(1, std::min(ctx->n_sm * 4, (fs.n_veh + 256) / 256)), 256, 0, st>>>(fs, ctx->fs_off64.as<i64>(), ctx->fs_off32.as<int>(),
@@ -1632,6 +1631,18 @@ extern "C" int amod_state_build(amod_ctx* ctx, int32_t mode, int32_t cap, int64_
     ep.req_onid = ctx->rq_onid.as<int>(); ep.req_dnid = ctx->rq_dnid.as<int>(); ep.req_clp = ctx->rq_clp.as<double>(); ep.req_cld = ctx->rq_cld.as<double>();
     ep.req_tr = ctx->rq_tr.as<double>(); ep.req_ts = ctx->rq_ts.as<double>(); ep.search = ctx->fs_search.as<int>();
     return dispatch_tt(ctx, [&](auto tt) { return build_impl(ctx, &ep, AMOD_LOC_DEVICE, stats, tt); });
+}
+
+extern "C" int amod_state_build(amod_ctx* ctx, int32_t mode, int32_t cap, int64_t T, const int32_t* search_rids, int32_t n_search, amod_stats* stats) {
+    if (!ctx || n_search < 0 || (n_search && !search_rids)) return AMOD_E_BADARG;
+    if (!ctx->fs_valid) return ctx->fail(AMOD_E_BADARG, "amod_state_create first");
+    for (int i = 0; i < n_search; i++)
+        if (search_rids[i] < 0 || search_rids[i] >= ctx->fs_req_n) return ctx->fail(AMOD_E_BADARG, "search[%d] names an unknown request", i);
+    CK(cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    CK(ctx->fs_search.ensure(4 * (size_t)std::max(n_search, 1)));
+    if (n_search) CK(cudaMemcpyAsync(ctx->fs_search.p, search_rids, 4 * (size_t)n_search, cudaMemcpyHostToDevice, st));
+    return state_build_dev(ctx, mode, cap, T, n_search, stats);
 }
 
 extern "C" int amod_state_download(amod_ctx* ctx, int32_t* nid, double* t, int32_t* load, int32_t* status, int32_t* reb_node, double* reb_ddl,
@@ -1651,6 +1662,8 @@ extern "C" int amod_state_download(amod_ctx* ctx, int32_t* nid, double* t, int32
     CK(cudaStreamSynchronize(st));
     return AMOD_OK;
 }
+
+#include "fleet_api.cuh"
 
 extern "C" int amod_gather_bench(amod_ctx* ctx, const int32_t* o_dev, const int32_t* d_dev, float* out_dev, int64_t n, int iters,
                                  double* ms) {

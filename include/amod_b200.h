@@ -258,6 +258,51 @@ int amod_state_build(amod_ctx* ctx, int32_t mode, int32_t cap, int64_t T, const 
 int amod_state_download(amod_ctx* ctx, int32_t* nid, double* t, int32_t* load, int32_t* status, int32_t* reb_node, double* reb_ddl,
                         int32_t* sche_len, int32_t* sche_code /*[n_veh*max_stops]*/, uint8_t* sche_onboard);
 
+/* ---- SURVEY.md 8f-3 (second half): the vehicles' state advance, the request life cycle and the apply step ON THE DEVICE ----
+ * replaces, for a simulator that keeps its epoch state in HBM:
+ *   Veh.move_to_time + update_service_status_after_veh_finish_a_leg / pop_leg / pop_step / cut_step   src/simulator/vehicle.py:73-226
+ *   Platform.upd_vehs_and_reqs_stat_to_time (pick / drop info, walk-away scan)                          src/simulator/platform.py:213-233
+ *   upd_schedule_for_vehicles_in_selected_vt_pairs + Veh.build_route / add_leg / clear_route            src/dispatcher/scheduling.py:110-119,
+ *                                                                                                       vehicle.py:231-310
+ *   the considered-request list of assign_orders_through_osp                                            src/dispatcher/dispatch_osp.py:33-37
+ * Needs amod_routes_upload first.  The fleet owns a resident state (amod_state_*): its vehicle rows are what amod_fleet_build
+ * feeds to the unchanged pool pipeline, so one epoch is
+ *   amod_fleet_advance(T) -> amod_fleet_add_requests(arrivals) -> amod_fleet_build -> amod_greedy_assign ->
+ *   amod_fleet_apply_selected -> amod_npo_match -> amod_fleet_apply(rebalancing stops)
+ * with only the arrivals going up and the `done` events coming down.  Request status values are the reference's
+ * (types.py:11-16: 1 PENDING 2 PICKING 3 ONBOARD 4 COMPLETE 5 WALKAWAY), vehicle status types.py:18-21.  All pointers are host
+ * memory.  Results are bit-identical to the reference's float64 arithmetic (tests/golden/trace_fleet_*.npz). */
+int amod_fleet_create(amod_ctx* ctx, int32_t n_veh, int32_t max_stops_per_veh, int32_t max_route_steps_per_veh, int32_t request_capacity,
+                      const int32_t* start_nid /*[n_veh] platform.py:50-55*/, const double* node_lng, const double* node_lat /*[n_nodes]*/);
+/* Req.__init__ (request.py:25-41) for the requests first_rid .. first_rid+n-1 (ids are consecutive, platform.py:262) */
+int amod_fleet_add_requests(amod_ctx* ctx, int32_t first_rid, int32_t n, const int32_t* onid, const int32_t* dnid, const double* clp,
+                            const double* cld, const double* tr, const double* ts);
+/* platform.py:213-233 to time T; update_stats = verify_the_current_epoch_is_in_the_main_study_horizon(T).  *n_events = number of
+ * (rid, pod, time) tuples the vehicles' move_to_time returned; amod_fleet_events copies them out (any order; (veh, seq) sorts
+ * them into the reference's). */
+int amod_fleet_advance(amod_ctx* ctx, int64_t T, int32_t update_stats, int32_t* n_events);
+int amod_fleet_events(amod_ctx* ctx, int32_t* veh, int32_t* seq, int32_t* rid, int32_t* pod, double* time, int32_t cap);
+int amod_fleet_set_status(amod_ctx* ctx, const int32_t* rids, int32_t n, int32_t status);
+/* Veh.build_route for a batch of vehicles (each at most once): stop codes 2*rid + drop-off, -1 = rebalancing stop (reb_node[i], reb_ddl[i]) */
+int amod_fleet_apply(amod_ctx* ctx, int32_t n, const int32_t* veh, const int32_t* sche_off /*[n+1]*/, const int32_t* sche_code,
+                     const int32_t* reb_node /*[n]*/, const double* reb_ddl /*[n]*/);
+/* the apply step on the device pool: entries == NULL applies the selection of the last amod_greedy_assign without it leaving the
+ * device; mark_picking: the trips' requests become PICKING (scheduling.py:116-117); reset_considered: PICKING -> PENDING first
+ * (dispatch_osp.py:77-78) */
+int amod_fleet_apply_selected(amod_ctx* ctx, const int32_t* entries, int32_t n, int32_t mark_picking, int32_t reset_considered);
+/* pool build from the fleet state; OSP searches the considered requests (found on the device), SBA / OSP-NR the last n_new */
+int amod_fleet_build(amod_ctx* ctx, int32_t mode, int32_t cap, int64_t T, int32_t n_new, amod_stats* stats, int32_t* n_search);
+/* one array of the fleet state -> host (mirror / tests); bytes must be the array's exact size */
+enum { AMOD_FLEET_NID = 0 /*i32[V]*/, AMOD_FLEET_LNG, AMOD_FLEET_LAT, AMOD_FLEET_T_TO_NID, AMOD_FLEET_D_TO_NID /*f64[V]*/, AMOD_FLEET_TNID,
+       AMOD_FLEET_LOAD, AMOD_FLEET_STATUS /*i32[V]*/, AMOD_FLEET_STATE_TIME, AMOD_FLEET_T, AMOD_FLEET_D /*f64[V]*/,
+       AMOD_FLEET_STATS /*f64[8][V]: Ds Ts Ds_empty Ts_empty Dr Tr Lt Ld*/, AMOD_FLEET_HAS_STEP /*u8[V]*/, AMOD_FLEET_STEP_T, AMOD_FLEET_STEP_D /*f64[V]*/,
+       AMOD_FLEET_STEP_U, AMOD_FLEET_STEP_V, AMOD_FLEET_SCHE_LEN /*i32[V]*/, AMOD_FLEET_SCHE_CODE /*i32[V][max_stops]*/,
+       AMOD_FLEET_SCHE_ONBOARD /*u8[V][max_stops]*/, AMOD_FLEET_REB_NODE /*i32[V]*/, AMOD_FLEET_REB_DDL /*f64[V]*/, AMOD_FLEET_LEG_HEAD,
+       AMOD_FLEET_LEG_N /*i32[V]*/, AMOD_FLEET_LEG_RID, AMOD_FLEET_LEG_POD, AMOD_FLEET_LEG_TNID /*i32[V][max_stops+1]*/, AMOD_FLEET_LEG_DDL,
+       AMOD_FLEET_LEG_T, AMOD_FLEET_LEG_D /*f64[V][max_stops+1]*/, AMOD_FLEET_LEG_SB, AMOD_FLEET_LEG_SE /*i32[V][max_stops+1]*/,
+       AMOD_FLEET_REQ_STATUS /*i32[n_req]*/, AMOD_FLEET_REQ_TP, AMOD_FLEET_REQ_TD /*f64[n_req]*/ };
+int amod_fleet_array(amod_ctx* ctx, int32_t which, void* out_host, int64_t bytes);
+
 /* Raw travel-time gather out[i] = tt[o[i]][d[i]] (route_functions.py:22-25): used by the
  * L2-gather roofline microbenchmark.  Device pointers.  Returns device ms in *ms. */
 int amod_gather_bench(amod_ctx* ctx, const int32_t* o_dev, const int32_t* d_dev, float* out_dev,
