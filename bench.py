@@ -570,6 +570,14 @@ def main():
         if pyref:
             cpu["python_reference"] = pyref
         line["cpu_baseline"] = cpu
+    if not (args.no_cpu or world > 1) and args.config == "cfg2":
+        # beyond the metric: one whole simulated epoch with the fleet resident on the device, for information
+        try:
+            sys.path.insert(0, os.path.join(ROOT, "scripts"))
+            import prof_fleet
+            line["fleet_epoch"] = prof_fleet.measure(veh=2000, cap=4, epochs=110, tail=40, device=local)
+        except Exception as exc:      # never costs the bench line
+            line["fleet_epoch"] = {"error": f"{type(exc).__name__}: {exc}"[:300]}
     print_json(line)
     if world > 1:
         dist.destroy_process_group()
