@@ -34,8 +34,10 @@ class RoadGraph:
 
 
 def make_road_graph(n_nodes: int = N_NODES_MANHATTAN, seed: int = 0, nx: int | None = None,
-                    with_paths: bool = False, n_stations: int = 101) -> RoadGraph:
-    """Directed 4-neighbour grid, per-direction jittered edge times quantised to 1/8 s."""
+                    with_paths: bool = False, n_stations: int = 101, edge_times: tuple | None = None) -> RoadGraph:
+    """Directed 4-neighbour grid, per-direction jittered edge times quantised to 1/8 s.  `edge_times`: draw every edge's time
+    from these exact values instead (e.g. (10, 15, 30): paths then end exactly on epoch boundaries, the tie cases of
+    vehicle.py:104-127)."""
     from scipy.sparse import csr_matrix
     from scipy.sparse.csgraph import dijkstra
 
@@ -57,6 +59,8 @@ def make_road_graph(n_nodes: int = N_NODES_MANHATTAN, seed: int = 0, nx: int | N
     src, dst, length = np.concatenate(src), np.concatenate(dst), np.concatenate(length)
     speed = 5.5 * rng.uniform(0.7, 1.3, size=src.size)         # m/s, per directed edge
     t_edge = np.maximum(np.round(length / speed * 8.0), 1.0) / 8.0
+    if edge_times is not None:
+        t_edge = rng.choice(np.asarray(edge_times, dtype=np.float64), size=src.size)
     w = csr_matrix((t_edge, (src, dst)), shape=(n_nodes, n_nodes))
     if with_paths:
         tt64, pred0 = dijkstra(w, directed=True, return_predecessors=True)

@@ -15,7 +15,19 @@ A_EXACT = ("nid", "lng", "lat", "t_to_nid", "d_to_nid", "tnid", "load", "status"
            "Ds", "Ts", "Ds_empty", "Ts_empty", "Dr", "Tr", "Lt", "Ld", "has_step", "step_t", "step_d", "step_u", "step_v")
 
 
+_graphs = {}
+
+
 class FleetTrace:
+    def graph(self):
+        """The road graph the trace was recorded on (tests/golden/make_trace_fleet.py: gspec)."""
+        from amod_b200 import synth
+        sp = self.spec
+        key = (sp["n_nodes"], sp["seed"], tuple(sp.get("edge_times") or ()))
+        if key not in _graphs:
+            _graphs[key] = synth.make_road_graph(sp["n_nodes"], seed=sp["seed"], with_paths=True, edge_times=sp.get("edge_times"))
+        return _graphs[key]
+
     def __init__(self, which: str):
         z = np.load(os.path.join(GOLDEN, f"trace_fleet_{which}.npz"))
         self.z = {k: z[k] for k in z.files}

@@ -5,6 +5,8 @@ apply step), so that the device-resident fleet (amod_fleet_*, amod_b200/fleet.py
 
     python tests/golden/make_trace_fleet.py sba     # cfg1: SBA + greedy + NPO, 100 vehicles cap 4, 258 epochs (~2 min)
     python tests/golden/make_trace_fleet.py osp     # OSP + greedy + NPO, 40 vehicles cap 4, 110 epochs (warm-up / wind-down in SBA)
+    python tests/golden/make_trace_fleet.py ties    # SBA, 30 vehicles cap 3 on a 144-node grid whose edges take exactly 10 / 15 / 30 s:
+                                                    # legs and steps end exactly on epoch boundaries (step.t == dT, pct == 1, leg.t == dT)
 
 Everything recorded comes from the reference's own code (greedy_assignment in place of the Gurobi ILP as README.md:29
 sanctions; the OSP wall-clock cut-off disabled as everywhere in this repository).  Per epoch:
@@ -57,14 +59,20 @@ class Ragged:
 
 def record(which: str):
     cap = 4
-    graph = synth.make_road_graph(seed=0, with_paths=True)
+    gspec = dict(kind="grid", n_nodes=synth.N_NODES_MANHATTAN, seed=0)
+    trip = 600.0
     t0 = 18 * 3600 + 30 * 60
     if which == "sba":
         fleet, disp, warm, main, wind, n_req = 100, "SBA", 30, 60, 39, 1700
-    else:
+    elif which == "osp":
         fleet, disp, warm, main, wind, n_req = 40, "OSP", 10, 35, 10, 520
+    else:       # "ties": every edge takes 10, 15 or 30 s, so legs and steps end exactly on the 30 s epoch boundaries
+        fleet, disp, warm, main, wind, n_req = 30, "SBA", 5, 25, 5, 300
+        gspec = dict(kind="grid", n_nodes=144, seed=7, edge_times=[10.0, 15.0, 30.0])
+        trip, cap = 150.0, 3
+    graph = synth.make_road_graph(gspec["n_nodes"], seed=gspec["seed"], with_paths=True, edge_times=gspec.get("edge_times"))
     horizon_min = warm + main + wind
-    on, dn, tm = synth.make_request_stream(graph, n_req, t0, t0 + (horizon_min + 6) * 60, seed=1, mean_trip_sec=600.0)
+    on, dn, tm = synth.make_request_stream(graph, n_req, t0, t0 + (horizon_min + 6) * 60, seed=1, mean_trip_sec=trip)
     ref = rh.setup_reference(f"/tmp/amod_ref_trace_fleet_{which}", graph, on, dn, tm, fleet_size=fleet, capacity=cap, dispatcher=disp,
                              warmup_min=warm, main_min=main, winddown_min=wind)
     Veh = ref.platform.Veh
@@ -197,8 +205,7 @@ def record(which: str):
     out["T"] = Ts
     out["start_nid"] = np.asarray([int(graph.stations[int(i * len(graph.stations) / V)]) for i in range(V)], dtype=np.int32)
     out["result"] = np.asarray(pf.main_sim_result, dtype=np.float64)
-    out["spec"] = np.array(json.dumps(dict(kind="grid", n_nodes=graph.n_nodes, seed=0, cap=cap, fleet=V, dispatcher=disp,
-                                           warmup_min=warm, main_min=main, winddown_min=wind)))
+    out["spec"] = np.array(json.dumps(dict(gspec, cap=cap, fleet=V, dispatcher=disp, warmup_min=warm, main_min=main, winddown_min=wind)))
     path = os.path.join(HERE, f"trace_fleet_{which}.npz")
     np.savez_compressed(path, **out)
     print(f"{which}: {E} epochs in {time.time() - t:.0f}s, {len(reqs)} requests, result {pf.main_sim_result}, "

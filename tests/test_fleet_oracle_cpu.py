@@ -8,19 +8,16 @@ import pytest
 HERE = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, os.path.join(os.path.dirname(HERE), "oracle"))
 
-from amod_b200 import synth
 import fleet_oracle
 import fleet_util
 
 
-@pytest.fixture(scope="module")
-def graph():
-    return synth.make_road_graph(seed=0, with_paths=True)
-
-
-@pytest.mark.parametrize("which", ["sba", "osp"])
-def test_fleet_oracle_reproduces_the_reference_horizon(which, graph):
+@pytest.mark.parametrize("which", ["sba", "osp", "ties"])
+def test_fleet_oracle_reproduces_the_reference_horizon(which):
+    """`ties`: a grid whose edges take exactly 10 / 15 / 30 s, so steps and legs end exactly on the 30 s epoch boundaries
+    (step.t == dT: pct == 1 and a zero-length remainder; leg.t == dT: the step loop finishes the leg, vehicle.py:104-127)."""
     tr = fleet_util.FleetTrace(which)
+    graph = tr.graph()
     fleet = fleet_oracle.FleetOracle(graph, tr.z["start_nid"])
     n = fleet_util.replay_open_loop(tr, fleet)
     assert n == tr.E

@@ -32,25 +32,37 @@ def builder(graph):
     b.close()
 
 
+_builders = {}
+
+
+def _builder_for(tr):
+    g = tr.graph()
+    if id(g) not in _builders:
+        _builders[id(g)] = PoolBuilder(g.tt)
+    return g, _builders[id(g)]
+
+
 def _final(tr, x, n):
     fu._same("final Tp", x["req_tp"], tr.z["req_tp"], n)
     fu._same("final Td", x["req_td"], tr.z["req_td"], n)
     fu._same("final status", x["req_status"], tr.z["req_status"], n)
 
 
-@pytest.mark.parametrize("which", ["sba", "osp"])
-def test_device_fleet_replays_the_reference_horizon_open_loop(which, graph, builder):
+@pytest.mark.parametrize("which", ["sba", "osp", "ties"])
+def test_device_fleet_replays_the_reference_horizon_open_loop(which):
     tr = fu.FleetTrace(which)
+    graph, builder = _builder_for(tr)
     sim = DeviceFleetSim(builder, graph, tr.z["start_nid"], max_stops=24, max_route_steps=4096, request_capacity=4096)
     n = fu.replay_open_loop(tr, sim)
     assert n == tr.E
     _final(tr, sim.export(), n)
 
 
-@pytest.mark.parametrize("which", ["sba", "osp"])
-def test_device_fleet_runs_the_reference_horizon_closed_loop(which, graph, builder):
+@pytest.mark.parametrize("which", ["sba", "osp", "ties"])
+def test_device_fleet_runs_the_reference_horizon_closed_loop(which):
     """Only the arrivals go in; everything else happens on the device, for the whole horizon."""
     tr = fu.FleetTrace(which)
+    graph, builder = _builder_for(tr)
     z, cap = tr.z, tr.spec["cap"]
     sim = DeviceFleetSim(builder, graph, z["start_nid"], max_stops=24, max_route_steps=4096, request_capacity=4096)
     main_mode = marshal.MODE_OSP if tr.spec["dispatcher"] == "OSP" else marshal.MODE_SBA
@@ -117,3 +129,50 @@ def test_device_fleet_at_cfg2_scale_against_the_cpu_restatement(graph, builder):
         for c in ("t", "d", "tnid", "status", "n_legs", "leg_rid", "leg_pod", "leg_tnid", "leg_ddl", "leg_t", "leg_d", "leg_n_steps"):
             fu._same("end." + c, x[c], y[c], e)
     assert picked > 200 and dropped > 0          # the fleet really moved and served
+
+
+def test_fleet_errors_are_reported_not_swallowed(graph, builder):
+    """Error behaviour of the C-ABI: capacity, bad arguments and broken invariants come back as codes + messages."""
+    from amod_b200 import capi
+    from amod_b200.pool import AmodError
+    start = graph.stations[:8].astype(np.int32)
+    # a route that does not fit the per-vehicle step region -> AMOD_E_CAPACITY naming the size needed
+    sim = DeviceFleetSim(builder, graph, start, max_stops=8, max_route_steps=8, request_capacity=64)
+    far = int(np.argmax(graph.tt[start[0] - 1])) + 1
+    sim.add_requests(0, [far], [int(start[0])], [0.0], [float(graph.tt[far - 1, start[0] - 1])], [420.0], [5000.0])
+    with pytest.raises(AmodError) as ei:
+        sim.apply([0], [0, 2], [0, 0], [1, -1], [far, int(start[0])], [420.0, 5000.0])
+    assert ei.value.code == capi.E_CAPACITY and "steps" in str(ei.value)
+    # requests must arrive in id order; unknown vehicles / requests are refused
+    sim = DeviceFleetSim(builder, graph, start, max_stops=8, max_route_steps=2048, request_capacity=64)
+    with pytest.raises(AmodError):
+        sim.add_requests(3, [far], [far], [0.0], [0.0], [420.0], [840.0])
+    with pytest.raises(AmodError):
+        sim.apply([99], [0, 0], [], [], [], [])
+    with pytest.raises(AmodError):
+        sim.apply([0], [0, 1], [5], [1], [far], [420.0])          # request 5 was never added
+    with pytest.raises(AmodError):
+        sim.set_status([7], 2)
+    # picking up a request that is not PICKING trips the reference's assertion (request.py:49) as an error, not silently
+    sim = DeviceFleetSim(builder, graph, start, max_stops=8, max_route_steps=2048, request_capacity=64)
+    near = int(start[0])
+    sim.add_requests(0, [near], [far], [0.0], [float(graph.tt[near - 1, far - 1])], [420.0], [9000.0])
+    sim.apply([0], [0, 2], [0, 0], [1, -1], [near, far], [420.0, 9000.0])     # status left PENDING on purpose
+    with pytest.raises(AmodError) as ei:
+        sim.advance(30, False)
+    assert "invariant" in str(ei.value)
+
+
+def test_idle_fleet_and_empty_epochs(graph, builder):
+    """No requests at all: vehicles stay idle at their stations, time advances, every build is the V basic pairs."""
+    start = graph.stations[:16].astype(np.int32)
+    sim = DeviceFleetSim(builder, graph, start, max_stops=8, max_route_steps=1024, request_capacity=64)
+    for e in range(3):
+        T = 30 * (e + 1)
+        ev = sim.advance(T, True)
+        assert ev["veh"].size == 0
+        n_sel = sim.dispatch(marshal.MODE_OSP if e else marshal.MODE_SBA, 4, T, 0)
+        assert n_sel == 16 and sim.rebalance(T) == 0
+        x = sim.export()
+        assert (x["status"] == 1).all() and (x["state_time"] == T).all() and (x["nid"] == start).all() and x["sche_len"].sum() == 0
+        assert x["Ts"].sum() == 0 and x["n_legs"].sum() == 0
