@@ -45,8 +45,7 @@ class DeviceFleetSim:
                                                      start.ctypes.data, lng.ctypes.data, lat.ctypes.data))
         self.n_req = 0
         # the host keeps the immutable request fields it uploaded (to name stops in export(); not a fallback for anything)
-        self._onid = np.zeros(0, np.int32); self._dnid = np.zeros(0, np.int32)
-        self._clp = np.zeros(0, np.float64); self._cld = np.zeros(0, np.float64)
+        self._req_cols = [np.zeros(1024, np.int32), np.zeros(1024, np.int32), np.zeros(1024, np.float64), np.zeros(1024, np.float64)]
         self.last_stats: dict = {}
         self.last_n_search = 0
 
@@ -57,9 +56,17 @@ class DeviceFleetSim:
         n = int(cols[0].size)
         b = self.b
         b._check(b.lib.amod_fleet_add_requests(b.h, int(first), n, *[c.ctypes.data for c in cols]))
-        self.n_req = int(first) + n
-        self._onid = np.concatenate([self._onid, cols[0]]); self._dnid = np.concatenate([self._dnid, cols[1]])
-        self._clp = np.concatenate([self._clp, cols[2]]); self._cld = np.concatenate([self._cld, cols[3]])
+        top = int(first) + n
+        if top > self._req_cols[0].size:
+            self._req_cols = [np.concatenate([a, np.zeros(max(top, 2 * a.size) - a.size, a.dtype)]) for a in self._req_cols]
+        for a, c in zip(self._req_cols, cols[:4]):
+            a[int(first):top] = c
+        self.n_req = top
+
+    _onid = property(lambda self: self._req_cols[0][:self.n_req])
+    _dnid = property(lambda self: self._req_cols[1][:self.n_req])
+    _clp = property(lambda self: self._req_cols[2][:self.n_req])
+    _cld = property(lambda self: self._req_cols[3][:self.n_req])
 
     # ---- platform.py:213-233 ---------------------------------------------------------------------------------------
     def advance(self, T, update_stats: bool) -> dict:
