@@ -1307,8 +1307,10 @@ extern "C" int amod_greedy_assign(amod_ctx* ctx, int32_t* order_out, int32_t* se
     Control* ctl = ctx->ctl.as<Control>();
     const PoolBufs pb = pool_bufs_of(ctx);
     const size_t Pz = (size_t)P;
-    CK(ctx->ga_pos.ensure(8 * (GA_BUCKETS * Pz + 2))); CK(ctx->ga_rank.ensure(4 * Pz)); CK(ctx->ga_order.ensure(4 * Pz));
-    CK(ctx->ga_state.ensure(Pz)); CK(ctx->ga_bv.ensure(4 * (size_t)(V + 1))); CK(ctx->ga_br.ensure(4 * (size_t)(R + 1)));
+    const int nb = std::max(1, ctx->h_ctl->max_tlen + 1);      // score = len(trip): buckets 0 .. the pool's longest trip
+    if (nb > GA_BUCKETS) return ctx->fail(AMOD_E_LIMIT, "a pair score is outside 0..%d", GA_BUCKETS - 1);
+    CK(ctx->ga_pos.ensure(8 * ((size_t)nb * Pz + 2))); CK(ctx->ga_rank.ensure(4 * Pz)); CK(ctx->ga_order.ensure(4 * Pz));
+    CK(ctx->ga_state.ensure(Pz)); CK(ctx->ga_bv.ensure(8 * (size_t)(V + 1))); CK(ctx->ga_br.ensure(8 * (size_t)(R + 1)));
     CK(ctx->ga_tv.ensure((size_t)V + 1)); CK(ctx->ga_tr.ensure((size_t)R + 1)); CK(ctx->ga_sel.ensure(4 * Pz)); CK(ctx->ga_cnt.ensure(32));
     CK(ctx->partial.ensure(2 * 8 * (size_t)(ctx->n_sm + 1)));
     const int G = ctx->n_sm * 2;
@@ -1318,19 +1320,22 @@ extern "C" int amod_greedy_assign(amod_ctx* ctx, int32_t* order_out, int32_t* se
     int* n_left = ctx->ga_cnt.as<int>();
     CK(cudaMemsetAsync(ctx->ga_cnt.p, 0, 32, st));
     // 1. rank = position after the stable sort by -score (counting sort through one prefix sum)
-    scan_dev(ctx, InScoreBucket{pb.ent_tlen, ctl}, pos, FinNone{});
+    scan_dev(ctx, InScoreBucket{pb.ent_tlen, ctl, nb}, pos, FinNone{});
     k_ga_init<<<G, 256, 0, st>>>(ctl, pb.ent_tlen, pos, ctx->ga_rank.as<int>(), ctx->ga_order.as<int>(), ctx->ga_state.as<uint8_t>(),
-                                ctx->ga_bv.as<int>(), V, ctx->ga_br.as<int>(), R, ctx->ga_tv.as<uint8_t>(), ctx->ga_tr.as<uint8_t>(), err);
-    // 2. rounds
+                                ctx->ga_bv.as<int>(), V, ctx->ga_br.as<int>(), R, ctx->ga_tv.as<uint8_t>(), ctx->ga_tr.as<uint8_t>(), err, nb);
+    // 2. rounds: keep, then drop + post the survivors' ranks into the other set of minima (two launches per round)
     int rounds = 0;
+    int* bv[2] = {ctx->ga_bv.as<int>(), ctx->ga_bv.as<int>() + V};
+    int* br[2] = {ctx->ga_br.as<int>(), ctx->ga_br.as<int>() + R};
+    k_ga_min<<<G, 256, 0, st>>>(ctl, pb, ctx->ga_rank.as<int>(), ctx->ga_state.as<uint8_t>(), bv[0], br[0]);
     for (;;) {
         for (int rep = 0; rep < 4; rep++) {       // four rounds per host check
+            const int cur = rounds & 1;
             if (rep == 3) CK(cudaMemsetAsync(n_left, 0, 4, st));
-            k_ga_min<<<G, 256, 0, st>>>(ctl, pb, ctx->ga_rank.as<int>(), ctx->ga_state.as<uint8_t>(), ctx->ga_bv.as<int>(), ctx->ga_br.as<int>());
-            k_ga_keep<<<G, 256, 0, st>>>(ctl, pb, ctx->ga_rank.as<int>(), ctx->ga_state.as<uint8_t>(), ctx->ga_bv.as<int>(), ctx->ga_br.as<int>(),
+            k_ga_keep<<<G, 256, 0, st>>>(ctl, pb, ctx->ga_rank.as<int>(), ctx->ga_state.as<uint8_t>(), bv[cur], br[cur],
                                         ctx->ga_tv.as<uint8_t>(), ctx->ga_tr.as<uint8_t>());
-            k_ga_drop<<<G, 256, 0, st>>>(ctl, pb, ctx->ga_state.as<uint8_t>(), ctx->ga_tv.as<uint8_t>(), ctx->ga_tr.as<uint8_t>(),
-                                        ctx->ga_bv.as<int>(), V, ctx->ga_br.as<int>(), R, n_left);
+            k_ga_drop<<<G, 256, 0, st>>>(ctl, pb, ctx->ga_rank.as<int>(), ctx->ga_state.as<uint8_t>(), ctx->ga_tv.as<uint8_t>(), ctx->ga_tr.as<uint8_t>(),
+                                        bv[cur], V, br[cur], R, bv[cur ^ 1], br[cur ^ 1], n_left);
             rounds++;
         }
         int left = 0;

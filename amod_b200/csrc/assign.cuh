@@ -3,7 +3,8 @@
 // and keeps a pair iff its vehicle and all its requests are still free.  With the total order
 // (rank in the sorted list) this equals: a pair is kept iff no kept pair of smaller rank shares a resource.
 // Rounds: every undecided pair that is the smallest-rank undecided pair on its vehicle and on each of its
-// requests is kept (all of them at once); pairs touching a taken resource are dropped; repeat.
+// requests is kept (all of them at once); pairs touching a taken resource are dropped; repeat.  A round is two launches
+// (k_ga_keep, k_ga_drop): the survivors post their ranks for the next round while they are being counted.
 #pragma once
 #include "common.cuh"
 #include "pool.cuh"
@@ -13,30 +14,32 @@
 #define GA_KEPT 1
 #define GA_DROPPED 2
 
-// stable counting sort by descending score: scan over [bucket][entry] flags
+// stable counting sort by descending score: scan over [bucket][entry] flags; nb = highest score of the pool + 1 buckets
+// (Control::max_tlen, left by k_pool_meta), at most GA_BUCKETS
 struct InScoreBucket {
-    const int* tlen; const Control* ctl;
-    __device__ __forceinline__ i64 size() const { return (i64)GA_BUCKETS * ctl->n_ent; }
+    const int* tlen; const Control* ctl; int nb;
+    __device__ __forceinline__ i64 size() const { return (i64)nb * ctl->n_ent; }
     __device__ __forceinline__ i64 operator()(i64 i) const {
         const i64 P = ctl->n_ent;
         const int b = (int)(i / P);
-        return tlen[i - (i64)b * P] == GA_BUCKETS - 1 - b;
+        return tlen[i - (i64)b * P] == nb - 1 - b;
     }
 };
 
 __global__ void k_ga_init(const Control* __restrict__ ctl, const int* __restrict__ tlen, const i64* __restrict__ pos, int* __restrict__ rank,
                           int* __restrict__ order, uint8_t* __restrict__ state, int* best_v, int n_veh, int* best_r, int n_req,
-                          uint8_t* taken_v, uint8_t* taken_r, unsigned long long* err) {
+                          uint8_t* taken_v, uint8_t* taken_r, unsigned long long* err, int nb) {
     const i64 P = ctl->n_ent;
     const i64 stride = (i64)gridDim.x * blockDim.x;
     for (i64 e = (i64)blockIdx.x * blockDim.x + threadIdx.x; e < P; e += stride) {
         const int s = tlen[e];
-        if (s < 0 || s >= GA_BUCKETS) { atomicOr(err, 1ull); continue; }
-        const int r = (int)pos[(i64)(GA_BUCKETS - 1 - s) * P + e];
+        if (s < 0 || s >= nb) { atomicOr(err, 1ull); continue; }
+        const int r = (int)pos[(i64)(nb - 1 - s) * P + e];
         rank[e] = r; order[r] = (int)e; state[e] = GA_UNDECIDED;
     }
-    for (i64 x = (i64)blockIdx.x * blockDim.x + threadIdx.x; x < n_veh; x += stride) { best_v[x] = 0x7fffffff; taken_v[x] = 0; }
-    for (i64 x = (i64)blockIdx.x * blockDim.x + threadIdx.x; x < n_req; x += stride) { best_r[x] = 0x7fffffff; taken_r[x] = 0; }
+    // (both sets of per-resource minima: best_v / best_r hold 2 x n entries)
+    for (i64 x = (i64)blockIdx.x * blockDim.x + threadIdx.x; x < n_veh; x += stride) { best_v[x] = 0x7fffffff; best_v[n_veh + x] = 0x7fffffff; taken_v[x] = 0; }
+    for (i64 x = (i64)blockIdx.x * blockDim.x + threadIdx.x; x < n_req; x += stride) { best_r[x] = 0x7fffffff; best_r[n_req + x] = 0x7fffffff; taken_r[x] = 0; }
 }
 
 __global__ void k_ga_min(const Control* __restrict__ ctl, PoolBufs pb, const int* __restrict__ rank, const uint8_t* __restrict__ state,
@@ -67,9 +70,11 @@ __global__ void k_ga_keep(const Control* __restrict__ ctl, PoolBufs pb, const in
     }
 }
 
-// drop pairs touching a taken resource, reset the per-resource minima for the next round, count what is left
-__global__ void k_ga_drop(const Control* __restrict__ ctl, PoolBufs pb, uint8_t* __restrict__ state, const uint8_t* __restrict__ taken_v,
-                          const uint8_t* __restrict__ taken_r, int* best_v, int n_veh, int* best_r, int n_req, int* n_left) {
+// drop pairs touching a taken resource and count what is left; the survivors already post their rank to the NEXT round's
+// per-resource minima (two sets of minima alternate), and this round's set is reset for the round after: two launches per round
+__global__ void k_ga_drop(const Control* __restrict__ ctl, PoolBufs pb, const int* __restrict__ rank, uint8_t* __restrict__ state,
+                          const uint8_t* __restrict__ taken_v, const uint8_t* __restrict__ taken_r, int* best_v, int n_veh, int* best_r, int n_req,
+                          int* next_v, int* next_r, int* n_left) {
     const i64 P = ctl->n_ent;
     const i64 stride = (i64)gridDim.x * blockDim.x;
     int left = 0;
@@ -77,7 +82,11 @@ __global__ void k_ga_drop(const Control* __restrict__ ctl, PoolBufs pb, uint8_t*
         if (state[e] != GA_UNDECIDED) continue;
         bool hit = taken_v[pb.ent_veh[e]];
         for (i64 t = pb.trip_off[e]; t < pb.trip_off[e + 1] && !hit; t++) hit = taken_r[pb.trip_req[t]];
-        if (hit) state[e] = GA_DROPPED; else left++;
+        if (hit) { state[e] = GA_DROPPED; continue; }
+        left++;
+        const int r = rank[e];
+        atomicMin(&next_v[pb.ent_veh[e]], r);
+        for (i64 t = pb.trip_off[e]; t < pb.trip_off[e + 1]; t++) atomicMin(&next_r[pb.trip_req[t]], r);
     }
     for (i64 x = (i64)blockIdx.x * blockDim.x + threadIdx.x; x < n_veh; x += stride) best_v[x] = 0x7fffffff;
     for (i64 x = (i64)blockIdx.x * blockDim.x + threadIdx.x; x < n_req; x += stride) best_r[x] = 0x7fffffff;

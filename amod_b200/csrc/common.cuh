@@ -94,7 +94,7 @@ struct Control {
     i64 need_tuples;      // feasible-insertion records per launch region (x regions) the search would have needed
     i64 need_tasks, need_chunks, need_trips[MAX_LEVELS], need_sch[MAX_LEVELS], need_ent, need_ptr, need_pst;
     int max_level_nonempty;
-    int pad;
+    int max_tlen;         // longest trip of a pool entry (= the highest score the greedy assigner will see, assign.cuh)
     int n_heavy[MAX_LEVELS];  // trips with very many feasible schedules, classified by a whole block each
     int pad2;
     Stats stats;

@@ -91,6 +91,7 @@ k_pool_meta(const DEpoch* __restrict__ epp, LevelSet ls, const int* __restrict__
             int np = 0;
             for (int k = ep.veh_sche_off[v]; k < ep.veh_sche_off[v + 1]; k++) np += ep.sche_code[k] >= 0 && !(ep.sche_code[k] & 1);
             pb.ent_veh[e] = v; pb.ent_kind[e] = AMOD_KIND_CURRENT; pb.ent_nfeas[e] = 1; pb.ent_tlen[e] = np; pb.ent_slen[e] = cur_len;
+            if (np > ctl->max_tlen) atomicMax(&ctl->max_tlen, np);
             pb.ent_src[e] = SRC_INPUT; pb.ent_trip[e] = v;
             atomicAdd(&part[e / seg], (unsigned long long)np); atomicAdd(&part[part_vg + e / seg], (unsigned long long)cur_len);
         }
@@ -98,6 +99,7 @@ k_pool_meta(const DEpoch* __restrict__ epp, LevelSet ls, const int* __restrict__
     for (int k = 1; k < ls.n; k++) {
         const Level& lv = ls.lv[k];
         const int n = ctl->n_trips[k];
+        if (n > 0 && gtid == 0) atomicMax(&ctl->max_tlen, k);
         for (int base = blockIdx.x * blockDim.x; base < n; base += stride) {      // (whole warps iterate together)
             const int t = base + threadIdx.x;
             const bool valid = t < n;
