@@ -87,7 +87,8 @@ struct amod_ctx {
     GraphSlot graphs[3];
     unsigned long long buf_gen = 0;
     bool use_graph = true;
-    int gen_inline = GEN_INLINE;   // AMOD_GEN_INLINE=0 forces candidate recomputation in k_gen_emit (tests)
+    int gen_pairs_occ[3] = {0, 0, 0};   // resident blocks per SM of k_gen_pairs<4 / 8 / AMOD_MAX_TRIP>
+    int gen_wide = 0;              // AMOD_GEN_WIDE=1: k_gen_emit ranks every row's pairs through memory, the path of rows with > 32 pairs (tests)
     int heavy_min = -1;            // AMOD_HEAVY_MIN overrides the block-per-trip classification threshold (tests)
     int level_hint[3] = {0, 0, 0};   // deepest non-empty trip level seen so far (+1 is searched before looking further)
     // capacities (grown from the sizes an epoch needed; persisted across epochs)
@@ -96,7 +97,7 @@ struct amod_ctx {
     i64 cap_trips[MAX_LEVELS], cap_sch[MAX_LEVELS];
     // workspace
     DevBuf len0, S0, s0pos, perm_base, perm_nitems, perm_off, perm_cnt, perm_pos, flag8, pos, major_off, partial, scan_sites, task_veh[2], task_base[2], task_q[2], task_nchunk[2], task_chunk0, trip_pos,
-        row_desc, task_nfeas, chunk_cnt, lane_cnt, chunk_pos, tuples, tup_cnt, tup_pos, sq_onid, sq_clp, hash, row_cnt, row_off, tmp_j, tmp_q, heavy_list, gen_partial, gen_cache, task_first;
+        row_desc, task_nfeas, chunk_cnt, lane_cnt, chunk_pos, tuples, tup_cnt, tup_pos, sq_onid, sq_clp, hash, row_cnt, row_off, gen_pairs, heavy_list, gen_partial, task_first;
     LevelBufs lv[MAX_LEVELS];
     // pool
     DevBuf veh_cnt, veh_off, ent_veh, ent_kind, ent_nfeas, ent_tlen, ent_slen, ent_src, ent_trip, ent_cost, ent_delay,
@@ -284,7 +285,7 @@ extern "C" int amod_create(amod_ctx** out, int device, int n_nodes, const void* 
     if ((e = ctx->d_epoch.ensure(sizeof(DEpoch))) != cudaSuccess) return bail("cudaMalloc", e);
     ctx->use_graph = getenv("AMOD_NO_GRAPH") == nullptr;
     if (const char* hm = getenv("AMOD_HEAVY_MIN")) ctx->heavy_min = atoi(hm);
-    if (const char* gi = getenv("AMOD_GEN_INLINE")) ctx->gen_inline = std::max(0, std::min(GEN_INLINE, atoi(gi)));
+    if (const char* gi = getenv("AMOD_GEN_WIDE")) ctx->gen_wide = atoi(gi) != 0;
     apply_l2_policy(ctx, ctx->stream);
     apply_l2_policy(ctx, ctx->side);         // k_basic<fill>, candidate generation: the side branch looks travel times up too
     cudaEventCreate(&ctx->ev0); cudaEventCreate(&ctx->ev1);
@@ -300,7 +301,7 @@ extern "C" void amod_destroy(amod_ctx* ctx) {
                      &ctx->partial, &ctx->scan_sites,
                      &ctx->task_veh[0], &ctx->task_veh[1], &ctx->task_base[0], &ctx->task_base[1], &ctx->task_q[0], &ctx->task_q[1],
                      &ctx->task_nchunk[0], &ctx->task_nchunk[1], &ctx->task_chunk0, &ctx->trip_pos, &ctx->row_desc, &ctx->task_nfeas, &ctx->chunk_cnt,
-                     &ctx->lane_cnt, &ctx->chunk_pos, &ctx->tuples, &ctx->tup_cnt, &ctx->tup_pos, &ctx->sq_onid, &ctx->sq_clp, &ctx->hash, &ctx->row_cnt, &ctx->row_off, &ctx->tmp_j, &ctx->tmp_q, &ctx->heavy_list, &ctx->gen_partial, &ctx->gen_cache, &ctx->task_first,
+                     &ctx->lane_cnt, &ctx->chunk_pos, &ctx->tuples, &ctx->tup_cnt, &ctx->tup_pos, &ctx->sq_onid, &ctx->sq_clp, &ctx->hash, &ctx->row_cnt, &ctx->row_off, &ctx->gen_pairs, &ctx->heavy_list, &ctx->gen_partial, &ctx->task_first,
                      &ctx->veh_cnt, &ctx->veh_off, &ctx->ent_veh, &ctx->ent_kind, &ctx->ent_nfeas, &ctx->ent_tlen, &ctx->ent_slen,
                      &ctx->ent_src, &ctx->ent_trip, &ctx->ent_cost, &ctx->ent_delay, &ctx->trip_off, &ctx->sche_off, &ctx->trip_req,
                      &ctx->sche_code, &ctx->ga_pos, &ctx->ga_rank, &ctx->ga_order, &ctx->ga_state, &ctx->ga_bv, &ctx->ga_br, &ctx->ga_tv, &ctx->ga_tr,
@@ -476,7 +477,7 @@ static int ensure_buffers(amod_ctx* ctx, int V, i64 n_screen, int max_level, con
     }
     CK(ctx->task_chunk0.ensure(8 * (T + 2))); CK(ctx->trip_pos.ensure(8 * (T + 2)));
     CK(ctx->row_desc.ensure(2 * sizeof(RowDesc) * (size_t)ctx->cap_rows)); CK(ctx->task_nfeas.ensure(4 * T)); CK(ctx->chunk_cnt.ensure(4 * C)); CK(ctx->lane_cnt.ensure(64 * C)); CK(ctx->chunk_pos.ensure(8 * (C + 2)));
-    CK(ctx->tmp_j.ensure(4 * T)); CK(ctx->tmp_q.ensure(4 * T));
+    CK(ctx->gen_pairs.ensure(sizeof(int2) * T));      // (j, q) pairs of a level's candidates = the next level's tasks
     {   // one record region per block of the search launch
         const size_t n_regions = (size_t)ctx->n_sm * GRID_EVAL_PER_SM;
         const size_t region = ((size_t)ctx->cap_tuples + n_regions - 1) / n_regions;
@@ -503,10 +504,10 @@ static int ensure_buffers(amod_ctx* ctx, int V, i64 n_screen, int max_level, con
     ls->n = max_level + 1;
     CK(ctx->row_cnt.ensure(4 * max_trips)); CK(ctx->row_off.ensure(8 * (max_trips + 2))); CK(ctx->heavy_list.ensure(4 * max_trips));
     unsigned hsz = 64; while (hsz < 2u * (unsigned)max_trips + 2u) hsz <<= 1;
-    CK(ctx->hash.ensure(2 * 4 * (size_t)hsz));      // two tables: level k+1's is cleared while level k's is read
+    CK(ctx->hash.ensure(2 * 8 * (size_t)hsz));      // two tables: level k+1's is cleared while level k's is read
     ctx->hash_slots = hsz;
-    CK(ctx->gen_partial.ensure(8 * (size_t)ctx->n_sm * GRID_WARP_PER_SM));
-    CK(ctx->gen_cache.ensure(sizeof(int2) * GEN_INLINE * max_trips)); CK(ctx->task_first.ensure(8 * (max_trips + 2)));
+    CK(ctx->gen_partial.ensure(8 * ((size_t)ctx->n_sm * GRID_WARP_PER_SM + 1)));      // segment sums + the pair-buffer cursor
+    CK(ctx->task_first.ensure(8 * (max_trips + 2)));
     CK(ctx->veh_cnt.ensure(4 * (size_t)(V + 1))); CK(ctx->veh_off.ensure(8 * (size_t)(V + 2)));
     const size_t E = (size_t)ctx->cap_ent, PT = (size_t)ctx->cap_ptr, PS = (size_t)ctx->cap_pst;
     CK(ctx->ent_veh.ensure(4 * E)); CK(ctx->ent_kind.ensure(4 * E)); CK(ctx->ent_nfeas.ensure(4 * E)); CK(ctx->ent_tlen.ensure(4 * E));
@@ -601,7 +602,7 @@ static int enqueue_build(amod_ctx* ctx, int mode, int cap, Table<TT> tt, int max
         return sz;
     };
     auto hash_of = [&](int k) -> TripHash {        // two tables by level parity: k+1's is cleared while k's is read
-        TripHash th; th.slots = ctx->hash.as<int>() + (size_t)(k & 1) * ctx->hash_slots;
+        TripHash th; th.slots = ctx->hash.as<unsigned long long>() + (size_t)(k & 1) * ctx->hash_slots;
         th.mask = hash_size_of(k) ? hash_size_of(k) - 1 : 0;
         return th;
     };
@@ -636,8 +637,9 @@ static int enqueue_build(amod_ctx* ctx, int mode, int cap, Table<TT> tt, int max
                   FinTrips{&ctl->n_trips[k], (i64)lv.cap_trips, &ctl->need_trips[k], &ctl->overflow}, (i64*)scan_site(ctx, k));
         CK(edge(st, sd));                                         // fork
         const TripHash th = hash_of(k);
-        launch_k(sd, G, 256, k_compact_trips, ctl, cur, tv, tb, tq, tnf, ctx->trip_pos.as<i64>(), prev, lv, th, dstats, d, sba,
-                                          ctx->major_off.as<i64>(), ctx->task_first.as<i64>(), ctx->gen_partial.as<unsigned long long>(), GE);
+        auto kct = KM_OF(k) == 4 ? k_compact_trips<4> : KM_OF(k) == 8 ? k_compact_trips<8> : k_compact_trips<AMOD_MAX_TRIP>;
+        launch_k(sd, G, 256, kct, ctl, cur, tv, tb, tq, tnf, ctx->trip_pos.as<i64>(), prev, lv, th, dstats, d, sba,
+                                          ctx->major_off.as<i64>(), ctx->task_first.as<i64>(), ctx->gen_partial.as<unsigned long long>(), GE + 1);
         cudaEvent_t named = get_sync_event(ctx, n_sync++);        // the level's trips have their rows (s0, nfeas)
         CK(cudaEventRecord(named, sd));
         // main: costs to their encounter positions -> list order per trip -> schedules straight into their final rows
@@ -651,16 +653,20 @@ static int enqueue_build(amod_ctx* ctx, int mode, int cap, Table<TT> tt, int max
         if (k < max_level) {
             // ---- candidates of size k+1 (dispatch_osp.py:183-216), their tasks and rows ----------------------
             const TripHash thn = hash_of(k + 1);
-            launch_k(sd, GE, WARPS_PER_BLOCK * 32, k_gen_count, d, ctl, ls.lv[1], lv, th, ctx->row_cnt.as<int>(), ctx->gen_cache.as<int2>(),
-                                                            ctx->gen_partial.as<unsigned long long>(), thn.slots, thn.mask ? thn.mask + 1 : 0u);
+            unsigned long long* gpart = ctx->gen_partial.as<unsigned long long>();
+            // one wave: the grid is what fits (the rows are dealt cyclically; a second wave would only start when the first has drained)
+            auto kgp = KM_OF(k) == 4 ? k_gen_pairs<4> : KM_OF(k) == 8 ? k_gen_pairs<8> : k_gen_pairs<AMOD_MAX_TRIP>;
+            int& occ = ctx->gen_pairs_occ[KM_OF(k) == 4 ? 0 : KM_OF(k) == 8 ? 1 : 2];
+            if (occ == 0) { if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kgp, WARPS_PER_BLOCK * 32, 0) != cudaSuccess || occ < 1) occ = 1; }
+            launch_k(sd, ctx->n_sm * std::min(occ, GRID_WARP_PER_SM), WARPS_PER_BLOCK * 32, kgp, ctl, ls.lv[1], lv, th, ctx->row_cnt.as<int>(), ctx->row_off.as<int>(),
+                                                            ctx->gen_pairs.as<int2>(), ctx->cap_tasks, gpart, GE, gpart + GE, thn.slots, thn.mask ? thn.mask + 1 : 0u);
             GenOut go;
-            go.tmp_j = ctx->tmp_j.as<int>(); go.tmp_q = ctx->tmp_q.as<int>();
             go.task_veh = ctx->task_veh[nxt].as<int>(); go.task_base = ctx->task_base[nxt].as<int>(); go.task_q = ctx->task_q[nxt].as<int>();
             go.task_row0 = row0; go.rows = rows_buf[nxt]; go.task_nfeas = tnf; go.task_first = ctx->task_first.as<i64>();
             go.cap_tasks = ctx->cap_tasks; go.cap_rows = ctx->cap_rows; go.cap_chunks = ctx->cap_chunks;
             go.G_next = std::max(1, 32 / (lv.stride + 1));
-            launch_k(sd, GE, WARPS_PER_BLOCK * 32, k_gen_emit, ctl, nxt, ls.lv[1], lv, th, len0, ctx->row_cnt.as<int>(), ctx->gen_cache.as<int2>(),
-                                                           ctx->gen_partial.as<unsigned long long>(), go, ctx->gen_inline);
+            launch_k(sd, GE, WARPS_PER_BLOCK * 32, k_gen_emit, ctl, nxt, lv, len0, ctx->row_cnt.as<int>(), ctx->row_off.as<int>(),
+                                                           ctx->gen_pairs.as<int2>(), gpart, go, ctx->gen_wide);
             ctx->n_launches += 2;
         }
         CK(edge(sd, st));                                         // join

@@ -452,43 +452,92 @@ k_expand_rows(Control* __restrict__ ctl, int which, Level prev, const int* __res
 // ---------------------------------------------------------------------------------------------
 // Trip lookup table of one level: (vehicle, ascending request tuple) -> trip index.
 // Replaces the reference's `list in list` scans (dispatch_osp.py:194,202).
+// Open addressing, 8 B slots: (32-bit fingerprint of the key) << 32 | trip index.  A lookup is a chain of dependent
+// L2 round trips and the candidate kernels are nothing but such chains (a level has fewer trips than the GPU has
+// warps), so the chain is kept short: a miss ends at the first slot (empty, or another fingerprint), a hit costs one
+// more round trip (vehicle and the whole tuple are loaded together and compared without an early exit).
 // ---------------------------------------------------------------------------------------------
-struct TripHash { int* slots; unsigned mask; };
+struct TripHash { unsigned long long* slots; unsigned mask; };
+#define HASH_EMPTY 0xffffffffffffffffull
+// Tuples live in registers, so everything below is unrolled to a compile-time bound KMAX >= k; the kernels are instantiated for
+// KMAX = 4, 8 and AMOD_MAX_TRIP and the host picks the smallest that holds the level's trips (registers = resident warps).
+#define KM_OF(k) ((k) <= 4 ? 4 : (k) <= 8 ? 8 : AMOD_MAX_TRIP)
 
-__device__ __forceinline__ unsigned hash_trip(int v, const int* r, int k, int skip, int extra) {
-    // hash of the ascending tuple (r minus element `skip`, plus `extra` merged in order)
-    unsigned long long h = 0x9E3779B97F4A7C15ull ^ (unsigned long long)(unsigned)v * 0xD6E8FEB86659FD93ull;
-    bool put = extra < 0;
-    for (int m = 0; m < k; m++) {
-        if (m == skip) continue;
-        if (!put && extra < r[m]) { h = (h ^ (unsigned)extra) * 0xFF51AFD7ED558CCDull; h ^= h >> 32; put = true; }
-        h = (h ^ (unsigned)r[m]) * 0xFF51AFD7ED558CCDull; h ^= h >> 32;
-    }
-    if (!put) { h = (h ^ (unsigned)extra) * 0xFF51AFD7ED558CCDull; h ^= h >> 32; }
-    return (unsigned)(h ^ (h >> 29));
+template <int KMAX> struct ReqTuple { int r[KMAX]; };      // an ascending request tuple in registers (entries >= k are padding)
+
+template <int KMAX> __device__ __forceinline__ ReqTuple<KMAX> load_tuple(const int* __restrict__ p, int k) {
+    ReqTuple<KMAX> t;
+#pragma unroll
+    for (int m = 0; m < KMAX; m++) t.r[m] = m < k ? p[m] : 0x7fffffff;
+    return t;
 }
 
-// index of the trip (v, r minus r[skip] plus extra), or -1
-__device__ __forceinline__ int hash_find(const Level& lv, const TripHash& th, int v, const int* r, int skip, int extra) {
+// the ascending k-tuple (a minus a[skip]) plus `extra` (skip < 0: nothing removed, the result has k+1 entries)
+template <int KMAX> __device__ __forceinline__ ReqTuple<KMAX> merged_tuple(const ReqTuple<KMAX>& a, int k, int skip, int extra) {
+    if (skip < 0) skip = KMAX;
+    int pe = 0;                           // entries of (a minus skip) below extra
+#pragma unroll
+    for (int m = 0; m < KMAX; m++) pe += (m < k && m != skip && a.r[m] < extra) ? 1 : 0;
+    ReqTuple<KMAX> o;
+#pragma unroll
+    for (int w = 0; w < KMAX; w++) {      // rr = a minus skip: rr[i] = i < skip ? a[i] : a[i+1]
+        const int a_w = a.r[w];
+        const int a_n = w + 1 < KMAX ? a.r[(w + 1) % KMAX] : 0x7fffffff;
+        const int a_p = w > 0 ? a.r[(w + KMAX - 1) % KMAX] : 0;
+        const int rr_w = w < skip ? a_w : a_n;            // rr[w]
+        const int rr_p = w - 1 < skip ? a_p : a_w;        // rr[w-1]
+        o.r[w] = w < pe ? rr_w : (w == pe ? extra : rr_p);
+    }
+    return o;
+}
+
+template <int KMAX> __device__ __forceinline__ unsigned long long hash_tuple(int v, const ReqTuple<KMAX>& t, int k) {
+    unsigned long long h = 0x9E3779B97F4A7C15ull ^ (unsigned long long)(unsigned)v * 0xD6E8FEB86659FD93ull;
+#pragma unroll
+    for (int m = 0; m < KMAX; m++) if (m < k) { h = (h ^ (unsigned)t.r[m]) * 0xFF51AFD7ED558CCDull; h ^= h >> 32; }
+    return h;
+}
+__device__ __forceinline__ unsigned hash_slot(unsigned long long h) { return (unsigned)(h ^ (h >> 29)); }
+__device__ __forceinline__ unsigned hash_fp(unsigned long long h) { return (unsigned)(h >> 32); }
+
+template <int KMAX> __device__ __forceinline__ void hash_insert(const TripHash& th, int v, const ReqTuple<KMAX>& key, int k, int trip) {
+    const unsigned long long hv = hash_tuple(v, key, k);
+    const unsigned long long val = ((unsigned long long)hash_fp(hv) << 32) | (unsigned)trip;
+    unsigned h = hash_slot(hv) & th.mask;
+    while (atomicCAS(&th.slots[h], HASH_EMPTY, val) != HASH_EMPTY) h = (h + 1) & th.mask;
+}
+
+// A lookup in two halves, so that a lane can have the first probes of several lookups in flight at once.
+struct HashProbe { unsigned long long slot; unsigned h, fp; };
+template <int KMAX> __device__ __forceinline__ HashProbe hash_begin(const TripHash& th, int v, const ReqTuple<KMAX>& want, int k) {
+    const unsigned long long hv = hash_tuple(v, want, k);
+    HashProbe p; p.h = hash_slot(hv) & th.mask; p.fp = hash_fp(hv);
+    p.slot = th.slots[p.h];
+    return p;
+}
+// index of the trip (v, want), or -1
+template <int KMAX> __device__ __forceinline__ int hash_finish(const Level& lv, const TripHash& th, int v, const ReqTuple<KMAX>& want, HashProbe p) {
     const int k = lv.k;
-    unsigned h = hash_trip(v, r, k, skip, extra) & th.mask;
     for (;;) {
-        const int t = th.slots[h];
-        if (t < 0) return -1;
-        if (lv.trip_veh[t] == v) {
-            const int* c = lv.trip_req + (i64)t * k;
-            bool same = true, put = false;
-            int w = 0;
-            for (int m = 0; m < k && same; m++) {
-                if (m == skip) continue;
-                if (!put && extra < r[m]) { same = c[w++] == extra; put = true; if (!same) break; }
-                same = c[w++] == r[m];
-            }
-            if (same && !put) same = c[w++] == extra;
+        if (p.slot == HASH_EMPTY) return -1;
+        if ((unsigned)(p.slot >> 32) == p.fp) {
+            const int t = (int)(unsigned)p.slot;
+            const int* __restrict__ c = lv.trip_req + (i64)t * k;
+            const int tv = lv.trip_veh[t];
+            int cv[KMAX];
+#pragma unroll
+            for (int m = 0; m < KMAX; m++) cv[m] = m < k ? c[m] : 0;
+            bool same = tv == v;
+#pragma unroll
+            for (int m = 0; m < KMAX; m++) same &= (m >= k) | (cv[m] == want.r[m]);
             if (same) return t;
         }
-        h = (h + 1) & th.mask;
+        p.h = (p.h + 1) & th.mask;
+        p.slot = th.slots[p.h];
     }
+}
+template <int KMAX> __device__ __forceinline__ int hash_find(const Level& lv, const TripHash& th, int v, const ReqTuple<KMAX>& want) {
+    return hash_finish(lv, th, v, want, hash_begin(th, v, want, lv.k));
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -510,6 +559,7 @@ struct FinTrips {
     }
 };
 
+template <int KMAX>
 __global__ void k_compact_trips(const Control* __restrict__ ctl, int which, const int* __restrict__ task_veh,
                                 const int* __restrict__ task_base, const int* __restrict__ task_q,
                                 const int* __restrict__ task_nfeas,
@@ -544,15 +594,11 @@ __global__ void k_compact_trips(const Control* __restrict__ ctl, int which, cons
         cur.s0[o] = PACK_HI(tp);            // rows are task-major: the trip's first schedule follows those of all earlier tasks
         // trip = sorted(base trip + q)  (dispatch_osp.py:187)
         const int kb = prev.k, q = task_q[t];
-        const int* bq = prev.trip_req + (i64)task_base[t] * kb;
+        const ReqTuple<KMAX> trip = merged_tuple(load_tuple<KMAX>(prev.trip_req + (i64)task_base[t] * kb, kb), kb, -1, q);
         int* d = cur.trip_req + (i64)o * (kb + 1);
-        int w = 0; bool put = false;
-        for (int m = 0; m < kb; m++) { if (!put && q < bq[m]) { d[w++] = q; put = true; } d[w++] = bq[m]; }
-        if (!put) d[w++] = q;
-        if (th.mask) {        // the next level looks this one's trips up (table cleared two kernels back, by k_gen_count)
-            unsigned h = hash_trip(task_veh[t], d, kb + 1, -1, -1) & th.mask;
-            while (atomicCAS(&th.slots[h], -1, o) != -1) h = (h + 1) & th.mask;
-        }
+#pragma unroll
+        for (int m = 0; m < KMAX; m++) if (m <= kb) d[m] = trip.r[m];
+        if (th.mask) hash_insert(th, task_veh[t], trip, kb + 1, o);   // the next level looks this one's trips up (table cleared two kernels back, by k_gen_pairs)
     }
     nsch = warp_sum(nsch);
     if ((threadIdx.x & 31) == 0 && nsch) atomicAdd(&stats->n_sches, nsch);
@@ -684,14 +730,17 @@ k_classify_heavy(const Control* __restrict__ ctl, Level cur, const int* __restri
 // (i, j) order, j = second-lowest subset index.  One warp per row (= trip_i); lanes scan the
 // vehicle's size-1 trips for the request to add.
 //
-// Two launches, no scan kernel in between: every block owns a contiguous segment of trips.
-// MODE 0 counts per row and leaves one packed (tasks | rows << 32) sum per block.
-// MODE 1 adds up the sums of the blocks before it, scans its own segment in shared memory, writes
-// (j, q) per row, ranks the row by j and emits the next level's tasks AND their row descriptors (one per
-// base schedule the task walks); the last block publishes the level's task / row / chunk counts.
+// Two launches, no scan kernel in between.
+// k_gen_pairs finds every row's (j, q) pairs ONCE and stores them in a region of the pair buffer claimed with one
+// atomicAdd per row (regions are in no particular order; the row keeps its base), and leaves one packed
+// (tasks | rows << 32) sum per contiguous segment of rows.
+// k_gen_emit (every block owns one such segment) adds up the sums of the segments before it, scans its own in shared
+// memory, ranks each row's pairs by j and emits the next level's tasks AND their row descriptors (one per base
+// schedule the task walks); the last block publishes the level's task / row / chunk counts.
+// A level has fewer rows than the GPU has warps, so both kernels last as long as the longest chain of dependent L2
+// round trips of one row: 4 to reach the vehicle's size-1 trips, 2 per lookup phase (see TripHash).
 // ---------------------------------------------------------------------------------------------
 struct GenOut {
-    int* tmp_j; int* tmp_q;
     int* task_veh; int* task_base; int* task_q; i64* task_row0;
     RowDesc* rows; int* task_nfeas;
     i64* task_first;          // [trips of the level + 1] first task spawned by each trip (-> veh_start of the next level)
@@ -704,100 +753,146 @@ __device__ __forceinline__ void gen_segment(int n, int* lo, int* hi) {
     *hi = min(n, *lo + seg);
 }
 
-#define GEN_INLINE 8      // (j, q) pairs a row hands from the count pass to the emit pass without recomputing them
+#define GEN_NS 2          // 32-wide slices of a vehicle's size-1 trips a warp handles in one go (first probes in flight together)
+struct GenWarp { int j[GEN_NS * 32]; int r[GEN_NS * 32]; unsigned char list[GEN_NS * 32]; };
 
-// Candidates of row t, in the order of the vehicle's size-1 trips.  MODE 0 counts them and keeps the first
-// GEN_INLINE (j, q) pairs in `cache`; MODE 1 stores all of them at tmp[off..] (rows that did not fit the cache).
+// Candidates of row t among the vehicle's size-1 trips [c0, c0 + 32*GEN_NS) below a1: per slice s, lane `lane` holds
+// the request rv[s] of size-1 trip c0 + 32 s + lane and jv[s] = the second-lowest subset index, or -1 (no candidate).
 // The k lookups of a candidate are not walked one after the other: every lane first tries the subset without
 // mine[0]; the (few) survivors' remaining k-1 lookups are then spread over the lanes, one lookup deep.
-template <int MODE>
-__device__ __forceinline__ int gen_row(const Level& l1, const Level& prev, const TripHash& th, int t, int lane, i64 off,
-                                       int* __restrict__ tmp_j, int* __restrict__ tmp_q, int* __restrict__ s_j /*[32], this warp's*/,
-                                       int2* __restrict__ cache) {
-    const int v = prev.trip_veh[t], k = prev.k;
-    const int a0 = l1.veh_start[v], a1 = l1.veh_start[v + 1];
-    const int* mine = prev.trip_req + (i64)t * k;
-    int cnt = 0;
-    for (int c0 = a0; c0 < a1; c0 += 32) {
-        const int c = c0 + lane;
-        int j = -1, r = -1;
-        if (c < a1) {
-            r = l1.trip_req[c];
-            if (k == 1) {
-                if (c > t) j = c;                       // all pairs i<j (dispatch_osp.py:183-186)
-            } else {
-                bool in = false;
-                for (int m = 0; m < k; m++) in |= mine[m] == r;
-                if (!in) {                              // every other k-subset must exist with a larger index
-                    const int u = hash_find(prev, th, v, mine, 0, r);
-                    if (u > t) j = u;
-                }
-            }
-        }
-        if (k > 1) {
-            const unsigned surv = __ballot_sync(FULL, j >= 0);
-            __syncwarp();
-            s_j[lane] = j;
-            __syncwarp();
-            const int items = __popc(surv) * (k - 1);
-            for (int it0 = 0; it0 < items; it0 += 32) {
-                const int it = it0 + lane;
-                const bool valid = it < items;
-                const int si = valid ? it / (k - 1) : 0, d = 1 + (valid ? it % (k - 1) : 0);
-                const int src = __fns(surv, 0, si + 1);          // lane of the si-th survivor
-                const int rr = __shfl_sync(FULL, r, src);
-                if (valid) {
-                    const int u = hash_find(prev, th, v, mine, d, rr);
-                    atomicMin(&s_j[src], u > t ? u : -1);        // j = lowest subset index; any subset missing or not above t: rejected
-                }
-            }
-            __syncwarp();
-            j = s_j[lane];
-        }
-        const unsigned bal = __ballot_sync(FULL, j >= 0);
-        if (j >= 0) {
-            const int p = cnt + __popc(bal & ((1u << lane) - 1u));
-            if (MODE == 1) { tmp_j[off + p] = j; tmp_q[off + p] = r; }
-            else if (p < GEN_INLINE) cache[p] = make_int2(j, r);
-        }
-        cnt += __popc(bal);
+template <int KMAX>
+__device__ __forceinline__ void gen_block(const Level& l1, const Level& prev, const TripHash& th, int t, int v, const ReqTuple<KMAX>& mine,
+                                          int c0, int a1, int lane, GenWarp& sh, int (&jv)[GEN_NS], int (&rv)[GEN_NS]) {
+    const int k = prev.k;
+#pragma unroll
+    for (int s = 0; s < GEN_NS; s++) { const int c = c0 + 32 * s + lane; rv[s] = c < a1 ? l1.trip_req[c] : -1; jv[s] = -1; }
+    if (k == 1) {                                   // all pairs i<j (dispatch_osp.py:183-186)
+#pragma unroll
+        for (int s = 0; s < GEN_NS; s++) { const int c = c0 + 32 * s + lane; if (c < a1 && c > t) jv[s] = c; }
+        return;
     }
-    return cnt;
+    // every other k-subset must exist with a larger index; first the one without mine[0]
+    HashProbe pb[GEN_NS];
+    bool go[GEN_NS];
+#pragma unroll
+    for (int s = 0; s < GEN_NS; s++) {
+        go[s] = false;
+        if (c0 + 32 * s < a1) {                     // (warp-uniform)
+            bool in = rv[s] < 0;
+#pragma unroll
+            for (int m = 0; m < KMAX; m++) in |= (m < k) & (mine.r[m] == rv[s]);
+            go[s] = !in;
+            if (go[s]) pb[s] = hash_begin(th, v, merged_tuple(mine, k, 0, rv[s]), k);
+        }
+    }
+    int nsurv = 0;
+    const unsigned lt = (1u << lane) - 1u;
+    __syncwarp();
+#pragma unroll
+    for (int s = 0; s < GEN_NS; s++) {
+        if (c0 + 32 * s < a1) {
+            if (go[s]) { const int u = hash_finish(prev, th, v, merged_tuple(mine, k, 0, rv[s]), pb[s]); if (u > t) jv[s] = u; }
+            const unsigned bal = __ballot_sync(FULL, jv[s] >= 0);
+            const int slot = 32 * s + lane;
+            sh.j[slot] = jv[s]; sh.r[slot] = rv[s];
+            if (jv[s] >= 0) sh.list[nsurv + __popc(bal & lt)] = (unsigned char)slot;
+            nsurv += __popc(bal);
+        }
+    }
+    __syncwarp();
+    const int items = nsurv * (k - 1);
+    for (int it0 = 0; it0 < items; it0 += 32) {
+        const int it = it0 + lane;
+        if (it < items) {
+            const int si = it / (k - 1), d = 1 + it % (k - 1);
+            const int slot = sh.list[si];
+            const int u = hash_find(prev, th, v, merged_tuple(mine, k, d, sh.r[slot]));
+            atomicMin(&sh.j[slot], u > t ? u : -1);      // j = lowest subset index; any subset missing or not above t: rejected
+        }
+    }
+    __syncwarp();
+#pragma unroll
+    for (int s = 0; s < GEN_NS; s++) if (c0 + 32 * s < a1) jv[s] = sh.j[32 * s + lane];
+    __syncwarp();
 }
 
+template <int KMAX>
 __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32)
-k_gen_count(const DEpoch* __restrict__ epp, const Control* __restrict__ ctl, Level l1, Level prev, TripHash th,
-            int* __restrict__ row_cnt, int2* __restrict__ row_cache, unsigned long long* __restrict__ blk_partial,
-            int* __restrict__ next_hash, unsigned next_hash_size) {
+k_gen_pairs(const Control* __restrict__ ctl, Level l1, Level prev, TripHash th,
+            int* __restrict__ row_cnt, int* __restrict__ row_base, int2* __restrict__ pairs, i64 cap_pairs,
+            unsigned long long* __restrict__ blk_partial, int n_seg /* blocks of the emit pass */, unsigned long long* __restrict__ cursor,
+            unsigned long long* __restrict__ next_hash, unsigned next_hash_size) {
     pdl_enter();
-    __shared__ int s_j[WARPS_PER_BLOCK][32];
+    __shared__ GenWarp s_w[WARPS_PER_BLOCK];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    GenWarp& sh = s_w[wib];
     const int n = ctl->overflow ? 0 : ctl->n_trips[prev.k];
     const unsigned gtid = blockIdx.x * blockDim.x + threadIdx.x, gsz = gridDim.x * blockDim.x;
     // the lookup table the NEXT level will build into (the other buffer; its last readers are two kernels back)
-    for (unsigned x = gtid; x < next_hash_size; x += gsz) next_hash[x] = -1;
-    // Rows are dealt out cyclically over ALL warps of the grid (a vehicle's trips are consecutive rows and a heavy vehicle's rows scan
-    // several 32-wide slices of its size-1 trips: contiguous rows per block would leave whole blocks with nothing but heavy rows); the
-    // emit pass owns contiguous segments, so every row adds its (tasks | rows << 32) to the sum of the segment it belongs to
-    // (blk_partial is zeroed by k_compact_trips, the kernel before this one on the branch).
-    const int seg = max(1, (n + (int)gridDim.x - 1) / (int)gridDim.x);
+    for (unsigned x = gtid; x < next_hash_size; x += gsz) next_hash[x] = HASH_EMPTY;
+    // Rows are dealt out cyclically over ALL warps of the grid (a vehicle's trips are consecutive rows); the emit pass owns
+    // contiguous segments, so every row adds its (tasks | rows << 32) to the sum of the segment it belongs to
+    // (blk_partial and the cursor are zeroed by k_compact_trips, the kernel before this one on the branch).
+    const int seg = max(1, (n + n_seg - 1) / n_seg);
+    const unsigned lt = (1u << lane) - 1u;
+    const int k = prev.k;
     for (int t = blockIdx.x * WARPS_PER_BLOCK + wib; t < n; t += gridDim.x * WARPS_PER_BLOCK) {
-        const int cnt = gen_row<0>(l1, prev, th, t, lane, 0, nullptr, nullptr, s_j[wib], row_cache + (i64)t * GEN_INLINE);
+        const int v = prev.trip_veh[t];
+        const ReqTuple<KMAX> mine = load_tuple<KMAX>(prev.trip_req + (i64)t * k, k);
+        const int a0 = l1.veh_start[v], a1 = l1.veh_start[v + 1];
+        int jv[GEN_NS], rv[GEN_NS];
+        int cnt = 0;
+        i64 base = 0;
+        if (a1 - a0 <= 32 * GEN_NS) {
+            gen_block(l1, prev, th, t, v, mine, a0, a1, lane, sh, jv, rv);
+            int pos[GEN_NS];
+#pragma unroll
+            for (int s = 0; s < GEN_NS; s++) { const unsigned bal = __ballot_sync(FULL, jv[s] >= 0); pos[s] = cnt + __popc(bal & lt); cnt += __popc(bal); }
+            if (cnt) {
+                if (lane == 0) base = (i64)atomicAdd(cursor, (unsigned long long)cnt);
+                base = __shfl_sync(FULL, base, 0);
+                if (base + cnt <= cap_pairs) {       // (else the emit pass reports the task overflow and the epoch is rerun)
+#pragma unroll
+                    for (int s = 0; s < GEN_NS; s++) if (jv[s] >= 0) pairs[base + pos[s]] = make_int2(jv[s], rv[s]);
+                }
+            }
+        } else {                                     // a vehicle with more size-1 trips: count, claim, find again
+            for (int c0 = a0; c0 < a1; c0 += 32 * GEN_NS) {
+                gen_block(l1, prev, th, t, v, mine, c0, a1, lane, sh, jv, rv);
+#pragma unroll
+                for (int s = 0; s < GEN_NS; s++) cnt += __popc(__ballot_sync(FULL, jv[s] >= 0));
+            }
+            if (cnt) {
+                if (lane == 0) base = (i64)atomicAdd(cursor, (unsigned long long)cnt);
+                base = __shfl_sync(FULL, base, 0);
+                int w = 0;
+                for (int c0 = a0; c0 < a1; c0 += 32 * GEN_NS) {
+                    gen_block(l1, prev, th, t, v, mine, c0, a1, lane, sh, jv, rv);
+#pragma unroll
+                    for (int s = 0; s < GEN_NS; s++) {
+                        const unsigned bal = __ballot_sync(FULL, jv[s] >= 0);
+                        if (jv[s] >= 0 && base + cnt <= cap_pairs) pairs[base + w + __popc(bal & lt)] = make_int2(jv[s], rv[s]);
+                        w += __popc(bal);
+                    }
+                }
+            }
+        }
         if (lane == 0) {
             row_cnt[t] = cnt;
+            row_base[t] = (int)min(base, (i64)0x7fffffff);
             if (cnt) atomicAdd(&blk_partial[t / seg], (unsigned long long)cnt | ((unsigned long long)cnt * (unsigned long long)prev.nfeas[t]) << 32);
         }
     }
 }
 
 __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32)
-k_gen_emit(Control* __restrict__ ctl, int which_next, Level l1, Level prev, TripHash th, const int* __restrict__ len0,
-           const int* __restrict__ row_cnt, const int2* __restrict__ row_cache, const unsigned long long* __restrict__ blk_partial,
-           GenOut o, int inline_max /* <= GEN_INLINE; 0 forces the recompute path (tests) */) {
+k_gen_emit(Control* __restrict__ ctl, int which_next, Level prev, const int* __restrict__ len0,
+           const int* __restrict__ row_cnt, const int* __restrict__ row_base, const int2* __restrict__ pairs,
+           const unsigned long long* __restrict__ blk_partial, GenOut o, int wide /* != 0: every row ranks through memory (tests) */) {
     pdl_enter();
-    __shared__ int s_j[WARPS_PER_BLOCK][32];
     __shared__ i64 s_scan[SCAN_THREADS / 32 + 1];
     __shared__ i64 s_off[WARPS_PER_BLOCK * 32];
+    __shared__ int s_q[WARPS_PER_BLOCK][32];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const int n = ctl->overflow ? 0 : ctl->n_trips[prev.k];
     int lo, hi;
@@ -810,6 +905,7 @@ k_gen_emit(Control* __restrict__ ctl, int which_next, Level l1, Level prev, Trip
     i64 carry;
     block_excl_scan(p, &carry, s_scan);
     unsigned long long n_tasks = 0, n_items = 0;
+    const int k = prev.k;
     for (int base = lo; base < hi; base += WARPS_PER_BLOCK * 32) {
         const int tt = base + threadIdx.x;
         i64 x = 0;
@@ -825,16 +921,32 @@ k_gen_emit(Control* __restrict__ ctl, int which_next, Level l1, Level prev, Trip
             if (lane == 0) o.task_first[t] = off;
             if (cnt == 0) continue;
             if (off + cnt > o.cap_tasks || rbase + (i64)cnt * S > o.cap_rows) continue;   // reported by the last block; the epoch is rerun
-            const int v = prev.trip_veh[t], k = prev.k;
-            const int l = len0[v] + 2 * k;
+            if ((i64)row_base[t] + cnt > o.cap_tasks) continue;                           // (its pairs did not fit the pair buffer: same overflow)
+            const int v = prev.trip_veh[t];
+            const int2* __restrict__ pp = pairs + row_base[t];
             const i64 s0 = prev.s0[t];
-            // rank by j (k == 1 rows are already in j order) and emit the next level's tasks
-            if (cnt <= inline_max) {                   // the count pass left the (j, q) pairs
-                const int2* cc = row_cache + (i64)t * GEN_INLINE;
+            const int l = len0[v] + 2 * k;
+            // rank the pairs by j (k == 1 rows are already in j order) and emit the next level's tasks
+            const bool narrow = cnt <= 32 && !wide;
+            if (narrow) {
+                int2 me = make_int2(0x7fffffff, 0);
+                if (lane < cnt) me = pp[lane];
+                int rank = lane;
+                if (k > 1) { rank = 0; for (int y = 0; y < cnt; y++) rank += __shfl_sync(FULL, me.x, y) < me.x; }
                 if (lane < cnt) {
-                    const int2 me = cc[lane];
-                    int rank = lane;
-                    if (k > 1) { rank = 0; for (int y = 0; y < cnt; y++) rank += cc[y].x < me.x; }
+                    const i64 w = off + rank;
+                    if (BOK(w >= 0 && w < o.cap_tasks && rank < cnt)) {
+                        o.task_veh[w] = v; o.task_base[w] = t; o.task_q[w] = me.y;
+                        o.task_row0[w] = rbase + (i64)rank * S;
+                        o.task_nfeas[w] = 0;
+                    }
+                    s_q[wib][rank & 31] = me.y;
+                }
+            } else {
+                for (int e = lane; e < cnt; e += 32) {
+                    const int2 me = pp[e];
+                    int rank = e;
+                    if (k > 1) { rank = 0; for (int y = 0; y < cnt; y++) rank += pp[y].x < me.x; }
                     const i64 w = off + rank;
                     if (BOK(w >= 0 && w < o.cap_tasks && rank < cnt)) {
                         o.task_veh[w] = v; o.task_base[w] = t; o.task_q[w] = me.y;
@@ -842,33 +954,17 @@ k_gen_emit(Control* __restrict__ ctl, int which_next, Level l1, Level prev, Trip
                         o.task_nfeas[w] = 0;
                     }
                 }
-            } else {
-                gen_row<1>(l1, prev, th, t, lane, off, o.tmp_j, o.tmp_q, s_j[wib], nullptr);
-                __syncwarp();
-                for (int e = lane; e < cnt; e += 32) {
-                    int rank = e;
-                    if (k > 1) {
-                        const int j = o.tmp_j[off + e];
-                        rank = 0;
-                        for (int y = 0; y < cnt; y++) rank += o.tmp_j[off + y] < j;
-                    }
-                    const i64 w = off + rank;
-                    if (BOK(w >= 0 && w < o.cap_tasks && rank < cnt)) {
-                        o.task_veh[w] = v; o.task_base[w] = t; o.task_q[w] = o.tmp_q[off + e];
-                        o.task_row0[w] = rbase + (i64)rank * S;
-                        o.task_nfeas[w] = 0;
-                    }
-                }
             }
             __syncwarp();
             // ... and one row descriptor per (task, base schedule): task `off + e` owns rows rbase + e*S ..
-            const i64 n_rows = (i64)cnt * S;
-            for (i64 idx = lane; idx < n_rows; idx += 32) {
-                const int e = (int)(idx / S), xs = (int)(idx - (i64)e * S);
+            const int n_rows = cnt * S;            // (< 2^31: bounded by cap_rows above)
+            for (int idx = lane; idx < n_rows; idx += 32) {
+                const int e = idx / S, xs = idx - e * S;
                 RowDesc d;
-                d.v = v; d.q = o.task_q[off + e]; d.s = xs; d.l = l; d.s0 = s0; d.task = (int)(off + e); d.pad = 0;
+                d.v = v; d.q = narrow ? s_q[wib][e] : o.task_q[off + e]; d.s = xs; d.l = l; d.s0 = s0; d.task = (int)(off + e); d.pad = 0;
                 if (BOK(rbase + idx < o.cap_rows)) o.rows[rbase + idx] = d;
             }
+            __syncwarp();
             if (lane == 0) { n_tasks += (unsigned long long)cnt; n_items += (unsigned long long)n_rows * (unsigned long long)(l + 1); }
         }
         carry += tile_tot;

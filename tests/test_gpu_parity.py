@@ -309,10 +309,10 @@ def test_pinned_fetch_and_repeated_builds_are_identical():
     b.close()
 
 
-def test_candidate_recompute_path(monkeypatch):
-    """k_gen_emit normally takes a row's (j, q) candidates from the count pass (first GEN_INLINE of them); rows with
-    more recompute them.  Force every row onto the recompute path and compare with the reference goldens."""
-    monkeypatch.setenv("AMOD_GEN_INLINE", "0")
+def test_candidate_wide_rank_path(monkeypatch):
+    """k_gen_emit ranks a row's (j, q) pairs by shuffles when there are at most 32 of them and through memory otherwise.
+    Force every row onto the memory path and compare with the reference goldens."""
+    monkeypatch.setenv("AMOD_GEN_WIDE", "1")
     for family in ("rand_real_osp_cap4", "rand_ties_osp_cap8"):
         if family not in golden_families(("rand_",)):
             continue
