@@ -87,7 +87,7 @@ struct amod_ctx {
     GraphSlot graphs[3];
     unsigned long long buf_gen = 0;
     bool use_graph = true;
-    int gen_pairs_occ[3] = {0, 0, 0};   // resident blocks per SM of k_gen_pairs<4 / 8 / AMOD_MAX_TRIP>
+    int gen_pairs_occ[4] = {0, 0, 0, 0};   // resident blocks per SM of k_gen_pairs<1 / 4 / 8 / AMOD_MAX_TRIP>
     int gen_wide = 0;              // AMOD_GEN_WIDE=1: k_gen_emit ranks every row's pairs through memory, the path of rows with > 32 pairs (tests)
     int heavy_min = -1;            // AMOD_HEAVY_MIN overrides the block-per-trip classification threshold (tests)
     int level_hint[3] = {0, 0, 0};   // deepest non-empty trip level seen so far (+1 is searched before looking further)
@@ -162,14 +162,18 @@ static inline int nblk(i64 n, int per) { return (int)((n + per - 1) / per); }
 // touching memory (pdl_enter(), common.cuh).  AMOD_NO_PDL=1 launches them plainly (A/B: profiles/r02_pdl_ab.txt).
 static bool g_pdl = getenv("AMOD_NO_PDL") == nullptr;
 template <typename... KArgs, typename... Args>
-static inline void launch_k(cudaStream_t st, int grid, int block, void (*kern)(KArgs...), Args&&... args) {
+static inline void launch_ks(cudaStream_t st, int grid, int block, size_t smem, void (*kern)(KArgs...), Args&&... args) {
     cudaLaunchConfig_t cfg; memset(&cfg, 0, sizeof cfg);
-    cfg.gridDim = dim3((unsigned)grid); cfg.blockDim = dim3((unsigned)block); cfg.stream = st;
+    cfg.gridDim = dim3((unsigned)grid); cfg.blockDim = dim3((unsigned)block); cfg.stream = st; cfg.dynamicSmemBytes = smem;
     cudaLaunchAttribute at[1];
     at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     at[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = at; cfg.numAttrs = g_pdl ? 1 : 0;
     cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+}
+template <typename... KArgs, typename... Args>
+static inline void launch_k(cudaStream_t st, int grid, int block, void (*kern)(KArgs...), Args&&... args) {
+    launch_ks(st, grid, block, 0, kern, static_cast<Args&&>(args)...);
 }
 
 // exclusive scan (length and result sizes live on the device; no synchronisation)
@@ -637,7 +641,7 @@ static int enqueue_build(amod_ctx* ctx, int mode, int cap, Table<TT> tt, int max
                   FinTrips{&ctl->n_trips[k], (i64)lv.cap_trips, &ctl->need_trips[k], &ctl->overflow}, (i64*)scan_site(ctx, k));
         CK(edge(st, sd));                                         // fork
         const TripHash th = hash_of(k);
-        auto kct = KM_OF(k) == 4 ? k_compact_trips<4> : KM_OF(k) == 8 ? k_compact_trips<8> : k_compact_trips<AMOD_MAX_TRIP>;
+        auto kct = KM_IDX(k) == 0 ? k_compact_trips<1> : KM_IDX(k) == 1 ? k_compact_trips<4> : KM_IDX(k) == 2 ? k_compact_trips<8> : k_compact_trips<AMOD_MAX_TRIP>;
         launch_k(sd, G, 256, kct, ctl, cur, tv, tb, tq, tnf, ctx->trip_pos.as<i64>(), prev, lv, th, dstats, d, sba,
                                           ctx->major_off.as<i64>(), ctx->task_first.as<i64>(), ctx->gen_partial.as<unsigned long long>(), GE + 1);
         cudaEvent_t named = get_sync_event(ctx, n_sync++);        // the level's trips have their rows (s0, nfeas)
@@ -655,8 +659,8 @@ static int enqueue_build(amod_ctx* ctx, int mode, int cap, Table<TT> tt, int max
             const TripHash thn = hash_of(k + 1);
             unsigned long long* gpart = ctx->gen_partial.as<unsigned long long>();
             // one wave: the grid is what fits (the rows are dealt cyclically; a second wave would only start when the first has drained)
-            auto kgp = KM_OF(k) == 4 ? k_gen_pairs<4> : KM_OF(k) == 8 ? k_gen_pairs<8> : k_gen_pairs<AMOD_MAX_TRIP>;
-            int& occ = ctx->gen_pairs_occ[KM_OF(k) == 4 ? 0 : KM_OF(k) == 8 ? 1 : 2];
+            auto kgp = KM_IDX(k) == 0 ? k_gen_pairs<1> : KM_IDX(k) == 1 ? k_gen_pairs<4> : KM_IDX(k) == 2 ? k_gen_pairs<8> : k_gen_pairs<AMOD_MAX_TRIP>;
+            int& occ = ctx->gen_pairs_occ[KM_IDX(k)];
             if (occ == 0) { if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kgp, WARPS_PER_BLOCK * 32, 0) != cudaSuccess || occ < 1) occ = 1; }
             launch_k(sd, ctx->n_sm * std::min(occ, GRID_WARP_PER_SM), WARPS_PER_BLOCK * 32, kgp, ctl, ls.lv[1], lv, th, ctx->row_cnt.as<int>(), ctx->row_off.as<int>(),
                                                             ctx->gen_pairs.as<int2>(), ctx->cap_tasks, gpart, GE, gpart + GE, thn.slots, thn.mask ? thn.mask + 1 : 0u);

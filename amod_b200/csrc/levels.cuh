@@ -460,8 +460,9 @@ k_expand_rows(Control* __restrict__ ctl, int which, Level prev, const int* __res
 struct TripHash { unsigned long long* slots; unsigned mask; };
 #define HASH_EMPTY 0xffffffffffffffffull
 // Tuples live in registers, so everything below is unrolled to a compile-time bound KMAX >= k; the kernels are instantiated for
-// KMAX = 4, 8 and AMOD_MAX_TRIP and the host picks the smallest that holds the level's trips (registers = resident warps).
-#define KM_OF(k) ((k) <= 4 ? 4 : (k) <= 8 ? 8 : AMOD_MAX_TRIP)
+// KMAX = 1, 4, 8 and AMOD_MAX_TRIP and the host picks the smallest that holds the level's trips (registers = resident warps).
+#define KM_OF(k) ((k) <= 1 ? 1 : (k) <= 4 ? 4 : (k) <= 8 ? 8 : AMOD_MAX_TRIP)
+#define KM_IDX(k) ((k) <= 1 ? 0 : (k) <= 4 ? 1 : (k) <= 8 ? 2 : 3)
 
 template <int KMAX> struct ReqTuple { int r[KMAX]; };      // an ascending request tuple in registers (entries >= k are padding)
 
@@ -766,7 +767,7 @@ __device__ __forceinline__ void gen_block(const Level& l1, const Level& prev, co
     const int k = prev.k;
 #pragma unroll
     for (int s = 0; s < GEN_NS; s++) { const int c = c0 + 32 * s + lane; rv[s] = c < a1 ? l1.trip_req[c] : -1; jv[s] = -1; }
-    if (k == 1) {                                   // all pairs i<j (dispatch_osp.py:183-186)
+    if (KMAX == 1 || k == 1) {                      // all pairs i<j (dispatch_osp.py:183-186)
 #pragma unroll
         for (int s = 0; s < GEN_NS; s++) { const int c = c0 + 32 * s + lane; if (c < a1 && c > t) jv[s] = c; }
         return;

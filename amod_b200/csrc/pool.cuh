@@ -68,33 +68,44 @@ k_pool_meta(const DEpoch* __restrict__ epp, LevelSet ls, const int* __restrict__
     if (over || n_ent == 0) return;
     const i64 seg = scan_seg_len(n_ent, part_vg);
     const int gtid = blockIdx.x * blockDim.x + threadIdx.x, stride = gridDim.x * blockDim.x;
-    for (int v = gtid; v <= n_veh; v += stride) {
-        const i64 e0 = pool_veh_off(ls, mode, v);
-        veh_off[v] = e0;
-        if (v == n_veh) break;
-        const int cur_len = ep.veh_sche_off[v + 1] - ep.veh_sche_off[v];
-        // compute_sche_cost walks of the fixed pairs (dispatch_osp.py:125,148, dispatch_sba.py:69)
-        atomicAdd(&ctl->stats.n_lookups, (unsigned long long)((sba ? 0 : len0[v]) + (mode == AMOD_MODE_OSP_NR ? 0 : cur_len)));
-        if (sba) {
-            const i64 e = (i64)ctl->n_trips[1] + v;
-            pb.ent_veh[e] = v; pb.ent_kind[e] = AMOD_KIND_SBA_EMPTY; pb.ent_nfeas[e] = 1; pb.ent_tlen[e] = 0; pb.ent_slen[e] = cur_len;
-            pb.ent_src[e] = SRC_INPUT; pb.ent_trip[e] = v;
-            atomicAdd(&part[part_vg + e / seg], (unsigned long long)cur_len);
-            continue;
+    unsigned long long look = 0;      // compute_sche_cost walks of the fixed pairs (dispatch_osp.py:125,148, dispatch_sba.py:69)
+    int max_np = 0;
+    for (int base = blockIdx.x * blockDim.x; base <= n_veh; base += stride) {      // (whole warps iterate together: one atomic per warp and sum)
+        const int v = base + threadIdx.x;
+        const bool valid = v < n_veh;
+        i64 e0 = 0, e1 = 0;
+        int cur_len = 0, l0 = 0, np = 0;
+        if (v <= n_veh) { e0 = pool_veh_off(ls, mode, v); veh_off[v] = e0; }
+        if (valid) {
+            const int c0 = ep.veh_sche_off[v], c1 = ep.veh_sche_off[v + 1];
+            cur_len = c1 - c0; l0 = len0[v];
+            look += (unsigned long long)((sba ? 0 : l0) + (mode == AMOD_MODE_OSP_NR ? 0 : cur_len));
+            if (sba) {
+                const i64 e = (i64)ctl->n_trips[1] + v;
+                e0 = e;
+                pb.ent_veh[e] = v; pb.ent_kind[e] = AMOD_KIND_SBA_EMPTY; pb.ent_nfeas[e] = 1; pb.ent_tlen[e] = 0; pb.ent_slen[e] = cur_len;
+                pb.ent_src[e] = SRC_INPUT; pb.ent_trip[e] = v;
+            } else {
+                const i64 e = e0;
+                pb.ent_veh[e] = v; pb.ent_kind[e] = AMOD_KIND_BASIC; pb.ent_nfeas[e] = ls.lv[0].nfeas[v]; pb.ent_tlen[e] = 0;
+                pb.ent_slen[e] = l0; pb.ent_src[e] = 0; pb.ent_trip[e] = v;
+                if (mode == AMOD_MODE_OSP) {
+                    e1 = pool_veh_off(ls, mode, v + 1) - 1;
+                    for (int k = c0; k < c1; k++) np += ep.sche_code[k] >= 0 && !(ep.sche_code[k] & 1);
+                    pb.ent_veh[e1] = v; pb.ent_kind[e1] = AMOD_KIND_CURRENT; pb.ent_nfeas[e1] = 1; pb.ent_tlen[e1] = np; pb.ent_slen[e1] = cur_len;
+                    pb.ent_src[e1] = SRC_INPUT; pb.ent_trip[e1] = v;
+                }
+            }
         }
-        i64 e = e0;
-        pb.ent_veh[e] = v; pb.ent_kind[e] = AMOD_KIND_BASIC; pb.ent_nfeas[e] = ls.lv[0].nfeas[v]; pb.ent_tlen[e] = 0;
-        pb.ent_slen[e] = len0[v]; pb.ent_src[e] = 0; pb.ent_trip[e] = v;
-        atomicAdd(&part[part_vg + e / seg], (unsigned long long)len0[v]);
-        if (mode == AMOD_MODE_OSP) {
-            e = pool_veh_off(ls, mode, v + 1) - 1;
-            int np = 0;
-            for (int k = ep.veh_sche_off[v]; k < ep.veh_sche_off[v + 1]; k++) np += ep.sche_code[k] >= 0 && !(ep.sche_code[k] & 1);
-            pb.ent_veh[e] = v; pb.ent_kind[e] = AMOD_KIND_CURRENT; pb.ent_nfeas[e] = 1; pb.ent_tlen[e] = np; pb.ent_slen[e] = cur_len;
-            if (np > ctl->max_tlen) atomicMax(&ctl->max_tlen, np);
-            pb.ent_src[e] = SRC_INPUT; pb.ent_trip[e] = v;
-            atomicAdd(&part[e / seg], (unsigned long long)np); atomicAdd(&part[part_vg + e / seg], (unsigned long long)cur_len);
-        }
+        max_np = max(max_np, np);
+        pool_len_partials(part, part_vg, seg, valid, e0, 0, sba ? cur_len : l0, lane);                  // the SBA empty pair / the basic pair
+        pool_len_partials(part, part_vg, seg, valid && mode == AMOD_MODE_OSP, e1, np, cur_len, lane);   // the current schedule's pair
+    }
+    look = warp_sum(look);
+    for (int o = 16; o; o >>= 1) max_np = max(max_np, __shfl_xor_sync(FULL, max_np, o));
+    if (lane == 0) {
+        if (look) atomicAdd(&ctl->stats.n_lookups, look);
+        if (max_np > 0) atomicMax(&ctl->max_tlen, max_np);
     }
     for (int k = 1; k < ls.n; k++) {
         const Level& lv = ls.lv[k];
@@ -131,6 +142,11 @@ struct InEntLen {   // scan input over pool entries
     __device__ __forceinline__ i64 operator()(i64 i) const { return (i64)p[i]; }
 };
 
+#define POOL_BATCH 8      // stops of one entry whose look-ups are in flight together
+
+// One thread per entry.  An entry's walk is a chain of dependent round trips (stop -> node -> travel time), so the stops are
+// taken POOL_BATCH at a time: all their codes / nodes first (a stored schedule carries its nodes), then all their travel
+// times and request times, and only then the left-to-right float64 sums (scheduling.py:101-107, :126-137) from registers.
 template <typename TT>
 __global__ void k_pool_payload(const DEpoch* __restrict__ epp, Table<TT> tt, LevelSet ls, const Control* __restrict__ ctl, PoolBufs pb) {
     pdl_enter();
@@ -139,39 +155,71 @@ __global__ void k_pool_payload(const DEpoch* __restrict__ epp, Table<TT> tt, Lev
     const i64 stride = (i64)gridDim.x * blockDim.x;
     for (i64 e = (i64)blockIdx.x * blockDim.x + threadIdx.x; e < n_ent; e += stride) {
         const int v = pb.ent_veh[e], src = pb.ent_src[e], t = pb.ent_trip[e];
-        const int slen = (int)(pb.sche_off[e + 1] - pb.sche_off[e]);
-        int* sc = pb.sche_code + pb.sche_off[e];
-        int* tr = pb.trip_req + pb.trip_off[e];
-        if (!BOK(e < pb.cap_ent && pb.sche_off[e + 1] <= pb.cap_pst && pb.trip_off[e + 1] <= pb.cap_ptr && pb.sche_off[e] >= 0 && pb.trip_off[e] >= 0)) continue;
-        if (src == SRC_INPUT) {
-            const int* in = ep.sche_code + ep.veh_sche_off[v];
-            int w = 0;
-            for (int m = 0; m < slen; m++) sc[m] = in[m];
-            if (pb.trip_off[e + 1] > pb.trip_off[e]) {     // picking requests, ascending (dispatch_osp.py:121-124)
-                for (int m = 0; m < slen; m++) if (in[m] >= 0 && !(in[m] & 1)) {
-                    int r = in[m] >> 1, x = w++;
-                    while (x > 0 && tr[x - 1] > r) { tr[x] = tr[x - 1]; x--; }
-                    tr[x] = r;
-                }
-            }
-        } else {
-            const Level& lv = ls.lv[src];
-            const i64 s0 = lv.s0[t];
-            const Stop* in = lv.sch + s0 * lv.stride;   // rows are in list order: element 0 = best (scheduling.py:32-34)
-            for (int m = 0; m < slen; m++) sc[m] = in[m].code;
-            for (int m = 0; m < src; m++) tr[m] = lv.trip_req[(i64)t * src + m];
-        }
-        // cost walk (scheduling.py:101-107) and delay (:126-137)
+        const i64 so0 = pb.sche_off[e], so1 = pb.sche_off[e + 1], to0 = pb.trip_off[e], to1 = pb.trip_off[e + 1];
+        const int slen = (int)(so1 - so0);
+        int* sc = pb.sche_code + so0;
+        int* tr = pb.trip_req + to0;
+        if (!BOK(e < pb.cap_ent && so1 <= pb.cap_pst && to1 <= pb.cap_ptr && so0 >= 0 && to0 >= 0)) continue;
+        const bool input = src == SRC_INPUT;
+        const Level& lv = ls.lv[input ? 0 : src];
+        const Stop* __restrict__ in = nullptr;       // rows are in list order: element 0 = best (scheduling.py:32-34)
+        const int* __restrict__ inc = nullptr;
+        if (input) inc = ep.sche_code + ep.veh_sche_off[v];
+        else in = lv.sch + lv.s0[t] * lv.stride;
         double acc = ep.veh_t[v], delay = 0.0;
         int nid = ep.veh_nid[v];
-        for (int m = 0; m < slen; m++) {
-            int node, pod; double ddl;
-            stop_info(ep, v, sc[m], node, ddl, pod);
-            acc += tt(nid, node);
-            if (pod == -1) { const int r = sc[m] >> 1; delay += (ep.T + acc - ep.tr[r] - ep.ts[r]); }
-            nid = node;
+        const double cost_stored = (input || src == 0) ? 0.0 : lv.cost[t];
+        if (!input)
+            for (int m0 = 0; m0 < src; m0 += 4) {
+                int q[4];
+#pragma unroll
+                for (int u = 0; u < 4; u++) if (m0 + u < src) q[u] = lv.trip_req[(i64)t * src + m0 + u];
+#pragma unroll
+                for (int u = 0; u < 4; u++) if (m0 + u < src) tr[m0 + u] = q[u];
+            }
+        int w = 0;
+        for (int m0 = 0; m0 < slen; m0 += POOL_BATCH) {
+            int code[POOL_BATCH], node[POOL_BATCH];
+#pragma unroll
+            for (int u = 0; u < POOL_BATCH; u++) {
+                code[u] = -1; node[u] = 1;
+                if (m0 + u < slen) {
+                    if (input) code[u] = inc[m0 + u];
+                    else { const Stop sp = in[m0 + u]; code[u] = sp.code; node[u] = sp.node; }
+                }
+            }
+            if (input) {
+#pragma unroll
+                for (int u = 0; u < POOL_BATCH; u++)
+                    if (m0 + u < slen) node[u] = code[u] < 0 ? ep.reb_node[v] : ((code[u] & 1) ? ep.dnid[code[u] >> 1] : ep.onid[code[u] >> 1]);
+            }
+            TT leg[POOL_BATCH];
+            double rtr[POOL_BATCH], rts[POOL_BATCH];
+#pragma unroll
+            for (int u = 0; u < POOL_BATCH; u++) {
+                leg[u] = (TT)0; rtr[u] = 0.0; rts[u] = 0.0;
+                if (m0 + u < slen) {
+                    leg[u] = tt.raw(u ? node[u - 1] : nid, node[u]);
+                    if (code[u] >= 0 && (code[u] & 1)) { rtr[u] = ep.tr[code[u] >> 1]; rts[u] = ep.ts[code[u] >> 1]; }
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < POOL_BATCH; u++) {
+                if (m0 + u < slen) {
+                    sc[m0 + u] = code[u];
+                    acc += (double)leg[u];
+                    if (code[u] >= 0 && (code[u] & 1)) delay += (ep.T + acc - rtr[u] - rts[u]);
+                    nid = node[u];
+                    if (input && to1 > to0 && code[u] >= 0 && !(code[u] & 1)) {     // picking requests, ascending (dispatch_osp.py:121-124)
+                        const int r = code[u] >> 1;
+                        int x = w++;
+                        while (x > 0 && tr[x - 1] > r) { tr[x] = tr[x - 1]; x--; }
+                        tr[x] = r;
+                    }
+                }
+            }
         }
-        pb.ent_cost[e] = (src == SRC_INPUT || src == 0) ? acc : ls.lv[src].cost[t];
+        pb.ent_cost[e] = (input || src == 0) ? acc : cost_stored;
         pb.ent_delay[e] = delay;
     }
 }
