@@ -117,7 +117,7 @@ struct amod_ctx {
     // greedy assignment
     DevBuf ga_pos, ga_rank, ga_order, ga_state, ga_bv, ga_br, ga_tv, ga_tr, ga_sel, ga_cnt;
     // npo
-    DevBuf npo_in, npo_vm, npo_rm, npo_rb, npo_vb, npo_rdt, npo_mdt, npo_cnt, npo_grp, npo_rg;
+    DevBuf npo_in, npo_vm, npo_rm, npo_rb, npo_vb, npo_rdt, npo_mdt, npo_cnt, npo_grp, npo_rg, npo_D, npo_best, npo_tie, npo_scr;
     // routes (8f-2)
     int* d_pred = nullptr; void* d_dist = nullptr;
     DevBuf rt_in, rt_len, rt_off, rt_u, rt_v, rt_t, rt_d, rt_lt, rt_ld, rt_err;
@@ -310,7 +310,7 @@ extern "C" void amod_destroy(amod_ctx* ctx) {
                      &ctx->ent_src, &ctx->ent_trip, &ctx->ent_cost, &ctx->ent_delay, &ctx->trip_off, &ctx->sche_off, &ctx->trip_req,
                      &ctx->sche_code, &ctx->ga_pos, &ctx->ga_rank, &ctx->ga_order, &ctx->ga_state, &ctx->ga_bv, &ctx->ga_br, &ctx->ga_tv, &ctx->ga_tr,
                      &ctx->ga_sel, &ctx->ga_cnt, &ctx->npo_in, &ctx->npo_vm, &ctx->npo_rm, &ctx->npo_rb, &ctx->npo_vb, &ctx->npo_rdt,
-                     &ctx->npo_mdt, &ctx->npo_cnt, &ctx->npo_grp, &ctx->npo_rg};
+                     &ctx->npo_mdt, &ctx->npo_cnt, &ctx->npo_grp, &ctx->npo_rg, &ctx->npo_D, &ctx->npo_best, &ctx->npo_tie, &ctx->npo_scr};
     for (DevBuf* b : all) b->release();
     for (auto& l : ctx->lv) { l.trip_veh.release(); l.trip_req.release(); l.s0.release(); l.nfeas.release(); l.cost.release();
                               l.sch.release(); l.sch_cost.release(); l.final.release(); l.veh_start.release(); }
@@ -1404,16 +1404,21 @@ static int npo_impl(amod_ctx* ctx, const int32_t* idle_nid, int n_idle, const in
         hi = h_idle.data();
         for (int i = 0; i < n_idle; i++) if (hi[i] < 1 || hi[i] > ctx->n_nodes) return ctx->fail(AMOD_E_BADARG, "idle node out of range");
     }
-    std::vector<int> by_node(n_idle);
-    for (int i = 0; i < n_idle; i++) by_node[i] = i;
-    std::stable_sort(by_node.begin(), by_node.end(), [&](int a, int b) { return hi[a] < hi[b]; });
-    std::vector<int> g_node, g_start;
-    for (int i = 0; i < n_idle; i++)
-        if (i == 0 || hi[by_node[i]] != hi[by_node[i - 1]]) { g_node.push_back(hi[by_node[i]]); g_start.push_back(i); }
+    // counting sort by node (stable: vehicles of a group stay in fleet order)
+    std::vector<int> by_node(n_idle), g_node, g_start;
+    {
+        std::vector<int> cnt((size_t)ctx->n_nodes + 2, 0);
+        for (int i = 0; i < n_idle; i++) cnt[hi[i] + 1]++;
+        for (int nd = 1; nd <= ctx->n_nodes; nd++)
+            if (cnt[nd + 1]) { g_node.push_back(nd); g_start.push_back(cnt[nd]); cnt[nd + 1] += cnt[nd]; } else cnt[nd + 1] = cnt[nd];
+        std::vector<int> pos((size_t)ctx->n_nodes + 2, 0);
+        for (size_t gi = 0; gi < g_node.size(); gi++) pos[g_node[gi]] = g_start[gi];
+        for (int i = 0; i < n_idle; i++) by_node[pos[hi[i]]++] = i;
+    }
     g_start.push_back(n_idle);
     const int G = (int)g_node.size();
-    // packed upload: node[G] | start[G+1] | veh[n_idle] | head[G] (zero)
-    std::vector<int> packed((size_t)G + (size_t)G + 1 + (size_t)n_idle + (size_t)G, 0);
+    // packed upload: node[G] | start[G+1] | veh[n_idle] | head[G] (zero) | hrank[G] (set on the device)
+    std::vector<int> packed((size_t)G + (size_t)G + 1 + (size_t)n_idle + 2 * (size_t)G, 0);
     memcpy(packed.data(), g_node.data(), 4 * (size_t)G);
     memcpy(packed.data() + G, g_start.data(), 4 * ((size_t)G + 1));
     memcpy(packed.data() + 2 * (size_t)G + 1, by_node.data(), 4 * (size_t)n_idle);
@@ -1421,18 +1426,30 @@ static int npo_impl(amod_ctx* ctx, const int32_t* idle_nid, int n_idle, const in
     CK(cudaMemcpyAsync(ctx->npo_grp.p, packed.data(), 4 * packed.size(), cudaMemcpyHostToDevice, st));
     NpoGroups grp;
     grp.node = ctx->npo_grp.as<int>(); grp.start = grp.node + G; grp.veh = grp.start + G + 1;
-    grp.head = ctx->npo_grp.as<int>() + 2 * (size_t)G + 1 + (size_t)n_idle; grp.n_groups = G;
+    grp.head = ctx->npo_grp.as<int>() + 2 * (size_t)G + 1 + (size_t)n_idle; grp.hrank = grp.head + G; grp.n_groups = G;
     CK(ctx->npo_vm.ensure(4 * (size_t)n_idle)); CK(ctx->npo_rm.ensure(4 * (size_t)n_pend)); CK(ctx->npo_mdt.ensure(8 * (size_t)n_pend));
-    CK(ctx->npo_cnt.ensure(4));
+    CK(ctx->npo_cnt.ensure(16));
+    CK(ctx->npo_D.ensure(2 * sizeof(TT) * (size_t)G * (size_t)n_pend)); CK(ctx->npo_best.ensure(4 * (size_t)n_pend)); CK(ctx->npo_tie.ensure((size_t)n_pend));
+    CK(ctx->npo_scr.ensure(sizeof(NpoPick) * (size_t)n_pend));
     CK(cudaMemsetAsync(ctx->npo_vm.p, 0xff, 4 * (size_t)n_idle, st));
     CK(cudaMemsetAsync(ctx->npo_rm.p, 0xff, 4 * (size_t)n_pend, st));
-    CK(cudaMemsetAsync(ctx->npo_cnt.p, 0, 4, st));
+    CK(cudaMemsetAsync(ctx->npo_cnt.p, 0, 16, st));
+    int* d_cnt = ctx->npo_cnt.as<int>();
+    unsigned long long* d_cursor = (unsigned long long*)(ctx->npo_cnt.as<char>() + 8);
+    TT* D = ctx->npo_D.as<TT>();
+    TT* DT = D + (size_t)G * (size_t)n_pend;
+    k_npo_matrix<TT><<<ctx->n_sm * 8, 256, 0, st>>>(tt, grp, d_pend, n_pend, D, DT);
     int matched = 0, rounds = 0;
-    while (matched < target) {
-        // every group runs until it is exhausted or blocked by a request that prefers another group for now
-        k_npo_group_run<TT><<<G, NPO_THREADS, 0, st>>>(tt, grp, d_pend, n_pend, ctx->npo_vm.as<int>(), ctx->npo_rm.as<int>(),
-                                                      ctx->npo_mdt.as<double>(), ctx->npo_cnt.as<int>());
-        rounds++;
+    int per_sync = 2;             // rounds between two looks at the match count (a round after the last match returns at once):
+    while (matched < target) {    // 2, 4, 8, 8, ... - a handful of idle vehicles is matched in one or two rounds
+        for (int i = 0; i < per_sync; i++) {
+            k_npo_best<TT><<<(n_pend + 7) / 8, 256, 0, st>>>(DT, grp, n_pend, ctx->npo_rm.as<int>(), ctx->npo_best.as<int>(), ctx->npo_tie.as<uint8_t>(),
+                                                                d_cnt, target, d_cursor);
+            k_npo_accept<TT><<<G, NPO_THREADS, 0, st>>>(D, grp, n_pend, ctx->npo_vm.as<int>(), ctx->npo_rm.as<int>(), ctx->npo_mdt.as<double>(),
+                                                        ctx->npo_best.as<int>(), ctx->npo_tie.as<uint8_t>(), ctx->npo_scr.as<NpoPick>(), d_cursor, d_cnt);
+        }
+        rounds += per_sync;
+        per_sync = std::min(8, per_sync * 2);
         int prev = matched;
         CK(cudaMemcpyAsync(&matched, ctx->npo_cnt.p, 4, cudaMemcpyDeviceToHost, st));
         CK(cudaStreamSynchronize(st));
@@ -1444,10 +1461,12 @@ static int npo_impl(amod_ctx* ctx, const int32_t* idle_nid, int n_idle, const in
     CK(cudaMemcpyAsync(mdt.data(), ctx->npo_mdt.p, 8 * (size_t)n_pend, cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
     // selection order of the reference: ascending (dt, request rank, vehicle rank)
-    std::vector<int> order;
-    for (int r = 0; r < n_pend; r++) if (rm[r] >= 0) order.push_back(r);
-    std::sort(order.begin(), order.end(), [&](int a, int b) { return mdt[a] < mdt[b] || (mdt[a] == mdt[b] && a < b); });
-    for (size_t i = 0; i < order.size(); i++) { out_pend[i] = order[i]; out_idle[i] = rm[order[i]]; out_dt[i] = mdt[order[i]]; }
+    struct Sel { double dt; int r; };
+    std::vector<Sel> order;
+    order.reserve((size_t)target);
+    for (int r = 0; r < n_pend; r++) if (rm[r] >= 0) order.push_back(Sel{mdt[r], r});
+    std::sort(order.begin(), order.end(), [](const Sel& a, const Sel& b) { return a.dt < b.dt || (a.dt == b.dt && a.r < b.r); });
+    for (size_t i = 0; i < order.size(); i++) { out_pend[i] = order[i].r; out_idle[i] = rm[order[i].r]; out_dt[i] = order[i].dt; }
     *n_out = (int)order.size();
     if (n_rounds) *n_rounds = rounds;
     return AMOD_OK;

@@ -59,6 +59,17 @@ struct TupleOut {
 
 struct LaneCount { int n, evals, lookups; };
 
+// x / d for 32-bit x by one multiplication (d fixed per launch): q = hi(x * floor(2^32 / d)) is the quotient or one below it
+struct FastDiv {
+    unsigned d, m;
+    __device__ __forceinline__ explicit FastDiv(unsigned dd) : d(dd), m(dd > 1 ? (unsigned)(0x100000000ull / dd) : 0u) {}
+    __device__ __forceinline__ unsigned div(unsigned x) const {
+        if (d <= 1) return x;
+        unsigned q = __umulhi(x, m);
+        return q + ((x - q * d) >= d ? 1u : 0u);
+    }
+};
+
 // Walk j = i+1 .. for one (sub_sche, i).  `A` = accumulated time at the inserted pick-up.
 // Every feasible (i, j) is appended to the block's record region with its cost.
 template <typename TT>
@@ -123,7 +134,7 @@ k_eval(const DEpoch* __restrict__ epp, Table<TT> tt, Level prev, Level cur, Cont
     const int n_chunks = ctl->overflow ? 0 : ctl->n_chunks[which];
     const int cap = ep.cap;
     // the block sums of the two scans that follow (schedules per chunk; feasible tasks | their schedules << 32) are left as we go
-    const int seg_chunks = (int)scan_seg_len(n_chunks, part_vg), seg_tasks = (int)scan_seg_len(ctl->n_tasks[which], part_vg);
+    const FastDiv seg_chunks((unsigned)scan_seg_len(n_chunks, part_vg)), seg_tasks((unsigned)scan_seg_len(ctl->n_tasks[which], part_vg));
     TupleOut out;
     out.region = tup + (i64)blockIdx.x * region_cap; out.cap = region_cap; out.cursor = &s_cursor; out.c = 0; out.tag = 0;
 
@@ -154,19 +165,19 @@ k_eval(const DEpoch* __restrict__ epp, Table<TT> tt, Level prev, Level cur, Cont
             o_src = rd.s0 + rd.s;                                 // rows are stored in list order: row s IS feasible_sches[s]
             o_PD = tt(o_P, o_D);
         }
-        const int o_w = own ? o_l + 1 : 0;
-        const int o_woff = warp_excl_sum(o_w, lane);              // first lane of the row
-        const int items = __shfl_sync(FULL, o_woff + o_w, 31);
-        // staged stops and legs of the rows before this one: one packed scan (stops < 2^12 | legs << 12)
-        const int o_sl = own ? o_l : 0;
-        const int o_gl = own ? 5 * o_l + 2 : 0;
-        const int o_pk = warp_excl_sum(o_sl | (o_gl << 12), lane);
-        const int o_soff = o_pk & 0xfff;                          // first staged stop of the row
-        const int o_goff = o_pk >> 12;                            // first staged leg of the row
+        // One prefix sum over the rows' lengths places everything: row j (owner lane j) starts at lane L + j, its staged stops at
+        // slot L and its staged legs (5l+2 per row) at slot 5L + 2j, L = stops of the rows before it.
+        const int o_len = own ? o_l : 0;
+        const int o_L = warp_excl_sum(o_len, lane);
+        const int o_j = min(lane, nr);
+        const int o_woff = o_L + o_j;                             // first lane of the row
+        const int items = __shfl_sync(FULL, o_L + o_len, 31) + nr;
+        const int o_soff = o_L;                                   // first staged stop of the row
+        const int o_goff = 5 * o_L + 2 * o_j;                     // first staged leg of the row
 
-        // lane -> (row, pick-up index): found once, by shuffles over the few owner lanes
-        int r = 0;
-        for (int j = 1; j < nr; j++) if (lane >= __shfl_sync(FULL, o_woff, j)) r = j;
+        // lane -> (row, pick-up index): the rows' first lanes as a bit mask (a single row of more than 31 stops starts at lane 0)
+        const unsigned starts = __reduce_or_sync(FULL, own ? (1u << (o_woff & 31)) : 0u);
+        const int r = __popc(starts & (0xffffffffu >> (31 - lane))) - 1;
         const int i_first = lane - __shfl_sync(FULL, o_woff, r);
         const int l = __shfl_sync(FULL, o_l, r);
         const int soff = __shfl_sync(FULL, o_soff, r), goff = __shfl_sync(FULL, o_goff, r);
@@ -268,13 +279,13 @@ k_eval(const DEpoch* __restrict__ epp, Table<TT> tt, Level prev, Level cur, Cont
             lane_cnt[(i64)c * 64 + it0 + lane] = (uint8_t)o.n;     // <= 64 items per chunk
             if (o.n) {      // block sums of the scan over tasks: (task has a feasible schedule) | (its schedules) << 32
                 const int before = atomicAdd(&task_nfeas[task], o.n);
-                atomicAdd(&part[part_vg + task / seg_tasks], (before == 0 ? 1ull : 0ull) | ((unsigned long long)o.n << 32));
+                atomicAdd(&part[part_vg + seg_tasks.div((unsigned)task)], (before == 0 ? 1ull : 0ull) | ((unsigned long long)o.n << 32));
             }
             cnt_total += o.n;
         }
         if (items <= 32) lane_cnt[(i64)c * 64 + 32 + lane] = 0;
         cnt_total = warp_sum(cnt_total);
-        if (lane == 0) { chunk_cnt[c] = cnt_total; if (cnt_total) atomicAdd(&part[c / seg_chunks], (unsigned long long)cnt_total); }
+        if (lane == 0) { chunk_cnt[c] = cnt_total; if (cnt_total) atomicAdd(&part[seg_chunks.div((unsigned)c)], (unsigned long long)cnt_total); }
     }
     acc_evals = warp_sum(acc_evals);
     acc_lookups = warp_sum(acc_lookups);

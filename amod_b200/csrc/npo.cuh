@@ -7,26 +7,30 @@
 #pragma once
 #include "common.cuh"
 
-#define NPO_THREADS 256
-#define NPO_CACHE_BYTES 32768
+#define NPO_THREADS 1024
+#define NPO_SCAP 2048
+#define NPO_UNROLL 4        // requests a thread has in flight per step of a pass
 
 struct Key { double dt; int idx; };
 __device__ __forceinline__ bool key_less(const Key& a, const Key& b) { return a.dt < b.dt || (a.dt == b.dt && a.idx < b.idx); }
+__device__ __forceinline__ bool key_eq(const Key& a, const Key& b) { return a.dt == b.dt && a.idx == b.idx; }
+#define KEY_INF Key{DINF, 0x7fffffff}
+struct NpoPick { double dt; int r; int pad; };
 
-__device__ __forceinline__ Key block_min_key(Key k, Key* smem) {
+__device__ __forceinline__ Key warp_min_key(Key k) {
     for (int o = 16; o; o >>= 1) {
         Key t; t.dt = __shfl_xor_sync(FULL, k.dt, o); t.idx = __shfl_xor_sync(FULL, k.idx, o);
         if (key_less(t, k)) k = t;
     }
+    return k;
+}
+__device__ __forceinline__ Key block_min_key(Key k, Key* smem) {
+    k = warp_min_key(k);
     int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     if (lane == 0) smem[w] = k;
     __syncthreads();
     if (w == 0) {
-        k = lane < NPO_THREADS / 32 ? smem[lane] : Key{DINF, 0x7fffffff};
-        for (int o = 16; o; o >>= 1) {
-            Key t; t.dt = __shfl_xor_sync(FULL, k.dt, o); t.idx = __shfl_xor_sync(FULL, k.idx, o);
-            if (key_less(t, k)) k = t;
-        }
+        k = warp_min_key(lane < NPO_THREADS / 32 ? smem[lane] : KEY_INF);
         if (lane == 0) smem[0] = k;
     }
     __syncthreads();
@@ -36,94 +40,188 @@ __device__ __forceinline__ Key block_min_key(Key k, Key* smem) {
 }
 
 // Idle vehicles standing at the same node (a station, platform.py:50-55) have the same travel time to every request and are
-// taken in rank order, so they form a GROUP: a node, its vehicles in fleet order and a head pointer.  A request's best free
-// vehicle is the head of the group minimising (dt, head's rank); every vehicle of a group has the same best free request
-// (min (dt, request rank)); an edge is committed when the two agree.  The searches run over groups (tens to thousands)
-// instead of vehicles, and a minimum found in an earlier round stays valid for as long as that partner is free (the free sets
-// only shrink), so most rounds touch a handful of requests and groups.
+// taken in rank order, so they form a GROUP: a node, its vehicles in fleet order and a head pointer (vehicles already matched).
+// A request's best free vehicle is the head of the group minimising (dt, head's rank); every free vehicle of a group has the
+// same order of preference over the free requests, (dt, request rank).
+//
+// Rounds.  k_npo_best gives every free request its best group.  k_npo_accept (one block per group) then accepts, all at once,
+// the longest PREFIX of the group's preference order made of requests that name this group as their best: its i-th element
+// goes to the group's i-th free vehicle.  Why that is the reference's stable sort + greedy scan (rebalancing_npo.py:48-59):
+// by induction over the prefix, once elements 0..i-1 are matched the i-th free vehicle's smallest remaining edge is element i,
+// and element i's smallest remaining edge leads into this group (to that very vehicle, the lowest free rank) - the edge is
+// locally dominant, and a locally dominant edge is always taken by the sorted scan; matches made elsewhere in the same round
+// only remove alternatives.  Ties: "best" was decided with the group's HEAD vehicle; a request whose dt ties with another
+// group's may lose that tie against a later vehicle of this group, so such a request is only accepted as element 0 and ends
+// the prefix anywhere else.  The globally smallest remaining edge is always element 0 of its group, so every round makes
+// progress; a station with a thousand idle vehicles is served in a few rounds instead of a thousand dependent steps.
 struct NpoGroups {
     const int* node;      // [n_groups]
     const int* start;     // [n_groups+1] into veh[]
     const int* veh;       // vehicle ranks, grouped by node, ascending within a group
     int* head;            // [n_groups] vehicles of the group already matched
+    int* hrank;           // [n_groups] rank of the group's head vehicle, -1 when the group is exhausted
     int n_groups;
 };
 
-// One block per group.  The block repeatedly (1) finds the group's best free request r under (dt, request rank), (2) checks that
-// r prefers this group: no other group with free vehicles offers r a smaller (dt, rank of its head vehicle), and (3) commits
-// r to the group's head vehicle.  It stops when the group is exhausted, no request is free, or its best request prefers
-// another group for now (that request will be settled elsewhere, or come back once the other group runs out: next launch).
-// All groups run concurrently; the decisions are safe under that concurrency because everything they read is monotone:
-// a request never becomes free again, a group never regains a vehicle, and heads only move to higher ranks, so "r prefers
-// g" can only turn from false to true.  A request is claimed by compare-and-swap, so it is matched exactly once.
-// This is the reference's stable sort + greedy scan (rebalancing_npo.py:48-59): the edges of one group are accepted in
-// (dt, request rank) order and each takes the lowest free vehicle rank, exactly as the sorted scan meets them.
+// D[g][r] = travel time from group g's node to request r's origin (the only table look-ups of the match), hrank
+template <typename TT>
+__global__ void k_npo_matrix(Table<TT> tt, NpoGroups g, const int* __restrict__ pend_onid, int n_pend, TT* __restrict__ D, TT* __restrict__ DT) {
+    const i64 n = (i64)g.n_groups * n_pend, stride = (i64)gridDim.x * blockDim.x;
+    for (i64 e = (i64)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += stride) {
+        const int x = (int)(e / n_pend), r = (int)(e - (i64)x * n_pend);
+        const TT d = tt.raw(g.node[x], pend_onid[r]);
+        D[e] = d;                                   // [group][request]: a group's block walks its row (k_npo_accept)
+        DT[(i64)r * g.n_groups + x] = d;            // [request][group]: a request's warp walks its row (k_npo_best)
+    }
+    for (i64 x = (i64)blockIdx.x * blockDim.x + threadIdx.x; x < g.n_groups; x += stride) g.hrank[x] = g.veh[g.start[x]];
+}
+
+// per free request (one warp each, lanes over the groups): the group offering the smallest (dt, rank of its head vehicle), and
+// whether another group ties in dt
+template <typename TT>
+__global__ void k_npo_best(const TT* __restrict__ DT, NpoGroups g, int n_pend, const int* __restrict__ req_match,
+                           int* __restrict__ best_g, uint8_t* __restrict__ tie, const int* __restrict__ n_matched, int target,
+                           unsigned long long* __restrict__ cursor) {
+    const int gt = blockIdx.x * blockDim.x + threadIdx.x;
+    if (gt == 0) *cursor = 0ull;                 // the accept kernel's scratch list starts empty every round
+    if (*n_matched >= target) return;
+    const int r = gt >> 5, lane = threadIdx.x & 31;
+    if (r >= n_pend || req_match[r] >= 0) return;     // (warp-uniform)
+    const TT* __restrict__ row = DT + (i64)r * g.n_groups;
+    Key best = KEY_INF;
+    int bg = -1, same = 0;                       // same = groups seen with best.dt besides the best one
+    for (int x = lane; x < g.n_groups; x += 32) {
+        const int hr = g.hrank[x];
+        if (hr < 0) continue;
+        const Key c{(double)row[x], hr};
+        if (c.dt == best.dt) same++;
+        else if (c.dt < best.dt) same = 0;
+        if (key_less(c, best)) { best = c; bg = x; }
+    }
+    for (int o = 16; o; o >>= 1) {
+        Key t; t.dt = __shfl_xor_sync(FULL, best.dt, o); t.idx = __shfl_xor_sync(FULL, best.idx, o);
+        const int tg = __shfl_xor_sync(FULL, bg, o), ts = __shfl_xor_sync(FULL, same, o);
+        if (tg < 0) continue;                    // (the partner saw no group at all)
+        if (bg < 0) { best = t; bg = tg; same = ts; continue; }
+        if (t.dt == best.dt) same += ts + 1;
+        else if (t.dt < best.dt) same = ts;
+        if (key_less(t, best)) { best = t; bg = tg; }
+    }
+    if (lane == 0) { best_g[r] = bg; tie[r] = same > 0; }
+}
+
 template <typename TT>
 __global__ void __launch_bounds__(NPO_THREADS)
-k_npo_group_run(Table<TT> tt, NpoGroups g, const int* __restrict__ pend_onid, int n_pend, int* veh_match, int* req_match,
-                double* __restrict__ match_dt, int* n_matched) {
+k_npo_accept(const TT* __restrict__ D, NpoGroups g, int n_pend, int* veh_match, int* req_match, double* __restrict__ match_dt,
+             const int* __restrict__ best_g, const uint8_t* __restrict__ tie, NpoPick* __restrict__ scratch,
+             unsigned long long* __restrict__ cursor, int* n_matched) {
     __shared__ Key smem[NPO_THREADS / 32];
-    __shared__ int s_flag;
-    __shared__ TT s_dt[NPO_CACHE_BYTES / sizeof(TT)];     // the group's travel times to the first requests: gathered once, not per step
-    constexpr int NC = NPO_CACHE_BYTES / sizeof(TT);
+    __shared__ Key s_two[NPO_THREADS / 32][2];
+    __shared__ int s_w;
+    __shared__ unsigned long long s_base;
+    __shared__ NpoPick s_pick[NPO_SCAP];         // the accepted set of this round (beyond NPO_SCAP: a stretch of the global scratch list)
     const int x = blockIdx.x;
-    const int nid = g.node[x];
     const int size = g.start[x + 1] - g.start[x];
-    volatile int* vhead = g.head;
-    volatile int* vreq = req_match;
-    if (vhead[x] >= size) return;
-    // a request known to be taken carries +inf here: the free set as this block knows it (requests taken by other groups in the
-    // meantime are discovered when the compare-and-swap fails; everything read is monotone, so a stale view only costs a retry)
-    for (int r = threadIdx.x; r < n_pend && r < NC; r += NPO_THREADS) s_dt[r] = req_match[r] >= 0 ? (TT)INFINITY : tt.raw(nid, pend_onid[r]);
-    __syncthreads();
-    for (int step = 0; step < 2 * n_pend + 64; step++) {      // (bounded: a launch can never spin; the host relaunches while matches are made)
-        const int head = vhead[x];
-        if (head >= size) return;
-        // (1) the group's best free request
-        Key k{DINF, 0x7fffffff};
-        for (int r = threadIdx.x; r < n_pend && r < NC; r += NPO_THREADS) {
-            Key c{(double)s_dt[r], r};
-            if (key_less(c, k)) k = c;
+    const int head = g.head[x];
+    const int c = size - head;
+    if (c <= 0) return;
+    const TT* __restrict__ Dg = D + (i64)x * n_pend;
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    // pass 1: first = head of the group's preference order; A = its first request that names another group; t1 < t2 = its first
+    // two requests that name this group but tie in dt with another
+    Key first = KEY_INF, A = KEY_INF, t1 = KEY_INF, t2 = KEY_INF;
+    for (int r0 = threadIdx.x; r0 < n_pend; r0 += NPO_UNROLL * NPO_THREADS) {
+        int rm[NPO_UNROLL], bg[NPO_UNROLL]; TT d[NPO_UNROLL]; uint8_t ti[NPO_UNROLL];
+#pragma unroll
+        for (int u = 0; u < NPO_UNROLL; u++) {
+            const int r = r0 + u * NPO_THREADS;
+            rm[u] = 0; bg[u] = -1; d[u] = (TT)0; ti[u] = 0;
+            if (r < n_pend) { rm[u] = req_match[r]; d[u] = Dg[r]; bg[u] = best_g[r]; ti[u] = tie[r]; }
         }
-        for (int r = NC + threadIdx.x; r < n_pend; r += NPO_THREADS) {      // beyond the cache: straight from memory
-            if (vreq[r] >= 0) continue;
-            Key c{tt(nid, pend_onid[r]), r};
-            if (key_less(c, k)) k = c;
+#pragma unroll
+        for (int u = 0; u < NPO_UNROLL; u++) {
+            const int r = r0 + u * NPO_THREADS;
+            if (r >= n_pend || rm[u] >= 0) continue;
+            const Key k{(double)d[u], r};
+            if (key_less(k, first)) first = k;
+            if (bg[u] != x) { if (key_less(k, A)) A = k; }
+            else if (ti[u]) { if (key_less(k, t1)) { t2 = t1; t1 = k; } else if (key_less(k, t2)) t2 = k; }
         }
-        k = block_min_key(k, smem);
-        if (k.idx == 0x7fffffff || !(k.dt < DINF)) return;
-        const int r = k.idx, v = g.veh[g.start[x] + head], on = pend_onid[r];
-        // taken by another group since this block last looked?  (ONE thread reads: the answer must be the same for the whole block)
-        if (threadIdx.x == 0) {
-            s_flag = vreq[r] >= 0 ? 2 : 1;
-            if (s_flag == 2 && r < NC) s_dt[r] = (TT)INFINITY;      // forget it and look again
+    }
+    first = block_min_key(first, smem);
+    if (first.idx == 0x7fffffff) return;         // no free request
+    A = block_min_key(A, smem);
+    {   // smallest two of the tie proposers
+        for (int o = 16; o; o >>= 1) {
+            Key u1, u2;
+            u1.dt = __shfl_xor_sync(FULL, t1.dt, o); u1.idx = __shfl_xor_sync(FULL, t1.idx, o);
+            u2.dt = __shfl_xor_sync(FULL, t2.dt, o); u2.idx = __shfl_xor_sync(FULL, t2.idx, o);
+            if (key_less(u1, t1)) { t2 = key_less(t1, u2) ? t1 : u2; t1 = u1; }
+            else if (key_less(u1, t2)) t2 = u1;
         }
+        if (lane == 0) { s_two[w][0] = t1; s_two[w][1] = t2; }
         __syncthreads();
-        if (s_flag == 2) { __syncthreads(); continue; }
-        // (2) does r prefer this group?
-        const Key mine{k.dt, v};
-        bool lose = false;
-        for (int y = threadIdx.x; y < g.n_groups && !lose; y += NPO_THREADS) {
-            if (y == x) continue;
-            const int hy = vhead[y];
-            if (hy >= g.start[y + 1] - g.start[y]) continue;
-            Key c{tt(g.node[y], on), g.veh[g.start[y] + hy]};
-            if (key_less(c, mine)) lose = true;
-        }
-        if (lose) s_flag = 0;
-        __syncthreads();
-        if (!s_flag) return;
-        // (3) commit
-        if (threadIdx.x == 0) {
-            if (atomicCAS(&req_match[r], -1, v) == -1) {
-                veh_match[v] = r; match_dt[r] = k.dt;
-                vhead[x] = head + 1;
-                atomicAdd(n_matched, 1);
+        t1 = KEY_INF; t2 = KEY_INF;
+        for (int y = 0; y < NPO_THREADS / 32; y++)
+            for (int z = 0; z < 2; z++) {
+                const Key u = s_two[y][z];
+                if (key_less(u, t1)) { t2 = t1; t1 = u; } else if (key_less(u, t2) && !key_eq(u, t1)) t2 = u;
             }
-            if (r < NC) s_dt[r] = (TT)INFINITY;       // taken, by this group or (compare-and-swap failed) by another
-            __threadfence();
+        __syncthreads();
+    }
+    const Key B = key_eq(t1, first) ? t2 : t1;   // a tying request may only be accepted as element 0
+    const Key stop = key_less(A, B) ? A : B;
+    // pass 2: the requests before `stop` (all name this group), into the shared list; counted as they go
+    if (threadIdx.x == 0) s_w = 0;
+    __syncthreads();
+    NpoPick* S = s_pick;
+    for (int attempt = 0; attempt < 2; attempt++) {
+        for (int r0 = threadIdx.x; r0 < n_pend; r0 += NPO_UNROLL * NPO_THREADS) {
+            int rm[NPO_UNROLL], bg[NPO_UNROLL]; TT d[NPO_UNROLL];
+#pragma unroll
+            for (int u = 0; u < NPO_UNROLL; u++) {
+                const int r = r0 + u * NPO_THREADS;
+                rm[u] = 0; bg[u] = -1; d[u] = (TT)0;
+                if (r < n_pend) { rm[u] = req_match[r]; d[u] = Dg[r]; bg[u] = best_g[r]; }
+            }
+#pragma unroll
+            for (int u = 0; u < NPO_UNROLL; u++) {
+                const int r = r0 + u * NPO_THREADS;
+                if (r >= n_pend || rm[u] >= 0 || bg[u] != x) continue;
+                const Key k{(double)d[u], r};
+                if (key_less(k, stop)) {
+                    const int p = atomicAdd(&s_w, 1);
+                    if (attempt || p < NPO_SCAP) { S[p].dt = k.dt; S[p].r = r; }
+                }
+            }
         }
         __syncthreads();
+        if (attempt || s_w <= NPO_SCAP) break;
+        // too many for shared memory: claim a stretch of the global list (the accepted sets of one round are disjoint: <= n_pend in total)
+        const int need = s_w;
+        __syncthreads();
+        if (threadIdx.x == 0) { s_base = atomicAdd(cursor, (unsigned long long)need); s_w = 0; }
+        __syncthreads();
+        S = scratch + s_base;
+    }
+    const int m = s_w;
+    if (m == 0) return;                          // the head of this group's order names another group: wait for it
+    // pass 3: rank within the accepted set = which of the group's free vehicles takes the request
+    const int* __restrict__ vv = g.veh + g.start[x] + head;
+    for (int e = threadIdx.x; e < m; e += NPO_THREADS) {
+        const Key k{S[e].dt, S[e].r};
+        int rank = 0;
+        for (int y = 0; y < m; y++) { const Key u{S[y].dt, S[y].r}; rank += key_less(u, k) ? 1 : 0; }
+        if (rank < c) {
+            const int v = vv[rank];
+            req_match[k.idx] = v; veh_match[v] = k.idx; match_dt[k.idx] = k.dt;
+        }
+    }
+    if (threadIdx.x == 0) {
+        const int acc = min(m, c);
+        g.head[x] = head + acc;
+        g.hrank[x] = head + acc < size ? g.veh[g.start[x] + head + acc] : -1;
+        atomicAdd(n_matched, acc);
     }
 }
 
