@@ -1428,18 +1428,42 @@ static int npo_impl(amod_ctx* ctx, const int32_t* idle_nid, int n_idle, const in
     grp.node = ctx->npo_grp.as<int>(); grp.start = grp.node + G; grp.veh = grp.start + G + 1;
     grp.head = ctx->npo_grp.as<int>() + 2 * (size_t)G + 1 + (size_t)n_idle; grp.hrank = grp.head + G; grp.n_groups = G;
     CK(ctx->npo_vm.ensure(4 * (size_t)n_idle)); CK(ctx->npo_rm.ensure(4 * (size_t)n_pend)); CK(ctx->npo_mdt.ensure(8 * (size_t)n_pend));
-    CK(ctx->npo_cnt.ensure(16));
+    CK(ctx->npo_cnt.ensure(32));
     CK(ctx->npo_D.ensure(2 * sizeof(TT) * (size_t)G * (size_t)n_pend)); CK(ctx->npo_best.ensure(4 * (size_t)n_pend)); CK(ctx->npo_tie.ensure((size_t)n_pend));
     CK(ctx->npo_scr.ensure(sizeof(NpoPick) * (size_t)n_pend));
     CK(cudaMemsetAsync(ctx->npo_vm.p, 0xff, 4 * (size_t)n_idle, st));
     CK(cudaMemsetAsync(ctx->npo_rm.p, 0xff, 4 * (size_t)n_pend, st));
-    CK(cudaMemsetAsync(ctx->npo_cnt.p, 0, 16, st));
+    CK(cudaMemsetAsync(ctx->npo_cnt.p, 0, 32, st));      // matched | - | cursor (8 B) | barrier | rounds | error
     int* d_cnt = ctx->npo_cnt.as<int>();
     unsigned long long* d_cursor = (unsigned long long*)(ctx->npo_cnt.as<char>() + 8);
     TT* D = ctx->npo_D.as<TT>();
     TT* DT = D + (size_t)G * (size_t)n_pend;
     k_npo_matrix<TT><<<ctx->n_sm * 8, 256, 0, st>>>(tt, grp, d_pend, n_pend, D, DT);
     int matched = 0, rounds = 0;
+    // every round in one cooperative launch when all the groups' blocks are resident together (AMOD_NPO_NO_PERSIST=1: never)
+    {
+        static int occ_blocks = -1;
+        if (occ_blocks < 0) { if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_blocks, k_npo_rounds<TT>, NPO_THREADS, 0) != cudaSuccess) occ_blocks = 0; cudaGetLastError(); }
+        int coop = 0;
+        cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, ctx->device);
+        if (coop && G <= occ_blocks * ctx->n_sm && !getenv("AMOD_NPO_NO_PERSIST")) {
+            unsigned* d_bar = (unsigned*)(ctx->npo_cnt.as<char>() + 16);
+            int* d_rounds = (int*)(ctx->npo_cnt.as<char>() + 20);
+            int* d_err = (int*)(ctx->npo_cnt.as<char>() + 24);
+            const TT* cD = D; const TT* cDT = DT;
+            int np = n_pend, tg = target, max_rounds = target + 8;
+            int* vm = ctx->npo_vm.as<int>(); int* rmm = ctx->npo_rm.as<int>(); double* md = ctx->npo_mdt.as<double>();
+            int* bgp = ctx->npo_best.as<int>(); uint8_t* tp = ctx->npo_tie.as<uint8_t>(); NpoPick* scr = ctx->npo_scr.as<NpoPick>();
+            void* args[] = {&cD, &cDT, &grp, &np, &vm, &rmm, &md, &bgp, &tp, &scr, &d_cursor, &d_cnt, &tg, &d_bar, &max_rounds, &d_rounds, &d_err};
+            if (cudaLaunchCooperativeKernel((void*)k_npo_rounds<TT>, dim3((unsigned)G), dim3(NPO_THREADS), args, 0, st) == cudaSuccess) {
+                int h[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+                CK(cudaMemcpyAsync(h, ctx->npo_cnt.p, 32, cudaMemcpyDeviceToHost, st));
+                CK(cudaStreamSynchronize(st));
+                if (h[6]) return ctx->fail(AMOD_E_CUDA, "npo: the device-wide barrier timed out");
+                matched = h[0]; rounds = h[5];
+            } else cudaGetLastError();       // (not launchable after all: the per-round launches below do the work)
+        }
+    }
     int per_sync = 2;             // rounds between two looks at the match count (a round after the last match returns at once):
     while (matched < target) {    // 2, 4, 8, 8, ... - a handful of idle vehicles is matched in one or two rounds
         for (int i = 0; i < per_sync; i++) {

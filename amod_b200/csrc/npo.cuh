@@ -76,22 +76,21 @@ __global__ void k_npo_matrix(Table<TT> tt, NpoGroups g, const int* __restrict__ 
     for (i64 x = (i64)blockIdx.x * blockDim.x + threadIdx.x; x < g.n_groups; x += stride) g.hrank[x] = g.veh[g.start[x]];
 }
 
+// Everything the rounds change is read with ld.global.cg (L2): the persistent variant runs many rounds inside one launch, and a
+// line cached in an SM's L1 in an earlier round would be stale.
+__device__ __forceinline__ int ldcg_i(const int* p) { return __ldcg(p); }
+__device__ __forceinline__ int ldcg_b(const uint8_t* p) { return (int)__ldcg((const unsigned char*)p); }
+
 // per free request (one warp each, lanes over the groups): the group offering the smallest (dt, rank of its head vehicle), and
 // whether another group ties in dt
 template <typename TT>
-__global__ void k_npo_best(const TT* __restrict__ DT, NpoGroups g, int n_pend, const int* __restrict__ req_match,
-                           int* __restrict__ best_g, uint8_t* __restrict__ tie, const int* __restrict__ n_matched, int target,
-                           unsigned long long* __restrict__ cursor) {
-    const int gt = blockIdx.x * blockDim.x + threadIdx.x;
-    if (gt == 0) *cursor = 0ull;                 // the accept kernel's scratch list starts empty every round
-    if (*n_matched >= target) return;
-    const int r = gt >> 5, lane = threadIdx.x & 31;
-    if (r >= n_pend || req_match[r] >= 0) return;     // (warp-uniform)
+__device__ __forceinline__ void npo_best_request(const TT* __restrict__ DT, const NpoGroups& g, int r, int lane,
+                                                 int* __restrict__ best_g, uint8_t* __restrict__ tie) {
     const TT* __restrict__ row = DT + (i64)r * g.n_groups;
     Key best = KEY_INF;
     int bg = -1, same = 0;                       // same = groups seen with best.dt besides the best one
     for (int x = lane; x < g.n_groups; x += 32) {
-        const int hr = g.hrank[x];
+        const int hr = ldcg_i(g.hrank + x);
         if (hr < 0) continue;
         const Key c{(double)row[x], hr};
         if (c.dt == best.dt) same++;
@@ -111,18 +110,38 @@ __global__ void k_npo_best(const TT* __restrict__ DT, NpoGroups g, int n_pend, c
 }
 
 template <typename TT>
-__global__ void __launch_bounds__(NPO_THREADS)
-k_npo_accept(const TT* __restrict__ D, NpoGroups g, int n_pend, int* veh_match, int* req_match, double* __restrict__ match_dt,
-             const int* __restrict__ best_g, const uint8_t* __restrict__ tie, NpoPick* __restrict__ scratch,
-             unsigned long long* __restrict__ cursor, int* n_matched) {
-    __shared__ Key smem[NPO_THREADS / 32];
-    __shared__ Key s_two[NPO_THREADS / 32][2];
-    __shared__ int s_w;
-    __shared__ unsigned long long s_base;
-    __shared__ NpoPick s_pick[NPO_SCAP];         // the accepted set of this round (beyond NPO_SCAP: a stretch of the global scratch list)
-    const int x = blockIdx.x;
+__global__ void k_npo_best(const TT* __restrict__ DT, NpoGroups g, int n_pend, const int* __restrict__ req_match,
+                           int* __restrict__ best_g, uint8_t* __restrict__ tie, const int* __restrict__ n_matched, int target,
+                           unsigned long long* __restrict__ cursor) {
+    const int gt = blockIdx.x * blockDim.x + threadIdx.x;
+    if (gt == 0) *cursor = 0ull;                 // the accept kernel's scratch list starts empty every round
+    if (*n_matched >= target) return;
+    const int r = gt >> 5, lane = threadIdx.x & 31;
+    if (r >= n_pend || req_match[r] >= 0) return;     // (warp-uniform)
+    npo_best_request(DT, g, r, lane, best_g, tie);
+}
+
+struct NpoShared {
+    Key smem[NPO_THREADS / 32];
+    Key s_two[NPO_THREADS / 32][2];
+    int s_w;
+    unsigned long long s_base;
+    NpoPick s_pick[NPO_SCAP];                    // the accepted set of this round (beyond NPO_SCAP: a stretch of the global scratch list)
+};
+
+// one round of group x (the whole block); every exit is taken by all threads together
+template <typename TT>
+__device__ __forceinline__ void npo_accept_group(NpoShared& sh, const TT* __restrict__ D, const NpoGroups& g, int x, int n_pend, int* veh_match,
+                                                 int* req_match, double* __restrict__ match_dt, const int* __restrict__ best_g,
+                                                 const uint8_t* __restrict__ tie, NpoPick* __restrict__ scratch,
+                                                 unsigned long long* __restrict__ cursor, int* n_matched) {
+    Key* smem = sh.smem;
+    Key (*s_two)[2] = sh.s_two;
+    int& s_w = sh.s_w;
+    unsigned long long& s_base = sh.s_base;
+    NpoPick* s_pick = sh.s_pick;
     const int size = g.start[x + 1] - g.start[x];
-    const int head = g.head[x];
+    const int head = ldcg_i(g.head + x);
     const int c = size - head;
     if (c <= 0) return;
     const TT* __restrict__ Dg = D + (i64)x * n_pend;
@@ -136,7 +155,7 @@ k_npo_accept(const TT* __restrict__ D, NpoGroups g, int n_pend, int* veh_match, 
         for (int u = 0; u < NPO_UNROLL; u++) {
             const int r = r0 + u * NPO_THREADS;
             rm[u] = 0; bg[u] = -1; d[u] = (TT)0; ti[u] = 0;
-            if (r < n_pend) { rm[u] = req_match[r]; d[u] = Dg[r]; bg[u] = best_g[r]; ti[u] = tie[r]; }
+            if (r < n_pend) { rm[u] = ldcg_i(req_match + r); d[u] = Dg[r]; bg[u] = ldcg_i(best_g + r); ti[u] = (uint8_t)ldcg_b(tie + r); }
         }
 #pragma unroll
         for (int u = 0; u < NPO_UNROLL; u++) {
@@ -182,7 +201,7 @@ k_npo_accept(const TT* __restrict__ D, NpoGroups g, int n_pend, int* veh_match, 
             for (int u = 0; u < NPO_UNROLL; u++) {
                 const int r = r0 + u * NPO_THREADS;
                 rm[u] = 0; bg[u] = -1; d[u] = (TT)0;
-                if (r < n_pend) { rm[u] = req_match[r]; d[u] = Dg[r]; bg[u] = best_g[r]; }
+                if (r < n_pend) { rm[u] = ldcg_i(req_match + r); d[u] = Dg[r]; bg[u] = ldcg_i(best_g + r); }
             }
 #pragma unroll
             for (int u = 0; u < NPO_UNROLL; u++) {
@@ -223,6 +242,58 @@ k_npo_accept(const TT* __restrict__ D, NpoGroups g, int n_pend, int* veh_match, 
         g.hrank[x] = head + acc < size ? g.veh[g.start[x] + head + acc] : -1;
         atomicAdd(n_matched, acc);
     }
+    __syncthreads();                             // (the shared list is reused by the next round of the persistent variant)
+}
+
+template <typename TT>
+__global__ void __launch_bounds__(NPO_THREADS)
+k_npo_accept(const TT* __restrict__ D, NpoGroups g, int n_pend, int* veh_match, int* req_match, double* __restrict__ match_dt,
+             const int* __restrict__ best_g, const uint8_t* __restrict__ tie, NpoPick* __restrict__ scratch,
+             unsigned long long* __restrict__ cursor, int* n_matched) {
+    __shared__ NpoShared sh;
+    npo_accept_group(sh, D, g, (int)blockIdx.x, n_pend, veh_match, req_match, match_dt, best_g, tie, scratch, cursor, n_matched);
+}
+
+// All rounds in ONE launch when every group's block is resident at once (cooperative launch: tens of groups - the stations - is
+// the case that needs many rounds): the two phases of a round are separated by a device-wide barrier (arrive with a release,
+// spin on an acquire load; bounded, so a fault cannot hang the device) instead of a kernel boundary, and the host synchronises once.
+__device__ __forceinline__ bool npo_grid_barrier(unsigned* bar, unsigned want, int* err) {
+    __shared__ int s_ok;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        atomicAdd(bar, 1u);
+        unsigned v = 0;
+        long long spins = 0;
+        do { asm volatile("ld.acquire.gpu.u32 %0, [%1];" : "=r"(v) : "l"(bar) : "memory"); } while (v < want && ++spins < (1ll << 26) && !ldcg_i(err));
+        if (v < want) atomicExch(err, 1);
+        s_ok = v >= want;
+        __threadfence();
+    }
+    __syncthreads();
+    return s_ok != 0;
+}
+
+template <typename TT>
+__global__ void __launch_bounds__(NPO_THREADS)
+k_npo_rounds(const TT* __restrict__ D, const TT* __restrict__ DT, NpoGroups g, int n_pend, int* veh_match, int* req_match,
+             double* __restrict__ match_dt, int* best_g, uint8_t* tie, NpoPick* __restrict__ scratch,
+             unsigned long long* cursor, int* n_matched, int target, unsigned* bar, int max_rounds, int* rounds_out, int* err) {
+    __shared__ NpoShared sh;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = gridDim.x * (NPO_THREADS / 32);
+    unsigned phase = 0;
+    int round = 0;
+    while (round < max_rounds) {
+        if (blockIdx.x == 0 && threadIdx.x == 0) *cursor = 0ull;
+        for (int r = blockIdx.x * (NPO_THREADS / 32) + warp; r < n_pend; r += nw)
+            if (ldcg_i(req_match + r) < 0) npo_best_request(DT, g, r, lane, best_g, tie);
+        if (!npo_grid_barrier(bar, ++phase * gridDim.x, err)) break;
+        npo_accept_group(sh, D, g, (int)blockIdx.x, n_pend, veh_match, req_match, match_dt, best_g, tie, scratch, cursor, n_matched);
+        round++;
+        if (!npo_grid_barrier(bar, ++phase * gridDim.x, err)) break;
+        if (ldcg_i(n_matched) >= target) break;       // (read after the barrier: the same answer in every block)
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) *rounds_out = round;
 }
 
 template <typename TT>

@@ -120,18 +120,26 @@ def test_cuda_npo_matches_reference(family):
         assert np.array_equal(T + od[order] + 240, z[f"c{i}_m_ddl"])
 
 
-def test_cuda_npo_matches_oracle_with_ties():
+@pytest.mark.parametrize("persistent", [True, False], ids=["one-launch", "launch-per-round"])
+def test_cuda_npo_matches_oracle_with_ties(persistent, monkeypatch):
+    """Both forms of the prefix rounds (all rounds in one cooperative launch / two launches per round), on tables full of exact
+    ties, with stations (many idle vehicles on one node), more vehicles than requests and the reverse."""
     import oracle
-    tt = synth.random_table(30, 9, "ties")
-    b = builder_for(tt)
+    if not persistent:
+        monkeypatch.setenv("AMOD_NPO_NO_PERSIST", "1")
     rng = np.random.default_rng(4)
-    for n_idle, n_pend in ((40, 25), (25, 40), (1, 7), (300, 200)):
-        idle = rng.integers(1, 31, size=n_idle).astype(np.int32)
-        pend = rng.integers(1, 31, size=n_pend).astype(np.int32)
-        a = oracle.npo_match(tt, idle, pend)
-        g = b.npo_match(idle, pend)
-        for x, y in zip(a, g):
-            assert np.array_equal(x, y)
+    for kind, n_nodes in (("ties", 30), ("ties", 200), ("real", 200)):
+        tt = synth.random_table(n_nodes, 9, kind)
+        b = PoolBuilder(tt)
+        for n_idle, n_pend in ((40, 25), (25, 40), (1, 7), (300, 200), (900, 1100), (2500, 600)):
+            stations = rng.integers(1, n_nodes + 1, size=5)
+            idle = np.where(rng.random(n_idle) < 0.6, rng.choice(stations, n_idle), rng.integers(1, n_nodes + 1, size=n_idle)).astype(np.int32)
+            pend = rng.integers(1, n_nodes + 1, size=n_pend).astype(np.int32)
+            a = oracle.npo_match(tt, idle, pend)
+            g = b.npo_match(idle, pend)
+            for x, y in zip(a, g):
+                assert np.array_equal(x, y), (kind, n_nodes, n_idle, n_pend)
+        b.close()
 
 
 def test_seam_functions_return_reference_style_records():
