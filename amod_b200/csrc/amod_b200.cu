@@ -88,6 +88,7 @@ struct amod_ctx {
     unsigned long long buf_gen = 0;
     bool use_graph = true;
     int gen_pairs_occ[4] = {0, 0, 0, 0};   // resident blocks per SM of k_gen_pairs<1 / 4 / 8 / AMOD_MAX_TRIP>
+    unsigned hash_fp_mask = 0xffffffffu;   // AMOD_HASH_FP_BITS=n keeps n bits of the slots' fingerprints (tests: forces the full-tuple comparison to reject)
     int gen_wide = 0;              // AMOD_GEN_WIDE=1: k_gen_emit ranks every row's pairs through memory, the path of rows with > 32 pairs (tests)
     int heavy_min = -1;            // AMOD_HEAVY_MIN overrides the block-per-trip classification threshold (tests)
     int level_hint[3] = {0, 0, 0};   // deepest non-empty trip level seen so far (+1 is searched before looking further)
@@ -290,6 +291,7 @@ extern "C" int amod_create(amod_ctx** out, int device, int n_nodes, const void* 
     ctx->use_graph = getenv("AMOD_NO_GRAPH") == nullptr;
     if (const char* hm = getenv("AMOD_HEAVY_MIN")) ctx->heavy_min = atoi(hm);
     if (const char* gi = getenv("AMOD_GEN_WIDE")) ctx->gen_wide = atoi(gi) != 0;
+    if (const char* fb = getenv("AMOD_HASH_FP_BITS")) { const int n = std::max(0, std::min(32, atoi(fb))); ctx->hash_fp_mask = n >= 32 ? 0xffffffffu : ((1u << n) - 1u); }
     apply_l2_policy(ctx, ctx->stream);
     apply_l2_policy(ctx, ctx->side);         // k_basic<fill>, candidate generation: the side branch looks travel times up too
     cudaEventCreate(&ctx->ev0); cudaEventCreate(&ctx->ev1);
@@ -608,6 +610,7 @@ static int enqueue_build(amod_ctx* ctx, int mode, int cap, Table<TT> tt, int max
     auto hash_of = [&](int k) -> TripHash {        // two tables by level parity: k+1's is cleared while k's is read
         TripHash th; th.slots = ctx->hash.as<unsigned long long>() + (size_t)(k & 1) * ctx->hash_slots;
         th.mask = hash_size_of(k) ? hash_size_of(k) - 1 : 0;
+        th.fp_mask = ctx->hash_fp_mask;
         return th;
     };
     RowDesc* rows_buf[2] = {ctx->row_desc.as<RowDesc>(), ctx->row_desc.as<RowDesc>() + ctx->cap_rows};
@@ -631,7 +634,7 @@ static int enqueue_build(amod_ctx* ctx, int mode, int cap, Table<TT> tt, int max
         const int Gk = std::max(1, 32 / (prev.stride + 1));      // rows per chunk: Gk * (longest schedule + 1) <= 32 lanes
         RowDesc* rows = rows_buf[cur];
         CK(cudaEventRecord(get_event(ctx, n_ev++), st));
-        launch_k(st, GEV, WARPS_PER_BLOCK * 32, k_eval<TT>, d, tt, prev, lv, ctl, cur, Gk, rows, ctx->chunk_cnt.as<int>(),
+        launch_k(st, GEV, EVAL_WARPS * 32, k_eval<TT>, d, tt, prev, lv, ctl, cur, Gk, rows, ctx->chunk_cnt.as<int>(),
                                                        ctx->lane_cnt.as<uint8_t>(), tnf, dstats, scan_site(ctx, k), half,
                                                        tup, tup_cnt, region_cap);
         CK(cudaEventRecord(get_event(ctx, n_ev++), st));
@@ -1455,7 +1458,7 @@ static int npo_impl(amod_ctx* ctx, const int32_t* idle_nid, int n_idle, const in
             int* vm = ctx->npo_vm.as<int>(); int* rmm = ctx->npo_rm.as<int>(); double* md = ctx->npo_mdt.as<double>();
             int* bgp = ctx->npo_best.as<int>(); uint8_t* tp = ctx->npo_tie.as<uint8_t>(); NpoPick* scr = ctx->npo_scr.as<NpoPick>();
             void* args[] = {&cD, &cDT, &grp, &np, &vm, &rmm, &md, &bgp, &tp, &scr, &d_cursor, &d_cnt, &tg, &d_bar, &max_rounds, &d_rounds, &d_err};
-            if (cudaLaunchCooperativeKernel((void*)k_npo_rounds<TT>, dim3((unsigned)G), dim3(NPO_THREADS), args, 0, st) == cudaSuccess) {
+            if (cudaLaunchCooperativeKernel((void*)k_npo_rounds<TT>, dim3((unsigned)(occ_blocks * ctx->n_sm)), dim3(NPO_THREADS), args, 0, st) == cudaSuccess) {
                 int h[8] = {0, 0, 0, 0, 0, 0, 0, 0};
                 CK(cudaMemcpyAsync(h, ctx->npo_cnt.p, 32, cudaMemcpyDeviceToHost, st));
                 CK(cudaStreamSynchronize(st));

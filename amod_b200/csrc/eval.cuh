@@ -24,6 +24,9 @@
 #ifndef EVAL_BLOCKS_PER_SM
 #define EVAL_BLOCKS_PER_SM 4
 #endif
+#ifndef EVAL_WARPS
+#define EVAL_WARPS WARPS_PER_BLOCK     // warps per block of the insertion search
+#endif
 #define STAGE_SLOTS 96    // stops staged per warp step: nsub*l <= 32 (whole schedules) or l <= 38
 #define LEG_SLOTS 200     // travel times staged per warp step: nsub*(5l+2) <= 192
 
@@ -112,13 +115,13 @@ __device__ __forceinline__ void walk_j(const TT* __restrict__ lg, double PD, con
 // A chunk = G consecutive rows (base schedules) of the level's global row list, whatever task or
 // vehicle they belong to; G is chosen per level so that G * (longest schedule + 1) <= 32 lanes.
 template <typename TT>
-__global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, EVAL_BLOCKS_PER_SM)
+__global__ void __launch_bounds__(EVAL_WARPS * 32, EVAL_BLOCKS_PER_SM)
 k_eval(const DEpoch* __restrict__ epp, Table<TT> tt, Level prev, Level cur, Control* __restrict__ ctl, int which, int G,
        const RowDesc* __restrict__ rows, int* __restrict__ chunk_cnt, uint8_t* __restrict__ lane_cnt,
        int* __restrict__ task_nfeas, Stats* stats, unsigned long long* __restrict__ part, int part_vg,
        Tuple* __restrict__ tup, int* __restrict__ tup_cnt, int region_cap) {
     pdl_enter();
-    __shared__ WarpStage<TT> stage_all[WARPS_PER_BLOCK];
+    __shared__ WarpStage<TT> stage_all[EVAL_WARPS];
     __shared__ DEpoch s_ep;       // the epoch header once per block: array pointers without a second indirection
     __shared__ int s_cursor;      // feasible-insertion records appended by this block
     if (threadIdx.x < sizeof(DEpoch) / 4) ((int*)&s_ep)[threadIdx.x] = ((const int*)epp)[threadIdx.x];
@@ -127,7 +130,7 @@ k_eval(const DEpoch* __restrict__ epp, Table<TT> tt, Level prev, Level cur, Cont
     const DEpoch& ep = s_ep;
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     WarpStage<TT>& st = stage_all[wib];
-    const int warp0 = blockIdx.x * WARPS_PER_BLOCK + wib, nwarps = gridDim.x * WARPS_PER_BLOCK;
+    const int warp0 = blockIdx.x * EVAL_WARPS + wib, nwarps = gridDim.x * EVAL_WARPS;
     unsigned long long acc_evals = 0, acc_lookups = 0;
     const double T = ep.T;
     const int n_rows = ctl->overflow ? 0 : ctl->n_rows[which];

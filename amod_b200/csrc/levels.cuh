@@ -457,7 +457,7 @@ k_expand_rows(Control* __restrict__ ctl, int which, Level prev, const int* __res
 // warps), so the chain is kept short: a miss ends at the first slot (empty, or another fingerprint), a hit costs one
 // more round trip (vehicle and the whole tuple are loaded together and compared without an early exit).
 // ---------------------------------------------------------------------------------------------
-struct TripHash { unsigned long long* slots; unsigned mask; };
+struct TripHash { unsigned long long* slots; unsigned mask; unsigned fp_mask; };   // fp_mask: bits of the fingerprint kept (all; tests keep two)
 #define HASH_EMPTY 0xffffffffffffffffull
 // Tuples live in registers, so everything below is unrolled to a compile-time bound KMAX >= k; the kernels are instantiated for
 // KMAX = 1, 4, 8 and AMOD_MAX_TRIP and the host picks the smallest that holds the level's trips (registers = resident warps).
@@ -503,7 +503,7 @@ __device__ __forceinline__ unsigned hash_fp(unsigned long long h) { return (unsi
 
 template <int KMAX> __device__ __forceinline__ void hash_insert(const TripHash& th, int v, const ReqTuple<KMAX>& key, int k, int trip) {
     const unsigned long long hv = hash_tuple(v, key, k);
-    const unsigned long long val = ((unsigned long long)hash_fp(hv) << 32) | (unsigned)trip;
+    const unsigned long long val = ((unsigned long long)(hash_fp(hv) & th.fp_mask) << 32) | (unsigned)trip;
     unsigned h = hash_slot(hv) & th.mask;
     while (atomicCAS(&th.slots[h], HASH_EMPTY, val) != HASH_EMPTY) h = (h + 1) & th.mask;
 }
@@ -512,7 +512,7 @@ template <int KMAX> __device__ __forceinline__ void hash_insert(const TripHash& 
 struct HashProbe { unsigned long long slot; unsigned h, fp; };
 template <int KMAX> __device__ __forceinline__ HashProbe hash_begin(const TripHash& th, int v, const ReqTuple<KMAX>& want, int k) {
     const unsigned long long hv = hash_tuple(v, want, k);
-    HashProbe p; p.h = hash_slot(hv) & th.mask; p.fp = hash_fp(hv);
+    HashProbe p; p.h = hash_slot(hv) & th.mask; p.fp = hash_fp(hv) & th.fp_mask;
     p.slot = th.slots[p.h];
     return p;
 }

@@ -90,9 +90,10 @@ __device__ __forceinline__ void npo_best_request(const TT* __restrict__ DT, cons
     Key best = KEY_INF;
     int bg = -1, same = 0;                       // same = groups seen with best.dt besides the best one
     for (int x = lane; x < g.n_groups; x += 32) {
+        const TT d = row[x];                     // (both loads in flight before the first is looked at)
         const int hr = ldcg_i(g.hrank + x);
         if (hr < 0) continue;
-        const Key c{(double)row[x], hr};
+        const Key c{(double)d, hr};
         if (c.dt == best.dt) same++;
         else if (c.dt < best.dt) same = 0;
         if (key_less(c, best)) { best = c; bg = x; }
@@ -288,7 +289,8 @@ k_npo_rounds(const TT* __restrict__ D, const TT* __restrict__ DT, NpoGroups g, i
         for (int r = blockIdx.x * (NPO_THREADS / 32) + warp; r < n_pend; r += nw)
             if (ldcg_i(req_match + r) < 0) npo_best_request(DT, g, r, lane, best_g, tie);
         if (!npo_grid_barrier(bar, ++phase * gridDim.x, err)) break;
-        npo_accept_group(sh, D, g, (int)blockIdx.x, n_pend, veh_match, req_match, match_dt, best_g, tie, scratch, cursor, n_matched);
+        if ((int)blockIdx.x < g.n_groups)       // (the grid fills the device: the blocks beyond the groups only serve the requests' phase)
+            npo_accept_group(sh, D, g, (int)blockIdx.x, n_pend, veh_match, req_match, match_dt, best_g, tie, scratch, cursor, n_matched);
         round++;
         if (!npo_grid_barrier(bar, ++phase * gridDim.x, err)) break;
         if (ldcg_i(n_matched) >= target) break;       // (read after the barrier: the same answer in every block)

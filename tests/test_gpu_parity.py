@@ -332,6 +332,22 @@ def test_candidate_wide_rank_path(monkeypatch):
         b.close()
 
 
+def test_trip_lookup_with_colliding_fingerprints(monkeypatch):
+    """The trip lookup table keeps a 32-bit fingerprint beside each trip index so that a miss ends at the first probe; a hit is
+    still verified against the vehicle and the whole request tuple.  With the fingerprints cut to two bits most probes meet a
+    matching fingerprint of ANOTHER trip: the verification must reject it and the probe must go on."""
+    monkeypatch.setenv("AMOD_HASH_FP_BITS", "2")
+    for family in ("rand_real_osp_cap4", "rand_ties_osp_cap8", "sim_osp_cap4"):
+        if family not in golden_families(("rand_", "sim_")):
+            continue
+        tt, cases = load_golden(family)
+        b = PoolBuilder(tt)          # a fresh context reads the override
+        for ep, gold in cases[:3]:
+            ok, why = marshal.pools_equal(b.build_pool(ep), gold, rtol=0.0, check_kind=True)
+            assert ok, f"{family}: {why}"
+        b.close()
+
+
 def test_cuda_pool_at_cfg4_fleet_scale_and_sharded():
     """BASELINE.json configs[3] scale: 8,000 vehicles (bench.py's weak-scaling fleet for N = 4), capacity 4.  The
     whole-fleet pool is bit-exact against the oracle, and the four interleaved rank slices, built one after the
