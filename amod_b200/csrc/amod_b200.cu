@@ -118,7 +118,7 @@ struct amod_ctx {
     // greedy assignment
     DevBuf ga_pos, ga_rank, ga_order, ga_state, ga_bv, ga_br, ga_tv, ga_tr, ga_sel, ga_cnt;
     // npo
-    DevBuf npo_in, npo_vm, npo_rm, npo_rb, npo_vb, npo_rdt, npo_mdt, npo_cnt, npo_grp, npo_rg, npo_D, npo_best, npo_tie, npo_scr;
+    DevBuf npo_in, npo_vm, npo_rm, npo_rb, npo_vb, npo_rdt, npo_mdt, npo_cnt, npo_grp, npo_rg, npo_D, npo_best, npo_tie, npo_scr, npo_out, ga_sync;
     // routes (8f-2)
     int* d_pred = nullptr; void* d_dist = nullptr;
     DevBuf rt_in, rt_len, rt_off, rt_u, rt_v, rt_t, rt_d, rt_lt, rt_ld, rt_err;
@@ -312,7 +312,7 @@ extern "C" void amod_destroy(amod_ctx* ctx) {
                      &ctx->ent_src, &ctx->ent_trip, &ctx->ent_cost, &ctx->ent_delay, &ctx->trip_off, &ctx->sche_off, &ctx->trip_req,
                      &ctx->sche_code, &ctx->ga_pos, &ctx->ga_rank, &ctx->ga_order, &ctx->ga_state, &ctx->ga_bv, &ctx->ga_br, &ctx->ga_tv, &ctx->ga_tr,
                      &ctx->ga_sel, &ctx->ga_cnt, &ctx->npo_in, &ctx->npo_vm, &ctx->npo_rm, &ctx->npo_rb, &ctx->npo_vb, &ctx->npo_rdt,
-                     &ctx->npo_mdt, &ctx->npo_cnt, &ctx->npo_grp, &ctx->npo_rg, &ctx->npo_D, &ctx->npo_best, &ctx->npo_tie, &ctx->npo_scr};
+                     &ctx->npo_mdt, &ctx->npo_cnt, &ctx->npo_grp, &ctx->npo_rg, &ctx->npo_D, &ctx->npo_best, &ctx->npo_tie, &ctx->npo_scr, &ctx->npo_out, &ctx->ga_sync};
     for (DevBuf* b : all) b->release();
     for (auto& l : ctx->lv) { l.trip_veh.release(); l.trip_req.release(); l.s0.release(); l.nfeas.release(); l.cost.release();
                               l.sch.release(); l.sch_cost.release(); l.final.release(); l.veh_start.release(); }
@@ -1341,7 +1341,34 @@ extern "C" int amod_greedy_assign(amod_ctx* ctx, int32_t* order_out, int32_t* se
     int* bv[2] = {ctx->ga_bv.as<int>(), ctx->ga_bv.as<int>() + V};
     int* br[2] = {ctx->ga_br.as<int>(), ctx->ga_br.as<int>() + R};
     k_ga_min<<<G, 256, 0, st>>>(ctl, pb, ctx->ga_rank.as<int>(), ctx->ga_state.as<uint8_t>(), bv[0], br[0]);
-    for (;;) {
+    bool done = false;
+    {   // every round in one cooperative launch (AMOD_GA_NO_PERSIST=1: two launches per round, a host check every four rounds)
+        static int occ = -1;
+        if (occ < 0) { if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_ga_rounds, 256, 0) != cudaSuccess) occ = 0; cudaGetLastError(); }
+        int coop = 0;
+        cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, ctx->device);
+        if (coop && occ >= 2 && !getenv("AMOD_GA_NO_PERSIST")) {
+            CK(ctx->ga_sync.ensure(32));
+            CK(cudaMemsetAsync(ctx->ga_sync.p, 0, 32, st));      // left[2] | barrier | error | rounds
+            int* d_left = ctx->ga_sync.as<int>(); unsigned* d_bar = (unsigned*)(d_left + 2); int* d_err = d_left + 3; int* d_rounds = d_left + 4;
+            const Control* cctl = ctl; PoolBufs pbb = pb;
+            const int* rk = ctx->ga_rank.as<int>(); uint8_t* stt = ctx->ga_state.as<uint8_t>();
+            int* bv0 = bv[0]; int* br0 = br[0]; int* bv1 = bv[1]; int* br1 = br[1];
+            int nv = V, nr = R, max_rounds = 4 * (V + 8);
+            uint8_t* tv = ctx->ga_tv.as<uint8_t>(); uint8_t* tr = ctx->ga_tr.as<uint8_t>();
+            void* args[] = {&cctl, &pbb, &rk, &stt, &bv0, &br0, &bv1, &br1, &nv, &nr, &tv, &tr, &d_left, &d_bar, &d_err, &max_rounds, &d_rounds};
+            if (cudaLaunchCooperativeKernel((void*)k_ga_rounds, dim3((unsigned)G), dim3(256), args, 0, st) == cudaSuccess) {
+                int h[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+                CK(cudaMemcpyAsync(h, ctx->ga_sync.p, 32, cudaMemcpyDeviceToHost, st));
+                CK(cudaStreamSynchronize(st));
+                if (h[3]) return ctx->fail(AMOD_E_CUDA, "greedy assignment: the device-wide barrier timed out");
+                rounds = h[4];
+                if (rounds >= max_rounds) return ctx->fail(AMOD_E_CUDA, "greedy assignment did not converge");
+                done = true;
+            } else cudaGetLastError();
+        }
+    }
+    while (!done) {
         for (int rep = 0; rep < 4; rep++) {       // four rounds per host check
             const int cur = rounds & 1;
             if (rep == 3) CK(cudaMemsetAsync(n_left, 0, 4, st));
@@ -1482,12 +1509,25 @@ static int npo_impl(amod_ctx* ctx, const int32_t* idle_nid, int n_idle, const in
         CK(cudaStreamSynchronize(st));
         if (matched == prev) return ctx->fail(AMOD_E_CUDA, "npo: no progress in round %d", rounds);
     }
+    // selection order of the reference: ascending (dt, request rank, vehicle rank)
+    if (n_pend <= NPO_ORDER_MAX) {      // ordered on the device: three short copies come back
+        const size_t M = (size_t)matched;
+        CK(ctx->npo_out.ensure(16 * (size_t)target + 64));
+        int* o_idle = ctx->npo_out.as<int>(); int* o_pend = o_idle + target; double* o_dt = (double*)(ctx->npo_out.as<char>() + 8 * (((size_t)target + 7) & ~(size_t)7));
+        k_npo_order<<<(n_pend * 32 + 255) / 256, 256, 0, st>>>(ctx->npo_rm.as<int>(), ctx->npo_mdt.as<double>(), n_pend, o_idle, o_pend, o_dt);
+        CK(cudaMemcpyAsync(out_idle, o_idle, 4 * M, cudaMemcpyDeviceToHost, st));
+        CK(cudaMemcpyAsync(out_pend, o_pend, 4 * M, cudaMemcpyDeviceToHost, st));
+        CK(cudaMemcpyAsync(out_dt, o_dt, 8 * M, cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        *n_out = matched;
+        if (n_rounds) *n_rounds = rounds;
+        return AMOD_OK;
+    }
     std::vector<int> rm(n_pend);
     std::vector<double> mdt(n_pend);
     CK(cudaMemcpyAsync(rm.data(), ctx->npo_rm.p, 4 * (size_t)n_pend, cudaMemcpyDeviceToHost, st));
     CK(cudaMemcpyAsync(mdt.data(), ctx->npo_mdt.p, 8 * (size_t)n_pend, cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
-    // selection order of the reference: ascending (dt, request rank, vehicle rank)
     struct Sel { double dt; int r; };
     std::vector<Sel> order;
     order.reserve((size_t)target);

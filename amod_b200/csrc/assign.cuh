@@ -94,6 +94,59 @@ __global__ void k_ga_drop(const Control* __restrict__ ctl, PoolBufs pb, const in
     if ((threadIdx.x & 31) == 0 && left) atomicAdd(n_left, left);
 }
 
+// All rounds in one cooperative launch (every block resident): the keep and drop phases of a round as above, separated by a
+// device-wide barrier instead of a kernel boundary, the count of undecided pairs read on the device - one host synchronisation for the
+// whole assignment.  An entry is handled by the same thread in every phase; what other threads change (the per-resource minima,
+// the taken flags, the counts) is read from L2.
+__global__ void __launch_bounds__(256)
+k_ga_rounds(const Control* __restrict__ ctl, PoolBufs pb, const int* __restrict__ rank, uint8_t* __restrict__ state,
+            int* bv0, int* br0, int* bv1, int* br1, int n_veh, int n_req, uint8_t* taken_v, uint8_t* taken_r,
+            int* n_left /* [2] */, unsigned* bar, int* err, int max_rounds, int* rounds_out) {
+    const i64 P = ctl->n_ent;
+    const i64 stride = (i64)gridDim.x * blockDim.x, t0 = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+    unsigned phase = 0;
+    int round = 0;
+    while (round < max_rounds) {
+        const int cur = round & 1;
+        const int* best_v = cur ? bv1 : bv0; const int* best_r = cur ? br1 : br0;
+        int* next_v = cur ? bv0 : bv1; int* next_r = cur ? br0 : br1;
+        for (i64 e = t0; e < P; e += stride) {        // keep
+            if (state[e] != GA_UNDECIDED) continue;
+            const int r = rank[e], v = pb.ent_veh[e];
+            const i64 a = pb.trip_off[e], b = pb.trip_off[e + 1];
+            bool top = ldcg_i(best_v + v) == r;
+            for (i64 t = a; t < b && top; t++) top = ldcg_i(best_r + pb.trip_req[t]) == r;
+            if (!top) continue;
+            state[e] = GA_KEPT;
+            taken_v[v] = 1;
+            for (i64 t = a; t < b; t++) taken_r[pb.trip_req[t]] = 1;
+        }
+        if (!grid_barrier(bar, ++phase * gridDim.x, err)) break;
+        if (t0 == 0) n_left[cur ^ 1] = 0;             // the other round's count: every block has read it (they all passed this barrier)
+        int left = 0;
+        for (i64 e = t0; e < P; e += stride) {        // drop, count, post the survivors' ranks for the next round
+            if (state[e] != GA_UNDECIDED) continue;
+            const int v = pb.ent_veh[e];
+            const i64 a = pb.trip_off[e], b = pb.trip_off[e + 1];
+            bool hit = ldcg_b(taken_v + v) != 0;
+            for (i64 t = a; t < b && !hit; t++) hit = ldcg_b(taken_r + pb.trip_req[t]) != 0;
+            if (hit) { state[e] = GA_DROPPED; continue; }
+            left++;
+            const int r = rank[e];
+            atomicMin(&next_v[v], r);
+            for (i64 t = a; t < b; t++) atomicMin(&next_r[pb.trip_req[t]], r);
+        }
+        for (i64 x = t0; x < n_veh; x += stride) ((int*)best_v)[x] = 0x7fffffff;
+        for (i64 x = t0; x < n_req; x += stride) ((int*)best_r)[x] = 0x7fffffff;
+        left = warp_sum(left);
+        if ((threadIdx.x & 31) == 0 && left) atomicAdd(&n_left[cur], left);
+        round++;
+        if (!grid_barrier(bar, ++phase * gridDim.x, err)) break;
+        if (ldcg_i(n_left + cur) == 0) break;
+    }
+    if (t0 == 0) *rounds_out = round;
+}
+
 struct InKeptByRank {       // scan input over sorted positions: 1 if the pair at that position was kept
     const int* order; const uint8_t* state; const Control* ctl;
     __device__ __forceinline__ i64 size() const { return ctl->n_ent; }

@@ -172,3 +172,26 @@ __device__ __forceinline__ double warp_excl_min(double x, int lane) {  // +inf f
     return lane == 0 ? __longlong_as_double(0x7ff0000000000000LL) : e;
 }
 #define DINF __longlong_as_double(0x7ff0000000000000LL)
+
+// Kernels that run many rounds inside one (cooperative) launch: what the rounds change is read with ld.global.cg (L2), because a
+// line cached in an SM's L1 in an earlier round would be stale, and the phases of a round are separated by a device-wide barrier
+// (arrive with a release, spin on an acquire load; bounded, so a fault cannot hang the device; all blocks must be resident).
+__device__ __forceinline__ int ldcg_i(const int* p) { return __ldcg(p); }
+__device__ __forceinline__ int ldcg_b(const uint8_t* p) { return (int)__ldcg((const unsigned char*)p); }
+__device__ __forceinline__ bool grid_barrier(unsigned* bar, unsigned want, int* err) {
+    __shared__ int s_ok;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        atomicAdd(bar, 1u);
+        unsigned v = 0;
+        long long spins = 0;
+        do { asm volatile("ld.acquire.gpu.u32 %0, [%1];" : "=r"(v) : "l"(bar) : "memory"); } while (v < want && ++spins < (1ll << 26) && !ldcg_i(err));
+        if (v < want) atomicExch(err, 1);
+        s_ok = v >= want;
+        __threadfence();
+    }
+    __syncthreads();
+    return s_ok != 0;
+}
+

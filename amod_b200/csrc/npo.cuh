@@ -24,21 +24,6 @@ __device__ __forceinline__ Key warp_min_key(Key k) {
     }
     return k;
 }
-__device__ __forceinline__ Key block_min_key(Key k, Key* smem) {
-    k = warp_min_key(k);
-    int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    if (lane == 0) smem[w] = k;
-    __syncthreads();
-    if (w == 0) {
-        k = warp_min_key(lane < NPO_THREADS / 32 ? smem[lane] : KEY_INF);
-        if (lane == 0) smem[0] = k;
-    }
-    __syncthreads();
-    k = smem[0];
-    __syncthreads();
-    return k;
-}
-
 // Idle vehicles standing at the same node (a station, platform.py:50-55) have the same travel time to every request and are
 // taken in rank order, so they form a GROUP: a node, its vehicles in fleet order and a head pointer (vehicles already matched).
 // A request's best free vehicle is the head of the group minimising (dt, head's rank); every free vehicle of a group has the
@@ -78,8 +63,6 @@ __global__ void k_npo_matrix(Table<TT> tt, NpoGroups g, const int* __restrict__ 
 
 // Everything the rounds change is read with ld.global.cg (L2): the persistent variant runs many rounds inside one launch, and a
 // line cached in an SM's L1 in an earlier round would be stale.
-__device__ __forceinline__ int ldcg_i(const int* p) { return __ldcg(p); }
-__device__ __forceinline__ int ldcg_b(const uint8_t* p) { return (int)__ldcg((const unsigned char*)p); }
 
 // per free request (one warp each, lanes over the groups): the group offering the smallest (dt, rank of its head vehicle), and
 // whether another group ties in dt
@@ -122,9 +105,24 @@ __global__ void k_npo_best(const TT* __restrict__ DT, NpoGroups g, int n_pend, c
     npo_best_request(DT, g, r, lane, best_g, tie);
 }
 
+// (first, A, t1 <= t2) of a set of requests, see npo_accept_group; two sets are merged element-wise (smallest two of the four ties)
+struct NpoQuad { Key first, A, t1, t2; };
+__device__ __forceinline__ Key key_shfl_xor(const Key& k, int o) {
+    Key t; t.dt = __shfl_xor_sync(FULL, k.dt, o); t.idx = __shfl_xor_sync(FULL, k.idx, o);
+    return t;
+}
+__device__ __forceinline__ NpoQuad quad_shfl_xor(const NpoQuad& q, int o) {
+    return NpoQuad{key_shfl_xor(q.first, o), key_shfl_xor(q.A, o), key_shfl_xor(q.t1, o), key_shfl_xor(q.t2, o)};
+}
+__device__ __forceinline__ void quad_merge(NpoQuad& a, const NpoQuad& b) {
+    if (key_less(b.first, a.first)) a.first = b.first;
+    if (key_less(b.A, a.A)) a.A = b.A;
+    if (key_less(b.t1, a.t1)) { a.t2 = key_less(a.t1, b.t2) ? a.t1 : b.t2; a.t1 = b.t1; }
+    else if (key_less(b.t1, a.t2)) a.t2 = b.t1;
+}
+
 struct NpoShared {
-    Key smem[NPO_THREADS / 32];
-    Key s_two[NPO_THREADS / 32][2];
+    NpoQuad quad[NPO_THREADS / 32];
     int s_w;
     unsigned long long s_base;
     NpoPick s_pick[NPO_SCAP];                    // the accepted set of this round (beyond NPO_SCAP: a stretch of the global scratch list)
@@ -136,8 +134,6 @@ __device__ __forceinline__ void npo_accept_group(NpoShared& sh, const TT* __rest
                                                  int* req_match, double* __restrict__ match_dt, const int* __restrict__ best_g,
                                                  const uint8_t* __restrict__ tie, NpoPick* __restrict__ scratch,
                                                  unsigned long long* __restrict__ cursor, int* n_matched) {
-    Key* smem = sh.smem;
-    Key (*s_two)[2] = sh.s_two;
     int& s_w = sh.s_w;
     unsigned long long& s_base = sh.s_base;
     NpoPick* s_pick = sh.s_pick;
@@ -168,27 +164,22 @@ __device__ __forceinline__ void npo_accept_group(NpoShared& sh, const TT* __rest
             else if (ti[u]) { if (key_less(k, t1)) { t2 = t1; t1 = k; } else if (key_less(k, t2)) t2 = k; }
         }
     }
-    first = block_min_key(first, smem);
-    if (first.idx == 0x7fffffff) return;         // no free request
-    A = block_min_key(A, smem);
-    {   // smallest two of the tie proposers
-        for (int o = 16; o; o >>= 1) {
-            Key u1, u2;
-            u1.dt = __shfl_xor_sync(FULL, t1.dt, o); u1.idx = __shfl_xor_sync(FULL, t1.idx, o);
-            u2.dt = __shfl_xor_sync(FULL, t2.dt, o); u2.idx = __shfl_xor_sync(FULL, t2.idx, o);
-            if (key_less(u1, t1)) { t2 = key_less(t1, u2) ? t1 : u2; t1 = u1; }
-            else if (key_less(u1, t2)) t2 = u1;
+    {   // one block-wide reduction for all four
+        NpoQuad q{first, A, t1, t2};
+        for (int o = 16; o; o >>= 1) quad_merge(q, quad_shfl_xor(q, o));
+        if (lane == 0) sh.quad[w] = q;
+        __syncthreads();
+        if (w == 0) {
+            q = lane < NPO_THREADS / 32 ? sh.quad[lane] : NpoQuad{KEY_INF, KEY_INF, KEY_INF, KEY_INF};
+            for (int o = 16; o; o >>= 1) quad_merge(q, quad_shfl_xor(q, o));
+            if (lane == 0) sh.quad[0] = q;
         }
-        if (lane == 0) { s_two[w][0] = t1; s_two[w][1] = t2; }
         __syncthreads();
-        t1 = KEY_INF; t2 = KEY_INF;
-        for (int y = 0; y < NPO_THREADS / 32; y++)
-            for (int z = 0; z < 2; z++) {
-                const Key u = s_two[y][z];
-                if (key_less(u, t1)) { t2 = t1; t1 = u; } else if (key_less(u, t2) && !key_eq(u, t1)) t2 = u;
-            }
+        q = sh.quad[0];
         __syncthreads();
+        first = q.first; A = q.A; t1 = q.t1; t2 = q.t2;
     }
+    if (first.idx == 0x7fffffff) return;         // no free request
     const Key B = key_eq(t1, first) ? t2 : t1;   // a tying request may only be accepted as element 0
     const Key stop = key_less(A, B) ? A : B;
     // pass 2: the requests before `stop` (all name this group), into the shared list; counted as they go
@@ -258,23 +249,6 @@ k_npo_accept(const TT* __restrict__ D, NpoGroups g, int n_pend, int* veh_match, 
 // All rounds in ONE launch when every group's block is resident at once (cooperative launch: tens of groups - the stations - is
 // the case that needs many rounds): the two phases of a round are separated by a device-wide barrier (arrive with a release,
 // spin on an acquire load; bounded, so a fault cannot hang the device) instead of a kernel boundary, and the host synchronises once.
-__device__ __forceinline__ bool npo_grid_barrier(unsigned* bar, unsigned want, int* err) {
-    __shared__ int s_ok;
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        __threadfence();
-        atomicAdd(bar, 1u);
-        unsigned v = 0;
-        long long spins = 0;
-        do { asm volatile("ld.acquire.gpu.u32 %0, [%1];" : "=r"(v) : "l"(bar) : "memory"); } while (v < want && ++spins < (1ll << 26) && !ldcg_i(err));
-        if (v < want) atomicExch(err, 1);
-        s_ok = v >= want;
-        __threadfence();
-    }
-    __syncthreads();
-    return s_ok != 0;
-}
-
 template <typename TT>
 __global__ void __launch_bounds__(NPO_THREADS)
 k_npo_rounds(const TT* __restrict__ D, const TT* __restrict__ DT, NpoGroups g, int n_pend, int* veh_match, int* req_match,
@@ -288,14 +262,31 @@ k_npo_rounds(const TT* __restrict__ D, const TT* __restrict__ DT, NpoGroups g, i
         if (blockIdx.x == 0 && threadIdx.x == 0) *cursor = 0ull;
         for (int r = blockIdx.x * (NPO_THREADS / 32) + warp; r < n_pend; r += nw)
             if (ldcg_i(req_match + r) < 0) npo_best_request(DT, g, r, lane, best_g, tie);
-        if (!npo_grid_barrier(bar, ++phase * gridDim.x, err)) break;
+        if (!grid_barrier(bar, ++phase * gridDim.x, err)) break;
         if ((int)blockIdx.x < g.n_groups)       // (the grid fills the device: the blocks beyond the groups only serve the requests' phase)
             npo_accept_group(sh, D, g, (int)blockIdx.x, n_pend, veh_match, req_match, match_dt, best_g, tie, scratch, cursor, n_matched);
         round++;
-        if (!npo_grid_barrier(bar, ++phase * gridDim.x, err)) break;
+        if (!grid_barrier(bar, ++phase * gridDim.x, err)) break;
         if (ldcg_i(n_matched) >= target) break;       // (read after the barrier: the same answer in every block)
     }
     if (blockIdx.x == 0 && threadIdx.x == 0) *rounds_out = round;
+}
+
+// The reference's selection order: ascending (dt, request rank) over the matched requests.  A warp per matched request counts
+// the matched requests before it and writes the triple to that place (used up to NPO_ORDER_MAX requests; beyond, the host sorts).
+#define NPO_ORDER_MAX 16384
+__global__ void k_npo_order(const int* __restrict__ req_match, const double* __restrict__ match_dt, int n_pend,
+                            int* __restrict__ out_idle, int* __restrict__ out_pend, double* __restrict__ out_dt) {
+    const int r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (r >= n_pend) return;
+    const int v = req_match[r];
+    if (v < 0) return;
+    const Key k{match_dt[r], r};
+    int before = 0;
+    for (int y = lane; y < n_pend; y += 32)
+        if (req_match[y] >= 0) { const Key u{match_dt[y], y}; before += key_less(u, k) ? 1 : 0; }
+    before = warp_sum(before);
+    if (lane == 0) { out_idle[before] = v; out_pend[before] = r; out_dt[before] = k.dt; }
 }
 
 template <typename TT>

@@ -197,8 +197,12 @@ def test_cuda_long_schedules_take_two_warp_steps(mode=marshal.MODE_SBA):
     assert got.stats["n_evals"] == ref.stats["n_evals"] and got.stats["n_lookups"] == ref.stats["n_lookups"]
 
 
-def test_cuda_greedy_assignment_matches_reference_and_oracle():
-    """Next row: greedy_assignment over the device-resident pool."""
+@pytest.mark.parametrize("persistent", [True, False], ids=["one-launch", "launch-per-round"])
+def test_cuda_greedy_assignment_matches_reference_and_oracle(persistent, monkeypatch):
+    """Next row: greedy_assignment over the device-resident pool; both forms of the rounds (all rounds in one
+    cooperative launch / two launches per round with a host check every four rounds)."""
+    if not persistent:
+        monkeypatch.setenv("AMOD_GA_NO_PERSIST", "1")
     import oracle
     z = np.load(os.path.join(GOLDEN, "greedy.npz"))
     for g in range(int(z["n"])):
