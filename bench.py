@@ -99,27 +99,58 @@ class ClockSampler(threading.Thread):
     def __init__(self, gpu_index: int):
         super().__init__(daemon=True)
         self.gpu = gpu_index
-        self.rows = []
+        self.rows = []          # (perf_counter at arrival, fields)
         self.proc = None
+        self.t_mark = None
 
     def run(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
                                           "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             for line in self.proc.stdout:
-                self.rows.append([x.strip() for x in line.split(",")])
+                self.rows.append((time.perf_counter(), [x.strip() for x in line.split(",")]))
         except Exception:
             pass
 
-    def stop(self) -> dict:
+    def wait_first(self, timeout_s: float = 8.0):
+        """nvidia-smi needs a moment to come up (longer on a fresh box): the timed region starts once it is streaming."""
+        t = time.perf_counter()
+        while not self.rows and time.perf_counter() - t < timeout_s:
+            time.sleep(0.02)
+
+    def mark(self):
+        self.t_mark = time.perf_counter()
+
+    def needs_sample(self) -> bool:
+        """True while no row has arrived since mark() (for at most 1.5 s after the first question)."""
+        if any(ts >= (self.t_mark or 0.0) for ts, _r in self.rows):
+            return False
+        if not hasattr(self, "_asked"):
+            self._asked = time.perf_counter()
+        self.extended = True
+        return time.perf_counter() - self._asked < 1.5
+
+    def stop(self, load_fn=None) -> dict:
+        """Rows that arrived since mark().  The timed regions of a short run (K x 0.5 ms) can be shorter than the 100 ms sampling
+        period: then the SAME steps keep running (untimed) until one row has arrived, so that the clocks are always read under the
+        load that was timed, and the JSON says so."""
+        t_mark = self.t_mark if self.t_mark is not None else 0.0
+        inside = [r for ts, r in self.rows if ts >= t_mark]
+        how = "during the timed regions"
+        if not inside and load_fn is not None:
+            while self.needs_sample():
+                load_fn()
+            inside = [r for ts, r in self.rows if ts >= t_mark]
+        if getattr(self, "extended", False):
+            how = "under the same steps (untimed) right after the timed regions, which were shorter than the 100 ms sampling period"
         if self.proc:
             self.proc.terminate()
-        sm = [float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit()]
-        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
+        sm = [float(r[0]) for r in inside if r and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in inside if len(r) > 1 and r[1].replace(".", "").isdigit()]
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = sorted({names[i] for r in self.rows if len(r) >= 7 for i in range(4) if r[3 + i].lower() == "active"})
+        reasons = sorted({names[i] for r in inside if len(r) >= 7 for i in range(4) if r[3 + i].lower() == "active"})
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": reasons, "samples": len(sm)}
+                "reasons": reasons, "samples": len(sm), "sampled": how}
 
 
 def host_threads() -> int:
@@ -409,12 +440,14 @@ def main():
         parity["ok"] = None
 
     # ---- device-resident arm (value) ---------------------------------------------------------------
-    for i in range(args.warmup):
-        step_resident(i)
     sampler = ClockSampler(local) if rank == 0 else None
     if sampler:
         sampler.start()
-        time.sleep(0.25)
+        sampler.wait_first()
+    for i in range(args.warmup):
+        step_resident(i)
+    if sampler:
+        sampler.mark()
     barrier()                       # every rank enters the timed region together
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     evals = launches = entries = 0
@@ -491,7 +524,18 @@ def main():
         dist.all_reduce(tot_e, op=dist.ReduceOp.SUM)
     e_evals_all, e_h2d_all, e_d2h_all = (float(x) for x in tot_e.tolist())
     e2e_val = e_evals_all / float(t_e.item())
-    clocks = sampler.stop() if sampler else None       # sampled across both timed regions (resident and end-to-end)
+    # clocks: sampled across both timed regions (resident and end-to-end); a run shorter than the sampling period keeps stepping (every
+    # rank together, untimed) until one reading has arrived
+    if world > 1:
+        while True:
+            need = torch.tensor([1.0 if (sampler is not None and sampler.needs_sample()) else 0.0], device=dev)
+            dist.broadcast(need, 0)
+            if need.item() == 0.0:
+                break
+            step_resident(0)
+        clocks = sampler.stop() if sampler else None
+    else:
+        clocks = sampler.stop(lambda: step_resident(0)) if sampler else None
 
     if rank != 0:
         if world > 1:

@@ -131,7 +131,8 @@ def test_cuda_npo_matches_oracle_with_ties(persistent, monkeypatch):
     for kind, n_nodes in (("ties", 30), ("ties", 200), ("real", 200)):
         tt = synth.random_table(n_nodes, 9, kind)
         b = PoolBuilder(tt)
-        for n_idle, n_pend in ((40, 25), (25, 40), (1, 7), (300, 200), (900, 1100), (2500, 600)):
+        sizes = ((40, 25), (25, 40), (1, 7), (300, 200), (900, 1100), (2500, 600)) + (((60, 17000),) if kind == "real" else ())   # (> 16,384 requests: ordered on the host)
+        for n_idle, n_pend in sizes:
             stations = rng.integers(1, n_nodes + 1, size=5)
             idle = np.where(rng.random(n_idle) < 0.6, rng.choice(stations, n_idle), rng.integers(1, n_nodes + 1, size=n_idle)).astype(np.int32)
             pend = rng.integers(1, n_nodes + 1, size=n_pend).astype(np.int32)
