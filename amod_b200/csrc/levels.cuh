@@ -611,62 +611,108 @@ __global__ void k_compact_trips(const Control* __restrict__ ctl, int which, cons
 // order = [records, newest first] + [non-records in encounter order]; order[0] is the best schedule
 // (first-encountered minimum).  One warp per trip.
 // ---------------------------------------------------------------------------------------------
+// one trip by the whole warp (more than CLASSIFY_SMALL schedules)
+__device__ __forceinline__ void classify_warp(const Level& cur, int t, i64 s0, int nf, int lane) {
+    const double* __restrict__ cost = cur.sch_cost + s0;
+    int* __restrict__ fin = cur.final + s0;       // encounter position -> row (list order)
+    const int r0 = (int)s0;
+    if (nf <= 32) {     // one warp step decides everything
+        const bool in = lane < nf;
+        const double c = in ? cost[lane] : DINF;
+        const double before = warp_excl_min(c, lane);      // (outside the &&: every lane takes part in the shuffles)
+        const bool isrec = in && c < before;
+        const unsigned br = __ballot_sync(FULL, isrec), bn = __ballot_sync(FULL, in && !isrec);
+        const unsigned lt = (1u << lane) - 1u;
+        const int nrec1 = __popc(br);
+        if (!BOK(s0 + nf <= cur.cap_sch)) return;
+        if (isrec) fin[lane] = r0 + nrec1 - 1 - __popc(br & lt);
+        else if (in) fin[lane] = r0 + nrec1 + __popc(bn & lt);
+        const double best = warp_min(c);
+        if (lane == 0) cur.cost[t] = best;
+        return;
+    }
+    // pass 1: number of records
+    double running = DINF;
+    int nrec = 0;
+    for (int b = 0; b < nf; b += 32) {
+        const double c = b + lane < nf ? cost[b + lane] : DINF;
+        const double incoming = fmin(running, warp_excl_min(c, lane));
+        nrec += __popc(__ballot_sync(FULL, c < incoming));
+        running = fmin(running, warp_min(c));
+    }
+    // pass 2: positions
+    double run2 = DINF;
+    int rec_before = 0, non_before = 0;
+    for (int b = 0; b < nf; b += 32) {
+        const bool in = b + lane < nf;
+        const double c = in ? cost[b + lane] : DINF;
+        const double incoming = fmin(run2, warp_excl_min(c, lane));
+        const bool isrec = in && c < incoming;
+        const unsigned br = __ballot_sync(FULL, isrec), bn = __ballot_sync(FULL, in && !isrec);
+        const unsigned lt = (1u << lane) - 1u;
+        if (isrec) fin[b + lane] = r0 + nrec - 1 - (rec_before + __popc(br & lt));
+        else if (in) fin[b + lane] = r0 + nrec + non_before + __popc(bn & lt);
+        rec_before += __popc(br); non_before += __popc(bn);
+        run2 = fmin(run2, warp_min(c));
+    }
+    if (lane == 0) cur.cost[t] = running;
+}
+
+// With many more trips than warps (the SBA peak epoch: a million trips with one to five feasible schedules each) a warp takes 32
+// consecutive trips: those with a handful of schedules are decided by ONE lane each, walking the trip's costs as the reference's loop
+// does; the others go through the whole warp one after the other.  Otherwise (the OSP levels: ~10^4 trips) a warp per trip.
+#define CLASSIFY_SMALL 8
 __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32)
 k_classify(Control* __restrict__ ctl, Level cur, int heavy_min, int* __restrict__ heavy_list) {
     pdl_enter();
     const int lane = threadIdx.x & 31;
     const int n = ctl->overflow ? 0 : ctl->n_trips[cur.k];
     const int nwarps = gridDim.x * WARPS_PER_BLOCK;
-    for (int t = blockIdx.x * WARPS_PER_BLOCK + (threadIdx.x >> 5); t < n; t += nwarps) {
-        const i64 s0 = cur.s0[t];
-        const int nf = cur.nfeas[t];
-        const double* __restrict__ cost = cur.sch_cost + s0;
-        int* __restrict__ fin = cur.final + s0;       // encounter position -> row (list order)
-        const int r0 = (int)s0;
-        if (heavy_min > 0 && nf >= heavy_min) {      // left to k_classify_heavy (one block per such trip)
-            if (lane == 0) heavy_list[atomicAdd(&ctl->n_heavy[cur.k], 1)] = t;
-            continue;
+    if (n < nwarps * 4) {        // fewer trips than lanes to spread them over (the OSP levels): a warp per trip
+        for (int t = blockIdx.x * WARPS_PER_BLOCK + (threadIdx.x >> 5); t < n; t += nwarps) {
+            const int nf = cur.nfeas[t];
+            if (heavy_min > 0 && nf >= heavy_min) {      // left to k_classify_heavy (one block per such trip)
+                if (lane == 0) heavy_list[atomicAdd(&ctl->n_heavy[cur.k], 1)] = t;
+                continue;
+            }
+            classify_warp(cur, t, cur.s0[t], nf, lane);
         }
-        if (nf <= 32) {     // the common case: one warp step decides everything
-            const bool in = lane < nf;
-            const double c = in ? cost[lane] : DINF;
-            const double before = warp_excl_min(c, lane);      // (outside the &&: every lane takes part in the shuffles)
-            const bool isrec = in && c < before;
-            const unsigned br = __ballot_sync(FULL, isrec), bn = __ballot_sync(FULL, in && !isrec);
-            const unsigned lt = (1u << lane) - 1u;
-            const int nrec1 = __popc(br);
-            if (!BOK(s0 + nf <= cur.cap_sch)) continue;
-            if (isrec) fin[lane] = r0 + nrec1 - 1 - __popc(br & lt);
-            else if (in) fin[lane] = r0 + nrec1 + __popc(bn & lt);
-            const double best = warp_min(c);
-            if (lane == 0) cur.cost[t] = best;
-            continue;
+        return;
+    }
+    for (int t0 = (blockIdx.x * WARPS_PER_BLOCK + (threadIdx.x >> 5)) * 32; t0 < n; t0 += nwarps * 32) {
+        const int t = t0 + lane;
+        i64 s0 = 0;
+        int nf = 0;
+        if (t < n) { s0 = cur.s0[t]; nf = cur.nfeas[t]; }
+        const bool heavy = t < n && heavy_min > 0 && nf >= heavy_min;      // left to k_classify_heavy (one block per such trip)
+        if (heavy) heavy_list[atomicAdd(&ctl->n_heavy[cur.k], 1)] = t;
+        const bool small = t < n && !heavy && nf <= CLASSIFY_SMALL;
+        if (small && BOK(s0 + nf <= cur.cap_sch)) {
+            const double* __restrict__ cost = cur.sch_cost + s0;
+            int* __restrict__ fin = cur.final + s0;
+            double c[CLASSIFY_SMALL];
+#pragma unroll
+            for (int x = 0; x < CLASSIFY_SMALL; x++) c[x] = x < nf ? cost[x] : DINF;
+            double run = DINF;
+            int nrec = 0;
+#pragma unroll
+            for (int x = 0; x < CLASSIFY_SMALL; x++) if (c[x] < run) { run = c[x]; nrec++; }
+            double run2 = DINF;
+            int rb = 0, nb = 0;
+#pragma unroll
+            for (int x = 0; x < CLASSIFY_SMALL; x++)
+                if (x < nf) {
+                    if (c[x] < run2) { run2 = c[x]; fin[x] = (int)s0 + nrec - 1 - rb; rb++; }
+                    else { fin[x] = (int)s0 + nrec + nb; nb++; }
+                }
+            cur.cost[t] = run;
         }
-        // pass 1: number of records
-        double running = DINF;
-        int nrec = 0;
-        for (int b = 0; b < nf; b += 32) {
-            const double c = b + lane < nf ? cost[b + lane] : DINF;
-            const double incoming = fmin(running, warp_excl_min(c, lane));
-            nrec += __popc(__ballot_sync(FULL, c < incoming));
-            running = fmin(running, warp_min(c));
+        unsigned todo = __ballot_sync(FULL, t < n && !heavy && !small);
+        while (todo) {
+            const int src = __ffs(todo) - 1;
+            todo &= todo - 1;
+            classify_warp(cur, t0 + src, __shfl_sync(FULL, s0, src), __shfl_sync(FULL, nf, src), lane);
         }
-        // pass 2: positions
-        double run2 = DINF;
-        int rec_before = 0, non_before = 0;
-        for (int b = 0; b < nf; b += 32) {
-            const bool in = b + lane < nf;
-            const double c = in ? cost[b + lane] : DINF;
-            const double incoming = fmin(run2, warp_excl_min(c, lane));
-            const bool isrec = in && c < incoming;
-            const unsigned br = __ballot_sync(FULL, isrec), bn = __ballot_sync(FULL, in && !isrec);
-            const unsigned lt = (1u << lane) - 1u;
-            if (isrec) fin[b + lane] = r0 + nrec - 1 - (rec_before + __popc(br & lt));
-            else if (in) fin[b + lane] = r0 + nrec + non_before + __popc(bn & lt);
-            rec_before += __popc(br); non_before += __popc(bn);
-            run2 = fmin(run2, warp_min(c));
-        }
-        if (lane == 0) cur.cost[t] = running;
     }
 }
 
