@@ -1459,6 +1459,8 @@ static int npo_impl(amod_ctx* ctx, const int32_t* idle_nid, int n_idle, const in
     grp.head = ctx->npo_grp.as<int>() + 2 * (size_t)G + 1 + (size_t)n_idle; grp.hrank = grp.head + G; grp.n_groups = G;
     CK(ctx->npo_vm.ensure(4 * (size_t)n_idle)); CK(ctx->npo_rm.ensure(4 * (size_t)n_pend)); CK(ctx->npo_mdt.ensure(8 * (size_t)n_pend));
     CK(ctx->npo_cnt.ensure(32));
+    if (2.0 * sizeof(TT) * (double)G * (double)n_pend > 32e9)      // the group x request travel times are held twice (both orientations)
+        return ctx->fail(AMOD_E_LIMIT, "npo: %d vehicle nodes x %d requests need more than 32 GB of travel times", G, n_pend);
     CK(ctx->npo_D.ensure(2 * sizeof(TT) * (size_t)G * (size_t)n_pend)); CK(ctx->npo_best.ensure(4 * (size_t)n_pend)); CK(ctx->npo_tie.ensure((size_t)n_pend));
     CK(ctx->npo_scr.ensure(sizeof(NpoPick) * (size_t)n_pend));
     CK(cudaMemsetAsync(ctx->npo_vm.p, 0xff, 4 * (size_t)n_idle, st));
