@@ -598,7 +598,7 @@ static int enqueue_build(amod_ctx* ctx, int mode, int cap, Table<TT> tt, int max
     // ---- levels 1..max_level ----------------------------------------------------------------------------
     // Two branches per level once the schedule offsets are known (fork after the scans):
     //   main: k_place_cost -> k_classify -> k_place_rows     (orders the level's schedules, writes them)
-    //   side: k_compact_trips -> k_gen_count -> k_gen_emit
+    //   side: k_compact_trips -> k_gen_pairs -> k_gen_emit
     //         (names and indexes the level's trips, prepares level k+1's tasks and rows; touches no schedule)
     // They meet again before k_eval<count> of level k+1.  Buffers both branches touch at once are doubled
     // (task lists, row descriptors, Control::n_rows / n_chunks, scan partials).
